@@ -1,0 +1,418 @@
+/*
+ * pegasus_b200.h — C ABI of the B200-native LSM read/compaction engine for the Pegasus replica
+ * server.  This is the drop-in boundary: everything a reference-side binding (the C++ class
+ * that takes RocksDB's place behind `replication_app_base`, or a cgo/JNI stub) needs is declared
+ * here with plain pointers and sizes.  No torch / CUDA / C++ types cross it, no exception does.
+ *
+ * Two layers, both exported by libpegasus_b200.so:
+ *
+ *   1. pgs_*       the device engine: partitions, HBM-resident sorted runs, compaction,
+ *                  batched point lookup, range scan.   (what RocksDB's DB::* calls become)
+ *   2. pgs_rrdb_*  the rrdb operator surface of one replica (`pegasus_server_impl`):
+ *                  on_get / on_multi_get / on_batch_get / on_sortkey_count / on_ttl /
+ *                  on_get_scanner / on_scan / on_clear_scanner / on_put ... with request and
+ *                  response structs mirroring idl/rrdb.thrift.
+ *
+ * Citations are relative to the reference tree (apache/incubator-pegasus):
+ *   plugin API ............ src/replica/replication_app_base.h:114-360
+ *   read handlers ......... src/server/pegasus_read_service.h:52-85,
+ *                           src/server/pegasus_server_impl.cpp:418-1549
+ *   write handlers ........ src/server/pegasus_server_write.cpp:92-222,
+ *                           src/server/rocksdb_wrapper.cpp:129-246
+ *   compaction filter ..... src/server/key_ttl_compaction_filter.h:55-203
+ *   manual compaction ..... src/server/pegasus_manual_compact_service.cpp:83-313,
+ *                           src/server/pegasus_server_impl.cpp:3373-3456
+ *   key / value schema .... src/base/pegasus_key_schema.h:41-183,
+ *                           src/base/pegasus_value_schema.h:44-226
+ *
+ * Error convention (all `int32_t` returns and every `error` field): the integer values of
+ * rocksdb::Status::Code, exactly as the reference puts them on the wire
+ * (src/include/pegasus/error_def.h:57-69, PERR = -1000 - code).  CUDA faults map to
+ * PGS_IO_ERROR, detected data damage to PGS_CORRUPTION.
+ */
+#ifndef PEGASUS_B200_H_
+#define PEGASUS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGS_API __attribute__((visibility("default")))
+
+/* ---- status codes = rocksdb::Status::Code ------------------------------------------------ */
+enum {
+    PGS_OK = 0,
+    PGS_NOT_FOUND = 1,
+    PGS_CORRUPTION = 2,
+    PGS_NOT_SUPPORTED = 3,
+    PGS_INVALID_ARGUMENT = 4,
+    PGS_IO_ERROR = 5,
+    PGS_MERGE_IN_PROGRESS = 6,
+    PGS_INCOMPLETE = 7,
+    PGS_SHUTDOWN_IN_PROGRESS = 8,
+    PGS_TIMED_OUT = 9,
+    PGS_ABORTED = 10,
+    PGS_BUSY = 11,
+    PGS_EXPIRED = 12,
+    PGS_TRY_AGAIN = 13
+};
+
+/* rrdb.thrift filter_type (idl/rrdb.thrift:27-33) */
+enum { PGS_FT_NO_FILTER = 0, PGS_FT_MATCH_ANYWHERE = 1, PGS_FT_MATCH_PREFIX = 2, PGS_FT_MATCH_POSTFIX = 3 };
+
+/* internal-key value types, as RocksDB's ValueType (dbformat.h, not in tree) */
+enum { PGS_TYPE_DELETION = 0, PGS_TYPE_VALUE = 1 };
+
+typedef struct pgs_engine pgs_engine;       /* one per GPU                                   */
+typedef struct pgs_partition pgs_partition; /* one per replica (gpid) = one RocksDB instance */
+
+typedef struct {
+    const uint8_t *data;
+    uint32_t len;
+} pgs_blob;
+
+/* ============================================================================================
+ * 1. device engine
+ * ========================================================================================== */
+
+typedef struct {
+    int32_t device;            /* CUDA ordinal; -1 = current                                  */
+    uint32_t block_size;       /* target data block bytes; 0 -> 4096 (RocksDB default, never
+                                  overridden by Pegasus: pegasus_server_impl_init.cpp:666-848) */
+    uint32_t restart_interval; /* 0 -> 16 (pegasus_server_impl_init.cpp:716-718)              */
+    uint32_t ctas_per_sm;      /* compaction kernel residency; 0 -> 2                         */
+    uint32_t flags;            /* PGS_ENGINE_* below                                          */
+} pgs_engine_config;
+
+#define PGS_ENGINE_NO_TMA 1u /* debug: stage blocks with plain loads instead of cp.async.bulk */
+
+PGS_API int32_t pgs_engine_open(const pgs_engine_config *cfg, pgs_engine **out);
+PGS_API void pgs_engine_close(pgs_engine *e);
+/* the CUDA stream (cudaStream_t) every kernel of this engine is launched on; lets a harness
+ * record events on it. */
+PGS_API void *pgs_engine_stream(pgs_engine *e);
+PGS_API int32_t pgs_engine_sync(pgs_engine *e);
+/* number of kernels this engine has launched so far */
+PGS_API uint64_t pgs_engine_launches(pgs_engine *e);
+/* thread-local description of the last failure on the calling thread */
+PGS_API const char *pgs_last_error(void);
+
+/* replaces rocksdb::DB::Open for one replica (pegasus_server_impl.cpp:1551-1860) */
+PGS_API int32_t pgs_partition_create(pgs_engine *e, int32_t app_id, int32_t pidx,
+                                     uint32_t data_version, pgs_partition **out);
+PGS_API void pgs_partition_destroy(pgs_partition *p);
+
+typedef struct {
+    uint64_t run_id;
+    int32_t level;
+    uint32_t n_blocks;
+    uint64_t n_records;
+    uint64_t n_tombstones;
+    uint64_t data_bytes;      /* encoded block bytes resident in HBM (incl. 16 B block padding) */
+    uint64_t raw_key_bytes;   /* sum of user-key bytes  (algorithmic bytes)          */
+    uint64_t raw_value_bytes; /* sum of value bytes                                             */
+    uint32_t max_ukey_len;
+    uint32_t max_value_len;
+    uint32_t max_block_size;
+    uint32_t max_block_records;
+    uint64_t smallest_seq;
+    uint64_t largest_seq;
+} pgs_run_info;
+
+/* Install one sorted run (an SST's data blocks) in HBM.  `data` holds `n_blocks` RocksDB-format
+ * data blocks (entries `varint shared, varint non_shared, varint value_len, key_delta, value`
+ * over internal keys `user_key || fixed64_le(seq<<8|type)`, restart array, restart count; no
+ * 5-byte trailer); block i occupies [blk_off[i], blk_off[i]+blk_size[i]) and every blk_off is a
+ * multiple of 16.  The device builds its own index (last key, record count per block).
+ * level 0: the run becomes the newest L0 run.  level>=1: newest run of that level.
+ * Replaces flush / IngestExternalFile (rocksdb_wrapper.cpp:248-270). */
+PGS_API int32_t pgs_run_upload(pgs_partition *p, int32_t level, const uint8_t *data,
+                               uint64_t data_bytes, const uint64_t *blk_off,
+                               const uint32_t *blk_size, uint32_t n_blocks, uint64_t *run_id_out);
+PGS_API int32_t pgs_run_drop(pgs_partition *p, uint64_t run_id);
+PGS_API int32_t pgs_run_info_get(pgs_partition *p, uint64_t run_id, pgs_run_info *out);
+/* run ids in read order (newest first: L0 by recency, then L1, L2, ...) */
+PGS_API int32_t pgs_run_list(pgs_partition *p, uint64_t *ids, uint32_t cap, uint32_t *n_out);
+/* copy a run's raw blocks + handles back to the host (checkpoint / egress / tests) */
+PGS_API int32_t pgs_run_download(pgs_partition *p, uint64_t run_id, uint8_t *data,
+                                 uint64_t data_cap, uint64_t *blk_off, uint32_t *blk_size,
+                                 uint32_t blk_cap);
+
+/* ---- compaction ---------------------------------------------------------------------------
+ * KeyWithTTLCompactionFilter snapshot (key_ttl_compaction_filter.h:140-157).  `ops` is the
+ * binary form of the `user_specified_compaction` app-env produced by pgs_compaction_ops_parse.
+ */
+typedef struct {
+    uint8_t enabled;       /* Factory::_enabled                                               */
+    uint8_t validate_hash; /* replica.split.validate_partition_hash                            */
+    uint8_t reserved[2];
+    uint32_t data_version;
+    uint32_t default_ttl;
+    int32_t pidx;
+    int32_t partition_version;
+    const uint8_t *ops; /* may be NULL */
+    uint32_t ops_len;
+} pgs_filter_params;
+
+typedef struct {
+    uint64_t new_run_id;
+    uint64_t in_records, out_records;
+    uint64_t in_bytes;  /* sum(user key + value) over input records  = "merged bytes"          */
+    uint64_t out_bytes; /* sum(user key + value) over surviving records                        */
+    uint64_t in_block_bytes, out_block_bytes;
+    uint64_t dropped_shadowed;  /* older versions of a user key                                */
+    uint64_t dropped_tombstone; /* deletions removed at the bottommost level                   */
+    uint64_t dropped_expired;   /* Filter(): expire_ts <= now                                  */
+    uint64_t dropped_user;      /* Filter(): user-specified delete op                          */
+    uint64_t dropped_stale;     /* Filter(): stale split data                                  */
+    uint64_t ttl_rewritten;     /* Filter(): value_changed                                     */
+    uint32_t n_tiles;
+    uint32_t n_launches;
+    float device_ms; /* CUDA-event time of the plan + merge kernels                            */
+    float merge_kernel_ms;
+} pgs_compact_result;
+
+/* k-way merge of `k` runs of one partition into one new run at `out_level`, newest version of
+ * each user key wins, tombstones dropped iff `bottommost` (-1 = derive from the partition: true
+ * iff no older run stays outside the input set), Filter() fused.  `now` = epoch_now()
+ * (pegasus_utils.h:39-41) passed explicitly.  Replaces DB::CompactRange
+ * (pegasus_server_impl.cpp:3373-3394) and the background compaction job. */
+PGS_API int32_t pgs_compact(pgs_partition *p, const uint64_t *run_ids, uint32_t k,
+                            int32_t out_level, int32_t bottommost, const pgs_filter_params *fp,
+                            uint32_t now, pgs_compact_result *out);
+
+/* Parse the JSON of the `user_specified_compaction` env (compaction_operation.cpp:162-186) into
+ * the binary ops table.  Invalid JSON / rules yield an empty table like the reference.  Returns
+ * bytes written (<= cap) or a negative status. */
+PGS_API int64_t pgs_compaction_ops_parse(const char *json, uint32_t json_len, uint32_t data_version,
+                                         uint8_t *out, uint32_t cap, uint32_t *n_ops_out);
+
+/* ---- batched point lookup: DB::Get / DB::MultiGet ------------------------------------------ */
+typedef struct {
+    int32_t status;     /* PGS_OK | PGS_NOT_FOUND                                             */
+    uint32_t expire_ts; /* header field of the found record                                   */
+    uint32_t value_off; /* user data (header stripped) inside the arena                       */
+    uint32_t value_len;
+    uint8_t expired;    /* found but hidden by TTL -> status is PGS_NOT_FOUND                 */
+    uint8_t reserved[3];
+} pgs_get_result;
+
+/* keys: n raw Pegasus keys back to back, key i = keys[key_off[i] .. key_off[i+1]).
+ * Values of found, unexpired records are written to `arena` (host memory).  A record whose
+ * value does not fit gets PGS_INCOMPLETE and *arena_used is the total need. */
+PGS_API int32_t pgs_get_batch(pgs_partition *p, const uint8_t *keys, const uint32_t *key_off,
+                              uint32_t n, uint32_t now, uint8_t *arena, uint64_t arena_cap,
+                              pgs_get_result *results, uint64_t *arena_used);
+
+/* ---- range scan: NewIterator + Seek + Next/Prev loop --------------------------------------- */
+typedef struct {
+    pgs_blob start, stop; /* raw keys                                                          */
+    uint8_t start_inclusive, stop_inclusive;
+    uint8_t reverse;
+    uint8_t no_value;
+    uint8_t key_mode;         /* 0: return the raw key (scan); 1: sort key only (multi_get)    */
+    uint8_t return_expire_ts;
+    uint8_t count_only;
+    uint8_t validate_hash;    /* request flag && server flag, already combined                 */
+    uint8_t prefix_same_as_start; /* ReadOptions of the data CF (pegasus_server_impl_init.cpp:835-840) */
+    uint8_t skip_first_exclusive; /* 1 for the first batch (first_exclusive logic)             */
+    uint8_t reserved[2];
+    int32_t hash_filter_type, sort_filter_type;
+    pgs_blob hash_filter, sort_filter;
+    uint32_t max_count;      /* loop guard `count < max_count`                                 */
+    uint32_t max_iter_count; /* range_read_limiter max_count                                   */
+    uint64_t max_iter_size;  /* range_read_limiter max_size, 0 = none                          */
+    int32_t pidx, partition_version;
+} pgs_scan_request;
+
+typedef struct {
+    uint32_t key_off, key_len;
+    uint32_t value_off, value_len;
+    uint32_t expire_ts;
+} pgs_kv;
+
+typedef struct {
+    int32_t status;     /* iterator status: PGS_OK or an error                                 */
+    uint32_t n_kvs;     /* records returned (= count unless count_only)                        */
+    uint32_t count;     /* records in state kNormal                                            */
+    uint32_t iter_count, expire_count, filter_count;
+    uint64_t size;      /* sum(len(key)+len(value)) of returned records                        */
+    uint8_t complete;   /* loop left through the stop key                                      */
+    uint8_t iter_valid; /* iterator still valid when the loop ended                            */
+    uint8_t reserved[2];
+    uint32_t resume_len;/* raw key the iterator stands on (if iter_valid)                      */
+    uint64_t arena_used;
+} pgs_scan_result;
+
+PGS_API int32_t pgs_range_scan(pgs_partition *p, const pgs_scan_request *req, uint32_t now,
+                               uint8_t *arena, uint64_t arena_cap, pgs_kv *kvs, uint32_t kv_cap,
+                               uint8_t *resume_key, uint32_t resume_cap, pgs_scan_result *out);
+
+/* ============================================================================================
+ * host-side helpers of the product (no device work)
+ * ========================================================================================== */
+
+/* pegasus_key_schema.h:41-98,150-165 */
+PGS_API int32_t pgs_generate_key(const uint8_t *hk, uint32_t hk_len, const uint8_t *sk,
+                                 uint32_t sk_len, uint8_t *out, uint32_t cap);
+PGS_API int32_t pgs_generate_next_blob(const uint8_t *hk, uint32_t hk_len, const uint8_t *sk,
+                                       uint32_t sk_len, int32_t with_sort_key, uint8_t *out,
+                                       uint32_t cap);
+PGS_API uint64_t pgs_key_hash(const uint8_t *raw_key, uint32_t len);
+PGS_API uint64_t pgs_crc64(const uint8_t *data, uint64_t len, uint64_t init);
+
+/* Sorted-run builder (the flush side: memtable -> data blocks).  Records must be added in
+ * internal-key order (user key ascending, seq descending).  Produces exactly the layout
+ * pgs_run_upload takes. */
+typedef struct pgs_run_builder pgs_run_builder;
+PGS_API pgs_run_builder *pgs_run_builder_new(uint32_t block_size, uint32_t restart_interval);
+PGS_API int32_t pgs_run_builder_add(pgs_run_builder *b, const uint8_t *ukey, uint32_t ukey_len,
+                                    uint64_t seq, uint8_t type, const uint8_t *value,
+                                    uint32_t value_len);
+/* bulk variant: n records, key i = keys[key_off[i]..key_off[i+1]), same for values */
+PGS_API int32_t pgs_run_builder_add_many(pgs_run_builder *b, uint64_t n, const uint8_t *keys,
+                                         const uint64_t *key_off, const uint8_t *vals,
+                                         const uint64_t *val_off, const uint64_t *seq,
+                                         const uint8_t *type);
+PGS_API int32_t pgs_run_builder_finish(pgs_run_builder *b, const uint8_t **data,
+                                       uint64_t *data_bytes, const uint64_t **blk_off,
+                                       const uint32_t **blk_size, uint32_t *n_blocks);
+PGS_API void pgs_run_builder_free(pgs_run_builder *b);
+
+/* Decode raw blocks into flat records (egress / tests).  Two-call protocol: pass NULL outputs
+ * to get the sizes. */
+typedef struct {
+    uint64_t n_records, key_bytes, value_bytes;
+} pgs_decode_sizes;
+PGS_API int32_t pgs_blocks_decode(const uint8_t *data, const uint64_t *blk_off,
+                                  const uint32_t *blk_size, uint32_t n_blocks,
+                                  pgs_decode_sizes *sizes, uint8_t *keys, uint64_t *key_off,
+                                  uint8_t *vals, uint64_t *val_off, uint64_t *seq, uint8_t *type);
+
+/* ============================================================================================
+ * 2. rrdb operator surface of one replica  (pegasus_server_impl)
+ * ========================================================================================== */
+
+typedef struct pgs_server pgs_server;
+
+typedef struct {
+    /* [pegasus.server] knobs, defaults as pegasus_server_impl_init.cpp:456-511 */
+    uint32_t rocksdb_max_iteration_count;          /* 0 -> 1000                               */
+    uint32_t rocksdb_multi_get_max_iteration_count;/* 0 -> 3000                               */
+    uint64_t rocksdb_multi_get_max_iteration_size; /* 0 -> 30 MB                              */
+    uint32_t l0_compaction_trigger;                /* 0 -> 4                                  */
+    uint64_t memtable_bytes;                       /* 0 -> 64 MB                              */
+    uint8_t prefix_filter;                         /* rocksdb_filter_type == "prefix" (default 1) */
+    uint8_t cluster_id;                            /* timetag cluster id, default 1           */
+    uint8_t reserved[6];
+} pgs_server_options;
+
+/* replication_app_base::open/start: creates the partition on `e`, data version 1
+ * (pegasus_server_impl_test.cpp:356-360). envs = "k1\0v1\0k2\0v2\0..." (n_envs pairs), the
+ * app envs of replication_app_base.cpp:216-245. */
+PGS_API int32_t pgs_rrdb_start(pgs_engine *e, int32_t app_id, int32_t pidx,
+                               const pgs_server_options *opt, const char *envs, uint32_t n_envs,
+                               pgs_server **out);
+PGS_API void pgs_rrdb_stop(pgs_server *s);
+PGS_API pgs_partition *pgs_rrdb_partition(pgs_server *s);
+/* update_app_envs (pegasus_server_impl.cpp:2728-2741): default_ttl,
+ * replica.split.validate_partition_hash, user_specified_compaction, manual_compact.* */
+PGS_API int32_t pgs_rrdb_update_app_envs(pgs_server *s, const char *envs, uint32_t n_envs,
+                                         uint32_t now);
+PGS_API void pgs_rrdb_set_partition_version(pgs_server *s, int32_t partition_version);
+
+/* responses own their bytes inside the server handle's response object */
+typedef struct {
+    int32_t error, app_id, partition_index;
+    int32_t ttl_seconds;       /* on_ttl                                                      */
+    int64_t count;             /* on_sortkey_count                                            */
+    int64_t context_id;        /* scan                                                        */
+    int32_t kv_count;          /* only_return_count (-1 = unset)                              */
+    uint32_t n_kvs;
+    const pgs_kv *kvs;         /* key/value offsets into arena                                */
+    const uint32_t *hk_len;    /* batch_get: hash-key length of kvs[i].key (hk||sk)           */
+    const uint8_t *arena;
+    uint64_t arena_len;
+    uint32_t iteration_count, expire_count, filter_count;
+} pgs_response;
+
+typedef struct pgs_response_buf pgs_response_buf; /* reusable response storage */
+PGS_API pgs_response_buf *pgs_response_new(void);
+PGS_API void pgs_response_free(pgs_response_buf *r);
+PGS_API const pgs_response *pgs_response_view(pgs_response_buf *r);
+
+typedef struct {
+    pgs_blob hash_key;
+    const pgs_blob *sort_keys;
+    uint32_t n_sort_keys;
+    int32_t max_kv_count, max_kv_size;
+    uint8_t no_value, start_inclusive, stop_inclusive, reverse;
+    pgs_blob start_sortkey, stop_sortkey;
+    int32_t sort_key_filter_type;
+    pgs_blob sort_key_filter_pattern;
+} pgs_multi_get_request; /* idl/rrdb.thrift multi_get_request */
+
+typedef struct {
+    pgs_blob start_key, stop_key;
+    uint8_t start_inclusive, stop_inclusive, no_value;
+    uint8_t validate_partition_hash; /* default true when unset                               */
+    uint8_t return_expire_ts, full_scan, only_return_count, reserved;
+    int32_t batch_size;
+    int32_t hash_key_filter_type;
+    pgs_blob hash_key_filter_pattern;
+    int32_t sort_key_filter_type;
+    pgs_blob sort_key_filter_pattern;
+} pgs_get_scanner_request; /* idl/rrdb.thrift get_scanner_request */
+
+typedef struct {
+    pgs_blob hash_key, sort_key;
+} pgs_full_key;
+
+/* read handlers (pegasus_read_service.h:52-68); `now` = epoch_now() made explicit */
+PGS_API int32_t pgs_rrdb_get(pgs_server *s, pgs_blob raw_key, uint32_t now, pgs_response_buf *r);
+PGS_API int32_t pgs_rrdb_ttl(pgs_server *s, pgs_blob raw_key, uint32_t now, pgs_response_buf *r);
+PGS_API int32_t pgs_rrdb_multi_get(pgs_server *s, const pgs_multi_get_request *q, uint32_t now,
+                                   pgs_response_buf *r);
+PGS_API int32_t pgs_rrdb_batch_get(pgs_server *s, const pgs_full_key *keys, uint32_t n,
+                                   uint32_t now, pgs_response_buf *r);
+PGS_API int32_t pgs_rrdb_sortkey_count(pgs_server *s, pgs_blob hash_key, uint32_t now,
+                                       pgs_response_buf *r);
+PGS_API int32_t pgs_rrdb_get_scanner(pgs_server *s, const pgs_get_scanner_request *q,
+                                     uint32_t now, pgs_response_buf *r);
+PGS_API int32_t pgs_rrdb_scan(pgs_server *s, int64_t context_id, uint32_t now,
+                              pgs_response_buf *r);
+PGS_API void pgs_rrdb_clear_scanner(pgs_server *s, int64_t context_id);
+
+/* many independent `get`s in one launch: what a batching front-end in front of the LOCAL_APP
+ * thread pool would call. results[i].status / value in arena as pgs_get_batch. */
+PGS_API int32_t pgs_rrdb_get_many(pgs_server *s, const uint8_t *keys, const uint32_t *key_off,
+                                  uint32_t n, uint32_t now, uint8_t *arena, uint64_t arena_cap,
+                                  pgs_get_result *results, uint64_t *arena_used);
+
+/* write handlers -> memtable (pegasus_server_write.cpp:151-222, rocksdb_wrapper.cpp:129-219).
+ * `decree` / `timestamp_us` are the mutation's; expire_ts_seconds as update_request. */
+PGS_API int32_t pgs_rrdb_put(pgs_server *s, pgs_blob raw_key, pgs_blob user_value,
+                             uint32_t expire_ts_seconds, int64_t decree, uint64_t timestamp_us,
+                             uint32_t now);
+PGS_API int32_t pgs_rrdb_remove(pgs_server *s, pgs_blob raw_key, int64_t decree);
+PGS_API int32_t pgs_rrdb_multi_put(pgs_server *s, pgs_blob hash_key, const pgs_blob *sort_keys,
+                                   const pgs_blob *values, uint32_t n, uint32_t expire_ts_seconds,
+                                   int64_t decree, uint64_t timestamp_us, uint32_t now);
+PGS_API int32_t pgs_rrdb_multi_remove(pgs_server *s, pgs_blob hash_key, const pgs_blob *sort_keys,
+                                      uint32_t n, int64_t decree, int64_t *count);
+/* flush_all_family_columns (pegasus_server_impl.cpp:3471): memtable -> L0 run in HBM, then the
+ * L0 trigger check (L0 count >= trigger -> L0(+L1) -> L1 compaction with the filter at `now`).
+ * `now` (epoch_now) also feeds the default-TTL substitution of puts (rocksdb_wrapper.cpp:280-288). */
+PGS_API int32_t pgs_rrdb_flush(pgs_server *s, uint32_t now);
+/* do_manual_compact (pegasus_server_impl.cpp:3373-3456): whole-CF CompactRange, bottommost
+ * level forced. */
+PGS_API int32_t pgs_rrdb_manual_compact(pgs_server *s, uint32_t now, pgs_compact_result *out);
+PGS_API int64_t pgs_rrdb_last_flushed_decree(pgs_server *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEGASUS_B200_H_ */

@@ -1,0 +1,1080 @@
+// compact.cu — level compaction on the GPU: k-way merge of HBM-resident sorted runs with
+// KeyWithTTLCompactionFilter fused into the merge.
+//
+// Replaces (reference file:line):
+//   DB::CompactRange / background compaction job ....... src/server/pegasus_server_impl.cpp:3373-3394
+//   RocksDB MergingIterator + CompactionIterator + BlockBasedTableBuilder (v8.5.3, not in tree;
+//   semantics restated in SURVEY.md Appendix A)
+//   KeyWithTTLCompactionFilter::Filter .................. src/server/key_ttl_compaction_filter.h:55-121
+//   compaction_operation / compaction_filter_rule ....... src/server/compaction_operation.cpp:33-113,
+//                                                         src/server/compaction_filter_rule.cpp:31-90
+//
+// Shape of the computation (B200-first, no tensor cores: this is byte/integer work bound by HBM):
+//   k_plan   one thread per input block ranks the block's last user key against every run's block
+//            index (binary search) => cumulative shared-memory weight of everything <= that key.
+//            Keys where the weight crosses a multiple of the tile budget become tile boundaries:
+//            tile q = user keys in (U_q, U_q+1], a contiguous block range per run.
+//   k_merge  persistent CTAs take tiles in ticket order.  Per tile:
+//              TMA (cp.async.bulk) stages each run's block slice into shared memory,
+//              one warp per block decodes restart-interval prefix compression into an arena of
+//              full user keys, every record binary-searches the other runs' records for its merge
+//              rank (and finds out whether a newer version shadows it), the compaction filter runs
+//              per surviving record, survivors are re-encoded into 4 KB-target data blocks
+//              (restart interval 16) whose byte offsets come from block-wide scans, the tile's
+//              output position comes from a decoupled look-back over tile aggregates, and warps
+//              copy entries shared -> global with destination-aligned 16-byte stores.
+//            Output blocks stay contiguous and in key order, so the new run needs no second pass.
+#include <algorithm>
+#include <cstring>
+
+#include "device_util.cuh"
+#include "engine.h"
+
+namespace pgs {
+
+constexpr uint32_t kMergeThreads = 512;
+constexpr uint32_t kMergeWarps = kMergeThreads / 32;
+constexpr uint32_t kMaxTileBlocks = 256;
+constexpr uint32_t kMaxOutBlocks = 256;
+constexpr uint32_t kRecExtra = 48; // per-record shared-memory bytes besides the key slot
+
+enum : uint8_t { F_VALID = 1, F_SHADOW = 2, F_KEEP = 4, F_TOMB = 8, F_NEWTS = 16 };
+
+struct TileAgg {
+    unsigned long long bytes;
+    uint32_t blocks, recs, keyb, flag;
+    uint32_t pad[2];
+};
+static_assert(sizeof(TileAgg) == 32, "TileAgg");
+
+struct MergeStats {
+    unsigned long long in_records, in_bytes, out_records, out_bytes;
+    unsigned long long dropped_shadowed, dropped_tombstone, dropped_expired, dropped_user, dropped_stale, ttl_rewritten;
+    unsigned long long out_tomb, out_raw_key, out_raw_val, min_seq, max_seq;
+    uint32_t max_ukey, max_vlen, max_blk_size, max_blk_rec;
+    uint32_t error, error_tile;
+};
+
+struct MergeParams {
+    RunDev runs[kMaxRuns];
+    uint32_t k;
+    // plan
+    uint32_t *split_pos; // [(Q+1)*k]
+    uint32_t *split_ref; // [Q+1]  run<<28 | block
+    uint32_t Q;
+    unsigned long long tile_weight; // T
+    uint32_t rec_cost;
+    uint32_t total_blocks;
+    // tile pipeline
+    uint32_t *ticket;
+    TileAgg *agg, *inc;
+    uint32_t KS, pool_bytes, warp_scratch, use_tma;
+    // filter + policy
+    uint32_t now, enabled, validate_hash, data_version, default_ttl;
+    int32_t pidx, partition_version;
+    const uint8_t *ops;
+    uint32_t n_ops;
+    uint32_t bottommost, block_size, restart_interval;
+    const unsigned long long *crc_table;
+    // output run
+    uint8_t *out_data;
+    unsigned long long out_cap;
+    unsigned long long *out_blk_off;
+    uint32_t *out_blk_size, *out_blk_rec, *out_ikey_off;
+    uint8_t *out_ikeys;
+    uint32_t out_blk_cap, out_ikey_cap;
+    MergeStats *stats;
+};
+
+// ------------------------------------------------------------------------------------------------
+// k_plan
+// ------------------------------------------------------------------------------------------------
+PGS_DEV unsigned long long run_weight(const RunDev &r, uint32_t pos, uint32_t rec_cost)
+{
+    return r.blk_off[pos] + (unsigned long long)r.blk_rec[pos] * rec_cost;
+}
+
+__global__ void __launch_bounds__(256) k_plan(const __grid_constant__ MergeParams P)
+{
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P.total_blocks) return;
+    uint32_t i = 0, b = g;
+    while (b >= P.runs[i].nb) { b -= P.runs[i].nb; i++; }
+    const RunDev &ri = P.runs[i];
+    const uint8_t *U = ri.ikeys + ri.ikey_off[b];
+    uint32_t ulen = ri.ikey_off[b + 1] - ri.ikey_off[b];
+    uint32_t pos[kMaxRuns];
+    unsigned long long Wb = 0, W = 0;
+    for (uint32_t j = 0; j < P.k; j++) {
+        const RunDev &rj = P.runs[j];
+        uint32_t lo = 0, hi = rj.nb; // upper bound: #blocks with last key <= U
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            const uint8_t *kp = rj.ikeys + rj.ikey_off[mid];
+            uint32_t kl = rj.ikey_off[mid + 1] - rj.ikey_off[mid];
+            if (cmp_bytes(kp, kl, U, ulen) <= 0) lo = mid + 1; else hi = mid;
+        }
+        uint32_t ub = lo, lb = lo;
+        while (lb > 0) {
+            const uint8_t *kp = rj.ikeys + rj.ikey_off[lb - 1];
+            uint32_t kl = rj.ikey_off[lb] - rj.ikey_off[lb - 1];
+            if (cmp_bytes(kp, kl, U, ulen) != 0) break;
+            lb--;
+        }
+        pos[j] = ub;
+        W += run_weight(rj, ub, P.rec_cost);
+        Wb += run_weight(rj, lb, P.rec_cost);
+    }
+    unsigned long long q_lo = Wb / P.tile_weight + 1, q_hi = W / P.tile_weight;
+    if (q_hi > P.Q - 1) q_hi = P.Q - 1;
+    for (unsigned long long q = q_lo; q <= q_hi; q++) {
+        for (uint32_t j = 0; j < P.k; j++) P.split_pos[q * P.k + j] = pos[j];
+        P.split_ref[q] = (i << 28) | b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// compaction filter on the device
+// ------------------------------------------------------------------------------------------------
+PGS_DEV bool dev_pattern_match(const uint8_t *v, uint32_t vl, uint32_t match_type, const uint8_t *pat, uint32_t pl)
+{
+    // string_pattern_match: compaction_filter_rule.cpp:31-54 (empty pattern never matches)
+    if (pl == 0 || vl < pl) return false;
+    if (match_type == MATCH_PREFIX) {
+        for (uint32_t i = 0; i < pl; i++) if (v[i] != pat[i]) return false;
+        return true;
+    }
+    if (match_type == MATCH_POSTFIX) {
+        const uint8_t *s = v + vl - pl;
+        for (uint32_t i = 0; i < pl; i++) if (s[i] != pat[i]) return false;
+        return true;
+    }
+    if (match_type == MATCH_ANYWHERE) {
+        for (uint32_t s = 0; s + pl <= vl; s++) {
+            uint32_t i = 0;
+            while (i < pl && v[s + i] == pat[i]) i++;
+            if (i == pl) return true;
+        }
+        return false;
+    }
+    return false;
+}
+
+PGS_DEV uint32_t ld_u32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+PGS_DEV uint32_t ld_u16(const uint8_t *p) { return p[0] | (p[1] << 8); }
+
+// user_specified_operation_filter: key_ttl_compaction_filter.h:94-108 over the binary ops table.
+// Every op sees the value as of entry (entry_ts); returns true when a delete op fired.
+PGS_DEV bool dev_user_ops(const MergeParams &P, const uint8_t *hk, uint32_t hkl, const uint8_t *sk, uint32_t skl,
+                          uint32_t entry_ts, uint32_t &new_ts, bool &changed)
+{
+    const uint8_t *p = P.ops + 4;
+    for (uint32_t o = 0; o < P.n_ops; o++) {
+        uint32_t op_type = p[0], ttl_type = p[1], n_rules = ld_u16(p + 2), ttl_value = ld_u32(p + 4);
+        p += 8;
+        bool all = n_rules > 0; // all_rules_match: empty rule set => false (compaction_operation.cpp:37-39)
+        for (uint32_t r = 0; r < n_rules; r++) {
+            uint32_t rt = p[0], mt = p[1], pl = ld_u16(p + 2), start_ttl = ld_u32(p + 4), stop_ttl = ld_u32(p + 8);
+            const uint8_t *pat = p + 12;
+            p += 12 + ((pl + 3) & ~3u);
+            if (!all) continue;
+            bool m;
+            if (rt == RULE_HASHKEY) m = dev_pattern_match(hk, hkl, mt, pat, pl);
+            else if (rt == RULE_SORTKEY) m = dev_pattern_match(sk, skl, mt, pat, pl);
+            else { // ttl_range_rule::match, compaction_filter_rule.cpp:76-90 (u32 arithmetic)
+                if (entry_ts == 0 && start_ttl == 0 && stop_ttl == 0) m = true;
+                else m = (uint32_t)(start_ttl + P.now) <= entry_ts && (uint32_t)(stop_ttl + P.now) >= entry_ts;
+            }
+            all = m;
+        }
+        if (!all) continue;
+        if (op_type == OP_DELETE) return true; // delete_key::filter
+        // update_ttl::filter, compaction_operation.cpp:77-113
+        uint32_t ts;
+        if (ttl_type == TTL_FROM_NOW) ts = P.now + ttl_value;
+        else if (ttl_type == TTL_FROM_CURRENT) { if (entry_ts == 0) continue; ts = ttl_value + entry_ts; }
+        else if (ttl_type == TTL_TIMESTAMP) ts = ttl_value - kEpochBegin;
+        else continue;
+        new_ts = ts;
+        changed = true;
+    }
+    return false;
+}
+
+PGS_DEV unsigned long long dev_crc64(const unsigned long long *tab, const uint8_t *p, uint32_t n)
+{
+    unsigned long long c = ~0ull; // init 0 -> ~init
+    for (uint32_t i = 0; i < n; i++) c = tab[(uint8_t)(c ^ p[i])] ^ (c >> 8);
+    return ~c;
+}
+
+// KeyWithTTLCompactionFilter::Filter (key_ttl_compaction_filter.h:55-92).
+// returns 0 keep, 1 expired, 2 user op, 3 stale split data
+PGS_DEV uint32_t dev_filter(const MergeParams &P, const unsigned long long *crc_tab, const uint8_t *ukey, uint32_t klen,
+                            const uint8_t *val, uint32_t vlen, uint32_t &new_ts, bool &changed)
+{
+    changed = false;
+    if (!P.enabled || klen < 2 || vlen < 4) return 0;
+    uint32_t expire_ts = be32(val);
+    if (P.default_ttl != 0 && expire_ts == 0) {
+        expire_ts = P.now + P.default_ttl;
+        new_ts = expire_ts;
+        changed = true;
+    }
+    uint32_t hkl = be16(ukey);
+    if (hkl > klen - 2) hkl = klen - 2; // malformed key: never read outside it
+    const uint8_t *hk = ukey + 2, *sk = ukey + 2 + hkl;
+    uint32_t skl = klen - 2 - hkl;
+    if (P.n_ops) {
+        if (dev_user_ops(P, hk, hkl, sk, skl, expire_ts, new_ts, changed)) return 2;
+    }
+    if (ts_expired(P.now, expire_ts)) return 1;
+    if (P.validate_hash && P.partition_version >= 0 && P.pidx <= P.partition_version) {
+        // check_pegasus_key_hash: pegasus_key_schema.h:150-183
+        unsigned long long h = hkl > 0 ? dev_crc64(crc_tab, hk, hkl) : dev_crc64(crc_tab, sk, skl);
+        if ((long long)(h & (unsigned long long)(long long)P.partition_version) != (long long)P.pidx) return 3;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_merge
+// ------------------------------------------------------------------------------------------------
+struct TileShared {
+    unsigned long long mbar;
+    unsigned long long base_bytes;
+    uint32_t base_blocks, base_recs, base_keyb;
+    uint32_t tile, error;
+    uint32_t in_bytes, n_rec, n_blk_in, n_valid, n_surv, n_ob;
+    uint32_t has_lo, has_hi, ulo_len, uhi_len;
+    uint32_t tile_bytes, tile_keyb;
+    uint32_t lo[kMaxRuns], nblk[kMaxRuns], nrec[kMaxRuns], in_off[kMaxRuns], rec_base[kMaxRuns], blk_base[kMaxRuns];
+    uint32_t vlo[kMaxRuns], vhi[kMaxRuns];
+    uint32_t scan[33];
+    unsigned long long stat[16];
+    unsigned long long min_seq, max_seq;
+    uint32_t max_ukey, max_vlen, max_blk_size, max_blk_rec;
+    uint32_t tb_off[kMaxTileBlocks], tb_size[kMaxTileBlocks], tb_rec[kMaxTileBlocks], tb_nrec[kMaxTileBlocks];
+    uint32_t cut[kMaxOutBlocks + 1], ob_off[kMaxOutBlocks + 1], ob_size[kMaxOutBlocks], ob_keyoff[kMaxOutBlocks + 1];
+    unsigned long long crc[256];
+};
+
+enum { ST_IN_REC = 0, ST_IN_BYTES, ST_OUT_REC, ST_OUT_BYTES, ST_SHADOW, ST_TOMB, ST_EXPIRED, ST_USER, ST_STALE, ST_TTL,
+       ST_OUT_TOMB, ST_OUT_KEY, ST_OUT_VAL };
+
+struct RecArrays {
+    uint8_t *in;
+    uint8_t *arena;
+    unsigned long long *trailer;
+    uint32_t *voff, *vlen, *newts, *R, *E;
+    uint16_t *klen, *rank, *order, *surv, *shr, *blkid;
+    uint8_t *flags;
+    uint32_t total;
+};
+PGS_DEV RecArrays carve(uint8_t *pool, uint32_t in_bytes, uint32_t n, uint32_t KS)
+{
+    RecArrays a;
+    uint32_t n8 = (n + 8) & ~7u; // >= n+1, multiple of 8
+    uint32_t off = ((in_bytes + 15) & ~15u) + 16;
+    a.in = pool;
+    a.arena = pool + off; off += n8 * KS;
+    a.trailer = (unsigned long long *)(pool + off); off += n8 * 8;
+    a.voff = (uint32_t *)(pool + off); off += n8 * 4;
+    a.vlen = (uint32_t *)(pool + off); off += n8 * 4;
+    a.newts = (uint32_t *)(pool + off); off += n8 * 4;
+    a.R = (uint32_t *)(pool + off); off += n8 * 4;
+    a.E = (uint32_t *)(pool + off); off += n8 * 4;
+    a.klen = (uint16_t *)(pool + off); off += n8 * 2;
+    a.rank = (uint16_t *)(pool + off); off += n8 * 2;
+    a.order = (uint16_t *)(pool + off); off += n8 * 2;
+    a.surv = (uint16_t *)(pool + off); off += n8 * 2;
+    a.shr = (uint16_t *)(pool + off); off += n8 * 2;
+    a.blkid = (uint16_t *)(pool + off); off += n8 * 2;
+    a.flags = pool + off; off += n8;
+    a.total = off;
+    return a;
+}
+
+// exclusive scan of f(i), i in [0,n), into out[0..n] (out[n] = total); all threads call it.
+template <class F>
+PGS_DEV uint32_t chunked_scan(uint32_t n, uint32_t *out, uint32_t *scratch, F f)
+{
+    uint32_t ipt = (n + blockDim.x - 1) / blockDim.x;
+    uint32_t begin = min(threadIdx.x * ipt, n), end = min(begin + ipt, n);
+    uint32_t local = 0;
+    for (uint32_t i = begin; i < end; i++) local += f(i);
+    uint32_t total;
+    uint32_t pre = block_excl_scan(local, scratch, &total);
+    for (uint32_t i = begin; i < end; i++) { uint32_t v = f(i); out[i] = pre; pre += v; }
+    if (threadIdx.x == 0) out[n] = total;
+    __syncthreads();
+    return total;
+}
+
+PGS_DEV void publish(TileAgg *slot, unsigned long long bytes, uint32_t blocks, uint32_t recs, uint32_t keyb)
+{
+    slot->bytes = bytes;
+    slot->blocks = blocks;
+    slot->recs = recs;
+    slot->keyb = keyb;
+    __threadfence();
+    *(volatile uint32_t *)&slot->flag = 1;
+}
+
+__global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__ MergeParams P)
+{
+    extern __shared__ __align__(128) uint8_t dyn[];
+    __shared__ TileShared S;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t KS = P.KS, RI = P.restart_interval;
+    uint8_t *ulo = dyn, *uhi = dyn + KS + 8;
+    uint8_t *wscr = dyn + 2 * (KS + 8) + warp * P.warp_scratch;
+    uint8_t *pool = dyn + 2 * (KS + 8) + kMergeWarps * P.warp_scratch;
+
+    if (tid == 0) {
+        mbar_init((uint64_t *)&S.mbar, 1);
+        mbar_fence_init();
+    }
+    if (P.validate_hash)
+        for (uint32_t i = tid; i < 256; i += kMergeThreads) S.crc[i] = P.crc_table[i];
+    __syncthreads();
+    uint32_t phase = 0;
+
+    for (;;) {
+        if (tid == 0) S.tile = atomicAdd(P.ticket, 1u);
+        if (tid < 16) S.stat[tid] = 0;
+        if (tid == 32) { S.error = 0; S.min_seq = ~0ull; S.max_seq = 0; S.max_ukey = 0; S.max_vlen = 0; S.max_blk_size = 0; S.max_blk_rec = 0; }
+        __syncthreads();
+        const uint32_t tile = S.tile;
+        if (tile >= P.Q) break;
+        const bool first = tile == 0, last = tile == P.Q - 1;
+
+        // ---- tile setup ---------------------------------------------------------------------
+        if (tid < P.k) {
+            const RunDev &r = P.runs[tid];
+            uint32_t lo = first ? 0 : P.split_pos[tile * P.k + tid];
+            uint32_t hi = last ? r.nb : P.split_pos[(tile + 1) * P.k + tid];
+            uint32_t err = 0;
+            if (lo == 0xFFFFFFFFu || hi == 0xFFFFFFFFu || lo > r.nb || hi > r.nb || lo > hi) { err = PGS_ABORTED; lo = hi = 0; }
+            uint32_t hi_ex = last ? r.nb : min(hi + 1, r.nb);
+            S.lo[tid] = lo;
+            S.nblk[tid] = hi_ex - lo;
+            S.in_off[tid] = (uint32_t)(r.blk_off[hi_ex] - r.blk_off[lo]); // bytes, offsets fixed below
+            S.nrec[tid] = r.blk_rec[hi_ex] - r.blk_rec[lo];
+            if (err) atomicMax(&S.error, err);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t bytes = 0, recs = 0, blks = 0;
+            for (uint32_t j = 0; j < P.k; j++) {
+                uint32_t bj = S.in_off[j];
+                S.in_off[j] = bytes;
+                S.rec_base[j] = recs;
+                S.blk_base[j] = blks;
+                bytes += bj;
+                recs += S.nrec[j];
+                blks += S.nblk[j];
+            }
+            S.in_bytes = bytes;
+            S.n_rec = recs;
+            S.n_blk_in = blks;
+            RecArrays a0 = carve(pool, bytes, recs, KS);
+            if (a0.total > P.pool_bytes || blks > kMaxTileBlocks || recs > 65000) atomicMax(&S.error, (uint32_t)PGS_ABORTED);
+            S.has_lo = !first;
+            S.has_hi = !last;
+        }
+        __syncthreads();
+        const RecArrays A = carve(pool, S.in_bytes, S.n_rec, KS);
+        bool tile_ok = S.error == 0;
+        if (tile_ok) {
+            if (P.use_tma) {
+                if (tid == 0) {
+                    // generic-proxy writes of the previous tile precede async-proxy writes to the same bytes
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (S.in_bytes) mbar_expect_tx((uint64_t *)&S.mbar, S.in_bytes);
+                    for (uint32_t j = 0; j < P.k; j++) {
+                        uint32_t bytes = (j + 1 < P.k ? S.in_off[j + 1] : S.in_bytes) - S.in_off[j];
+                        if (bytes) tma_load_1d(A.in + S.in_off[j], P.runs[j].data + P.runs[j].blk_off[S.lo[j]], bytes, (uint64_t *)&S.mbar);
+                    }
+                }
+            } else {
+                for (uint32_t j = 0; j < P.k; j++) {
+                    uint32_t bytes = (j + 1 < P.k ? S.in_off[j + 1] : S.in_bytes) - S.in_off[j];
+                    const uint4 *src = (const uint4 *)(P.runs[j].data + P.runs[j].blk_off[S.lo[j]]);
+                    uint4 *dst = (uint4 *)(A.in + S.in_off[j]);
+                    for (uint32_t i = tid; i < bytes / 16; i += kMergeThreads) dst[i] = src[i];
+                }
+            }
+            // boundary keys (zero padded slots)
+            for (uint32_t which = 0; which < 2; which++) {
+                if (which == 0 ? first : last) continue;
+                uint32_t ref = P.split_ref[tile + which];
+                const RunDev &r = P.runs[ref >> 28];
+                uint32_t b = ref & 0x0FFFFFFFu;
+                uint32_t off = r.ikey_off[b], len = r.ikey_off[b + 1] - off;
+                uint8_t *dst = which == 0 ? ulo : uhi;
+                for (uint32_t i = tid; i < KS + 8; i += kMergeThreads) dst[i] = i < len ? r.ikeys[off + i] : 0;
+                if (tid == 0) { if (which == 0) S.ulo_len = len; else S.uhi_len = len; }
+            }
+            // block table
+            for (uint32_t t = tid; t < S.n_blk_in; t += kMergeThreads) {
+                uint32_t j = 0;
+                while (j + 1 < P.k && t >= S.blk_base[j + 1]) j++;
+                const RunDev &r = P.runs[j];
+                uint32_t gb = S.lo[j] + (t - S.blk_base[j]);
+                S.tb_off[t] = S.in_off[j] + (uint32_t)(r.blk_off[gb] - r.blk_off[S.lo[j]]);
+                S.tb_size[t] = r.blk_size[gb];
+                S.tb_rec[t] = S.rec_base[j] + (r.blk_rec[gb] - r.blk_rec[S.lo[j]]);
+                S.tb_nrec[t] = r.blk_rec[gb + 1] - r.blk_rec[gb];
+            }
+            if (P.use_tma && S.in_bytes) {
+                mbar_wait((uint64_t *)&S.mbar, phase);
+                phase ^= 1;
+            }
+        }
+        __syncthreads();
+
+        // ---- decode: one warp per block ---------------------------------------------------------
+        if (tile_ok) {
+            for (uint32_t t = warp; t < S.n_blk_in; t += kMergeWarps) {
+                const uint8_t *base = A.in + S.tb_off[t];
+                uint32_t size = S.tb_size[t], rec0 = S.tb_rec[t], expect = S.tb_nrec[t];
+                uint32_t err = 0, nr = 0;
+                if (size < 8) err = PGS_CORRUPTION;
+                if (!err) {
+                    nr = ld_u32(base + size - 4);
+                    if (nr == 0 || (unsigned long long)nr * 4 + 4 > size) err = PGS_CORRUPTION;
+                }
+                uint32_t limit = err ? 0 : size - 4 - 4 * nr;
+                uint32_t p = 0, prev_klen = 0, i = 0;
+                while (!err && p < limit && i < expect) {
+                    uint32_t shared, non_shared, vlen, h = 0, c;
+                    c = get_varint32(base + p, limit - p, shared);
+                    h += c;
+                    if (c) { c = get_varint32(base + p + h, limit - p - h, non_shared); h += c; }
+                    if (c) { c = get_varint32(base + p + h, limit - p - h, vlen); h += c; }
+                    if (!c) { err = PGS_CORRUPTION; break; }
+                    uint32_t klen = shared + non_shared;
+                    if (shared > prev_klen || klen < 8 || klen - 8 > KS || (unsigned long long)p + h + non_shared + vlen > limit) {
+                        err = PGS_CORRUPTION;
+                        break;
+                    }
+                    for (uint32_t x = lane; x < non_shared; x += 32) wscr[shared + x] = base[p + h + x];
+                    __syncwarp();
+                    uint32_t ulen = klen - 8, r = rec0 + i;
+                    uint32_t words = (ulen + 7) >> 3;
+                    for (uint32_t w = lane; w < words; w += 32) {
+                        unsigned long long v = *(const unsigned long long *)(wscr + 8 * w);
+                        uint32_t keep = ulen - 8 * w;
+                        if (keep < 8) v &= (1ull << (8 * keep)) - 1;
+                        *(unsigned long long *)(A.arena + (size_t)r * KS + 8 * w) = v;
+                    }
+                    if (lane == 0) {
+                        unsigned long long tr = 0;
+                        for (int x = 7; x >= 0; x--) tr = (tr << 8) | wscr[ulen + x];
+                        A.trailer[r] = tr;
+                        A.klen[r] = (uint16_t)ulen;
+                        A.voff[r] = S.tb_off[t] + p + h + non_shared;
+                        A.vlen[r] = vlen;
+                        A.flags[r] = 0;
+                    }
+                    __syncwarp();
+                    prev_klen = klen;
+                    p += h + non_shared + vlen;
+                    i++;
+                }
+                if (!err && (i != expect || p != limit)) err = PGS_CORRUPTION;
+                if (err && lane == 0) atomicMax(&S.error, err);
+            }
+        }
+        __syncthreads();
+        tile_ok = S.error == 0;
+
+        // ---- valid range of every run's slice: user keys in (U_lo, U_hi] ---------------------------
+        if (tile_ok && tid < P.k) {
+            uint32_t n = S.nrec[tid], base = S.rec_base[tid];
+            uint32_t vlo = 0, vhi = n;
+            for (uint32_t which = 0; which < 2; which++) {
+                if (which == 0 ? !S.has_lo : !S.has_hi) continue;
+                const uint8_t *U = which == 0 ? ulo : uhi;
+                uint32_t ul = which == 0 ? S.ulo_len : S.uhi_len;
+                uint32_t lo = 0, hi = n; // #records with ukey <= U
+                while (lo < hi) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (cmp_slots(A.arena + (size_t)(base + mid) * KS, A.klen[base + mid], U, ul) <= 0) lo = mid + 1; else hi = mid;
+                }
+                if (which == 0) vlo = lo; else vhi = lo;
+            }
+            if (vhi < vlo) vhi = vlo;
+            S.vlo[tid] = vlo;
+            S.vhi[tid] = vhi;
+        }
+        __syncthreads();
+        if (tile_ok && tid == 0) {
+            uint32_t nv = 0;
+            for (uint32_t j = 0; j < P.k; j++) nv += S.vhi[j] - S.vlo[j];
+            S.n_valid = nv;
+        }
+
+        // ---- merge rank + shadow detection: one thread per record ------------------------------------
+        if (tile_ok) {
+            for (uint32_t r = tid; r < S.n_rec; r += kMergeThreads) {
+                uint32_t j = 0;
+                while (j + 1 < P.k && r >= S.rec_base[j + 1]) j++;
+                uint32_t idx = r - S.rec_base[j];
+                if (idx < S.vlo[j] || idx >= S.vhi[j]) { A.flags[r] = 0; continue; }
+                const uint8_t *key = A.arena + (size_t)r * KS;
+                uint32_t kl = A.klen[r];
+                unsigned long long tr = A.trailer[r];
+                uint32_t rank = idx - S.vlo[j];
+                bool shadow = false;
+                if (idx > 0 && A.klen[r - 1] == kl && cmp_slots(A.arena + (size_t)(r - 1) * KS, kl, key, kl) == 0) shadow = true;
+                for (uint32_t o = 0; o < P.k; o++) {
+                    if (o == j) continue;
+                    uint32_t base = S.rec_base[o], lo = S.vlo[o], hi = S.vhi[o];
+                    while (lo < hi) { // first position whose internal key is not before ours
+                        uint32_t mid = (lo + hi) >> 1, q = base + mid;
+                        int c = cmp_slots(A.arena + (size_t)q * KS, A.klen[q], key, kl);
+                        bool before;
+                        if (c != 0) before = c < 0;
+                        else {
+                            unsigned long long tq = A.trailer[q];
+                            before = tq > tr || (tq == tr && o < j);
+                        }
+                        if (before) lo = mid + 1; else hi = mid;
+                    }
+                    rank += lo - S.vlo[o];
+                    if (lo > S.vlo[o]) {
+                        uint32_t q = base + lo - 1;
+                        if (A.klen[q] == kl && cmp_slots(A.arena + (size_t)q * KS, kl, key, kl) == 0) shadow = true;
+                    }
+                }
+                A.rank[r] = (uint16_t)rank;
+                A.flags[r] = F_VALID | (shadow ? F_SHADOW : 0);
+            }
+        }
+        __syncthreads();
+
+        // ---- compaction filter + tombstone policy; scatter into merged order -----------------------------
+        if (tile_ok) {
+            unsigned long long s_in = 0, s_inb = 0, s_sh = 0, s_tomb = 0, s_exp = 0, s_user = 0, s_stale = 0, s_ttl = 0;
+            for (uint32_t r = tid; r < S.n_rec; r += kMergeThreads) {
+                uint8_t f = A.flags[r];
+                if (!(f & F_VALID)) continue;
+                uint32_t kl = A.klen[r], vl = A.vlen[r];
+                s_in++;
+                s_inb += kl + vl;
+                A.order[A.rank[r]] = (uint16_t)r;
+                if (f & F_SHADOW) { s_sh++; continue; }
+                uint8_t type = (uint8_t)A.trailer[r];
+                if (type == PGS_TYPE_VALUE) {
+                    uint32_t nts = 0;
+                    bool changed;
+                    uint8_t *val = A.in + A.voff[r];
+                    uint32_t why = dev_filter(P, S.crc, A.arena + (size_t)r * KS, kl, val, vl, nts, changed);
+                    if (why) {
+                        if (why == 1) s_exp++; else if (why == 2) s_user++; else s_stale++;
+                        // Decision::kRemove turns the entry into a deletion; it disappears only at the bottommost level
+                        if (!P.bottommost) { f |= F_KEEP | F_TOMB; A.vlen[r] = 0; }
+                    } else {
+                        f |= F_KEEP;
+                        if (changed) {
+                            s_ttl++;
+                            val[0] = (uint8_t)(nts >> 24); val[1] = (uint8_t)(nts >> 16); val[2] = (uint8_t)(nts >> 8); val[3] = (uint8_t)nts;
+                        }
+                    }
+                } else if (type == PGS_TYPE_DELETION) {
+                    if (P.bottommost) s_tomb++; else f |= F_KEEP | F_TOMB;
+                } else {
+                    f |= F_KEEP;
+                }
+                A.flags[r] = f;
+            }
+            atomicAdd(&S.stat[ST_IN_REC], s_in);
+            atomicAdd(&S.stat[ST_IN_BYTES], s_inb);
+            atomicAdd(&S.stat[ST_SHADOW], s_sh);
+            atomicAdd(&S.stat[ST_TOMB], s_tomb);
+            atomicAdd(&S.stat[ST_EXPIRED], s_exp);
+            atomicAdd(&S.stat[ST_USER], s_user);
+            atomicAdd(&S.stat[ST_STALE], s_stale);
+            atomicAdd(&S.stat[ST_TTL], s_ttl);
+        }
+        __syncthreads();
+
+        // ---- survivors in merged order ---------------------------------------------------------------------
+        uint32_t m = 0;
+        if (tile_ok) {
+            const uint32_t nv = S.n_valid;
+            m = chunked_scan(nv, A.E, S.scan, [&](uint32_t p) -> uint32_t { return (A.flags[A.order[p]] & F_KEEP) ? 1u : 0u; });
+            for (uint32_t p = tid; p < nv; p += kMergeThreads) {
+                uint32_t r = A.order[p];
+                if (A.flags[r] & F_KEEP) A.surv[A.E[p]] = (uint16_t)r;
+            }
+            __syncthreads();
+            // raw sizes decide the block cuts (a block closes once it holds >= block_size raw bytes)
+            chunked_scan(m, A.R, S.scan, [&](uint32_t p) -> uint32_t { uint32_t r = A.surv[p]; return A.klen[r] + 8u + A.vlen[r] + 3u; });
+            if (tid == 0) {
+                uint32_t nb = 0, pos = 0;
+                S.cut[0] = 0;
+                while (pos < m && nb < kMaxOutBlocks) {
+                    uint32_t target = A.R[pos] + P.block_size;
+                    uint32_t lo = pos + 1, hi = m;
+                    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (A.R[mid] >= target) hi = mid; else lo = mid + 1; }
+                    pos = lo;
+                    S.cut[++nb] = pos;
+                }
+                if (pos < m) atomicMax(&S.error, (uint32_t)PGS_ABORTED);
+                S.n_ob = nb;
+                S.n_surv = m;
+            }
+            __syncthreads();
+            tile_ok = S.error == 0;
+        }
+        if (tile_ok) {
+            const uint32_t nob = S.n_ob;
+            // prefix compression against the previous survivor + encoded sizes
+            chunked_scan(m, A.E, S.scan, [&](uint32_t p) -> uint32_t {
+                uint32_t lo = 0, hi = nob; // last cut <= p
+                while (lo + 1 < hi) { uint32_t mid = (lo + hi) >> 1; if (S.cut[mid] <= p) lo = mid; else hi = mid; }
+                uint32_t r = A.surv[p], kl = A.klen[r], shared = 0;
+                if ((p - S.cut[lo]) % RI != 0) {
+                    uint32_t q = A.surv[p - 1];
+                    shared = lcp_slots(A.arena + (size_t)q * KS, A.klen[q], A.arena + (size_t)r * KS, kl);
+                }
+                A.shr[p] = (uint16_t)shared;
+                A.blkid[p] = (uint16_t)lo;
+                uint32_t ns = kl + 8 - shared, vl = A.vlen[r];
+                return varint_len(shared) + varint_len(ns) + varint_len(vl) + ns + vl;
+            });
+            if (tid < nob) {
+                uint32_t cnt = S.cut[tid + 1] - S.cut[tid];
+                uint32_t nrest = (cnt + RI - 1) / RI;
+                S.ob_size[tid] = A.E[S.cut[tid + 1]] - A.E[S.cut[tid]] + 4 * (nrest + 1);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t off = 0, koff = 0;
+                for (uint32_t b = 0; b < nob; b++) {
+                    S.ob_off[b] = off;
+                    S.ob_keyoff[b] = koff;
+                    off += (S.ob_size[b] + kBlockAlign - 1) & ~(kBlockAlign - 1);
+                    koff += A.klen[A.surv[S.cut[b + 1] - 1]];
+                }
+                S.ob_off[nob] = off;
+                S.ob_keyoff[nob] = koff;
+                S.tile_bytes = off;
+                S.tile_keyb = koff;
+            }
+            __syncthreads();
+        } else if (tid == 0) {
+            S.n_ob = 0; S.n_surv = 0; S.tile_bytes = 0; S.tile_keyb = 0;
+        }
+        __syncthreads();
+
+        // ---- decoupled look-back: where does this tile's output start? ----------------------------------------
+        if (warp == 0) {
+            unsigned long long my_bytes = S.tile_bytes;
+            uint32_t my_blocks = S.n_ob, my_recs = S.n_surv, my_keyb = S.tile_keyb;
+            if (lane == 0 && tile > 0) publish(&P.agg[tile], my_bytes, my_blocks, my_recs, my_keyb);
+            unsigned long long ex_bytes = 0;
+            uint32_t ex_blocks = 0, ex_recs = 0, ex_keyb = 0;
+            int64_t look = (int64_t)tile - 1;
+            while (look >= 0) {
+                int64_t idx = look - lane;
+                uint32_t have_inc = 0;
+                unsigned long long b = 0;
+                uint32_t bl = 0, rc = 0, kb = 0;
+                if (idx >= 0) {
+                    for (;;) {
+                        if (*(volatile uint32_t *)&P.inc[idx].flag) { have_inc = 1; break; }
+                        if (*(volatile uint32_t *)&P.agg[idx].flag) break;
+                    }
+                    __threadfence();
+                    const volatile TileAgg *s = have_inc ? &P.inc[idx] : &P.agg[idx];
+                    b = s->bytes; bl = s->blocks; rc = s->recs; kb = s->keyb;
+                }
+                uint32_t inc_mask = __ballot_sync(kFull, have_inc);
+                uint32_t stop = inc_mask ? (uint32_t)__ffs(inc_mask) - 1 : 31; // nearest predecessor with an inclusive prefix
+                if (lane > stop || idx < 0) { b = 0; bl = 0; rc = 0; kb = 0; }
+                for (uint32_t d = 16; d; d >>= 1) {
+                    b += __shfl_xor_sync(kFull, b, d);
+                    bl += __shfl_xor_sync(kFull, bl, d);
+                    rc += __shfl_xor_sync(kFull, rc, d);
+                    kb += __shfl_xor_sync(kFull, kb, d);
+                }
+                ex_bytes += b; ex_blocks += bl; ex_recs += rc; ex_keyb += kb;
+                if (inc_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) {
+                publish(&P.inc[tile], ex_bytes + my_bytes, ex_blocks + my_blocks, ex_recs + my_recs, ex_keyb + my_keyb);
+                S.base_bytes = ex_bytes;
+                S.base_blocks = ex_blocks;
+                S.base_recs = ex_recs;
+                S.base_keyb = ex_keyb;
+                if (ex_bytes + my_bytes > P.out_cap || ex_blocks + my_blocks > P.out_blk_cap || ex_keyb + my_keyb > P.out_ikey_cap)
+                    atomicMax(&S.error, (uint32_t)PGS_ABORTED);
+            }
+        }
+        __syncthreads();
+        tile_ok = S.error == 0;
+
+        // ---- write the tile's blocks ------------------------------------------------------------------------------
+        if (tile_ok && m > 0) {
+            const uint32_t nob = S.n_ob;
+            uint8_t *out = P.out_data + S.base_bytes;
+            unsigned long long s_outb = 0, s_otomb = 0, s_okey = 0, s_oval = 0, mn_seq = ~0ull, mx_seq = 0;
+            uint32_t mx_k = 0, mx_v = 0;
+            for (uint32_t p = warp; p < m; p += kMergeWarps) {
+                uint32_t r = A.surv[p], b = A.blkid[p];
+                uint32_t kl = A.klen[r], vl = A.vlen[r], shared = A.shr[p];
+                uint8_t f = A.flags[r];
+                unsigned long long tr = A.trailer[r];
+                uint8_t type = (f & F_TOMB) ? (uint8_t)PGS_TYPE_DELETION : (uint8_t)tr;
+                unsigned long long seq = (P.bottommost && type == PGS_TYPE_VALUE) ? 0ull : (tr >> 8);
+                unsigned long long otr = (seq << 8) | type;
+                uint32_t ns = kl + 8 - shared;
+                uint32_t h = 0;
+                if (lane == 0) {
+                    h = put_varint32(wscr, shared);
+                    h += put_varint32(wscr + h, ns);
+                    h += put_varint32(wscr + h, vl);
+                }
+                h = __shfl_sync(kFull, h, 0);
+                const uint8_t *ks = A.arena + (size_t)r * KS + shared;
+                for (uint32_t x = lane; x < kl - shared; x += 32) wscr[h + x] = ks[x];
+                if (lane < 8) wscr[h + kl - shared + lane] = (uint8_t)(otr >> (8 * lane));
+                __syncwarp();
+                uint8_t *dst = out + S.ob_off[b] + (A.E[p] - A.E[S.cut[b]]);
+                uint32_t hs = h + ns;
+                warp_copy_s2g(dst, wscr, hs, lane);
+                warp_copy_s2g(dst + hs, A.in + A.voff[r], vl, lane);
+                __syncwarp();
+                if (lane == 0) {
+                    s_outb += kl + vl;
+                    s_otomb += type == PGS_TYPE_DELETION;
+                    s_okey += kl;
+                    s_oval += vl;
+                    mx_k = max(mx_k, kl);
+                    mx_v = max(mx_v, vl);
+                    mn_seq = seq < mn_seq ? seq : mn_seq;
+                    mx_seq = seq > mx_seq ? seq : mx_seq;
+                }
+            }
+            if (lane == 0) {
+                atomicAdd(&S.stat[ST_OUT_BYTES], s_outb);
+                atomicAdd(&S.stat[ST_OUT_TOMB], s_otomb);
+                atomicAdd(&S.stat[ST_OUT_KEY], s_okey);
+                atomicAdd(&S.stat[ST_OUT_VAL], s_oval);
+                atomicMax(&S.max_ukey, mx_k);
+                atomicMax(&S.max_vlen, mx_v);
+                atomicMin(&S.min_seq, mn_seq);
+                atomicMax(&S.max_seq, mx_seq);
+            }
+            // restart arrays, padding, index entries: one thread per output block
+            for (uint32_t b = tid; b < nob; b += kMergeThreads) {
+                uint32_t c0 = S.cut[b], c1 = S.cut[b + 1], cnt = c1 - c0;
+                uint32_t nrest = (cnt + RI - 1) / RI;
+                uint32_t ent = A.E[c1] - A.E[c0];
+                uint8_t *bp = out + S.ob_off[b];
+                uint8_t *rp = bp + ent;
+                for (uint32_t i = 0; i <= nrest; i++) {
+                    uint32_t v = i < nrest ? A.E[c0 + i * RI] - A.E[c0] : nrest;
+                    rp[4 * i] = (uint8_t)v; rp[4 * i + 1] = (uint8_t)(v >> 8); rp[4 * i + 2] = (uint8_t)(v >> 16); rp[4 * i + 3] = (uint8_t)(v >> 24);
+                }
+                for (uint32_t x = S.ob_size[b]; x < S.ob_off[b + 1] - S.ob_off[b]; x++) bp[x] = 0;
+                uint32_t g = S.base_blocks + b;
+                P.out_blk_off[g] = S.base_bytes + S.ob_off[b];
+                P.out_blk_size[g] = S.ob_size[b];
+                P.out_blk_rec[g] = S.base_recs + c0;
+                P.out_ikey_off[g] = S.base_keyb + S.ob_keyoff[b];
+                uint32_t lr = A.surv[c1 - 1], lk = A.klen[lr];
+                uint8_t *kd = P.out_ikeys + S.base_keyb + S.ob_keyoff[b];
+                const uint8_t *ksrc = A.arena + (size_t)lr * KS;
+                for (uint32_t x = 0; x < lk; x++) kd[x] = ksrc[x];
+                atomicMax(&S.max_blk_size, S.ob_size[b]);
+                atomicMax(&S.max_blk_rec, cnt);
+            }
+            if (tid == 0) S.stat[ST_OUT_REC] = m;
+        }
+        if (last && tid == 0) { // sentinels of the new run's index
+            uint32_t g = S.base_blocks + S.n_ob;
+            if (g <= P.out_blk_cap) {
+                P.out_blk_off[g] = S.base_bytes + S.tile_bytes;
+                P.out_blk_rec[g] = S.base_recs + S.n_surv;
+                P.out_ikey_off[g] = S.base_keyb + S.tile_keyb;
+            }
+        }
+        __syncthreads();
+        if (tid < 16 && S.stat[tid]) {
+            unsigned long long *g = &P.stats->in_records;
+            static_assert(ST_OUT_VAL == 12, "stat layout");
+            // MergeStats starts with in_records,in_bytes,out_records,out_bytes,dropped_shadowed,dropped_tombstone,
+            // dropped_expired,dropped_user,dropped_stale,ttl_rewritten,out_tomb,out_raw_key,out_raw_val
+            atomicAdd(g + tid, S.stat[tid]);
+        }
+        if (tid == 0) {
+            if (S.error) {
+                atomicMax(&P.stats->error, S.error);
+                atomicMin(&P.stats->error_tile, tile);
+            } else if (S.n_surv) {
+                atomicMax(&P.stats->max_ukey, S.max_ukey);
+                atomicMax(&P.stats->max_vlen, S.max_vlen);
+                atomicMax(&P.stats->max_blk_size, S.max_blk_size);
+                atomicMax(&P.stats->max_blk_rec, S.max_blk_rec);
+                atomicMin(&P.stats->min_seq, S.min_seq);
+                atomicMax(&P.stats->max_seq, S.max_seq);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static uint64_t *g_crc_dev[16] = {nullptr};
+
+} // namespace pgs
+
+using namespace pgs;
+
+namespace pgs {
+const uint64_t *crc64_table();
+}
+
+extern "C" int32_t pgs_compact(pgs_partition *ph, const uint64_t *run_ids, uint32_t k, int32_t out_level,
+                               int32_t bottommost, const pgs_filter_params *fp, uint32_t now,
+                               pgs_compact_result *out)
+{
+    if (!ph || !run_ids || k == 0 || out_level < 0) return PGS_INVALID_ARGUMENT;
+    Partition &part = ph->p;
+    Engine *e = part.eng;
+    pgs_compact_result res{};
+    std::vector<std::shared_ptr<Run>> in;
+    {
+        std::lock_guard<std::mutex> g(part.mu);
+        for (uint32_t i = 0; i < k; i++) {
+            auto r = part.find(run_ids[i]);
+            if (!r) { set_error("compact: unknown run %llu", (unsigned long long)run_ids[i]); return PGS_NOT_FOUND; }
+            for (auto &x : in) if (x == r) return PGS_INVALID_ARGUMENT;
+            in.push_back(r);
+        }
+        if (bottommost < 0) { // true iff every run outside the input set is newer than every input
+            size_t first_in = part.runs.size();
+            for (size_t i = 0; i < part.runs.size(); i++)
+                if (std::find(in.begin(), in.end(), part.runs[i]) != in.end()) { first_in = i; break; }
+            bottommost = 1;
+            for (size_t i = first_in; i < part.runs.size(); i++)
+                if (std::find(in.begin(), in.end(), part.runs[i]) == in.end()) bottommost = 0;
+        }
+    }
+    if (k > kMaxRuns) { set_error("compact: %u runs > %u per merge", k, kMaxRuns); return PGS_NOT_SUPPORTED; }
+    PGS_CUDA(cudaSetDevice(e->device));
+  for (int rigorous = 0; rigorous < 2; rigorous++) {
+    cudaStream_t st = e->stream;
+
+    MergeParams P{};
+    P.k = k;
+    uint32_t max_ukey = 0, max_blk = 0, max_blk_rec = 0;
+    uint64_t total_blocks = 0, n_rec = 0, raw_key = 0, raw_val = 0, in_block_bytes = 0;
+    for (uint32_t i = 0; i < k; i++) {
+        P.runs[i] = in[i]->dev();
+        const pgs_run_info &fi = in[i]->info;
+        max_ukey = std::max(max_ukey, fi.max_ukey_len);
+        max_blk = std::max(max_blk, fi.max_block_size);
+        max_blk_rec = std::max(max_blk_rec, fi.max_block_records);
+        total_blocks += fi.n_blocks;
+        n_rec += fi.n_records;
+        raw_key += fi.raw_key_bytes;
+        raw_val += fi.raw_value_bytes;
+        in_block_bytes += fi.data_bytes;
+        if (fi.n_blocks >= (1u << 28)) return PGS_NOT_SUPPORTED;
+    }
+    if (max_ukey > kMaxUkeyLen) { set_error("compact: user key of %u bytes > %u", max_ukey, kMaxUkeyLen); return PGS_NOT_SUPPORTED; }
+    const uint32_t KS = std::max(8u, (max_ukey + 7) & ~7u);
+    P.KS = KS;
+    P.rec_cost = KS + kRecExtra;
+    P.warp_scratch = (KS + 48 + 15) & ~15u;
+    P.total_blocks = (uint32_t)total_blocks;
+    P.use_tma = (e->cfg.flags & PGS_ENGINE_NO_TMA) ? 0 : 1;
+    P.block_size = e->cfg.block_size;
+    P.restart_interval = e->cfg.restart_interval;
+    P.bottommost = bottommost ? 1 : 0;
+    P.now = now;
+    P.data_version = part.data_version;
+    std::vector<uint8_t> ops_host;
+    if (fp) {
+        P.enabled = fp->enabled;
+        P.validate_hash = fp->validate_hash;
+        P.default_ttl = fp->default_ttl;
+        P.pidx = fp->pidx;
+        P.partition_version = fp->partition_version;
+        if (fp->ops && fp->ops_len >= 4) {
+            memcpy(&P.n_ops, fp->ops, 4);
+            ops_host.assign(fp->ops, fp->ops + fp->ops_len);
+        }
+    }
+
+    cudaFuncAttributes attr;
+    PGS_CUDA(cudaFuncGetAttributes(&attr, k_merge));
+    uint32_t ctas = e->cfg.ctas_per_sm;
+    const uint32_t fixed_dyn = 2 * (KS + 8) + kMergeWarps * P.warp_scratch;
+    const uint64_t maxw = (((uint64_t)max_blk + 15) & ~15ull) + 16 + (uint64_t)max_blk_rec * P.rec_cost;
+    uint32_t dyn = 0;
+    uint64_t T = 0;
+    for (;; ctas--) {
+        if (ctas == 0) { set_error("compact: blocks/records too large for shared memory (k=%u, max block %u B)", k, max_blk); return PGS_NOT_SUPPORTED; }
+        uint64_t per_cta = (228ull * 1024) / ctas - 1024; // SM shared memory split, 1 KB reserved per CTA
+        per_cta = std::min<uint64_t>(per_cta, (uint64_t)e->max_smem_optin);
+        if (per_cta < attr.sharedSizeBytes + fixed_dyn + 1024) continue;
+        dyn = (uint32_t)((per_cta - attr.sharedSizeBytes) & ~127ull);
+        uint64_t pool = dyn - fixed_dyn;
+        // a tile holds < T of whole blocks, the group of blocks that end on the boundary key
+        // (one per run at worst) and one partial block per run.  Groups larger than two blocks are
+        // rare, so the first attempt budgets k+2 blocks of slack; the kernel verifies every tile and
+        // the host retries with the rigorous 2k bound if one did not fit.
+        uint64_t overhead = (rigorous ? 2ull * k : (uint64_t)k + 2) * maxw + 256;
+        if (pool > overhead + maxw) { T = pool - overhead; P.pool_bytes = (uint32_t)pool; break; }
+    }
+    uint64_t W_total = 0;
+    for (uint32_t i = 0; i < k; i++) W_total += in[i]->info.data_bytes + in[i]->info.n_records * P.rec_cost;
+    uint64_t Q = std::max<uint64_t>(1, (W_total + T - 1) / T);
+    if (Q > 0x7FFFFFF0ull) return PGS_NOT_SUPPORTED;
+    P.Q = (uint32_t)Q;
+    P.tile_weight = T;
+
+    // output capacity bounds
+    const uint64_t RIv = P.restart_interval;
+    uint64_t raw_total = raw_key + raw_val + 11 * n_rec;
+    uint64_t blk_cap = raw_total / P.block_size + Q + 2;
+    uint64_t out_cap = raw_key + raw_val + 23 * n_rec + 19 * blk_cap + 4 * (n_rec / RIv + blk_cap) + 256;
+    out_cap = (out_cap + 255) & ~255ull;
+    uint64_t ikey_cap = std::min<uint64_t>(raw_key, blk_cap * (uint64_t)std::max(1u, max_ukey)) + 16;
+    if (blk_cap > 0xFFFFFFF0ull || ikey_cap > 0xFFFFFFF0ull) return PGS_NOT_SUPPORTED;
+
+    auto outr = std::make_shared<Run>();
+    outr->level = out_level;
+    outr->data_cap = out_cap + 256;
+    uint32_t *d_split_pos = nullptr, *d_split_ref = nullptr, *d_ticket = nullptr;
+    TileAgg *d_agg = nullptr;
+    MergeStats *d_stats = nullptr;
+    uint8_t *d_ops = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_split_pos); cudaFree(d_split_ref); cudaFree(d_ticket); cudaFree(d_agg); cudaFree(d_stats); cudaFree(d_ops);
+    };
+#define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr); } } while (0)
+    CK(cudaMalloc(&outr->d_data, outr->data_cap));
+    CK(cudaMalloc(&outr->d_blk_off, sizeof(uint64_t) * (blk_cap + 1)));
+    CK(cudaMalloc(&outr->d_blk_size, sizeof(uint32_t) * (blk_cap + 1)));
+    CK(cudaMalloc(&outr->d_blk_rec, sizeof(uint32_t) * (blk_cap + 1)));
+    CK(cudaMalloc(&outr->d_ikey_off, sizeof(uint32_t) * (blk_cap + 1)));
+    CK(cudaMalloc(&outr->d_ikeys, ikey_cap));
+    CK(cudaMalloc(&d_split_pos, sizeof(uint32_t) * (Q + 1) * k));
+    CK(cudaMalloc(&d_split_ref, sizeof(uint32_t) * (Q + 1)));
+    CK(cudaMalloc(&d_ticket, 256));
+    CK(cudaMalloc(&d_agg, sizeof(TileAgg) * 2 * Q));
+    CK(cudaMalloc(&d_stats, sizeof(MergeStats)));
+    CK(cudaMemsetAsync(d_split_pos, 0xFF, sizeof(uint32_t) * (Q + 1) * k, st));
+    CK(cudaMemsetAsync(d_split_ref, 0xFF, sizeof(uint32_t) * (Q + 1), st));
+    CK(cudaMemsetAsync(d_ticket, 0, 256, st));
+    CK(cudaMemsetAsync(d_agg, 0, sizeof(TileAgg) * 2 * Q, st));
+    MergeStats hs{};
+    hs.min_seq = ~0ull;
+    hs.error_tile = 0xFFFFFFFFu;
+    CK(cudaMemcpyAsync(d_stats, &hs, sizeof hs, cudaMemcpyHostToDevice, st));
+    if (!ops_host.empty()) {
+        CK(cudaMalloc(&d_ops, ops_host.size()));
+        CK(cudaMemcpyAsync(d_ops, ops_host.data(), ops_host.size(), cudaMemcpyHostToDevice, st));
+        P.ops = d_ops;
+    }
+    if (P.validate_hash) {
+        int dev = e->device;
+        if (!g_crc_dev[dev & 15]) {
+            uint64_t *t = nullptr;
+            CK(cudaMalloc(&t, 256 * 8));
+            CK(cudaMemcpyAsync(t, crc64_table(), 256 * 8, cudaMemcpyHostToDevice, st));
+            g_crc_dev[dev & 15] = t;
+        }
+        P.crc_table = (const unsigned long long *)g_crc_dev[dev & 15];
+    }
+    P.split_pos = d_split_pos;
+    P.split_ref = d_split_ref;
+    P.ticket = d_ticket;
+    P.agg = d_agg;
+    P.inc = d_agg + Q;
+    P.out_data = outr->d_data;
+    P.out_cap = out_cap;
+    P.out_blk_off = (unsigned long long *)outr->d_blk_off;
+    P.out_blk_size = outr->d_blk_size;
+    P.out_blk_rec = outr->d_blk_rec;
+    P.out_ikey_off = outr->d_ikey_off;
+    P.out_ikeys = outr->d_ikeys;
+    P.out_blk_cap = (uint32_t)blk_cap;
+    P.out_ikey_cap = (uint32_t)ikey_cap;
+    P.stats = d_stats;
+
+    cudaEvent_t ev0, ev1, ev2;
+    CK(cudaEventCreate(&ev0));
+    CK(cudaEventCreate(&ev1));
+    CK(cudaEventCreate(&ev2));
+    CK(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CK(cudaFuncSetAttribute(k_merge, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaEventRecord(ev0, st));
+    k_plan<<<(uint32_t)((total_blocks + 255) / 256), 256, 0, st>>>(P);
+    CK(cudaEventRecord(ev1, st));
+    uint32_t grid = (uint32_t)std::min<uint64_t>(Q, (uint64_t)ctas * e->sm_count);
+    k_merge<<<grid, kMergeThreads, dyn, st>>>(P);
+    CK(cudaEventRecord(ev2, st));
+    e->launches += 2;
+    CK(cudaMemcpyAsync(&hs, d_stats, sizeof hs, cudaMemcpyDeviceToHost, st));
+    TileAgg fin{};
+    CK(cudaMemcpyAsync(&fin, d_agg + Q + (Q - 1), sizeof fin, cudaMemcpyDeviceToHost, st));
+    cudaError_t se = cudaStreamSynchronize(st);
+    if (se != cudaSuccess) { cleanup(); return cuda_fail(se, "compaction kernels"); }
+    float ms_total = 0, ms_merge = 0;
+    cudaEventElapsedTime(&ms_total, ev0, ev2);
+    cudaEventElapsedTime(&ms_merge, ev1, ev2);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+    cleanup();
+#undef CK
+    if (hs.error) {
+        set_error("compaction kernel failed with status %u at tile %u of %u (T=%llu, dyn smem %u)", hs.error, hs.error_tile,
+                  P.Q, (unsigned long long)T, dyn);
+        if (hs.error == PGS_ABORTED && !rigorous) continue; // a tile did not fit: retry with the rigorous bound
+        return (int32_t)hs.error;
+    }
+    res.in_records = hs.in_records; res.out_records = hs.out_records;
+    res.in_bytes = hs.in_bytes; res.out_bytes = hs.out_bytes;
+    res.in_block_bytes = in_block_bytes; res.out_block_bytes = fin.bytes;
+    res.dropped_shadowed = hs.dropped_shadowed; res.dropped_tombstone = hs.dropped_tombstone;
+    res.dropped_expired = hs.dropped_expired; res.dropped_user = hs.dropped_user; res.dropped_stale = hs.dropped_stale;
+    res.ttl_rewritten = hs.ttl_rewritten;
+    res.n_tiles = P.Q; res.n_launches = 2;
+    res.device_ms = ms_total; res.merge_kernel_ms = ms_merge;
+
+    outr->info.level = out_level;
+    outr->info.n_blocks = fin.blocks;
+    outr->info.n_records = fin.recs;
+    outr->info.n_tombstones = hs.out_tomb;
+    outr->info.data_bytes = fin.bytes;
+    outr->info.raw_key_bytes = hs.out_raw_key;
+    outr->info.raw_value_bytes = hs.out_raw_val;
+    outr->info.max_ukey_len = hs.max_ukey;
+    outr->info.max_value_len = hs.max_vlen;
+    outr->info.max_block_size = hs.max_blk_size;
+    outr->info.max_block_records = hs.max_blk_rec;
+    outr->info.smallest_seq = hs.min_seq;
+    outr->info.largest_seq = hs.max_seq;
+    {
+        std::lock_guard<std::mutex> g(part.mu);
+        for (auto &r : in) part.runs.erase(std::find(part.runs.begin(), part.runs.end(), r));
+        if (fin.blocks > 0) {
+            outr->id = e->next_run_id++;
+            outr->info.run_id = outr->id;
+            part.insert(outr);
+            res.new_run_id = outr->id;
+        }
+    }
+    if (out) *out = res;
+    return PGS_OK;
+  }
+    return PGS_ABORTED;
+}

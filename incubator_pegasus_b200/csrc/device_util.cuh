@@ -1,0 +1,195 @@
+// device_util.cuh — device-side primitives shared by the sm_100a kernels: TMA bulk copies and
+// mbarriers (inline PTX), varint decode, byte-string compares, warp/block scans, misaligned
+// warp copies.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "format.h"
+
+namespace pgs {
+
+#define PGS_DEV __device__ __forceinline__
+
+constexpr uint32_t kWarp = 32;
+constexpr uint32_t kFull = 0xffffffffu;
+
+// ---- shared-memory addressing / mbarrier / TMA bulk (cp.async.bulk) ----------------------------
+PGS_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+PGS_DEV void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+PGS_DEV void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+PGS_DEV void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+PGS_DEV bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+PGS_DEV void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy through the TMA unit; bytes % 16 == 0, both addresses 16-aligned
+PGS_DEV void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---- varint (RocksDB util/coding.h encoding) ---------------------------------------------------
+// returns bytes consumed, 0 on malformed / out of range
+PGS_DEV uint32_t get_varint32(const uint8_t *p, uint32_t avail, uint32_t &v)
+{
+    uint32_t r = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < 5; i++) {
+        if (i >= avail) return 0;
+        uint32_t b = p[i];
+        r |= (b & 127u) << (7 * i);
+        if (!(b & 128u)) { v = r; return i + 1; }
+    }
+    return 0;
+}
+PGS_DEV uint32_t put_varint32(uint8_t *p, uint32_t v)
+{
+    uint32_t n = 0;
+    while (v >= 128) { p[n++] = (uint8_t)(v | 128); v >>= 7; }
+    p[n++] = (uint8_t)v;
+    return n;
+}
+
+// ---- byte-string compare -------------------------------------------------------------------------
+// generic pointers, any alignment; returns <0, 0, >0 like memcmp-then-length
+PGS_DEV int cmp_bytes(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb)
+{
+    uint32_t m = la < lb ? la : lb;
+    for (uint32_t i = 0; i < m; i++) {
+        int d = (int)a[i] - (int)b[i];
+        if (d) return d;
+    }
+    return la < lb ? -1 : (la > lb ? 1 : 0);
+}
+PGS_DEV uint64_t bswap64(uint64_t x)
+{
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+}
+// both keys live in 8-byte aligned slots that are zero padded up to a multiple of 8:
+// word-wise big-endian compare + length tie-break == bytewise lexicographic compare
+PGS_DEV int cmp_slots(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb)
+{
+    uint32_t m = la < lb ? la : lb;
+    uint32_t words = (m + 7) >> 3;
+    const uint64_t *wa = (const uint64_t *)a, *wb = (const uint64_t *)b;
+    for (uint32_t i = 0; i < words; i++) {
+        uint64_t x = wa[i], y = wb[i];
+        if (x != y) {
+            x = bswap64(x);
+            y = bswap64(y);
+            return x < y ? -1 : 1;
+        }
+    }
+    return la < lb ? -1 : (la > lb ? 1 : 0);
+}
+// longest common prefix of two zero-padded 8-aligned slots, capped at min(la, lb)
+PGS_DEV uint32_t lcp_slots(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb)
+{
+    uint32_t m = la < lb ? la : lb;
+    uint32_t words = (m + 7) >> 3;
+    const uint64_t *wa = (const uint64_t *)a, *wb = (const uint64_t *)b;
+    for (uint32_t i = 0; i < words; i++) {
+        uint64_t d = wa[i] ^ wb[i];
+        if (d) {
+            uint32_t n = i * 8 + ((__ffsll((long long)d) - 1) >> 3); // little-endian: lowest set byte
+            return n < m ? n : m;
+        }
+    }
+    return m;
+}
+
+// ---- scans -----------------------------------------------------------------------------------------
+PGS_DEV uint32_t warp_incl_scan(uint32_t v, uint32_t lane)
+{
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        uint32_t n = __shfl_up_sync(kFull, v, d);
+        if (lane >= d) v += n;
+    }
+    return v;
+}
+// exclusive scan of one value per thread over the whole CTA (blockDim.x <= 1024, multiple of 32).
+// `scratch` = 33 uint32 in shared memory.  Returns the exclusive prefix, *total = sum.
+PGS_DEV uint32_t block_excl_scan(uint32_t v, uint32_t *scratch, uint32_t *total)
+{
+    uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t inc = warp_incl_scan(v, lane);
+    __syncthreads(); // scratch may still be read from a previous call
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < nw ? scratch[lane] : 0;
+        uint32_t ws = warp_incl_scan(w, lane);
+        scratch[lane] = ws - w;
+        if (lane == 31) scratch[32] = ws;
+    }
+    __syncthreads();
+    *total = scratch[32];
+    return scratch[warp] + inc - v;
+}
+
+// ---- warp copies ------------------------------------------------------------------------------------
+// byte-granular copy (any address space), all 32 lanes participate
+PGS_DEV void warp_copy_bytes(uint8_t *dst, const uint8_t *src, uint32_t n, uint32_t lane)
+{
+    for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+}
+// shared -> global copy of n bytes, arbitrary alignment on both sides.  The body is written with
+// 16-byte stores aligned on the destination; source words are re-aligned with funnel shifts.
+PGS_DEV void warp_copy_s2g(uint8_t *dst, const uint8_t *src, uint32_t n, uint32_t lane)
+{
+    uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
+    if (head > n) head = n;
+    if (lane < head) dst[lane] = src[lane];
+    dst += head;
+    src += head;
+    n -= head;
+    uint32_t chunks = n >> 4;
+    uint32_t sh = (uint32_t)((uintptr_t)src & 3) * 8;
+    const uint32_t *sw = (const uint32_t *)((uintptr_t)src & ~(uintptr_t)3);
+    for (uint32_t c = lane; c < chunks; c += 32) {
+        const uint32_t *w = sw + c * 4;
+        uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+        uint4 o;
+        if (sh == 0) {
+            o = make_uint4(w0, w1, w2, w3);
+        } else {
+            uint32_t w4 = w[4];
+            o.x = __funnelshift_r(w0, w1, sh);
+            o.y = __funnelshift_r(w1, w2, sh);
+            o.z = __funnelshift_r(w2, w3, sh);
+            o.w = __funnelshift_r(w3, w4, sh);
+        }
+        *reinterpret_cast<uint4 *>(dst + c * 16) = o;
+    }
+    uint32_t done = chunks << 4;
+    uint32_t tail = n - done;
+    if (lane < tail) dst[done + lane] = src[done + lane];
+}
+
+} // namespace pgs

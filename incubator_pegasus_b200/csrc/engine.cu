@@ -1,0 +1,405 @@
+// engine.cu — device engine plumbing: engine / partition handles, run upload (RocksDB-format
+// blocks -> HBM) with the device-built block index, run download, run bookkeeping.
+// Replaces for this path: DB::Open (pegasus_server_impl.cpp:1551-1860), flush /
+// IngestExternalFile (rocksdb_wrapper.cpp:248-270) as far as "a sorted run appears in the DB".
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "device_util.cuh"
+#include "engine.h"
+
+namespace pgs {
+
+static thread_local std::string g_last_error;
+void set_error(const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+int32_t cuda_fail(cudaError_t e, const char *what)
+{
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return PGS_IO_ERROR; // CUDA faults map to kIOError
+}
+
+Run::~Run()
+{
+    cudaFree(d_data);
+    cudaFree(d_blk_off);
+    cudaFree(d_blk_size);
+    cudaFree(d_blk_rec);
+    cudaFree(d_ikey_off);
+    cudaFree(d_ikeys);
+}
+Engine::~Engine()
+{
+    if (h_pinned) cudaFreeHost(h_pinned);
+    if (stream) cudaStreamDestroy(stream);
+}
+void *Engine::pinned(size_t bytes)
+{
+    if (bytes > h_pinned_cap) {
+        if (h_pinned) cudaFreeHost(h_pinned);
+        h_pinned = nullptr;
+        size_t cap = bytes + (bytes >> 2) + 4096;
+        if (cudaMallocHost(&h_pinned, cap) != cudaSuccess) { h_pinned_cap = 0; return nullptr; }
+        h_pinned_cap = cap;
+    }
+    return h_pinned;
+}
+std::shared_ptr<Run> Partition::find(uint64_t id)
+{
+    for (auto &r : runs)
+        if (r->id == id) return r;
+    return nullptr;
+}
+void Partition::insert(std::shared_ptr<Run> r)
+{
+    size_t pos = 0;
+    while (pos < runs.size() && runs[pos]->level < r->level) pos++;
+    runs.insert(runs.begin() + pos, std::move(r));
+}
+
+// ------------------------------------------------------------------------------------------------
+// index build: one warp walks one block (entries are sequential inside a restart interval and
+// the last key needs every delta before it), the running internal key lives in a per-warp
+// shared-memory scratch.
+// ------------------------------------------------------------------------------------------------
+struct IndexStats {
+    unsigned long long n_records, n_tomb, raw_key, raw_val, min_seq, max_seq;
+    uint32_t max_ukey, max_vlen, max_blk_rec, error;
+};
+constexpr uint32_t kIdxWarps = 8;
+constexpr uint32_t kIdxScratch = kMaxUkeyLen + 16;
+
+template <bool kEmitKey>
+__global__ void __launch_bounds__(kIdxWarps * 32)
+k_index_walk(const uint8_t *__restrict__ data, const uint64_t *__restrict__ blk_off,
+             const uint32_t *__restrict__ blk_size, uint32_t nb, uint32_t *__restrict__ nrec_out,
+             uint32_t *__restrict__ lastlen_out, const uint32_t *__restrict__ ikey_off,
+             uint8_t *__restrict__ ikeys, IndexStats *__restrict__ stats)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t b = blockIdx.x * kIdxWarps + warp;
+    if (b >= nb) return;
+    uint8_t *scr = smem + warp * kIdxScratch;
+    const uint8_t *base = data + blk_off[b];
+    uint32_t size = blk_size[b];
+    uint32_t err = 0;
+    uint32_t nr = 0;
+    if (size < 8) err = PGS_CORRUPTION;
+    if (!err) {
+        const uint8_t *t = base + size - 4;
+        nr = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+        if (nr == 0 || (uint64_t)nr * 4 + 4 > size) err = PGS_CORRUPTION;
+    }
+    uint32_t limit = err ? 0 : size - 4 - 4 * nr;
+    uint32_t p = 0, prev_klen = 0, nrec = 0;
+    unsigned long long raw_key = 0, raw_val = 0, n_tomb = 0, min_seq = ~0ull, max_seq = 0;
+    uint32_t max_ukey = 0, max_vlen = 0;
+    while (!err && p < limit) {
+        uint32_t shared, non_shared, vlen, h = 0, c;
+        c = get_varint32(base + p, limit - p, shared);
+        h += c;
+        if (c) { c = get_varint32(base + p + h, limit - p - h, non_shared); h += c; }
+        if (c) { c = get_varint32(base + p + h, limit - p - h, vlen); h += c; }
+        if (!c) { err = PGS_CORRUPTION; break; }
+        uint32_t klen = shared + non_shared;
+        if (shared > prev_klen || klen < 8 || (uint64_t)p + h + non_shared + vlen > limit) { err = PGS_CORRUPTION; break; }
+        if (klen > kMaxUkeyLen + 8) { err = PGS_NOT_SUPPORTED; break; }
+        for (uint32_t i = lane; i < non_shared; i += 32) scr[shared + i] = base[p + h + i];
+        __syncwarp();
+        if (!kEmitKey && lane == 0) {
+            unsigned long long tr = 0;
+            for (int i = 7; i >= 0; i--) tr = (tr << 8) | scr[klen - 8 + i];
+            unsigned long long seq = tr >> 8;
+            n_tomb += ((uint8_t)tr == PGS_TYPE_DELETION);
+            min_seq = seq < min_seq ? seq : min_seq;
+            max_seq = seq > max_seq ? seq : max_seq;
+            raw_key += klen - 8;
+            raw_val += vlen;
+            max_ukey = max(max_ukey, klen - 8);
+            max_vlen = max(max_vlen, vlen);
+        }
+        __syncwarp();
+        nrec++;
+        prev_klen = klen;
+        p += h + non_shared + vlen;
+    }
+    if (!err && nrec == 0) err = PGS_CORRUPTION;
+    if (kEmitKey) {
+        if (!err) {
+            uint32_t ulen = prev_klen - 8;
+            uint8_t *dst = ikeys + ikey_off[b];
+            for (uint32_t i = lane; i < ulen; i += 32) dst[i] = scr[i];
+        }
+    } else if (lane == 0) {
+        nrec_out[b] = nrec;
+        lastlen_out[b] = err ? 0 : prev_klen - 8;
+        atomicAdd(&stats->n_records, (unsigned long long)nrec);
+        atomicAdd(&stats->n_tomb, n_tomb);
+        atomicAdd(&stats->raw_key, raw_key);
+        atomicAdd(&stats->raw_val, raw_val);
+        atomicMin(&stats->min_seq, min_seq);
+        atomicMax(&stats->max_seq, max_seq);
+        atomicMax(&stats->max_ukey, max_ukey);
+        atomicMax(&stats->max_vlen, max_vlen);
+        atomicMax(&stats->max_blk_rec, nrec);
+    }
+    if (err && lane == 0) atomicMax(&stats->error, err);
+}
+
+int32_t build_index(Engine *e, Run *r, const uint64_t *h_blk_off, const uint32_t *h_blk_size)
+{
+    uint32_t nb = r->info.n_blocks;
+    cudaStream_t st = e->stream;
+    uint32_t *d_nrec = nullptr, *d_lastlen = nullptr;
+    IndexStats *d_stats = nullptr;
+    PGS_CUDA(cudaMalloc(&d_nrec, sizeof(uint32_t) * nb));
+    PGS_CUDA(cudaMalloc(&d_lastlen, sizeof(uint32_t) * nb));
+    PGS_CUDA(cudaMalloc(&d_stats, sizeof(IndexStats)));
+    IndexStats hs{};
+    hs.min_seq = ~0ull;
+    PGS_CUDA(cudaMemcpyAsync(d_stats, &hs, sizeof hs, cudaMemcpyHostToDevice, st));
+    uint32_t grid = (nb + kIdxWarps - 1) / kIdxWarps;
+    size_t smem = kIdxWarps * kIdxScratch;
+    PGS_CUDA(cudaFuncSetAttribute(k_index_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PGS_CUDA(cudaFuncSetAttribute(k_index_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_index_walk<false><<<grid, kIdxWarps * 32, smem, st>>>(r->d_data, r->d_blk_off, r->d_blk_size, nb, d_nrec,
+                                                            d_lastlen, nullptr, nullptr, d_stats);
+    e->launches++;
+    std::vector<uint32_t> nrec(nb), lastlen(nb);
+    PGS_CUDA(cudaMemcpyAsync(nrec.data(), d_nrec, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
+    PGS_CUDA(cudaMemcpyAsync(lastlen.data(), d_lastlen, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
+    PGS_CUDA(cudaMemcpyAsync(&hs, d_stats, sizeof hs, cudaMemcpyDeviceToHost, st));
+    PGS_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_nrec);
+    cudaFree(d_lastlen);
+    if (hs.error) {
+        cudaFree(d_stats);
+        set_error("run upload: block scan failed with status %u", hs.error);
+        return (int32_t)hs.error;
+    }
+    std::vector<uint32_t> rec_cum(nb + 1), key_cum(nb + 1);
+    uint64_t rc = 0, kc = 0;
+    uint32_t max_blk = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+        rec_cum[b] = (uint32_t)rc;
+        key_cum[b] = (uint32_t)kc;
+        rc += nrec[b];
+        kc += lastlen[b];
+        max_blk = std::max(max_blk, h_blk_size[b]);
+    }
+    if (rc > 0xFFFFFFF0ull || kc > 0xFFFFFFF0ull) {
+        cudaFree(d_stats);
+        set_error("run too large for 32-bit record / index-key offsets");
+        return PGS_NOT_SUPPORTED;
+    }
+    rec_cum[nb] = (uint32_t)rc;
+    key_cum[nb] = (uint32_t)kc;
+    PGS_CUDA(cudaMalloc(&r->d_blk_rec, sizeof(uint32_t) * (nb + 1)));
+    PGS_CUDA(cudaMalloc(&r->d_ikey_off, sizeof(uint32_t) * (nb + 1)));
+    PGS_CUDA(cudaMalloc(&r->d_ikeys, kc + 16));
+    PGS_CUDA(cudaMemcpyAsync(r->d_blk_rec, rec_cum.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
+    PGS_CUDA(cudaMemcpyAsync(r->d_ikey_off, key_cum.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
+    k_index_walk<true><<<grid, kIdxWarps * 32, smem, st>>>(r->d_data, r->d_blk_off, r->d_blk_size, nb, nullptr,
+                                                           nullptr, r->d_ikey_off, r->d_ikeys, d_stats);
+    e->launches++;
+    PGS_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_stats);
+    r->info.n_records = hs.n_records;
+    r->info.n_tombstones = hs.n_tomb;
+    r->info.raw_key_bytes = hs.raw_key;
+    r->info.raw_value_bytes = hs.raw_val;
+    r->info.max_ukey_len = hs.max_ukey;
+    r->info.max_value_len = hs.max_vlen;
+    r->info.max_block_size = max_blk;
+    r->info.max_block_records = hs.max_blk_rec;
+    r->info.smallest_seq = hs.min_seq;
+    r->info.largest_seq = hs.max_seq;
+    return PGS_OK;
+}
+
+} // namespace pgs
+
+using namespace pgs;
+
+extern "C" {
+
+const char *pgs_last_error(void) { return g_last_error.c_str(); }
+
+int32_t pgs_engine_open(const pgs_engine_config *cfg, pgs_engine **out)
+{
+    if (!out) return PGS_INVALID_ARGUMENT;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        // no CPU fallback: the engine exists only on a GPU
+        set_error("no CUDA device: %s", cudaGetErrorString(ce));
+        return PGS_IO_ERROR;
+    }
+    auto *h = new pgs_engine;
+    Engine &e = h->e;
+    if (cfg) e.cfg = *cfg;
+    if (!e.cfg.block_size) e.cfg.block_size = kDefaultBlockSize;
+    if (!e.cfg.restart_interval) e.cfg.restart_interval = kDefaultRestartInterval;
+    if (!e.cfg.ctas_per_sm) e.cfg.ctas_per_sm = 2;
+    int dev = e.cfg.device;
+    if (dev < 0) cudaGetDevice(&dev);
+    e.device = dev;
+    cudaError_t err = cudaSetDevice(dev);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e.sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (err != cudaSuccess) {
+        delete h;
+        return cuda_fail(err, "engine open");
+    }
+    *out = h;
+    return PGS_OK;
+}
+void pgs_engine_close(pgs_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->e.device);
+    cudaStreamSynchronize(e->e.stream);
+    delete e;
+}
+void *pgs_engine_stream(pgs_engine *e) { return (void *)e->e.stream; }
+int32_t pgs_engine_sync(pgs_engine *e)
+{
+    PGS_CUDA(cudaSetDevice(e->e.device));
+    PGS_CUDA(cudaStreamSynchronize(e->e.stream));
+    return PGS_OK;
+}
+uint64_t pgs_engine_launches(pgs_engine *e) { return e->e.launches.load(); }
+
+int32_t pgs_partition_create(pgs_engine *e, int32_t app_id, int32_t pidx, uint32_t data_version,
+                             pgs_partition **out)
+{
+    if (!e || !out || data_version > 1) return PGS_INVALID_ARGUMENT; // PEGASUS_DATA_VERSION_MAX = 1
+    auto *p = new pgs_partition;
+    p->p.eng = &e->e;
+    p->p.app_id = app_id;
+    p->p.pidx = pidx;
+    p->p.data_version = data_version;
+    *out = p;
+    return PGS_OK;
+}
+void pgs_partition_destroy(pgs_partition *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->p.eng->device);
+    cudaStreamSynchronize(p->p.eng->stream);
+    delete p;
+}
+
+int32_t pgs_run_upload(pgs_partition *ph, int32_t level, const uint8_t *data, uint64_t data_bytes,
+                       const uint64_t *blk_off, const uint32_t *blk_size, uint32_t n_blocks,
+                       uint64_t *run_id_out)
+{
+    if (!ph || level < 0 || (n_blocks && (!data || !blk_off || !blk_size))) return PGS_INVALID_ARGUMENT;
+    Partition &p = ph->p;
+    Engine *e = p.eng;
+    if (n_blocks == 0) {
+        if (run_id_out) *run_id_out = 0;
+        return PGS_OK;
+    }
+    uint64_t prev_end = 0;
+    for (uint32_t b = 0; b < n_blocks; b++) {
+        if (blk_off[b] % kBlockAlign || blk_off[b] < prev_end || blk_off[b] + blk_size[b] > data_bytes) {
+            set_error("run upload: bad block handle %u", b);
+            return PGS_INVALID_ARGUMENT;
+        }
+        prev_end = blk_off[b] + blk_size[b];
+    }
+    PGS_CUDA(cudaSetDevice(e->device));
+    auto r = std::make_shared<Run>();
+    r->level = level;
+    r->info.level = level;
+    r->info.n_blocks = n_blocks;
+    uint64_t end = (prev_end + kBlockAlign - 1) / kBlockAlign * kBlockAlign;
+    r->info.data_bytes = end;
+    r->data_cap = end + 256;
+    PGS_CUDA(cudaMalloc(&r->d_data, r->data_cap));
+    PGS_CUDA(cudaMalloc(&r->d_blk_off, sizeof(uint64_t) * (n_blocks + 1)));
+    PGS_CUDA(cudaMalloc(&r->d_blk_size, sizeof(uint32_t) * n_blocks));
+    cudaStream_t st = e->stream;
+    PGS_CUDA(cudaMemsetAsync(r->d_data + (data_bytes < end ? data_bytes : end), 0, r->data_cap - (data_bytes < end ? data_bytes : end), st));
+    PGS_CUDA(cudaMemcpyAsync(r->d_data, data, data_bytes < end ? data_bytes : end, cudaMemcpyHostToDevice, st));
+    std::vector<uint64_t> off(blk_off, blk_off + n_blocks);
+    off.push_back(end);
+    PGS_CUDA(cudaMemcpyAsync(r->d_blk_off, off.data(), sizeof(uint64_t) * (n_blocks + 1), cudaMemcpyHostToDevice, st));
+    PGS_CUDA(cudaMemcpyAsync(r->d_blk_size, blk_size, sizeof(uint32_t) * n_blocks, cudaMemcpyHostToDevice, st));
+    PGS_CUDA(cudaStreamSynchronize(st)); // `off` and the caller's buffers may go away
+    int32_t rc = build_index(e, r.get(), blk_off, blk_size);
+    if (rc != PGS_OK) return rc;
+    r->id = e->next_run_id++;
+    r->info.run_id = r->id;
+    {
+        std::lock_guard<std::mutex> g(p.mu);
+        p.insert(r);
+    }
+    if (run_id_out) *run_id_out = r->id;
+    return PGS_OK;
+}
+
+int32_t pgs_run_drop(pgs_partition *ph, uint64_t run_id)
+{
+    Partition &p = ph->p;
+    std::lock_guard<std::mutex> g(p.mu);
+    for (size_t i = 0; i < p.runs.size(); i++)
+        if (p.runs[i]->id == run_id) {
+            cudaSetDevice(p.eng->device);
+            cudaStreamSynchronize(p.eng->stream);
+            p.runs.erase(p.runs.begin() + i);
+            return PGS_OK;
+        }
+    return PGS_NOT_FOUND;
+}
+int32_t pgs_run_info_get(pgs_partition *ph, uint64_t run_id, pgs_run_info *out)
+{
+    Partition &p = ph->p;
+    std::lock_guard<std::mutex> g(p.mu);
+    auto r = p.find(run_id);
+    if (!r) return PGS_NOT_FOUND;
+    *out = r->info;
+    return PGS_OK;
+}
+int32_t pgs_run_list(pgs_partition *ph, uint64_t *ids, uint32_t cap, uint32_t *n_out)
+{
+    Partition &p = ph->p;
+    std::lock_guard<std::mutex> g(p.mu);
+    uint32_t n = (uint32_t)p.runs.size();
+    if (n_out) *n_out = n;
+    for (uint32_t i = 0; i < n && i < cap; i++) ids[i] = p.runs[i]->id;
+    return n <= cap ? PGS_OK : PGS_INCOMPLETE;
+}
+int32_t pgs_run_download(pgs_partition *ph, uint64_t run_id, uint8_t *data, uint64_t data_cap,
+                         uint64_t *blk_off, uint32_t *blk_size, uint32_t blk_cap)
+{
+    Partition &p = ph->p;
+    std::shared_ptr<Run> r;
+    {
+        std::lock_guard<std::mutex> g(p.mu);
+        r = p.find(run_id);
+    }
+    if (!r) return PGS_NOT_FOUND;
+    if (data_cap < r->info.data_bytes || blk_cap < r->info.n_blocks) return PGS_INCOMPLETE;
+    Engine *e = p.eng;
+    PGS_CUDA(cudaSetDevice(e->device));
+    PGS_CUDA(cudaMemcpyAsync(data, r->d_data, r->info.data_bytes, cudaMemcpyDeviceToHost, e->stream));
+    PGS_CUDA(cudaMemcpyAsync(blk_off, r->d_blk_off, sizeof(uint64_t) * r->info.n_blocks, cudaMemcpyDeviceToHost, e->stream));
+    PGS_CUDA(cudaMemcpyAsync(blk_size, r->d_blk_size, sizeof(uint32_t) * r->info.n_blocks, cudaMemcpyDeviceToHost, e->stream));
+    PGS_CUDA(cudaStreamSynchronize(e->stream));
+    return PGS_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,88 @@
+// engine.h — internal C++ view of the device engine (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pegasus_b200.h"
+#include "format.h"
+
+namespace pgs {
+
+// what kernels see of one HBM-resident sorted run
+struct RunDev {
+    const uint8_t *data;      // blocks, each start 16-aligned; readable up to blk_off[nb] (+slack)
+    const uint64_t *blk_off;  // [nb+1] byte offset of block b; blk_off[nb] = 16-aligned end
+    const uint32_t *blk_size; // [nb]   exact encoded size
+    const uint32_t *blk_rec;  // [nb+1] cumulative record count
+    const uint32_t *ikey_off; // [nb+1] offsets into ikeys
+    const uint8_t *ikeys;     // last user key of every block, back to back
+    uint32_t nb;
+    uint32_t max_ukey_len;
+};
+
+struct Run {
+    uint64_t id = 0;
+    int32_t level = 0;
+    pgs_run_info info{};
+    // device allocations (owned)
+    uint8_t *d_data = nullptr;
+    uint64_t *d_blk_off = nullptr;
+    uint32_t *d_blk_size = nullptr;
+    uint32_t *d_blk_rec = nullptr;
+    uint32_t *d_ikey_off = nullptr;
+    uint8_t *d_ikeys = nullptr;
+    uint64_t data_cap = 0;
+    RunDev dev() const
+    {
+        return RunDev{d_data, d_blk_off, d_blk_size, d_blk_rec, d_ikey_off, d_ikeys, info.n_blocks, info.max_ukey_len};
+    }
+    ~Run();
+};
+
+struct Engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    pgs_engine_config cfg{};
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    std::atomic<uint64_t> launches{0};
+    std::atomic<uint64_t> next_run_id{1};
+    // reusable pinned staging + device scratch
+    std::mutex mu;
+    void *h_pinned = nullptr;
+    size_t h_pinned_cap = 0;
+    void *pinned(size_t bytes);
+    ~Engine();
+};
+
+struct Partition {
+    Engine *eng;
+    int32_t app_id, pidx;
+    uint32_t data_version;
+    std::mutex mu;
+    std::vector<std::shared_ptr<Run>> runs; // read order: L0 newest first, then L1, L2 ...
+    std::shared_ptr<Run> find(uint64_t id);
+    void insert(std::shared_ptr<Run> r);
+};
+
+void set_error(const char *fmt, ...);
+int32_t cuda_fail(cudaError_t e, const char *what);
+#define PGS_CUDA(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) return ::pgs::cuda_fail(_e, #expr);                                 \
+    } while (0)
+
+// scans an uploaded / freshly merged run's blocks on the device and fills the index + info
+int32_t build_index(Engine *e, Run *r, const uint64_t *h_blk_off, const uint32_t *h_blk_size);
+
+} // namespace pgs
+
+struct pgs_engine { pgs::Engine e; };
+struct pgs_partition { pgs::Partition p; };

@@ -1,0 +1,751 @@
+// orc_rrdb.cpp — CPU ORACLE (test infrastructure only): the rrdb operator surface of one
+// replica (pegasus_server_impl) on a semantic LSM model: memtable + sorted runs of
+// (user key, seq, type, value), newest version wins, tombstones hide.  Handlers restate
+// src/server/pegasus_server_impl.cpp:418-1549 and the helpers at :2350-2504; the write side
+// restates src/server/rocksdb_wrapper.cpp:129-219 / pegasus_write_service_impl.h:90-169.
+// Wall-clock limits of range_read_limiter (range_read_limiter.h:64-84) are not modelled: `now`
+// is an argument and no test runs 30 s.
+#include "orc_internal.h"
+
+#include <algorithm>
+#include <climits>
+#include <random>
+#include <unordered_map>
+
+namespace orc {
+
+struct View { // what a RocksDB iterator sees: newest non-deleted version of every user key
+    std::vector<std::pair<std::string, std::string>> kv;
+};
+
+struct Iter { // rocksdb::Iterator over a pinned View
+    std::shared_ptr<View> v;
+    size_t pos = 0;
+    bool ok = false;
+    bool prefix_mode = false;
+    std::string prefix;
+    bool has_upper = false;
+    std::string upper;
+    bool Valid() const { return ok; }
+    sv key() const { return v->kv[pos].first; }
+    sv value() const { return v->kv[pos].second; }
+    void check()
+    {
+        ok = pos < v->kv.size();
+        if (ok && prefix_mode && hashkey_prefix(key()) != sv(prefix)) ok = false;
+        if (ok && has_upper && key().compare(upper) >= 0) ok = false;
+    }
+    void Seek(sv target, bool prefix_same_as_start)
+    {
+        pos = std::lower_bound(v->kv.begin(), v->kv.end(), target,
+                               [](const std::pair<std::string, std::string> &a, sv b) { return sv(a.first).compare(b) < 0; }) -
+              v->kv.begin();
+        prefix_mode = prefix_same_as_start && target.size() >= 2; // InDomain
+        if (prefix_mode) prefix = std::string(hashkey_prefix(target));
+        check();
+    }
+    void SeekForPrev(sv target) // total order
+    {
+        size_t ub = std::upper_bound(v->kv.begin(), v->kv.end(), target,
+                                     [](sv b, const std::pair<std::string, std::string> &a) { return b.compare(a.first) < 0; }) -
+                    v->kv.begin();
+        prefix_mode = false;
+        if (ub == 0) { ok = false; return; }
+        pos = ub - 1;
+        ok = true;
+    }
+    void Next() { pos++; check(); }
+    void Prev()
+    {
+        if (pos == 0) { ok = false; return; }
+        pos--;
+        ok = true;
+    }
+};
+
+struct ScanContext { // pegasus_scan_context.h:33-95
+    Iter it;
+    std::string stop;
+    bool stop_inclusive;
+    int hash_key_filter_type, sort_key_filter_type;
+    std::string hash_key_filter_pattern, sort_key_filter_pattern;
+    int32_t batch_size;
+    bool no_value, validate_partition_hash, return_expire_ts, only_return_count;
+};
+
+struct Resp {
+    pgs_response view{};
+    std::vector<pgs_kv> kvs;
+    std::vector<uint32_t> hk_len;
+    std::string arena;
+    void reset(int32_t app_id, int32_t pidx)
+    {
+        view = pgs_response{};
+        view.app_id = app_id;
+        view.partition_index = pidx;
+        view.kv_count = -1;
+        view.context_id = 0;
+        kvs.clear();
+        hk_len.clear();
+        arena.clear();
+    }
+    void add(sv key, sv value, uint32_t expire_ts)
+    {
+        pgs_kv kv;
+        kv.key_off = (uint32_t)arena.size(); kv.key_len = (uint32_t)key.size();
+        arena.append(key.data(), key.size());
+        kv.value_off = (uint32_t)arena.size(); kv.value_len = (uint32_t)value.size();
+        arena.append(value.data(), value.size());
+        kv.expire_ts = expire_ts;
+        kvs.push_back(kv);
+    }
+    void seal()
+    {
+        view.n_kvs = (uint32_t)kvs.size();
+        view.kvs = kvs.data();
+        view.hk_len = hk_len.empty() ? nullptr : hk_len.data();
+        view.arena = (const uint8_t *)arena.data();
+        view.arena_len = arena.size();
+    }
+};
+
+enum RangeState { kNormal, kExpired, kFiltered, kHashInvalid };
+
+struct Limiter { // range_read_limiter.h:37-103 without the clock
+    uint32_t max_count; uint64_t max_size;
+    uint32_t count = 0; uint64_t size = 0;
+    Limiter(uint32_t c, uint64_t s) : max_count(c), max_size(s) {}
+    bool valid() const { return count < max_count && !(max_size > 0 && size >= max_size); }
+};
+
+struct Server {
+    int32_t app_id, pidx;
+    pgs_server_options opt;
+    uint32_t data_version = 1; // pegasus_server_impl_test.cpp:356-360
+    uint32_t default_ttl = 0;
+    bool validate_partition_hash = false; // server flag, env replica.split.validate_partition_hash
+    int32_t partition_version = -1;
+    std::vector<Op> ops;
+    uint64_t last_seq = 0;
+    int64_t last_flushed_decree = 0;
+    std::map<std::string, Rec> mem;
+    struct LRun { int level; Run run; };
+    std::vector<LRun> runs; // read order: L0 newest first, then L1, L2, ...
+    std::shared_ptr<View> view;
+    int64_t ctx_counter;
+    std::unordered_map<int64_t, std::unique_ptr<ScanContext>> ctx;
+
+    Server()
+    {
+        std::mt19937_64 rng(12345);
+        ctx_counter = (int64_t)(rng() % (2ull << 31)) << 32; // pegasus_scan_context.h:113-114
+    }
+    FilterParams fparams() const
+    {
+        FilterParams fp;
+        fp.enabled = true;
+        fp.validate_hash = validate_partition_hash;
+        fp.data_version = data_version;
+        fp.default_ttl = default_ttl;
+        fp.pidx = pidx;
+        fp.partition_version = partition_version;
+        fp.ops = &ops;
+        return fp;
+    }
+    void write(Rec r) { view.reset(); mem[r.ukey] = std::move(r); }
+    void flush_mem()
+    {
+        if (mem.empty()) return;
+        LRun lr{0, {}};
+        for (auto &kv : mem) lr.run.recs.push_back(kv.second);
+        mem.clear();
+        runs.insert(runs.begin(), std::move(lr));
+        view.reset();
+    }
+    void compact_runs(size_t first, size_t last /*exclusive*/, int out_level, uint32_t now, orc_compact_stats *st)
+    {
+        std::vector<const Run *> in;
+        for (size_t i = first; i < last; i++) in.push_back(&runs[i].run);
+        bool bottommost = last == runs.size();
+        Run out = compact(in, bottommost, fparams(), now, st);
+        runs.erase(runs.begin() + first, runs.begin() + last);
+        size_t pos = 0;
+        while (pos < runs.size() && runs[pos].level < out_level) pos++;
+        runs.insert(runs.begin() + pos, LRun{out_level, std::move(out)});
+        view.reset();
+    }
+    void maybe_compact(uint32_t now)
+    {
+        uint32_t trigger = opt.l0_compaction_trigger ? opt.l0_compaction_trigger : 4;
+        size_t l0 = 0;
+        while (l0 < runs.size() && runs[l0].level == 0) l0++;
+        if (l0 < trigger) return;
+        size_t last = l0;
+        while (last < runs.size() && runs[last].level == 1) last++;
+        compact_runs(0, last, 1, now, nullptr);
+    }
+    std::shared_ptr<View> get_view()
+    {
+        flush_mem(); // mirrors the product: reads see the memtable through an L0 run
+        if (view) return view;
+        std::vector<const Rec *> all;
+        for (auto &lr : runs)
+            for (auto &r : lr.run.recs) all.push_back(&r);
+        std::stable_sort(all.begin(), all.end(), [](const Rec *a, const Rec *b) {
+            return cmp_internal(a->ukey, a->seq, a->type, b->ukey, b->seq, b->type) < 0;
+        });
+        auto v = std::make_shared<View>();
+        const Rec *prev = nullptr;
+        for (const Rec *r : all) {
+            if (prev && prev->ukey == r->ukey) continue;
+            prev = r;
+            if (r->type == PGS_TYPE_VALUE) v->kv.emplace_back(r->ukey, r->value);
+        }
+        view = v;
+        return v;
+    }
+    bool db_get(sv key, std::string *value)
+    {
+        auto v = get_view();
+        auto it = std::lower_bound(v->kv.begin(), v->kv.end(), key,
+                                   [](const std::pair<std::string, std::string> &a, sv b) { return sv(a.first).compare(b) < 0; });
+        if (it == v->kv.end() || sv(it->first) != key) return false;
+        *value = it->second;
+        return true;
+    }
+    sv user_data(sv raw) const { return raw.substr(user_data_offset(data_version)); }
+
+    // validate_key_value_for_scan: pegasus_server_impl.cpp:2382-2432
+    RangeState validate_for_scan(sv key, sv value, int hft, sv hpat, int sft, sv spat, uint32_t now,
+                                 bool request_validate_hash) const
+    {
+        if (ts_expired(now, extract_expire_ts(data_version, value))) return kExpired;
+        if (request_validate_hash && validate_partition_hash) {
+            if (partition_version < 0 || pidx > partition_version || !check_key_hash(key, pidx, partition_version))
+                return kHashInvalid;
+        }
+        if (hft != PGS_FT_NO_FILTER || sft != PGS_FT_NO_FILTER) {
+            sv hk, sk;
+            restore_key(key, hk, sk);
+            if (hft != PGS_FT_NO_FILTER && !validate_filter(hft, hpat, hk)) return kFiltered;
+            if (sft != PGS_FT_NO_FILTER && !validate_filter(sft, spat, sk)) return kFiltered;
+        }
+        return kNormal;
+    }
+    // append_key_value: :2434-2460
+    void append_kv(Resp &r, sv key, sv value, bool no_value, bool request_expire_ts) const
+    {
+        uint32_t ets = request_expire_ts ? extract_expire_ts(data_version, value) : 0;
+        r.add(key, no_value ? sv() : user_data(value), ets);
+    }
+    // append_key_value_for_multi_get: :2462-2504
+    RangeState append_for_multi_get(Resp &r, sv key, sv value, int sft, sv spat, uint32_t now, bool no_value) const
+    {
+        if (ts_expired(now, extract_expire_ts(data_version, value))) return kExpired;
+        sv hk, sk;
+        restore_key(key, hk, sk);
+        if (sft != PGS_FT_NO_FILTER && !validate_filter(sft, spat, sk)) return kFiltered;
+        r.add(sk, no_value ? sv() : user_data(value), 0);
+        return kNormal;
+    }
+};
+
+static inline sv bsv(const pgs_blob &b) { return sv((const char *)b.data, b.len); }
+static inline bool filter_type_supported(int t) { return t >= PGS_FT_NO_FILTER && t <= PGS_FT_MATCH_POSTFIX; }
+
+// on_get: pegasus_server_impl.cpp:418-494
+static int32_t on_get(Server &s, sv key, uint32_t now, Resp &r)
+{
+    r.reset(s.app_id, s.pidx);
+    std::string value;
+    int32_t st = s.db_get(key, &value) ? PGS_OK : PGS_NOT_FOUND;
+    if (st == PGS_OK && ts_expired(now, extract_expire_ts(s.data_version, value))) {
+        st = PGS_NOT_FOUND;
+        r.view.expire_count = 1;
+    }
+    r.view.error = st;
+    if (st == PGS_OK) r.add(sv(), s.user_data(value), 0);
+    r.seal();
+    return st;
+}
+
+// on_ttl: :1088-1149
+static int32_t on_ttl(Server &s, sv key, uint32_t now, Resp &r)
+{
+    r.reset(s.app_id, s.pidx);
+    std::string value;
+    int32_t st = s.db_get(key, &value) ? PGS_OK : PGS_NOT_FOUND;
+    uint32_t expire_ts = 0;
+    if (st == PGS_OK) {
+        expire_ts = extract_expire_ts(s.data_version, value);
+        if (ts_expired(now, expire_ts)) { st = PGS_NOT_FOUND; r.view.expire_count = 1; }
+    }
+    r.view.error = st;
+    if (st == PGS_OK) r.view.ttl_seconds = expire_ts > 0 ? (int32_t)(expire_ts - now) : -1;
+    r.seal();
+    return st;
+}
+
+// on_multi_get: :496-904
+static int32_t on_multi_get(Server &s, const pgs_multi_get_request &q, uint32_t now, Resp &r)
+{
+    r.reset(s.app_id, s.pidx);
+    if (!filter_type_supported(q.sort_key_filter_type)) {
+        r.view.error = PGS_INVALID_ARGUMENT;
+        r.seal();
+        return r.view.error;
+    }
+    uint32_t cfg_count = s.opt.rocksdb_multi_get_max_iteration_count ? s.opt.rocksdb_multi_get_max_iteration_count : 3000;
+    uint64_t cfg_size = s.opt.rocksdb_multi_get_max_iteration_size ? s.opt.rocksdb_multi_get_max_iteration_size : 30ull << 20;
+    uint32_t max_kv_count = cfg_count, max_iteration_count = cfg_count;
+    if (q.max_kv_count > 0 && (uint32_t)q.max_kv_count < max_kv_count) max_kv_count = q.max_kv_count;
+    int32_t max_kv_size = q.max_kv_size > 0 ? q.max_kv_size : INT_MAX;
+    int32_t max_iteration_size_config = cfg_size > 0 ? (int32_t)std::min<uint64_t>(cfg_size, INT_MAX) : INT_MAX;
+    int32_t max_iteration_size = std::min(max_kv_size, max_iteration_size_config);
+    int32_t count = 0;
+    int64_t size = 0;
+    sv hash_key = bsv(q.hash_key);
+
+    if (q.n_sort_keys == 0) {
+        std::string start = generate_key(hash_key, bsv(q.start_sortkey));
+        bool start_inclusive = q.start_inclusive;
+        std::string stop;
+        bool stop_inclusive;
+        if (q.stop_sortkey.len == 0) { stop = next_blob(hash_key); stop_inclusive = false; }
+        else { stop = generate_key(hash_key, bsv(q.stop_sortkey)); stop_inclusive = q.stop_inclusive; }
+        if (q.sort_key_filter_type == PGS_FT_MATCH_PREFIX && q.sort_key_filter_pattern.len > 0) {
+            std::string ps = generate_key(hash_key, bsv(q.sort_key_filter_pattern));
+            std::string pe = next_blob(hash_key, bsv(q.sort_key_filter_pattern));
+            if (sv(ps).compare(start) > 0) { start = ps; start_inclusive = true; }
+            if (sv(pe).compare(stop) <= 0) { stop = pe; stop_inclusive = false; }
+        }
+        int c = sv(start).compare(stop);
+        if (c > 0 || (c == 0 && (!start_inclusive || !stop_inclusive))) {
+            r.view.error = PGS_OK;
+            r.seal();
+            return PGS_OK;
+        }
+        Iter it;
+        it.v = s.get_view();
+        bool complete = false;
+        Limiter lim(max_iteration_count, (uint64_t)max_iteration_size);
+        bool prefix = s.opt.prefix_filter;
+        if (!q.reverse) {
+            it.Seek(start, prefix);
+            bool first_exclusive = !start_inclusive;
+            while ((uint32_t)count < max_kv_count && lim.valid() && it.Valid()) {
+                int c2 = it.key().compare(stop);
+                if (c2 > 0 || (c2 == 0 && !stop_inclusive)) { complete = true; break; }
+                if (first_exclusive) {
+                    first_exclusive = false;
+                    if (it.key().compare(start) == 0) { it.Next(); continue; }
+                }
+                lim.count++;
+                size_t before = r.kvs.size();
+                RangeState st = s.append_for_multi_get(r, it.key(), it.value(), q.sort_key_filter_type,
+                                                       bsv(q.sort_key_filter_pattern), now, q.no_value);
+                if (st == kNormal) {
+                    count++;
+                    uint64_t kv_size = r.kvs[before].key_len + r.kvs[before].value_len;
+                    size += kv_size;
+                    lim.size += kv_size;
+                } else if (st == kExpired) r.view.expire_count++;
+                else if (st == kFiltered) r.view.filter_count++;
+                if (c2 == 0) { complete = true; break; }
+                it.Next();
+            }
+        } else {
+            it.SeekForPrev(stop);
+            bool first_exclusive = !stop_inclusive;
+            Resp rev;
+            rev.reset(0, 0);
+            while ((uint32_t)count < max_kv_count && lim.valid() && it.Valid()) {
+                int c2 = it.key().compare(start);
+                if (c2 < 0 || (c2 == 0 && !start_inclusive)) { complete = true; break; }
+                if (first_exclusive) {
+                    first_exclusive = false;
+                    if (it.key().compare(stop) == 0) { it.Prev(); continue; }
+                }
+                lim.count++;
+                size_t before = rev.kvs.size();
+                RangeState st = s.append_for_multi_get(rev, it.key(), it.value(), q.sort_key_filter_type,
+                                                       bsv(q.sort_key_filter_pattern), now, q.no_value);
+                if (st == kNormal) {
+                    count++;
+                    uint64_t kv_size = rev.kvs[before].key_len + rev.kvs[before].value_len;
+                    size += kv_size;
+                    lim.size += kv_size;
+                } else if (st == kExpired) r.view.expire_count++;
+                else if (st == kFiltered) r.view.filter_count++;
+                if (c2 == 0) { complete = true; break; }
+                it.Prev();
+            }
+            for (size_t i = rev.kvs.size(); i-- > 0;) {
+                const pgs_kv &kv = rev.kvs[i];
+                r.add(sv(rev.arena).substr(kv.key_off, kv.key_len), sv(rev.arena).substr(kv.value_off, kv.value_len), 0);
+            }
+        }
+        r.view.iteration_count = lim.count;
+        r.view.error = PGS_OK;
+        if (it.Valid() && !complete) r.view.error = PGS_INCOMPLETE;
+    } else {
+        bool exceed_limit = false;
+        for (uint32_t i = 0; i < q.n_sort_keys; i++) {
+            std::string key = generate_key(hash_key, bsv(q.sort_keys[i]));
+            std::string value;
+            if (!s.db_get(key, &value)) continue;
+            if (ts_expired(now, extract_expire_ts(s.data_version, value))) { r.view.expire_count++; continue; }
+            if (count >= (int32_t)max_kv_count || size >= max_kv_size) { exceed_limit = true; break; }
+            sv ud = q.no_value ? sv() : s.user_data(value);
+            r.add(bsv(q.sort_keys[i]), ud, 0);
+            count++;
+            size += q.sort_keys[i].len + ud.size();
+        }
+        r.view.error = exceed_limit ? PGS_INCOMPLETE : PGS_OK;
+    }
+    r.seal();
+    return r.view.error;
+}
+
+// on_batch_get: :906-1016
+static int32_t on_batch_get(Server &s, const pgs_full_key *keys, uint32_t n, uint32_t now, Resp &r)
+{
+    r.reset(s.app_id, s.pidx);
+    if (n == 0) { r.view.error = PGS_INVALID_ARGUMENT; r.seal(); return r.view.error; }
+    for (uint32_t i = 0; i < n; i++) {
+        std::string key = generate_key(bsv(keys[i].hash_key), bsv(keys[i].sort_key));
+        std::string value;
+        if (!s.db_get(key, &value)) continue;
+        if (ts_expired(now, extract_expire_ts(s.data_version, value))) { r.view.expire_count++; continue; }
+        std::string hs(bsv(keys[i].hash_key));
+        hs += bsv(keys[i].sort_key);
+        r.add(hs, s.user_data(value), 0);
+        r.hk_len.push_back(keys[i].hash_key.len);
+    }
+    r.view.error = PGS_OK;
+    r.seal();
+    return PGS_OK;
+}
+
+// on_sortkey_count: :1018-1086
+static int32_t on_sortkey_count(Server &s, sv hash_key, uint32_t now, Resp &r)
+{
+    r.reset(s.app_id, s.pidx);
+    std::string start = generate_key(hash_key, sv()), stop = next_blob(hash_key);
+    Iter it;
+    it.v = s.get_view();
+    it.has_upper = true;
+    it.upper = stop;
+    it.Seek(start, s.opt.prefix_filter);
+    int64_t cnt = 0;
+    while (it.Valid()) {
+        r.view.iteration_count++;
+        if (ts_expired(now, extract_expire_ts(s.data_version, it.value()))) r.view.expire_count++;
+        else cnt++;
+        it.Next();
+    }
+    r.view.count = cnt;
+    r.view.error = PGS_OK;
+    r.seal();
+    return PGS_OK;
+}
+
+// the shared batch loop of on_get_scanner (:1266-1320) and on_scan (:1444-1490)
+static void scan_loop(Server &s, Iter &it, sv start, sv stop, bool stop_inclusive, bool &first_exclusive,
+                      uint32_t batch_count, uint32_t limiter_max, int hft, sv hpat, int sft, sv spat,
+                      bool no_value, bool validate_hash, bool return_expire_ts, bool only_return_count,
+                      uint32_t now, Resp &r, bool &complete, int32_t &count)
+{
+    Limiter lim(limiter_max, 0);
+    while ((uint32_t)count < batch_count && lim.valid() && it.Valid()) {
+        int c = it.key().compare(stop);
+        if (c > 0 || (c == 0 && !stop_inclusive)) { complete = true; break; }
+        if (first_exclusive) {
+            first_exclusive = false;
+            if (it.key().compare(start) == 0) { it.Next(); continue; }
+        }
+        lim.count++;
+        RangeState st = s.validate_for_scan(it.key(), it.value(), hft, hpat, sft, spat, now, validate_hash);
+        if (st == kNormal) {
+            count++;
+            if (!only_return_count) s.append_kv(r, it.key(), it.value(), no_value, return_expire_ts);
+        } else if (st == kExpired) r.view.expire_count++;
+        else if (st == kFiltered) r.view.filter_count++;
+        if (c == 0) { complete = true; break; }
+        it.Next();
+    }
+    r.view.iteration_count = lim.count;
+}
+
+// on_get_scanner: :1151-1397
+static int32_t on_get_scanner(Server &s, const pgs_get_scanner_request &q, uint32_t now, Resp &r)
+{
+    r.reset(s.app_id, s.pidx);
+    if (!filter_type_supported(q.hash_key_filter_type) || !filter_type_supported(q.sort_key_filter_type)) {
+        r.view.error = PGS_INVALID_ARGUMENT;
+        r.seal();
+        return r.view.error;
+    }
+    bool prefix_same_as_start = s.opt.prefix_filter;
+    if (s.opt.prefix_filter) {
+        sv hk, sk;
+        sv sk_in = bsv(q.start_key);
+        if (sk_in.size() >= 2) restore_key(sk_in, hk, sk);
+        if (hk.empty() || q.full_scan) prefix_same_as_start = false; // total_order_seek
+    }
+    bool start_inclusive = q.start_inclusive, stop_inclusive = q.stop_inclusive;
+    std::string start(bsv(q.start_key)), stop(bsv(q.stop_key));
+    if (q.hash_key_filter_type == PGS_FT_MATCH_PREFIX && q.hash_key_filter_pattern.len > 0) {
+        std::string ps = generate_key(bsv(q.hash_key_filter_pattern), sv());
+        if (sv(ps).compare(start) > 0) { start = ps; start_inclusive = true; }
+    }
+    int c = sv(start).compare(stop);
+    if (c > 0 || (c == 0 && (!start_inclusive || !stop_inclusive))) {
+        r.view.error = PGS_OK;
+        r.seal();
+        return PGS_OK;
+    }
+    Iter it;
+    it.v = s.get_view();
+    it.Seek(start, prefix_same_as_start);
+    bool complete = false, first_exclusive = !start_inclusive;
+    int32_t count = 0;
+    uint32_t cfg = s.opt.rocksdb_max_iteration_count ? s.opt.rocksdb_max_iteration_count : 1000;
+    uint32_t batch_count = cfg;
+    if (q.batch_size > 0 && (uint32_t)q.batch_size < batch_count) batch_count = q.batch_size;
+    scan_loop(s, it, start, stop, stop_inclusive, first_exclusive, batch_count, cfg, q.hash_key_filter_type,
+              bsv(q.hash_key_filter_pattern), q.sort_key_filter_type, bsv(q.sort_key_filter_pattern), q.no_value,
+              q.validate_partition_hash, q.return_expire_ts, q.only_return_count, now, r, complete, count);
+    if (q.only_return_count) r.view.kv_count = count;
+    r.view.error = PGS_OK;
+    if (it.Valid() && !complete) {
+        auto ctx = std::make_unique<ScanContext>();
+        ctx->it = it;
+        ctx->stop = stop;
+        ctx->stop_inclusive = q.stop_inclusive; // NB: the request's flag, as the reference (:1368)
+        ctx->hash_key_filter_type = q.hash_key_filter_type;
+        ctx->hash_key_filter_pattern = std::string(bsv(q.hash_key_filter_pattern));
+        ctx->sort_key_filter_type = q.sort_key_filter_type;
+        ctx->sort_key_filter_pattern = std::string(bsv(q.sort_key_filter_pattern));
+        ctx->batch_size = (int32_t)batch_count;
+        ctx->no_value = q.no_value;
+        ctx->validate_partition_hash = q.validate_partition_hash;
+        ctx->return_expire_ts = q.return_expire_ts;
+        ctx->only_return_count = q.only_return_count;
+        int64_t handle = s.ctx_counter++;
+        s.ctx[handle] = std::move(ctx);
+        r.view.context_id = handle;
+    } else {
+        r.view.context_id = -1; // SCAN_CONTEXT_ID_COMPLETED
+    }
+    r.seal();
+    return r.view.error;
+}
+
+// on_scan: :1399-1547
+static int32_t on_scan(Server &s, int64_t context_id, uint32_t now, Resp &r)
+{
+    r.reset(s.app_id, s.pidx);
+    auto f = s.ctx.find(context_id);
+    if (f == s.ctx.end()) { r.view.error = PGS_NOT_FOUND; r.seal(); return r.view.error; }
+    std::unique_ptr<ScanContext> ctx = std::move(f->second);
+    s.ctx.erase(f);
+    bool complete = false, first_exclusive = false;
+    int32_t count = 0;
+    uint32_t cfg = s.opt.rocksdb_max_iteration_count ? s.opt.rocksdb_max_iteration_count : 1000;
+    uint32_t batch_count = cfg;
+    if (ctx->batch_size > 0 && (uint32_t)ctx->batch_size < batch_count) batch_count = ctx->batch_size;
+    scan_loop(s, ctx->it, sv(), ctx->stop, ctx->stop_inclusive, first_exclusive, batch_count, batch_count,
+              ctx->hash_key_filter_type, ctx->hash_key_filter_pattern, ctx->sort_key_filter_type,
+              ctx->sort_key_filter_pattern, ctx->no_value, ctx->validate_partition_hash, ctx->return_expire_ts,
+              ctx->only_return_count, now, r, complete, count);
+    if (ctx->only_return_count) r.view.kv_count = count;
+    r.view.error = PGS_OK;
+    if (ctx->it.Valid() && !complete) {
+        int64_t handle = s.ctx_counter++;
+        s.ctx[handle] = std::move(ctx);
+        r.view.context_id = handle;
+    } else {
+        r.view.context_id = -1;
+    }
+    r.seal();
+    return r.view.error;
+}
+
+static void parse_envs(const char *envs, uint32_t n, std::vector<std::pair<std::string, std::string>> &out)
+{
+    const char *p = envs;
+    for (uint32_t i = 0; i < n; i++) {
+        std::string k(p);
+        p += k.size() + 1;
+        std::string v(p);
+        p += v.size() + 1;
+        out.emplace_back(std::move(k), std::move(v));
+    }
+}
+
+} // namespace orc
+
+using namespace orc;
+struct orc_server { Server s; };
+static inline Resp &R(pgs_response_buf *r) { return *reinterpret_cast<Resp *>(r); }
+static inline sv bsv2(pgs_blob b) { return sv((const char *)b.data, b.len); }
+
+extern "C" {
+
+pgs_response_buf *orc_response_new(void) { return reinterpret_cast<pgs_response_buf *>(new Resp); }
+void orc_response_free(pgs_response_buf *r) { delete reinterpret_cast<Resp *>(r); }
+const pgs_response *orc_response_view(pgs_response_buf *r) { return &R(r).view; }
+
+int32_t orc_rrdb_update_app_envs(orc_server *h, const char *envs, uint32_t n_envs, uint32_t now)
+{
+    Server &s = h->s;
+    std::vector<std::pair<std::string, std::string>> kv;
+    parse_envs(envs, n_envs, kv);
+    for (auto &e : kv) {
+        if (e.first == "default_ttl") { // pegasus_server_impl.cpp:2814-2826
+            s.default_ttl = (uint32_t)strtoul(e.second.c_str(), nullptr, 10);
+        } else if (e.first == "replica.split.validate_partition_hash") { // :2966-2983
+            s.validate_partition_hash = e.second == "true";
+        } else if (e.first == "user_specified_compaction") { // :2985-3001
+            s.ops = e.second.empty() ? std::vector<Op>() : ops_from_json(e.second, s.data_version);
+        }
+    }
+    (void)now;
+    return PGS_OK;
+}
+
+orc_server *orc_rrdb_start(int32_t app_id, int32_t pidx, const pgs_server_options *opt,
+                           const char *envs, uint32_t n_envs)
+{
+    auto *h = new orc_server;
+    h->s.app_id = app_id;
+    h->s.pidx = pidx;
+    h->s.opt = opt ? *opt : pgs_server_options{};
+    if (!opt) h->s.opt.prefix_filter = 1;
+    if (!h->s.opt.cluster_id) h->s.opt.cluster_id = 1;
+    if (envs && n_envs) orc_rrdb_update_app_envs(h, envs, n_envs, 0);
+    return h;
+}
+void orc_rrdb_stop(orc_server *s) { delete s; }
+void orc_rrdb_set_partition_version(orc_server *s, int32_t pv) { s->s.partition_version = pv; }
+
+int32_t orc_rrdb_get(orc_server *s, pgs_blob key, uint32_t now, pgs_response_buf *r) { return on_get(s->s, bsv2(key), now, R(r)); }
+int32_t orc_rrdb_ttl(orc_server *s, pgs_blob key, uint32_t now, pgs_response_buf *r) { return on_ttl(s->s, bsv2(key), now, R(r)); }
+int32_t orc_rrdb_multi_get(orc_server *s, const pgs_multi_get_request *q, uint32_t now, pgs_response_buf *r)
+{
+    return on_multi_get(s->s, *q, now, R(r));
+}
+int32_t orc_rrdb_batch_get(orc_server *s, const pgs_full_key *keys, uint32_t n, uint32_t now, pgs_response_buf *r)
+{
+    return on_batch_get(s->s, keys, n, now, R(r));
+}
+int32_t orc_rrdb_sortkey_count(orc_server *s, pgs_blob hk, uint32_t now, pgs_response_buf *r)
+{
+    return on_sortkey_count(s->s, bsv2(hk), now, R(r));
+}
+int32_t orc_rrdb_get_scanner(orc_server *s, const pgs_get_scanner_request *q, uint32_t now, pgs_response_buf *r)
+{
+    return on_get_scanner(s->s, *q, now, R(r));
+}
+int32_t orc_rrdb_scan(orc_server *s, int64_t context_id, uint32_t now, pgs_response_buf *r)
+{
+    return on_scan(s->s, context_id, now, R(r));
+}
+void orc_rrdb_clear_scanner(orc_server *s, int64_t context_id) { s->s.ctx.erase(context_id); }
+
+// write_batch_put_ctx: rocksdb_wrapper.cpp:129-183 (local write, no timetag verification)
+static void put_one(Server &s, sv raw_key, sv user_value, uint32_t expire_ts, uint64_t timestamp_us, uint32_t now)
+{
+    uint64_t timetag = timestamp_us << 8u | (uint64_t)(s.opt.cluster_id << 1u);
+    if (s.default_ttl != 0 && expire_ts == 0) expire_ts = now + s.default_ttl; // db_expire_ts :280-288
+    Rec r;
+    r.ukey = std::string(raw_key);
+    r.seq = ++s.last_seq;
+    r.type = PGS_TYPE_VALUE;
+    r.value = generate_value(s.data_version, expire_ts, timetag, user_value);
+    s.write(std::move(r));
+}
+static void del_one(Server &s, sv raw_key)
+{
+    Rec r;
+    r.ukey = std::string(raw_key);
+    r.seq = ++s.last_seq;
+    r.type = PGS_TYPE_DELETION;
+    s.write(std::move(r));
+}
+
+int32_t orc_rrdb_put(orc_server *h, pgs_blob key, pgs_blob value, uint32_t expire_ts, int64_t decree,
+                     uint64_t timestamp_us, uint32_t now)
+{
+    put_one(h->s, bsv2(key), bsv2(value), expire_ts, timestamp_us, now);
+    h->s.last_flushed_decree = decree;
+    return PGS_OK;
+}
+int32_t orc_rrdb_remove(orc_server *h, pgs_blob key, int64_t decree)
+{
+    del_one(h->s, bsv2(key));
+    h->s.last_flushed_decree = decree;
+    return PGS_OK;
+}
+int32_t orc_rrdb_multi_put(orc_server *h, pgs_blob hash_key, const pgs_blob *sort_keys, const pgs_blob *values,
+                           uint32_t n, uint32_t expire_ts, int64_t decree, uint64_t timestamp_us, uint32_t now)
+{
+    Server &s = h->s;
+    s.last_flushed_decree = decree;
+    if (n == 0) { // pegasus_write_service_impl.h:112-119: empty_put + kInvalidArgument
+        put_one(s, sv(), sv(), 0, timestamp_us, 0);
+        return PGS_INVALID_ARGUMENT;
+    }
+    for (uint32_t i = 0; i < n; i++)
+        put_one(s, generate_key(bsv2(hash_key), bsv2(sort_keys[i])), bsv2(values[i]), expire_ts, timestamp_us, now);
+    return PGS_OK;
+}
+int32_t orc_rrdb_multi_remove(orc_server *h, pgs_blob hash_key, const pgs_blob *sort_keys, uint32_t n,
+                              int64_t decree, int64_t *count)
+{
+    Server &s = h->s;
+    s.last_flushed_decree = decree;
+    if (count) *count = 0;
+    if (n == 0) {
+        put_one(s, sv(), sv(), 0, 0, 0);
+        return PGS_INVALID_ARGUMENT;
+    }
+    for (uint32_t i = 0; i < n; i++) del_one(s, generate_key(bsv2(hash_key), bsv2(sort_keys[i])));
+    if (count) *count = n;
+    return PGS_OK;
+}
+int32_t orc_rrdb_flush(orc_server *h, uint32_t now)
+{
+    h->s.flush_mem();
+    h->s.maybe_compact(now);
+    return PGS_OK;
+}
+int32_t orc_rrdb_manual_compact(orc_server *h, uint32_t now, orc_compact_stats *st)
+{
+    Server &s = h->s;
+    s.flush_mem();
+    orc_compact_stats local{};
+    if (!s.runs.empty()) {
+        int level = 1;
+        for (auto &lr : s.runs) level = std::max(level, lr.level);
+        s.compact_runs(0, s.runs.size(), level, now, &local);
+    }
+    if (st) *st = local;
+    return PGS_OK;
+}
+int64_t orc_rrdb_last_flushed_decree(orc_server *h) { return h->s.last_flushed_decree; }
+uint32_t orc_rrdb_run_count(orc_server *h) { return (uint32_t)h->s.runs.size(); }
+orc_run *orc_rrdb_dump(orc_server *h)
+{
+    Server &s = h->s;
+    s.flush_mem();
+    std::vector<const Run *> in;
+    for (auto &lr : s.runs) in.push_back(&lr.run);
+    FilterParams nofilter;
+    auto *out = new orc_run;
+    out->run = compact(in, false, nofilter, 0, nullptr);
+    return out;
+}
+
+} // extern "C"
