@@ -184,6 +184,14 @@ PGS_API int32_t pgs_compact(pgs_partition *p, const uint64_t *run_ids, uint32_t 
                             int32_t out_level, int32_t bottommost, const pgs_filter_params *fp,
                             uint32_t now, pgs_compact_result *out);
 
+/* Same with flags.  KEEP_INPUTS leaves the input runs installed, DISCARD_OUTPUT does not install
+ * the merged run (its buffers return to the pool): together they let a harness repeat one job. */
+#define PGS_COMPACT_KEEP_INPUTS 1u
+#define PGS_COMPACT_DISCARD_OUTPUT 2u
+PGS_API int32_t pgs_compact_ex(pgs_partition *p, const uint64_t *run_ids, uint32_t k,
+                               int32_t out_level, int32_t bottommost, const pgs_filter_params *fp,
+                               uint32_t now, uint32_t flags, pgs_compact_result *out);
+
 /* Parse the JSON of the `user_specified_compaction` env (compaction_operation.cpp:162-186) into
  * the binary ops table.  Invalid JSON / rules yield an empty table like the reference.  Returns
  * bytes written (<= cap) or a negative status. */

@@ -168,6 +168,8 @@ def lib() -> C.CDLL:
     L.pgs_run_download.argtypes = [vp, C.c_uint64, vp, C.c_uint64, vp, vp, C.c_uint32]
     L.pgs_compact.argtypes = [vp, u64p, C.c_uint32, C.c_int32, C.c_int32, C.POINTER(FilterParams), C.c_uint32,
                               C.POINTER(CompactResult)]
+    L.pgs_compact_ex.argtypes = [vp, u64p, C.c_uint32, C.c_int32, C.c_int32, C.POINTER(FilterParams), C.c_uint32,
+                                 C.c_uint32, C.POINTER(CompactResult)]
     L.pgs_compaction_ops_parse.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, vp, C.c_uint32, u32p]
     L.pgs_compaction_ops_parse.restype = C.c_int64
     L.pgs_generate_key.argtypes = [vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32]
@@ -419,7 +421,7 @@ class Partition:
 
     def compact(self, run_ids, out_level: int = 1, bottommost: int = -1, now: int = 0, enabled: bool = True,
                 default_ttl: int = 0, validate_hash: bool = False, pidx: int = 0, partition_version: int = -1,
-                ops: np.ndarray | None = None, data_version: int = 1) -> CompactResult:
+                ops: np.ndarray | None = None, data_version: int = 1, flags: int = 0) -> CompactResult:
         ids = np.array(list(run_ids), np.uint64)
         fp = FilterParams()
         fp.enabled = 1 if enabled else 0
@@ -433,8 +435,8 @@ class Partition:
             fp.ops = self._ops_keepalive.ctypes.data_as(u8p)
             fp.ops_len = self._ops_keepalive.shape[0]
         res = CompactResult()
-        _check(lib().pgs_compact(self.h, ids.ctypes.data_as(u64p), ids.shape[0], out_level, bottommost, C.byref(fp),
-                                 now, C.byref(res)), "compact")
+        _check(lib().pgs_compact_ex(self.h, ids.ctypes.data_as(u64p), ids.shape[0], out_level, bottommost,
+                                    C.byref(fp), now, flags, C.byref(res)), "compact")
         return res
 
     def get_batch(self, keys: np.ndarray, key_off: np.ndarray, now: int, arena_cap: int | None = None):

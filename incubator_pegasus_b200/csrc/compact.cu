@@ -844,6 +844,13 @@ extern "C" int32_t pgs_compact(pgs_partition *ph, const uint64_t *run_ids, uint3
                                int32_t bottommost, const pgs_filter_params *fp, uint32_t now,
                                pgs_compact_result *out)
 {
+    return pgs_compact_ex(ph, run_ids, k, out_level, bottommost, fp, now, 0, out);
+}
+
+extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, uint32_t k, int32_t out_level,
+                                  int32_t bottommost, const pgs_filter_params *fp, uint32_t now, uint32_t flags,
+                                  pgs_compact_result *out)
+{
     if (!ph || !run_ids || k == 0 || out_level < 0) return PGS_INVALID_ARGUMENT;
     Partition &part = ph->p;
     Engine *e = part.eng;
@@ -958,20 +965,23 @@ extern "C" int32_t pgs_compact(pgs_partition *ph, const uint64_t *run_ids, uint3
     MergeStats *d_stats = nullptr;
     uint8_t *d_ops = nullptr;
     auto cleanup = [&]() {
-        cudaFree(d_split_pos); cudaFree(d_split_ref); cudaFree(d_ticket); cudaFree(d_agg); cudaFree(d_stats); cudaFree(d_ops);
+        cudaFreeAsync(d_split_pos, st); cudaFreeAsync(d_split_ref, st); cudaFreeAsync(d_ticket, st);
+        cudaFreeAsync(d_agg, st); cudaFreeAsync(d_stats, st); cudaFreeAsync(d_ops, st);
+        d_split_pos = d_split_ref = d_ticket = nullptr; d_agg = nullptr; d_stats = nullptr; d_ops = nullptr;
     };
+    outr->pool_stream = st;
 #define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr); } } while (0)
-    CK(cudaMalloc(&outr->d_data, outr->data_cap));
-    CK(cudaMalloc(&outr->d_blk_off, sizeof(uint64_t) * (blk_cap + 1)));
-    CK(cudaMalloc(&outr->d_blk_size, sizeof(uint32_t) * (blk_cap + 1)));
-    CK(cudaMalloc(&outr->d_blk_rec, sizeof(uint32_t) * (blk_cap + 1)));
-    CK(cudaMalloc(&outr->d_ikey_off, sizeof(uint32_t) * (blk_cap + 1)));
-    CK(cudaMalloc(&outr->d_ikeys, ikey_cap));
-    CK(cudaMalloc(&d_split_pos, sizeof(uint32_t) * (Q + 1) * k));
-    CK(cudaMalloc(&d_split_ref, sizeof(uint32_t) * (Q + 1)));
-    CK(cudaMalloc(&d_ticket, 256));
-    CK(cudaMalloc(&d_agg, sizeof(TileAgg) * 2 * Q));
-    CK(cudaMalloc(&d_stats, sizeof(MergeStats)));
+    CK(cudaMallocAsync(&outr->d_data, outr->data_cap, st));
+    CK(cudaMallocAsync(&outr->d_blk_off, sizeof(uint64_t) * (blk_cap + 1), st));
+    CK(cudaMallocAsync(&outr->d_blk_size, sizeof(uint32_t) * (blk_cap + 1), st));
+    CK(cudaMallocAsync(&outr->d_blk_rec, sizeof(uint32_t) * (blk_cap + 1), st));
+    CK(cudaMallocAsync(&outr->d_ikey_off, sizeof(uint32_t) * (blk_cap + 1), st));
+    CK(cudaMallocAsync(&outr->d_ikeys, ikey_cap, st));
+    CK(cudaMallocAsync(&d_split_pos, sizeof(uint32_t) * (Q + 1) * k, st));
+    CK(cudaMallocAsync(&d_split_ref, sizeof(uint32_t) * (Q + 1), st));
+    CK(cudaMallocAsync(&d_ticket, 256, st));
+    CK(cudaMallocAsync(&d_agg, sizeof(TileAgg) * 2 * Q, st));
+    CK(cudaMallocAsync(&d_stats, sizeof(MergeStats), st));
     CK(cudaMemsetAsync(d_split_pos, 0xFF, sizeof(uint32_t) * (Q + 1) * k, st));
     CK(cudaMemsetAsync(d_split_ref, 0xFF, sizeof(uint32_t) * (Q + 1), st));
     CK(cudaMemsetAsync(d_ticket, 0, 256, st));
@@ -981,7 +991,7 @@ extern "C" int32_t pgs_compact(pgs_partition *ph, const uint64_t *run_ids, uint3
     hs.error_tile = 0xFFFFFFFFu;
     CK(cudaMemcpyAsync(d_stats, &hs, sizeof hs, cudaMemcpyHostToDevice, st));
     if (!ops_host.empty()) {
-        CK(cudaMalloc(&d_ops, ops_host.size()));
+        CK(cudaMallocAsync(&d_ops, ops_host.size(), st));
         CK(cudaMemcpyAsync(d_ops, ops_host.data(), ops_host.size(), cudaMemcpyHostToDevice, st));
         P.ops = d_ops;
     }
@@ -1065,8 +1075,9 @@ extern "C" int32_t pgs_compact(pgs_partition *ph, const uint64_t *run_ids, uint3
     outr->info.largest_seq = hs.max_seq;
     {
         std::lock_guard<std::mutex> g(part.mu);
-        for (auto &r : in) part.runs.erase(std::find(part.runs.begin(), part.runs.end(), r));
-        if (fin.blocks > 0) {
+        if (!(flags & PGS_COMPACT_KEEP_INPUTS))
+            for (auto &r : in) part.runs.erase(std::find(part.runs.begin(), part.runs.end(), r));
+        if (fin.blocks > 0 && !(flags & PGS_COMPACT_DISCARD_OUTPUT)) {
             outr->id = e->next_run_id++;
             outr->info.run_id = outr->id;
             part.insert(outr);

@@ -29,6 +29,15 @@ int32_t cuda_fail(cudaError_t e, const char *what)
 
 Run::~Run()
 {
+    if (pool_stream) { // stream-ordered pool: the bytes go back to the pool without a device sync
+        cudaFreeAsync(d_data, pool_stream);
+        cudaFreeAsync(d_blk_off, pool_stream);
+        cudaFreeAsync(d_blk_size, pool_stream);
+        cudaFreeAsync(d_blk_rec, pool_stream);
+        cudaFreeAsync(d_ikey_off, pool_stream);
+        cudaFreeAsync(d_ikeys, pool_stream);
+        return;
+    }
     cudaFree(d_data);
     cudaFree(d_blk_off);
     cudaFree(d_blk_size);
@@ -258,6 +267,13 @@ int32_t pgs_engine_open(const pgs_engine_config *cfg, pgs_engine **out)
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e.sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (err == cudaSuccess) { // keep freed compaction buffers in the stream-ordered pool
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (err != cudaSuccess) {
         delete h;
         return cuda_fail(err, "engine open");

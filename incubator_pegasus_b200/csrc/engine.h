@@ -38,6 +38,7 @@ struct Run {
     uint32_t *d_ikey_off = nullptr;
     uint8_t *d_ikeys = nullptr;
     uint64_t data_cap = 0;
+    cudaStream_t pool_stream = nullptr; // set when the buffers came from cudaMallocAsync on that stream
     RunDev dev() const
     {
         return RunDev{d_data, d_blk_off, d_blk_size, d_blk_rec, d_ikey_off, d_ikeys, info.n_blocks, info.max_ukey_len};
