@@ -226,8 +226,8 @@ typedef struct {
     uint8_t count_only;
     uint8_t validate_hash;    /* request flag && server flag, already combined                 */
     uint8_t prefix_same_as_start; /* ReadOptions of the data CF (pegasus_server_impl_init.cpp:835-840) */
-    uint8_t skip_first_exclusive; /* 1 for the first batch (first_exclusive logic)             */
-    uint8_t reserved[2];
+    uint8_t skip_first_exclusive; /* unused: exclusiveness of `start` is start_inclusive        */
+    uint8_t reserved[2];          /* reserved[0] = 1: `stop` is an iterate_upper_bound (sortkey_count) */
     int32_t hash_filter_type, sort_filter_type;
     pgs_blob hash_filter, sort_filter;
     uint32_t max_count;      /* loop guard `count < max_count`                                 */
@@ -258,6 +258,17 @@ typedef struct {
 PGS_API int32_t pgs_range_scan(pgs_partition *p, const pgs_scan_request *req, uint32_t now,
                                uint8_t *arena, uint64_t arena_cap, pgs_kv *kvs, uint32_t kv_cap,
                                uint8_t *resume_key, uint32_t resume_cap, pgs_scan_result *out);
+
+/* Many independent scans in one launch (what a batching front-end in front of the SCAN / LOCAL_APP
+ * thread pools submits).  Request i may use up to arena_stride bytes / kv_stride records on the
+ * device; the outputs come back packed: request i's records are kvs[kv_base[i] .. kv_base[i+1]),
+ * their offsets are relative to arena + arena_base[i] (arena_base / kv_base have n+1 entries),
+ * its resume key (if iter_valid) is resume_keys + i*resume_stride. */
+PGS_API int32_t pgs_range_scan_many(pgs_partition *p, const pgs_scan_request *reqs, uint32_t n,
+                                    uint32_t now, uint64_t arena_stride, uint32_t kv_stride,
+                                    uint8_t *arena, uint64_t arena_cap, pgs_kv *kvs, uint64_t kv_cap,
+                                    uint8_t *resume_keys, uint32_t resume_stride,
+                                    pgs_scan_result *results, uint64_t *arena_base, uint32_t *kv_base);
 
 /* ============================================================================================
  * host-side helpers of the product (no device work)

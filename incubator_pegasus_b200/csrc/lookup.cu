@@ -1,0 +1,1148 @@
+// lookup.cu — read path on the GPU.
+//
+//   k_get   batched point lookup (DB::Get / DB::MultiGet as used by on_get / on_multi_get(sort_keys) /
+//           on_batch_get / on_ttl, src/server/pegasus_server_impl.cpp:441,804,948,1106): one warp per
+//           key; for each run newest -> oldest: binary search of the block index (last user key per
+//           block), TMA-stage the 4 KB data block into the warp's shared-memory slot, binary search of
+//           the restart array, linear decode of one restart interval, user-key compare; newest version
+//           wins, a tombstone ends the search; TTL check and header strip fused.
+//   k_scan  range scan (NewIterator + Seek + Next/Prev loops of on_multi_get range mode, on_get_scanner,
+//           on_scan, on_sortkey_count, :617-756,1243-1320,1444-1490,1042-1062): one CTA per request;
+//           chunks of blocks of every run are staged with TMA, decoded, merged by rank (the same merge
+//           the compaction kernel uses), newest version / tombstone visibility applied, then the
+//           reference's loop (stop key, first-exclusive, range_read_limiter counts and sizes, TTL /
+//           hash / sort-key filters) is evaluated with block-wide scans instead of a serial walk.
+#include <algorithm>
+#include <cstring>
+
+#include "device_util.cuh"
+#include "engine.h"
+
+namespace pgs {
+
+constexpr uint32_t kGetWarps = 8;
+constexpr uint32_t kGetBlockBuf = 8192; // per-warp staging; larger blocks are read in place from HBM
+constexpr uint32_t kMaxReadRuns = 32;
+
+struct ReadRuns {
+    RunDev runs[kMaxReadRuns];
+    uint32_t n;
+};
+
+PGS_DEV uint32_t ld32le(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+// warp-cooperative bytewise compare of a (shared/generic) and b; every lane returns the same result
+PGS_DEV int warp_cmp(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb, uint32_t lane)
+{
+    uint32_t m = la < lb ? la : lb;
+    for (uint32_t base = 0; base < m; base += 32) {
+        uint32_t i = base + lane;
+        int d = 0;
+        if (i < m) d = (int)a[i] - (int)b[i];
+        uint32_t ne = __ballot_sync(kFull, d != 0);
+        if (ne) {
+            int first = __ffs(ne) - 1;
+            return __shfl_sync(kFull, d, first);
+        }
+    }
+    return la < lb ? -1 : (la > lb ? 1 : 0);
+}
+
+// first block of `r` whose last user key >= key (every lane computes the same answer)
+PGS_DEV uint32_t index_lower_bound(const RunDev &r, const uint8_t *key, uint32_t klen)
+{
+    uint32_t lo = 0, hi = r.nb;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        uint32_t o = r.ikey_off[mid], l = r.ikey_off[mid + 1] - o;
+        if (cmp_bytes(r.ikeys + o, l, key, klen) < 0) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+PGS_DEV uint32_t index_upper_bound(const RunDev &r, const uint8_t *key, uint32_t klen)
+{
+    uint32_t lo = 0, hi = r.nb;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        uint32_t o = r.ikey_off[mid], l = r.ikey_off[mid + 1] - o;
+        if (cmp_bytes(r.ikeys + o, l, key, klen) <= 0) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_get
+// ------------------------------------------------------------------------------------------------
+struct GetParams {
+    ReadRuns rr;
+    const uint8_t *keys;
+    const uint32_t *key_off;
+    uint32_t n, now, data_version, use_tma;
+    uint32_t KS; // scratch bytes per warp for the running key
+    pgs_get_result *results;
+    uint8_t *arena;
+    unsigned long long arena_cap;
+    unsigned long long *arena_cursor;
+    uint32_t *error;
+};
+
+__global__ void __launch_bounds__(kGetWarps * 32) k_get(const __grid_constant__ GetParams P)
+{
+    extern __shared__ __align__(128) uint8_t dyn[];
+    __shared__ __align__(8) unsigned long long mbar[kGetWarps];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *buf = dyn + warp * (kGetBlockBuf + 16);
+    uint8_t *scr = dyn + kGetWarps * (kGetBlockBuf + 16) + warp * (P.KS + 16);
+    if (lane == 0) {
+        mbar_init((uint64_t *)&mbar[warp], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    uint32_t phase = 0;
+    for (uint32_t q = blockIdx.x * kGetWarps + warp; q < P.n; q += gridDim.x * kGetWarps) {
+        const uint8_t *key = P.keys + P.key_off[q];
+        const uint32_t klen = P.key_off[q + 1] - P.key_off[q];
+        pgs_get_result res;
+        res.status = PGS_NOT_FOUND;
+        res.expire_ts = 0; res.value_off = 0; res.value_len = 0; res.expired = 0;
+        res.reserved[0] = res.reserved[1] = res.reserved[2] = 0;
+        bool done = false;
+        for (uint32_t ri = 0; ri < P.rr.n && !done; ri++) {
+            const RunDev &r = P.rr.runs[ri];
+            uint32_t b = index_lower_bound(r, key, klen);
+            if (b >= r.nb) continue;
+            const uint8_t *gsrc = r.data + r.blk_off[b];
+            uint32_t size = r.blk_size[b];
+            const uint8_t *base;
+            bool in_smem = P.use_tma && size <= kGetBlockBuf;
+            if (in_smem) {
+                uint32_t bytes = (size + 15) & ~15u;
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx((uint64_t *)&mbar[warp], bytes);
+                    tma_load_1d(buf, gsrc, bytes, (uint64_t *)&mbar[warp]);
+                }
+                mbar_wait((uint64_t *)&mbar[warp], phase);
+                phase ^= 1;
+                base = buf;
+            } else {
+                base = gsrc;
+            }
+            uint32_t err = 0;
+            if (size < 8) err = PGS_CORRUPTION;
+            uint32_t nr = err ? 0 : ld32le(base + size - 4);
+            if (!err && (nr == 0 || (unsigned long long)nr * 4 + 4 > size)) err = PGS_CORRUPTION;
+            if (err) { if (lane == 0) atomicMax(P.error, err); break; }
+            const uint32_t limit = size - 4 - 4 * nr;
+            // last restart point whose user key < key
+            uint32_t lo = 0, hi = nr - 1;
+            while (lo < hi) {
+                uint32_t mid = (lo + hi + 1) >> 1;
+                uint32_t p = ld32le(base + limit + 4 * mid);
+                uint32_t sh, ns, vl, h = 0, c;
+                if (p >= limit) { err = PGS_CORRUPTION; break; }
+                c = get_varint32(base + p, limit - p, sh); h += c;
+                if (c) { c = get_varint32(base + p + h, limit - p - h, ns); h += c; }
+                if (c) { c = get_varint32(base + p + h, limit - p - h, vl); h += c; }
+                if (!c || sh != 0 || ns < 8 || p + h + ns > limit) { err = PGS_CORRUPTION; break; }
+                if (warp_cmp(base + p + h, ns - 8, key, klen, lane) < 0) lo = mid; else hi = mid - 1;
+            }
+            if (err) { if (lane == 0) atomicMax(P.error, err); break; }
+            uint32_t p = ld32le(base + limit + 4 * lo), prev_klen = 0;
+            while (p < limit) {
+                uint32_t sh, ns, vl, h = 0, c;
+                c = get_varint32(base + p, limit - p, sh); h += c;
+                if (c) { c = get_varint32(base + p + h, limit - p - h, ns); h += c; }
+                if (c) { c = get_varint32(base + p + h, limit - p - h, vl); h += c; }
+                uint32_t kl = sh + ns;
+                if (!c || sh > prev_klen || kl < 8 || kl - 8 > P.KS || (unsigned long long)p + h + ns + vl > limit) { err = PGS_CORRUPTION; break; }
+                for (uint32_t x = lane; x < ns; x += 32) scr[sh + x] = base[p + h + x];
+                __syncwarp();
+                int c3 = warp_cmp(scr, kl - 8, key, klen, lane);
+                if (c3 >= 0) {
+                    if (c3 == 0) { // newest version of the key in this run
+                        done = true;
+                        uint8_t type = scr[kl - 8];
+                        if (type == PGS_TYPE_VALUE) {
+                            const uint8_t *val = base + p + h + ns;
+                            uint32_t hdr = user_data_offset(P.data_version);
+                            uint32_t ets = vl >= 4 ? be32(val) : 0;
+                            res.expire_ts = ets;
+                            if (ts_expired(P.now, ets)) {
+                                res.expired = 1; // check_if_record_expired -> NotFound (pegasus_server_impl.cpp:443-448)
+                            } else {
+                                uint32_t ulen = vl >= hdr ? vl - hdr : 0;
+                                unsigned long long off = 0;
+                                if (lane == 0) off = atomicAdd(P.arena_cursor, (unsigned long long)((ulen + 3) & ~3u));
+                                off = __shfl_sync(kFull, off, 0);
+                                if (off + ulen > P.arena_cap) {
+                                    res.status = PGS_INCOMPLETE;
+                                } else {
+                                    res.status = PGS_OK;
+                                    res.value_off = (uint32_t)off;
+                                    res.value_len = ulen;
+                                    if (in_smem) warp_copy_s2g(P.arena + off, val + hdr, ulen, lane);
+                                    else warp_copy_bytes(P.arena + off, val + hdr, ulen, lane);
+                                }
+                            }
+                        }
+                    }
+                    break; // first entry >= key: either the hit or proof of absence in this run
+                }
+                __syncwarp();
+                prev_klen = kl;
+                p += h + ns + vl;
+            }
+            if (err) { if (lane == 0) atomicMax(P.error, err); break; }
+            __syncwarp();
+        }
+        if (lane == 0) P.results[q] = res;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_scan
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kScanThreads = 256;
+constexpr uint32_t kScanWarps = kScanThreads / 32;
+constexpr uint32_t kScanMaxBlocks = 128;
+constexpr uint32_t kScanRecExtra = 48;
+
+struct ScanReqDev {
+    uint32_t start_off, start_len, stop_off, stop_len, hf_off, hf_len, sf_off, sf_len;
+    uint8_t start_inclusive, stop_inclusive, reverse, no_value, key_mode, return_expire_ts, count_only, validate_hash;
+    uint8_t prefix_same_as_start, has_upper, pad[2];
+    int32_t hash_filter_type, sort_filter_type;
+    uint32_t max_count, max_iter_count;
+    unsigned long long max_iter_size;
+    int32_t pidx, partition_version;
+};
+
+struct ScanParams {
+    ReadRuns rr;
+    const ScanReqDev *reqs;
+    const uint8_t *blob; // request byte strings
+    uint32_t n, now, data_version, use_tma;
+    uint32_t KS, pool_bytes, warp_scratch;
+    pgs_scan_result *results;
+    pgs_kv *kvs;
+    uint32_t kv_stride;
+    uint8_t *arena;
+    unsigned long long arena_stride;
+    uint8_t *resume;
+    uint32_t resume_stride;
+    const unsigned long long *crc_table;
+    uint32_t *error;
+};
+
+struct ScanShared {
+    unsigned long long mbar;
+    uint32_t error, done;
+    uint32_t in_bytes, n_rec, n_blk, n_valid, n_vis;
+    uint32_t lo_len, hi_len, has_lo, has_hi, lo_incl, hi_incl; // chunk validity bounds
+    uint32_t cur[kMaxReadRuns], nblk[kMaxReadRuns], nrec[kMaxReadRuns], in_off[kMaxReadRuns], rec_base[kMaxReadRuns], blk_base[kMaxReadRuns];
+    uint32_t vlo[kMaxReadRuns], vhi[kMaxReadRuns], more[kMaxReadRuns];
+    uint32_t tb_off[kScanMaxBlocks], tb_size[kScanMaxBlocks], tb_rec[kScanMaxBlocks], tb_nrec[kScanMaxBlocks];
+    uint32_t scan[33];
+    // carried loop state
+    uint32_t count, iter_count, expire_count, filter_count, n_out;
+    unsigned long long size, arena_used;
+    uint32_t complete, iter_valid, lookahead, resume_len, first_chunk;
+    uint32_t P, F; // per chunk
+    unsigned long long crc[256];
+};
+
+struct ScanArrays {
+    uint8_t *in, *arena;
+    unsigned long long *trailer;
+    uint32_t *voff, *vlen, *A1, *A2, *A3;
+    uint16_t *klen, *rank, *order, *vis;
+    uint8_t *flags, *state;
+    uint32_t total;
+};
+PGS_DEV ScanArrays scan_carve(uint8_t *pool, uint32_t in_bytes, uint32_t n, uint32_t KS)
+{
+    ScanArrays a;
+    uint32_t n8 = (n + 8) & ~7u;
+    uint32_t off = ((in_bytes + 15) & ~15u) + 16;
+    a.in = pool;
+    a.arena = pool + off; off += n8 * KS;
+    a.trailer = (unsigned long long *)(pool + off); off += n8 * 8;
+    a.voff = (uint32_t *)(pool + off); off += n8 * 4;
+    a.vlen = (uint32_t *)(pool + off); off += n8 * 4;
+    a.A1 = (uint32_t *)(pool + off); off += n8 * 4;
+    a.A2 = (uint32_t *)(pool + off); off += n8 * 4;
+    a.A3 = (uint32_t *)(pool + off); off += n8 * 4;
+    a.klen = (uint16_t *)(pool + off); off += n8 * 2;
+    a.rank = (uint16_t *)(pool + off); off += n8 * 2;
+    a.order = (uint16_t *)(pool + off); off += n8 * 2;
+    a.vis = (uint16_t *)(pool + off); off += n8 * 2;
+    a.flags = pool + off; off += n8;
+    a.state = pool + off; off += n8;
+    a.total = off;
+    return a;
+}
+
+template <class F>
+PGS_DEV uint32_t scan_chunked(uint32_t n, uint32_t *out, uint32_t *scratch, F f)
+{
+    uint32_t ipt = (n + blockDim.x - 1) / blockDim.x;
+    uint32_t begin = min(threadIdx.x * ipt, n), end = min(begin + ipt, n);
+    uint32_t local = 0;
+    for (uint32_t i = begin; i < end; i++) local += f(i);
+    uint32_t total;
+    uint32_t pre = block_excl_scan(local, scratch, &total);
+    for (uint32_t i = begin; i < end; i++) { uint32_t v = f(i); out[i] = pre; pre += v; }
+    if (threadIdx.x == 0) out[n] = total;
+    __syncthreads();
+    return total;
+}
+
+// validate_filter of the read path: pegasus_server_impl.cpp:2350-2380 (empty pattern matches)
+PGS_DEV bool dev_validate_filter(int32_t type, const uint8_t *pat, uint32_t pl, const uint8_t *v, uint32_t vl)
+{
+    if (type == PGS_FT_NO_FILTER) return true;
+    if (type < PGS_FT_NO_FILTER || type > PGS_FT_MATCH_POSTFIX) return false;
+    if (pl == 0) return true;
+    if (vl < pl) return false;
+    if (type == PGS_FT_MATCH_PREFIX) {
+        for (uint32_t i = 0; i < pl; i++) if (v[i] != pat[i]) return false;
+        return true;
+    }
+    if (type == PGS_FT_MATCH_POSTFIX) {
+        for (uint32_t i = 0; i < pl; i++) if (v[vl - pl + i] != pat[i]) return false;
+        return true;
+    }
+    for (uint32_t s = 0; s + pl <= vl; s++) {
+        uint32_t i = 0;
+        while (i < pl && v[s + i] == pat[i]) i++;
+        if (i == pl) return true;
+    }
+    return false;
+}
+
+enum : uint8_t { SF_VALID = 1, SF_SHADOW = 2 };
+enum : uint8_t { RS_NORMAL = 0, RS_EXPIRED = 1, RS_FILTERED = 2, RS_HASH_INVALID = 3 };
+
+__global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ ScanParams P)
+{
+    extern __shared__ __align__(128) uint8_t dyn[];
+    __shared__ ScanShared S;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t KS = P.KS, NR = P.rr.n;
+    // bounds of the current chunk, zero padded slots: lo = exclusive/inclusive lower, hi = upper
+    uint8_t *klo = dyn, *khi = dyn + KS + 8, *kpre = dyn + 2 * (KS + 8);
+    uint8_t *wscr = dyn + 3 * (KS + 8) + warp * P.warp_scratch;
+    uint8_t *pool = dyn + 3 * (KS + 8) + kScanWarps * P.warp_scratch;
+
+    if (tid == 0) { mbar_init((uint64_t *)&S.mbar, 1); mbar_fence_init(); }
+    __syncthreads();
+    uint32_t phase = 0;
+
+    for (uint32_t rq = blockIdx.x; rq < P.n; rq += gridDim.x) {
+        const ScanReqDev &Q = P.reqs[rq];
+        const uint8_t *start = P.blob + Q.start_off, *stop = P.blob + Q.stop_off;
+        const uint8_t *hf = P.blob + Q.hf_off, *sf = P.blob + Q.sf_off;
+        const bool rev = Q.reverse != 0;
+        // the range end in iteration direction ("stop" forward, "start" reverse) and its inclusiveness
+        const uint8_t *endk = rev ? start : stop;
+        const uint32_t endl = rev ? Q.start_len : Q.stop_len;
+        const bool end_incl = rev ? Q.start_inclusive : Q.stop_inclusive;
+        pgs_kv *kvs = P.kvs + (size_t)rq * P.kv_stride;
+        uint8_t *arena = P.arena + (size_t)rq * P.arena_stride;
+
+        // prefix_same_as_start: the iterator only lives inside the seek key's hash-key prefix
+        uint32_t pre_len = 0;
+        if (Q.prefix_same_as_start && !rev && Q.start_len >= 2) {
+            uint32_t hl = be16(start);
+            if (2 + hl <= Q.start_len) pre_len = 2 + hl;
+        }
+        if (tid == 0) {
+            S.count = S.iter_count = S.expire_count = S.filter_count = S.n_out = 0;
+            S.size = 0; S.arena_used = 0;
+            S.complete = 0; S.iter_valid = 0; S.lookahead = 0; S.resume_len = 0; S.done = 0; S.error = 0; S.first_chunk = 1;
+        }
+        if (P.crc_table && Q.validate_hash)
+            for (uint32_t i = tid; i < 256; i += kScanThreads) S.crc[i] = P.crc_table[i];
+        // initial cursors: forward: first block whose last key >= start; reverse: first block whose last key >= stop
+        for (uint32_t j = tid; j < NR; j += kScanThreads) {
+            const RunDev &r = P.rr.runs[j];
+            const uint8_t *sk = rev ? stop : start;
+            uint32_t sl = rev ? Q.stop_len : Q.start_len;
+            uint32_t b = index_lower_bound(r, sk, sl);
+            if (rev && b >= r.nb) b = r.nb ? r.nb - 1 : 0;
+            S.cur[j] = b;
+        }
+        // first chunk bound in iteration direction = the seek key
+        for (uint32_t i = tid; i < KS + 8; i += kScanThreads) {
+            const uint8_t *sk = rev ? stop : start;
+            uint32_t sl = rev ? Q.stop_len : Q.start_len;
+            uint8_t v = i < sl && i < KS ? sk[i] : 0;
+            if (rev) khi[i] = v; else klo[i] = v;
+            kpre[i] = i < pre_len ? start[i] : 0;
+        }
+        if (tid == 0) {
+            uint32_t sl = rev ? Q.stop_len : Q.start_len;
+            if (sl > KS) sl = KS; // longer than any stored key: the truncated prefix compares the same way below
+            if (rev) { S.hi_len = sl; S.has_hi = 1; S.hi_incl = Q.stop_inclusive; S.has_lo = 0; S.lo_len = 0; S.lo_incl = 0; }
+            else { S.lo_len = sl; S.has_lo = 1; S.lo_incl = Q.start_inclusive; S.has_hi = 0; S.hi_len = 0; S.hi_incl = 1; }
+        }
+        __syncthreads();
+        // keys longer than KS cannot exist in the runs; a seek key longer than KS that shares its first KS
+        // bytes with a stored key sorts after it: make the truncated bound exclusive/inclusive accordingly
+        if (tid == 0) {
+            uint32_t sl = rev ? Q.stop_len : Q.start_len;
+            if (sl > KS) { if (rev) S.hi_incl = 1; else S.lo_incl = 0; }
+        }
+        __syncthreads();
+
+        // ================================ chunk loop ==========================================
+        for (;;) {
+            __syncthreads();
+            const bool stop_now = S.done || S.error;
+            __syncthreads();
+            if (stop_now) break;
+            // ---- choose blocks ------------------------------------------------------------------
+            if (tid == 0) {
+                uint32_t active = 0;
+                for (uint32_t j = 0; j < NR; j++) {
+                    const RunDev &r = P.rr.runs[j];
+                    bool has = rev ? (r.nb > 0 && S.cur[j] != 0xFFFFFFFFu) : (S.cur[j] < r.nb);
+                    S.nblk[j] = has ? 1 : 0;
+                    active += has;
+                }
+                uint32_t bytes = 0, recs = 0, blks = 0;
+                if (active) {
+                    // per-run budget of the pool, at least one block each; a wanted range end limits the first fetch
+                    uint32_t budget = (P.pool_bytes - 64) / active;
+                    for (uint32_t j = 0; j < NR; j++) {
+                        if (!S.nblk[j]) continue;
+                        const RunDev &r = P.rr.runs[j];
+                        uint32_t c = S.cur[j], m = 1;
+                        if (!S.lookahead) {
+                            uint32_t want_end = rev ? (index_lower_bound(r, endk, endl)) : index_lower_bound(r, endk, endl);
+                            uint32_t maxm = rev ? (c >= want_end ? c - want_end + 1 : 1) : (want_end >= c ? want_end - c + 1 : 1);
+                            if (!rev && maxm > r.nb - c) maxm = r.nb - c;
+                            if (rev && maxm > c + 1) maxm = c + 1;
+                            while (m < maxm) {
+                                uint32_t lo_b = rev ? c - m : c, hi_b = rev ? c + 1 : c + m + 1;
+                                unsigned long long w = (r.blk_off[hi_b] - r.blk_off[lo_b]) + 32 +
+                                                       (unsigned long long)(r.blk_rec[hi_b] - r.blk_rec[lo_b]) * (KS + kScanRecExtra);
+                                if (w > budget) break;
+                                m++;
+                            }
+                        }
+                        S.nblk[j] = m;
+                    }
+                    for (uint32_t j = 0; j < NR; j++) {
+                        const RunDev &r = P.rr.runs[j];
+                        uint32_t m = S.nblk[j];
+                        S.in_off[j] = bytes; S.rec_base[j] = recs; S.blk_base[j] = blks;
+                        S.nrec[j] = 0; S.more[j] = 0;
+                        if (!m) continue;
+                        uint32_t lo_b = rev ? S.cur[j] + 1 - m : S.cur[j], hi_b = lo_b + m;
+                        bytes += (uint32_t)(r.blk_off[hi_b] - r.blk_off[lo_b]);
+                        S.nrec[j] = r.blk_rec[hi_b] - r.blk_rec[lo_b];
+                        recs += S.nrec[j];
+                        blks += m;
+                        S.more[j] = rev ? (lo_b > 0) : (hi_b < r.nb);
+                    }
+                }
+                S.in_bytes = bytes; S.n_rec = recs; S.n_blk = blks;
+                ScanArrays a0 = scan_carve(pool, bytes, recs, KS);
+                if (a0.total > P.pool_bytes || blks > kScanMaxBlocks || recs > 65000) S.error = PGS_NOT_SUPPORTED;
+                if (!active) S.done = 1; // every run exhausted: the iterator is invalid
+            }
+            __syncthreads();
+            if (S.done || S.error) break;
+            const ScanArrays A = scan_carve(pool, S.in_bytes, S.n_rec, KS);
+            // ---- stage + block table ----------------------------------------------------------------
+            if (P.use_tma) {
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx((uint64_t *)&S.mbar, S.in_bytes);
+                    for (uint32_t j = 0; j < NR; j++) {
+                        uint32_t m = S.nblk[j];
+                        if (!m) continue;
+                        const RunDev &r = P.rr.runs[j];
+                        uint32_t lo_b = rev ? S.cur[j] + 1 - m : S.cur[j];
+                        tma_load_1d(A.in + S.in_off[j], r.data + r.blk_off[lo_b], (uint32_t)(r.blk_off[lo_b + m] - r.blk_off[lo_b]), (uint64_t *)&S.mbar);
+                    }
+                }
+            } else {
+                for (uint32_t j = 0; j < NR; j++) {
+                    uint32_t m = S.nblk[j];
+                    if (!m) continue;
+                    const RunDev &r = P.rr.runs[j];
+                    uint32_t lo_b = rev ? S.cur[j] + 1 - m : S.cur[j];
+                    uint32_t bytes = (uint32_t)(r.blk_off[lo_b + m] - r.blk_off[lo_b]);
+                    const uint4 *src = (const uint4 *)(r.data + r.blk_off[lo_b]);
+                    uint4 *dst = (uint4 *)(A.in + S.in_off[j]);
+                    for (uint32_t i = tid; i < bytes / 16; i += kScanThreads) dst[i] = src[i];
+                }
+            }
+            for (uint32_t t = tid; t < S.n_blk; t += kScanThreads) {
+                uint32_t j = 0;
+                while (j + 1 < NR && t >= S.blk_base[j + 1]) j++;
+                const RunDev &r = P.rr.runs[j];
+                uint32_t m = S.nblk[j];
+                uint32_t lo_b = rev ? S.cur[j] + 1 - m : S.cur[j];
+                uint32_t gb = lo_b + (t - S.blk_base[j]);
+                S.tb_off[t] = S.in_off[j] + (uint32_t)(r.blk_off[gb] - r.blk_off[lo_b]);
+                S.tb_size[t] = r.blk_size[gb];
+                S.tb_rec[t] = S.rec_base[j] + (r.blk_rec[gb] - r.blk_rec[lo_b]);
+                S.tb_nrec[t] = r.blk_rec[gb + 1] - r.blk_rec[gb];
+            }
+            // chunk's far bound: everything up to the nearest "last loaded block" key of a run that has more blocks
+            if (tid == 0) {
+                int best = -1;
+                uint32_t best_b = 0;
+                for (uint32_t j = 0; j < NR; j++) {
+                    if (!S.nblk[j] || !S.more[j]) continue;
+                    const RunDev &r = P.rr.runs[j];
+                    uint32_t m = S.nblk[j];
+                    // forward: last key of the last loaded block; reverse: last key of the block before the first loaded one
+                    uint32_t bb = rev ? (S.cur[j] + 1 - m) - 1 : S.cur[j] + m - 1;
+                    if (best < 0) { best = (int)j; best_b = bb; continue; }
+                    const RunDev &rb = P.rr.runs[best];
+                    int c = cmp_bytes(r.ikeys + r.ikey_off[bb], r.ikey_off[bb + 1] - r.ikey_off[bb],
+                                      rb.ikeys + rb.ikey_off[best_b], rb.ikey_off[best_b + 1] - rb.ikey_off[best_b]);
+                    if (rev ? c > 0 : c < 0) { best = (int)j; best_b = bb; }
+                }
+                S.P = (uint32_t)best; S.F = best_b; // reuse as scratch: run / block of the far bound
+            }
+            if (P.use_tma) { mbar_wait((uint64_t *)&S.mbar, phase); phase ^= 1; }
+            __syncthreads();
+            {
+                int best = (int)S.P;
+                uint8_t *dst = rev ? klo : khi;
+                if (best >= 0) {
+                    const RunDev &rb = P.rr.runs[best];
+                    uint32_t o = rb.ikey_off[S.F], l = rb.ikey_off[S.F + 1] - o;
+                    for (uint32_t i = tid; i < KS + 8; i += kScanThreads) dst[i] = i < l ? rb.ikeys[o + i] : 0;
+                    if (tid == 0) { if (rev) { S.lo_len = l; S.has_lo = 1; S.lo_incl = 0; } else { S.hi_len = l; S.has_hi = 1; S.hi_incl = 1; } }
+                } else if (tid == 0) {
+                    if (rev) S.has_lo = 0; else S.has_hi = 0;
+                }
+            }
+            __syncthreads();
+
+            // ---- decode: one warp per block ---------------------------------------------------------------
+            for (uint32_t t = warp; t < S.n_blk; t += kScanWarps) {
+                const uint8_t *base = A.in + S.tb_off[t];
+                uint32_t size = S.tb_size[t], rec0 = S.tb_rec[t], expect = S.tb_nrec[t];
+                uint32_t err = 0, nr = 0;
+                if (size < 8) err = PGS_CORRUPTION;
+                if (!err) { nr = ld32le(base + size - 4); if (nr == 0 || (unsigned long long)nr * 4 + 4 > size) err = PGS_CORRUPTION; }
+                uint32_t limit = err ? 0 : size - 4 - 4 * nr;
+                uint32_t p = 0, prev_klen = 0, i = 0;
+                while (!err && p < limit && i < expect) {
+                    uint32_t sh, ns, vl, h = 0, c;
+                    c = get_varint32(base + p, limit - p, sh); h += c;
+                    if (c) { c = get_varint32(base + p + h, limit - p - h, ns); h += c; }
+                    if (c) { c = get_varint32(base + p + h, limit - p - h, vl); h += c; }
+                    if (!c) { err = PGS_CORRUPTION; break; }
+                    uint32_t kl = sh + ns;
+                    if (sh > prev_klen || kl < 8 || kl - 8 > KS || (unsigned long long)p + h + ns + vl > limit) { err = PGS_CORRUPTION; break; }
+                    for (uint32_t x = lane; x < ns; x += 32) wscr[sh + x] = base[p + h + x];
+                    __syncwarp();
+                    uint32_t ulen = kl - 8, r = rec0 + i, words = (ulen + 7) >> 3;
+                    for (uint32_t w = lane; w < words; w += 32) {
+                        unsigned long long v = *(const unsigned long long *)(wscr + 8 * w);
+                        uint32_t keep = ulen - 8 * w;
+                        if (keep < 8) v &= (1ull << (8 * keep)) - 1;
+                        *(unsigned long long *)(A.arena + (size_t)r * KS + 8 * w) = v;
+                    }
+                    if (lane == 0) {
+                        unsigned long long tr = 0;
+                        for (int x = 7; x >= 0; x--) tr = (tr << 8) | wscr[ulen + x];
+                        A.trailer[r] = tr;
+                        A.klen[r] = (uint16_t)ulen;
+                        A.voff[r] = S.tb_off[t] + p + h + ns;
+                        A.vlen[r] = vl;
+                        A.flags[r] = 0;
+                    }
+                    __syncwarp();
+                    prev_klen = kl;
+                    p += h + ns + vl;
+                    i++;
+                }
+                if (!err && (i != expect || p != limit)) err = PGS_CORRUPTION;
+                if (err && lane == 0) atomicMax(&S.error, err);
+            }
+            __syncthreads();
+            if (S.error) break;
+
+            // ---- validity window per run: lo (<|<=) key (<=) hi, plus the iterator's prefix ---------------------
+            if (tid < NR) {
+                uint32_t n = S.nrec[tid], base = S.rec_base[tid], vlo = 0, vhi = n;
+                if (S.has_lo) { // first index with key > lo (exclusive) or >= lo (inclusive)
+                    uint32_t lo = 0, hi = n;
+                    while (lo < hi) {
+                        uint32_t mid = (lo + hi) >> 1;
+                        int c = cmp_slots(A.arena + (size_t)(base + mid) * KS, A.klen[base + mid], klo, S.lo_len);
+                        if (S.lo_incl ? c < 0 : c <= 0) lo = mid + 1; else hi = mid;
+                    }
+                    vlo = lo;
+                }
+                if (S.has_hi) {
+                    uint32_t lo = 0, hi = n;
+                    while (lo < hi) {
+                        uint32_t mid = (lo + hi) >> 1;
+                        int c = cmp_slots(A.arena + (size_t)(base + mid) * KS, A.klen[base + mid], khi, S.hi_len);
+                        if (S.hi_incl ? c <= 0 : c < 0) lo = mid + 1; else hi = mid;
+                    }
+                    vhi = lo;
+                }
+                if (vhi < vlo) vhi = vlo;
+                S.vlo[tid] = vlo;
+                S.vhi[tid] = vhi;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t nv = 0;
+                for (uint32_t j = 0; j < NR; j++) nv += S.vhi[j] - S.vlo[j];
+                S.n_valid = nv;
+            }
+            // ---- merge rank + shadowing ----------------------------------------------------------------------------
+            for (uint32_t r = tid; r < S.n_rec; r += kScanThreads) {
+                uint32_t j = 0;
+                while (j + 1 < NR && r >= S.rec_base[j + 1]) j++;
+                uint32_t idx = r - S.rec_base[j];
+                if (idx < S.vlo[j] || idx >= S.vhi[j]) { A.flags[r] = 0; continue; }
+                const uint8_t *key = A.arena + (size_t)r * KS;
+                uint32_t kl = A.klen[r];
+                unsigned long long tr = A.trailer[r];
+                uint32_t rank = idx - S.vlo[j];
+                bool shadow = idx > 0 && A.klen[r - 1] == kl && cmp_slots(A.arena + (size_t)(r - 1) * KS, kl, key, kl) == 0;
+                for (uint32_t o = 0; o < NR; o++) {
+                    if (o == j || S.vhi[o] == S.vlo[o]) continue;
+                    uint32_t base = S.rec_base[o], lo = S.vlo[o], hi = S.vhi[o];
+                    while (lo < hi) {
+                        uint32_t mid = (lo + hi) >> 1, q = base + mid;
+                        int c = cmp_slots(A.arena + (size_t)q * KS, A.klen[q], key, kl);
+                        bool before = c != 0 ? c < 0 : (A.trailer[q] > tr || (A.trailer[q] == tr && o < j));
+                        if (before) lo = mid + 1; else hi = mid;
+                    }
+                    rank += lo - S.vlo[o];
+                    if (lo > S.vlo[o]) {
+                        uint32_t q = base + lo - 1;
+                        if (A.klen[q] == kl && cmp_slots(A.arena + (size_t)q * KS, kl, key, kl) == 0) shadow = true;
+                    }
+                }
+                A.rank[r] = (uint16_t)rank;
+                A.flags[r] = SF_VALID | (shadow ? SF_SHADOW : 0);
+            }
+            __syncthreads();
+            for (uint32_t r = tid; r < S.n_rec; r += kScanThreads)
+                if (A.flags[r] & SF_VALID) A.order[A.rank[r]] = (uint16_t)r;
+            __syncthreads();
+            // ---- visible records in iteration order ---------------------------------------------------------------------
+            const uint32_t nv = S.n_valid;
+            auto at = [&](uint32_t p) -> uint32_t { return A.order[rev ? nv - 1 - p : p]; };
+            uint32_t nvis = scan_chunked(nv, A.A1, S.scan, [&](uint32_t p) -> uint32_t {
+                uint32_t r = at(p);
+                return (!(A.flags[r] & SF_SHADOW) && (uint8_t)A.trailer[r] == PGS_TYPE_VALUE) ? 1u : 0u;
+            });
+            for (uint32_t p = tid; p < nv; p += kScanThreads) {
+                uint32_t r = at(p);
+                if (!(A.flags[r] & SF_SHADOW) && (uint8_t)A.trailer[r] == PGS_TYPE_VALUE) A.vis[A.A1[p]] = (uint16_t)r;
+            }
+            __syncthreads();
+            // prefix bound: visible records outside the seek prefix end the iterator
+            // per visible record: in-prefix, in-range, state, sizes
+            //   A2 <- 1 if state==normal (count prefix), A3 <- output bytes if normal (size prefix)
+            for (uint32_t v = tid; v < nvis; v += kScanThreads) {
+                uint32_t r = A.vis[v];
+                const uint8_t *key = A.arena + (size_t)r * KS;
+                uint32_t kl = A.klen[r];
+                uint8_t st;
+                bool in_prefix = true;
+                if (pre_len) {
+                    in_prefix = kl >= pre_len;
+                    for (uint32_t i = 0; in_prefix && i < pre_len; i++) in_prefix = key[i] == kpre[i];
+                }
+                int c = cmp_bytes(key, kl, endk, endl);
+                bool in_range = rev ? (c > 0 || (c == 0 && end_incl)) : (c < 0 || (c == 0 && end_incl));
+                if (Q.has_upper && !rev) in_prefix = in_prefix && c < 0; // iterate_upper_bound (sortkey_count)
+                const uint8_t *val = A.in + A.voff[r];
+                uint32_t vl = A.vlen[r];
+                uint32_t ets = vl >= 4 ? be32(val) : 0;
+                uint32_t hkl = kl >= 2 ? be16(key) : 0;
+                if (hkl + 2 > kl) hkl = kl >= 2 ? kl - 2 : 0;
+                const uint8_t *hk = key + 2, *sk = key + 2 + hkl;
+                uint32_t skl = kl >= 2 ? kl - 2 - hkl : 0;
+                if (ts_expired(P.now, ets)) st = RS_EXPIRED;
+                else {
+                    st = RS_NORMAL;
+                    if (Q.validate_hash) { // validate_key_value_for_scan: :2397-2404
+                        bool bad = Q.partition_version < 0 || Q.pidx > Q.partition_version;
+                        if (!bad && kl >= 2) {
+                            unsigned long long hcrc = ~0ull;
+                            const uint8_t *hp = hkl ? hk : sk;
+                            uint32_t hn = hkl ? hkl : skl;
+                            for (uint32_t i = 0; i < hn; i++) hcrc = S.crc[(uint8_t)(hcrc ^ hp[i])] ^ (hcrc >> 8);
+                            hcrc = ~hcrc;
+                            bad = (long long)(hcrc & (unsigned long long)(long long)Q.partition_version) != (long long)Q.pidx;
+                        }
+                        if (bad) st = RS_HASH_INVALID;
+                    }
+                    if (st == RS_NORMAL && Q.hash_filter_type != PGS_FT_NO_FILTER && !dev_validate_filter(Q.hash_filter_type, hf, Q.hf_len, hk, hkl)) st = RS_FILTERED;
+                    if (st == RS_NORMAL && Q.sort_filter_type != PGS_FT_NO_FILTER && !dev_validate_filter(Q.sort_filter_type, sf, Q.sf_len, sk, skl)) st = RS_FILTERED;
+                }
+                uint32_t hdr = user_data_offset(P.data_version);
+                uint32_t out_k = Q.key_mode == 1 ? skl : kl;
+                uint32_t out_v = Q.no_value ? 0 : (vl >= hdr ? vl - hdr : 0);
+                A.state[v] = st | (in_prefix ? 0x10 : 0) | (in_range ? 0x20 : 0);
+                A.A2[v] = st == RS_NORMAL ? 1u : 0u;
+                A.A3[v] = st == RS_NORMAL ? out_k + out_v : 0u;
+            }
+            __syncthreads();
+            // count / size prefixes over the visible list (in place: A2, A3 become exclusive prefixes)
+            scan_chunked(nvis, A.A1, S.scan, [&](uint32_t v) -> uint32_t { return A.A2[v]; });
+            for (uint32_t v = tid; v <= nvis; v += kScanThreads) A.A2[v] = A.A1[v];
+            __syncthreads();
+            scan_chunked(nvis, A.A1, S.scan, [&](uint32_t v) -> uint32_t { return A.A3[v]; });
+            // A1 = size prefix, A2 = count prefix
+            // ---- the reference loop, evaluated for all positions at once ---------------------------------------------
+            if (tid == 0) { S.P = nvis; S.F = nvis; S.n_vis = nvis; }
+            __syncthreads();
+            for (uint32_t v = tid; v < nvis; v += kScanThreads) {
+                uint8_t s = A.state[v];
+                // F: first position where the iterator is out of its prefix or beyond the range end
+                if (!(s & 0x10) || !(s & 0x20)) atomicMin(&S.F, v);
+                // P: first position where `count < max_count && limiter.valid()` fails
+                bool ok = !S.lookahead && (S.count + A.A2[v] < Q.max_count) && (S.iter_count + v < Q.max_iter_count) &&
+                          (Q.max_iter_size == 0 || S.size + A.A1[v] < Q.max_iter_size);
+                if (!ok) atomicMin(&S.P, v);
+            }
+            __syncthreads();
+            const uint32_t Pp = S.P, Ff = S.F;
+            const uint32_t nproc = min(Pp, Ff); // processed positions [0, nproc)
+            // ---- emit ------------------------------------------------------------------------------------------------------
+            if (!S.lookahead && nproc > 0 && !Q.count_only) {
+                uint32_t hdr = user_data_offset(P.data_version);
+                for (uint32_t v = warp; v < nproc; v += kScanWarps) {
+                    if ((A.state[v] & 0xF) != RS_NORMAL) continue;
+                    uint32_t r = A.vis[v], kl = A.klen[r], vl = A.vlen[r];
+                    const uint8_t *key = A.arena + (size_t)r * KS;
+                    uint32_t koff = 0, klen_out = kl;
+                    if (Q.key_mode == 1) { uint32_t hkl = kl >= 2 ? be16(key) : 0; if (hkl + 2 > kl) hkl = kl >= 2 ? kl - 2 : 0; koff = 2 + hkl; klen_out = kl >= 2 ? kl - koff : 0; }
+                    uint32_t vlen_out = Q.no_value ? 0 : (vl >= hdr ? vl - hdr : 0);
+                    uint32_t slot = S.n_out + (A.A2[v]);
+                    unsigned long long aoff = S.arena_used + A.A1[v];
+                    if (slot >= P.kv_stride || aoff + klen_out + vlen_out > P.arena_stride) { if (lane == 0) atomicMax(&S.error, (uint32_t)PGS_ABORTED); continue; }
+                    warp_copy_bytes(arena + aoff, key + koff, klen_out, lane);
+                    if (vlen_out) warp_copy_s2g(arena + aoff + klen_out, A.in + A.voff[r] + hdr, vlen_out, lane);
+                    if (lane == 0) {
+                        pgs_kv kv;
+                        kv.key_off = (uint32_t)aoff; kv.key_len = klen_out;
+                        kv.value_off = (uint32_t)aoff + klen_out; kv.value_len = vlen_out;
+                        kv.expire_ts = Q.return_expire_ts && vl >= 4 ? be32(A.in + A.voff[r]) : 0;
+                        kvs[slot] = kv;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- advance the loop state -----------------------------------------------------------------------------------------
+            if (tid == 0) {
+                uint32_t nvis_ = S.n_vis;
+                if (!S.lookahead) {
+                    uint32_t exp = 0, fil = 0;
+                    for (uint32_t v = 0; v < nproc; v++) { uint8_t s = A.state[v] & 0xF; exp += s == RS_EXPIRED; fil += s == RS_FILTERED; }
+                    uint32_t normals = A.A2[nproc];
+                    S.expire_count += exp; S.filter_count += fil;
+                    S.iter_count += nproc;
+                    S.count += normals;
+                    if (!Q.count_only) { S.n_out += normals; S.arena_used += A.A1[nproc]; }
+                    S.size += A.A1[nproc];
+                    // a processed record equal to the range end completes the scan (`if (c == 0) complete`)
+                    bool hit_end = false;
+                    if (nproc > 0 && end_incl) {
+                        uint32_t r = A.vis[nproc - 1];
+                        hit_end = cmp_bytes(A.arena + (size_t)r * KS, A.klen[r], endk, endl) == 0;
+                    }
+                    if (hit_end) { S.complete = 1; S.iter_valid = 1; S.done = 1; }
+                    else if (Pp <= Ff && Pp < nvis_) { // limits ended the loop while the iterator stands on vis[Pp]
+                        uint32_t r = A.vis[Pp];
+                        bool valid = (A.state[Pp] & 0x10) != 0;
+                        S.iter_valid = valid; S.done = 1;
+                        if (valid) { S.resume_len = A.klen[r]; for (uint32_t i = 0; i < A.klen[r] && i < P.resume_stride; i++) P.resume[(size_t)rq * P.resume_stride + i] = A.arena[(size_t)r * KS + i]; }
+                    } else if (Ff < nvis_) { // reached a record outside the prefix (iterator invalid) or past the end (complete)
+                        uint8_t s = A.state[Ff];
+                        if (!(s & 0x10)) { S.iter_valid = 0; S.done = 1; }
+                        else { S.complete = 1; S.iter_valid = 1; S.done = 1; }
+                    } else {
+                        // chunk fully consumed.  Did the limits run out exactly here?
+                        bool ok = (S.count < Q.max_count) && (S.iter_count < Q.max_iter_count) && (Q.max_iter_size == 0 || S.size < Q.max_iter_size);
+                        if (!ok) S.lookahead = 1; // need to know whether the iterator is still valid
+                    }
+                } else if (nvis_ > 0) { // look-ahead: the iterator stands on the first visible record
+                    uint32_t r = A.vis[0];
+                    bool valid = (A.state[0] & 0x10) != 0;
+                    S.iter_valid = valid; S.done = 1;
+                    if (valid) { S.resume_len = A.klen[r]; for (uint32_t i = 0; i < A.klen[r] && i < P.resume_stride; i++) P.resume[(size_t)rq * P.resume_stride + i] = A.arena[(size_t)r * KS + i]; }
+                }
+                if (!S.done) { // move every run's cursor past the consumed key range
+                    bool any_more = false;
+                    for (uint32_t j = 0; j < NR; j++) any_more |= S.more[j] != 0;
+                    if (!any_more) { S.done = 1; S.iter_valid = 0; }
+                }
+                S.first_chunk = 0;
+            }
+            __syncthreads();
+            if (!S.done) {
+                // next chunk: forward: lower bound = this chunk's far bound (exclusive); cursors = first block whose
+                // last key > bound.  reverse: upper bound = far bound (inclusive), cursor = first block with last key >= bound
+                for (uint32_t i = tid; i < KS + 8; i += kScanThreads) { if (rev) khi[i] = klo[i]; else klo[i] = khi[i]; }
+                if (tid == 0) {
+                    if (rev) { S.hi_len = S.lo_len; S.has_hi = 1; S.hi_incl = 1; }
+                    else { S.lo_len = S.hi_len; S.has_lo = 1; S.lo_incl = 0; }
+                }
+                __syncthreads();
+                for (uint32_t j = tid; j < NR; j += kScanThreads) {
+                    const RunDev &r = P.rr.runs[j];
+                    if (rev) {
+                        uint32_t b = index_lower_bound(r, khi, S.hi_len);
+                        if (b >= r.nb) b = r.nb ? r.nb - 1 : 0xFFFFFFFFu;
+                        // blocks after b hold only keys > bound; b itself may hold keys <= bound
+                        S.cur[j] = r.nb ? b : 0xFFFFFFFFu;
+                        // a run whose every key is > bound has nothing left: its first block's ... handled by validity window
+                    } else {
+                        S.cur[j] = index_upper_bound(r, klo, S.lo_len);
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // ---- result -----------------------------------------------------------------------------------------------------------------
+        if (tid == 0) {
+            pgs_scan_result res;
+            memset(&res, 0, sizeof res);
+            res.status = S.error ? (int32_t)S.error : PGS_OK;
+            res.n_kvs = S.n_out;
+            res.count = S.count;
+            res.iter_count = S.iter_count;
+            res.expire_count = S.expire_count;
+            res.filter_count = S.filter_count;
+            res.size = S.size;
+            res.complete = (uint8_t)S.complete;
+            res.iter_valid = (uint8_t)S.iter_valid;
+            res.resume_len = S.iter_valid ? S.resume_len : 0;
+            res.arena_used = S.arena_used;
+            P.results[rq] = res;
+            if (S.error) atomicMax(P.error, S.error);
+        }
+        __syncthreads();
+    }
+}
+
+
+// pack the per-request output slices densely so that one D2H copy brings a whole batch back
+__global__ void k_pack_offsets(const pgs_scan_result *__restrict__ res, uint32_t n, unsigned long long *__restrict__ abase,
+                               uint32_t *__restrict__ kbase)
+{
+    __shared__ uint32_t scratch[33];
+    __shared__ unsigned long long carry_a;
+    __shared__ uint32_t carry_k;
+    if (threadIdx.x == 0) { carry_a = 0; carry_k = 0; }
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t a = i < n ? (uint32_t)((res[i].arena_used + 15) & ~15ull) : 0;
+        uint32_t k = i < n ? res[i].n_kvs : 0;
+        uint32_t ta, tk;
+        uint32_t pa = block_excl_scan(a, scratch, &ta);
+        uint32_t pk = block_excl_scan(k, scratch, &tk);
+        if (i < n) { abase[i] = carry_a + pa; kbase[i] = carry_k + pk; }
+        __syncthreads();
+        if (threadIdx.x == 0) { carry_a += ta; carry_k += tk; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { abase[n] = carry_a; kbase[n] = carry_k; }
+}
+__global__ void k_pack_copy(const pgs_scan_result *__restrict__ res, uint32_t n, const uint8_t *__restrict__ arena,
+                            unsigned long long arena_stride, const pgs_kv *__restrict__ kvs, uint32_t kv_stride,
+                            const unsigned long long *__restrict__ abase, const uint32_t *__restrict__ kbase,
+                            uint8_t *__restrict__ parena, pgs_kv *__restrict__ pkvs)
+{
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        uint32_t chunks = (uint32_t)((res[i].arena_used + 15) >> 4);
+        const uint4 *src = (const uint4 *)(arena + (size_t)i * arena_stride);
+        uint4 *dst = (uint4 *)(parena + abase[i]);
+        for (uint32_t c = threadIdx.x; c < chunks; c += blockDim.x) dst[c] = src[c];
+        for (uint32_t k = threadIdx.x; k < res[i].n_kvs; k += blockDim.x) pkvs[kbase[i] + k] = kvs[(size_t)i * kv_stride + k];
+    }
+}
+
+static uint64_t *g_crc_dev_rd[16] = {nullptr};
+const uint64_t *crc64_table();
+
+static int32_t snapshot_runs(Partition &part, std::vector<std::shared_ptr<Run>> &runs, ReadRuns &rr, uint32_t &KS,
+                             const std::vector<std::shared_ptr<Run>> *pinned = nullptr)
+{
+    if (pinned) {
+        runs = *pinned;
+    } else {
+        std::lock_guard<std::mutex> g(part.mu);
+        runs = part.runs;
+    }
+    if (runs.size() > kMaxReadRuns) {
+        set_error("read: %zu runs > %u (compact first)", runs.size(), kMaxReadRuns);
+        return PGS_NOT_SUPPORTED;
+    }
+    rr.n = (uint32_t)runs.size();
+    uint32_t mk = 0;
+    for (uint32_t i = 0; i < rr.n; i++) { rr.runs[i] = runs[i]->dev(); mk = std::max(mk, runs[i]->info.max_ukey_len); }
+    if (mk > kMaxUkeyLen) return PGS_NOT_SUPPORTED;
+    KS = std::max(8u, (mk + 7) & ~7u);
+    return PGS_OK;
+}
+
+int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uint32_t now, unsigned long long arena_stride,
+                  uint32_t kv_stride, uint8_t *arena, uint64_t arena_cap, pgs_kv *kvs, uint64_t kv_cap, uint8_t *resume,
+                  uint32_t resume_stride, pgs_scan_result *results, uint64_t *arena_base, uint32_t *kv_base,
+                  const std::vector<std::shared_ptr<Run>> *pinned)
+{
+    Engine *e = part.eng;
+    std::vector<std::shared_ptr<Run>> runs;
+    ScanParams P{};
+    int32_t rc = snapshot_runs(part, runs, P.rr, P.KS, pinned);
+    if (rc != PGS_OK) return rc;
+    if (n == 0) return PGS_OK;
+    PGS_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    // flatten requests
+    std::vector<ScanReqDev> dev(n);
+    std::string blob;
+    bool need_crc = false;
+    for (uint32_t i = 0; i < n; i++) {
+        const pgs_scan_request &q = reqs[i];
+        ScanReqDev &d = dev[i];
+        memset(&d, 0, sizeof d);
+        auto put = [&](const pgs_blob &b, uint32_t &off, uint32_t &len) {
+            off = (uint32_t)blob.size();
+            len = b.len;
+            if (b.len) blob.append((const char *)b.data, b.len);
+        };
+        put(q.start, d.start_off, d.start_len);
+        put(q.stop, d.stop_off, d.stop_len);
+        put(q.hash_filter, d.hf_off, d.hf_len);
+        put(q.sort_filter, d.sf_off, d.sf_len);
+        d.start_inclusive = q.start_inclusive; d.stop_inclusive = q.stop_inclusive; d.reverse = q.reverse;
+        d.no_value = q.no_value; d.key_mode = q.key_mode; d.return_expire_ts = q.return_expire_ts;
+        d.count_only = q.count_only; d.validate_hash = q.validate_hash; d.prefix_same_as_start = q.prefix_same_as_start;
+        d.has_upper = q.reserved[0]; // iterate_upper_bound (internal flag used by sortkey_count)
+        d.hash_filter_type = q.hash_filter_type; d.sort_filter_type = q.sort_filter_type;
+        d.max_count = q.max_count; d.max_iter_count = q.max_iter_count; d.max_iter_size = q.max_iter_size;
+        d.pidx = q.pidx; d.partition_version = q.partition_version;
+        need_crc |= q.validate_hash != 0;
+    }
+    blob.append(16, '\0');
+    if (resume_stride < P.KS) resume_stride = 0; // caller gave no room: resume keys are not reported
+    // shared memory: one request per CTA; small scans want several CTAs per SM
+    cudaFuncAttributes attr;
+    PGS_CUDA(cudaFuncGetAttributes(&attr, k_scan));
+    P.warp_scratch = (P.KS + 48 + 15) & ~15u;
+    uint32_t fixed_dyn = 3 * (P.KS + 8) + kScanWarps * P.warp_scratch;
+    uint32_t max_blk = 0, max_rec = 0;
+    for (auto &r : runs) { max_blk = std::max(max_blk, r->info.max_block_size); max_rec = std::max(max_rec, r->info.max_block_records); }
+    uint64_t one = (((uint64_t)max_blk + 15) & ~15ull) + 32 + (uint64_t)max_rec * (P.KS + kScanRecExtra);
+    uint64_t want = std::max<uint64_t>(one * std::max<size_t>(1, runs.size()) + 4096, 48 * 1024);
+    if (n == 1) want = std::max<uint64_t>(want, 160 * 1024);
+    uint64_t max_dyn = (uint64_t)e->max_smem_optin - attr.sharedSizeBytes - 256;
+    uint64_t dyn = std::min<uint64_t>(max_dyn, fixed_dyn + want);
+    if (dyn < fixed_dyn + one * std::max<size_t>(1, runs.size()) + 64) {
+        set_error("scan: blocks too large for shared memory");
+        return PGS_NOT_SUPPORTED;
+    }
+    dyn &= ~127ull;
+    P.pool_bytes = (uint32_t)(dyn - fixed_dyn);
+    P.n = n; P.now = now; P.data_version = part.data_version;
+    P.use_tma = (e->cfg.flags & PGS_ENGINE_NO_TMA) ? 0 : 1;
+    P.kv_stride = kv_stride; P.arena_stride = (arena_stride + 15) & ~15ull; P.resume_stride = resume_stride ? resume_stride : P.KS;
+
+    ScanReqDev *d_reqs = nullptr; uint8_t *d_blob = nullptr, *d_arena = nullptr, *d_resume = nullptr, *d_parena = nullptr;
+    pgs_scan_result *d_res = nullptr; pgs_kv *d_kvs = nullptr, *d_pkvs = nullptr; uint32_t *d_err = nullptr, *d_kbase = nullptr;
+    unsigned long long *d_abase = nullptr;
+    auto cleanup = [&]() {
+        cudaFreeAsync(d_reqs, st); cudaFreeAsync(d_blob, st); cudaFreeAsync(d_arena, st); cudaFreeAsync(d_resume, st);
+        cudaFreeAsync(d_parena, st); cudaFreeAsync(d_res, st); cudaFreeAsync(d_kvs, st); cudaFreeAsync(d_pkvs, st);
+        cudaFreeAsync(d_err, st); cudaFreeAsync(d_kbase, st); cudaFreeAsync(d_abase, st);
+    };
+#define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr); } } while (0)
+    CK(cudaMallocAsync(&d_reqs, sizeof(ScanReqDev) * n, st));
+    CK(cudaMallocAsync(&d_blob, blob.size(), st));
+    CK(cudaMallocAsync(&d_arena, P.arena_stride * n + 16, st));
+    CK(cudaMallocAsync(&d_kvs, sizeof(pgs_kv) * (size_t)kv_stride * n + 16, st));
+    CK(cudaMallocAsync(&d_resume, (size_t)P.resume_stride * n + 16, st));
+    CK(cudaMallocAsync(&d_res, sizeof(pgs_scan_result) * n, st));
+    CK(cudaMallocAsync(&d_err, 4, st));
+    CK(cudaMemcpyAsync(d_reqs, dev.data(), sizeof(ScanReqDev) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_err, 0, 4, st));
+    if (need_crc) {
+        int dv = e->device & 15;
+        if (!g_crc_dev_rd[dv]) {
+            uint64_t *t = nullptr;
+            CK(cudaMalloc(&t, 2048));
+            CK(cudaMemcpyAsync(t, crc64_table(), 2048, cudaMemcpyHostToDevice, st));
+            g_crc_dev_rd[dv] = t;
+        }
+        P.crc_table = (const unsigned long long *)g_crc_dev_rd[dv];
+    }
+    P.reqs = d_reqs; P.blob = d_blob; P.results = d_res; P.kvs = d_kvs; P.arena = d_arena; P.resume = d_resume; P.error = d_err;
+    CK(cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CK(cudaFuncSetAttribute(k_scan, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    uint32_t per_sm = (uint32_t)std::max<uint64_t>(1, (228ull * 1024) / (dyn + attr.sharedSizeBytes + 1024));
+    uint32_t grid = std::min<uint32_t>(n, per_sm * e->sm_count);
+    if (P.rr.n == 0) { // empty DB: every iterator is invalid from the start
+        std::vector<pgs_scan_result> z(n);
+        memset(z.data(), 0, sizeof(pgs_scan_result) * n);
+        memcpy(results, z.data(), sizeof(pgs_scan_result) * n);
+        if (arena_base) for (uint32_t i = 0; i <= n; i++) arena_base[i] = 0;
+        if (kv_base) for (uint32_t i = 0; i <= n; i++) kv_base[i] = 0;
+        cleanup();
+        cudaStreamSynchronize(st);
+        return PGS_OK;
+    }
+    k_scan<<<grid, kScanThreads, dyn, st>>>(P);
+    e->launches++;
+    uint32_t herr = 0;
+    if (n == 1) {
+        CK(cudaMemcpyAsync(results, d_res, sizeof(pgs_scan_result), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (!herr) {
+            if (results[0].arena_used > arena_cap || results[0].n_kvs > kv_cap) { cleanup(); return PGS_INCOMPLETE; }
+            if (results[0].arena_used) CK(cudaMemcpyAsync(arena, d_arena, results[0].arena_used, cudaMemcpyDeviceToHost, st));
+            if (results[0].n_kvs) CK(cudaMemcpyAsync(kvs, d_kvs, sizeof(pgs_kv) * results[0].n_kvs, cudaMemcpyDeviceToHost, st));
+            if (results[0].iter_valid && resume && resume_stride) CK(cudaMemcpyAsync(resume, d_resume, results[0].resume_len, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        if (arena_base) { arena_base[0] = 0; arena_base[1] = results[0].arena_used; }
+        if (kv_base) { kv_base[0] = 0; kv_base[1] = results[0].n_kvs; }
+    } else {
+        CK(cudaMallocAsync(&d_abase, sizeof(unsigned long long) * (n + 1), st));
+        CK(cudaMallocAsync(&d_kbase, sizeof(uint32_t) * (n + 1), st));
+        k_pack_offsets<<<1, 1024, 0, st>>>(d_res, n, d_abase, d_kbase);
+        std::vector<unsigned long long> ab(n + 1);
+        std::vector<uint32_t> kb(n + 1);
+        CK(cudaMemcpyAsync(ab.data(), d_abase, sizeof(unsigned long long) * (n + 1), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(kb.data(), d_kbase, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(results, d_res, sizeof(pgs_scan_result) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        e->launches++;
+        if (!herr) {
+            if (ab[n] > arena_cap || kb[n] > kv_cap) { cleanup(); set_error("scan_many: output arena too small"); return PGS_INCOMPLETE; }
+            CK(cudaMallocAsync(&d_parena, ab[n] + 16, st));
+            CK(cudaMallocAsync(&d_pkvs, sizeof(pgs_kv) * ((size_t)kb[n] + 1), st));
+            k_pack_copy<<<std::min<uint32_t>(n, 8 * e->sm_count), 128, 0, st>>>(d_res, n, d_arena, P.arena_stride, d_kvs, kv_stride, d_abase,
+                                                                              d_kbase, d_parena, d_pkvs);
+            e->launches++;
+            if (ab[n]) CK(cudaMemcpyAsync(arena, d_parena, ab[n], cudaMemcpyDeviceToHost, st));
+            if (kb[n]) CK(cudaMemcpyAsync(kvs, d_pkvs, sizeof(pgs_kv) * kb[n], cudaMemcpyDeviceToHost, st));
+            if (resume && resume_stride) CK(cudaMemcpyAsync(resume, d_resume, (size_t)P.resume_stride * n, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        if (arena_base) for (uint32_t i = 0; i <= n; i++) arena_base[i] = ab[i];
+        if (kv_base) for (uint32_t i = 0; i <= n; i++) kv_base[i] = kb[i];
+    }
+    cleanup();
+#undef CK
+    if (herr) {
+        set_error("scan kernel failed with status %u", herr);
+        // PGS_ABORTED = a request's output did not fit its arena / kv slice: the caller may retry with more room
+        return herr == PGS_CORRUPTION ? PGS_CORRUPTION : (herr == PGS_NOT_SUPPORTED ? PGS_NOT_SUPPORTED : (herr == PGS_ABORTED ? PGS_ABORTED : PGS_IO_ERROR));
+    }
+    return PGS_OK;
+}
+
+} // namespace pgs
+
+using namespace pgs;
+
+extern "C" int32_t pgs_get_batch(pgs_partition *ph, const uint8_t *keys, const uint32_t *key_off, uint32_t n,
+                                 uint32_t now, uint8_t *arena, uint64_t arena_cap, pgs_get_result *results,
+                                 uint64_t *arena_used)
+{
+    if (!ph || (n && (!keys || !key_off || !results))) return PGS_INVALID_ARGUMENT;
+    Partition &part = ph->p;
+    Engine *e = part.eng;
+    if (arena_used) *arena_used = 0;
+    if (n == 0) return PGS_OK;
+    std::vector<std::shared_ptr<Run>> runs;
+    GetParams P{};
+    int32_t rc = snapshot_runs(part, runs, P.rr, P.KS);
+    if (rc != PGS_OK) return rc;
+    if (P.rr.n == 0) {
+        for (uint32_t i = 0; i < n; i++) { memset(&results[i], 0, sizeof results[i]); results[i].status = PGS_NOT_FOUND; }
+        return PGS_OK;
+    }
+    PGS_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    uint64_t key_bytes = key_off[n];
+    uint8_t *d_keys = nullptr, *d_arena = nullptr;
+    uint32_t *d_off = nullptr, *d_err = nullptr;
+    pgs_get_result *d_res = nullptr;
+    unsigned long long *d_cur = nullptr;
+    auto cleanup = [&]() {
+        cudaFreeAsync(d_keys, st); cudaFreeAsync(d_arena, st); cudaFreeAsync(d_off, st); cudaFreeAsync(d_err, st);
+        cudaFreeAsync(d_res, st); cudaFreeAsync(d_cur, st);
+    };
+#define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr); } } while (0)
+    CK(cudaMallocAsync(&d_keys, key_bytes + 16, st));
+    CK(cudaMallocAsync(&d_off, sizeof(uint32_t) * (n + 1), st));
+    CK(cudaMallocAsync(&d_res, sizeof(pgs_get_result) * n, st));
+    CK(cudaMallocAsync(&d_arena, arena_cap + 16, st));
+    CK(cudaMallocAsync(&d_cur, 8, st));
+    CK(cudaMallocAsync(&d_err, 4, st));
+    CK(cudaMemcpyAsync(d_keys, keys, key_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_off, key_off, sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_cur, 0, 8, st));
+    CK(cudaMemsetAsync(d_err, 0, 4, st));
+    P.keys = d_keys; P.key_off = d_off; P.n = n; P.now = now; P.data_version = part.data_version;
+    P.use_tma = (e->cfg.flags & PGS_ENGINE_NO_TMA) ? 0 : 1;
+    P.results = d_res; P.arena = d_arena; P.arena_cap = arena_cap; P.arena_cursor = d_cur; P.error = d_err;
+    size_t dyn = kGetWarps * (kGetBlockBuf + 16) + kGetWarps * (P.KS + 16);
+    CK(cudaFuncSetAttribute(k_get, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CK(cudaFuncSetAttribute(k_get, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    uint32_t per_sm = (uint32_t)std::max<size_t>(1, (228 * 1024) / (dyn + 2048));
+    uint32_t grid = std::min<uint32_t>((n + kGetWarps - 1) / kGetWarps, per_sm * e->sm_count);
+    k_get<<<grid, kGetWarps * 32, dyn, st>>>(P);
+    e->launches++;
+    uint32_t herr = 0;
+    unsigned long long used = 0;
+    CK(cudaMemcpyAsync(results, d_res, sizeof(pgs_get_result) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&used, d_cur, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (arena_used) *arena_used = used;
+    if (!herr && used) {
+        CK(cudaMemcpyAsync(arena, d_arena, std::min<unsigned long long>(used, arena_cap), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    cleanup();
+#undef CK
+    if (herr) { set_error("get kernel failed with status %u", herr); return herr == PGS_CORRUPTION ? PGS_CORRUPTION : PGS_IO_ERROR; }
+    return used > arena_cap ? PGS_INCOMPLETE : PGS_OK;
+}
+
+extern "C" int32_t pgs_range_scan(pgs_partition *ph, const pgs_scan_request *req, uint32_t now, uint8_t *arena,
+                                  uint64_t arena_cap, pgs_kv *kvs, uint32_t kv_cap, uint8_t *resume_key,
+                                  uint32_t resume_cap, pgs_scan_result *out)
+{
+    if (!ph || !req || !out) return PGS_INVALID_ARGUMENT;
+    return scan_many(ph->p, req, 1, now, arena_cap, kv_cap, arena, arena_cap, kvs, kv_cap, resume_key, resume_cap, out, nullptr, nullptr, nullptr);
+}
+
+extern "C" int32_t pgs_range_scan_many(pgs_partition *ph, const pgs_scan_request *reqs, uint32_t n, uint32_t now,
+                                       uint64_t arena_stride, uint32_t kv_stride, uint8_t *arena, uint64_t arena_cap,
+                                       pgs_kv *kvs, uint64_t kv_cap, uint8_t *resume_keys, uint32_t resume_stride,
+                                       pgs_scan_result *results, uint64_t *arena_base, uint32_t *kv_base)
+{
+    if (!ph || (n && (!reqs || !results))) return PGS_INVALID_ARGUMENT;
+    return scan_many(ph->p, reqs, n, now, arena_stride, kv_stride, arena, arena_cap, kvs, kv_cap, resume_keys, resume_stride, results,
+                     arena_base, kv_base, nullptr);
+}

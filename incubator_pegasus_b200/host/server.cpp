@@ -1,0 +1,674 @@
+// server.cpp — the rrdb operator surface of one replica on top of the device engine: the host-side
+// mirror of pegasus_server_impl (src/server/pegasus_server_impl.cpp:418-1549 read handlers,
+// :2728-3001 app envs, :3373-3456 manual compaction) and of the write path down to the memtable
+// (src/server/pegasus_server_write.cpp:92-222, src/server/rocksdb_wrapper.cpp:129-288,
+// src/server/pegasus_write_service_impl.h:90-169).  Handlers translate requests into engine calls
+// (pgs_get_batch / range scan / pgs_compact); the per-record loops themselves run in CUDA.
+//
+// Writes land in a host memtable; a read flushes it into an L0 run first (semantically neutral),
+// so the read path is purely the GPU's.  Scan contexts pin the run set they were opened on, like
+// a RocksDB iterator pins its super-version.
+#include <algorithm>
+#include <climits>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <random>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../csrc/engine.h"
+#include "host_internal.h"
+
+namespace pgs {
+
+int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uint32_t now, unsigned long long arena_stride,
+                  uint32_t kv_stride, uint8_t *arena, uint64_t arena_cap, pgs_kv *kvs, uint64_t kv_cap, uint8_t *resume,
+                  uint32_t resume_stride, pgs_scan_result *results, uint64_t *arena_base, uint32_t *kv_base,
+                  const std::vector<std::shared_ptr<Run>> *pinned);
+
+constexpr size_t kReadMaxRuns = 12; // a read-triggered flush compacts L0 once the run list grows past this
+
+struct Resp {
+    pgs_response view{};
+    std::vector<pgs_kv> kvs;
+    std::vector<uint32_t> hk_len;
+    std::string arena;
+    void reset(int32_t app_id, int32_t pidx)
+    {
+        view = pgs_response{};
+        view.app_id = app_id;
+        view.partition_index = pidx;
+        view.kv_count = -1;
+        kvs.clear();
+        hk_len.clear();
+        arena.clear();
+    }
+    void add(std::string_view key, std::string_view value, uint32_t expire_ts)
+    {
+        pgs_kv kv;
+        kv.key_off = (uint32_t)arena.size(); kv.key_len = (uint32_t)key.size();
+        arena.append(key.data(), key.size());
+        kv.value_off = (uint32_t)arena.size(); kv.value_len = (uint32_t)value.size();
+        arena.append(value.data(), value.size());
+        kv.expire_ts = expire_ts;
+        kvs.push_back(kv);
+    }
+    int32_t seal(int32_t error)
+    {
+        view.error = error;
+        view.n_kvs = (uint32_t)kvs.size();
+        view.kvs = kvs.data();
+        view.hk_len = hk_len.empty() ? nullptr : hk_len.data();
+        view.arena = (const uint8_t *)arena.data();
+        view.arena_len = arena.size();
+        return error;
+    }
+};
+
+struct MemRec { uint64_t seq; uint8_t type; std::string value; };
+
+struct ScanContext { // pegasus_scan_context.h:33-95, with the iterator replaced by (pinned runs, resume key)
+    std::vector<std::shared_ptr<Run>> runs;
+    std::string resume, stop;
+    bool stop_inclusive, prefix_mode;
+    int32_t hash_key_filter_type, sort_key_filter_type;
+    std::string hash_key_filter_pattern, sort_key_filter_pattern;
+    int32_t batch_size;
+    bool no_value, validate_partition_hash, return_expire_ts, only_return_count;
+};
+
+struct Server {
+    Engine *eng = nullptr;
+    pgs_partition *part = nullptr;
+    pgs_server_options opt{};
+    int32_t app_id = 0, pidx = 0;
+    uint32_t data_version = 1;
+    uint32_t default_ttl = 0;
+    bool validate_partition_hash = false;
+    int32_t partition_version = -1;
+    std::string ops_bin;
+    std::mutex mu;
+    std::map<std::string, MemRec> mem;
+    uint64_t mem_bytes = 0, last_seq = 0;
+    int64_t last_flushed_decree = 0;
+    int64_t ctx_counter = 0;
+    std::unordered_map<int64_t, std::unique_ptr<ScanContext>> ctx;
+
+    uint32_t cfg_scan_count() const { return opt.rocksdb_max_iteration_count ? opt.rocksdb_max_iteration_count : 1000; }
+    uint32_t cfg_mget_count() const { return opt.rocksdb_multi_get_max_iteration_count ? opt.rocksdb_multi_get_max_iteration_count : 3000; }
+    uint64_t cfg_mget_size() const { return opt.rocksdb_multi_get_max_iteration_size ? opt.rocksdb_multi_get_max_iteration_size : 30ull << 20; }
+
+    pgs_filter_params filter() const
+    {
+        pgs_filter_params fp{};
+        fp.enabled = 1; // enabled once start() knows the data version (pegasus_server_impl.cpp:1780-1784)
+        fp.validate_hash = validate_partition_hash;
+        fp.data_version = data_version;
+        fp.default_ttl = default_ttl;
+        fp.pidx = pidx;
+        fp.partition_version = partition_version;
+        fp.ops = ops_bin.size() > 4 ? (const uint8_t *)ops_bin.data() : nullptr;
+        fp.ops_len = (uint32_t)ops_bin.size();
+        return fp;
+    }
+    std::vector<std::shared_ptr<Run>> runs()
+    {
+        std::lock_guard<std::mutex> g(part->p.mu);
+        return part->p.runs;
+    }
+    int32_t flush_mem()
+    {
+        if (mem.empty()) return PGS_OK;
+        RunBuilder rb(eng->cfg.block_size, eng->cfg.restart_interval);
+        for (auto &kv : mem) {
+            int32_t st = rb.add(kv.first, kv.second.seq, kv.second.type, kv.second.value);
+            if (st != PGS_OK) return st;
+        }
+        rb.finish();
+        uint64_t id = 0;
+        int32_t st = pgs_run_upload(part, 0, (const uint8_t *)rb.data().data(), rb.data().size(), rb.blk_off().data(),
+                                    rb.blk_size().data(), (uint32_t)rb.blk_off().size(), &id);
+        if (st != PGS_OK) return st;
+        mem.clear();
+        mem_bytes = 0;
+        return PGS_OK;
+    }
+    // L0 (+ the L1 run) -> L1, the engine's stand-in for RocksDB's level0_file_num_compaction_trigger
+    int32_t compact_l0(uint32_t now)
+    {
+        auto rs = runs();
+        std::vector<uint64_t> ids;
+        for (auto &r : rs)
+            if (r->level <= 1) ids.push_back(r->id);
+        if (ids.size() < 2) return PGS_OK;
+        pgs_filter_params fp = filter();
+        return pgs_compact(part, ids.data(), (uint32_t)ids.size(), 1, -1, &fp, now, nullptr);
+    }
+    int32_t maybe_compact(uint32_t now)
+    {
+        uint32_t trigger = opt.l0_compaction_trigger ? opt.l0_compaction_trigger : 4;
+        uint32_t l0 = 0;
+        for (auto &r : runs()) l0 += r->level == 0;
+        return l0 >= trigger ? compact_l0(now) : PGS_OK;
+    }
+    int32_t prepare_read(uint32_t now)
+    {
+        int32_t st = flush_mem();
+        if (st != PGS_OK) return st;
+        if (runs().size() > kReadMaxRuns) st = compact_l0(now);
+        return st;
+    }
+    void mem_write(std::string key, uint8_t type, std::string value, uint32_t now)
+    {
+        mem_bytes += key.size() + value.size() + 16;
+        mem[std::move(key)] = MemRec{++last_seq, type, std::move(value)};
+        uint64_t cap = opt.memtable_bytes ? opt.memtable_bytes : 64ull << 20;
+        if (mem_bytes >= cap) {
+            if (flush_mem() == PGS_OK) maybe_compact(now);
+        }
+    }
+    // write_batch_put_ctx for a local write (rocksdb_wrapper.cpp:129-183): value = header || user data
+    void put_one(std::string_view raw_key, std::string_view user, uint32_t expire_ts, uint64_t timestamp_us, uint32_t now)
+    {
+        if (default_ttl != 0 && expire_ts == 0) expire_ts = now + default_ttl; // db_expire_ts :280-288
+        uint64_t timetag = timestamp_us << 8u | (uint64_t)(opt.cluster_id << 1u); // generate_timetag, pegasus_value_schema.h:44-47
+        std::string v(user_data_offset(data_version) + user.size(), '\0');
+        v[0] = (char)(expire_ts >> 24); v[1] = (char)(expire_ts >> 16); v[2] = (char)(expire_ts >> 8); v[3] = (char)expire_ts;
+        if (data_version == 1)
+            for (int i = 0; i < 8; i++) v[4 + i] = (char)(timetag >> (56 - 8 * i));
+        memcpy(&v[user_data_offset(data_version)], user.data(), user.size());
+        mem_write(std::string(raw_key), PGS_TYPE_VALUE, std::move(v), now);
+    }
+
+    // one range scan through the engine, growing the output buffers when a result does not fit
+    int32_t scan(const pgs_scan_request &rq, uint32_t now, const std::vector<std::shared_ptr<Run>> *pinned, uint64_t size_hint,
+                 std::vector<uint8_t> &arena, std::vector<pgs_kv> &kvs, std::string &resume, pgs_scan_result &res)
+    {
+        uint64_t cap = std::max<uint64_t>(size_hint, 1 << 20);
+        uint32_t kv_cap = rq.count_only ? 1 : std::max<uint32_t>(1, std::min<uint32_t>(rq.max_count, 65536));
+        for (;;) {
+            arena.resize(cap);
+            kvs.resize(kv_cap);
+            resume.assign(kMaxUkeyLen + 8, '\0');
+            int32_t st = scan_many(part->p, &rq, 1, now, cap, kv_cap, arena.data(), cap, kvs.data(), kv_cap, (uint8_t *)&resume[0],
+                                   (uint32_t)resume.size(), &res, nullptr, nullptr, pinned);
+            if (st == PGS_ABORTED && cap < (4ull << 30)) { cap *= 8; continue; }
+            if (st != PGS_OK) return st;
+            resume.resize(res.iter_valid ? res.resume_len : 0);
+            return PGS_OK;
+        }
+    }
+};
+
+static inline std::string_view bsv(const pgs_blob &b) { return std::string_view((const char *)b.data, b.len); }
+static inline pgs_blob blob_of(const std::string &s) { return pgs_blob{(const uint8_t *)s.data(), (uint32_t)s.size()}; }
+static inline bool filter_type_supported(int32_t t) { return t >= PGS_FT_NO_FILTER && t <= PGS_FT_MATCH_POSTFIX; }
+
+// rocksdb read error -> the replica fails itself on anything but NotFound (replica.cpp:444-459); the
+// engine's own failures surface as the same integers.
+static int32_t read_fail(Resp &r, int32_t st)
+{
+    r.kvs.clear();
+    r.arena.clear();
+    return r.seal(st);
+}
+
+// ---- on_get / on_ttl (pegasus_server_impl.cpp:418-494, 1088-1149) --------------------------------------
+static int32_t do_get(Server &s, std::string_view key, uint32_t now, Resp &r, bool ttl_only)
+{
+    r.reset(s.app_id, s.pidx);
+    int32_t st = s.prepare_read(now);
+    if (st != PGS_OK) return read_fail(r, st);
+    uint32_t off[2] = {0, (uint32_t)key.size()};
+    pgs_get_result gr{};
+    std::vector<uint8_t> arena(1 << 16);
+    uint64_t used = 0;
+    for (;;) {
+        st = pgs_get_batch(s.part, (const uint8_t *)key.data(), off, 1, now, arena.data(), arena.size(), &gr, &used);
+        if (st == PGS_INCOMPLETE && used > arena.size()) { arena.resize(used + 64); continue; }
+        break;
+    }
+    if (st != PGS_OK) return read_fail(r, st);
+    if (gr.expired) r.view.expire_count = 1;
+    if (gr.status != PGS_OK) return r.seal(PGS_NOT_FOUND);
+    if (ttl_only) {
+        r.view.ttl_seconds = gr.expire_ts > 0 ? (int32_t)(gr.expire_ts - now) : -1;
+        return r.seal(PGS_OK);
+    }
+    r.add(std::string_view(), std::string_view((const char *)arena.data() + gr.value_off, gr.value_len), 0);
+    return r.seal(PGS_OK);
+}
+
+// ---- on_multi_get (:496-904) ----------------------------------------------------------------------------------
+static int32_t do_multi_get(Server &s, const pgs_multi_get_request &q, uint32_t now, Resp &r)
+{
+    r.reset(s.app_id, s.pidx);
+    if (!filter_type_supported(q.sort_key_filter_type)) return r.seal(PGS_INVALID_ARGUMENT);
+    int32_t st = s.prepare_read(now);
+    if (st != PGS_OK) return read_fail(r, st);
+    uint32_t max_kv_count = s.cfg_mget_count(), max_iteration_count = s.cfg_mget_count();
+    if (q.max_kv_count > 0 && (uint32_t)q.max_kv_count < max_kv_count) max_kv_count = q.max_kv_count;
+    int32_t max_kv_size = q.max_kv_size > 0 ? q.max_kv_size : INT_MAX;
+    int32_t max_iteration_size_config = s.cfg_mget_size() > 0 ? (int32_t)std::min<uint64_t>(s.cfg_mget_size(), INT_MAX) : INT_MAX;
+    int32_t max_iteration_size = std::min(max_kv_size, max_iteration_size_config);
+    std::string_view hash_key = bsv(q.hash_key);
+
+    if (q.n_sort_keys == 0) {
+        std::string start = make_key(hash_key, bsv(q.start_sortkey));
+        bool start_inclusive = q.start_inclusive;
+        std::string stop;
+        bool stop_inclusive;
+        if (q.stop_sortkey.len == 0) { stop = make_next(make_key(hash_key, {})); stop_inclusive = false; }
+        else { stop = make_key(hash_key, bsv(q.stop_sortkey)); stop_inclusive = q.stop_inclusive; }
+        if (q.sort_key_filter_type == PGS_FT_MATCH_PREFIX && q.sort_key_filter_pattern.len > 0) { // :558-578
+            std::string ps = make_key(hash_key, bsv(q.sort_key_filter_pattern));
+            std::string pe = make_next(ps);
+            if (std::string_view(ps).compare(start) > 0) { start = ps; start_inclusive = true; }
+            if (std::string_view(pe).compare(stop) <= 0) { stop = pe; stop_inclusive = false; }
+        }
+        int c = std::string_view(start).compare(stop);
+        if (c > 0 || (c == 0 && (!start_inclusive || !stop_inclusive))) return r.seal(PGS_OK); // :581-607
+        pgs_scan_request rq{};
+        rq.start = blob_of(start);
+        rq.stop = blob_of(stop);
+        rq.start_inclusive = start_inclusive;
+        rq.stop_inclusive = stop_inclusive;
+        rq.reverse = q.reverse;
+        rq.no_value = q.no_value;
+        rq.key_mode = 1;
+        rq.prefix_same_as_start = s.opt.prefix_filter && !q.reverse; // reverse: total_order_seek (:679-688)
+        rq.sort_filter_type = q.sort_key_filter_type;
+        rq.sort_filter = q.sort_key_filter_pattern;
+        rq.max_count = max_kv_count;
+        rq.max_iter_count = max_iteration_count;
+        rq.max_iter_size = (uint64_t)max_iteration_size;
+        rq.pidx = s.pidx;
+        rq.partition_version = s.partition_version;
+        std::vector<uint8_t> arena;
+        std::vector<pgs_kv> kvs;
+        std::string resume;
+        pgs_scan_result res{};
+        st = s.scan(rq, now, nullptr, 0, arena, kvs, resume, res);
+        if (st != PGS_OK) return read_fail(r, st);
+        if (res.status != PGS_OK) return read_fail(r, res.status);
+        for (uint32_t i = 0; i < res.n_kvs; i++) { // reverse mode: re-reverse so that kvs ascend by sort key (:758-764)
+            const pgs_kv &kv = kvs[q.reverse ? res.n_kvs - 1 - i : i];
+            r.add(std::string_view((const char *)arena.data() + kv.key_off, kv.key_len),
+                  std::string_view((const char *)arena.data() + kv.value_off, kv.value_len), 0);
+        }
+        r.view.iteration_count = res.iter_count;
+        r.view.expire_count = res.expire_count;
+        r.view.filter_count = res.filter_count;
+        return r.seal(res.iter_valid && !res.complete ? PGS_INCOMPLETE : PGS_OK); // :777-787
+    }
+    // sort_keys given: MultiGet (:789-864)
+    std::string keys;
+    std::vector<uint32_t> off(1, 0);
+    for (uint32_t i = 0; i < q.n_sort_keys; i++) {
+        keys += make_key(hash_key, bsv(q.sort_keys[i]));
+        off.push_back((uint32_t)keys.size());
+    }
+    std::vector<pgs_get_result> gr(q.n_sort_keys);
+    std::vector<uint8_t> arena(1 << 20);
+    uint64_t used = 0;
+    for (;;) {
+        st = pgs_get_batch(s.part, (const uint8_t *)keys.data(), off.data(), q.n_sort_keys, now, arena.data(), arena.size(), gr.data(), &used);
+        if (st == PGS_INCOMPLETE && used > arena.size()) { arena.resize(used + 64); continue; }
+        break;
+    }
+    if (st != PGS_OK) return read_fail(r, st);
+    int32_t count = 0;
+    int64_t size = 0;
+    bool exceed_limit = false;
+    for (uint32_t i = 0; i < q.n_sort_keys; i++) {
+        if (gr[i].expired) { r.view.expire_count++; continue; }
+        if (gr[i].status != PGS_OK) continue;
+        if (count >= (int32_t)max_kv_count || size >= max_kv_size) { exceed_limit = true; break; }
+        std::string_view v = q.no_value ? std::string_view() : std::string_view((const char *)arena.data() + gr[i].value_off, gr[i].value_len);
+        r.add(bsv(q.sort_keys[i]), v, 0);
+        count++;
+        size += q.sort_keys[i].len + v.size();
+    }
+    return r.seal(exceed_limit ? PGS_INCOMPLETE : PGS_OK);
+}
+
+// ---- on_batch_get (:906-1016) ---------------------------------------------------------------------------------
+static int32_t do_batch_get(Server &s, const pgs_full_key *fk, uint32_t n, uint32_t now, Resp &r)
+{
+    r.reset(s.app_id, s.pidx);
+    if (n == 0) return r.seal(PGS_INVALID_ARGUMENT);
+    int32_t st = s.prepare_read(now);
+    if (st != PGS_OK) return read_fail(r, st);
+    std::string keys;
+    std::vector<uint32_t> off(1, 0);
+    for (uint32_t i = 0; i < n; i++) {
+        keys += make_key(bsv(fk[i].hash_key), bsv(fk[i].sort_key));
+        off.push_back((uint32_t)keys.size());
+    }
+    std::vector<pgs_get_result> gr(n);
+    std::vector<uint8_t> arena(1 << 20);
+    uint64_t used = 0;
+    for (;;) {
+        st = pgs_get_batch(s.part, (const uint8_t *)keys.data(), off.data(), n, now, arena.data(), arena.size(), gr.data(), &used);
+        if (st == PGS_INCOMPLETE && used > arena.size()) { arena.resize(used + 64); continue; }
+        break;
+    }
+    if (st != PGS_OK) return read_fail(r, st);
+    for (uint32_t i = 0; i < n; i++) {
+        if (gr[i].expired) { r.view.expire_count++; continue; }
+        if (gr[i].status != PGS_OK) continue;
+        std::string hs(bsv(fk[i].hash_key));
+        hs += bsv(fk[i].sort_key);
+        r.add(hs, std::string_view((const char *)arena.data() + gr[i].value_off, gr[i].value_len), 0);
+        r.hk_len.push_back(fk[i].hash_key.len);
+    }
+    return r.seal(PGS_OK);
+}
+
+// ---- on_sortkey_count (:1018-1086) --------------------------------------------------------------------------------
+static int32_t do_sortkey_count(Server &s, std::string_view hash_key, uint32_t now, Resp &r)
+{
+    r.reset(s.app_id, s.pidx);
+    int32_t st = s.prepare_read(now);
+    if (st != PGS_OK) return read_fail(r, st);
+    std::string start = make_key(hash_key, {}), stop = make_next(start);
+    pgs_scan_request rq{};
+    rq.start = blob_of(start);
+    rq.stop = blob_of(stop);
+    rq.start_inclusive = 1;
+    rq.stop_inclusive = 0;
+    rq.count_only = 1;
+    rq.reserved[0] = 1; // iterate_upper_bound = stop
+    rq.prefix_same_as_start = s.opt.prefix_filter;
+    rq.max_count = UINT32_MAX; // the loop is only time limited (:1052)
+    rq.max_iter_count = UINT32_MAX;
+    rq.pidx = s.pidx;
+    rq.partition_version = s.partition_version;
+    std::vector<uint8_t> arena;
+    std::vector<pgs_kv> kvs;
+    std::string resume;
+    pgs_scan_result res{};
+    st = s.scan(rq, now, nullptr, 0, arena, kvs, resume, res);
+    if (st != PGS_OK) return read_fail(r, st);
+    if (res.status != PGS_OK) { r.view.count = 0; return read_fail(r, res.status); }
+    r.view.count = res.count;
+    r.view.iteration_count = res.iter_count;
+    r.view.expire_count = res.expire_count;
+    return r.seal(PGS_OK);
+}
+
+// ---- on_get_scanner / on_scan (:1151-1547) ----------------------------------------------------------------------------
+static int32_t scan_batch(Server &s, std::unique_ptr<ScanContext> ctx, bool start_inclusive, uint32_t limiter_max, uint32_t now, Resp &r)
+{
+    uint32_t batch_count = s.cfg_scan_count();
+    if (ctx->batch_size > 0 && (uint32_t)ctx->batch_size < batch_count) batch_count = ctx->batch_size;
+    pgs_scan_request rq{};
+    rq.start = blob_of(ctx->resume);
+    rq.stop = blob_of(ctx->stop);
+    rq.start_inclusive = start_inclusive;
+    rq.stop_inclusive = ctx->stop_inclusive;
+    rq.no_value = ctx->no_value;
+    rq.key_mode = 0;
+    rq.return_expire_ts = ctx->return_expire_ts;
+    rq.count_only = ctx->only_return_count;
+    rq.validate_hash = ctx->validate_partition_hash && s.validate_partition_hash; // request flag && server flag (:2397)
+    rq.prefix_same_as_start = ctx->prefix_mode;
+    rq.hash_filter_type = ctx->hash_key_filter_type;
+    rq.sort_filter_type = ctx->sort_key_filter_type;
+    rq.hash_filter = blob_of(ctx->hash_key_filter_pattern);
+    rq.sort_filter = blob_of(ctx->sort_key_filter_pattern);
+    rq.max_count = batch_count;
+    rq.max_iter_count = limiter_max ? limiter_max : batch_count;
+    rq.max_iter_size = 0;
+    rq.pidx = s.pidx;
+    rq.partition_version = s.partition_version;
+    std::vector<uint8_t> arena;
+    std::vector<pgs_kv> kvs;
+    std::string resume;
+    pgs_scan_result res{};
+    int32_t st = s.scan(rq, now, &ctx->runs, 0, arena, kvs, resume, res);
+    if (st != PGS_OK) return read_fail(r, st);
+    if (res.status != PGS_OK) return read_fail(r, res.status);
+    for (uint32_t i = 0; i < res.n_kvs; i++)
+        r.add(std::string_view((const char *)arena.data() + kvs[i].key_off, kvs[i].key_len),
+              std::string_view((const char *)arena.data() + kvs[i].value_off, kvs[i].value_len), kvs[i].expire_ts);
+    if (ctx->only_return_count) r.view.kv_count = (int32_t)res.count;
+    r.view.iteration_count = res.iter_count;
+    r.view.expire_count = res.expire_count;
+    r.view.filter_count = res.filter_count;
+    if (res.iter_valid && !res.complete) { // park the cursor (:1360-1387)
+        ctx->resume = resume;
+        int64_t handle = s.ctx_counter++;
+        s.ctx[handle] = std::move(ctx);
+        r.view.context_id = handle;
+    } else {
+        r.view.context_id = -1; // SCAN_CONTEXT_ID_COMPLETED
+    }
+    return r.seal(PGS_OK);
+}
+
+static int32_t do_get_scanner(Server &s, const pgs_get_scanner_request &q, uint32_t now, Resp &r)
+{
+    r.reset(s.app_id, s.pidx);
+    if (!filter_type_supported(q.hash_key_filter_type) || !filter_type_supported(q.sort_key_filter_type))
+        return r.seal(PGS_INVALID_ARGUMENT);
+    int32_t st = s.prepare_read(now);
+    if (st != PGS_OK) return read_fail(r, st);
+    bool prefix_mode = s.opt.prefix_filter;
+    if (s.opt.prefix_filter) { // :1188-1198
+        uint32_t hl = q.start_key.len >= 2 ? be16(q.start_key.data) : 0;
+        if (hl == 0 || q.full_scan) prefix_mode = false; // total_order_seek
+    }
+    bool start_inclusive = q.start_inclusive;
+    std::string start(bsv(q.start_key)), stop(bsv(q.stop_key));
+    if (q.hash_key_filter_type == PGS_FT_MATCH_PREFIX && q.hash_key_filter_pattern.len > 0) { // :1207-1223
+        std::string ps = make_key(bsv(q.hash_key_filter_pattern), {});
+        if (std::string_view(ps).compare(start) > 0) { start = ps; start_inclusive = true; }
+    }
+    int c = std::string_view(start).compare(stop);
+    if (c > 0 || (c == 0 && (!start_inclusive || !q.stop_inclusive))) return r.seal(PGS_OK); // empty range, context_id default
+    auto ctx = std::make_unique<ScanContext>();
+    ctx->runs = s.runs();
+    ctx->resume = start;
+    ctx->stop = stop;
+    ctx->stop_inclusive = q.stop_inclusive;
+    ctx->prefix_mode = prefix_mode;
+    ctx->hash_key_filter_type = q.hash_key_filter_type;
+    ctx->sort_key_filter_type = q.sort_key_filter_type;
+    ctx->hash_key_filter_pattern = std::string(bsv(q.hash_key_filter_pattern));
+    ctx->sort_key_filter_pattern = std::string(bsv(q.sort_key_filter_pattern));
+    uint32_t batch_count = s.cfg_scan_count();
+    if (q.batch_size > 0 && (uint32_t)q.batch_size < batch_count) batch_count = q.batch_size;
+    ctx->batch_size = (int32_t)batch_count;
+    ctx->no_value = q.no_value;
+    ctx->validate_partition_hash = q.validate_partition_hash;
+    ctx->return_expire_ts = q.return_expire_ts;
+    ctx->only_return_count = q.only_return_count;
+    // on_get_scanner's limiter counts up to rocksdb_max_iteration_count, on_scan's up to batch_count (:1252-1266 vs :1434-1442)
+    return scan_batch(s, std::move(ctx), start_inclusive, s.cfg_scan_count(), now, r);
+}
+
+static int32_t do_scan(Server &s, int64_t context_id, uint32_t now, Resp &r)
+{
+    r.reset(s.app_id, s.pidx);
+    auto f = s.ctx.find(context_id);
+    if (f == s.ctx.end()) return r.seal(PGS_NOT_FOUND); // :1542-1544
+    std::unique_ptr<ScanContext> ctx = std::move(f->second);
+    s.ctx.erase(f);
+    return scan_batch(s, std::move(ctx), true, 0, now, r);
+}
+
+static void parse_envs(const char *envs, uint32_t n, std::vector<std::pair<std::string, std::string>> &out)
+{
+    const char *p = envs;
+    for (uint32_t i = 0; i < n; i++) {
+        std::string k(p);
+        p += k.size() + 1;
+        std::string v(p);
+        p += v.size() + 1;
+        out.emplace_back(std::move(k), std::move(v));
+    }
+}
+
+} // namespace pgs
+
+using namespace pgs;
+struct pgs_server { Server s; };
+struct pgs_response_buf { Resp r; };
+
+extern "C" {
+
+pgs_response_buf *pgs_response_new(void) { return new pgs_response_buf; }
+void pgs_response_free(pgs_response_buf *r) { delete r; }
+const pgs_response *pgs_response_view(pgs_response_buf *r) { return &r->r.view; }
+
+int32_t pgs_rrdb_update_app_envs(pgs_server *h, const char *envs, uint32_t n_envs, uint32_t now)
+{
+    Server &s = h->s;
+    std::lock_guard<std::mutex> g(s.mu);
+    std::vector<std::pair<std::string, std::string>> kv;
+    if (envs && n_envs) parse_envs(envs, n_envs, kv);
+    for (auto &e : kv) {
+        if (e.first == "default_ttl") { // update_default_ttl, pegasus_server_impl.cpp:2814-2826
+            s.default_ttl = (uint32_t)strtoul(e.second.c_str(), nullptr, 10);
+        } else if (e.first == "replica.split.validate_partition_hash") { // :2966-2983
+            s.validate_partition_hash = e.second == "true";
+        } else if (e.first == "user_specified_compaction") { // :2985-3001
+            s.ops_bin.clear();
+            if (!e.second.empty()) ops_parse(e.second, s.data_version, s.ops_bin, nullptr);
+        }
+    }
+    (void)now;
+    return PGS_OK;
+}
+
+int32_t pgs_rrdb_start(pgs_engine *e, int32_t app_id, int32_t pidx, const pgs_server_options *opt, const char *envs,
+                       uint32_t n_envs, pgs_server **out)
+{
+    if (!e || !out) return PGS_INVALID_ARGUMENT;
+    auto *h = new pgs_server;
+    Server &s = h->s;
+    s.eng = &e->e;
+    s.app_id = app_id;
+    s.pidx = pidx;
+    if (opt) s.opt = *opt; else s.opt.prefix_filter = 1;
+    if (!s.opt.cluster_id) s.opt.cluster_id = 1;
+    int32_t st = pgs_partition_create(e, app_id, pidx, s.data_version, &s.part);
+    if (st != PGS_OK) { delete h; return st; }
+    std::mt19937_64 rng(std::random_device{}());
+    s.ctx_counter = (int64_t)(rng() % (1ull << 31)) << 32; // pegasus_scan_context.h:113-114, kept non-negative
+    if (envs && n_envs) pgs_rrdb_update_app_envs(h, envs, n_envs, 0);
+    *out = h;
+    return PGS_OK;
+}
+void pgs_rrdb_stop(pgs_server *h)
+{
+    if (!h) return;
+    h->s.ctx.clear();
+    pgs_partition_destroy(h->s.part);
+    delete h;
+}
+pgs_partition *pgs_rrdb_partition(pgs_server *h) { return h->s.part; }
+void pgs_rrdb_set_partition_version(pgs_server *h, int32_t pv) { h->s.partition_version = pv; }
+
+#define LOCKED(h) std::lock_guard<std::mutex> _g((h)->s.mu)
+int32_t pgs_rrdb_get(pgs_server *h, pgs_blob key, uint32_t now, pgs_response_buf *r) { LOCKED(h); return do_get(h->s, bsv(key), now, r->r, false); }
+int32_t pgs_rrdb_ttl(pgs_server *h, pgs_blob key, uint32_t now, pgs_response_buf *r) { LOCKED(h); return do_get(h->s, bsv(key), now, r->r, true); }
+int32_t pgs_rrdb_multi_get(pgs_server *h, const pgs_multi_get_request *q, uint32_t now, pgs_response_buf *r) { LOCKED(h); return do_multi_get(h->s, *q, now, r->r); }
+int32_t pgs_rrdb_batch_get(pgs_server *h, const pgs_full_key *k, uint32_t n, uint32_t now, pgs_response_buf *r) { LOCKED(h); return do_batch_get(h->s, k, n, now, r->r); }
+int32_t pgs_rrdb_sortkey_count(pgs_server *h, pgs_blob hk, uint32_t now, pgs_response_buf *r) { LOCKED(h); return do_sortkey_count(h->s, bsv(hk), now, r->r); }
+int32_t pgs_rrdb_get_scanner(pgs_server *h, const pgs_get_scanner_request *q, uint32_t now, pgs_response_buf *r) { LOCKED(h); return do_get_scanner(h->s, *q, now, r->r); }
+int32_t pgs_rrdb_scan(pgs_server *h, int64_t context_id, uint32_t now, pgs_response_buf *r) { LOCKED(h); return do_scan(h->s, context_id, now, r->r); }
+void pgs_rrdb_clear_scanner(pgs_server *h, int64_t context_id) { LOCKED(h); h->s.ctx.erase(context_id); }
+
+int32_t pgs_rrdb_get_many(pgs_server *h, const uint8_t *keys, const uint32_t *key_off, uint32_t n, uint32_t now,
+                          uint8_t *arena, uint64_t arena_cap, pgs_get_result *results, uint64_t *arena_used)
+{
+    LOCKED(h);
+    int32_t st = h->s.prepare_read(now);
+    if (st != PGS_OK) return st;
+    return pgs_get_batch(h->s.part, keys, key_off, n, now, arena, arena_cap, results, arena_used);
+}
+
+int32_t pgs_rrdb_put(pgs_server *h, pgs_blob key, pgs_blob value, uint32_t expire_ts, int64_t decree,
+                     uint64_t timestamp_us, uint32_t now)
+{
+    LOCKED(h);
+    h->s.put_one(bsv(key), bsv(value), expire_ts, timestamp_us, now);
+    h->s.last_flushed_decree = decree;
+    return PGS_OK;
+}
+int32_t pgs_rrdb_remove(pgs_server *h, pgs_blob key, int64_t decree)
+{
+    LOCKED(h);
+    h->s.mem_write(std::string(bsv(key)), PGS_TYPE_DELETION, std::string(), 0);
+    h->s.last_flushed_decree = decree;
+    return PGS_OK;
+}
+int32_t pgs_rrdb_multi_put(pgs_server *h, pgs_blob hash_key, const pgs_blob *sort_keys, const pgs_blob *values,
+                           uint32_t n, uint32_t expire_ts, int64_t decree, uint64_t timestamp_us, uint32_t now)
+{
+    LOCKED(h);
+    Server &s = h->s;
+    s.last_flushed_decree = decree;
+    if (n == 0) { // request.kvs is empty: kInvalidArgument, but an empty record still advances the decree
+        s.put_one({}, {}, 0, timestamp_us, 0); // empty_put (pegasus_write_service_impl.h:90-99,112-119)
+        return PGS_INVALID_ARGUMENT;
+    }
+    for (uint32_t i = 0; i < n; i++) s.put_one(make_key(bsv(hash_key), bsv(sort_keys[i])), bsv(values[i]), expire_ts, timestamp_us, now);
+    return PGS_OK;
+}
+int32_t pgs_rrdb_multi_remove(pgs_server *h, pgs_blob hash_key, const pgs_blob *sort_keys, uint32_t n, int64_t decree,
+                              int64_t *count)
+{
+    LOCKED(h);
+    Server &s = h->s;
+    s.last_flushed_decree = decree;
+    if (count) *count = 0;
+    if (n == 0) {
+        s.put_one({}, {}, 0, 0, 0);
+        return PGS_INVALID_ARGUMENT;
+    }
+    for (uint32_t i = 0; i < n; i++) s.mem_write(make_key(bsv(hash_key), bsv(sort_keys[i])), PGS_TYPE_DELETION, std::string(), 0);
+    if (count) *count = n;
+    return PGS_OK;
+}
+int32_t pgs_rrdb_flush(pgs_server *h, uint32_t now)
+{
+    LOCKED(h);
+    int32_t st = h->s.flush_mem();
+    if (st != PGS_OK) return st;
+    return h->s.maybe_compact(now);
+}
+int32_t pgs_rrdb_manual_compact(pgs_server *h, uint32_t now, pgs_compact_result *out)
+{
+    LOCKED(h);
+    Server &s = h->s;
+    if (out) memset(out, 0, sizeof *out);
+    int32_t st = s.flush_mem(); // flush_all_family_columns(true), pegasus_server_impl.cpp:3373-3388
+    if (st != PGS_OK) return st;
+    auto rs = s.runs();
+    if (rs.empty()) return PGS_OK;
+    int32_t level = 1;
+    std::vector<uint64_t> ids;
+    for (auto &r : rs) { level = std::max(level, r->level); ids.push_back(r->id); }
+    if (ids.size() > kMaxRuns) { // deeper than one merge launch: fold the oldest runs first
+        while (ids.size() > kMaxRuns) {
+            std::vector<uint64_t> tail(ids.end() - kMaxRuns, ids.end());
+            pgs_filter_params fp = s.filter();
+            pgs_compact_result cr{};
+            st = pgs_compact(s.part, tail.data(), kMaxRuns, level, 1, &fp, now, &cr);
+            if (st != PGS_OK) return st;
+            ids.resize(ids.size() - kMaxRuns);
+            if (cr.new_run_id) ids.push_back(cr.new_run_id);
+        }
+    }
+    pgs_filter_params fp = s.filter();
+    return pgs_compact(s.part, ids.data(), (uint32_t)ids.size(), level, 1, &fp, now, out); // bottommost_level_compaction = force
+}
+int64_t pgs_rrdb_last_flushed_decree(pgs_server *h) { return h->s.last_flushed_decree; }
+
+} // extern "C"

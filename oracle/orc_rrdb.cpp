@@ -129,6 +129,7 @@ struct Server {
     uint64_t last_seq = 0;
     int64_t last_flushed_decree = 0;
     std::map<std::string, Rec> mem;
+    uint64_t mem_bytes = 0;
     struct LRun { int level; Run run; };
     std::vector<LRun> runs; // read order: L0 newest first, then L1, L2, ...
     std::shared_ptr<View> view;
@@ -138,7 +139,7 @@ struct Server {
     Server()
     {
         std::mt19937_64 rng(12345);
-        ctx_counter = (int64_t)(rng() % (2ull << 31)) << 32; // pegasus_scan_context.h:113-114
+        ctx_counter = (int64_t)(rng() % (1ull << 31)) << 32; // pegasus_scan_context.h:113-114 (kept non-negative: the reference's 2^32 range can overflow into the reserved negative ids)
     }
     FilterParams fparams() const
     {
@@ -152,9 +153,18 @@ struct Server {
         fp.ops = &ops;
         return fp;
     }
-    void write(Rec r) { view.reset(); mem[r.ukey] = std::move(r); }
+    void write(Rec r, uint32_t now)
+    {
+        view.reset();
+        mem_bytes += r.ukey.size() + r.value.size() + 16;
+        std::string k = r.ukey;
+        mem[k] = std::move(r);
+        uint64_t cap = opt.memtable_bytes ? opt.memtable_bytes : 64ull << 20;
+        if (mem_bytes >= cap) { flush_mem(); maybe_compact(now); }
+    }
     void flush_mem()
     {
+        mem_bytes = 0;
         if (mem.empty()) return;
         LRun lr{0, {}};
         for (auto &kv : mem) lr.run.recs.push_back(kv.second);
@@ -171,22 +181,32 @@ struct Server {
         runs.erase(runs.begin() + first, runs.begin() + last);
         size_t pos = 0;
         while (pos < runs.size() && runs[pos].level < out_level) pos++;
-        runs.insert(runs.begin() + pos, LRun{out_level, std::move(out)});
+        if (!out.recs.empty()) runs.insert(runs.begin() + pos, LRun{out_level, std::move(out)}); // an empty output installs no run
         view.reset();
+    }
+    void compact_l0(uint32_t now)
+    {
+        size_t last = 0;
+        while (last < runs.size() && runs[last].level <= 1) last++;
+        if (last < 2) return;
+        compact_runs(0, last, 1, now, nullptr);
     }
     void maybe_compact(uint32_t now)
     {
         uint32_t trigger = opt.l0_compaction_trigger ? opt.l0_compaction_trigger : 4;
         size_t l0 = 0;
         while (l0 < runs.size() && runs[l0].level == 0) l0++;
-        if (l0 < trigger) return;
-        size_t last = l0;
-        while (last < runs.size() && runs[last].level == 1) last++;
-        compact_runs(0, last, 1, now, nullptr);
+        if (l0 >= trigger) compact_l0(now);
+    }
+    // the product flushes the memtable before a read (and folds L0 once more than 12 runs pile up);
+    // both steps are invisible in RocksDB terms but the fold runs the compaction filter at `now`.
+    void prepare_read(uint32_t now)
+    {
+        flush_mem();
+        if (runs.size() > 12) compact_l0(now);
     }
     std::shared_ptr<View> get_view()
     {
-        flush_mem(); // mirrors the product: reads see the memtable through an L0 run
         if (view) return view;
         std::vector<const Rec *> all;
         for (auto &lr : runs)
@@ -257,6 +277,7 @@ static inline bool filter_type_supported(int t) { return t >= PGS_FT_NO_FILTER &
 static int32_t on_get(Server &s, sv key, uint32_t now, Resp &r)
 {
     r.reset(s.app_id, s.pidx);
+    s.prepare_read(now);
     std::string value;
     int32_t st = s.db_get(key, &value) ? PGS_OK : PGS_NOT_FOUND;
     if (st == PGS_OK && ts_expired(now, extract_expire_ts(s.data_version, value))) {
@@ -273,6 +294,7 @@ static int32_t on_get(Server &s, sv key, uint32_t now, Resp &r)
 static int32_t on_ttl(Server &s, sv key, uint32_t now, Resp &r)
 {
     r.reset(s.app_id, s.pidx);
+    s.prepare_read(now);
     std::string value;
     int32_t st = s.db_get(key, &value) ? PGS_OK : PGS_NOT_FOUND;
     uint32_t expire_ts = 0;
@@ -295,6 +317,7 @@ static int32_t on_multi_get(Server &s, const pgs_multi_get_request &q, uint32_t 
         r.seal();
         return r.view.error;
     }
+    s.prepare_read(now);
     uint32_t cfg_count = s.opt.rocksdb_multi_get_max_iteration_count ? s.opt.rocksdb_multi_get_max_iteration_count : 3000;
     uint64_t cfg_size = s.opt.rocksdb_multi_get_max_iteration_size ? s.opt.rocksdb_multi_get_max_iteration_size : 30ull << 20;
     uint32_t max_kv_count = cfg_count, max_iteration_count = cfg_count;
@@ -412,6 +435,7 @@ static int32_t on_batch_get(Server &s, const pgs_full_key *keys, uint32_t n, uin
 {
     r.reset(s.app_id, s.pidx);
     if (n == 0) { r.view.error = PGS_INVALID_ARGUMENT; r.seal(); return r.view.error; }
+    s.prepare_read(now);
     for (uint32_t i = 0; i < n; i++) {
         std::string key = generate_key(bsv(keys[i].hash_key), bsv(keys[i].sort_key));
         std::string value;
@@ -431,6 +455,7 @@ static int32_t on_batch_get(Server &s, const pgs_full_key *keys, uint32_t n, uin
 static int32_t on_sortkey_count(Server &s, sv hash_key, uint32_t now, Resp &r)
 {
     r.reset(s.app_id, s.pidx);
+    s.prepare_read(now);
     std::string start = generate_key(hash_key, sv()), stop = next_blob(hash_key);
     Iter it;
     it.v = s.get_view();
@@ -486,6 +511,7 @@ static int32_t on_get_scanner(Server &s, const pgs_get_scanner_request &q, uint3
         r.seal();
         return r.view.error;
     }
+    s.prepare_read(now);
     bool prefix_same_as_start = s.opt.prefix_filter;
     if (s.opt.prefix_filter) {
         sv hk, sk;
@@ -664,7 +690,7 @@ static void put_one(Server &s, sv raw_key, sv user_value, uint32_t expire_ts, ui
     r.seq = ++s.last_seq;
     r.type = PGS_TYPE_VALUE;
     r.value = generate_value(s.data_version, expire_ts, timetag, user_value);
-    s.write(std::move(r));
+    s.write(std::move(r), now);
 }
 static void del_one(Server &s, sv raw_key)
 {
@@ -672,7 +698,7 @@ static void del_one(Server &s, sv raw_key)
     r.ukey = std::string(raw_key);
     r.seq = ++s.last_seq;
     r.type = PGS_TYPE_DELETION;
-    s.write(std::move(r));
+    s.write(std::move(r), 0);
 }
 
 int32_t orc_rrdb_put(orc_server *h, pgs_blob key, pgs_blob value, uint32_t expire_ts, int64_t decree,
