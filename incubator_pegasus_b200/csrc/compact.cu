@@ -243,17 +243,17 @@ PGS_DEV uint32_t dev_filter(const MergeParams &P, const unsigned long long *crc_
 struct TileShared {
     unsigned long long mbar;
     unsigned long long base_bytes;
+    unsigned long long min_seq, max_seq;
     uint32_t base_blocks, base_recs, base_keyb;
     uint32_t tile, error;
     uint32_t in_bytes, n_rec, n_blk_in, n_valid, n_surv, n_ob;
     uint32_t has_lo, has_hi, ulo_len, uhi_len;
     uint32_t tile_bytes, tile_keyb;
-    uint32_t lo[kMaxRuns], nblk[kMaxRuns], nrec[kMaxRuns], in_off[kMaxRuns], rec_base[kMaxRuns], blk_base[kMaxRuns];
-    uint32_t vlo[kMaxRuns], vhi[kMaxRuns];
-    uint32_t scan[33];
-    unsigned long long stat[16];
-    unsigned long long min_seq, max_seq;
     uint32_t max_ukey, max_vlen, max_blk_size, max_blk_rec;
+    uint32_t lo[kMaxRuns], nblk[kMaxRuns], nrec[kMaxRuns], in_off[kMaxRuns], rec_base[kMaxRuns], blk_base[kMaxRuns];
+    uint32_t vlo[kMaxRuns], vhi[kMaxRuns], nabove[kMaxRuns];
+    uint32_t scan[33];
+    uint32_t stat[16];
     uint32_t tb_off[kMaxTileBlocks], tb_size[kMaxTileBlocks], tb_rec[kMaxTileBlocks], tb_nrec[kMaxTileBlocks];
     uint32_t cut[kMaxOutBlocks + 1], ob_off[kMaxOutBlocks + 1], ob_size[kMaxOutBlocks], ob_keyoff[kMaxOutBlocks + 1];
     unsigned long long crc[256];
@@ -266,7 +266,7 @@ struct RecArrays {
     uint8_t *in;
     uint8_t *arena;
     unsigned long long *trailer;
-    uint32_t *voff, *vlen, *newts, *R, *E;
+    uint32_t *voff, *vlen, *koff, *R, *E;
     uint16_t *klen, *rank, *order, *surv, *shr, *blkid;
     uint8_t *flags;
     uint32_t total;
@@ -281,7 +281,7 @@ PGS_DEV RecArrays carve(uint8_t *pool, uint32_t in_bytes, uint32_t n, uint32_t K
     a.trailer = (unsigned long long *)(pool + off); off += n8 * 8;
     a.voff = (uint32_t *)(pool + off); off += n8 * 4;
     a.vlen = (uint32_t *)(pool + off); off += n8 * 4;
-    a.newts = (uint32_t *)(pool + off); off += n8 * 4;
+    a.koff = (uint32_t *)(pool + off); off += n8 * 4;
     a.R = (uint32_t *)(pool + off); off += n8 * 4;
     a.E = (uint32_t *)(pool + off); off += n8 * 4;
     a.klen = (uint16_t *)(pool + off); off += n8 * 2;
@@ -295,17 +295,17 @@ PGS_DEV RecArrays carve(uint8_t *pool, uint32_t in_bytes, uint32_t n, uint32_t K
     return a;
 }
 
-// exclusive scan of f(i), i in [0,n), into out[0..n] (out[n] = total); all threads call it.
+// exclusive scan of f(i), i in [0,n), into out[0..n] (out[n] = total); f is evaluated once per element.
 template <class F>
 PGS_DEV uint32_t chunked_scan(uint32_t n, uint32_t *out, uint32_t *scratch, F f)
 {
     uint32_t ipt = (n + blockDim.x - 1) / blockDim.x;
     uint32_t begin = min(threadIdx.x * ipt, n), end = min(begin + ipt, n);
     uint32_t local = 0;
-    for (uint32_t i = begin; i < end; i++) local += f(i);
+    for (uint32_t i = begin; i < end; i++) { uint32_t v = f(i); out[i] = v; local += v; }
     uint32_t total;
     uint32_t pre = block_excl_scan(local, scratch, &total);
-    for (uint32_t i = begin; i < end; i++) { uint32_t v = f(i); out[i] = pre; pre += v; }
+    for (uint32_t i = begin; i < end; i++) { uint32_t v = out[i]; out[i] = pre; pre += v; }
     if (threadIdx.x == 0) out[n] = total;
     __syncthreads();
     return total;
@@ -321,6 +321,8 @@ PGS_DEV void publish(TileAgg *slot, unsigned long long bytes, uint32_t blocks, u
     *(volatile uint32_t *)&slot->flag = 1;
 }
 
+PGS_DEV uint32_t varint_byte(uint32_t v, uint32_t j, uint32_t len) { return ((v >> (7 * j)) & 0x7fu) | (j + 1 < len ? 0x80u : 0u); }
+
 __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__ MergeParams P)
 {
     extern __shared__ __align__(128) uint8_t dyn[];
@@ -328,8 +330,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t KS = P.KS, RI = P.restart_interval;
     uint8_t *ulo = dyn, *uhi = dyn + KS + 8;
-    uint8_t *wscr = dyn + 2 * (KS + 8) + warp * P.warp_scratch;
-    uint8_t *pool = dyn + 2 * (KS + 8) + kMergeWarps * P.warp_scratch;
+    uint8_t *pool = dyn + 2 * (KS + 8);
 
     if (tid == 0) {
         mbar_init((uint64_t *)&S.mbar, 1);
@@ -343,7 +344,8 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
     for (;;) {
         if (tid == 0) S.tile = atomicAdd(P.ticket, 1u);
         if (tid < 16) S.stat[tid] = 0;
-        if (tid == 32) { S.error = 0; S.min_seq = ~0ull; S.max_seq = 0; S.max_ukey = 0; S.max_vlen = 0; S.max_blk_size = 0; S.max_blk_rec = 0; }
+        if (tid >= 32 && tid < 32 + kMaxRuns) { S.vlo[tid - 32] = 0; S.nabove[tid - 32] = 0; }
+        if (tid == 64) { S.error = 0; S.min_seq = ~0ull; S.max_seq = 0; S.max_ukey = 0; S.max_vlen = 0; S.max_blk_size = 0; S.max_blk_rec = 0; }
         __syncthreads();
         const uint32_t tile = S.tile;
         if (tile >= P.Q) break;
@@ -382,6 +384,11 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
             if (a0.total > P.pool_bytes || blks > kMaxTileBlocks || recs > 65000) atomicMax(&S.error, (uint32_t)PGS_ABORTED);
             S.has_lo = !first;
             S.has_hi = !last;
+            if (!S.error && P.use_tma) {
+                // generic-proxy writes of the previous tile precede async-proxy writes to the same bytes
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (bytes) mbar_expect_tx((uint64_t *)&S.mbar, bytes); // the copies are issued right after the barrier
+            }
         }
         __syncthreads();
         const RecArrays A = carve(pool, S.in_bytes, S.n_rec, KS);
@@ -389,9 +396,6 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
         if (tile_ok) {
             if (P.use_tma) {
                 if (tid == 0) {
-                    // generic-proxy writes of the previous tile precede async-proxy writes to the same bytes
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    if (S.in_bytes) mbar_expect_tx((uint64_t *)&S.mbar, S.in_bytes);
                     for (uint32_t j = 0; j < P.k; j++) {
                         uint32_t bytes = (j + 1 < P.k ? S.in_off[j + 1] : S.in_bytes) - S.in_off[j];
                         if (bytes) tma_load_1d(A.in + S.in_off[j], P.runs[j].data + P.runs[j].blk_off[S.lo[j]], bytes, (uint64_t *)&S.mbar);
@@ -434,9 +438,10 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
         }
         __syncthreads();
 
-        // ---- decode: one warp per block ---------------------------------------------------------
+        // ---- decode step 1: one THREAD per block walks the entry headers --------------------------
+        // (entries are sequential inside a block; blocks are independent: 32 blocks advance per warp instruction)
         if (tile_ok) {
-            for (uint32_t t = warp; t < S.n_blk_in; t += kMergeWarps) {
+            for (uint32_t t = tid; t < S.n_blk_in; t += kMergeThreads) {
                 const uint8_t *base = A.in + S.tb_off[t];
                 uint32_t size = S.tb_size[t], rec0 = S.tb_rec[t], expect = S.tb_nrec[t];
                 uint32_t err = 0, nr = 0;
@@ -453,60 +458,84 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
                     h += c;
                     if (c) { c = get_varint32(base + p + h, limit - p - h, non_shared); h += c; }
                     if (c) { c = get_varint32(base + p + h, limit - p - h, vlen); h += c; }
-                    if (!c) { err = PGS_CORRUPTION; break; }
                     uint32_t klen = shared + non_shared;
-                    if (shared > prev_klen || klen < 8 || klen - 8 > KS || (unsigned long long)p + h + non_shared + vlen > limit) {
+                    if (!c || shared > prev_klen || klen < 8 || klen - 8 > KS || (unsigned long long)p + h + non_shared + vlen > limit) {
                         err = PGS_CORRUPTION;
                         break;
                     }
-                    for (uint32_t x = lane; x < non_shared; x += 32) wscr[shared + x] = base[p + h + x];
-                    __syncwarp();
-                    uint32_t ulen = klen - 8, r = rec0 + i;
-                    uint32_t words = (ulen + 7) >> 3;
-                    for (uint32_t w = lane; w < words; w += 32) {
-                        unsigned long long v = *(const unsigned long long *)(wscr + 8 * w);
-                        uint32_t keep = ulen - 8 * w;
-                        if (keep < 8) v &= (1ull << (8 * keep)) - 1;
-                        *(unsigned long long *)(A.arena + (size_t)r * KS + 8 * w) = v;
-                    }
-                    if (lane == 0) {
-                        unsigned long long tr = 0;
-                        for (int x = 7; x >= 0; x--) tr = (tr << 8) | wscr[ulen + x];
-                        A.trailer[r] = tr;
-                        A.klen[r] = (uint16_t)ulen;
-                        A.voff[r] = S.tb_off[t] + p + h + non_shared;
-                        A.vlen[r] = vlen;
-                        A.flags[r] = 0;
-                    }
-                    __syncwarp();
+                    uint32_t r = rec0 + i;
+                    A.rank[r] = (uint16_t)shared;      // scratch until the rank phase
+                    A.order[r] = (uint16_t)non_shared; // scratch until the scatter phase
+                    A.koff[r] = S.tb_off[t] + p + h;
+                    A.klen[r] = (uint16_t)(klen - 8);
+                    A.voff[r] = S.tb_off[t] + p + h + non_shared;
+                    A.vlen[r] = vlen;
+                    A.trailer[r] = 0;
                     prev_klen = klen;
                     p += h + non_shared + vlen;
                     i++;
                 }
                 if (!err && (i != expect || p != limit)) err = PGS_CORRUPTION;
-                if (err && lane == 0) atomicMax(&S.error, err);
+                if (err) atomicMax(&S.error, err);
             }
         }
         __syncthreads();
         tile_ok = S.error == 0;
 
-        // ---- valid range of every run's slice: user keys in (U_lo, U_hi] ---------------------------
-        if (tile_ok && tid < P.k) {
-            uint32_t n = S.nrec[tid], base = S.rec_base[tid];
-            uint32_t vlo = 0, vhi = n;
-            for (uint32_t which = 0; which < 2; which++) {
-                if (which == 0 ? !S.has_lo : !S.has_hi) continue;
-                const uint8_t *U = which == 0 ? ulo : uhi;
-                uint32_t ul = which == 0 ? S.ulo_len : S.uhi_len;
-                uint32_t lo = 0, hi = n; // #records with ukey <= U
-                while (lo < hi) {
-                    uint32_t mid = (lo + hi) >> 1;
-                    if (cmp_slots(A.arena + (size_t)(base + mid) * KS, A.klen[base + mid], U, ul) <= 0) lo = mid + 1; else hi = mid;
+        // ---- decode step 2: one WARP per block rebuilds the keys, two key bytes per lane -------------
+        // lane L owns internal-key positions 2L and 2L+1 (+64 per pass): the running value of a position is the
+        // byte last written by an entry whose shared prefix ends at or before it.
+        if (tile_ok) {
+            for (uint32_t t = warp; t < S.n_blk_in; t += kMergeWarps) {
+                const uint32_t rec0 = S.tb_rec[t], nrec = S.tb_nrec[t];
+                uint32_t maxk = 0;
+                for (uint32_t i = lane; i < nrec; i += 32) maxk = max(maxk, (uint32_t)A.klen[rec0 + i] + 8);
+                maxk = __reduce_max_sync(kFull, maxk);
+                for (uint32_t pass = 0; pass * 64 < maxk; pass++) {
+                    const uint32_t p0 = pass * 64 + 2 * lane, p1 = p0 + 1;
+                    uint32_t c0 = 0, c1 = 0;
+                    for (uint32_t i = 0; i < nrec; i++) {
+                        const uint32_t r = rec0 + i;
+                        const uint32_t sh = A.rank[r], ns = A.order[r], ulen = A.klen[r];
+                        const uint8_t *d = A.in + A.koff[r];
+                        if (p0 >= sh && p0 < sh + ns) c0 = d[p0 - sh];
+                        if (p1 >= sh && p1 < sh + ns) c1 = d[p1 - sh];
+                        const uint32_t pad = (ulen + 7) & ~7u; // slots are zero padded to 8 bytes
+                        if (p0 < pad) {
+                            uint32_t b0 = p0 < ulen ? c0 : 0, b1 = p1 < ulen ? c1 : 0;
+                            *(uint16_t *)(A.arena + (size_t)r * KS + p0) = (uint16_t)(b0 | (b1 << 8));
+                        }
+                        // the 8 bytes after the user key are the (seq<<8|type) trailer, little endian
+                        uint32_t lo = 0, hi = 0;
+                        if (p0 >= ulen && p0 < ulen + 8) { uint32_t j = p0 - ulen; if (j < 4) lo |= c0 << (8 * j); else hi |= c0 << (8 * (j - 4)); }
+                        if (p1 >= ulen && p1 < ulen + 8) { uint32_t j = p1 - ulen; if (j < 4) lo |= c1 << (8 * j); else hi |= c1 << (8 * (j - 4)); }
+                        if (pass * 64 < ulen + 8 && pass * 64 + 64 > ulen) {
+                            lo = __reduce_or_sync(kFull, lo);
+                            hi = __reduce_or_sync(kFull, hi);
+                            if (lane == 0) A.trailer[r] |= ((unsigned long long)hi << 32) | lo;
+                        }
+                    }
                 }
-                if (which == 0) vlo = lo; else vhi = lo;
             }
-            if (vhi < vlo) vhi = vlo;
-            S.vlo[tid] = vlo;
+        }
+        __syncthreads();
+
+        // ---- valid range of every run's slice: user keys in (U_lo, U_hi]; records at or below U_lo form a
+        //      prefix of a slice, records above U_hi a suffix, so counting them gives the window -----------
+        if (tile_ok) {
+            for (uint32_t r = tid; r < S.n_rec; r += kMergeThreads) {
+                uint32_t j = 0;
+                while (j + 1 < P.k && r >= S.rec_base[j + 1]) j++;
+                const uint8_t *key = A.arena + (size_t)r * KS;
+                uint32_t kl = A.klen[r];
+                if (S.has_lo && cmp_slots(key, kl, ulo, S.ulo_len) <= 0) atomicAdd(&S.vlo[j], 1u);
+                else if (S.has_hi && cmp_slots(key, kl, uhi, S.uhi_len) > 0) atomicAdd(&S.nabove[j], 1u);
+            }
+        }
+        __syncthreads();
+        if (tile_ok && tid < P.k) {
+            uint32_t vhi = S.nrec[tid] - S.nabove[tid];
+            if (vhi < S.vlo[tid]) vhi = S.vlo[tid];
             S.vhi[tid] = vhi;
         }
         __syncthreads();
@@ -549,7 +578,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
                         if (A.klen[q] == kl && cmp_slots(A.arena + (size_t)q * KS, kl, key, kl) == 0) shadow = true;
                     }
                 }
-                A.rank[r] = (uint16_t)rank;
+                A.shr[r] = (uint16_t)rank; // rank[] / order[] still hold decode scratch of other records' neighbours: use shr
                 A.flags[r] = F_VALID | (shadow ? F_SHADOW : 0);
             }
         }
@@ -557,14 +586,14 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
 
         // ---- compaction filter + tombstone policy; scatter into merged order -----------------------------
         if (tile_ok) {
-            unsigned long long s_in = 0, s_inb = 0, s_sh = 0, s_tomb = 0, s_exp = 0, s_user = 0, s_stale = 0, s_ttl = 0;
+            uint32_t s_in = 0, s_inb = 0, s_sh = 0, s_tomb = 0, s_exp = 0, s_user = 0, s_stale = 0, s_ttl = 0;
             for (uint32_t r = tid; r < S.n_rec; r += kMergeThreads) {
                 uint8_t f = A.flags[r];
                 if (!(f & F_VALID)) continue;
                 uint32_t kl = A.klen[r], vl = A.vlen[r];
                 s_in++;
                 s_inb += kl + vl;
-                A.order[A.rank[r]] = (uint16_t)r;
+                A.order[A.shr[r]] = (uint16_t)r;
                 if (f & F_SHADOW) { s_sh++; continue; }
                 uint8_t type = (uint8_t)A.trailer[r];
                 if (type == PGS_TYPE_VALUE) {
@@ -590,18 +619,25 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
                 }
                 A.flags[r] = f;
             }
-            atomicAdd(&S.stat[ST_IN_REC], s_in);
-            atomicAdd(&S.stat[ST_IN_BYTES], s_inb);
-            atomicAdd(&S.stat[ST_SHADOW], s_sh);
-            atomicAdd(&S.stat[ST_TOMB], s_tomb);
-            atomicAdd(&S.stat[ST_EXPIRED], s_exp);
-            atomicAdd(&S.stat[ST_USER], s_user);
-            atomicAdd(&S.stat[ST_STALE], s_stale);
-            atomicAdd(&S.stat[ST_TTL], s_ttl);
+            // one shared-memory atomic per warp and counter (a tile's counts fit 32 bits)
+            s_in = __reduce_add_sync(kFull, s_in); s_inb = __reduce_add_sync(kFull, s_inb);
+            s_sh = __reduce_add_sync(kFull, s_sh); s_tomb = __reduce_add_sync(kFull, s_tomb);
+            s_exp = __reduce_add_sync(kFull, s_exp); s_user = __reduce_add_sync(kFull, s_user);
+            s_stale = __reduce_add_sync(kFull, s_stale); s_ttl = __reduce_add_sync(kFull, s_ttl);
+            if (lane == 0) {
+                if (s_in) atomicAdd(&S.stat[ST_IN_REC], s_in);
+                if (s_inb) atomicAdd(&S.stat[ST_IN_BYTES], s_inb);
+                if (s_sh) atomicAdd(&S.stat[ST_SHADOW], s_sh);
+                if (s_tomb) atomicAdd(&S.stat[ST_TOMB], s_tomb);
+                if (s_exp) atomicAdd(&S.stat[ST_EXPIRED], s_exp);
+                if (s_user) atomicAdd(&S.stat[ST_USER], s_user);
+                if (s_stale) atomicAdd(&S.stat[ST_STALE], s_stale);
+                if (s_ttl) atomicAdd(&S.stat[ST_TTL], s_ttl);
+            }
         }
         __syncthreads();
 
-        // ---- survivors in merged order ---------------------------------------------------------------------
+        // ---- survivors in merged order, output block layout ---------------------------------------------------
         uint32_t m = 0;
         if (tile_ok) {
             const uint32_t nv = S.n_valid;
@@ -611,22 +647,21 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
                 if (A.flags[r] & F_KEEP) A.surv[A.E[p]] = (uint16_t)r;
             }
             __syncthreads();
-            // raw sizes decide the block cuts (a block closes once it holds >= block_size raw bytes)
+            // raw sizes decide the block cuts: an entry starts a new block when its raw offset enters the next
+            // block_size window (blocks hold ~block_size raw bytes; every entry's block is known in parallel)
             chunked_scan(m, A.R, S.scan, [&](uint32_t p) -> uint32_t { uint32_t r = A.surv[p]; return A.klen[r] + 8u + A.vlen[r] + 3u; });
-            if (tid == 0) {
-                uint32_t nb = 0, pos = 0;
-                S.cut[0] = 0;
-                while (pos < m && nb < kMaxOutBlocks) {
-                    uint32_t target = A.R[pos] + P.block_size;
-                    uint32_t lo = pos + 1, hi = m;
-                    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (A.R[mid] >= target) hi = mid; else lo = mid + 1; }
-                    pos = lo;
-                    S.cut[++nb] = pos;
-                }
-                if (pos < m) atomicMax(&S.error, (uint32_t)PGS_ABORTED);
-                S.n_ob = nb;
-                S.n_surv = m;
+            const uint32_t BS = P.block_size;
+            uint32_t nob = chunked_scan(m, A.E, S.scan, [&](uint32_t p) -> uint32_t {
+                return (p == 0 || A.R[p] / BS != A.R[p - 1] / BS) ? 1u : 0u;
+            });
+            if (nob > kMaxOutBlocks) { if (tid == 0) atomicMax(&S.error, (uint32_t)PGS_ABORTED); nob = 0; }
+            for (uint32_t p = tid; p < m; p += kMergeThreads) {
+                bool firstp = p == 0 || A.R[p] / BS != A.R[p - 1] / BS;
+                uint32_t b = A.E[p] + (firstp ? 1u : 0u) - 1u; // E = exclusive count of block starts before p
+                A.blkid[p] = (uint16_t)b;
+                if (firstp && b < kMaxOutBlocks) S.cut[b] = p;
             }
+            if (tid == 0) { S.cut[nob] = m; S.n_ob = nob; S.n_surv = m; }
             __syncthreads();
             tile_ok = S.error == 0;
         }
@@ -634,38 +669,35 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
             const uint32_t nob = S.n_ob;
             // prefix compression against the previous survivor + encoded sizes
             chunked_scan(m, A.E, S.scan, [&](uint32_t p) -> uint32_t {
-                uint32_t lo = 0, hi = nob; // last cut <= p
-                while (lo + 1 < hi) { uint32_t mid = (lo + hi) >> 1; if (S.cut[mid] <= p) lo = mid; else hi = mid; }
+                uint32_t b = A.blkid[p];
                 uint32_t r = A.surv[p], kl = A.klen[r], shared = 0;
-                if ((p - S.cut[lo]) % RI != 0) {
+                if ((p - S.cut[b]) % RI != 0) {
                     uint32_t q = A.surv[p - 1];
                     shared = lcp_slots(A.arena + (size_t)q * KS, A.klen[q], A.arena + (size_t)r * KS, kl);
                 }
                 A.shr[p] = (uint16_t)shared;
-                A.blkid[p] = (uint16_t)lo;
                 uint32_t ns = kl + 8 - shared, vl = A.vlen[r];
                 return varint_len(shared) + varint_len(ns) + varint_len(vl) + ns + vl;
             });
-            if (tid < nob) {
-                uint32_t cnt = S.cut[tid + 1] - S.cut[tid];
-                uint32_t nrest = (cnt + RI - 1) / RI;
-                S.ob_size[tid] = A.E[S.cut[tid + 1]] - A.E[S.cut[tid]] + 4 * (nrest + 1);
-            }
-            __syncthreads();
-            if (tid == 0) {
+            if (warp == 0) { // block sizes, 16-byte aligned offsets and index-key offsets: one warp, shuffle scans
                 uint32_t off = 0, koff = 0;
-                for (uint32_t b = 0; b < nob; b++) {
-                    S.ob_off[b] = off;
-                    S.ob_keyoff[b] = koff;
-                    off += (S.ob_size[b] + kBlockAlign - 1) & ~(kBlockAlign - 1);
-                    koff += A.klen[A.surv[S.cut[b + 1] - 1]];
+                for (uint32_t b0 = 0; b0 < nob; b0 += 32) {
+                    uint32_t b = b0 + lane, sz = 0, al = 0, kl = 0;
+                    if (b < nob) {
+                        uint32_t cnt = S.cut[b + 1] - S.cut[b];
+                        uint32_t nrest = (cnt + RI - 1) / RI;
+                        sz = A.E[S.cut[b + 1]] - A.E[S.cut[b]] + 4 * (nrest + 1);
+                        al = (sz + kBlockAlign - 1) & ~(kBlockAlign - 1);
+                        kl = A.klen[A.surv[S.cut[b + 1] - 1]];
+                        S.ob_size[b] = sz;
+                    }
+                    uint32_t ia = warp_incl_scan(al, lane), ik = warp_incl_scan(kl, lane);
+                    if (b < nob) { S.ob_off[b] = off + ia - al; S.ob_keyoff[b] = koff + ik - kl; }
+                    off += __shfl_sync(kFull, ia, 31);
+                    koff += __shfl_sync(kFull, ik, 31);
                 }
-                S.ob_off[nob] = off;
-                S.ob_keyoff[nob] = koff;
-                S.tile_bytes = off;
-                S.tile_keyb = koff;
+                if (lane == 0) { S.ob_off[nob] = off; S.ob_keyoff[nob] = koff; S.tile_bytes = off; S.tile_keyb = koff; }
             }
-            __syncthreads();
         } else if (tid == 0) {
             S.n_ob = 0; S.n_surv = 0; S.tile_bytes = 0; S.tile_keyb = 0;
         }
@@ -723,43 +755,40 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
         if (tile_ok && m > 0) {
             const uint32_t nob = S.n_ob;
             uint8_t *out = P.out_data + S.base_bytes;
-            unsigned long long s_outb = 0, s_otomb = 0, s_okey = 0, s_oval = 0, mn_seq = ~0ull, mx_seq = 0;
-            uint32_t mx_k = 0, mx_v = 0;
+            uint32_t s_outb = 0, s_otomb = 0, s_okey = 0, s_oval = 0, mx_k = 0, mx_v = 0;
+            unsigned long long mn_seq = ~0ull, mx_seq = 0;
             for (uint32_t p = warp; p < m; p += kMergeWarps) {
-                uint32_t r = A.surv[p], b = A.blkid[p];
-                uint32_t kl = A.klen[r], vl = A.vlen[r], shared = A.shr[p];
-                uint8_t f = A.flags[r];
-                unsigned long long tr = A.trailer[r];
-                uint8_t type = (f & F_TOMB) ? (uint8_t)PGS_TYPE_DELETION : (uint8_t)tr;
-                unsigned long long seq = (P.bottommost && type == PGS_TYPE_VALUE) ? 0ull : (tr >> 8);
-                unsigned long long otr = (seq << 8) | type;
-                uint32_t ns = kl + 8 - shared;
-                uint32_t h = 0;
-                if (lane == 0) {
-                    h = put_varint32(wscr, shared);
-                    h += put_varint32(wscr + h, ns);
-                    h += put_varint32(wscr + h, vl);
-                }
-                h = __shfl_sync(kFull, h, 0);
-                const uint8_t *ks = A.arena + (size_t)r * KS + shared;
-                for (uint32_t x = lane; x < kl - shared; x += 32) wscr[h + x] = ks[x];
-                if (lane < 8) wscr[h + kl - shared + lane] = (uint8_t)(otr >> (8 * lane));
-                __syncwarp();
+                const uint32_t r = A.surv[p], b = A.blkid[p];
+                const uint32_t kl = A.klen[r], vl = A.vlen[r], shared = A.shr[p];
+                const uint8_t f = A.flags[r];
+                const unsigned long long tr = A.trailer[r];
+                const uint8_t type = (f & F_TOMB) ? (uint8_t)PGS_TYPE_DELETION : (uint8_t)tr;
+                const unsigned long long seq = (P.bottommost && type == PGS_TYPE_VALUE) ? 0ull : (tr >> 8);
+                const unsigned long long otr = (seq << 8) | type;
+                const uint32_t kd = kl - shared, ns = kd + 8;
+                const uint32_t l1 = varint_len(shared), l2 = varint_len(ns), l3 = varint_len(vl);
+                const uint32_t h = l1 + l2 + l3, hs = h + ns;
                 uint8_t *dst = out + S.ob_off[b] + (A.E[p] - A.E[S.cut[b]]);
-                uint32_t hs = h + ns;
-                warp_copy_s2g(dst, wscr, hs, lane);
-                warp_copy_s2g(dst + hs, A.in + A.voff[r], vl, lane);
-                __syncwarp();
-                if (lane == 0) {
-                    s_outb += kl + vl;
-                    s_otomb += type == PGS_TYPE_DELETION;
-                    s_okey += kl;
-                    s_oval += vl;
-                    mx_k = max(mx_k, kl);
-                    mx_v = max(mx_v, vl);
-                    mn_seq = seq < mn_seq ? seq : mn_seq;
-                    mx_seq = seq > mx_seq ? seq : mx_seq;
+                const uint8_t *ksrc = A.arena + (size_t)r * KS + shared;
+                // entry head = 3 varints | key delta | trailer: every lane produces one byte, stores coalesce
+                for (uint32_t i = lane; i < hs; i += 32) {
+                    uint32_t v;
+                    if (i < l1) v = varint_byte(shared, i, l1);
+                    else if (i < l1 + l2) v = varint_byte(ns, i - l1, l2);
+                    else if (i < h) v = varint_byte(vl, i - l1 - l2, l3);
+                    else if (i < h + kd) v = ksrc[i - h];
+                    else v = (uint32_t)(otr >> (8 * (i - h - kd))) & 0xffu;
+                    dst[i] = (uint8_t)v;
                 }
+                warp_copy_s2g(dst + hs, A.in + A.voff[r], vl, lane);
+                s_outb += kl + vl;
+                s_otomb += type == PGS_TYPE_DELETION;
+                s_okey += kl;
+                s_oval += vl;
+                mx_k = max(mx_k, kl);
+                mx_v = max(mx_v, vl);
+                mn_seq = seq < mn_seq ? seq : mn_seq;
+                mx_seq = seq > mx_seq ? seq : mx_seq;
             }
             if (lane == 0) {
                 atomicAdd(&S.stat[ST_OUT_BYTES], s_outb);
@@ -811,7 +840,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
             static_assert(ST_OUT_VAL == 12, "stat layout");
             // MergeStats starts with in_records,in_bytes,out_records,out_bytes,dropped_shadowed,dropped_tombstone,
             // dropped_expired,dropped_user,dropped_stale,ttl_rewritten,out_tomb,out_raw_key,out_raw_val
-            atomicAdd(g + tid, S.stat[tid]);
+            atomicAdd(g + tid, (unsigned long long)S.stat[tid]);
         }
         if (tid == 0) {
             if (S.error) {
@@ -923,7 +952,7 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     cudaFuncAttributes attr;
     PGS_CUDA(cudaFuncGetAttributes(&attr, k_merge));
     uint32_t ctas = e->cfg.ctas_per_sm;
-    const uint32_t fixed_dyn = 2 * (KS + 8) + kMergeWarps * P.warp_scratch;
+    const uint32_t fixed_dyn = 2 * (KS + 8);
     const uint64_t maxw = (((uint64_t)max_blk + 15) & ~15ull) + 16 + (uint64_t)max_blk_rec * P.rec_cost;
     uint32_t dyn = 0;
     uint64_t T = 0;

@@ -331,9 +331,10 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t KS = P.KS, NR = P.rr.n;
     // bounds of the current chunk, zero padded slots: lo = exclusive/inclusive lower, hi = upper
-    uint8_t *klo = dyn, *khi = dyn + KS + 8, *kpre = dyn + 2 * (KS + 8);
-    uint8_t *wscr = dyn + 3 * (KS + 8) + warp * P.warp_scratch;
-    uint8_t *pool = dyn + 3 * (KS + 8) + kScanWarps * P.warp_scratch;
+    const uint32_t slot = (KS + 8 + 15) & ~15u; // keeps `pool` (the TMA destination) 16-byte aligned
+    uint8_t *klo = dyn, *khi = dyn + slot, *kpre = dyn + 2 * slot;
+    uint8_t *wscr = dyn + 3 * slot + warp * P.warp_scratch;
+    uint8_t *pool = dyn + 3 * slot + kScanWarps * P.warp_scratch;
 
     if (tid == 0) { mbar_init((uint64_t *)&S.mbar, 1); mbar_fence_init(); }
     __syncthreads();
@@ -944,7 +945,7 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
     cudaFuncAttributes attr;
     PGS_CUDA(cudaFuncGetAttributes(&attr, k_scan));
     P.warp_scratch = (P.KS + 48 + 15) & ~15u;
-    uint32_t fixed_dyn = 3 * (P.KS + 8) + kScanWarps * P.warp_scratch;
+    uint32_t fixed_dyn = 3 * ((P.KS + 8 + 15) & ~15u) + kScanWarps * P.warp_scratch;
     uint32_t max_blk = 0, max_rec = 0;
     for (auto &r : runs) { max_blk = std::max(max_blk, r->info.max_block_size); max_rec = std::max(max_rec, r->info.max_block_records); }
     uint64_t one = (((uint64_t)max_blk + 15) & ~15ull) + 32 + (uint64_t)max_rec * (P.KS + kScanRecExtra);
