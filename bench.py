@@ -86,15 +86,42 @@ def gen_runs(records_per_run: int, seed: int):
                                  seed=seed)
 
 
-def cpu_compaction(runs, threads: int):
+def cpu_block_runs(runs):
+    """block-encode the sample for the CPU path (setup, not timed)."""
+    import oracle_py as orc
+    return [orc.BlockRunCPU.from_run(orc.Run.from_records(r)) for r in runs]
+
+
+def cpu_compaction(bruns, threads: int):
     """oracle block-level compaction on host cores; returns (merged GB/s, seconds, in_bytes)."""
     import oracle_py as orc
-    oruns = [orc.Run.from_records(r) for r in runs]
-    bruns = [orc.BlockRunCPU.from_run(o) for o in oruns]
-    del oruns
     fp = orc.filter_params(enabled=True)
     _out, st, secs = orc.compact_blocks(bruns, True, fp, NOW, threads)
     return st.in_bytes / secs / 1e9, secs, int(st.in_bytes)
+
+
+def zipf_ids(rng, n_items: int, n: int, theta: float = 0.99):
+    """YCSB zipfian(theta) over n_items, scrambled."""
+    w = 1.0 / np.power(np.arange(1, n_items + 1, dtype=np.float64), theta)
+    cdf = np.cumsum(w)
+    cdf /= cdf[-1]
+    ranks = np.searchsorted(cdf, rng.random(n))
+    perm = rng.permutation(n_items)
+    return perm[np.minimum(ranks, n_items - 1)]
+
+
+def read_workload(records_per_run: int, n_get: int, n_scan: int, seed: int):
+    """keys of the read legs: zipfian hash keys of the synthetic data set; gets pick a random sort key."""
+    from incubator_pegasus_b200 import synth
+    rng = np.random.default_rng(seed + 77)
+    per_run_hash = (int(records_per_run * 0.9) + 63) // 64  # own hash keys of runs 1.. (synth.compaction_runs)
+    n_hash = (records_per_run + 63) // 64 + (RUNS - 1) * per_run_hash
+    gh = zipf_ids(rng, n_hash, n_get).astype(np.uint64)
+    gs = rng.integers(0, 64, n_get).astype(np.uint64)
+    get_keys = synth.make_keys(gh, gs, HK, SK, seed)
+    sh = zipf_ids(rng, n_hash, n_scan).astype(np.uint64)
+    scan_keys = synth.make_keys(sh, np.zeros(n_scan, np.uint64), HK, SK, seed)[:, 2:2 + HK]
+    return get_keys, scan_keys
 
 
 def reference_arm(args, rank: int, world: int):
@@ -102,11 +129,11 @@ def reference_arm(args, rank: int, world: int):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = min(args.records_per_run, args.cpu_sample_records)
-    runs = gen_runs(sample, 1000)
+    sample = min(args.records_per_run, args.cpu_sample_records or max(250_000, 20_000 * threads))
+    bruns = cpu_block_runs(gen_runs(sample, 1000))
     vals = []
     for _ in range(args.warmup + args.steps):
-        gbs, secs, in_bytes = cpu_compaction(runs, threads)
+        gbs, secs, in_bytes = cpu_compaction(bruns, threads)
         vals.append((gbs, secs))
     timed = vals[args.warmup:]
     ms = 1e3 * sum(s for _, s in timed) / len(timed)
@@ -130,11 +157,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--records-per-run", type=int, default=2_500_000)
-    ap.add_argument("--cpu-sample-records", type=int, default=500_000)
+    ap.add_argument("--cpu-sample-records", type=int, default=0, help="records per run of the CPU sample; 0 = scale with cores")
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--no-tma", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-reads", action="store_true")
+    ap.add_argument("--n-get", type=int, default=262144)
+    ap.add_argument("--n-scan", type=int, default=16384)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -241,6 +271,77 @@ def main():
                "timed": "host wall clock around upload(4 runs)+compact, barrier+synchronize both sides"}
         part2.close()
 
+    # ---- read path on the same partition (4 overlapping runs resident): YCSB-C shaped, zipfian hash keys ----------
+    reads = None
+    if not args.skip_reads:
+        gk, sk = read_workload(args.records_per_run, args.n_get, args.n_scan, 1000 + rank)
+        gkeys = np.ascontiguousarray(gk.reshape(-1))
+        goff = (np.arange(args.n_get + 1, dtype=np.uint32) * np.uint32(gk.shape[1]))
+        hashkeys = [bytes(r) for r in sk]
+        garena_cap = args.n_get * (VAL + 8)
+        reps = max(3, args.steps)
+        # gets
+        part.get_batch(gkeys, goff, NOW, arena_cap=garena_cap)
+        g_ms, g_wall, found, probes = [], [], 0, 0
+        for _ in range(reps):
+            barrier()
+            t0 = time.perf_counter()
+            st, gres, garena, gused = part.get_batch(gkeys, goff, NOW, arena_cap=garena_cap)
+            g_wall.append((time.perf_counter() - t0) * 1e3)
+            g_ms.append(eng.last_kernel_ms)
+            probes = eng.last_blocks_probed
+        found = sum(1 for i in range(0, args.n_get, max(1, args.n_get // 4096)) if gres[i].status == 0)
+        found_frac = found / len(range(0, args.n_get, max(1, args.n_get // 4096)))
+        # prefix scans = multi_get(hash_key, all sort keys)
+        arena = np.zeros(args.n_scan * 24576, np.uint8)
+        kvs = np.zeros(args.n_scan * 80 * 5, np.uint32)
+        part.prefix_scan_many(hashkeys[:256], NOW, max_records=80, arena_stride=24576, arena=arena, kvs=kvs)
+        s_ms, s_wall = [], []
+        for _ in range(reps):
+            barrier()
+            t0 = time.perf_counter()
+            st, sres, _a, _k, abase, kbase = part.prefix_scan_many(hashkeys, NOW, max_records=80, arena_stride=24576, arena=arena, kvs=kvs)
+            s_wall.append((time.perf_counter() - t0) * 1e3)
+            s_ms.append(eng.last_kernel_ms)
+            assert st == 0, st
+        returned = int(kbase[-1])
+        iterated = int(sum(sres[i].iter_count for i in range(args.n_scan)))
+        scan_bytes = int(abase[-1])
+        gm, sm = sum(g_ms) / len(g_ms), sum(s_ms) / len(s_ms)
+        nb_log = 18
+        get_algo = probes * (4096 + nb_log * 58) + args.n_get * (2 + HK + SK) + int(gused)
+        scan_algo = returned * 2 * (2 + HK + SK + 12 + VAL) + (iterated - returned) * (2 + HK + SK + 12 + VAL)
+        vals = torch.tensor([args.n_get / (gm / 1e3), args.n_get / (min(g_wall) / 1e3), returned / (sm / 1e3), returned / (min(s_wall) / 1e3)],
+                            dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(vals, op=dist.ReduceOp.SUM)  # partitions are independent: whole-job keys/s = sum over ranks
+        reads = {
+            "get": {"metric": "get_keys_per_s", "value": float(vals[0]), "e2e": float(vals[1]), "unit": "keys/s", "batch": args.n_get,
+                    "kernel_ms": gm, "found_frac_sampled": found_frac, "blocks_probed_per_key": probes / args.n_get,
+                    "roofline": {"bound": "hbm", "kernel": "k_get", "achieved": get_algo / (gm / 1e3) / 1e9, "peak": load_peaks()[0], "unit": "GB/s",
+                                 "frac": get_algo / (gm / 1e3) / 1e9 / load_peaks()[0], "algorithmic_bytes_per_launch": get_algo}},
+            "scan": {"metric": "scan_keys_per_s", "value": float(vals[2]), "e2e": float(vals[3]), "unit": "keys/s", "requests": args.n_scan,
+                     "returned_per_launch": returned, "iterated_per_launch": iterated, "kernel_ms": sm, "d2h_bytes": scan_bytes,
+                     "roofline": {"bound": "hbm", "kernel": "k_scan", "achieved": scan_algo / (sm / 1e3) / 1e9, "peak": load_peaks()[0], "unit": "GB/s",
+                                  "frac": scan_algo / (sm / 1e3) / 1e9 / load_peaks()[0], "algorithmic_bytes_per_launch": scan_algo}},
+            "workload": "YCSB-C shaped: zipfian(0.99) hash keys over the 4 resident overlapping runs; get(hk,sk) and multi_get(hk, all sort keys)",
+        }
+        if rank == 0 and world == 1 and not args.skip_cpu:
+            import oracle_py as orc
+            threads = os.cpu_count() or 1
+            bruns = [orc.BlockRunCPU.from_blocks(hr) for hr in reversed(host_runs)]  # newest first
+            ng = min(args.n_get, 200_000)
+            f, vb, secs = orc.get_many(bruns, gkeys[: ng * gk.shape[1]], goff[: ng + 1], NOW, threads)
+            reads["get"]["cpu_baseline"] = {"value": ng / secs, "unit": "keys/s", "cores": threads, "kind": "port",
+                                            "sample": f"{ng} gets over the same 4 block runs, {secs:.2f} s"}
+            nsc = min(args.n_scan, 8192)
+            hk_flat = np.ascontiguousarray(sk[:nsc].reshape(-1))
+            hk_off = (np.arange(nsc + 1, dtype=np.uint32) * np.uint32(HK))
+            cnt, nb_, secs = orc.prefix_scan_many(bruns, hk_flat, hk_off, NOW, threads)
+            reads["scan"]["cpu_baseline"] = {"value": cnt / secs, "unit": "keys/s", "cores": threads, "kind": "port",
+                                             "sample": f"{nsc} prefix scans ({cnt} records) over the same 4 block runs, {secs:.2f} s"}
+            del bruns
+
     # ---- roofline of the dominant kernel ------------------------------------------------------------
     peak, peak_src = load_peaks()
     k_ms = sum(merge_ms) / len(merge_ms)
@@ -262,9 +363,9 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         threads = os.cpu_count() or 1
-        sample = min(args.records_per_run, args.cpu_sample_records)
+        sample = min(args.records_per_run, args.cpu_sample_records or max(250_000, 20_000 * threads))
         sruns = runs if sample == args.records_per_run else gen_runs(sample, 1000)
-        gbs, secs, sb = cpu_compaction(sruns, threads)
+        gbs, secs, sb = cpu_compaction(cpu_block_runs(sruns), threads)
         cpu = {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port",
                "sample": f"{RUNS} runs x {sample} records ({sb / 1e9:.2f} GB merged), oracle block-level compaction, {secs:.2f} s"}
 
@@ -279,7 +380,7 @@ def main():
                        "survivors": int(res.out_records), "tiles": int(res.n_tiles), "filter": "KeyWithTTLCompactionFilter on",
                        "l2": "inputs (2.9 GB of blocks) larger than the 126 MB L2", "ctas_per_sm": args.ctas_per_sm or 2,
                        "tma": not args.no_tma, "input_gen_s": round(gen_s, 1)},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "reads": reads, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "wall_ms_per_step": wall_ms / args.steps,
         }
         print(json.dumps(line), flush=True)

@@ -97,6 +97,11 @@ PGS_API void *pgs_engine_stream(pgs_engine *e);
 PGS_API int32_t pgs_engine_sync(pgs_engine *e);
 /* number of kernels this engine has launched so far */
 PGS_API uint64_t pgs_engine_launches(pgs_engine *e);
+/* device time (CUDA events on the engine stream) of the kernels of the last pgs_get_batch /
+ * pgs_range_scan(_many) call, without the host<->device copies around them */
+PGS_API float pgs_engine_last_kernel_ms(pgs_engine *e);
+/* data blocks fetched by the last pgs_get_batch (one per run probed per key) */
+PGS_API uint64_t pgs_engine_last_blocks_probed(pgs_engine *e);
 /* thread-local description of the last failure on the calling thread */
 PGS_API const char *pgs_last_error(void);
 

@@ -158,6 +158,12 @@ def lib() -> C.CDLL:
     L.pgs_engine_sync.argtypes = [vp]
     L.pgs_engine_launches.argtypes = [vp]
     L.pgs_engine_launches.restype = C.c_uint64
+    L.pgs_engine_last_kernel_ms.argtypes = [vp]
+    L.pgs_engine_last_kernel_ms.restype = C.c_float
+    L.pgs_engine_last_blocks_probed.argtypes = [vp]
+    L.pgs_engine_last_blocks_probed.restype = C.c_uint64
+    L.pgs_range_scan_many.argtypes = [vp, C.POINTER(ScanRequest), C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, vp, C.c_uint64,
+                                      vp, C.c_uint64, vp, C.c_uint32, vp, vp, vp]
     L.pgs_partition_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(vp)]
     L.pgs_partition_destroy.argtypes = [vp]
     L.pgs_partition_destroy.restype = None
@@ -362,6 +368,14 @@ class Engine:
     def launches(self) -> int:
         return int(lib().pgs_engine_launches(self.h))
 
+    @property
+    def last_kernel_ms(self) -> float:
+        return float(lib().pgs_engine_last_kernel_ms(self.h))
+
+    @property
+    def last_blocks_probed(self) -> int:
+        return int(lib().pgs_engine_last_blocks_probed(self.h))
+
     def partition(self, app_id: int = 1, pidx: int = 0, data_version: int = 1) -> "Partition":
         return Partition(self, app_id, pidx, data_version)
 
@@ -438,6 +452,37 @@ class Partition:
         _check(lib().pgs_compact_ex(self.h, ids.ctypes.data_as(u64p), ids.shape[0], out_level, bottommost,
                                     C.byref(fp), now, flags, C.byref(res)), "compact")
         return res
+
+    def prefix_scan_many(self, hashkeys, now: int, max_records: int = 1000, arena_stride: int = 32768, arena=None, kvs=None):
+        """multi_get(hash_key, all sort keys) for many hash keys in one launch (pgs_range_scan_many).
+        Returns (status, results, arena, kvs, arena_base, kv_base)."""
+        n = len(hashkeys)
+        reqs = (ScanRequest * n)()
+        keep = []
+        for i, hk in enumerate(hashkeys):
+            start = len(hk).to_bytes(2, "big") + hk
+            stop = bytearray(start)
+            while stop[-1] == 0xFF:
+                stop.pop()
+            stop[-1] += 1
+            for name, b in (("start", start), ("stop", bytes(stop))):
+                buf = (C.c_uint8 * len(b)).from_buffer_copy(b)
+                keep.append(buf)
+                setattr(reqs[i], name, Blob(C.cast(buf, u8p), len(b)))
+            reqs[i].start_inclusive = 1
+            reqs[i].stop_inclusive = 0
+            reqs[i].key_mode = 1
+            reqs[i].prefix_same_as_start = 1
+            reqs[i].max_count = max_records
+            reqs[i].max_iter_count = 3000
+        arena = np.zeros(n * arena_stride, np.uint8) if arena is None else arena
+        kvs = np.zeros(n * max_records * 5, np.uint32) if kvs is None else kvs
+        results = (ScanResult * n)()
+        abase = np.zeros(n + 1, np.uint64)
+        kbase = np.zeros(n + 1, np.uint32)
+        st = lib().pgs_range_scan_many(self.h, reqs, n, now, arena_stride, max_records, _ptr(arena), arena.shape[0], _ptr(kvs),
+                                       kvs.shape[0] // 5, None, 0, results, _ptr(abase), _ptr(kbase))
+        return st, results, arena, kvs, abase, kbase
 
     def get_batch(self, keys: np.ndarray, key_off: np.ndarray, now: int, arena_cap: int | None = None):
         n = key_off.shape[0] - 1

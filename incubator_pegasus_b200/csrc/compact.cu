@@ -35,7 +35,7 @@ namespace pgs {
 constexpr uint32_t kMergeThreads = 512;
 constexpr uint32_t kMergeWarps = kMergeThreads / 32;
 constexpr uint32_t kMaxTileBlocks = 256;
-constexpr uint32_t kMaxOutBlocks = 256;
+constexpr uint32_t kMaxOutBlocks = 128;
 constexpr uint32_t kRecExtra = 48; // per-record shared-memory bytes besides the key slot
 
 enum : uint8_t { F_VALID = 1, F_SHADOW = 2, F_KEEP = 4, F_TOMB = 8, F_NEWTS = 16 };
@@ -252,6 +252,8 @@ struct TileShared {
     uint32_t max_ukey, max_vlen, max_blk_size, max_blk_rec;
     uint32_t lo[kMaxRuns], nblk[kMaxRuns], nrec[kMaxRuns], in_off[kMaxRuns], rec_base[kMaxRuns], blk_base[kMaxRuns];
     uint32_t vlo[kMaxRuns], vhi[kMaxRuns], nabove[kMaxRuns];
+    uint32_t nx_tile, nx_err; // next tile's ticket + slice metadata, fetched while this tile is being written
+    uint32_t nx_lo[kMaxRuns], nx_nblk[kMaxRuns], nx_nrec[kMaxRuns], nx_bytes[kMaxRuns];
     uint32_t scan[33];
     uint32_t stat[16];
     uint32_t tb_off[kMaxTileBlocks], tb_size[kMaxTileBlocks], tb_rec[kMaxTileBlocks], tb_nrec[kMaxTileBlocks];
@@ -321,7 +323,29 @@ PGS_DEV void publish(TileAgg *slot, unsigned long long bytes, uint32_t blocks, u
     *(volatile uint32_t *)&slot->flag = 1;
 }
 
-PGS_DEV uint32_t varint_byte(uint32_t v, uint32_t j, uint32_t len) { return ((v >> (7 * j)) & 0x7fu) | (j + 1 < len ? 0x80u : 0u); }
+PGS_DEV uint32_t varint_byte(uint32_t v, uint32_t j, uint32_t len) { return ((v >> ((7 * j) & 31)) & 0x7fu) | (j + 1 < len ? 0x80u : 0u); }
+
+// one warp takes the next ticket and loads that tile's per-run slice metadata into S.nx_*
+PGS_DEV void fetch_next_tile(const MergeParams &P, TileShared &S, uint32_t lane)
+{
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(P.ticket, 1u);
+    t = __shfl_sync(kFull, t, 0);
+    if (lane == 0) { S.nx_tile = t; S.nx_err = 0; }
+    __syncwarp();
+    if (t < P.Q && lane < P.k) {
+        const RunDev &r = P.runs[lane];
+        const bool first = t == 0, last = t == P.Q - 1;
+        uint32_t lo = first ? 0 : P.split_pos[t * P.k + lane];
+        uint32_t hi = last ? r.nb : P.split_pos[(t + 1) * P.k + lane];
+        if (lo == 0xFFFFFFFFu || hi == 0xFFFFFFFFu || lo > r.nb || hi > r.nb || lo > hi) { atomicMax(&S.nx_err, (uint32_t)PGS_ABORTED); lo = hi = 0; }
+        uint32_t hi_ex = last ? r.nb : min(hi + 1, r.nb);
+        S.nx_lo[lane] = lo;
+        S.nx_nblk[lane] = hi_ex - lo;
+        S.nx_bytes[lane] = (uint32_t)(r.blk_off[hi_ex] - r.blk_off[lo]);
+        S.nx_nrec[lane] = r.blk_rec[hi_ex] - r.blk_rec[lo];
+    }
+}
 
 __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__ MergeParams P)
 {
@@ -338,32 +362,26 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
     }
     if (P.validate_hash)
         for (uint32_t i = tid; i < 256; i += kMergeThreads) S.crc[i] = P.crc_table[i];
+    if (warp == 0) fetch_next_tile(P, S, lane);
     __syncthreads();
     uint32_t phase = 0;
 
     for (;;) {
-        if (tid == 0) S.tile = atomicAdd(P.ticket, 1u);
+        if (tid == 0) S.tile = S.nx_tile;
         if (tid < 16) S.stat[tid] = 0;
         if (tid >= 32 && tid < 32 + kMaxRuns) { S.vlo[tid - 32] = 0; S.nabove[tid - 32] = 0; }
-        if (tid == 64) { S.error = 0; S.min_seq = ~0ull; S.max_seq = 0; S.max_ukey = 0; S.max_vlen = 0; S.max_blk_size = 0; S.max_blk_rec = 0; }
+        if (tid == 64) { S.error = S.nx_err; S.min_seq = ~0ull; S.max_seq = 0; S.max_ukey = 0; S.max_vlen = 0; S.max_blk_size = 0; S.max_blk_rec = 0; }
         __syncthreads();
         const uint32_t tile = S.tile;
         if (tile >= P.Q) break;
         const bool first = tile == 0, last = tile == P.Q - 1;
 
-        // ---- tile setup ---------------------------------------------------------------------
+        // ---- tile setup (slice metadata was prefetched into S.nx_*) ---------------------------
         if (tid < P.k) {
-            const RunDev &r = P.runs[tid];
-            uint32_t lo = first ? 0 : P.split_pos[tile * P.k + tid];
-            uint32_t hi = last ? r.nb : P.split_pos[(tile + 1) * P.k + tid];
-            uint32_t err = 0;
-            if (lo == 0xFFFFFFFFu || hi == 0xFFFFFFFFu || lo > r.nb || hi > r.nb || lo > hi) { err = PGS_ABORTED; lo = hi = 0; }
-            uint32_t hi_ex = last ? r.nb : min(hi + 1, r.nb);
-            S.lo[tid] = lo;
-            S.nblk[tid] = hi_ex - lo;
-            S.in_off[tid] = (uint32_t)(r.blk_off[hi_ex] - r.blk_off[lo]); // bytes, offsets fixed below
-            S.nrec[tid] = r.blk_rec[hi_ex] - r.blk_rec[lo];
-            if (err) atomicMax(&S.error, err);
+            S.lo[tid] = S.nx_lo[tid];
+            S.nblk[tid] = S.nx_nblk[tid];
+            S.in_off[tid] = S.nx_bytes[tid]; // bytes, offsets fixed below
+            S.nrec[tid] = S.nx_nrec[tid];
         }
         __syncthreads();
         if (tid == 0) {
@@ -441,7 +459,9 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
         // ---- decode step 1: one THREAD per block walks the entry headers --------------------------
         // (entries are sequential inside a block; blocks are independent: 32 blocks advance per warp instruction)
         if (tile_ok) {
-            for (uint32_t t = tid; t < S.n_blk_in; t += kMergeThreads) {
+            // block t goes to lane t/16 of warp t%16: the walks are latency chains, spreading them over all warps
+            // lets every scheduler interleave several of them instead of one warp crawling through all blocks
+            for (uint32_t t = warp + kMergeWarps * lane; t < S.n_blk_in; t += kMergeThreads) {
                 const uint8_t *base = A.in + S.tb_off[t];
                 uint32_t size = S.tb_size[t], rec0 = S.tb_rec[t], expect = S.tb_nrec[t];
                 uint32_t err = 0, nr = 0;
@@ -453,11 +473,15 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
                 uint32_t limit = err ? 0 : size - 4 - 4 * nr;
                 uint32_t p = 0, prev_klen = 0, i = 0;
                 while (!err && p < limit && i < expect) {
-                    uint32_t shared, non_shared, vlen, h = 0, c;
-                    c = get_varint32(base + p, limit - p, shared);
-                    h += c;
-                    if (c) { c = get_varint32(base + p + h, limit - p - h, non_shared); h += c; }
-                    if (c) { c = get_varint32(base + p + h, limit - p - h, vlen); h += c; }
+                    uint32_t shared, non_shared, vlen, h, c;
+                    h = c = parse_header8(lds_u64_unaligned(base + p), shared, non_shared, vlen); // header bytes from registers
+                    if (!c) { // longer than 8 bytes: byte-wise decoder
+                        h = 0;
+                        c = get_varint32(base + p, limit - p, shared);
+                        h += c;
+                        if (c) { c = get_varint32(base + p + h, limit - p - h, non_shared); h += c; }
+                        if (c) { c = get_varint32(base + p + h, limit - p - h, vlen); h += c; }
+                    }
                     uint32_t klen = shared + non_shared;
                     if (!c || shared > prev_klen || klen < 8 || klen - 8 > KS || (unsigned long long)p + h + non_shared + vlen > limit) {
                         err = PGS_CORRUPTION;
@@ -470,7 +494,13 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
                     A.klen[r] = (uint16_t)(klen - 8);
                     A.voff[r] = S.tb_off[t] + p + h + non_shared;
                     A.vlen[r] = vlen;
-                    A.trailer[r] = 0;
+                    if (non_shared >= 8) { // the (seq<<8|type) trailer sits wholly in this entry's delta
+                        A.trailer[r] = lds_u64_unaligned(base + p + h + non_shared - 8);
+                        A.flags[r] = 0;
+                    } else {               // part of it is shared with the previous key: rebuilt in step 2
+                        A.trailer[r] = 0;
+                        A.flags[r] = 1;
+                    }
                     prev_klen = klen;
                     p += h + non_shared + vlen;
                     i++;
@@ -505,11 +535,11 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
                             uint32_t b0 = p0 < ulen ? c0 : 0, b1 = p1 < ulen ? c1 : 0;
                             *(uint16_t *)(A.arena + (size_t)r * KS + p0) = (uint16_t)(b0 | (b1 << 8));
                         }
-                        // the 8 bytes after the user key are the (seq<<8|type) trailer, little endian
-                        uint32_t lo = 0, hi = 0;
-                        if (p0 >= ulen && p0 < ulen + 8) { uint32_t j = p0 - ulen; if (j < 4) lo |= c0 << (8 * j); else hi |= c0 << (8 * (j - 4)); }
-                        if (p1 >= ulen && p1 < ulen + 8) { uint32_t j = p1 - ulen; if (j < 4) lo |= c1 << (8 * j); else hi |= c1 << (8 * (j - 4)); }
-                        if (pass * 64 < ulen + 8 && pass * 64 + 64 > ulen) {
+                        // rare: the 8 trailer bytes after the user key straddle the shared prefix
+                        if (A.flags[r] && pass * 64 < ulen + 8 && pass * 64 + 64 > ulen) {
+                            uint32_t lo = 0, hi = 0;
+                            if (p0 >= ulen && p0 < ulen + 8) { uint32_t j = p0 - ulen; if (j < 4) lo |= c0 << (8 * j); else hi |= c0 << (8 * (j - 4)); }
+                            if (p1 >= ulen && p1 < ulen + 8) { uint32_t j = p1 - ulen; if (j < 4) lo |= c1 << (8 * j); else hi |= c1 << (8 * (j - 4)); }
                             lo = __reduce_or_sync(kFull, lo);
                             hi = __reduce_or_sync(kFull, hi);
                             if (lane == 0) A.trailer[r] |= ((unsigned long long)hi << 32) | lo;
@@ -561,16 +591,17 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
                 for (uint32_t o = 0; o < P.k; o++) {
                     if (o == j) continue;
                     uint32_t base = S.rec_base[o], lo = S.vlo[o], hi = S.vhi[o];
+                    uint32_t lcp_lo = 0, lcp_hi = 0; // words shared with the keys just outside [lo, hi)
                     while (lo < hi) { // first position whose internal key is not before ours
-                        uint32_t mid = (lo + hi) >> 1, q = base + mid;
-                        int c = cmp_slots(A.arena + (size_t)q * KS, A.klen[q], key, kl);
+                        uint32_t mid = (lo + hi) >> 1, q = base + mid, d;
+                        int c = cmp_slots_from(A.arena + (size_t)q * KS, A.klen[q], key, kl, min(lcp_lo, lcp_hi), &d);
                         bool before;
                         if (c != 0) before = c < 0;
                         else {
                             unsigned long long tq = A.trailer[q];
                             before = tq > tr || (tq == tr && o < j);
                         }
-                        if (before) lo = mid + 1; else hi = mid;
+                        if (before) { lo = mid + 1; lcp_lo = d; } else { hi = mid; lcp_hi = d; }
                     }
                     rank += lo - S.vlo[o];
                     if (lo > S.vlo[o]) {
@@ -677,7 +708,9 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
                 }
                 A.shr[p] = (uint16_t)shared;
                 uint32_t ns = kl + 8 - shared, vl = A.vlen[r];
-                return varint_len(shared) + varint_len(ns) + varint_len(vl) + ns + vl;
+                uint32_t hs = varint_len(shared) + varint_len(ns) + varint_len(vl) + ns;
+                A.rank[p] = (uint16_t)hs; // entry head bytes (varints + key delta + trailer)
+                return hs + vl;
             });
             if (warp == 0) { // block sizes, 16-byte aligned offsets and index-key offsets: one warp, shuffle scans
                 uint32_t off = 0, koff = 0;
@@ -750,6 +783,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
         }
         __syncthreads();
         tile_ok = S.error == 0;
+        if (warp == kMergeWarps - 1) fetch_next_tile(P, S, lane); // overlaps the global-memory latency with the writes below
 
         // ---- write the tile's blocks ------------------------------------------------------------------------------
         if (tile_ok && m > 0) {
@@ -757,30 +791,20 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
             uint8_t *out = P.out_data + S.base_bytes;
             uint32_t s_outb = 0, s_otomb = 0, s_okey = 0, s_oval = 0, mx_k = 0, mx_v = 0;
             unsigned long long mn_seq = ~0ull, mx_seq = 0;
-            for (uint32_t p = warp; p < m; p += kMergeWarps) {
+            if (tid == 0) S.scan[0] = 0;
+            __syncthreads();
+            // (a) entry start offsets inside the tile's output + per-survivor stats, one thread per survivor
+            uint32_t max_chunks = 0;
+            for (uint32_t p = tid; p < m; p += kMergeThreads) {
                 const uint32_t r = A.surv[p], b = A.blkid[p];
-                const uint32_t kl = A.klen[r], vl = A.vlen[r], shared = A.shr[p];
+                const uint32_t kl = A.klen[r], vl = A.vlen[r];
+                const uint32_t eoff = S.ob_off[b] + (A.E[p] - A.E[S.cut[b]]);
+                A.R[p] = eoff;
                 const uint8_t f = A.flags[r];
                 const unsigned long long tr = A.trailer[r];
                 const uint8_t type = (f & F_TOMB) ? (uint8_t)PGS_TYPE_DELETION : (uint8_t)tr;
                 const unsigned long long seq = (P.bottommost && type == PGS_TYPE_VALUE) ? 0ull : (tr >> 8);
-                const unsigned long long otr = (seq << 8) | type;
-                const uint32_t kd = kl - shared, ns = kd + 8;
-                const uint32_t l1 = varint_len(shared), l2 = varint_len(ns), l3 = varint_len(vl);
-                const uint32_t h = l1 + l2 + l3, hs = h + ns;
-                uint8_t *dst = out + S.ob_off[b] + (A.E[p] - A.E[S.cut[b]]);
-                const uint8_t *ksrc = A.arena + (size_t)r * KS + shared;
-                // entry head = 3 varints | key delta | trailer: every lane produces one byte, stores coalesce
-                for (uint32_t i = lane; i < hs; i += 32) {
-                    uint32_t v;
-                    if (i < l1) v = varint_byte(shared, i, l1);
-                    else if (i < l1 + l2) v = varint_byte(ns, i - l1, l2);
-                    else if (i < h) v = varint_byte(vl, i - l1 - l2, l3);
-                    else if (i < h + kd) v = ksrc[i - h];
-                    else v = (uint32_t)(otr >> (8 * (i - h - kd))) & 0xffu;
-                    dst[i] = (uint8_t)v;
-                }
-                warp_copy_s2g(dst + hs, A.in + A.voff[r], vl, lane);
+                A.trailer[r] = (seq << 8) | type; // the trailer as written
                 s_outb += kl + vl;
                 s_otomb += type == PGS_TYPE_DELETION;
                 s_okey += kl;
@@ -789,6 +813,82 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
                 mx_v = max(mx_v, vl);
                 mn_seq = seq < mn_seq ? seq : mn_seq;
                 mx_seq = seq > mx_seq ? seq : mx_seq;
+                max_chunks = max(max_chunks, (vl >> 4) + 2);
+            }
+            s_outb = __reduce_add_sync(kFull, s_outb); s_otomb = __reduce_add_sync(kFull, s_otomb);
+            s_okey = __reduce_add_sync(kFull, s_okey); s_oval = __reduce_add_sync(kFull, s_oval);
+            mx_k = __reduce_max_sync(kFull, mx_k); mx_v = __reduce_max_sync(kFull, mx_v);
+            max_chunks = __reduce_max_sync(kFull, max_chunks);
+            for (uint32_t d = 16; d; d >>= 1) {
+                unsigned long long o1 = __shfl_xor_sync(kFull, mn_seq, d), o2 = __shfl_xor_sync(kFull, mx_seq, d);
+                mn_seq = o1 < mn_seq ? o1 : mn_seq;
+                mx_seq = o2 > mx_seq ? o2 : mx_seq;
+            }
+            if (lane == 0) atomicMax(&S.scan[0], max_chunks);
+            __syncthreads();
+            const uint32_t CH = S.scan[0];
+            // (b) values first: one thread per 16-byte destination-aligned chunk (CH slots per survivor), source words
+            //     re-aligned with funnel shifts.  The first and last chunk of a value are written as FULL 16-byte
+            //     stores whenever the bytes that do not belong to the value fall inside this entry's own head or
+            //     the next entry's head of the same block: those heads are written after the barrier below and
+            //     overwrite the spill.  Only where a spill could touch foreign bytes the exact byte range is stored.
+            for (uint32_t id = tid; id < m * CH; id += kMergeThreads) {
+                const uint32_t p = id / CH, c = id - p * CH;
+                const uint32_t r = A.surv[p];
+                const uint32_t vl = A.vlen[r];
+                if (vl == 0) continue;
+                const uint32_t hs = A.rank[p];
+                uint8_t *dv = out + A.R[p] + hs;
+                const uint32_t lead = (uint32_t)((uintptr_t)dv & 15);
+                const uint32_t nch = (lead + vl + 15) >> 4;
+                if (c >= nch) continue;
+                uint8_t *addr = dv - lead + (c << 4);
+                const uint32_t lo = c == 0 ? lead : 0;
+                const uint32_t rem = lead + vl - (c << 4);
+                const uint32_t hi = rem < 16 ? rem : 16;
+                const uint8_t *sp = A.in + A.voff[r] + (c << 4) - lead; // may start a few bytes before the value: still inside IN / the key slots
+                bool full = true;
+                if (lo > hs) full = false; // the spill before the value would reach the previous entry
+                if (hi < 16) {
+                    const bool block_last = p + 1 == S.cut[A.blkid[p] + 1];
+                    if (block_last || 16 - hi > A.rank[p + 1]) full = false;
+                }
+                if (full) {
+                    const uint32_t sh = (uint32_t)((uintptr_t)sp & 3) * 8;
+                    const uint32_t *w = (const uint32_t *)((uintptr_t)sp & ~(uintptr_t)3);
+                    uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+                    uint4 o4;
+                    if (sh == 0) o4 = make_uint4(w0, w1, w2, w3);
+                    else {
+                        uint32_t w4 = w[4];
+                        o4.x = __funnelshift_r(w0, w1, sh); o4.y = __funnelshift_r(w1, w2, sh);
+                        o4.z = __funnelshift_r(w2, w3, sh); o4.w = __funnelshift_r(w3, w4, sh);
+                    }
+                    *reinterpret_cast<uint4 *>(addr) = o4;
+                } else {
+                    for (uint32_t x = lo; x < hi; x++) addr[x] = sp[x];
+                }
+            }
+            __syncthreads();
+            // (c) entry heads = 3 varints | key delta | trailer: half a warp per survivor, one byte per lane, the
+            //     stores of a half-warp are consecutive bytes
+            for (uint32_t p = 2 * warp + (lane >> 4); p < m; p += 2 * kMergeWarps) {
+                const uint32_t hl = lane & 15;
+                const uint32_t r = A.surv[p];
+                const uint32_t kl = A.klen[r], vl = A.vlen[r], shared = A.shr[p], hs = A.rank[p];
+                const unsigned long long otr = A.trailer[r];
+                const uint32_t kd = kl - shared, ns = kd + 8;
+                const uint32_t l1 = varint_len(shared), l2 = varint_len(ns), l3 = varint_len(vl), h = l1 + l2 + l3;
+                uint8_t *dst = out + A.R[p];
+                const uint8_t *ksrc = A.arena + (size_t)r * KS + shared;
+                for (uint32_t i = hl; i < hs; i += 16) {
+                    uint32_t va = varint_byte(shared, i, l1), vb = varint_byte(ns, (i - l1) & 7, l2), vc = varint_byte(vl, (i - l1 - l2) & 7, l3);
+                    uint32_t ki = i - h;
+                    uint32_t vd = ksrc[ki < kd ? ki : 0];
+                    uint32_t ve = (uint32_t)(otr >> (8 * ((ki - kd) & 7))) & 0xffu;
+                    uint32_t v = i < l1 ? va : (i < l1 + l2 ? vb : (i < h ? vc : (ki < kd ? vd : ve)));
+                    dst[i] = (uint8_t)v;
+                }
             }
             if (lane == 0) {
                 atomicAdd(&S.stat[ST_OUT_BYTES], s_outb);

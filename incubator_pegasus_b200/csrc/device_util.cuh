@@ -107,6 +107,51 @@ PGS_DEV int cmp_slots(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t 
     }
     return la < lb ? -1 : (la > lb ? 1 : 0);
 }
+// same compare, skipping the first `start` 8-byte words (known equal); *diff = index of the first differing word
+// (or the number of compared words when one key is a prefix of the other).  Lets a binary search over sorted
+// keys skip the prefix shared with both bounds (LCP-aware search).
+PGS_DEV int cmp_slots_from(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb, uint32_t start, uint32_t *diff)
+{
+    uint32_t m = la < lb ? la : lb;
+    uint32_t words = (m + 7) >> 3;
+    const uint64_t *wa = (const uint64_t *)a, *wb = (const uint64_t *)b;
+    for (uint32_t i = start; i < words; i++) {
+        uint64_t x = wa[i], y = wb[i];
+        if (x != y) {
+            *diff = i;
+            x = bswap64(x);
+            y = bswap64(y);
+            return x < y ? -1 : 1;
+        }
+    }
+    *diff = words;
+    return la < lb ? -1 : (la > lb ? 1 : 0);
+}
+// 8 bytes at an arbitrary shared-memory address (three aligned 32-bit loads + funnel shifts)
+PGS_DEV uint64_t lds_u64_unaligned(const uint8_t *p)
+{
+    const uint32_t *w = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
+    uint32_t sh = (uint32_t)((uintptr_t)p & 3) * 8;
+    uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+    return ((uint64_t)hi << 32) | lo;
+}
+// three varint32 (shared, non_shared, value_len) out of the 8 header bytes in x; returns the header length, or 0
+// when the common shape (shared < 128, non_shared < 128, value_len < 2^21) does not apply and the caller must use
+// the byte-wise decoder
+PGS_DEV uint32_t parse_header8(uint64_t x, uint32_t &a, uint32_t &b, uint32_t &c)
+{
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    if (lo & 0x00008080u) return 0; // a multi-byte shared / non_shared length
+    a = lo & 0x7fu;
+    b = (lo >> 8) & 0x7fu;
+    uint32_t b2 = (lo >> 16) & 0xffu, b3 = lo >> 24, b4 = hi & 0xffu;
+    if (!(b2 & 0x80u)) { c = b2; return 3; }
+    if (!(b3 & 0x80u)) { c = (b2 & 0x7fu) | (b3 << 7); return 4; }
+    if (!(b4 & 0x80u)) { c = (b2 & 0x7fu) | ((b3 & 0x7fu) << 7) | (b4 << 14); return 5; }
+    return 0;
+}
+
 // longest common prefix of two zero-padded 8-aligned slots, capped at min(la, lb)
 PGS_DEV uint32_t lcp_slots(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb)
 {

@@ -48,6 +48,8 @@ Run::~Run()
 Engine::~Engine()
 {
     if (h_pinned) cudaFreeHost(h_pinned);
+    if (ev_a) cudaEventDestroy(ev_a);
+    if (ev_b) cudaEventDestroy(ev_b);
     if (stream) cudaStreamDestroy(stream);
 }
 void *Engine::pinned(size_t bytes)
@@ -267,6 +269,8 @@ int32_t pgs_engine_open(const pgs_engine_config *cfg, pgs_engine **out)
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e.sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (err == cudaSuccess) err = cudaEventCreate(&e.ev_a);
+    if (err == cudaSuccess) err = cudaEventCreate(&e.ev_b);
     if (err == cudaSuccess) { // keep freed compaction buffers in the stream-ordered pool
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
@@ -296,6 +300,8 @@ int32_t pgs_engine_sync(pgs_engine *e)
     return PGS_OK;
 }
 uint64_t pgs_engine_launches(pgs_engine *e) { return e->e.launches.load(); }
+float pgs_engine_last_kernel_ms(pgs_engine *e) { return e->e.last_kernel_ms; }
+uint64_t pgs_engine_last_blocks_probed(pgs_engine *e) { return e->e.last_blocks_probed; }
 
 int32_t pgs_partition_create(pgs_engine *e, int32_t app_id, int32_t pidx, uint32_t data_version,
                              pgs_partition **out)

@@ -54,6 +54,9 @@ struct Engine {
     int max_smem_optin = 0;
     std::atomic<uint64_t> launches{0};
     std::atomic<uint64_t> next_run_id{1};
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr; // bracket the kernels of the last read call
+    float last_kernel_ms = 0.f;
+    uint64_t last_blocks_probed = 0;
     // reusable pinned staging + device scratch
     std::mutex mu;
     void *h_pinned = nullptr;

@@ -82,7 +82,7 @@ struct GetParams {
     pgs_get_result *results;
     uint8_t *arena;
     unsigned long long arena_cap;
-    unsigned long long *arena_cursor;
+    unsigned long long *arena_cursor; // [0] = arena bytes, [1] = data blocks probed
     uint32_t *error;
 };
 
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kGetWarps * 32) k_get(const __grid_constant__ 
         mbar_fence_init();
     }
     __syncwarp();
-    uint32_t phase = 0;
+    uint32_t phase = 0, probes = 0;
     for (uint32_t q = blockIdx.x * kGetWarps + warp; q < P.n; q += gridDim.x * kGetWarps) {
         const uint8_t *key = P.keys + P.key_off[q];
         const uint32_t klen = P.key_off[q + 1] - P.key_off[q];
@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(kGetWarps * 32) k_get(const __grid_constant__ 
             const RunDev &r = P.rr.runs[ri];
             uint32_t b = index_lower_bound(r, key, klen);
             if (b >= r.nb) continue;
+            probes++;
             const uint8_t *gsrc = r.data + r.blk_off[b];
             uint32_t size = r.blk_size[b];
             const uint8_t *base;
@@ -198,6 +199,7 @@ __global__ void __launch_bounds__(kGetWarps * 32) k_get(const __grid_constant__ 
         }
         if (lane == 0) P.results[q] = res;
     }
+    if (lane == 0 && probes) atomicAdd(P.arena_cursor + 1, (unsigned long long)probes);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1007,7 +1009,9 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
         cudaStreamSynchronize(st);
         return PGS_OK;
     }
+    cudaEventRecord(e->ev_a, st);
     k_scan<<<grid, kScanThreads, dyn, st>>>(P);
+    cudaEventRecord(e->ev_b, st);
     e->launches++;
     uint32_t herr = 0;
     if (n == 1) {
@@ -1050,6 +1054,7 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
         if (arena_base) for (uint32_t i = 0; i <= n; i++) arena_base[i] = ab[i];
         if (kv_base) for (uint32_t i = 0; i <= n; i++) kv_base[i] = kb[i];
     }
+    cudaEventElapsedTime(&e->last_kernel_ms, e->ev_a, e->ev_b);
     cleanup();
 #undef CK
     if (herr) {
@@ -1097,11 +1102,11 @@ extern "C" int32_t pgs_get_batch(pgs_partition *ph, const uint8_t *keys, const u
     CK(cudaMallocAsync(&d_off, sizeof(uint32_t) * (n + 1), st));
     CK(cudaMallocAsync(&d_res, sizeof(pgs_get_result) * n, st));
     CK(cudaMallocAsync(&d_arena, arena_cap + 16, st));
-    CK(cudaMallocAsync(&d_cur, 8, st));
+    CK(cudaMallocAsync(&d_cur, 16, st));
     CK(cudaMallocAsync(&d_err, 4, st));
     CK(cudaMemcpyAsync(d_keys, keys, key_bytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_off, key_off, sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(d_cur, 0, 8, st));
+    CK(cudaMemsetAsync(d_cur, 0, 16, st));
     CK(cudaMemsetAsync(d_err, 0, 4, st));
     P.keys = d_keys; P.key_off = d_off; P.n = n; P.now = now; P.data_version = part.data_version;
     P.use_tma = (e->cfg.flags & PGS_ENGINE_NO_TMA) ? 0 : 1;
@@ -1111,14 +1116,19 @@ extern "C" int32_t pgs_get_batch(pgs_partition *ph, const uint8_t *keys, const u
     CK(cudaFuncSetAttribute(k_get, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     uint32_t per_sm = (uint32_t)std::max<size_t>(1, (228 * 1024) / (dyn + 2048));
     uint32_t grid = std::min<uint32_t>((n + kGetWarps - 1) / kGetWarps, per_sm * e->sm_count);
+    cudaEventRecord(e->ev_a, st);
     k_get<<<grid, kGetWarps * 32, dyn, st>>>(P);
+    cudaEventRecord(e->ev_b, st);
     e->launches++;
     uint32_t herr = 0;
-    unsigned long long used = 0;
+    unsigned long long cur2[2] = {0, 0};
     CK(cudaMemcpyAsync(results, d_res, sizeof(pgs_get_result) * n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&used, d_cur, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cur2, d_cur, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&e->last_kernel_ms, e->ev_a, e->ev_b);
+    const unsigned long long used = cur2[0];
+    e->last_blocks_probed = cur2[1];
     if (arena_used) *arena_used = used;
     if (!herr && used) {
         CK(cudaMemcpyAsync(arena, d_arena, std::min<unsigned long long>(used, arena_cap), cudaMemcpyDeviceToHost, st));
