@@ -453,36 +453,10 @@ class Partition:
                                     C.byref(fp), now, flags, C.byref(res)), "compact")
         return res
 
-    def prefix_scan_many(self, hashkeys, now: int, max_records: int = 1000, arena_stride: int = 32768, arena=None, kvs=None):
-        """multi_get(hash_key, all sort keys) for many hash keys in one launch (pgs_range_scan_many).
-        Returns (status, results, arena, kvs, arena_base, kv_base)."""
-        n = len(hashkeys)
-        reqs = (ScanRequest * n)()
-        keep = []
-        for i, hk in enumerate(hashkeys):
-            start = len(hk).to_bytes(2, "big") + hk
-            stop = bytearray(start)
-            while stop[-1] == 0xFF:
-                stop.pop()
-            stop[-1] += 1
-            for name, b in (("start", start), ("stop", bytes(stop))):
-                buf = (C.c_uint8 * len(b)).from_buffer_copy(b)
-                keep.append(buf)
-                setattr(reqs[i], name, Blob(C.cast(buf, u8p), len(b)))
-            reqs[i].start_inclusive = 1
-            reqs[i].stop_inclusive = 0
-            reqs[i].key_mode = 1
-            reqs[i].prefix_same_as_start = 1
-            reqs[i].max_count = max_records
-            reqs[i].max_iter_count = 3000
-        arena = np.zeros(n * arena_stride, np.uint8) if arena is None else arena
-        kvs = np.zeros(n * max_records * 5, np.uint32) if kvs is None else kvs
-        results = (ScanResult * n)()
-        abase = np.zeros(n + 1, np.uint64)
-        kbase = np.zeros(n + 1, np.uint32)
-        st = lib().pgs_range_scan_many(self.h, reqs, n, now, arena_stride, max_records, _ptr(arena), arena.shape[0], _ptr(kvs),
-                                       kvs.shape[0] // 5, None, 0, results, _ptr(abase), _ptr(kbase))
-        return st, results, arena, kvs, abase, kbase
+    def prefix_scan_batch(self, hashkeys, max_records: int = 1000, arena_stride: int = 32768) -> "ScanBatch":
+        """multi_get(hash_key, all sort keys) for many hash keys: the request structs are marshalled once, run() is
+        the C-ABI call (pgs_range_scan_many) from host buffers."""
+        return ScanBatch(self, hashkeys, max_records, arena_stride)
 
     def get_batch(self, keys: np.ndarray, key_off: np.ndarray, now: int, arena_cap: int | None = None):
         n = key_off.shape[0] - 1
@@ -492,3 +466,46 @@ class Partition:
         used = C.c_uint64()
         st = lib().pgs_get_batch(self.h, _ptr(keys), _ptr(key_off), n, now, _ptr(arena), cap, results, C.byref(used))
         return st, results, arena, used.value
+
+
+class ScanBatch:
+    def __init__(self, part: Partition, hashkeys, max_records: int, arena_stride: int):
+        self.part = part
+        n = len(hashkeys)
+        self.n = n
+        self.reqs = (ScanRequest * n)()
+        self._keep = []
+        for i, hk in enumerate(hashkeys):
+            start = len(hk).to_bytes(2, "big") + hk
+            stop = bytearray(start)
+            while stop[-1] == 0xFF:
+                stop.pop()
+            stop[-1] += 1
+            for name, b in (("start", start), ("stop", bytes(stop))):
+                buf = (C.c_uint8 * len(b)).from_buffer_copy(b)
+                self._keep.append(buf)
+                setattr(self.reqs[i], name, Blob(C.cast(buf, u8p), len(b)))
+            q = self.reqs[i]
+            q.start_inclusive, q.stop_inclusive, q.key_mode, q.prefix_same_as_start = 1, 0, 1, 1
+            q.max_count, q.max_iter_count = max_records, 3000
+        self.max_records, self.arena_stride = max_records, arena_stride
+        self.arena = np.zeros(n * arena_stride, np.uint8)
+        self.kvs = np.zeros(n * max_records * 5, np.uint32)
+        self.results = (ScanResult * n)()
+        self.abase = np.zeros(n + 1, np.uint64)
+        self.kbase = np.zeros(n + 1, np.uint32)
+
+    def run(self, now: int) -> int:
+        return lib().pgs_range_scan_many(self.part.h, self.reqs, self.n, now, self.arena_stride, self.max_records,
+                                         _ptr(self.arena), self.arena.shape[0], _ptr(self.kvs), self.kvs.shape[0] // 5, None, 0,
+                                         self.results, _ptr(self.abase), _ptr(self.kbase))
+
+    def records(self, i: int):
+        """(sort key, user value) pairs of request i"""
+        kv = self.kvs.reshape(-1, 5)
+        base = int(self.abase[i])
+        out = []
+        for j in range(int(self.kbase[i]), int(self.kbase[i + 1])):
+            ko, kl, vo, vl, _ = (int(x) for x in kv[j])
+            out.append((self.arena[base + ko:base + ko + kl].tobytes(), self.arena[base + vo:base + vo + vl].tobytes()))
+        return out

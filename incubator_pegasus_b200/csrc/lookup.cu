@@ -70,6 +70,34 @@ PGS_DEV uint32_t index_upper_bound(const RunDev &r, const uint8_t *key, uint32_t
     return lo;
 }
 
+// warp-cooperative 33-ary search over the block index: every round the 32 lanes probe 32 pivots at once, so the
+// chain of dependent global loads is ~log33(nb) long instead of log2(nb).  upper=false: first block whose last key
+// >= key; upper=true: first block whose last key > key.  All lanes return the same value.
+PGS_DEV uint32_t warp_index_bound(const RunDev &r, const uint8_t *key, uint32_t klen, uint32_t lane, bool upper)
+{
+    uint32_t lo = 0, hi = r.nb;
+    while (hi - lo > 32) {
+        uint32_t span = hi - lo;
+        uint32_t piv = lo + (uint32_t)(((unsigned long long)span * (lane + 1)) / 33);
+        uint32_t o = r.ikey_off[piv], l = r.ikey_off[piv + 1] - o;
+        int c = cmp_bytes(r.ikeys + o, l, key, klen);
+        bool before = upper ? c <= 0 : c < 0; // pivot block lies strictly before the answer
+        uint32_t m = __ballot_sync(kFull, before);
+        uint32_t cnt = __popc(m); // monotone: lanes 0..cnt-1 are true
+        uint32_t nlo = cnt == 0 ? lo : __shfl_sync(kFull, piv, cnt - 1) + 1;
+        uint32_t nhi = cnt == 32 ? hi : __shfl_sync(kFull, piv, cnt & 31);
+        lo = nlo;
+        hi = nhi;
+    }
+    bool before = false;
+    if (lo + lane < hi) {
+        uint32_t o = r.ikey_off[lo + lane], l = r.ikey_off[lo + lane + 1] - o;
+        int c = cmp_bytes(r.ikeys + o, l, key, klen);
+        before = upper ? c <= 0 : c < 0;
+    }
+    return lo + __popc(__ballot_sync(kFull, before));
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_get
 // ------------------------------------------------------------------------------------------------
@@ -109,7 +137,7 @@ __global__ void __launch_bounds__(kGetWarps * 32) k_get(const __grid_constant__ 
         bool done = false;
         for (uint32_t ri = 0; ri < P.rr.n && !done; ri++) {
             const RunDev &r = P.rr.runs[ri];
-            uint32_t b = index_lower_bound(r, key, klen);
+            uint32_t b = warp_index_bound(r, key, klen, lane, false);
             if (b >= r.nb) continue;
             probes++;
             const uint8_t *gsrc = r.data + r.blk_off[b];
@@ -243,7 +271,7 @@ struct ScanShared {
     uint32_t in_bytes, n_rec, n_blk, n_valid, n_vis;
     uint32_t lo_len, hi_len, has_lo, has_hi, lo_incl, hi_incl; // chunk validity bounds
     uint32_t cur[kMaxReadRuns], nblk[kMaxReadRuns], nrec[kMaxReadRuns], in_off[kMaxReadRuns], rec_base[kMaxReadRuns], blk_base[kMaxReadRuns];
-    uint32_t vlo[kMaxReadRuns], vhi[kMaxReadRuns], more[kMaxReadRuns];
+    uint32_t vlo[kMaxReadRuns], vhi[kMaxReadRuns], more[kMaxReadRuns], want_end[kMaxReadRuns];
     uint32_t tb_off[kScanMaxBlocks], tb_size[kScanMaxBlocks], tb_rec[kScanMaxBlocks], tb_nrec[kScanMaxBlocks];
     uint32_t scan[33];
     // carried loop state
@@ -367,14 +395,16 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
         }
         if (P.crc_table && Q.validate_hash)
             for (uint32_t i = tid; i < 256; i += kScanThreads) S.crc[i] = P.crc_table[i];
-        // initial cursors: forward: first block whose last key >= start; reverse: first block whose last key >= stop
-        for (uint32_t j = tid; j < NR; j += kScanThreads) {
+        // initial cursors (one warp per run, 33-ary index search): forward: first block whose last key >= start;
+        // reverse: first block whose last key >= stop.  want_end: first block whose last key >= the range end.
+        for (uint32_t j = warp; j < NR; j += kScanWarps) {
             const RunDev &r = P.rr.runs[j];
             const uint8_t *sk = rev ? stop : start;
             uint32_t sl = rev ? Q.stop_len : Q.start_len;
-            uint32_t b = index_lower_bound(r, sk, sl);
+            uint32_t b = warp_index_bound(r, sk, sl, lane, false);
             if (rev && b >= r.nb) b = r.nb ? r.nb - 1 : 0;
-            S.cur[j] = b;
+            uint32_t we = warp_index_bound(r, endk, endl, lane, false);
+            if (lane == 0) { S.cur[j] = b; S.want_end[j] = we; }
         }
         // first chunk bound in iteration direction = the seek key
         for (uint32_t i = tid; i < KS + 8; i += kScanThreads) {
@@ -423,7 +453,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                         const RunDev &r = P.rr.runs[j];
                         uint32_t c = S.cur[j], m = 1;
                         if (!S.lookahead) {
-                            uint32_t want_end = rev ? (index_lower_bound(r, endk, endl)) : index_lower_bound(r, endk, endl);
+                            uint32_t want_end = S.want_end[j];
                             uint32_t maxm = rev ? (c >= want_end ? c - want_end + 1 : 1) : (want_end >= c ? want_end - c + 1 : 1);
                             if (!rev && maxm > r.nb - c) maxm = r.nb - c;
                             if (rev && maxm > c + 1) maxm = c + 1;
@@ -803,17 +833,17 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                     else { S.lo_len = S.hi_len; S.has_lo = 1; S.lo_incl = 0; }
                 }
                 __syncthreads();
-                for (uint32_t j = tid; j < NR; j += kScanThreads) {
+                for (uint32_t j = warp; j < NR; j += kScanWarps) {
                     const RunDev &r = P.rr.runs[j];
-                    if (rev) {
-                        uint32_t b = index_lower_bound(r, khi, S.hi_len);
+                    uint32_t b;
+                    if (rev) { // blocks after b hold only keys > bound; b itself may hold keys <= bound
+                        b = warp_index_bound(r, khi, S.hi_len, lane, false);
                         if (b >= r.nb) b = r.nb ? r.nb - 1 : 0xFFFFFFFFu;
-                        // blocks after b hold only keys > bound; b itself may hold keys <= bound
-                        S.cur[j] = r.nb ? b : 0xFFFFFFFFu;
-                        // a run whose every key is > bound has nothing left: its first block's ... handled by validity window
+                        if (!r.nb) b = 0xFFFFFFFFu;
                     } else {
-                        S.cur[j] = index_upper_bound(r, klo, S.lo_len);
+                        b = warp_index_bound(r, klo, S.lo_len, lane, true);
                     }
+                    if (lane == 0) S.cur[j] = b;
                 }
                 __syncthreads();
             }
