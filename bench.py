@@ -386,7 +386,7 @@ def main():
                                    f"{HK}B hashkey/{SK}B sortkey/{VAL}B value (BASELINE.json configs[1])",
                        "records_per_step_per_gpu": n_records, "merged_bytes_per_step_per_gpu": in_bytes,
                        "survivors": int(res.out_records), "tiles": int(res.n_tiles), "filter": "KeyWithTTLCompactionFilter on",
-                       "l2": "inputs (2.9 GB of blocks) larger than the 126 MB L2", "ctas_per_sm": args.ctas_per_sm or 2,
+                       "l2": "inputs (2.9 GB of blocks) larger than the 126 MB L2", "ctas_per_sm": args.ctas_per_sm or 1,
                        "tma": not args.no_tma, "input_gen_s": round(gen_s, 1)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "reads": reads, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "wall_ms_per_step": wall_ms / args.steps,

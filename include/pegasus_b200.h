@@ -83,7 +83,7 @@ typedef struct {
     uint32_t block_size;       /* target data block bytes; 0 -> 4096 (RocksDB default, never
                                   overridden by Pegasus: pegasus_server_impl_init.cpp:666-848) */
     uint32_t restart_interval; /* 0 -> 16 (pegasus_server_impl_init.cpp:716-718)              */
-    uint32_t ctas_per_sm;      /* compaction kernel residency; 0 -> 2                         */
+    uint32_t ctas_per_sm;      /* compaction kernel residency: 1 = one 1024-thread CTA per SM (default), 2 = two 512-thread CTAs */
     uint32_t flags;            /* PGS_ENGINE_* below                                          */
 } pgs_engine_config;
 

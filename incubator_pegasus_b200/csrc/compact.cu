@@ -80,7 +80,7 @@ struct MergeParams {
     uint8_t *out_data;
     unsigned long long out_cap;
     unsigned long long *out_blk_off;
-    uint32_t *out_blk_size, *out_blk_rec, *out_ikey_off;
+    uint32_t *out_blk_size, *out_blk_rec, *out_ikey_off, *out_rec_off;
     uint8_t *out_ikeys;
     uint32_t out_blk_cap, out_ikey_cap;
     MergeStats *stats;
@@ -253,7 +253,8 @@ struct TileShared {
     uint32_t lo[kMaxRuns], nblk[kMaxRuns], nrec[kMaxRuns], in_off[kMaxRuns], rec_base[kMaxRuns], blk_base[kMaxRuns];
     uint32_t vlo[kMaxRuns], vhi[kMaxRuns], nabove[kMaxRuns];
     uint32_t nx_tile, nx_err; // next tile's ticket + slice metadata, fetched while this tile is being written
-    uint32_t nx_lo[kMaxRuns], nx_nblk[kMaxRuns], nx_nrec[kMaxRuns], nx_bytes[kMaxRuns];
+    uint32_t nx_lo[kMaxRuns], nx_nblk[kMaxRuns], nx_nrec[kMaxRuns], nx_bytes[kMaxRuns], nx_grec0[kMaxRuns];
+    uint32_t grec0[kMaxRuns]; // index of the slice's first record inside its run
     uint32_t scan[33];
     uint32_t stat[16];
     uint32_t tb_off[kMaxTileBlocks], tb_size[kMaxTileBlocks], tb_rec[kMaxTileBlocks], tb_nrec[kMaxTileBlocks];
@@ -343,12 +344,16 @@ PGS_DEV void fetch_next_tile(const MergeParams &P, TileShared &S, uint32_t lane)
         S.nx_lo[lane] = lo;
         S.nx_nblk[lane] = hi_ex - lo;
         S.nx_bytes[lane] = (uint32_t)(r.blk_off[hi_ex] - r.blk_off[lo]);
-        S.nx_nrec[lane] = r.blk_rec[hi_ex] - r.blk_rec[lo];
+        uint32_t g0 = r.blk_rec[lo];
+        S.nx_nrec[lane] = r.blk_rec[hi_ex] - g0;
+        S.nx_grec0[lane] = g0;
     }
 }
 
-__global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__ MergeParams P)
+template <uint32_t NT>
+__global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParams P)
 {
+    constexpr uint32_t NW = NT / 32;
     extern __shared__ __align__(128) uint8_t dyn[];
     __shared__ TileShared S;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
         mbar_fence_init();
     }
     if (P.validate_hash)
-        for (uint32_t i = tid; i < 256; i += kMergeThreads) S.crc[i] = P.crc_table[i];
+        for (uint32_t i = tid; i < 256; i += NT) S.crc[i] = P.crc_table[i];
     if (warp == 0) fetch_next_tile(P, S, lane);
     __syncthreads();
     uint32_t phase = 0;
@@ -382,6 +387,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
             S.nblk[tid] = S.nx_nblk[tid];
             S.in_off[tid] = S.nx_bytes[tid]; // bytes, offsets fixed below
             S.nrec[tid] = S.nx_nrec[tid];
+            S.grec0[tid] = S.nx_grec0[tid];
         }
         __syncthreads();
         if (tid == 0) {
@@ -424,7 +430,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
                     uint32_t bytes = (j + 1 < P.k ? S.in_off[j + 1] : S.in_bytes) - S.in_off[j];
                     const uint4 *src = (const uint4 *)(P.runs[j].data + P.runs[j].blk_off[S.lo[j]]);
                     uint4 *dst = (uint4 *)(A.in + S.in_off[j]);
-                    for (uint32_t i = tid; i < bytes / 16; i += kMergeThreads) dst[i] = src[i];
+                    for (uint32_t i = tid; i < bytes / 16; i += NT) dst[i] = src[i];
                 }
             }
             // boundary keys (zero padded slots)
@@ -435,11 +441,11 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
                 uint32_t b = ref & 0x0FFFFFFFu;
                 uint32_t off = r.ikey_off[b], len = r.ikey_off[b + 1] - off;
                 uint8_t *dst = which == 0 ? ulo : uhi;
-                for (uint32_t i = tid; i < KS + 8; i += kMergeThreads) dst[i] = i < len ? r.ikeys[off + i] : 0;
+                for (uint32_t i = tid; i < KS + 8; i += NT) dst[i] = i < len ? r.ikeys[off + i] : 0;
                 if (tid == 0) { if (which == 0) S.ulo_len = len; else S.uhi_len = len; }
             }
             // block table
-            for (uint32_t t = tid; t < S.n_blk_in; t += kMergeThreads) {
+            for (uint32_t t = tid; t < S.n_blk_in; t += NT) {
                 uint32_t j = 0;
                 while (j + 1 < P.k && t >= S.blk_base[j + 1]) j++;
                 const RunDev &r = P.runs[j];
@@ -449,6 +455,12 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
                 S.tb_rec[t] = S.rec_base[j] + (r.blk_rec[gb] - r.blk_rec[S.lo[j]]);
                 S.tb_nrec[t] = r.blk_rec[gb + 1] - r.blk_rec[gb];
             }
+            // every record's entry offset inside its block (device-built index): the header walk below needs no chain
+            for (uint32_t r = tid; r < S.n_rec; r += NT) {
+                uint32_t j = 0;
+                while (j + 1 < P.k && r >= S.rec_base[j + 1]) j++;
+                A.koff[r] = P.runs[j].rec_off[S.grec0[j] + (r - S.rec_base[j])];
+            }
             if (P.use_tma && S.in_bytes) {
                 mbar_wait((uint64_t *)&S.mbar, phase);
                 phase ^= 1;
@@ -456,56 +468,54 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
         }
         __syncthreads();
 
-        // ---- decode step 1: one THREAD per block walks the entry headers --------------------------
-        // (entries are sequential inside a block; blocks are independent: 32 blocks advance per warp instruction)
+        // ---- decode step 1: one THREAD per record parses its entry header (offsets come from the run's rec_off index) ----
         if (tile_ok) {
-            // block t goes to lane t/16 of warp t%16: the walks are latency chains, spreading them over all warps
-            // lets every scheduler interleave several of them instead of one warp crawling through all blocks
-            for (uint32_t t = warp + kMergeWarps * lane; t < S.n_blk_in; t += kMergeThreads) {
+            const uint32_t nblk = S.n_blk_in;
+            for (uint32_t r = tid; r < S.n_rec; r += NT) {
+                uint32_t lo = 0, hi = nblk; // block of record r: last t with tb_rec[t] <= r
+                while (lo + 1 < hi) { uint32_t mid = (lo + hi) >> 1; if (S.tb_rec[mid] <= r) lo = mid; else hi = mid; }
+                const uint32_t t = lo;
                 const uint8_t *base = A.in + S.tb_off[t];
-                uint32_t size = S.tb_size[t], rec0 = S.tb_rec[t], expect = S.tb_nrec[t];
+                const uint32_t size = S.tb_size[t], i = r - S.tb_rec[t], cnt = S.tb_nrec[t];
                 uint32_t err = 0, nr = 0;
                 if (size < 8) err = PGS_CORRUPTION;
                 if (!err) {
                     nr = ld_u32(base + size - 4);
                     if (nr == 0 || (unsigned long long)nr * 4 + 4 > size) err = PGS_CORRUPTION;
                 }
-                uint32_t limit = err ? 0 : size - 4 - 4 * nr;
-                uint32_t p = 0, prev_klen = 0, i = 0;
-                while (!err && p < limit && i < expect) {
+                const uint32_t limit = err ? 0 : size - 4 - 4 * nr;
+                const uint32_t p = A.koff[r];
+                if (!err && (p >= limit || (i == 0 && p != 0))) err = PGS_CORRUPTION;
+                if (!err) {
                     uint32_t shared, non_shared, vlen, h, c;
                     h = c = parse_header8(lds_u64_unaligned(base + p), shared, non_shared, vlen); // header bytes from registers
-                    if (!c) { // longer than 8 bytes: byte-wise decoder
+                    if (!c) { // uncommon shape: byte-wise decoder
                         h = 0;
                         c = get_varint32(base + p, limit - p, shared);
                         h += c;
                         if (c) { c = get_varint32(base + p + h, limit - p - h, non_shared); h += c; }
                         if (c) { c = get_varint32(base + p + h, limit - p - h, vlen); h += c; }
                     }
-                    uint32_t klen = shared + non_shared;
-                    if (!c || shared > prev_klen || klen < 8 || klen - 8 > KS || (unsigned long long)p + h + non_shared + vlen > limit) {
+                    const uint32_t klen = shared + non_shared;
+                    const unsigned long long end = (unsigned long long)p + h + non_shared + vlen;
+                    if (!c || klen < 8 || klen - 8 > KS || end > limit || (i == 0 && shared != 0) || (i + 1 == cnt && end != limit)) {
                         err = PGS_CORRUPTION;
-                        break;
+                    } else {
+                        A.rank[r] = (uint16_t)shared;      // scratch until the rank phase
+                        A.order[r] = (uint16_t)non_shared; // scratch until the scatter phase
+                        A.koff[r] = S.tb_off[t] + p + h;
+                        A.klen[r] = (uint16_t)(klen - 8);
+                        A.voff[r] = S.tb_off[t] + p + h + non_shared;
+                        A.vlen[r] = vlen;
+                        if (non_shared >= 8) { // the (seq<<8|type) trailer sits wholly in this entry's delta
+                            A.trailer[r] = lds_u64_unaligned(base + p + h + non_shared - 8);
+                            A.flags[r] = 0;
+                        } else {               // part of it is shared with the previous key: rebuilt in step 2
+                            A.trailer[r] = 0;
+                            A.flags[r] = 1;
+                        }
                     }
-                    uint32_t r = rec0 + i;
-                    A.rank[r] = (uint16_t)shared;      // scratch until the rank phase
-                    A.order[r] = (uint16_t)non_shared; // scratch until the scatter phase
-                    A.koff[r] = S.tb_off[t] + p + h;
-                    A.klen[r] = (uint16_t)(klen - 8);
-                    A.voff[r] = S.tb_off[t] + p + h + non_shared;
-                    A.vlen[r] = vlen;
-                    if (non_shared >= 8) { // the (seq<<8|type) trailer sits wholly in this entry's delta
-                        A.trailer[r] = lds_u64_unaligned(base + p + h + non_shared - 8);
-                        A.flags[r] = 0;
-                    } else {               // part of it is shared with the previous key: rebuilt in step 2
-                        A.trailer[r] = 0;
-                        A.flags[r] = 1;
-                    }
-                    prev_klen = klen;
-                    p += h + non_shared + vlen;
-                    i++;
                 }
-                if (!err && (i != expect || p != limit)) err = PGS_CORRUPTION;
                 if (err) atomicMax(&S.error, err);
             }
         }
@@ -516,17 +526,19 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
         // lane L owns internal-key positions 2L and 2L+1 (+64 per pass): the running value of a position is the
         // byte last written by an entry whose shared prefix ends at or before it.
         if (tile_ok) {
-            for (uint32_t t = warp; t < S.n_blk_in; t += kMergeWarps) {
+            for (uint32_t t = warp; t < S.n_blk_in; t += NW) {
                 const uint32_t rec0 = S.tb_rec[t], nrec = S.tb_nrec[t];
                 uint32_t maxk = 0;
                 for (uint32_t i = lane; i < nrec; i += 32) maxk = max(maxk, (uint32_t)A.klen[rec0 + i] + 8);
                 maxk = __reduce_max_sync(kFull, maxk);
                 for (uint32_t pass = 0; pass * 64 < maxk; pass++) {
                     const uint32_t p0 = pass * 64 + 2 * lane, p1 = p0 + 1;
-                    uint32_t c0 = 0, c1 = 0;
+                    uint32_t c0 = 0, c1 = 0, prev_klen = 0;
                     for (uint32_t i = 0; i < nrec; i++) {
                         const uint32_t r = rec0 + i;
                         const uint32_t sh = A.rank[r], ns = A.order[r], ulen = A.klen[r];
+                        if (sh > prev_klen) { if (lane == 0) atomicMax(&S.error, (uint32_t)PGS_CORRUPTION); break; } // a prefix longer than the previous key
+                        prev_klen = ulen + 8;
                         const uint8_t *d = A.in + A.koff[r];
                         if (p0 >= sh && p0 < sh + ns) c0 = d[p0 - sh];
                         if (p1 >= sh && p1 < sh + ns) c1 = d[p1 - sh];
@@ -553,7 +565,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
         // ---- valid range of every run's slice: user keys in (U_lo, U_hi]; records at or below U_lo form a
         //      prefix of a slice, records above U_hi a suffix, so counting them gives the window -----------
         if (tile_ok) {
-            for (uint32_t r = tid; r < S.n_rec; r += kMergeThreads) {
+            for (uint32_t r = tid; r < S.n_rec; r += NT) {
                 uint32_t j = 0;
                 while (j + 1 < P.k && r >= S.rec_base[j + 1]) j++;
                 const uint8_t *key = A.arena + (size_t)r * KS;
@@ -577,7 +589,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
 
         // ---- merge rank + shadow detection: one thread per record ------------------------------------
         if (tile_ok) {
-            for (uint32_t r = tid; r < S.n_rec; r += kMergeThreads) {
+            for (uint32_t r = tid; r < S.n_rec; r += NT) {
                 uint32_t j = 0;
                 while (j + 1 < P.k && r >= S.rec_base[j + 1]) j++;
                 uint32_t idx = r - S.rec_base[j];
@@ -618,7 +630,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
         // ---- compaction filter + tombstone policy; scatter into merged order -----------------------------
         if (tile_ok) {
             uint32_t s_in = 0, s_inb = 0, s_sh = 0, s_tomb = 0, s_exp = 0, s_user = 0, s_stale = 0, s_ttl = 0;
-            for (uint32_t r = tid; r < S.n_rec; r += kMergeThreads) {
+            for (uint32_t r = tid; r < S.n_rec; r += NT) {
                 uint8_t f = A.flags[r];
                 if (!(f & F_VALID)) continue;
                 uint32_t kl = A.klen[r], vl = A.vlen[r];
@@ -673,7 +685,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
         if (tile_ok) {
             const uint32_t nv = S.n_valid;
             m = chunked_scan(nv, A.E, S.scan, [&](uint32_t p) -> uint32_t { return (A.flags[A.order[p]] & F_KEEP) ? 1u : 0u; });
-            for (uint32_t p = tid; p < nv; p += kMergeThreads) {
+            for (uint32_t p = tid; p < nv; p += NT) {
                 uint32_t r = A.order[p];
                 if (A.flags[r] & F_KEEP) A.surv[A.E[p]] = (uint16_t)r;
             }
@@ -686,7 +698,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
                 return (p == 0 || A.R[p] / BS != A.R[p - 1] / BS) ? 1u : 0u;
             });
             if (nob > kMaxOutBlocks) { if (tid == 0) atomicMax(&S.error, (uint32_t)PGS_ABORTED); nob = 0; }
-            for (uint32_t p = tid; p < m; p += kMergeThreads) {
+            for (uint32_t p = tid; p < m; p += NT) {
                 bool firstp = p == 0 || A.R[p] / BS != A.R[p - 1] / BS;
                 uint32_t b = A.E[p] + (firstp ? 1u : 0u) - 1u; // E = exclusive count of block starts before p
                 A.blkid[p] = (uint16_t)b;
@@ -783,7 +795,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
         }
         __syncthreads();
         tile_ok = S.error == 0;
-        if (warp == kMergeWarps - 1) fetch_next_tile(P, S, lane); // overlaps the global-memory latency with the writes below
+        if (warp == NW - 1) fetch_next_tile(P, S, lane); // overlaps the global-memory latency with the writes below
 
         // ---- write the tile's blocks ------------------------------------------------------------------------------
         if (tile_ok && m > 0) {
@@ -795,11 +807,12 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
             __syncthreads();
             // (a) entry start offsets inside the tile's output + per-survivor stats, one thread per survivor
             uint32_t max_chunks = 0;
-            for (uint32_t p = tid; p < m; p += kMergeThreads) {
+            for (uint32_t p = tid; p < m; p += NT) {
                 const uint32_t r = A.surv[p], b = A.blkid[p];
                 const uint32_t kl = A.klen[r], vl = A.vlen[r];
                 const uint32_t eoff = S.ob_off[b] + (A.E[p] - A.E[S.cut[b]]);
                 A.R[p] = eoff;
+                P.out_rec_off[S.base_recs + p] = A.E[p] - A.E[S.cut[b]];
                 const uint8_t f = A.flags[r];
                 const unsigned long long tr = A.trailer[r];
                 const uint8_t type = (f & F_TOMB) ? (uint8_t)PGS_TYPE_DELETION : (uint8_t)tr;
@@ -832,7 +845,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
             //     stores whenever the bytes that do not belong to the value fall inside this entry's own head or
             //     the next entry's head of the same block: those heads are written after the barrier below and
             //     overwrite the spill.  Only where a spill could touch foreign bytes the exact byte range is stored.
-            for (uint32_t id = tid; id < m * CH; id += kMergeThreads) {
+            for (uint32_t id = tid; id < m * CH; id += NT) {
                 const uint32_t p = id / CH, c = id - p * CH;
                 const uint32_t r = A.surv[p];
                 const uint32_t vl = A.vlen[r];
@@ -872,7 +885,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
             __syncthreads();
             // (c) entry heads = 3 varints | key delta | trailer: half a warp per survivor, one byte per lane, the
             //     stores of a half-warp are consecutive bytes
-            for (uint32_t p = 2 * warp + (lane >> 4); p < m; p += 2 * kMergeWarps) {
+            for (uint32_t p = 2 * warp + (lane >> 4); p < m; p += 2 * NW) {
                 const uint32_t hl = lane & 15;
                 const uint32_t r = A.surv[p];
                 const uint32_t kl = A.klen[r], vl = A.vlen[r], shared = A.shr[p], hs = A.rank[p];
@@ -901,7 +914,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge(const __grid_constant__
                 atomicMax(&S.max_seq, mx_seq);
             }
             // restart arrays, padding, index entries: one thread per output block
-            for (uint32_t b = tid; b < nob; b += kMergeThreads) {
+            for (uint32_t b = tid; b < nob; b += NT) {
                 uint32_t c0 = S.cut[b], c1 = S.cut[b + 1], cnt = c1 - c0;
                 uint32_t nrest = (cnt + RI - 1) / RI;
                 uint32_t ent = A.E[c1] - A.E[c0];
@@ -1049,8 +1062,12 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
         }
     }
 
+    // ctas_per_sm: 2 -> two 512-thread CTAs per SM (default); 1 -> one 1024-thread CTA per SM with tiles twice as large
+    const bool big = e->cfg.ctas_per_sm == 1;
+    auto kern = big ? k_merge<1024> : k_merge<512>;
+    const uint32_t nthreads = big ? 1024 : 512;
     cudaFuncAttributes attr;
-    PGS_CUDA(cudaFuncGetAttributes(&attr, k_merge));
+    PGS_CUDA(cudaFuncGetAttributes(&attr, kern));
     uint32_t ctas = e->cfg.ctas_per_sm;
     const uint32_t fixed_dyn = 2 * (KS + 8);
     const uint64_t maxw = (((uint64_t)max_blk + 15) & ~15ull) + 16 + (uint64_t)max_blk_rec * P.rec_cost;
@@ -1106,6 +1123,7 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     CK(cudaMallocAsync(&outr->d_blk_rec, sizeof(uint32_t) * (blk_cap + 1), st));
     CK(cudaMallocAsync(&outr->d_ikey_off, sizeof(uint32_t) * (blk_cap + 1), st));
     CK(cudaMallocAsync(&outr->d_ikeys, ikey_cap, st));
+    CK(cudaMallocAsync(&outr->d_rec_off, sizeof(uint32_t) * (n_rec + 1), st));
     CK(cudaMallocAsync(&d_split_pos, sizeof(uint32_t) * (Q + 1) * k, st));
     CK(cudaMallocAsync(&d_split_ref, sizeof(uint32_t) * (Q + 1), st));
     CK(cudaMallocAsync(&d_ticket, 256, st));
@@ -1146,6 +1164,7 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     P.out_blk_rec = outr->d_blk_rec;
     P.out_ikey_off = outr->d_ikey_off;
     P.out_ikeys = outr->d_ikeys;
+    P.out_rec_off = outr->d_rec_off;
     P.out_blk_cap = (uint32_t)blk_cap;
     P.out_ikey_cap = (uint32_t)ikey_cap;
     P.stats = d_stats;
@@ -1154,13 +1173,13 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     CK(cudaEventCreate(&ev0));
     CK(cudaEventCreate(&ev1));
     CK(cudaEventCreate(&ev2));
-    CK(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    CK(cudaFuncSetAttribute(k_merge, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CK(cudaEventRecord(ev0, st));
     k_plan<<<(uint32_t)((total_blocks + 255) / 256), 256, 0, st>>>(P);
     CK(cudaEventRecord(ev1, st));
     uint32_t grid = (uint32_t)std::min<uint64_t>(Q, (uint64_t)ctas * e->sm_count);
-    k_merge<<<grid, kMergeThreads, dyn, st>>>(P);
+    kern<<<grid, nthreads, dyn, st>>>(P);
     CK(cudaEventRecord(ev2, st));
     e->launches += 2;
     CK(cudaMemcpyAsync(&hs, d_stats, sizeof hs, cudaMemcpyDeviceToHost, st));

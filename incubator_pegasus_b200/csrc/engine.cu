@@ -36,6 +36,7 @@ Run::~Run()
         cudaFreeAsync(d_blk_rec, pool_stream);
         cudaFreeAsync(d_ikey_off, pool_stream);
         cudaFreeAsync(d_ikeys, pool_stream);
+        cudaFreeAsync(d_rec_off, pool_stream);
         return;
     }
     cudaFree(d_data);
@@ -44,6 +45,7 @@ Run::~Run()
     cudaFree(d_blk_rec);
     cudaFree(d_ikey_off);
     cudaFree(d_ikeys);
+    cudaFree(d_rec_off);
 }
 Engine::~Engine()
 {
@@ -93,7 +95,8 @@ __global__ void __launch_bounds__(kIdxWarps * 32)
 k_index_walk(const uint8_t *__restrict__ data, const uint64_t *__restrict__ blk_off,
              const uint32_t *__restrict__ blk_size, uint32_t nb, uint32_t *__restrict__ nrec_out,
              uint32_t *__restrict__ lastlen_out, const uint32_t *__restrict__ ikey_off,
-             uint8_t *__restrict__ ikeys, IndexStats *__restrict__ stats)
+             uint8_t *__restrict__ ikeys, const uint32_t *__restrict__ blk_rec, uint32_t *__restrict__ rec_off,
+             IndexStats *__restrict__ stats)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -125,6 +128,7 @@ k_index_walk(const uint8_t *__restrict__ data, const uint64_t *__restrict__ blk_
         if (shared > prev_klen || klen < 8 || (uint64_t)p + h + non_shared + vlen > limit) { err = PGS_CORRUPTION; break; }
         if (klen > kMaxUkeyLen + 8) { err = PGS_NOT_SUPPORTED; break; }
         for (uint32_t i = lane; i < non_shared; i += 32) scr[shared + i] = base[p + h + i];
+        if (kEmitKey && lane == 0) rec_off[blk_rec[b] + nrec] = p;
         __syncwarp();
         if (!kEmitKey && lane == 0) {
             unsigned long long tr = 0;
@@ -183,7 +187,7 @@ int32_t build_index(Engine *e, Run *r, const uint64_t *h_blk_off, const uint32_t
     PGS_CUDA(cudaFuncSetAttribute(k_index_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PGS_CUDA(cudaFuncSetAttribute(k_index_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_index_walk<false><<<grid, kIdxWarps * 32, smem, st>>>(r->d_data, r->d_blk_off, r->d_blk_size, nb, d_nrec,
-                                                            d_lastlen, nullptr, nullptr, d_stats);
+                                                            d_lastlen, nullptr, nullptr, nullptr, nullptr, d_stats);
     e->launches++;
     std::vector<uint32_t> nrec(nb), lastlen(nb);
     PGS_CUDA(cudaMemcpyAsync(nrec.data(), d_nrec, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
@@ -217,10 +221,11 @@ int32_t build_index(Engine *e, Run *r, const uint64_t *h_blk_off, const uint32_t
     PGS_CUDA(cudaMalloc(&r->d_blk_rec, sizeof(uint32_t) * (nb + 1)));
     PGS_CUDA(cudaMalloc(&r->d_ikey_off, sizeof(uint32_t) * (nb + 1)));
     PGS_CUDA(cudaMalloc(&r->d_ikeys, kc + 16));
+    PGS_CUDA(cudaMalloc(&r->d_rec_off, sizeof(uint32_t) * (rc + 1)));
     PGS_CUDA(cudaMemcpyAsync(r->d_blk_rec, rec_cum.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
     PGS_CUDA(cudaMemcpyAsync(r->d_ikey_off, key_cum.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
     k_index_walk<true><<<grid, kIdxWarps * 32, smem, st>>>(r->d_data, r->d_blk_off, r->d_blk_size, nb, nullptr,
-                                                           nullptr, r->d_ikey_off, r->d_ikeys, d_stats);
+                                                           nullptr, r->d_ikey_off, r->d_ikeys, r->d_blk_rec, r->d_rec_off, d_stats);
     e->launches++;
     PGS_CUDA(cudaStreamSynchronize(st));
     cudaFree(d_stats);
@@ -261,7 +266,7 @@ int32_t pgs_engine_open(const pgs_engine_config *cfg, pgs_engine **out)
     if (cfg) e.cfg = *cfg;
     if (!e.cfg.block_size) e.cfg.block_size = kDefaultBlockSize;
     if (!e.cfg.restart_interval) e.cfg.restart_interval = kDefaultRestartInterval;
-    if (!e.cfg.ctas_per_sm) e.cfg.ctas_per_sm = 2;
+    if (!e.cfg.ctas_per_sm) e.cfg.ctas_per_sm = 1; // one 1024-thread CTA per SM measured faster than two 512-thread CTAs
     int dev = e.cfg.device;
     if (dev < 0) cudaGetDevice(&dev);
     e.device = dev;

@@ -22,6 +22,7 @@ struct RunDev {
     const uint32_t *blk_rec;  // [nb+1] cumulative record count
     const uint32_t *ikey_off; // [nb+1] offsets into ikeys
     const uint8_t *ikeys;     // last user key of every block, back to back
+    const uint32_t *rec_off;  // [n_records] byte offset of every entry inside its block (makes the header walk parallel)
     uint32_t nb;
     uint32_t max_ukey_len;
 };
@@ -37,11 +38,12 @@ struct Run {
     uint32_t *d_blk_rec = nullptr;
     uint32_t *d_ikey_off = nullptr;
     uint8_t *d_ikeys = nullptr;
+    uint32_t *d_rec_off = nullptr;
     uint64_t data_cap = 0;
     cudaStream_t pool_stream = nullptr; // set when the buffers came from cudaMallocAsync on that stream
     RunDev dev() const
     {
-        return RunDev{d_data, d_blk_off, d_blk_size, d_blk_rec, d_ikey_off, d_ikeys, info.n_blocks, info.max_ukey_len};
+        return RunDev{d_data, d_blk_off, d_blk_size, d_blk_rec, d_ikey_off, d_ikeys, d_rec_off, info.n_blocks, info.max_ukey_len};
     }
     ~Run();
 };
