@@ -32,8 +32,6 @@
 
 namespace pgs {
 
-constexpr uint32_t kMergeThreads = 512;
-constexpr uint32_t kMergeWarps = kMergeThreads / 32;
 constexpr uint32_t kMaxTileBlocks = 256;
 constexpr uint32_t kMaxOutBlocks = 128;
 constexpr uint32_t kRecExtra = 48; // per-record shared-memory bytes besides the key slot
@@ -845,8 +843,9 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             //     stores whenever the bytes that do not belong to the value fall inside this entry's own head or
             //     the next entry's head of the same block: those heads are written after the barrier below and
             //     overwrite the spill.  Only where a spill could touch foreign bytes the exact byte range is stored.
+            const uint32_t ch_magic = (uint32_t)((0x100000000ull + CH - 1) / CH); // id / CH by multiply-high (exact for id*CH < 2^32)
             for (uint32_t id = tid; id < m * CH; id += NT) {
-                const uint32_t p = id / CH, c = id - p * CH;
+                const uint32_t p = __umulhi(id, ch_magic), c = id - p * CH;
                 const uint32_t r = A.surv[p];
                 const uint32_t vl = A.vlen[r];
                 if (vl == 0) continue;
