@@ -176,9 +176,9 @@ int32_t build_index(Engine *e, Run *r, const uint64_t *h_blk_off, const uint32_t
     cudaStream_t st = e->stream;
     uint32_t *d_nrec = nullptr, *d_lastlen = nullptr;
     IndexStats *d_stats = nullptr;
-    PGS_CUDA(cudaMalloc(&d_nrec, sizeof(uint32_t) * nb));
-    PGS_CUDA(cudaMalloc(&d_lastlen, sizeof(uint32_t) * nb));
-    PGS_CUDA(cudaMalloc(&d_stats, sizeof(IndexStats)));
+    PGS_CUDA(cudaMallocAsync(&d_nrec, sizeof(uint32_t) * nb, st));
+    PGS_CUDA(cudaMallocAsync(&d_lastlen, sizeof(uint32_t) * nb, st));
+    PGS_CUDA(cudaMallocAsync(&d_stats, sizeof(IndexStats), st));
     IndexStats hs{};
     hs.min_seq = ~0ull;
     PGS_CUDA(cudaMemcpyAsync(d_stats, &hs, sizeof hs, cudaMemcpyHostToDevice, st));
@@ -194,10 +194,10 @@ int32_t build_index(Engine *e, Run *r, const uint64_t *h_blk_off, const uint32_t
     PGS_CUDA(cudaMemcpyAsync(lastlen.data(), d_lastlen, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
     PGS_CUDA(cudaMemcpyAsync(&hs, d_stats, sizeof hs, cudaMemcpyDeviceToHost, st));
     PGS_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_nrec);
-    cudaFree(d_lastlen);
+    cudaFreeAsync(d_nrec, st);
+    cudaFreeAsync(d_lastlen, st);
     if (hs.error) {
-        cudaFree(d_stats);
+        cudaFreeAsync(d_stats, st);
         set_error("run upload: block scan failed with status %u", hs.error);
         return (int32_t)hs.error;
     }
@@ -212,23 +212,23 @@ int32_t build_index(Engine *e, Run *r, const uint64_t *h_blk_off, const uint32_t
         max_blk = std::max(max_blk, h_blk_size[b]);
     }
     if (rc > 0xFFFFFFF0ull || kc > 0xFFFFFFF0ull) {
-        cudaFree(d_stats);
+        cudaFreeAsync(d_stats, st);
         set_error("run too large for 32-bit record / index-key offsets");
         return PGS_NOT_SUPPORTED;
     }
     rec_cum[nb] = (uint32_t)rc;
     key_cum[nb] = (uint32_t)kc;
-    PGS_CUDA(cudaMalloc(&r->d_blk_rec, sizeof(uint32_t) * (nb + 1)));
-    PGS_CUDA(cudaMalloc(&r->d_ikey_off, sizeof(uint32_t) * (nb + 1)));
-    PGS_CUDA(cudaMalloc(&r->d_ikeys, kc + 16));
-    PGS_CUDA(cudaMalloc(&r->d_rec_off, sizeof(uint32_t) * (rc + 1)));
+    PGS_CUDA(cudaMallocAsync(&r->d_blk_rec, sizeof(uint32_t) * (nb + 1), st));
+    PGS_CUDA(cudaMallocAsync(&r->d_ikey_off, sizeof(uint32_t) * (nb + 1), st));
+    PGS_CUDA(cudaMallocAsync(&r->d_ikeys, kc + 16, st));
+    PGS_CUDA(cudaMallocAsync(&r->d_rec_off, sizeof(uint32_t) * (rc + 1), st));
     PGS_CUDA(cudaMemcpyAsync(r->d_blk_rec, rec_cum.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
     PGS_CUDA(cudaMemcpyAsync(r->d_ikey_off, key_cum.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
     k_index_walk<true><<<grid, kIdxWarps * 32, smem, st>>>(r->d_data, r->d_blk_off, r->d_blk_size, nb, nullptr,
                                                            nullptr, r->d_ikey_off, r->d_ikeys, r->d_blk_rec, r->d_rec_off, d_stats);
     e->launches++;
     PGS_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_stats);
+    cudaFreeAsync(d_stats, st);
     r->info.n_records = hs.n_records;
     r->info.n_tombstones = hs.n_tomb;
     r->info.raw_key_bytes = hs.raw_key;
@@ -355,10 +355,11 @@ int32_t pgs_run_upload(pgs_partition *ph, int32_t level, const uint8_t *data, ui
     uint64_t end = (prev_end + kBlockAlign - 1) / kBlockAlign * kBlockAlign;
     r->info.data_bytes = end;
     r->data_cap = end + 256;
-    PGS_CUDA(cudaMalloc(&r->d_data, r->data_cap));
-    PGS_CUDA(cudaMalloc(&r->d_blk_off, sizeof(uint64_t) * (n_blocks + 1)));
-    PGS_CUDA(cudaMalloc(&r->d_blk_size, sizeof(uint32_t) * n_blocks));
     cudaStream_t st = e->stream;
+    r->pool_stream = st; // stream-ordered pool: repeated flush / compaction cycles reuse the same HBM without driver calls
+    PGS_CUDA(cudaMallocAsync(&r->d_data, r->data_cap, st));
+    PGS_CUDA(cudaMallocAsync(&r->d_blk_off, sizeof(uint64_t) * (n_blocks + 1), st));
+    PGS_CUDA(cudaMallocAsync(&r->d_blk_size, sizeof(uint32_t) * n_blocks, st));
     PGS_CUDA(cudaMemsetAsync(r->d_data + (data_bytes < end ? data_bytes : end), 0, r->data_cap - (data_bytes < end ? data_bytes : end), st));
     PGS_CUDA(cudaMemcpyAsync(r->d_data, data, data_bytes < end ? data_bytes : end, cudaMemcpyHostToDevice, st));
     std::vector<uint64_t> off(blk_off, blk_off + n_blocks);

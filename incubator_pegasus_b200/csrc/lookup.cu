@@ -21,7 +21,7 @@
 namespace pgs {
 
 constexpr uint32_t kGetWarps = 8;
-constexpr uint32_t kGetBlockBuf = 8192; // per-warp staging; larger blocks are read in place from HBM
+constexpr uint32_t kGetBlockBuf = 5120; // per-warp staging (a 4 KB-target block fits); larger blocks are read in place from HBM
 constexpr uint32_t kMaxReadRuns = 32;
 
 struct ReadRuns {
@@ -435,56 +435,59 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
             const bool stop_now = S.done || S.error;
             __syncthreads();
             if (stop_now) break;
-            // ---- choose blocks ------------------------------------------------------------------
-            if (tid == 0) {
-                uint32_t active = 0;
-                for (uint32_t j = 0; j < NR; j++) {
-                    const RunDev &r = P.rr.runs[j];
-                    bool has = rev ? (r.nb > 0 && S.cur[j] != 0xFFFFFFFFu) : (S.cur[j] < r.nb);
-                    S.nblk[j] = has ? 1 : 0;
-                    active += has;
+            // ---- choose blocks: warp 0, lane j = run j; a couple of independent global loads per run -----------
+            if (warp == 0) {
+                const uint32_t j = lane;
+                bool has = false;
+                uint32_t c = 0, m = 0, lo_b = 0, bytes_j = 0, recs_j = 0, more_j = 0;
+                const RunDev *rp = nullptr;
+                if (j < NR) {
+                    rp = &P.rr.runs[j];
+                    c = S.cur[j];
+                    has = rev ? (rp->nb > 0 && c != 0xFFFFFFFFu) : (c < rp->nb);
                 }
-                uint32_t bytes = 0, recs = 0, blks = 0;
-                if (active) {
-                    // per-run budget of the pool, at least one block each; a wanted range end limits the first fetch
-                    uint32_t budget = (P.pool_bytes - 64) / active;
-                    for (uint32_t j = 0; j < NR; j++) {
-                        if (!S.nblk[j]) continue;
-                        const RunDev &r = P.rr.runs[j];
-                        uint32_t c = S.cur[j], m = 1;
-                        if (!S.lookahead) {
-                            uint32_t want_end = S.want_end[j];
-                            uint32_t maxm = rev ? (c >= want_end ? c - want_end + 1 : 1) : (want_end >= c ? want_end - c + 1 : 1);
-                            if (!rev && maxm > r.nb - c) maxm = r.nb - c;
-                            if (rev && maxm > c + 1) maxm = c + 1;
-                            while (m < maxm) {
-                                uint32_t lo_b = rev ? c - m : c, hi_b = rev ? c + 1 : c + m + 1;
-                                unsigned long long w = (r.blk_off[hi_b] - r.blk_off[lo_b]) + 32 +
-                                                       (unsigned long long)(r.blk_rec[hi_b] - r.blk_rec[lo_b]) * (KS + kScanRecExtra);
-                                if (w > budget) break;
-                                m++;
-                            }
-                        }
-                        S.nblk[j] = m;
+                const uint32_t active = __popc(__ballot_sync(kFull, has));
+                if (has) {
+                    const RunDev &r = *rp;
+                    const uint32_t budget = (P.pool_bytes - 64) / active; // per-run share of the pool, at least one block each
+                    uint32_t maxm = 1;
+                    if (!S.lookahead) { // the wanted range end limits the first fetches
+                        uint32_t want_end = S.want_end[j];
+                        maxm = rev ? (c >= want_end ? c - want_end + 1 : 1) : (want_end >= c ? want_end - c + 1 : 1);
+                        if (!rev && maxm > r.nb - c) maxm = r.nb - c;
+                        if (rev && maxm > c + 1) maxm = c + 1;
                     }
-                    for (uint32_t j = 0; j < NR; j++) {
-                        const RunDev &r = P.rr.runs[j];
-                        uint32_t m = S.nblk[j];
-                        S.in_off[j] = bytes; S.rec_base[j] = recs; S.blk_base[j] = blks;
-                        S.nrec[j] = 0; S.more[j] = 0;
-                        if (!m) continue;
-                        uint32_t lo_b = rev ? S.cur[j] + 1 - m : S.cur[j], hi_b = lo_b + m;
-                        bytes += (uint32_t)(r.blk_off[hi_b] - r.blk_off[lo_b]);
-                        S.nrec[j] = r.blk_rec[hi_b] - r.blk_rec[lo_b];
-                        recs += S.nrec[j];
-                        blks += m;
-                        S.more[j] = rev ? (lo_b > 0) : (hi_b < r.nb);
+                    auto weight = [&](uint32_t mm) -> unsigned long long {
+                        uint32_t l = rev ? c + 1 - mm : c, h = l + mm;
+                        return (r.blk_off[h] - r.blk_off[l]) + 32 + (unsigned long long)(r.blk_rec[h] - r.blk_rec[l]) * (KS + kScanRecExtra);
+                    };
+                    m = maxm;
+                    if (maxm > 1 && weight(maxm) > budget) { // rare: largest m in [1, maxm) that fits (cumulative arrays)
+                        uint32_t lo = 1, hi = maxm;
+                        while (lo + 1 < hi) { uint32_t mid = (lo + hi) >> 1; if (weight(mid) <= budget) lo = mid; else hi = mid; }
+                        m = lo;
                     }
+                    lo_b = rev ? c + 1 - m : c;
+                    bytes_j = (uint32_t)(r.blk_off[lo_b + m] - r.blk_off[lo_b]);
+                    recs_j = r.blk_rec[lo_b + m] - r.blk_rec[lo_b];
+                    more_j = rev ? (lo_b > 0) : (lo_b + m < r.nb);
                 }
-                S.in_bytes = bytes; S.n_rec = recs; S.n_blk = blks;
-                ScanArrays a0 = scan_carve(pool, bytes, recs, KS);
-                if (a0.total > P.pool_bytes || blks > kScanMaxBlocks || recs > 65000) S.error = PGS_NOT_SUPPORTED;
-                if (!active) S.done = 1; // every run exhausted: the iterator is invalid
+                const uint32_t ib = warp_incl_scan(bytes_j, lane), ir = warp_incl_scan(recs_j, lane), im = warp_incl_scan(m, lane);
+                if (j < NR) {
+                    S.nblk[j] = m;
+                    S.in_off[j] = ib - bytes_j;
+                    S.rec_base[j] = ir - recs_j;
+                    S.blk_base[j] = im - m;
+                    S.nrec[j] = recs_j;
+                    S.more[j] = more_j;
+                }
+                const uint32_t bytes = __shfl_sync(kFull, ib, 31), recs = __shfl_sync(kFull, ir, 31), blks = __shfl_sync(kFull, im, 31);
+                if (lane == 0) {
+                    S.in_bytes = bytes; S.n_rec = recs; S.n_blk = blks;
+                    ScanArrays a0 = scan_carve(pool, bytes, recs, KS);
+                    if (a0.total > P.pool_bytes || blks > kScanMaxBlocks || recs > 65000) S.error = PGS_NOT_SUPPORTED;
+                    if (!active) S.done = 1; // every run exhausted: the iterator is invalid
+                }
             }
             __syncthreads();
             if (S.done || S.error) break;
