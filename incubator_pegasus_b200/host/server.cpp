@@ -95,6 +95,8 @@ struct Server {
     uint64_t mem_bytes = 0, last_seq = 0;
     int64_t last_flushed_decree = 0;
     int64_t ctx_counter = 0;
+    uint64_t manual_compact_last_finish_ms = 0; // pegasus_manual_compact_service: _manual_compact_last_finish_time_ms
+    bool manual_compact_disabled = false;
     std::unordered_map<int64_t, std::unique_ptr<ScanContext>> ctx;
 
     uint32_t cfg_scan_count() const { return opt.rocksdb_max_iteration_count ? opt.rocksdb_max_iteration_count : 1000; }
@@ -202,6 +204,33 @@ struct Server {
         }
     }
 };
+
+// do_manual_compact (pegasus_server_impl.cpp:3373-3456): flush, then CompactRange over the whole column family.
+// force=false is BottommostLevelCompaction::kSkip: a DB that already is one bottom run is left alone.
+static int32_t do_manual_compact(Server &s, uint32_t now, int32_t target_level, bool force, pgs_compact_result *out)
+{
+    if (out) memset(out, 0, sizeof *out);
+    int32_t st = s.flush_mem(); // flush_all_family_columns(true)
+    if (st != PGS_OK) return st;
+    auto rs = s.runs();
+    if (rs.empty()) return PGS_OK;
+    if (!force && rs.size() == 1 && rs[0]->level >= 1) return PGS_OK;
+    int32_t level = 1;
+    std::vector<uint64_t> ids;
+    for (auto &r : rs) { level = std::max(level, r->level); ids.push_back(r->id); }
+    if (target_level >= 1) level = target_level;
+    while (ids.size() > kMaxRuns) { // deeper than one merge launch: fold the oldest runs first
+        std::vector<uint64_t> tail(ids.end() - kMaxRuns, ids.end());
+        pgs_filter_params fp = s.filter();
+        pgs_compact_result cr{};
+        st = pgs_compact(s.part, tail.data(), kMaxRuns, level, 1, &fp, now, &cr);
+        if (st != PGS_OK) return st;
+        ids.resize(ids.size() - kMaxRuns);
+        if (cr.new_run_id) ids.push_back(cr.new_run_id);
+    }
+    pgs_filter_params fp = s.filter();
+    return pgs_compact(s.part, ids.data(), (uint32_t)ids.size(), level, 1, &fp, now, out);
+}
 
 static inline std::string_view bsv(const pgs_blob &b) { return std::string_view((const char *)b.data, b.len); }
 static inline pgs_blob blob_of(const std::string &s) { return pgs_blob{(const uint8_t *)s.data(), (uint32_t)s.size()}; }
@@ -541,8 +570,31 @@ int32_t pgs_rrdb_update_app_envs(pgs_server *h, const char *envs, uint32_t n_env
             if (!e.second.empty()) ops_parse(e.second, s.data_version, s.ops_bin, nullptr);
         }
     }
-    (void)now;
-    return PGS_OK;
+    // start_manual_compact_if_needed (pegasus_manual_compact_service.cpp:83-121): disabled flag, then the `once` rule:
+    // trigger_time (unix seconds) newer than the last finished manual compaction.  (`periodic` HH:MM rules need the
+    // wall clock of the host process and stay with the caller.)
+    std::map<std::string, std::string> m(kv.begin(), kv.end());
+    auto f = m.find("manual_compact.disabled");
+    s.manual_compact_disabled = f != m.end() && f->second == "true";
+    if (s.manual_compact_disabled) return PGS_OK;
+    f = m.find("manual_compact.once.trigger_time");
+    if (f == m.end()) return PGS_OK;
+    char *endp = nullptr;
+    long long trigger = strtoll(f->second.c_str(), &endp, 10);
+    if (f->second.empty() || *endp || trigger <= 0) return PGS_OK;
+    if ((uint64_t)trigger <= s.manual_compact_last_finish_ms / 1000) return PGS_OK; // check_once_compact :160-173
+    int32_t target_level = -1; // extract_manual_compact_opts :217-262
+    f = m.find("manual_compact.once.target_level");
+    if (f != m.end()) {
+        long tl = strtol(f->second.c_str(), &endp, 10);
+        if (!f->second.empty() && !*endp && (tl == -1 || (tl >= 1 && tl <= 6))) target_level = (int32_t)tl;
+    }
+    bool force = false; // default BottommostLevelCompaction::kSkip
+    f = m.find("manual_compact.once.bottommost_level_compaction");
+    if (f != m.end() && f->second == "force") force = true;
+    int32_t st = do_manual_compact(s, now, target_level, force, nullptr);
+    if (st == PGS_OK) s.manual_compact_last_finish_ms = ((uint64_t)now + kEpochBegin) * 1000;
+    return st;
 }
 
 int32_t pgs_rrdb_start(pgs_engine *e, int32_t app_id, int32_t pidx, const pgs_server_options *opt, const char *envs,
@@ -646,28 +698,9 @@ int32_t pgs_rrdb_flush(pgs_server *h, uint32_t now)
 int32_t pgs_rrdb_manual_compact(pgs_server *h, uint32_t now, pgs_compact_result *out)
 {
     LOCKED(h);
-    Server &s = h->s;
-    if (out) memset(out, 0, sizeof *out);
-    int32_t st = s.flush_mem(); // flush_all_family_columns(true), pegasus_server_impl.cpp:3373-3388
-    if (st != PGS_OK) return st;
-    auto rs = s.runs();
-    if (rs.empty()) return PGS_OK;
-    int32_t level = 1;
-    std::vector<uint64_t> ids;
-    for (auto &r : rs) { level = std::max(level, r->level); ids.push_back(r->id); }
-    if (ids.size() > kMaxRuns) { // deeper than one merge launch: fold the oldest runs first
-        while (ids.size() > kMaxRuns) {
-            std::vector<uint64_t> tail(ids.end() - kMaxRuns, ids.end());
-            pgs_filter_params fp = s.filter();
-            pgs_compact_result cr{};
-            st = pgs_compact(s.part, tail.data(), kMaxRuns, level, 1, &fp, now, &cr);
-            if (st != PGS_OK) return st;
-            ids.resize(ids.size() - kMaxRuns);
-            if (cr.new_run_id) ids.push_back(cr.new_run_id);
-        }
-    }
-    pgs_filter_params fp = s.filter();
-    return pgs_compact(s.part, ids.data(), (uint32_t)ids.size(), level, 1, &fp, now, out); // bottommost_level_compaction = force
+    int32_t st = do_manual_compact(h->s, now, -1, true, out); // bottommost_level_compaction = force
+    if (st == PGS_OK) h->s.manual_compact_last_finish_ms = ((uint64_t)now + kEpochBegin) * 1000;
+    return st;
 }
 int64_t pgs_rrdb_last_flushed_decree(pgs_server *h) { return h->s.last_flushed_decree; }
 

@@ -128,6 +128,7 @@ struct Server {
     std::vector<Op> ops;
     uint64_t last_seq = 0;
     int64_t last_flushed_decree = 0;
+    uint64_t manual_compact_last_finish_ms = 0;
     std::map<std::string, Rec> mem;
     uint64_t mem_bytes = 0;
     struct LRun { int level; Run run; };
@@ -637,7 +638,33 @@ int32_t orc_rrdb_update_app_envs(orc_server *h, const char *envs, uint32_t n_env
             s.ops = e.second.empty() ? std::vector<Op>() : ops_from_json(e.second, s.data_version);
         }
     }
-    (void)now;
+    // pegasus_manual_compact_service.cpp:83-121,160-173,217-262: disabled flag, `once` rule, options
+    std::map<std::string, std::string> m(kv.begin(), kv.end());
+    auto f = m.find("manual_compact.disabled");
+    if (f != m.end() && f->second == "true") return PGS_OK;
+    f = m.find("manual_compact.once.trigger_time");
+    if (f == m.end()) return PGS_OK;
+    char *endp = nullptr;
+    long long trigger = strtoll(f->second.c_str(), &endp, 10);
+    if (f->second.empty() || *endp || trigger <= 0) return PGS_OK;
+    if ((uint64_t)trigger <= s.manual_compact_last_finish_ms / 1000) return PGS_OK;
+    int target_level = -1;
+    f = m.find("manual_compact.once.target_level");
+    if (f != m.end()) {
+        long tl = strtol(f->second.c_str(), &endp, 10);
+        if (!f->second.empty() && !*endp && (tl == -1 || (tl >= 1 && tl <= 6))) target_level = (int)tl;
+    }
+    bool force = false;
+    f = m.find("manual_compact.once.bottommost_level_compaction");
+    if (f != m.end() && f->second == "force") force = true;
+    s.flush_mem();
+    if (!s.runs.empty() && (force || !(s.runs.size() == 1 && s.runs[0].level >= 1))) {
+        int level = 1;
+        for (auto &lr : s.runs) level = std::max(level, lr.level);
+        if (target_level >= 1) level = target_level;
+        s.compact_runs(0, s.runs.size(), level, now, nullptr);
+    }
+    s.manual_compact_last_finish_ms = ((uint64_t)now + kEpochBegin) * 1000;
     return PGS_OK;
 }
 
@@ -757,6 +784,7 @@ int32_t orc_rrdb_manual_compact(orc_server *h, uint32_t now, orc_compact_stats *
         for (auto &lr : s.runs) level = std::max(level, lr.level);
         s.compact_runs(0, s.runs.size(), level, now, &local);
     }
+    s.manual_compact_last_finish_ms = ((uint64_t)now + kEpochBegin) * 1000;
     if (st) *st = local;
     return PGS_OK;
 }

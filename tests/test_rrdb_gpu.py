@@ -311,3 +311,28 @@ def test_randomized_differential(engine):
     finally:
         for be in pair:
             be.close()
+
+
+def test_manual_compact_env_trigger(pair):
+    """pegasus_manual_compact_service `once` rule: trigger_time newer than the last finish starts a full compaction
+    with the filter; the same env again does nothing; `disabled` wins."""
+    unix = lambda now: now + 1451606400
+    for be in pair:
+        be.put(b"mc", b"keep", b"1")
+        be.put(b"mc", b"dead", b"2", expire_ts=NOW - 5, now=NOW - 10)
+        be.flush(NOW)
+        be.put(b"mc", b"keep2", b"3")
+        be.update_envs({"default_ttl": "900"})
+    for be in pair:
+        be.update_envs({"manual_compact.disabled": "true", "manual_compact.once.trigger_time": str(unix(NOW))}, now=NOW)
+    assert check(pair, "ttl", b"mc", b"keep", now=NOW)["ttl"] == -1  # nothing ran
+    for be in pair:
+        be.update_envs({"manual_compact.once.trigger_time": str(unix(NOW)), "manual_compact.once.bottommost_level_compaction": "force"}, now=NOW)
+    assert check(pair, "ttl", b"mc", b"keep", now=NOW)["ttl"] == 900  # default_ttl rewrite happened
+    assert check(pair, "get", b"mc", b"dead", now=NOW)["error"] == 1
+    for be in pair:
+        be.update_envs({"default_ttl": "100"})
+        be.update_envs({"manual_compact.once.trigger_time": str(unix(NOW))}, now=NOW + 50)  # not newer than the last finish
+        be.put(b"mc", b"later", b"4", now=NOW + 50)
+    assert check(pair, "ttl", b"mc", b"keep", now=NOW + 50)["ttl"] == 850
+    check(pair, "multi_get", b"mc", now=NOW + 50)
