@@ -274,26 +274,37 @@ def main():
     # ---- read path on the same partition (4 overlapping runs resident): YCSB-C shaped, zipfian hash keys ----------
     reads = None
     if not args.skip_reads:
+        pins = []
+
+        def pinned(n, dt):  # host buffers of the read legs live in pinned memory, like a server's I/O buffers
+            t = torch.empty(int(n) * np.dtype(dt).itemsize, dtype=torch.uint8).pin_memory()
+            pins.append(t)
+            return t.numpy().view(dt)
+
         gk, sk = read_workload(args.records_per_run, args.n_get, args.n_scan, 1000 + rank)
-        gkeys = np.ascontiguousarray(gk.reshape(-1))
-        goff = (np.arange(args.n_get + 1, dtype=np.uint32) * np.uint32(gk.shape[1]))
+        gkeys = pinned(gk.size, np.uint8)
+        gkeys[:] = gk.reshape(-1)
+        goff = pinned(args.n_get + 1, np.uint32)
+        goff[:] = np.arange(args.n_get + 1, dtype=np.uint32) * np.uint32(gk.shape[1])
         hashkeys = [bytes(r) for r in sk]
         garena_cap = args.n_get * (VAL + 8)
+        garena_buf = pinned(garena_cap, np.uint8)
+        gres_buf = (pgs.GetResult * args.n_get)()
         reps = max(3, args.steps)
         # gets
-        part.get_batch(gkeys, goff, NOW, arena_cap=garena_cap)
+        part.get_batch(gkeys, goff, NOW, arena_cap=garena_cap, arena=garena_buf, results=gres_buf)
         g_ms, g_wall, found, probes = [], [], 0, 0
         for _ in range(reps):
             barrier()
             t0 = time.perf_counter()
-            st, gres, garena, gused = part.get_batch(gkeys, goff, NOW, arena_cap=garena_cap)
+            st, gres, garena, gused = part.get_batch(gkeys, goff, NOW, arena_cap=garena_cap, arena=garena_buf, results=gres_buf)
             g_wall.append((time.perf_counter() - t0) * 1e3)
             g_ms.append(eng.last_kernel_ms)
             probes = eng.last_blocks_probed
         found = sum(1 for i in range(0, args.n_get, max(1, args.n_get // 4096)) if gres[i].status == 0)
         found_frac = found / len(range(0, args.n_get, max(1, args.n_get // 4096)))
         # prefix scans = multi_get(hash_key, all sort keys)
-        sb = part.prefix_scan_batch(hashkeys, max_records=80, arena_stride=24576)  # request structs marshalled once
+        sb = part.prefix_scan_batch(hashkeys, max_records=80, arena_stride=24576, alloc=pinned)  # request structs marshalled once
         assert sb.run(NOW) == 0
         s_ms, s_wall = [], []
         for _ in range(reps):

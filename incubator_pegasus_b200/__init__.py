@@ -453,23 +453,25 @@ class Partition:
                                     C.byref(fp), now, flags, C.byref(res)), "compact")
         return res
 
-    def prefix_scan_batch(self, hashkeys, max_records: int = 1000, arena_stride: int = 32768) -> "ScanBatch":
+    def prefix_scan_batch(self, hashkeys, max_records: int = 1000, arena_stride: int = 32768, alloc=None) -> "ScanBatch":
         """multi_get(hash_key, all sort keys) for many hash keys: the request structs are marshalled once, run() is
         the C-ABI call (pgs_range_scan_many) from host buffers."""
-        return ScanBatch(self, hashkeys, max_records, arena_stride)
+        return ScanBatch(self, hashkeys, max_records, arena_stride, alloc)
 
-    def get_batch(self, keys: np.ndarray, key_off: np.ndarray, now: int, arena_cap: int | None = None):
+    def get_batch(self, keys: np.ndarray, key_off: np.ndarray, now: int, arena_cap: int | None = None, arena=None, results=None):
         n = key_off.shape[0] - 1
-        results = (GetResult * n)()
+        results = (GetResult * n)() if results is None else results
         cap = arena_cap if arena_cap is not None else max(1 << 16, n * 1024)
-        arena = np.zeros(cap, np.uint8)
+        arena = np.zeros(cap, np.uint8) if arena is None else arena
+        cap = min(cap, arena.shape[0])
         used = C.c_uint64()
         st = lib().pgs_get_batch(self.h, _ptr(keys), _ptr(key_off), n, now, _ptr(arena), cap, results, C.byref(used))
         return st, results, arena, used.value
 
 
 class ScanBatch:
-    def __init__(self, part: Partition, hashkeys, max_records: int, arena_stride: int):
+    def __init__(self, part: Partition, hashkeys, max_records: int, arena_stride: int, alloc=None):
+        alloc = alloc or (lambda n, dt: np.zeros(n, dt))  # bench.py passes a pinned-memory allocator
         self.part = part
         n = len(hashkeys)
         self.n = n
@@ -489,8 +491,8 @@ class ScanBatch:
             q.start_inclusive, q.stop_inclusive, q.key_mode, q.prefix_same_as_start = 1, 0, 1, 1
             q.max_count, q.max_iter_count = max_records, 3000
         self.max_records, self.arena_stride = max_records, arena_stride
-        self.arena = np.zeros(n * arena_stride, np.uint8)
-        self.kvs = np.zeros(n * max_records * 5, np.uint32)
+        self.arena = alloc(n * arena_stride, np.uint8)
+        self.kvs = alloc(n * max_records * 5, np.uint32)
         self.results = (ScanResult * n)()
         self.abase = np.zeros(n + 1, np.uint64)
         self.kbase = np.zeros(n + 1, np.uint32)

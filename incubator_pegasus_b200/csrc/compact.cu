@@ -520,39 +520,48 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
         __syncthreads();
         tile_ok = S.error == 0;
 
-        // ---- decode step 2: one WARP per block rebuilds the keys, two key bytes per lane -------------
-        // lane L owns internal-key positions 2L and 2L+1 (+64 per pass): the running value of a position is the
-        // byte last written by an entry whose shared prefix ends at or before it.
+        // ---- decode step 2: HALF a warp per block rebuilds the keys, four key bytes per lane -----------
+        // lane L (0..15) of a half-warp owns internal-key positions 4L..4L+3 (+64 per pass): the running value of a
+        // position is the byte last written by an entry whose shared prefix ends at or before it.
         if (tile_ok) {
-            for (uint32_t t = warp; t < S.n_blk_in; t += NW) {
+            const uint32_t hl = lane & 15, sub = lane >> 4;
+            const uint32_t hmask = sub ? 0xffff0000u : 0x0000ffffu;
+            for (uint32_t t = 2 * warp + sub; t < S.n_blk_in; t += 2 * NW) {
                 const uint32_t rec0 = S.tb_rec[t], nrec = S.tb_nrec[t];
                 uint32_t maxk = 0;
-                for (uint32_t i = lane; i < nrec; i += 32) maxk = max(maxk, (uint32_t)A.klen[rec0 + i] + 8);
-                maxk = __reduce_max_sync(kFull, maxk);
+                for (uint32_t i = hl; i < nrec; i += 16) maxk = max(maxk, (uint32_t)A.klen[rec0 + i] + 8);
+                maxk = __reduce_max_sync(hmask, maxk);
                 for (uint32_t pass = 0; pass * 64 < maxk; pass++) {
-                    const uint32_t p0 = pass * 64 + 2 * lane, p1 = p0 + 1;
-                    uint32_t c0 = 0, c1 = 0, prev_klen = 0;
+                    const uint32_t p0 = pass * 64 + 4 * hl;
+                    uint32_t cur = 0, prev_klen = 0; // the four running bytes, little endian
                     for (uint32_t i = 0; i < nrec; i++) {
                         const uint32_t r = rec0 + i;
                         const uint32_t sh = A.rank[r], ns = A.order[r], ulen = A.klen[r];
-                        if (sh > prev_klen) { if (lane == 0) atomicMax(&S.error, (uint32_t)PGS_CORRUPTION); break; } // a prefix longer than the previous key
+                        if (sh > prev_klen) { if (hl == 0) atomicMax(&S.error, (uint32_t)PGS_CORRUPTION); break; } // a prefix longer than the previous key
                         prev_klen = ulen + 8;
                         const uint8_t *d = A.in + A.koff[r];
-                        if (p0 >= sh && p0 < sh + ns) c0 = d[p0 - sh];
-                        if (p1 >= sh && p1 < sh + ns) c1 = d[p1 - sh];
+#pragma unroll
+                        for (uint32_t x = 0; x < 4; x++) {
+                            const uint32_t p = p0 + x;
+                            if (p >= sh && p < sh + ns) cur = (cur & ~(0xffu << (8 * x))) | ((uint32_t)d[p - sh] << (8 * x));
+                        }
                         const uint32_t pad = (ulen + 7) & ~7u; // slots are zero padded to 8 bytes
                         if (p0 < pad) {
-                            uint32_t b0 = p0 < ulen ? c0 : 0, b1 = p1 < ulen ? c1 : 0;
-                            *(uint16_t *)(A.arena + (size_t)r * KS + p0) = (uint16_t)(b0 | (b1 << 8));
+                            uint32_t keep = ulen > p0 ? ulen - p0 : 0; // bytes of this word that belong to the user key
+                            uint32_t v = keep >= 4 ? cur : (cur & ((1u << (8 * keep)) - 1u));
+                            *(uint32_t *)(A.arena + (size_t)r * KS + p0) = v;
                         }
                         // rare: the 8 trailer bytes after the user key straddle the shared prefix
                         if (A.flags[r] && pass * 64 < ulen + 8 && pass * 64 + 64 > ulen) {
                             uint32_t lo = 0, hi = 0;
-                            if (p0 >= ulen && p0 < ulen + 8) { uint32_t j = p0 - ulen; if (j < 4) lo |= c0 << (8 * j); else hi |= c0 << (8 * (j - 4)); }
-                            if (p1 >= ulen && p1 < ulen + 8) { uint32_t j = p1 - ulen; if (j < 4) lo |= c1 << (8 * j); else hi |= c1 << (8 * (j - 4)); }
-                            lo = __reduce_or_sync(kFull, lo);
-                            hi = __reduce_or_sync(kFull, hi);
-                            if (lane == 0) A.trailer[r] |= ((unsigned long long)hi << 32) | lo;
+#pragma unroll
+                            for (uint32_t x = 0; x < 4; x++) {
+                                const uint32_t p = p0 + x, c = (cur >> (8 * x)) & 0xffu;
+                                if (p >= ulen && p < ulen + 8) { uint32_t j = p - ulen; if (j < 4) lo |= c << (8 * j); else hi |= c << (8 * (j - 4)); }
+                            }
+                            lo = __reduce_or_sync(hmask, lo);
+                            hi = __reduce_or_sync(hmask, hi);
+                            if (hl == 0) A.trailer[r] |= ((unsigned long long)hi << 32) | lo;
                         }
                     }
                 }
@@ -585,42 +594,53 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             S.n_valid = nv;
         }
 
-        // ---- merge rank + shadow detection: one thread per record ------------------------------------
+        // ---- merge rank + shadow detection -----------------------------------------------------------------
+        // (1) one thread per record: validity, position inside its own run, predecessor of the same run;
+        // (2) one thread per (record, other run): LCP-aware binary search for the number of that run's records that
+        //     sort before it; ranks accumulate with shared-memory atomics, so the searches of one record run in parallel.
         if (tile_ok) {
             for (uint32_t r = tid; r < S.n_rec; r += NT) {
                 uint32_t j = 0;
                 while (j + 1 < P.k && r >= S.rec_base[j + 1]) j++;
                 uint32_t idx = r - S.rec_base[j];
                 if (idx < S.vlo[j] || idx >= S.vhi[j]) { A.flags[r] = 0; continue; }
+                const uint32_t kl = A.klen[r];
+                bool shadow = idx > 0 && A.klen[r - 1] == kl && cmp_slots(A.arena + (size_t)(r - 1) * KS, kl, A.arena + (size_t)r * KS, kl) == 0;
+                A.R[r] = idx - S.vlo[j];
+                A.E[r] = shadow ? 1u : 0u;
+                A.flags[r] = F_VALID;
+            }
+        }
+        __syncthreads();
+        if (tile_ok && P.k > 1) {
+            const uint32_t km1 = P.k - 1, ntask = S.n_rec * km1;
+            for (uint32_t id = tid; id < ntask; id += NT) {
+                const uint32_t r = id / km1, oi = id - r * km1;
+                if (!(A.flags[r] & F_VALID)) continue;
+                uint32_t j = 0;
+                while (j + 1 < P.k && r >= S.rec_base[j + 1]) j++;
+                const uint32_t o = oi < j ? oi : oi + 1;
                 const uint8_t *key = A.arena + (size_t)r * KS;
-                uint32_t kl = A.klen[r];
-                unsigned long long tr = A.trailer[r];
-                uint32_t rank = idx - S.vlo[j];
-                bool shadow = false;
-                if (idx > 0 && A.klen[r - 1] == kl && cmp_slots(A.arena + (size_t)(r - 1) * KS, kl, key, kl) == 0) shadow = true;
-                for (uint32_t o = 0; o < P.k; o++) {
-                    if (o == j) continue;
-                    uint32_t base = S.rec_base[o], lo = S.vlo[o], hi = S.vhi[o];
-                    uint32_t lcp_lo = 0, lcp_hi = 0; // words shared with the keys just outside [lo, hi)
-                    while (lo < hi) { // first position whose internal key is not before ours
-                        uint32_t mid = (lo + hi) >> 1, q = base + mid, d;
-                        int c = cmp_slots_from(A.arena + (size_t)q * KS, A.klen[q], key, kl, min(lcp_lo, lcp_hi), &d);
-                        bool before;
-                        if (c != 0) before = c < 0;
-                        else {
-                            unsigned long long tq = A.trailer[q];
-                            before = tq > tr || (tq == tr && o < j);
-                        }
-                        if (before) { lo = mid + 1; lcp_lo = d; } else { hi = mid; lcp_hi = d; }
+                const uint32_t kl = A.klen[r];
+                const unsigned long long tr = A.trailer[r];
+                uint32_t base = S.rec_base[o], lo = S.vlo[o], hi = S.vhi[o];
+                uint32_t lcp_lo = 0, lcp_hi = 0; // words shared with the keys just outside [lo, hi)
+                while (lo < hi) { // first position whose internal key is not before ours
+                    uint32_t mid = (lo + hi) >> 1, q = base + mid, d;
+                    int c = cmp_slots_from(A.arena + (size_t)q * KS, A.klen[q], key, kl, min(lcp_lo, lcp_hi), &d);
+                    bool before;
+                    if (c != 0) before = c < 0;
+                    else {
+                        unsigned long long tq = A.trailer[q];
+                        before = tq > tr || (tq == tr && o < j);
                     }
-                    rank += lo - S.vlo[o];
-                    if (lo > S.vlo[o]) {
-                        uint32_t q = base + lo - 1;
-                        if (A.klen[q] == kl && cmp_slots(A.arena + (size_t)q * KS, kl, key, kl) == 0) shadow = true;
-                    }
+                    if (before) { lo = mid + 1; lcp_lo = d; } else { hi = mid; lcp_hi = d; }
                 }
-                A.shr[r] = (uint16_t)rank; // rank[] / order[] still hold decode scratch of other records' neighbours: use shr
-                A.flags[r] = F_VALID | (shadow ? F_SHADOW : 0);
+                if (lo > S.vlo[o]) {
+                    atomicAdd(&A.R[r], lo - S.vlo[o]);
+                    uint32_t q = base + lo - 1;
+                    if (A.klen[q] == kl && cmp_slots(A.arena + (size_t)q * KS, kl, key, kl) == 0) atomicOr(&A.E[r], 1u);
+                }
             }
         }
         __syncthreads();
@@ -634,8 +654,8 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                 uint32_t kl = A.klen[r], vl = A.vlen[r];
                 s_in++;
                 s_inb += kl + vl;
-                A.order[A.shr[r]] = (uint16_t)r;
-                if (f & F_SHADOW) { s_sh++; continue; }
+                A.order[A.R[r]] = (uint16_t)r;
+                if (A.E[r]) { s_sh++; continue; }
                 uint8_t type = (uint8_t)A.trailer[r];
                 if (type == PGS_TYPE_VALUE) {
                     uint32_t nts = 0;
