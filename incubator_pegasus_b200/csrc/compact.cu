@@ -25,6 +25,8 @@
 //              copy entries shared -> global with destination-aligned 16-byte stores.
 //            Output blocks stay contiguous and in key order, so the new run needs no second pass.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "device_util.cuh"
@@ -66,7 +68,7 @@ struct MergeParams {
     // tile pipeline
     uint32_t *ticket;
     TileAgg *agg, *inc;
-    uint32_t KS, pool_bytes, warp_scratch, use_tma;
+    uint32_t KS, pool_bytes, warp_scratch, use_tma, early_tma, variant;
     // filter + policy
     uint32_t now, enabled, validate_hash, data_version, default_ttl;
     int32_t pidx, partition_version;
@@ -82,6 +84,7 @@ struct MergeParams {
     uint8_t *out_ikeys;
     uint32_t out_blk_cap, out_ikey_cap;
     MergeStats *stats;
+    unsigned long long *phase_cycles; // [16] or null
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -270,14 +273,17 @@ struct RecArrays {
     uint32_t *voff, *vlen, *koff, *R, *E;
     uint16_t *klen, *rank, *order, *surv, *shr, *blkid;
     uint8_t *flags;
-    uint32_t total;
+    uint32_t total, arrays_end;
 };
-PGS_DEV RecArrays carve(uint8_t *pool, uint32_t in_bytes, uint32_t n, uint32_t KS)
+constexpr uint32_t kInPad = 64; // readable bytes after the staged blocks (unaligned word loads run a little past a value)
+// Record arrays grow from the start of the pool, the staged input blocks sit at its END: the next tile's blocks can
+// then be requested from the TMA unit while this tile's arrays are still live (see "early load" in k_merge).
+PGS_DEV uint32_t in_start(uint32_t pool_bytes, uint32_t in_bytes) { return pool_bytes - kInPad - ((in_bytes + 15) & ~15u); }
+PGS_DEV RecArrays carve(uint8_t *pool, uint32_t pool_bytes, uint32_t in_bytes, uint32_t n, uint32_t KS)
 {
     RecArrays a;
     uint32_t n8 = (n + 8) & ~7u; // >= n+1, multiple of 8
-    uint32_t off = ((in_bytes + 15) & ~15u) + 16;
-    a.in = pool;
+    uint32_t off = 0;
     a.arena = pool + off; off += n8 * KS;
     a.trailer = (unsigned long long *)(pool + off); off += n8 * 8;
     a.voff = (uint32_t *)(pool + off); off += n8 * 4;
@@ -292,7 +298,10 @@ PGS_DEV RecArrays carve(uint8_t *pool, uint32_t in_bytes, uint32_t n, uint32_t K
     a.shr = (uint16_t *)(pool + off); off += n8 * 2;
     a.blkid = (uint16_t *)(pool + off); off += n8 * 2;
     a.flags = pool + off; off += n8;
-    a.total = off;
+    off = (off + 15) & ~15u;
+    a.arrays_end = off;
+    a.total = off + ((in_bytes + 15) & ~15u) + kInPad; // <= pool_bytes when the tile fits
+    a.in = pool + (a.total <= pool_bytes ? in_start(pool_bytes, in_bytes) : 0);
     return a;
 }
 
@@ -368,6 +377,9 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
     if (warp == 0) fetch_next_tile(P, S, lane);
     __syncthreads();
     uint32_t phase = 0;
+    long long pt_last = P.phase_cycles ? clock64() : 0; // phase timing (diagnostics): thread 0 stamps every phase boundary
+#define PT(i) do { if (P.phase_cycles && tid == 0) { long long t_ = clock64(); atomicAdd(&P.phase_cycles[i], (unsigned long long)(t_ - pt_last)); pt_last = t_; } } while (0)
+    bool early = false; // thread 0: this tile's block loads were already issued during the previous tile's write phase
 
     for (;;) {
         if (tid == 0) S.tile = S.nx_tile;
@@ -402,27 +414,28 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             S.in_bytes = bytes;
             S.n_rec = recs;
             S.n_blk_in = blks;
-            RecArrays a0 = carve(pool, bytes, recs, KS);
+            RecArrays a0 = carve(pool, P.pool_bytes, bytes, recs, KS);
             if (a0.total > P.pool_bytes || blks > kMaxTileBlocks || recs > 65000) atomicMax(&S.error, (uint32_t)PGS_ABORTED);
             S.has_lo = !first;
             S.has_hi = !last;
-            if (!S.error && P.use_tma) {
+            if (!S.error && P.use_tma && !early) {
                 // generic-proxy writes of the previous tile precede async-proxy writes to the same bytes
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 if (bytes) mbar_expect_tx((uint64_t *)&S.mbar, bytes); // the copies are issued right after the barrier
             }
         }
         __syncthreads();
-        const RecArrays A = carve(pool, S.in_bytes, S.n_rec, KS);
+        const RecArrays A = carve(pool, P.pool_bytes, S.in_bytes, S.n_rec, KS);
         bool tile_ok = S.error == 0;
         if (tile_ok) {
             if (P.use_tma) {
-                if (tid == 0) {
+                if (tid == 0 && !early) {
                     for (uint32_t j = 0; j < P.k; j++) {
                         uint32_t bytes = (j + 1 < P.k ? S.in_off[j + 1] : S.in_bytes) - S.in_off[j];
                         if (bytes) tma_load_1d(A.in + S.in_off[j], P.runs[j].data + P.runs[j].blk_off[S.lo[j]], bytes, (uint64_t *)&S.mbar);
                     }
                 }
+                early = false;
             } else {
                 for (uint32_t j = 0; j < P.k; j++) {
                     uint32_t bytes = (j + 1 < P.k ? S.in_off[j + 1] : S.in_bytes) - S.in_off[j];
@@ -465,6 +478,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             }
         }
         __syncthreads();
+        PT(0);
 
         // ---- decode step 1: one THREAD per record parses its entry header (offsets come from the run's rec_off index) ----
         if (tile_ok) {
@@ -518,6 +532,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             }
         }
         __syncthreads();
+        PT(1);
         tile_ok = S.error == 0;
 
         // ---- decode step 2: HALF a warp per block rebuilds the keys, four key bytes per lane -----------
@@ -568,6 +583,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             }
         }
         __syncthreads();
+        PT(2);
 
         // ---- valid range of every run's slice: user keys in (U_lo, U_hi]; records at or below U_lo form a
         //      prefix of a slice, records above U_hi a suffix, so counting them gives the window -----------
@@ -588,6 +604,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             S.vhi[tid] = vhi;
         }
         __syncthreads();
+        PT(3);
         if (tile_ok && tid == 0) {
             uint32_t nv = 0;
             for (uint32_t j = 0; j < P.k; j++) nv += S.vhi[j] - S.vlo[j];
@@ -644,6 +661,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             }
         }
         __syncthreads();
+        PT(4);
 
         // ---- compaction filter + tombstone policy; scatter into merged order -----------------------------
         if (tile_ok) {
@@ -697,6 +715,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             }
         }
         __syncthreads();
+        PT(5);
 
         // ---- survivors in merged order, output block layout ---------------------------------------------------
         uint32_t m = 0;
@@ -765,6 +784,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             S.n_ob = 0; S.n_surv = 0; S.tile_bytes = 0; S.tile_keyb = 0;
         }
         __syncthreads();
+        PT(6);
 
         // ---- decoupled look-back: where does this tile's output start? ----------------------------------------
         if (warp == 0) {
@@ -812,6 +832,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             }
         }
         __syncthreads();
+        PT(7);
         tile_ok = S.error == 0;
         if (warp == NW - 1) fetch_next_tile(P, S, lane); // overlaps the global-memory latency with the writes below
 
@@ -844,7 +865,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                 mx_v = max(mx_v, vl);
                 mn_seq = seq < mn_seq ? seq : mn_seq;
                 mx_seq = seq > mx_seq ? seq : mx_seq;
-                max_chunks = max(max_chunks, (vl >> 4) + 2);
+                max_chunks = max(max_chunks, ((vl >> 4) + 3) >> 1); // pairs of 16-byte chunks
             }
             s_outb = __reduce_add_sync(kFull, s_outb); s_otomb = __reduce_add_sync(kFull, s_otomb);
             s_okey = __reduce_add_sync(kFull, s_okey); s_oval = __reduce_add_sync(kFull, s_oval);
@@ -857,15 +878,17 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             }
             if (lane == 0) atomicMax(&S.scan[0], max_chunks);
             __syncthreads();
+            PT(8);
             const uint32_t CH = S.scan[0];
-            // (b) values first: one thread per 16-byte destination-aligned chunk (CH slots per survivor), source words
-            //     re-aligned with funnel shifts.  The first and last chunk of a value are written as FULL 16-byte
-            //     stores whenever the bytes that do not belong to the value fall inside this entry's own head or
-            //     the next entry's head of the same block: those heads are written after the barrier below and
-            //     overwrite the spill.  Only where a spill could touch foreign bytes the exact byte range is stored.
+            // (b) values first: one thread per PAIR of 16-byte destination-aligned chunks (CH pairs per survivor),
+            //     source words re-aligned with funnel shifts.  The first and last chunk of a value are written as
+            //     FULL 16-byte stores whenever the bytes that do not belong to the value fall inside this entry's
+            //     own head or the next entry's head of the same block: those heads are written after the barrier
+            //     below and overwrite the spill.  Where a spill could touch foreign bytes, a tail is stored as
+            //     8/4/2/1-byte pieces (the chunk start is 16-aligned) and a head byte by byte.
             const uint32_t ch_magic = (uint32_t)((0x100000000ull + CH - 1) / CH); // id / CH by multiply-high (exact for id*CH < 2^32)
             for (uint32_t id = tid; id < m * CH; id += NT) {
-                const uint32_t p = __umulhi(id, ch_magic), c = id - p * CH;
+                const uint32_t p = CH == 1 ? id : __umulhi(id, ch_magic), c0 = (id - p * CH) << 1;
                 const uint32_t r = A.surv[p];
                 const uint32_t vl = A.vlen[r];
                 if (vl == 0) continue;
@@ -873,35 +896,66 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                 uint8_t *dv = out + A.R[p] + hs;
                 const uint32_t lead = (uint32_t)((uintptr_t)dv & 15);
                 const uint32_t nch = (lead + vl + 15) >> 4;
-                if (c >= nch) continue;
-                uint8_t *addr = dv - lead + (c << 4);
-                const uint32_t lo = c == 0 ? lead : 0;
-                const uint32_t rem = lead + vl - (c << 4);
-                const uint32_t hi = rem < 16 ? rem : 16;
-                const uint8_t *sp = A.in + A.voff[r] + (c << 4) - lead; // may start a few bytes before the value: still inside IN / the key slots
-                bool full = true;
-                if (lo > hs) full = false; // the spill before the value would reach the previous entry
-                if (hi < 16) {
-                    const bool block_last = p + 1 == S.cut[A.blkid[p] + 1];
-                    if (block_last || 16 - hi > A.rank[p + 1]) full = false;
-                }
-                if (full) {
-                    const uint32_t sh = (uint32_t)((uintptr_t)sp & 3) * 8;
-                    const uint32_t *w = (const uint32_t *)((uintptr_t)sp & ~(uintptr_t)3);
-                    uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+                if (c0 >= nch) continue;
+                const uint8_t *sp = A.in + A.voff[r] + (c0 << 4) - lead; // may start a few bytes before the value: still inside IN / the key slots
+                const uint32_t sh = (uint32_t)((uintptr_t)sp & 3) * 8;
+                const uint32_t *w = (const uint32_t *)((uintptr_t)sp & ~(uintptr_t)3);
+                uint32_t wv[9];
+#pragma unroll
+                for (uint32_t x = 0; x < 9; x++) wv[x] = w[x];
+#pragma unroll
+                for (uint32_t half = 0; half < 2; half++) {
+                    const uint32_t c = c0 + half;
+                    if (c >= nch) break;
                     uint4 o4;
-                    if (sh == 0) o4 = make_uint4(w0, w1, w2, w3);
-                    else {
-                        uint32_t w4 = w[4];
-                        o4.x = __funnelshift_r(w0, w1, sh); o4.y = __funnelshift_r(w1, w2, sh);
-                        o4.z = __funnelshift_r(w2, w3, sh); o4.w = __funnelshift_r(w3, w4, sh);
+                    o4.x = __funnelshift_r(wv[4 * half + 0], wv[4 * half + 1], sh); o4.y = __funnelshift_r(wv[4 * half + 1], wv[4 * half + 2], sh);
+                    o4.z = __funnelshift_r(wv[4 * half + 2], wv[4 * half + 3], sh); o4.w = __funnelshift_r(wv[4 * half + 3], wv[4 * half + 4], sh);
+                    uint8_t *addr = dv - lead + (c << 4);
+                    const uint32_t lo = c == 0 ? lead : 0;
+                    const uint32_t rem = lead + vl - (c << 4);
+                    const uint32_t hi = rem < 16 ? rem : 16;
+                    bool full = lo <= hs; // else the spill before the value would reach the previous entry
+                    if (hi < 16) {
+                        const bool block_last = p + 1 == S.cut[A.blkid[p] + 1];
+                        if (block_last || 16 - hi > A.rank[p + 1]) full = false;
                     }
-                    *reinterpret_cast<uint4 *>(addr) = o4;
-                } else {
-                    for (uint32_t x = lo; x < hi; x++) addr[x] = sp[x];
+                    if (full) {
+                        *reinterpret_cast<uint4 *>(addr) = o4;
+                    } else if (lo == 0) { // exact tail [0, hi), hi < 16
+                        uint32_t at = 0;
+                        if (hi & 8) { *reinterpret_cast<uint2 *>(addr) = make_uint2(o4.x, o4.y); at = 8; }
+                        const uint32_t q0 = (hi & 8) ? o4.z : o4.x, q1 = (hi & 8) ? o4.w : o4.y;
+                        uint32_t q = q0;
+                        if (hi & 4) { *reinterpret_cast<uint32_t *>(addr + at) = q0; at += 4; q = q1; }
+                        if (hi & 2) { *reinterpret_cast<uint16_t *>(addr + at) = (uint16_t)q; at += 2; q >>= 16; }
+                        if (hi & 1) addr[at] = (uint8_t)q;
+                    } else {
+                        const uint8_t *sb = sp + (half << 4);
+                        for (uint32_t x = lo; x < hi; x++) addr[x] = sb[x];
+                    }
                 }
             }
             __syncthreads();
+            PT(9);
+            // early load: the staged blocks are dead now.  When the next tile's blocks (end of the pool) do not reach
+            // into this tile's record arrays (start of the pool, still needed below), their TMA copies start here
+            // and run under the head writes, the block trailers and the next tile's setup.
+            if (tid == 0 && P.use_tma && P.early_tma && S.nx_tile < P.Q && !S.nx_err) {
+                uint32_t nb = 0, nr = 0, nbl = 0;
+                for (uint32_t j = 0; j < P.k; j++) { nb += S.nx_bytes[j]; nr += S.nx_nrec[j]; nbl += S.nx_nblk[j]; }
+                const RecArrays nx = carve(pool, P.pool_bytes, nb, nr, KS);
+                if (nb && nx.total <= P.pool_bytes && nbl <= kMaxTileBlocks && nr <= 65000 && in_start(P.pool_bytes, nb) >= A.arrays_end) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx((uint64_t *)&S.mbar, nb);
+                    uint8_t *dst = nx.in;
+                    for (uint32_t j = 0; j < P.k; j++) {
+                        const uint32_t bytes = S.nx_bytes[j];
+                        if (bytes) tma_load_1d(dst, P.runs[j].data + P.runs[j].blk_off[S.nx_lo[j]], bytes, (uint64_t *)&S.mbar);
+                        dst += bytes;
+                    }
+                    early = true;
+                }
+            }
             // (c) entry heads = 3 varints | key delta | trailer: half a warp per survivor, one byte per lane, the
             //     stores of a half-warp are consecutive bytes
             for (uint32_t p = 2 * warp + (lane >> 4); p < m; p += 2 * NW) {
@@ -967,6 +1021,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             }
         }
         __syncthreads();
+        PT(10);
         if (tid < 16 && S.stat[tid]) {
             unsigned long long *g = &P.stats->in_records;
             static_assert(ST_OUT_VAL == 12, "stat layout");
@@ -988,6 +1043,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             }
         }
         __syncthreads();
+        PT(11);
     }
 }
 
@@ -1063,6 +1119,12 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     P.warp_scratch = (KS + 48 + 15) & ~15u;
     P.total_blocks = (uint32_t)total_blocks;
     P.use_tma = (e->cfg.flags & PGS_ENGINE_NO_TMA) ? 0 : 1;
+    {
+        const char *ev = getenv("PGS_EARLY_TMA"); // diagnostics: 0 turns the early block load off
+        P.early_tma = (ev && ev[0] == '0') ? 0 : 1;
+        const char *vv = getenv("PGS_VARIANT");
+        P.variant = vv ? (uint32_t)atoi(vv) : 0;
+    }
     P.block_size = e->cfg.block_size;
     P.restart_interval = e->cfg.restart_interval;
     P.bottommost = bottommost ? 1 : 0;
@@ -1103,7 +1165,7 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
         // (one per run at worst) and one partial block per run.  Groups larger than two blocks are
         // rare, so the first attempt budgets k+2 blocks of slack; the kernel verifies every tile and
         // the host retries with the rigorous 2k bound if one did not fit.
-        uint64_t overhead = (rigorous ? 2ull * k : (uint64_t)k + 2) * maxw + 256;
+        uint64_t overhead = (rigorous ? 2ull * k : (uint64_t)k + 2) * maxw + 1024;
         if (pool > overhead + maxw) { T = pool - overhead; P.pool_bytes = (uint32_t)pool; break; }
     }
     uint64_t W_total = 0;
@@ -1174,6 +1236,9 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     P.split_pos = d_split_pos;
     P.split_ref = d_split_ref;
     P.ticket = d_ticket;
+    const char *pt_env = getenv("PGS_PHASE_TIMING"); // diagnostics: per-phase cycle totals of k_merge on stderr
+    const bool phase_timing = pt_env && pt_env[0] == '1';
+    P.phase_cycles = phase_timing ? (unsigned long long *)(d_ticket + 16) : nullptr;
     P.agg = d_agg;
     P.inc = d_agg + Q;
     P.out_data = outr->d_data;
@@ -1204,8 +1269,18 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     CK(cudaMemcpyAsync(&hs, d_stats, sizeof hs, cudaMemcpyDeviceToHost, st));
     TileAgg fin{};
     CK(cudaMemcpyAsync(&fin, d_agg + Q + (Q - 1), sizeof fin, cudaMemcpyDeviceToHost, st));
+    unsigned long long h_phase[16] = {0};
+    if (phase_timing) CK(cudaMemcpyAsync(h_phase, d_ticket + 16, sizeof h_phase, cudaMemcpyDeviceToHost, st));
     cudaError_t se = cudaStreamSynchronize(st);
     if (se != cudaSuccess) { cleanup(); return cuda_fail(se, "compaction kernels"); }
+    if (phase_timing) {
+        static const char *names[12] = {"setup", "decode1", "decode2", "window", "rank", "filter", "layout", "lookback", "write_a", "write_b", "write_c", "flush"};
+        unsigned long long tot = 0;
+        for (int i = 0; i < 12; i++) tot += h_phase[i];
+        fprintf(stderr, "[k_merge phases] tiles=%u", P.Q);
+        for (int i = 0; i < 12; i++) fprintf(stderr, " %s=%.1f%%", names[i], tot ? 100.0 * (double)h_phase[i] / (double)tot : 0.0);
+        fprintf(stderr, " cycles/tile=%.0f\n", P.Q ? (double)tot / P.Q : 0.0);
+    }
     float ms_total = 0, ms_merge = 0;
     cudaEventElapsedTime(&ms_total, ev0, ev2);
     cudaEventElapsedTime(&ms_merge, ev1, ev2);
