@@ -40,10 +40,12 @@ constexpr uint32_t kRecExtra = 48; // per-record shared-memory bytes besides the
 
 enum : uint8_t { F_VALID = 1, F_SHADOW = 2, F_KEEP = 4, F_TOMB = 8, F_NEWTS = 16 };
 
+// One look-back slot = two 16-byte halves, each written with ONE vector store and carrying its own flag, so a
+// reader gets data and validity in a single round trip (no fence, no second load).
 struct TileAgg {
     unsigned long long bytes;
-    uint32_t blocks, recs, keyb, flag;
-    uint32_t pad[2];
+    uint32_t blocks, flag0;
+    uint32_t recs, keyb, flag1, pad;
 };
 static_assert(sizeof(TileAgg) == 32, "TileAgg");
 
@@ -250,13 +252,17 @@ struct TileShared {
     uint32_t in_bytes, n_rec, n_blk_in, n_valid, n_surv, n_ob;
     uint32_t has_lo, has_hi, ulo_len, uhi_len;
     uint32_t tile_bytes, tile_keyb;
-    uint32_t max_ukey, max_vlen, max_blk_size, max_blk_rec;
+    uint32_t max_ukey, max_vlen, max_blk_size, max_blk_rec, max_ch;
     uint32_t lo[kMaxRuns], nblk[kMaxRuns], nrec[kMaxRuns], in_off[kMaxRuns], rec_base[kMaxRuns], blk_base[kMaxRuns];
     uint32_t vlo[kMaxRuns], vhi[kMaxRuns], nabove[kMaxRuns];
     uint32_t nx_tile, nx_err; // next tile's ticket + slice metadata, fetched while this tile is being written
     uint32_t nx_lo[kMaxRuns], nx_nblk[kMaxRuns], nx_nrec[kMaxRuns], nx_bytes[kMaxRuns], nx_grec0[kMaxRuns];
+    unsigned long long nx_boff[kMaxRuns]; // byte offset of the slice inside its run
+    uint32_t nx_krun[2], nx_koff[2], nx_klen[2]; // boundary keys of the next tile: run, offset and length inside its ikeys
+    uint32_t k_run[2], k_off[2];
     uint32_t grec0[kMaxRuns]; // index of the slice's first record inside its run
     uint32_t scan[33];
+    unsigned long long scan64[33];
     uint32_t stat[16];
     uint32_t tb_off[kMaxTileBlocks], tb_size[kMaxTileBlocks], tb_rec[kMaxTileBlocks], tb_nrec[kMaxTileBlocks];
     uint32_t cut[kMaxOutBlocks + 1], ob_off[kMaxOutBlocks + 1], ob_size[kMaxOutBlocks], ob_keyoff[kMaxOutBlocks + 1];
@@ -271,7 +277,7 @@ struct RecArrays {
     uint8_t *arena;
     unsigned long long *trailer;
     uint32_t *voff, *vlen, *koff, *R, *E;
-    uint16_t *klen, *rank, *order, *surv, *shr, *blkid;
+    uint16_t *klen, *rank, *order, *surv, *shr, *blkid, *pos;
     uint8_t *flags;
     uint32_t total, arrays_end;
 };
@@ -279,7 +285,7 @@ constexpr uint32_t kInPad = 64; // readable bytes after the staged blocks (unali
 // Record arrays grow from the start of the pool, the staged input blocks sit at its END: the next tile's blocks can
 // then be requested from the TMA unit while this tile's arrays are still live (see "early load" in k_merge).
 PGS_DEV uint32_t in_start(uint32_t pool_bytes, uint32_t in_bytes) { return pool_bytes - kInPad - ((in_bytes + 15) & ~15u); }
-PGS_DEV RecArrays carve(uint8_t *pool, uint32_t pool_bytes, uint32_t in_bytes, uint32_t n, uint32_t KS)
+PGS_DEV RecArrays carve(uint8_t *pool, uint32_t pool_bytes, uint32_t in_bytes, uint32_t n, uint32_t KS, uint32_t k)
 {
     RecArrays a;
     uint32_t n8 = (n + 8) & ~7u; // >= n+1, multiple of 8
@@ -297,6 +303,7 @@ PGS_DEV RecArrays carve(uint8_t *pool, uint32_t pool_bytes, uint32_t in_bytes, u
     a.surv = (uint16_t *)(pool + off); off += n8 * 2;
     a.shr = (uint16_t *)(pool + off); off += n8 * 2;
     a.blkid = (uint16_t *)(pool + off); off += n8 * 2;
+    a.pos = (uint16_t *)(pool + off); off += n8 * 2 * (k - 1); // merge positions inside the later runs
     a.flags = pool + off; off += n8;
     off = (off + 15) & ~15u;
     a.arrays_end = off;
@@ -306,31 +313,90 @@ PGS_DEV RecArrays carve(uint8_t *pool, uint32_t pool_bytes, uint32_t in_bytes, u
 }
 
 // exclusive scan of f(i), i in [0,n), into out[0..n] (out[n] = total); f is evaluated once per element.
+// scratch = 33 uint32 of shared memory; two barriers per call.
 template <class F>
 PGS_DEV uint32_t chunked_scan(uint32_t n, uint32_t *out, uint32_t *scratch, F f)
 {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     uint32_t ipt = (n + blockDim.x - 1) / blockDim.x;
     uint32_t begin = min(threadIdx.x * ipt, n), end = min(begin + ipt, n);
     uint32_t local = 0;
     for (uint32_t i = begin; i < end; i++) { uint32_t v = f(i); out[i] = v; local += v; }
-    uint32_t total;
-    uint32_t pre = block_excl_scan(local, scratch, &total);
+    const uint32_t inc = warp_incl_scan(local, lane);
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    // every warp scans the warp totals itself: one barrier less than a designated scanning warp
+    const uint32_t w = lane < nw ? scratch[lane] : 0, ws = warp_incl_scan(w, lane);
+    const uint32_t total = __shfl_sync(kFull, ws, 31);
+    uint32_t pre = __shfl_sync(kFull, ws - w, warp) + inc - local;
     for (uint32_t i = begin; i < end; i++) { uint32_t v = out[i]; out[i] = pre; pre += v; }
     if (threadIdx.x == 0) out[n] = total;
-    __syncthreads();
+    __syncthreads(); // results visible; scratch reusable
     return total;
 }
 
-PGS_DEV void publish(TileAgg *slot, unsigned long long bytes, uint32_t blocks, uint32_t recs, uint32_t keyb)
+// two exclusive scans in one pass: f(i) = (a, b) packed as a << 32 | b; neither running sum may pass 2^32.
+// scratch64 = 33 x 8 bytes of shared memory.
+template <class F>
+PGS_DEV unsigned long long chunked_scan2(uint32_t n, uint32_t *outA, uint32_t *outB, unsigned long long *scratch64, F f)
 {
-    slot->bytes = bytes;
-    slot->blocks = blocks;
-    slot->recs = recs;
-    slot->keyb = keyb;
-    __threadfence();
-    *(volatile uint32_t *)&slot->flag = 1;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t ipt = (n + blockDim.x - 1) / blockDim.x;
+    uint32_t begin = min(threadIdx.x * ipt, n), end = min(begin + ipt, n);
+    unsigned long long local = 0;
+    for (uint32_t i = begin; i < end; i++) { unsigned long long v = f(i); outA[i] = (uint32_t)(v >> 32); outB[i] = (uint32_t)v; local += v; }
+    unsigned long long inc = local;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        unsigned long long o = __shfl_up_sync(kFull, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) scratch64[warp] = inc;
+    __syncthreads();
+    // every warp scans the warp totals itself: one barrier less than a designated scanning warp
+    unsigned long long w = lane < nw ? scratch64[lane] : 0, ws = w;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        unsigned long long o = __shfl_up_sync(kFull, ws, d);
+        if (lane >= d) ws += o;
+    }
+    const unsigned long long total = __shfl_sync(kFull, ws, 31);
+    unsigned long long pre = __shfl_sync(kFull, ws - w, warp) + inc - local;
+    for (uint32_t i = begin; i < end; i++) {
+        unsigned long long v = ((unsigned long long)outA[i] << 32) | outB[i];
+        outA[i] = (uint32_t)(pre >> 32); outB[i] = (uint32_t)pre;
+        pre += v;
+    }
+    __syncthreads(); // results visible; scratch64 reusable
+    return total;
 }
 
+PGS_DEV uint4 ld_v4_volatile(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+PGS_DEV void st_v4_volatile(void *p, uint4 v)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+PGS_DEV void publish(TileAgg *slot, unsigned long long bytes, uint32_t blocks, uint32_t recs, uint32_t keyb)
+{
+    st_v4_volatile(slot, make_uint4((uint32_t)bytes, (uint32_t)(bytes >> 32), blocks, 1u));
+    st_v4_volatile((uint8_t *)slot + 16, make_uint4(recs, keyb, 1u, 0u));
+}
+
+// the varint32 encoding of v as little-endian bytes in a register (at most 5), *len = its length
+PGS_DEV unsigned long long varint_pack(uint32_t v, uint32_t &len)
+{
+    unsigned long long o = 0;
+    uint32_t n = 0;
+    while (v >= 128) { o |= (unsigned long long)((v & 127u) | 128u) << (8 * n); v >>= 7; n++; }
+    o |= (unsigned long long)v << (8 * n);
+    len = n + 1;
+    return o;
+}
 PGS_DEV uint32_t varint_byte(uint32_t v, uint32_t j, uint32_t len) { return ((v >> ((7 * j) & 31)) & 0x7fu) | (j + 1 < len ? 0x80u : 0u); }
 
 // one warp takes the next ticket and loads that tile's per-run slice metadata into S.nx_*
@@ -350,10 +416,29 @@ PGS_DEV void fetch_next_tile(const MergeParams &P, TileShared &S, uint32_t lane)
         uint32_t hi_ex = last ? r.nb : min(hi + 1, r.nb);
         S.nx_lo[lane] = lo;
         S.nx_nblk[lane] = hi_ex - lo;
-        S.nx_bytes[lane] = (uint32_t)(r.blk_off[hi_ex] - r.blk_off[lo]);
+        const unsigned long long bo = r.blk_off[lo];
+        S.nx_boff[lane] = bo;
+        S.nx_bytes[lane] = (uint32_t)(r.blk_off[hi_ex] - bo);
         uint32_t g0 = r.blk_rec[lo];
         S.nx_nrec[lane] = r.blk_rec[hi_ex] - g0;
         S.nx_grec0[lane] = g0;
+    }
+    if (t < P.Q && (lane == 16 || lane == 17)) { // where the tile's boundary user keys live: (U_lo, U_hi]
+        const uint32_t which = lane - 16;
+        const bool none = which == 0 ? t == 0 : t == P.Q - 1;
+        uint32_t run = 0, off = 0, len = 0;
+        if (!none) {
+            const uint32_t ref = P.split_ref[t + which];
+            run = ref >> 28;
+            const uint32_t b = ref & 0x0FFFFFFFu;
+            if (ref == 0xFFFFFFFFu || run >= P.k || b >= P.runs[run].nb) { atomicMax(&S.nx_err, (uint32_t)PGS_ABORTED); run = 0; }
+            else {
+                off = P.runs[run].ikey_off[b];
+                len = P.runs[run].ikey_off[b + 1] - off;
+                if (len > P.KS) { atomicMax(&S.nx_err, (uint32_t)PGS_ABORTED); len = 0; }
+            }
+        }
+        S.nx_krun[which] = run; S.nx_koff[which] = off; S.nx_klen[which] = len;
     }
 }
 
@@ -382,61 +467,52 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
     bool early = false; // thread 0: this tile's block loads were already issued during the previous tile's write phase
 
     for (;;) {
-        if (tid == 0) S.tile = S.nx_tile;
-        if (tid < 16) S.stat[tid] = 0;
-        if (tid >= 32 && tid < 32 + kMaxRuns) { S.vlo[tid - 32] = 0; S.nabove[tid - 32] = 0; }
-        if (tid == 64) { S.error = S.nx_err; S.min_seq = ~0ull; S.max_seq = 0; S.max_ukey = 0; S.max_vlen = 0; S.max_blk_size = 0; S.max_blk_rec = 0; }
+        // ---- tile setup (slice metadata and boundary-key references were prefetched into S.nx_*) -------------
+        if (tid == 0) {
+            const uint32_t t = S.nx_tile;
+            S.tile = t;
+            S.min_seq = ~0ull; S.max_seq = 0; S.max_ukey = 0; S.max_vlen = 0; S.max_blk_size = 0; S.max_blk_rec = 0; S.max_ch = 0;
+            uint32_t err = S.nx_err;
+            if (t < P.Q) {
+                uint32_t bytes = 0, recs = 0, blks = 0;
+                for (uint32_t j = 0; j < P.k; j++) {
+                    S.lo[j] = S.nx_lo[j]; S.nblk[j] = S.nx_nblk[j]; S.nrec[j] = S.nx_nrec[j]; S.grec0[j] = S.nx_grec0[j];
+                    S.in_off[j] = bytes; S.rec_base[j] = recs; S.blk_base[j] = blks;
+                    bytes += S.nx_bytes[j]; recs += S.nx_nrec[j]; blks += S.nx_nblk[j];
+                }
+                S.in_bytes = bytes; S.n_rec = recs; S.n_blk_in = blks;
+                S.k_run[0] = S.nx_krun[0]; S.k_run[1] = S.nx_krun[1];
+                S.k_off[0] = S.nx_koff[0]; S.k_off[1] = S.nx_koff[1];
+                S.ulo_len = S.nx_klen[0]; S.uhi_len = S.nx_klen[1];
+                S.has_lo = t != 0;
+                S.has_hi = t != P.Q - 1;
+                const RecArrays a0 = carve(pool, P.pool_bytes, bytes, recs, KS, P.k);
+                if (a0.total > P.pool_bytes || blks > kMaxTileBlocks || recs > 65000) err = max(err, (uint32_t)PGS_ABORTED);
+                if (!err && P.use_tma && !early) {
+                    // generic-proxy writes of the previous tile precede async-proxy writes to the same bytes
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (bytes) {
+                        mbar_expect_tx((uint64_t *)&S.mbar, bytes);
+                        for (uint32_t j = 0; j < P.k; j++) {
+                            const uint32_t bj = S.nx_bytes[j];
+                            if (bj) tma_load_1d(a0.in + S.in_off[j], P.runs[j].data + S.nx_boff[j], bj, (uint64_t *)&S.mbar);
+                        }
+                    }
+                }
+                early = false;
+            }
+            S.error = err;
+        }
+        if (tid >= 32 && tid < 48) S.stat[tid - 32] = 0;
+        if (tid >= 64 && tid < 64 + kMaxRuns) { S.vlo[tid - 64] = 0; S.nabove[tid - 64] = 0; }
         __syncthreads();
         const uint32_t tile = S.tile;
         if (tile >= P.Q) break;
         const bool first = tile == 0, last = tile == P.Q - 1;
-
-        // ---- tile setup (slice metadata was prefetched into S.nx_*) ---------------------------
-        if (tid < P.k) {
-            S.lo[tid] = S.nx_lo[tid];
-            S.nblk[tid] = S.nx_nblk[tid];
-            S.in_off[tid] = S.nx_bytes[tid]; // bytes, offsets fixed below
-            S.nrec[tid] = S.nx_nrec[tid];
-            S.grec0[tid] = S.nx_grec0[tid];
-        }
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t bytes = 0, recs = 0, blks = 0;
-            for (uint32_t j = 0; j < P.k; j++) {
-                uint32_t bj = S.in_off[j];
-                S.in_off[j] = bytes;
-                S.rec_base[j] = recs;
-                S.blk_base[j] = blks;
-                bytes += bj;
-                recs += S.nrec[j];
-                blks += S.nblk[j];
-            }
-            S.in_bytes = bytes;
-            S.n_rec = recs;
-            S.n_blk_in = blks;
-            RecArrays a0 = carve(pool, P.pool_bytes, bytes, recs, KS);
-            if (a0.total > P.pool_bytes || blks > kMaxTileBlocks || recs > 65000) atomicMax(&S.error, (uint32_t)PGS_ABORTED);
-            S.has_lo = !first;
-            S.has_hi = !last;
-            if (!S.error && P.use_tma && !early) {
-                // generic-proxy writes of the previous tile precede async-proxy writes to the same bytes
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                if (bytes) mbar_expect_tx((uint64_t *)&S.mbar, bytes); // the copies are issued right after the barrier
-            }
-        }
-        __syncthreads();
-        const RecArrays A = carve(pool, P.pool_bytes, S.in_bytes, S.n_rec, KS);
+        const RecArrays A = carve(pool, P.pool_bytes, S.in_bytes, S.n_rec, KS, P.k);
         bool tile_ok = S.error == 0;
         if (tile_ok) {
-            if (P.use_tma) {
-                if (tid == 0 && !early) {
-                    for (uint32_t j = 0; j < P.k; j++) {
-                        uint32_t bytes = (j + 1 < P.k ? S.in_off[j + 1] : S.in_bytes) - S.in_off[j];
-                        if (bytes) tma_load_1d(A.in + S.in_off[j], P.runs[j].data + P.runs[j].blk_off[S.lo[j]], bytes, (uint64_t *)&S.mbar);
-                    }
-                }
-                early = false;
-            } else {
+            if (!P.use_tma) {
                 for (uint32_t j = 0; j < P.k; j++) {
                     uint32_t bytes = (j + 1 < P.k ? S.in_off[j + 1] : S.in_bytes) - S.in_off[j];
                     const uint4 *src = (const uint4 *)(P.runs[j].data + P.runs[j].blk_off[S.lo[j]]);
@@ -444,33 +520,37 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                     for (uint32_t i = tid; i < bytes / 16; i += NT) dst[i] = src[i];
                 }
             }
-            // boundary keys (zero padded slots)
-            for (uint32_t which = 0; which < 2; which++) {
-                if (which == 0 ? first : last) continue;
-                uint32_t ref = P.split_ref[tile + which];
-                const RunDev &r = P.runs[ref >> 28];
-                uint32_t b = ref & 0x0FFFFFFFu;
-                uint32_t off = r.ikey_off[b], len = r.ikey_off[b + 1] - off;
-                uint8_t *dst = which == 0 ? ulo : uhi;
-                for (uint32_t i = tid; i < KS + 8; i += NT) dst[i] = i < len ? r.ikeys[off + i] : 0;
-                if (tid == 0) { if (which == 0) S.ulo_len = len; else S.uhi_len = len; }
-            }
-            // block table
-            for (uint32_t t = tid; t < S.n_blk_in; t += NT) {
-                uint32_t j = 0;
-                while (j + 1 < P.k && t >= S.blk_base[j + 1]) j++;
-                const RunDev &r = P.runs[j];
-                uint32_t gb = S.lo[j] + (t - S.blk_base[j]);
-                S.tb_off[t] = S.in_off[j] + (uint32_t)(r.blk_off[gb] - r.blk_off[S.lo[j]]);
-                S.tb_size[t] = r.blk_size[gb];
-                S.tb_rec[t] = S.rec_base[j] + (r.blk_rec[gb] - r.blk_rec[S.lo[j]]);
-                S.tb_nrec[t] = r.blk_rec[gb + 1] - r.blk_rec[gb];
-            }
-            // every record's entry offset inside its block (device-built index): the header walk below needs no chain
-            for (uint32_t r = tid; r < S.n_rec; r += NT) {
-                uint32_t j = 0;
-                while (j + 1 < P.k && r >= S.rec_base[j + 1]) j++;
-                A.koff[r] = P.runs[j].rec_off[S.grec0[j] + (r - S.rec_base[j])];
+            // the three index reads below are independent global-memory round trips: different warps take them so
+            // that they overlap instead of queueing behind each other
+            if (warp < 2) { // boundary keys (zero padded slots): warp 0 -> U_lo, warp 1 -> U_hi
+                if (!(warp == 0 ? first : last)) {
+                    const uint8_t *src = P.runs[S.k_run[warp]].ikeys + S.k_off[warp];
+                    const uint32_t len = warp == 0 ? S.ulo_len : S.uhi_len;
+                    uint8_t *dst = warp == 0 ? ulo : uhi;
+                    for (uint32_t i = lane; i < KS + 8; i += 64) {
+                        const uint32_t i2 = i + 32;
+                        const uint8_t v0 = i < len ? src[i] : 0, v1 = i2 < len ? src[i2] : 0;
+                        dst[i] = v0;
+                        if (i2 < KS + 8) dst[i2] = v1;
+                    }
+                }
+            } else if (warp < 4) { // block table
+                for (uint32_t t = tid - 64; t < S.n_blk_in; t += 64) {
+                    uint32_t j = 0;
+                    while (j + 1 < P.k && t >= S.blk_base[j + 1]) j++;
+                    const RunDev &r = P.runs[j];
+                    uint32_t gb = S.lo[j] + (t - S.blk_base[j]);
+                    S.tb_off[t] = S.in_off[j] + (uint32_t)(r.blk_off[gb] - r.blk_off[S.lo[j]]);
+                    S.tb_size[t] = r.blk_size[gb];
+                    S.tb_rec[t] = S.rec_base[j] + (r.blk_rec[gb] - r.blk_rec[S.lo[j]]);
+                    S.tb_nrec[t] = r.blk_rec[gb + 1] - r.blk_rec[gb];
+                }
+            } else { // every record's entry offset inside its block (device-built index): the header walk needs no chain
+                for (uint32_t r = tid - 128; r < S.n_rec; r += NT - 128) {
+                    uint32_t j = 0;
+                    while (j + 1 < P.k && r >= S.rec_base[j + 1]) j++;
+                    A.koff[r] = P.runs[j].rec_off[S.grec0[j] + (r - S.rec_base[j])];
+                }
             }
             if (P.use_tma && S.in_bytes) {
                 mbar_wait((uint64_t *)&S.mbar, phase);
@@ -500,7 +580,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                 if (!err && (p >= limit || (i == 0 && p != 0))) err = PGS_CORRUPTION;
                 if (!err) {
                     uint32_t shared, non_shared, vlen, h, c;
-                    h = c = parse_header8(lds_u64_unaligned(base + p), shared, non_shared, vlen); // header bytes from registers
+                    h = c = parse_header8(lds_u64_at(A.in, S.tb_off[t] + p), shared, non_shared, vlen); // header bytes from registers
                     if (!c) { // uncommon shape: byte-wise decoder
                         h = 0;
                         c = get_varint32(base + p, limit - p, shared);
@@ -520,7 +600,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                         A.voff[r] = S.tb_off[t] + p + h + non_shared;
                         A.vlen[r] = vlen;
                         if (non_shared >= 8) { // the (seq<<8|type) trailer sits wholly in this entry's delta
-                            A.trailer[r] = lds_u64_unaligned(base + p + h + non_shared - 8);
+                            A.trailer[r] = lds_u64_at(A.in, S.tb_off[t] + p + h + non_shared - 8);
                             A.flags[r] = 0;
                         } else {               // part of it is shared with the previous key: rebuilt in step 2
                             A.trailer[r] = 0;
@@ -536,8 +616,9 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
         tile_ok = S.error == 0;
 
         // ---- decode step 2: HALF a warp per block rebuilds the keys, four key bytes per lane -----------
-        // lane L (0..15) of a half-warp owns internal-key positions 4L..4L+3 (+64 per pass): the running value of a
-        // position is the byte last written by an entry whose shared prefix ends at or before it.
+        // lane L (0..15) of a half-warp owns internal-key positions 4L..4L+3 (+64 per pass) as one 32-bit word: an
+        // entry overwrites the bytes of the word that its delta covers (one unaligned load + byte mask) and inherits
+        // the rest from the entry before it.
         if (tile_ok) {
             const uint32_t hl = lane & 15, sub = lane >> 4;
             const uint32_t hmask = sub ? 0xffff0000u : 0x0000ffffu;
@@ -549,33 +630,34 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                 for (uint32_t pass = 0; pass * 64 < maxk; pass++) {
                     const uint32_t p0 = pass * 64 + 4 * hl;
                     uint32_t cur = 0, prev_klen = 0; // the four running bytes, little endian
+                    uint32_t sh = 0, ns = 0, ulen = 0, ko = 0, fl = 0;
+                    if (nrec) { sh = A.rank[rec0]; ns = A.order[rec0]; ulen = A.klen[rec0]; ko = A.koff[rec0]; fl = A.flags[rec0]; }
                     for (uint32_t i = 0; i < nrec; i++) {
                         const uint32_t r = rec0 + i;
-                        const uint32_t sh = A.rank[r], ns = A.order[r], ulen = A.klen[r];
-                        if (sh > prev_klen) { if (hl == 0) atomicMax(&S.error, (uint32_t)PGS_CORRUPTION); break; } // a prefix longer than the previous key
-                        prev_klen = ulen + 8;
-                        const uint8_t *d = A.in + A.koff[r];
-#pragma unroll
-                        for (uint32_t x = 0; x < 4; x++) {
-                            const uint32_t p = p0 + x;
-                            if (p >= sh && p < sh + ns) cur = (cur & ~(0xffu << (8 * x))) | ((uint32_t)d[p - sh] << (8 * x));
+                        const uint32_t c_sh = sh, c_ns = ns, c_ulen = ulen, c_ko = ko, c_fl = fl;
+                        if (i + 1 < nrec) { sh = A.rank[r + 1]; ns = A.order[r + 1]; ulen = A.klen[r + 1]; ko = A.koff[r + 1]; fl = A.flags[r + 1]; } // next entry's metadata in flight
+                        if (c_sh > prev_klen) { if (hl == 0) atomicMax(&S.error, (uint32_t)PGS_CORRUPTION); break; } // a prefix longer than the previous key
+                        prev_klen = c_ulen + 8;
+                        const uint32_t a = max(c_sh, p0), b = min(c_sh + c_ns, p0 + 4);
+                        if (a < b) {
+                            const uint32_t so = c_ko + (a - c_sh); // delta bytes for positions a..a+3 (offset inside IN, which is 16-aligned)
+                            const uint32_t *w = (const uint32_t *)A.in + (so >> 2);
+                            const uint32_t x = __funnelshift_r(w[0], w[1], (so & 3) * 8);
+                            const uint32_t s0 = 8 * (a - p0), s1 = 8 * (p0 + 4 - b);
+                            const uint32_t msk = (0xffffffffu << s0) & (0xffffffffu >> s1);
+                            cur = (cur & ~msk) | ((x << s0) & msk);
                         }
-                        const uint32_t pad = (ulen + 7) & ~7u; // slots are zero padded to 8 bytes
+                        const uint32_t pad = (c_ulen + 7) & ~7u; // slots are zero padded to 8 bytes
                         if (p0 < pad) {
-                            uint32_t keep = ulen > p0 ? ulen - p0 : 0; // bytes of this word that belong to the user key
-                            uint32_t v = keep >= 4 ? cur : (cur & ((1u << (8 * keep)) - 1u));
-                            *(uint32_t *)(A.arena + (size_t)r * KS + p0) = v;
+                            const uint32_t keep = c_ulen > p0 ? c_ulen - p0 : 0; // bytes of this word that belong to the user key
+                            *(uint32_t *)(A.arena + (size_t)r * KS + p0) = keep >= 4 ? cur : (cur & ((1u << (8 * keep)) - 1u));
                         }
                         // rare: the 8 trailer bytes after the user key straddle the shared prefix
-                        if (A.flags[r] && pass * 64 < ulen + 8 && pass * 64 + 64 > ulen) {
-                            uint32_t lo = 0, hi = 0;
-#pragma unroll
-                            for (uint32_t x = 0; x < 4; x++) {
-                                const uint32_t p = p0 + x, c = (cur >> (8 * x)) & 0xffu;
-                                if (p >= ulen && p < ulen + 8) { uint32_t j = p - ulen; if (j < 4) lo |= c << (8 * j); else hi |= c << (8 * (j - 4)); }
-                            }
-                            lo = __reduce_or_sync(hmask, lo);
-                            hi = __reduce_or_sync(hmask, hi);
+                        if (c_fl && pass * 64 < c_ulen + 8 && pass * 64 + 64 > c_ulen) {
+                            unsigned long long c = 0;
+                            if (p0 >= c_ulen) { if (p0 < c_ulen + 8) c = (unsigned long long)cur << (8 * (p0 - c_ulen)); }
+                            else if (c_ulen - p0 < 4) c = cur >> (8 * (c_ulen - p0));
+                            const uint32_t lo = __reduce_or_sync(hmask, (uint32_t)c), hi = __reduce_or_sync(hmask, (uint32_t)(c >> 32));
                             if (hl == 0) A.trailer[r] |= ((unsigned long long)hi << 32) | lo;
                         }
                     }
@@ -613,8 +695,6 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
 
         // ---- merge rank + shadow detection -----------------------------------------------------------------
         // (1) one thread per record: validity, position inside its own run, predecessor of the same run;
-        // (2) one thread per (record, other run): LCP-aware binary search for the number of that run's records that
-        //     sort before it; ranks accumulate with shared-memory atomics, so the searches of one record run in parallel.
         if (tile_ok) {
             for (uint32_t r = tid; r < S.n_rec; r += NT) {
                 uint32_t j = 0;
@@ -629,14 +709,21 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             }
         }
         __syncthreads();
+        // (2) one thread per (record of run j, LATER run o): LCP-aware binary search for the number of o's records that
+        //     sort before it (kept in pos[]); (3) one thread per (record of run o, EARLIER run j): the number of j's
+        //     records before it is an upper bound over j's monotone pos[] column -- integer compares only.  Every pair
+        //     of runs pays key compares in one direction; ranks accumulate with shared-memory atomics.
+        PT(12);
         if (tile_ok && P.k > 1) {
-            const uint32_t km1 = P.k - 1, ntask = S.n_rec * km1;
+            const uint32_t k = P.k, km1 = k - 1;
+            uint32_t ntask = 0;
+            for (uint32_t j = 0; j < k; j++) ntask += S.nrec[j] * (km1 - j);
             for (uint32_t id = tid; id < ntask; id += NT) {
-                const uint32_t r = id / km1, oi = id - r * km1;
+                uint32_t j = 0, local = id;
+                while (local >= S.nrec[j] * (km1 - j)) { local -= S.nrec[j] * (km1 - j); j++; }
+                const uint32_t nt = km1 - j, ri = local / nt;
+                const uint32_t o = j + 1 + (local - ri * nt), r = S.rec_base[j] + ri;
                 if (!(A.flags[r] & F_VALID)) continue;
-                uint32_t j = 0;
-                while (j + 1 < P.k && r >= S.rec_base[j + 1]) j++;
-                const uint32_t o = oi < j ? oi : oi + 1;
                 const uint8_t *key = A.arena + (size_t)r * KS;
                 const uint32_t kl = A.klen[r];
                 const unsigned long long tr = A.trailer[r];
@@ -653,10 +740,35 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                     }
                     if (before) { lo = mid + 1; lcp_lo = d; } else { hi = mid; lcp_hi = d; }
                 }
-                if (lo > S.vlo[o]) {
-                    atomicAdd(&A.R[r], lo - S.vlo[o]);
+                const uint32_t cnt = lo - S.vlo[o];
+                A.pos[(size_t)r * km1 + (o - 1)] = (uint16_t)cnt;
+                if (cnt) {
+                    atomicAdd(&A.R[r], cnt);
                     uint32_t q = base + lo - 1;
                     if (A.klen[q] == kl && cmp_slots(A.arena + (size_t)q * KS, kl, key, kl) == 0) atomicOr(&A.E[r], 1u);
+                }
+            }
+            __syncthreads();
+            PT(13);
+            ntask = 0;
+            for (uint32_t o = 1; o < k; o++) ntask += S.nrec[o] * o;
+            for (uint32_t id = tid; id < ntask; id += NT) {
+                uint32_t o = 1, local = id;
+                while (local >= S.nrec[o] * o) { local -= S.nrec[o] * o; o++; }
+                const uint32_t qi = local / o, j = local - qi * o, q = S.rec_base[o] + qi;
+                if (!(A.flags[q] & F_VALID)) continue;
+                const uint32_t me = qi - S.vlo[o]; // j's record r sorts before q  <=>  pos[r -> o] <= me
+                const uint32_t base = S.rec_base[j];
+                uint32_t lo = S.vlo[j], hi = S.vhi[j];
+                while (lo < hi) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (A.pos[(size_t)(base + mid) * km1 + (o - 1)] <= me) lo = mid + 1; else hi = mid;
+                }
+                const uint32_t cnt = lo - S.vlo[j];
+                if (cnt) {
+                    atomicAdd(&A.R[q], cnt);
+                    const uint32_t r = base + lo - 1, kl = A.klen[q];
+                    if (A.klen[r] == kl && cmp_slots(A.arena + (size_t)r * KS, kl, A.arena + (size_t)q * KS, kl) == 0) atomicOr(&A.E[q], 1u);
                 }
             }
         }
@@ -721,15 +833,18 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
         uint32_t m = 0;
         if (tile_ok) {
             const uint32_t nv = S.n_valid;
-            m = chunked_scan(nv, A.E, S.scan, [&](uint32_t p) -> uint32_t { return (A.flags[A.order[p]] & F_KEEP) ? 1u : 0u; });
+            // one pass scans both the survivor count and the survivors' raw sizes over the merged order.  Raw sizes
+            // decide the block cuts: an entry starts a new block when its raw offset enters the next block_size
+            // window (blocks hold ~block_size raw bytes; every entry's block is known in parallel)
+            m = (uint32_t)(chunked_scan2(nv, A.E, A.koff, S.scan64, [&](uint32_t p) -> unsigned long long {
+                const uint32_t r = A.order[p];
+                return (A.flags[r] & F_KEEP) ? ((1ull << 32) | (A.klen[r] + 8u + A.vlen[r] + 3u)) : 0ull;
+            }) >> 32);
             for (uint32_t p = tid; p < nv; p += NT) {
                 uint32_t r = A.order[p];
-                if (A.flags[r] & F_KEEP) A.surv[A.E[p]] = (uint16_t)r;
+                if (A.flags[r] & F_KEEP) { const uint32_t q = A.E[p]; A.surv[q] = (uint16_t)r; A.R[q] = A.koff[p]; }
             }
             __syncthreads();
-            // raw sizes decide the block cuts: an entry starts a new block when its raw offset enters the next
-            // block_size window (blocks hold ~block_size raw bytes; every entry's block is known in parallel)
-            chunked_scan(m, A.R, S.scan, [&](uint32_t p) -> uint32_t { uint32_t r = A.surv[p]; return A.klen[r] + 8u + A.vlen[r] + 3u; });
             const uint32_t BS = P.block_size;
             uint32_t nob = chunked_scan(m, A.E, S.scan, [&](uint32_t p) -> uint32_t {
                 return (p == 0 || A.R[p] / BS != A.R[p - 1] / BS) ? 1u : 0u;
@@ -794,32 +909,48 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             unsigned long long ex_bytes = 0;
             uint32_t ex_blocks = 0, ex_recs = 0, ex_keyb = 0;
             int64_t look = (int64_t)tile - 1;
-            while (look >= 0) {
-                int64_t idx = look - lane;
-                uint32_t have_inc = 0;
-                unsigned long long b = 0;
-                uint32_t bl = 0, rc = 0, kb = 0;
-                if (idx >= 0) {
-                    for (;;) {
-                        if (*(volatile uint32_t *)&P.inc[idx].flag) { have_inc = 1; break; }
-                        if (*(volatile uint32_t *)&P.agg[idx].flag) break;
+            while (look >= 0) { // 64 predecessors per round trip: lane L reads tiles look-L and look-32-L
+                uint32_t have_inc[2] = {0, 0};
+                unsigned long long b[2] = {0, 0};
+                uint32_t bl[2] = {0, 0}, rc[2] = {0, 0}, kb[2] = {0, 0};
+                const int64_t idx0 = look - lane, idx1 = look - 32 - lane;
+                uint32_t done = (idx0 < 0 ? 1u : 0u) | (idx1 < 0 ? 2u : 0u); // bit h: slot h is resolved (or before tile 0)
+                for (;;) { // both slots of each predecessor in one round trip; the inclusive prefix wins
+#pragma unroll
+                    for (uint32_t h = 0; h < 2; h++) {
+                        if (done >> h & 1) continue;
+                        const int64_t idx = h ? idx1 : idx0;
+                        const uint4 i0 = ld_v4_volatile(&P.inc[idx]), i1 = ld_v4_volatile((const uint8_t *)&P.inc[idx] + 16);
+                        const uint4 a0 = ld_v4_volatile(&P.agg[idx]), a1 = ld_v4_volatile((const uint8_t *)&P.agg[idx] + 16);
+                        if (i0.w && i1.z) { have_inc[h] = 1; b[h] = ((unsigned long long)i0.y << 32) | i0.x; bl[h] = i0.z; rc[h] = i1.x; kb[h] = i1.y; done |= 1u << h; }
+                        else if (a0.w && a1.z) { b[h] = ((unsigned long long)a0.y << 32) | a0.x; bl[h] = a0.z; rc[h] = a1.x; kb[h] = a1.y; done |= 1u << h; }
                     }
-                    __threadfence();
-                    const volatile TileAgg *s = have_inc ? &P.inc[idx] : &P.agg[idx];
-                    b = s->bytes; bl = s->blocks; rc = s->recs; kb = s->keyb;
+                    if (P.variant & 32) break; // diagnostics only: never wait for a predecessor (wrong offsets, right timing)
+                    // finished when every position before the nearest inclusive prefix is resolved (positions: the 32
+                    // lanes of half 0, then the 32 lanes of half 1)
+                    const uint32_t f0 = __ballot_sync(kFull, have_inc[0]), n0 = __ballot_sync(kFull, !(done & 1u));
+                    if (f0) { if (!(n0 & ((1u << (__ffs(f0) - 1)) - 1u))) break; continue; }
+                    if (n0) continue;
+                    const uint32_t f1 = __ballot_sync(kFull, have_inc[1]), n1 = __ballot_sync(kFull, !(done & 2u));
+                    if (f1) { if (!(n1 & ((1u << (__ffs(f1) - 1)) - 1u))) break; continue; }
+                    if (!n1) break;
                 }
-                uint32_t inc_mask = __ballot_sync(kFull, have_inc);
-                uint32_t stop = inc_mask ? (uint32_t)__ffs(inc_mask) - 1 : 31; // nearest predecessor with an inclusive prefix
-                if (lane > stop || idx < 0) { b = 0; bl = 0; rc = 0; kb = 0; }
+                const uint32_t inc0 = __ballot_sync(kFull, have_inc[0]), inc1 = __ballot_sync(kFull, have_inc[1]);
+                // nearest predecessor with an inclusive prefix: position = lane (first half) or 32 + lane (second half)
+                const uint32_t stop = inc0 ? (uint32_t)__ffs(inc0) - 1 : (inc1 ? 32u + (uint32_t)__ffs(inc1) - 1 : 63u);
+                if (lane > stop || idx0 < 0) { b[0] = 0; bl[0] = 0; rc[0] = 0; kb[0] = 0; }
+                if (32 + lane > stop || idx1 < 0) { b[1] = 0; bl[1] = 0; rc[1] = 0; kb[1] = 0; }
+                unsigned long long sb = b[0] + b[1];
+                uint32_t sbl = bl[0] + bl[1], src = rc[0] + rc[1], skb = kb[0] + kb[1];
                 for (uint32_t d = 16; d; d >>= 1) {
-                    b += __shfl_xor_sync(kFull, b, d);
-                    bl += __shfl_xor_sync(kFull, bl, d);
-                    rc += __shfl_xor_sync(kFull, rc, d);
-                    kb += __shfl_xor_sync(kFull, kb, d);
+                    sb += __shfl_xor_sync(kFull, sb, d);
+                    sbl += __shfl_xor_sync(kFull, sbl, d);
+                    src += __shfl_xor_sync(kFull, src, d);
+                    skb += __shfl_xor_sync(kFull, skb, d);
                 }
-                ex_bytes += b; ex_blocks += bl; ex_recs += rc; ex_keyb += kb;
-                if (inc_mask) break;
-                look -= 32;
+                ex_bytes += sb; ex_blocks += sbl; ex_recs += src; ex_keyb += skb;
+                if (inc0 | inc1) break;
+                look -= 64;
             }
             if (lane == 0) {
                 publish(&P.inc[tile], ex_bytes + my_bytes, ex_blocks + my_blocks, ex_recs + my_recs, ex_keyb + my_keyb);
@@ -830,28 +961,20 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                 if (ex_bytes + my_bytes > P.out_cap || ex_blocks + my_blocks > P.out_blk_cap || ex_keyb + my_keyb > P.out_ikey_cap)
                     atomicMax(&S.error, (uint32_t)PGS_ABORTED);
             }
-        }
-        __syncthreads();
-        PT(7);
-        tile_ok = S.error == 0;
-        if (warp == NW - 1) fetch_next_tile(P, S, lane); // overlaps the global-memory latency with the writes below
-
-        // ---- write the tile's blocks ------------------------------------------------------------------------------
-        if (tile_ok && m > 0) {
-            const uint32_t nob = S.n_ob;
-            uint8_t *out = P.out_data + S.base_bytes;
+            PT(8);
+        } else {
+          // ... while the other warps prepare the writes: nothing here needs the tile's output base
+          if (warp == NW - 1) fetch_next_tile(P, S, lane); // next ticket + slice metadata: global round trips under the look-back
+          if (tile_ok && m > 0) {
             uint32_t s_outb = 0, s_otomb = 0, s_okey = 0, s_oval = 0, mx_k = 0, mx_v = 0;
             unsigned long long mn_seq = ~0ull, mx_seq = 0;
-            if (tid == 0) S.scan[0] = 0;
-            __syncthreads();
             // (a) entry start offsets inside the tile's output + per-survivor stats, one thread per survivor
             uint32_t max_chunks = 0;
-            for (uint32_t p = tid; p < m; p += NT) {
+            for (uint32_t p = tid - 32; p < m; p += NT - 32) {
                 const uint32_t r = A.surv[p], b = A.blkid[p];
                 const uint32_t kl = A.klen[r], vl = A.vlen[r];
                 const uint32_t eoff = S.ob_off[b] + (A.E[p] - A.E[S.cut[b]]);
                 A.R[p] = eoff;
-                P.out_rec_off[S.base_recs + p] = A.E[p] - A.E[S.cut[b]];
                 const uint8_t f = A.flags[r];
                 const unsigned long long tr = A.trailer[r];
                 const uint8_t type = (f & F_TOMB) ? (uint8_t)PGS_TYPE_DELETION : (uint8_t)tr;
@@ -876,10 +999,28 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                 mn_seq = o1 < mn_seq ? o1 : mn_seq;
                 mx_seq = o2 > mx_seq ? o2 : mx_seq;
             }
-            if (lane == 0) atomicMax(&S.scan[0], max_chunks);
-            __syncthreads();
-            PT(8);
-            const uint32_t CH = S.scan[0];
+            if (lane == 0) {
+                atomicMax(&S.max_ch, max_chunks);
+                atomicAdd(&S.stat[ST_OUT_BYTES], s_outb);
+                atomicAdd(&S.stat[ST_OUT_TOMB], s_otomb);
+                atomicAdd(&S.stat[ST_OUT_KEY], s_okey);
+                atomicAdd(&S.stat[ST_OUT_VAL], s_oval);
+                atomicMax(&S.max_ukey, mx_k);
+                atomicMax(&S.max_vlen, mx_v);
+                atomicMin(&S.min_seq, mn_seq);
+                atomicMax(&S.max_seq, mx_seq);
+            }
+          }
+        }
+        __syncthreads();
+        PT(7);
+        tile_ok = S.error == 0;
+
+        // ---- write the tile's blocks ------------------------------------------------------------------------------
+        if (tile_ok && m > 0) {
+            const uint32_t nob = S.n_ob;
+            uint8_t *out = P.out_data + S.base_bytes;
+            const uint32_t CH = S.max_ch;
             // (b) values first: one thread per PAIR of 16-byte destination-aligned chunks (CH pairs per survivor),
             //     source words re-aligned with funnel shifts.  The first and last chunk of a value are written as
             //     FULL 16-byte stores whenever the bytes that do not belong to the value fall inside this entry's
@@ -897,9 +1038,10 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                 const uint32_t lead = (uint32_t)((uintptr_t)dv & 15);
                 const uint32_t nch = (lead + vl + 15) >> 4;
                 if (c0 >= nch) continue;
-                const uint8_t *sp = A.in + A.voff[r] + (c0 << 4) - lead; // may start a few bytes before the value: still inside IN / the key slots
-                const uint32_t sh = (uint32_t)((uintptr_t)sp & 3) * 8;
-                const uint32_t *w = (const uint32_t *)((uintptr_t)sp & ~(uintptr_t)3);
+                const int32_t so = (int32_t)(A.voff[r] + (c0 << 4)) - (int32_t)lead; // may start a few bytes before the value (even before IN): still inside the pool
+                const uint8_t *sp = A.in + so;
+                const uint32_t sh = (uint32_t)(so & 3) * 8;
+                const uint32_t *w = (const uint32_t *)A.in + (so >> 2); // IN is 16-aligned; the offset arithmetic keeps the loads in the shared window
                 uint32_t wv[9];
 #pragma unroll
                 for (uint32_t x = 0; x < 9; x++) wv[x] = w[x];
@@ -919,6 +1061,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                         const bool block_last = p + 1 == S.cut[A.blkid[p] + 1];
                         if (block_last || 16 - hi > A.rank[p + 1]) full = false;
                     }
+                    if (P.variant & 8) continue; // diagnostics only: no value stores
                     if (full) {
                         *reinterpret_cast<uint4 *>(addr) = o4;
                     } else if (lo == 0) { // exact tail [0, hi), hi < 16
@@ -943,21 +1086,24 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             if (tid == 0 && P.use_tma && P.early_tma && S.nx_tile < P.Q && !S.nx_err) {
                 uint32_t nb = 0, nr = 0, nbl = 0;
                 for (uint32_t j = 0; j < P.k; j++) { nb += S.nx_bytes[j]; nr += S.nx_nrec[j]; nbl += S.nx_nblk[j]; }
-                const RecArrays nx = carve(pool, P.pool_bytes, nb, nr, KS);
+                const RecArrays nx = carve(pool, P.pool_bytes, nb, nr, KS, P.k);
                 if (nb && nx.total <= P.pool_bytes && nbl <= kMaxTileBlocks && nr <= 65000 && in_start(P.pool_bytes, nb) >= A.arrays_end) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mbar_expect_tx((uint64_t *)&S.mbar, nb);
                     uint8_t *dst = nx.in;
                     for (uint32_t j = 0; j < P.k; j++) {
                         const uint32_t bytes = S.nx_bytes[j];
-                        if (bytes) tma_load_1d(dst, P.runs[j].data + P.runs[j].blk_off[S.nx_lo[j]], bytes, (uint64_t *)&S.mbar);
+                        if (bytes) tma_load_1d(dst, P.runs[j].data + S.nx_boff[j], bytes, (uint64_t *)&S.mbar);
                         dst += bytes;
                     }
                     early = true;
                 }
             }
-            // (c) entry heads = 3 varints | key delta | trailer: half a warp per survivor, one byte per lane, the
-            //     stores of a half-warp are consecutive bytes
+            // (c) entry heads = 3 varints | key delta | trailer.  A quarter warp per survivor; every lane assembles one
+            //     destination-aligned 32-bit word of the head from its three sources (packed varints in a register, key
+            //     bytes in the arena slot, trailer) with shifts and byte masks, and stores it whole; only a first or
+            //     last word that the head covers partly goes out byte by byte.
+            if (P.variant & 1) {
             for (uint32_t p = 2 * warp + (lane >> 4); p < m; p += 2 * NW) {
                 const uint32_t hl = lane & 15;
                 const uint32_t r = A.surv[p];
@@ -967,48 +1113,99 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                 const uint32_t l1 = varint_len(shared), l2 = varint_len(ns), l3 = varint_len(vl), h = l1 + l2 + l3;
                 uint8_t *dst = out + A.R[p];
                 const uint8_t *ksrc = A.arena + (size_t)r * KS + shared;
+                if (hl == 0) P.out_rec_off[S.base_recs + p] = A.R[p] - S.ob_off[A.blkid[p]]; // entry offset inside its block
                 for (uint32_t i = hl; i < hs; i += 16) {
                     uint32_t va = varint_byte(shared, i, l1), vb = varint_byte(ns, (i - l1) & 7, l2), vc = varint_byte(vl, (i - l1 - l2) & 7, l3);
                     uint32_t ki = i - h;
                     uint32_t vd = ksrc[ki < kd ? ki : 0];
                     uint32_t ve = (uint32_t)(otr >> (8 * ((ki - kd) & 7))) & 0xffu;
                     uint32_t v = i < l1 ? va : (i < l1 + l2 ? vb : (i < h ? vc : (ki < kd ? vd : ve)));
-                    dst[i] = (uint8_t)v;
+                    if (!(P.variant & 16)) dst[i] = (uint8_t)v;
                 }
             }
-            if (lane == 0) {
-                atomicAdd(&S.stat[ST_OUT_BYTES], s_outb);
-                atomicAdd(&S.stat[ST_OUT_TOMB], s_otomb);
-                atomicAdd(&S.stat[ST_OUT_KEY], s_okey);
-                atomicAdd(&S.stat[ST_OUT_VAL], s_oval);
-                atomicMax(&S.max_ukey, mx_k);
-                atomicMax(&S.max_vlen, mx_v);
-                atomicMin(&S.min_seq, mn_seq);
-                atomicMax(&S.max_seq, mx_seq);
+            } else {
+            for (uint32_t p = 4 * warp + (lane >> 3); p < m; p += 4 * NW) {
+                const uint32_t ql = lane & 7;
+                const uint32_t r = A.surv[p];
+                const uint32_t kl = A.klen[r], vl = A.vlen[r], shared = A.shr[p], hs = A.rank[p], doff = A.R[p];
+                const unsigned long long otr = A.trailer[r];
+                const uint32_t kd = kl - shared;
+                uint32_t l1, l2, l3;
+                unsigned long long hv = varint_pack(shared, l1);
+                const unsigned long long hv2 = varint_pack(kd + 8, l2), hv3 = varint_pack(vl, l3);
+                const uint32_t h = l1 + l2 + l3;
+                if (ql == 0) P.out_rec_off[S.base_recs + p] = doff - S.ob_off[A.blkid[p]]; // entry offset inside its block
+                uint8_t *dst = out + doff;
+                if (h > 8) { // lengths this large do not fit the packed register: one lane writes the head serially
+                    if (ql == 0) {
+                        uint8_t *d = dst;
+                        d += put_varint32(d, shared); d += put_varint32(d, kd + 8); d += put_varint32(d, vl);
+                        const uint8_t *ks = A.arena + (size_t)r * KS + shared;
+                        for (uint32_t i = 0; i < kd; i++) d[i] = ks[i];
+                        d += kd;
+                        for (uint32_t x = 0; x < 8; x++) d[x] = (uint8_t)(otr >> (8 * x));
+                    }
+                    continue;
+                }
+                hv |= (hv2 << (8 * l1)) | (hv3 << (8 * (l1 + l2)));
+                const uint32_t lead4 = doff & 3; // the tile's output base is 16-byte aligned
+                const uint32_t nwords = (lead4 + hs + 3) >> 2;
+                const int32_t kbase = (int32_t)(r * KS + shared) - (int32_t)h; // arena byte offset of head byte 0, were the key delta to start at byte h
+                for (uint32_t w = ql; w < nwords; w += 8) {
+                    const int32_t i0 = (int32_t)(4 * w) - (int32_t)lead4; // head byte held by the low byte of this word
+                    // bytes below index n inside this word: a byte mask
+                    auto lt = [&](uint32_t n) -> uint32_t {
+                        const int32_t d = (int32_t)n - i0;
+                        return d >= 4 ? 0xffffffffu : (d <= 0 ? 0u : ((1u << (8 * d)) - 1u));
+                    };
+                    const uint32_t m_h = lt(h), m_k = lt(h + kd), m_0 = lt(0), m_e = lt(hs);
+                    uint32_t word = 0;
+                    if (m_h) word |= (i0 >= 0 ? (uint32_t)(hv >> (8 * i0)) : (uint32_t)(hv << (8 * -i0))) & m_h;
+                    if (m_k & ~m_h) {
+                        const int32_t ko = kbase + i0;
+                        const uint32_t *kw = (const uint32_t *)A.arena + (ko >> 2);
+                        word |= __funnelshift_r(kw[0], kw[1], (uint32_t)(ko & 3) * 8) & m_k & ~m_h;
+                    }
+                    if (~m_k) {
+                        const int32_t j0 = i0 - (int32_t)(h + kd);
+                        const uint32_t tw = j0 >= 0 ? (j0 < 8 ? (uint32_t)(otr >> (8 * j0)) : 0u) : (j0 > -4 ? (uint32_t)(otr << (8 * -j0)) : 0u);
+                        word |= tw & ~m_k;
+                    }
+                    const uint32_t vm = m_e & ~m_0; // bytes of this word that belong to the head
+                    uint8_t *wp = dst + i0;
+                    if (vm == 0xffffffffu) *reinterpret_cast<uint32_t *>(wp) = word;
+                    else {
+#pragma unroll
+                        for (uint32_t x = 0; x < 4; x++) if ((vm >> (8 * x)) & 1u) wp[x] = (uint8_t)(word >> (8 * x));
+                    }
+                }
             }
-            // restart arrays, padding, index entries: one thread per output block
-            for (uint32_t b = tid; b < nob; b += NT) {
-                uint32_t c0 = S.cut[b], c1 = S.cut[b + 1], cnt = c1 - c0;
-                uint32_t nrest = (cnt + RI - 1) / RI;
-                uint32_t ent = A.E[c1] - A.E[c0];
+            }
+            // restart arrays, padding, index entries: one warp per output block
+            for (uint32_t b = warp; b < nob; b += NW) {
+                const uint32_t c0 = S.cut[b], c1 = S.cut[b + 1], cnt = c1 - c0;
+                const uint32_t nrest = (cnt + RI - 1) / RI;
+                const uint32_t ent = A.E[c1] - A.E[c0];
                 uint8_t *bp = out + S.ob_off[b];
                 uint8_t *rp = bp + ent;
-                for (uint32_t i = 0; i <= nrest; i++) {
+                for (uint32_t i = lane; i <= nrest; i += 32) {
                     uint32_t v = i < nrest ? A.E[c0 + i * RI] - A.E[c0] : nrest;
                     rp[4 * i] = (uint8_t)v; rp[4 * i + 1] = (uint8_t)(v >> 8); rp[4 * i + 2] = (uint8_t)(v >> 16); rp[4 * i + 3] = (uint8_t)(v >> 24);
                 }
-                for (uint32_t x = S.ob_size[b]; x < S.ob_off[b + 1] - S.ob_off[b]; x++) bp[x] = 0;
-                uint32_t g = S.base_blocks + b;
-                P.out_blk_off[g] = S.base_bytes + S.ob_off[b];
-                P.out_blk_size[g] = S.ob_size[b];
-                P.out_blk_rec[g] = S.base_recs + c0;
-                P.out_ikey_off[g] = S.base_keyb + S.ob_keyoff[b];
-                uint32_t lr = A.surv[c1 - 1], lk = A.klen[lr];
+                for (uint32_t x = S.ob_size[b] + lane; x < S.ob_off[b + 1] - S.ob_off[b]; x += 32) bp[x] = 0;
+                const uint32_t lr = A.surv[c1 - 1], lk = A.klen[lr];
                 uint8_t *kd = P.out_ikeys + S.base_keyb + S.ob_keyoff[b];
                 const uint8_t *ksrc = A.arena + (size_t)lr * KS;
-                for (uint32_t x = 0; x < lk; x++) kd[x] = ksrc[x];
-                atomicMax(&S.max_blk_size, S.ob_size[b]);
-                atomicMax(&S.max_blk_rec, cnt);
+                for (uint32_t x = lane; x < lk; x += 32) kd[x] = ksrc[x];
+                if (lane == 0) {
+                    const uint32_t g = S.base_blocks + b;
+                    P.out_blk_off[g] = S.base_bytes + S.ob_off[b];
+                    P.out_blk_size[g] = S.ob_size[b];
+                    P.out_blk_rec[g] = S.base_recs + c0;
+                    P.out_ikey_off[g] = S.base_keyb + S.ob_keyoff[b];
+                    atomicMax(&S.max_blk_size, S.ob_size[b]);
+                    atomicMax(&S.max_blk_rec, cnt);
+                }
             }
             if (tid == 0) S.stat[ST_OUT_REC] = m;
         }
@@ -1115,7 +1312,7 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     if (max_ukey > kMaxUkeyLen) { set_error("compact: user key of %u bytes > %u", max_ukey, kMaxUkeyLen); return PGS_NOT_SUPPORTED; }
     const uint32_t KS = std::max(8u, (max_ukey + 7) & ~7u);
     P.KS = KS;
-    P.rec_cost = KS + kRecExtra;
+    P.rec_cost = KS + kRecExtra + 2 * (k - 1);
     P.warp_scratch = (KS + 48 + 15) & ~15u;
     P.total_blocks = (uint32_t)total_blocks;
     P.use_tma = (e->cfg.flags & PGS_ENGINE_NO_TMA) ? 0 : 1;
@@ -1274,11 +1471,11 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     cudaError_t se = cudaStreamSynchronize(st);
     if (se != cudaSuccess) { cleanup(); return cuda_fail(se, "compaction kernels"); }
     if (phase_timing) {
-        static const char *names[12] = {"setup", "decode1", "decode2", "window", "rank", "filter", "layout", "lookback", "write_a", "write_b", "write_c", "flush"};
+        static const char *names[14] = {"setup", "decode1", "decode2", "window", "rank3", "filter", "layout", "a-wait", "lookback", "write_b", "write_c", "flush", "rank1", "rank2"};
         unsigned long long tot = 0;
-        for (int i = 0; i < 12; i++) tot += h_phase[i];
+        for (int i = 0; i < 14; i++) tot += h_phase[i];
         fprintf(stderr, "[k_merge phases] tiles=%u", P.Q);
-        for (int i = 0; i < 12; i++) fprintf(stderr, " %s=%.1f%%", names[i], tot ? 100.0 * (double)h_phase[i] / (double)tot : 0.0);
+        for (int i = 0; i < 14; i++) fprintf(stderr, " %s=%.1f%%", names[i], tot ? 100.0 * (double)h_phase[i] / (double)tot : 0.0);
         fprintf(stderr, " cycles/tile=%.0f\n", P.Q ? (double)tot / P.Q : 0.0);
     }
     float ms_total = 0, ms_merge = 0;

@@ -136,6 +136,16 @@ PGS_DEV uint64_t lds_u64_unaligned(const uint8_t *p)
     uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
     return ((uint64_t)hi << 32) | lo;
 }
+// same, addressed as (4-byte aligned base, byte offset): plain pointer arithmetic, so the compiler keeps the
+// loads in the shared address space (a uintptr_t round trip turns them into generic loads)
+PGS_DEV uint64_t lds_u64_at(const uint8_t *base4, uint32_t off)
+{
+    const uint32_t *w = (const uint32_t *)base4 + (off >> 2);
+    uint32_t sh = (off & 3) * 8;
+    uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+    return ((uint64_t)hi << 32) | lo;
+}
 // three varint32 (shared, non_shared, value_len) out of the 8 header bytes in x; returns the header length, or 0
 // when the common shape (shared < 128, non_shared < 128, value_len < 2^21) does not apply and the caller must use
 // the byte-wise decoder
