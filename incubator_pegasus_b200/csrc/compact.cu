@@ -40,12 +40,13 @@ constexpr uint32_t kRecExtra = 48; // per-record shared-memory bytes besides the
 
 enum : uint8_t { F_VALID = 1, F_SHADOW = 2, F_KEEP = 4, F_TOMB = 8, F_NEWTS = 16 };
 
-// One look-back slot = two 16-byte halves, each written with ONE vector store and carrying its own flag, so a
-// reader gets data and validity in a single round trip (no fence, no second load).
+// One look-back slot per tile = two 16-byte halves, each written with ONE vector store and carrying its own state
+// word, so a reader gets data and validity in a single round trip (no fence, no second load); halves whose states
+// differ were caught in the middle of an update and are read again.
 struct TileAgg {
     unsigned long long bytes;
-    uint32_t blocks, flag0;
-    uint32_t recs, keyb, flag1, pad;
+    uint32_t blocks, state0;
+    uint32_t recs, keyb, state1, pad;
 };
 static_assert(sizeof(TileAgg) == 32, "TileAgg");
 
@@ -69,7 +70,7 @@ struct MergeParams {
     uint32_t total_blocks;
     // tile pipeline
     uint32_t *ticket;
-    TileAgg *agg, *inc;
+    TileAgg *agg;
     uint32_t KS, pool_bytes, warp_scratch, use_tma, early_tma, variant;
     // filter + policy
     uint32_t now, enabled, validate_hash, data_version, default_ttl;
@@ -263,6 +264,11 @@ struct TileShared {
     uint32_t grec0[kMaxRuns]; // index of the slice's first record inside its run
     uint32_t scan[33];
     unsigned long long scan64[33];
+    unsigned long long lb_bytes[4];
+    uint32_t lb_blocks[4], lb_recs[4], lb_keyb[4], lb_inc[4];
+    long long prev_tile; // this CTA's previous tile and its inclusive prefix
+    unsigned long long prev_bytes;
+    uint32_t prev_blocks, prev_recs, prev_keyb;
     uint32_t stat[16];
     uint32_t tb_off[kMaxTileBlocks], tb_size[kMaxTileBlocks], tb_rec[kMaxTileBlocks], tb_nrec[kMaxTileBlocks];
     uint32_t cut[kMaxOutBlocks + 1], ob_off[kMaxOutBlocks + 1], ob_size[kMaxOutBlocks], ob_keyoff[kMaxOutBlocks + 1];
@@ -381,10 +387,11 @@ PGS_DEV void st_v4_volatile(void *p, uint4 v)
 {
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-PGS_DEV void publish(TileAgg *slot, unsigned long long bytes, uint32_t blocks, uint32_t recs, uint32_t keyb)
+// state 1 = the tile's own aggregate, 2 = inclusive prefix (overwrites the aggregate in place)
+PGS_DEV void publish(TileAgg *slot, unsigned long long bytes, uint32_t blocks, uint32_t recs, uint32_t keyb, uint32_t state)
 {
-    st_v4_volatile(slot, make_uint4((uint32_t)bytes, (uint32_t)(bytes >> 32), blocks, 1u));
-    st_v4_volatile((uint8_t *)slot + 16, make_uint4(recs, keyb, 1u, 0u));
+    st_v4_volatile(slot, make_uint4((uint32_t)bytes, (uint32_t)(bytes >> 32), blocks, state));
+    st_v4_volatile((uint8_t *)slot + 16, make_uint4(recs, keyb, state, 0u));
 }
 
 // the varint32 encoding of v as little-endian bytes in a register (at most 5), *len = its length
@@ -454,6 +461,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
     uint8_t *pool = dyn + 2 * (KS + 8);
 
     if (tid == 0) {
+        S.prev_tile = -1; S.prev_bytes = 0; S.prev_blocks = 0; S.prev_recs = 0; S.prev_keyb = 0;
         mbar_init((uint64_t *)&S.mbar, 1);
         mbar_fence_init();
     }
@@ -902,32 +910,48 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
         PT(6);
 
         // ---- decoupled look-back: where does this tile's output start? ----------------------------------------
-        if (warp == 0) {
-            unsigned long long my_bytes = S.tile_bytes;
-            uint32_t my_blocks = S.n_ob, my_recs = S.n_surv, my_keyb = S.tile_keyb;
-            if (lane == 0 && tile > 0) publish(&P.agg[tile], my_bytes, my_blocks, my_recs, my_keyb);
-            unsigned long long ex_bytes = 0;
+        // Warps 0..3 each resolve a window of 64 predecessors at the same time (one global round trip covers 256
+        // tiles, more than are ever in flight with one CTA per SM); warp 0 adds the windows up to the nearest
+        // inclusive prefix.
+        constexpr uint32_t LBW = 4;
+        if (warp < LBW) {
+            const unsigned long long my_bytes = S.tile_bytes;
+            const uint32_t my_blocks = S.n_ob, my_recs = S.n_surv, my_keyb = S.tile_keyb;
+            if (tid == 0) publish(&P.agg[tile], my_bytes, my_blocks, my_recs, my_keyb, 1u);
+            unsigned long long ex_bytes = 0; // thread 0 only
             uint32_t ex_blocks = 0, ex_recs = 0, ex_keyb = 0;
-            int64_t look = (int64_t)tile - 1;
-            while (look >= 0) { // 64 predecessors per round trip: lane L reads tiles look-L and look-32-L
+            int64_t look = (int64_t)tile - 1 - 64 * (int64_t)warp;
+            for (;;) { // lane L of window w reads tiles look-L and look-32-L; a tile before tile 0 is an inclusive prefix of zero
                 uint32_t have_inc[2] = {0, 0};
                 unsigned long long b[2] = {0, 0};
                 uint32_t bl[2] = {0, 0}, rc[2] = {0, 0}, kb[2] = {0, 0};
                 const int64_t idx0 = look - lane, idx1 = look - 32 - lane;
-                uint32_t done = (idx0 < 0 ? 1u : 0u) | (idx1 < 0 ? 2u : 0u); // bit h: slot h is resolved (or before tile 0)
-                for (;;) { // both slots of each predecessor in one round trip; the inclusive prefix wins
+                // Tiles at or before this CTA's previous tile need no load: its inclusive prefix is still in shared memory
+                // (every CTA takes tickets in increasing order), so a look-back reads only the tiles in between.
+                uint32_t done = 0; // bit h: slot h is resolved
+                const int64_t prev = S.prev_tile; // -1 before the CTA's first tile: "tile -1" has an inclusive prefix of zero
+#pragma unroll
+                for (uint32_t h = 0; h < 2; h++) {
+                    const int64_t idx = h ? idx1 : idx0;
+                    if (idx <= prev) {
+                        done |= 1u << h; have_inc[h] = 1;
+                        if (idx == prev) { b[h] = S.prev_bytes; bl[h] = S.prev_blocks; rc[h] = S.prev_recs; kb[h] = S.prev_keyb; }
+                    }
+                }
+                for (;;) { // both halves of each predecessor's slot in one round trip
 #pragma unroll
                     for (uint32_t h = 0; h < 2; h++) {
                         if (done >> h & 1) continue;
                         const int64_t idx = h ? idx1 : idx0;
-                        const uint4 i0 = ld_v4_volatile(&P.inc[idx]), i1 = ld_v4_volatile((const uint8_t *)&P.inc[idx] + 16);
                         const uint4 a0 = ld_v4_volatile(&P.agg[idx]), a1 = ld_v4_volatile((const uint8_t *)&P.agg[idx] + 16);
-                        if (i0.w && i1.z) { have_inc[h] = 1; b[h] = ((unsigned long long)i0.y << 32) | i0.x; bl[h] = i0.z; rc[h] = i1.x; kb[h] = i1.y; done |= 1u << h; }
-                        else if (a0.w && a1.z) { b[h] = ((unsigned long long)a0.y << 32) | a0.x; bl[h] = a0.z; rc[h] = a1.x; kb[h] = a1.y; done |= 1u << h; }
+                        if (a0.w && a0.w == a1.z) {
+                            have_inc[h] = a0.w == 2u;
+                            b[h] = ((unsigned long long)a0.y << 32) | a0.x; bl[h] = a0.z; rc[h] = a1.x; kb[h] = a1.y; done |= 1u << h;
+                        }
                     }
                     if (P.variant & 32) break; // diagnostics only: never wait for a predecessor (wrong offsets, right timing)
-                    // finished when every position before the nearest inclusive prefix is resolved (positions: the 32
-                    // lanes of half 0, then the 32 lanes of half 1)
+                    // finished when every position before the window's nearest inclusive prefix is resolved (positions:
+                    // the 32 lanes of half 0, then the 32 lanes of half 1)
                     const uint32_t f0 = __ballot_sync(kFull, have_inc[0]), n0 = __ballot_sync(kFull, !(done & 1u));
                     if (f0) { if (!(n0 & ((1u << (__ffs(f0) - 1)) - 1u))) break; continue; }
                     if (n0) continue;
@@ -938,8 +962,8 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                 const uint32_t inc0 = __ballot_sync(kFull, have_inc[0]), inc1 = __ballot_sync(kFull, have_inc[1]);
                 // nearest predecessor with an inclusive prefix: position = lane (first half) or 32 + lane (second half)
                 const uint32_t stop = inc0 ? (uint32_t)__ffs(inc0) - 1 : (inc1 ? 32u + (uint32_t)__ffs(inc1) - 1 : 63u);
-                if (lane > stop || idx0 < 0) { b[0] = 0; bl[0] = 0; rc[0] = 0; kb[0] = 0; }
-                if (32 + lane > stop || idx1 < 0) { b[1] = 0; bl[1] = 0; rc[1] = 0; kb[1] = 0; }
+                if (lane > stop) { b[0] = 0; bl[0] = 0; rc[0] = 0; kb[0] = 0; }
+                if (32 + lane > stop) { b[1] = 0; bl[1] = 0; rc[1] = 0; kb[1] = 0; }
                 unsigned long long sb = b[0] + b[1];
                 uint32_t sbl = bl[0] + bl[1], src = rc[0] + rc[1], skb = kb[0] + kb[1];
                 for (uint32_t d = 16; d; d >>= 1) {
@@ -948,12 +972,25 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                     src += __shfl_xor_sync(kFull, src, d);
                     skb += __shfl_xor_sync(kFull, skb, d);
                 }
-                ex_bytes += sb; ex_blocks += sbl; ex_recs += src; ex_keyb += skb;
-                if (inc0 | inc1) break;
-                look -= 64;
+                if (lane == 0) { S.lb_bytes[warp] = sb; S.lb_blocks[warp] = sbl; S.lb_recs[warp] = src; S.lb_keyb[warp] = skb; S.lb_inc[warp] = inc0 | inc1; }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                uint32_t found = 0;
+#pragma unroll
+                for (uint32_t w = 0; w < LBW; w++) found |= S.lb_inc[w];
+                if (tid == 0) {
+                    for (uint32_t w = 0; w < LBW; w++) {
+                        ex_bytes += S.lb_bytes[w]; ex_blocks += S.lb_blocks[w]; ex_recs += S.lb_recs[w]; ex_keyb += S.lb_keyb[w];
+                        if (S.lb_inc[w]) break;
+                    }
+                }
+                if (found) break;
+                asm volatile("bar.sync 1, 128;" ::: "memory"); // the windows' sums are consumed before the next round overwrites them
+                look -= 64 * LBW;
             }
-            if (lane == 0) {
-                publish(&P.inc[tile], ex_bytes + my_bytes, ex_blocks + my_blocks, ex_recs + my_recs, ex_keyb + my_keyb);
+            if (tid == 0) {
+                publish(&P.agg[tile], ex_bytes + my_bytes, ex_blocks + my_blocks, ex_recs + my_recs, ex_keyb + my_keyb, 2u);
+                S.prev_tile = (long long)tile;
+                S.prev_bytes = ex_bytes + my_bytes; S.prev_blocks = ex_blocks + my_blocks; S.prev_recs = ex_recs + my_recs; S.prev_keyb = ex_keyb + my_keyb;
                 S.base_bytes = ex_bytes;
                 S.base_blocks = ex_blocks;
                 S.base_recs = ex_recs;
@@ -970,7 +1007,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             unsigned long long mn_seq = ~0ull, mx_seq = 0;
             // (a) entry start offsets inside the tile's output + per-survivor stats, one thread per survivor
             uint32_t max_chunks = 0;
-            for (uint32_t p = tid - 32; p < m; p += NT - 32) {
+            for (uint32_t p = tid - 32 * LBW; p < m; p += NT - 32 * LBW) {
                 const uint32_t r = A.surv[p], b = A.blkid[p];
                 const uint32_t kl = A.klen[r], vl = A.vlen[r];
                 const uint32_t eoff = S.ob_off[b] + (A.E[p] - A.E[S.cut[b]]);
@@ -1405,12 +1442,12 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     CK(cudaMallocAsync(&d_split_pos, sizeof(uint32_t) * (Q + 1) * k, st));
     CK(cudaMallocAsync(&d_split_ref, sizeof(uint32_t) * (Q + 1), st));
     CK(cudaMallocAsync(&d_ticket, 256, st));
-    CK(cudaMallocAsync(&d_agg, sizeof(TileAgg) * 2 * Q, st));
+    CK(cudaMallocAsync(&d_agg, sizeof(TileAgg) * Q, st));
     CK(cudaMallocAsync(&d_stats, sizeof(MergeStats), st));
     CK(cudaMemsetAsync(d_split_pos, 0xFF, sizeof(uint32_t) * (Q + 1) * k, st));
     CK(cudaMemsetAsync(d_split_ref, 0xFF, sizeof(uint32_t) * (Q + 1), st));
     CK(cudaMemsetAsync(d_ticket, 0, 256, st));
-    CK(cudaMemsetAsync(d_agg, 0, sizeof(TileAgg) * 2 * Q, st));
+    CK(cudaMemsetAsync(d_agg, 0, sizeof(TileAgg) * Q, st));
     MergeStats hs{};
     hs.min_seq = ~0ull;
     hs.error_tile = 0xFFFFFFFFu;
@@ -1437,7 +1474,6 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     const bool phase_timing = pt_env && pt_env[0] == '1';
     P.phase_cycles = phase_timing ? (unsigned long long *)(d_ticket + 16) : nullptr;
     P.agg = d_agg;
-    P.inc = d_agg + Q;
     P.out_data = outr->d_data;
     P.out_cap = out_cap;
     P.out_blk_off = (unsigned long long *)outr->d_blk_off;
@@ -1465,7 +1501,7 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     e->launches += 2;
     CK(cudaMemcpyAsync(&hs, d_stats, sizeof hs, cudaMemcpyDeviceToHost, st));
     TileAgg fin{};
-    CK(cudaMemcpyAsync(&fin, d_agg + Q + (Q - 1), sizeof fin, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&fin, d_agg + (Q - 1), sizeof fin, cudaMemcpyDeviceToHost, st));
     unsigned long long h_phase[16] = {0};
     if (phase_timing) CK(cudaMemcpyAsync(h_phase, d_ticket + 16, sizeof h_phase, cudaMemcpyDeviceToHost, st));
     cudaError_t se = cudaStreamSynchronize(st);
