@@ -71,7 +71,7 @@ struct MergeParams {
     // tile pipeline
     uint32_t *ticket;
     TileAgg *agg;
-    uint32_t KS, pool_bytes, warp_scratch, use_tma, early_tma, variant;
+    uint32_t KS, pool_bytes, warp_scratch, use_tma, early_tma;
     // filter + policy
     uint32_t now, enabled, validate_hash, data_version, default_ttl;
     int32_t pidx, partition_version;
@@ -404,7 +404,6 @@ PGS_DEV unsigned long long varint_pack(uint32_t v, uint32_t &len)
     len = n + 1;
     return o;
 }
-PGS_DEV uint32_t varint_byte(uint32_t v, uint32_t j, uint32_t len) { return ((v >> ((7 * j) & 31)) & 0x7fu) | (j + 1 < len ? 0x80u : 0u); }
 
 // one warp takes the next ticket and loads that tile's per-run slice metadata into S.nx_*
 PGS_DEV void fetch_next_tile(const MergeParams &P, TileShared &S, uint32_t lane)
@@ -949,7 +948,6 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                             b[h] = ((unsigned long long)a0.y << 32) | a0.x; bl[h] = a0.z; rc[h] = a1.x; kb[h] = a1.y; done |= 1u << h;
                         }
                     }
-                    if (P.variant & 32) break; // diagnostics only: never wait for a predecessor (wrong offsets, right timing)
                     // finished when every position before the window's nearest inclusive prefix is resolved (positions:
                     // the 32 lanes of half 0, then the 32 lanes of half 1)
                     const uint32_t f0 = __ballot_sync(kFull, have_inc[0]), n0 = __ballot_sync(kFull, !(done & 1u));
@@ -1098,7 +1096,6 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                         const bool block_last = p + 1 == S.cut[A.blkid[p] + 1];
                         if (block_last || 16 - hi > A.rank[p + 1]) full = false;
                     }
-                    if (P.variant & 8) continue; // diagnostics only: no value stores
                     if (full) {
                         *reinterpret_cast<uint4 *>(addr) = o4;
                     } else if (lo == 0) { // exact tail [0, hi), hi < 16
@@ -1140,27 +1137,6 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             //     destination-aligned 32-bit word of the head from its three sources (packed varints in a register, key
             //     bytes in the arena slot, trailer) with shifts and byte masks, and stores it whole; only a first or
             //     last word that the head covers partly goes out byte by byte.
-            if (P.variant & 1) {
-            for (uint32_t p = 2 * warp + (lane >> 4); p < m; p += 2 * NW) {
-                const uint32_t hl = lane & 15;
-                const uint32_t r = A.surv[p];
-                const uint32_t kl = A.klen[r], vl = A.vlen[r], shared = A.shr[p], hs = A.rank[p];
-                const unsigned long long otr = A.trailer[r];
-                const uint32_t kd = kl - shared, ns = kd + 8;
-                const uint32_t l1 = varint_len(shared), l2 = varint_len(ns), l3 = varint_len(vl), h = l1 + l2 + l3;
-                uint8_t *dst = out + A.R[p];
-                const uint8_t *ksrc = A.arena + (size_t)r * KS + shared;
-                if (hl == 0) P.out_rec_off[S.base_recs + p] = A.R[p] - S.ob_off[A.blkid[p]]; // entry offset inside its block
-                for (uint32_t i = hl; i < hs; i += 16) {
-                    uint32_t va = varint_byte(shared, i, l1), vb = varint_byte(ns, (i - l1) & 7, l2), vc = varint_byte(vl, (i - l1 - l2) & 7, l3);
-                    uint32_t ki = i - h;
-                    uint32_t vd = ksrc[ki < kd ? ki : 0];
-                    uint32_t ve = (uint32_t)(otr >> (8 * ((ki - kd) & 7))) & 0xffu;
-                    uint32_t v = i < l1 ? va : (i < l1 + l2 ? vb : (i < h ? vc : (ki < kd ? vd : ve)));
-                    if (!(P.variant & 16)) dst[i] = (uint8_t)v;
-                }
-            }
-            } else {
             for (uint32_t p = 4 * warp + (lane >> 3); p < m; p += 4 * NW) {
                 const uint32_t ql = lane & 7;
                 const uint32_t r = A.surv[p];
@@ -1216,7 +1192,6 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                         for (uint32_t x = 0; x < 4; x++) if ((vm >> (8 * x)) & 1u) wp[x] = (uint8_t)(word >> (8 * x));
                     }
                 }
-            }
             }
             // restart arrays, padding, index entries: one warp per output block
             for (uint32_t b = warp; b < nob; b += NW) {
@@ -1356,8 +1331,6 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     {
         const char *ev = getenv("PGS_EARLY_TMA"); // diagnostics: 0 turns the early block load off
         P.early_tma = (ev && ev[0] == '0') ? 0 : 1;
-        const char *vv = getenv("PGS_VARIANT");
-        P.variant = vv ? (uint32_t)atoi(vv) : 0;
     }
     P.block_size = e->cfg.block_size;
     P.restart_interval = e->cfg.restart_interval;
