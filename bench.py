@@ -199,11 +199,12 @@ def main():
     n_records = sum(r.n for r in runs)
     gen_s = time.time() - t0
     # pinned host copies of the block bytes for the end-to-end leg
-    pinned = []
+    pinned, pinned_tensors = [], []
     for hr in host_runs:
         t = torch.empty(hr.data.shape[0], dtype=torch.uint8).pin_memory()
         t.numpy()[:] = hr.data
         pinned.append(pgs.BlockRun(t.numpy(), hr.blk_off, hr.blk_size))
+        pinned_tensors.append(t)
     h2d_bytes = sum(int(p.data.shape[0]) for p in pinned)
 
     eng = pgs.Engine(device=local_rank, ctas_per_sm=args.ctas_per_sm, flags=1 if args.no_tma else 0)
@@ -248,15 +249,23 @@ def main():
     if not args.skip_e2e:
         part2 = eng.partition(app_id=1, pidx=rank + 1000)
 
+        split = {"upload": 0.0, "compact": 0.0, "drop": 0.0}
+
         def e2e_step():
+            t0 = time.perf_counter()
             rid = [part2.upload(p) for p in pinned]            # H2D of the runs + device index build
+            t1 = time.perf_counter()
             r = part2.compact(rid, out_level=1, bottommost=1, now=NOW, enabled=True)  # result struct comes back
+            t2 = time.perf_counter()
             if r.new_run_id:
                 part2.drop(r.new_run_id)
+            t3 = time.perf_counter()
+            split["upload"] += (t1 - t0) * 1e3; split["compact"] += (t2 - t1) * 1e3; split["drop"] += (t3 - t2) * 1e3
             return r
 
         e2e_step()
         barrier()
+        split.update(upload=0.0, compact=0.0, drop=0.0)
         e0 = time.perf_counter()
         n_e2e = max(1, min(args.steps, 3))
         for _ in range(n_e2e):
@@ -266,9 +275,23 @@ def main():
         te = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        # what the host link of this box delivers for a plain pinned -> device copy (context for the number above)
+        probe = torch.empty(min(1 << 30, int(pinned_tensors[0].numel())), dtype=torch.uint8, device="cuda")
+        src = pinned_tensors[0][: probe.numel()]
+        probe.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        probe.copy_(src, non_blocking=True)
+        p1.record()
+        torch.cuda.synchronize()
+        h2d_probe = probe.numel() / (p0.elapsed_time(p1) / 1e3) / 1e9
+        del probe
         e2e = {"value": world * in_bytes / (float(te.item()) / 1e3) / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 128, "ms_per_step": float(te.item()),
-               "timed": "host wall clock around upload(4 runs)+compact, barrier+synchronize both sides"}
+               "timed": "host wall clock around upload(4 runs)+compact, barrier+synchronize both sides",
+               "h2d_link_probe_GBps": round(h2d_probe, 1),
+               "host_ms_per_step": {k: round(v / n_e2e, 2) for k, v in split.items()}}
         part2.close()
 
     # ---- read path on the same partition (4 overlapping runs resident): YCSB-C shaped, zipfian hash keys ----------

@@ -279,6 +279,8 @@ struct ScanShared {
     unsigned long long size, arena_used;
     uint32_t complete, iter_valid, lookahead, resume_len, first_chunk;
     uint32_t P, F; // per chunk
+    uint32_t cand_len[kMaxReadRuns];
+    uint32_t grec0[kMaxReadRuns]; // index of the slice's first record inside its run
     unsigned long long crc[256];
 };
 
@@ -363,8 +365,9 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
     // bounds of the current chunk, zero padded slots: lo = exclusive/inclusive lower, hi = upper
     const uint32_t slot = (KS + 8 + 15) & ~15u; // keeps `pool` (the TMA destination) 16-byte aligned
     uint8_t *klo = dyn, *khi = dyn + slot, *kpre = dyn + 2 * slot;
-    uint8_t *wscr = dyn + 3 * slot + warp * P.warp_scratch;
-    uint8_t *pool = dyn + 3 * slot + kScanWarps * P.warp_scratch;
+    uint8_t *kend = dyn + 3 * slot;  // the range end (first KS+8 bytes: no stored key is longer than KS)
+    uint8_t *cand = dyn + 4 * slot;  // one slot per run: its candidate for the chunk's far bound
+    uint8_t *pool = dyn + (4 + NR) * slot + kScanWarps * P.warp_scratch;
 
     if (tid == 0) { mbar_init((uint64_t *)&S.mbar, 1); mbar_fence_init(); }
     __syncthreads();
@@ -413,6 +416,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
             uint8_t v = i < sl && i < KS ? sk[i] : 0;
             if (rev) khi[i] = v; else klo[i] = v;
             kpre[i] = i < pre_len ? start[i] : 0;
+            kend[i] = i < endl ? endk[i] : 0;
         }
         if (tid == 0) {
             uint32_t sl = rev ? Q.stop_len : Q.start_len;
@@ -469,7 +473,9 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                     }
                     lo_b = rev ? c + 1 - m : c;
                     bytes_j = (uint32_t)(r.blk_off[lo_b + m] - r.blk_off[lo_b]);
-                    recs_j = r.blk_rec[lo_b + m] - r.blk_rec[lo_b];
+                    const uint32_t g0 = r.blk_rec[lo_b];
+                    recs_j = r.blk_rec[lo_b + m] - g0;
+                    S.grec0[j] = g0;
                     more_j = rev ? (lo_b > 0) : (lo_b + m < r.nb);
                 }
                 const uint32_t ib = warp_incl_scan(bytes_j, lane), ir = warp_incl_scan(recs_j, lane), im = warp_incl_scan(m, lane);
@@ -529,33 +535,41 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                 S.tb_rec[t] = S.rec_base[j] + (r.blk_rec[gb] - r.blk_rec[lo_b]);
                 S.tb_nrec[t] = r.blk_rec[gb + 1] - r.blk_rec[gb];
             }
-            // chunk's far bound: everything up to the nearest "last loaded block" key of a run that has more blocks
-            if (tid == 0) {
-                int best = -1;
-                uint32_t best_b = 0;
-                for (uint32_t j = 0; j < NR; j++) {
-                    if (!S.nblk[j] || !S.more[j]) continue;
+            // chunk's far bound: everything up to the nearest "last loaded block" key of a run that has more blocks.
+            // Every candidate key is first staged in shared memory (one warp per run, coalesced), then compared there:
+            // a byte-wise compare straight out of global memory would pay one round trip per byte.
+            for (uint32_t j = warp; j < NR; j += kScanWarps) {
+                uint32_t l = 0xFFFFFFFFu;
+                if (S.nblk[j] && S.more[j]) {
                     const RunDev &r = P.rr.runs[j];
-                    uint32_t m = S.nblk[j];
+                    const uint32_t m = S.nblk[j];
                     // forward: last key of the last loaded block; reverse: last key of the block before the first loaded one
-                    uint32_t bb = rev ? (S.cur[j] + 1 - m) - 1 : S.cur[j] + m - 1;
-                    if (best < 0) { best = (int)j; best_b = bb; continue; }
-                    const RunDev &rb = P.rr.runs[best];
-                    int c = cmp_bytes(r.ikeys + r.ikey_off[bb], r.ikey_off[bb + 1] - r.ikey_off[bb],
-                                      rb.ikeys + rb.ikey_off[best_b], rb.ikey_off[best_b + 1] - rb.ikey_off[best_b]);
-                    if (rev ? c > 0 : c < 0) { best = (int)j; best_b = bb; }
+                    const uint32_t bb = rev ? (S.cur[j] + 1 - m) - 1 : S.cur[j] + m - 1;
+                    const uint32_t o = r.ikey_off[bb];
+                    l = r.ikey_off[bb + 1] - o;
+                    for (uint32_t i = lane; i < KS + 8; i += 32) cand[j * slot + i] = i < l ? r.ikeys[o + i] : 0;
                 }
-                S.P = (uint32_t)best; S.F = best_b; // reuse as scratch: run / block of the far bound
+                if (lane == 0) S.cand_len[j] = l;
             }
             if (P.use_tma) { mbar_wait((uint64_t *)&S.mbar, phase); phase ^= 1; }
+            __syncthreads();
+            if (tid == 0) {
+                int best = -1;
+                for (uint32_t j = 0; j < NR; j++) {
+                    if (S.cand_len[j] == 0xFFFFFFFFu) continue;
+                    if (best < 0) { best = (int)j; continue; }
+                    int c = cmp_bytes(cand + j * slot, S.cand_len[j], cand + best * slot, S.cand_len[best]);
+                    if (rev ? c > 0 : c < 0) best = (int)j;
+                }
+                S.P = (uint32_t)best; // reuse as scratch: run of the far bound
+            }
             __syncthreads();
             {
                 int best = (int)S.P;
                 uint8_t *dst = rev ? klo : khi;
                 if (best >= 0) {
-                    const RunDev &rb = P.rr.runs[best];
-                    uint32_t o = rb.ikey_off[S.F], l = rb.ikey_off[S.F + 1] - o;
-                    for (uint32_t i = tid; i < KS + 8; i += kScanThreads) dst[i] = i < l ? rb.ikeys[o + i] : 0;
+                    const uint32_t l = S.cand_len[best];
+                    for (uint32_t i = tid; i < KS + 8; i += kScanThreads) dst[i] = cand[best * slot + i];
                     if (tid == 0) { if (rev) { S.lo_len = l; S.has_lo = 1; S.lo_incl = 0; } else { S.hi_len = l; S.has_hi = 1; S.hi_incl = 1; } }
                 } else if (tid == 0) {
                     if (rev) S.has_lo = 0; else S.has_hi = 0;
@@ -563,48 +577,93 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
             }
             __syncthreads();
 
-            // ---- decode: one warp per block ---------------------------------------------------------------
-            for (uint32_t t = warp; t < S.n_blk; t += kScanWarps) {
-                const uint8_t *base = A.in + S.tb_off[t];
-                uint32_t size = S.tb_size[t], rec0 = S.tb_rec[t], expect = S.tb_nrec[t];
-                uint32_t err = 0, nr = 0;
-                if (size < 8) err = PGS_CORRUPTION;
-                if (!err) { nr = ld32le(base + size - 4); if (nr == 0 || (unsigned long long)nr * 4 + 4 > size) err = PGS_CORRUPTION; }
-                uint32_t limit = err ? 0 : size - 4 - 4 * nr;
-                uint32_t p = 0, prev_klen = 0, i = 0;
-                while (!err && p < limit && i < expect) {
-                    uint32_t sh, ns, vl, h = 0, c;
-                    c = get_varint32(base + p, limit - p, sh); h += c;
-                    if (c) { c = get_varint32(base + p + h, limit - p - h, ns); h += c; }
-                    if (c) { c = get_varint32(base + p + h, limit - p - h, vl); h += c; }
-                    if (!c) { err = PGS_CORRUPTION; break; }
-                    uint32_t kl = sh + ns;
-                    if (sh > prev_klen || kl < 8 || kl - 8 > KS || (unsigned long long)p + h + ns + vl > limit) { err = PGS_CORRUPTION; break; }
-                    for (uint32_t x = lane; x < ns; x += 32) wscr[sh + x] = base[p + h + x];
-                    __syncwarp();
-                    uint32_t ulen = kl - 8, r = rec0 + i, words = (ulen + 7) >> 3;
-                    for (uint32_t w = lane; w < words; w += 32) {
-                        unsigned long long v = *(const unsigned long long *)(wscr + 8 * w);
-                        uint32_t keep = ulen - 8 * w;
-                        if (keep < 8) v &= (1ull << (8 * keep)) - 1;
-                        *(unsigned long long *)(A.arena + (size_t)r * KS + 8 * w) = v;
+            // ---- decode step 1: one THREAD per record parses its entry header; the entry's offset inside its block
+            //      comes from the run's rec_off index, so no thread walks a block's entry chain -------------------------
+            {
+                const uint32_t nblk = S.n_blk;
+                for (uint32_t r = tid; r < S.n_rec; r += kScanThreads) {
+                    uint32_t j = 0;
+                    while (j + 1 < NR && r >= S.rec_base[j + 1]) j++;
+                    uint32_t lo = 0, hi = nblk; // block of record r: last t with tb_rec[t] <= r
+                    while (lo + 1 < hi) { uint32_t mid = (lo + hi) >> 1; if (S.tb_rec[mid] <= r) lo = mid; else hi = mid; }
+                    const uint32_t t = lo;
+                    const uint8_t *base = A.in + S.tb_off[t];
+                    const uint32_t size = S.tb_size[t], i = r - S.tb_rec[t], cnt = S.tb_nrec[t];
+                    uint32_t err = 0, nr = 0;
+                    if (size < 8) err = PGS_CORRUPTION;
+                    if (!err) { nr = ld32le(base + size - 4); if (nr == 0 || (unsigned long long)nr * 4 + 4 > size) err = PGS_CORRUPTION; }
+                    const uint32_t limit = err ? 0 : size - 4 - 4 * nr;
+                    const uint32_t p = err ? 0 : P.rr.runs[j].rec_off[S.grec0[j] + (r - S.rec_base[j])];
+                    if (!err && (p >= limit || (i == 0 && p != 0))) err = PGS_CORRUPTION;
+                    if (!err) {
+                        uint32_t sh, ns, vl, h, c;
+                        h = c = parse_header8(lds_u64_at(A.in, S.tb_off[t] + p), sh, ns, vl); // header bytes from registers
+                        if (!c) { // uncommon shape: byte-wise decoder
+                            h = 0;
+                            c = get_varint32(base + p, limit - p, sh); h += c;
+                            if (c) { c = get_varint32(base + p + h, limit - p - h, ns); h += c; }
+                            if (c) { c = get_varint32(base + p + h, limit - p - h, vl); h += c; }
+                        }
+                        const uint32_t kl = sh + ns;
+                        const unsigned long long end = (unsigned long long)p + h + ns + vl;
+                        if (!c || kl < 8 || kl - 8 > KS || end > limit || (i == 0 && sh != 0) || (i + 1 == cnt && end != limit)) err = PGS_CORRUPTION;
+                        else {
+                            A.rank[r] = (uint16_t)sh;  // scratch until the rank phase
+                            A.order[r] = (uint16_t)ns; // scratch until the scatter phase
+                            A.A1[r] = S.tb_off[t] + p + h; // the key delta
+                            A.klen[r] = (uint16_t)(kl - 8);
+                            A.voff[r] = S.tb_off[t] + p + h + ns;
+                            A.vlen[r] = vl;
+                            if (ns >= 8) { A.trailer[r] = lds_u64_at(A.in, S.tb_off[t] + p + h + ns - 8); A.flags[r] = 0; }
+                            else { A.trailer[r] = 0; A.flags[r] = 1; } // part of the trailer is shared with the previous key: step 2
+                        }
                     }
-                    if (lane == 0) {
-                        unsigned long long tr = 0;
-                        for (int x = 7; x >= 0; x--) tr = (tr << 8) | wscr[ulen + x];
-                        A.trailer[r] = tr;
-                        A.klen[r] = (uint16_t)ulen;
-                        A.voff[r] = S.tb_off[t] + p + h + ns;
-                        A.vlen[r] = vl;
-                        A.flags[r] = 0;
-                    }
-                    __syncwarp();
-                    prev_klen = kl;
-                    p += h + ns + vl;
-                    i++;
+                    if (err) atomicMax(&S.error, err);
                 }
-                if (!err && (i != expect || p != limit)) err = PGS_CORRUPTION;
-                if (err && lane == 0) atomicMax(&S.error, err);
+            }
+            __syncthreads();
+            if (S.error) break;
+            // ---- decode step 2: HALF a warp per block rebuilds the keys, four key bytes per lane (see k_merge) ---------
+            {
+                const uint32_t hl = lane & 15, sub = lane >> 4;
+                const uint32_t hmask = sub ? 0xffff0000u : 0x0000ffffu;
+                for (uint32_t t = 2 * warp + sub; t < S.n_blk; t += 2 * kScanWarps) {
+                    const uint32_t rec0 = S.tb_rec[t], nrec = S.tb_nrec[t];
+                    uint32_t maxk = 0;
+                    for (uint32_t i = hl; i < nrec; i += 16) maxk = max(maxk, (uint32_t)A.klen[rec0 + i] + 8);
+                    maxk = __reduce_max_sync(hmask, maxk);
+                    for (uint32_t pass = 0; pass * 64 < maxk; pass++) {
+                        const uint32_t p0 = pass * 64 + 4 * hl;
+                        uint32_t cur = 0, prev_klen = 0; // the four running bytes, little endian
+                        for (uint32_t i = 0; i < nrec; i++) {
+                            const uint32_t r = rec0 + i;
+                            const uint32_t sh = A.rank[r], ns = A.order[r], ulen = A.klen[r], ko = A.A1[r], fl = A.flags[r];
+                            if (sh > prev_klen) { if (hl == 0) atomicMax(&S.error, (uint32_t)PGS_CORRUPTION); break; } // a prefix longer than the previous key
+                            prev_klen = ulen + 8;
+                            const uint32_t a = max(sh, p0), b = min(sh + ns, p0 + 4);
+                            if (a < b) {
+                                const uint32_t so = ko + (a - sh); // delta bytes for positions a..a+3
+                                const uint32_t *w = (const uint32_t *)A.in + (so >> 2);
+                                const uint32_t x = __funnelshift_r(w[0], w[1], (so & 3) * 8);
+                                const uint32_t s0 = 8 * (a - p0), s1 = 8 * (p0 + 4 - b);
+                                const uint32_t msk = (0xffffffffu << s0) & (0xffffffffu >> s1);
+                                cur = (cur & ~msk) | ((x << s0) & msk);
+                            }
+                            const uint32_t pad = (ulen + 7) & ~7u; // slots are zero padded to 8 bytes
+                            if (p0 < pad) {
+                                const uint32_t keep = ulen > p0 ? ulen - p0 : 0;
+                                *(uint32_t *)(A.arena + (size_t)r * KS + p0) = keep >= 4 ? cur : (cur & ((1u << (8 * keep)) - 1u));
+                            }
+                            if (fl && pass * 64 < ulen + 8 && pass * 64 + 64 > ulen) { // rare: the trailer straddles the shared prefix
+                                unsigned long long c = 0;
+                                if (p0 >= ulen) { if (p0 < ulen + 8) c = (unsigned long long)cur << (8 * (p0 - ulen)); }
+                                else if (ulen - p0 < 4) c = cur >> (8 * (ulen - p0));
+                                const uint32_t lo = __reduce_or_sync(hmask, (uint32_t)c), hi = __reduce_or_sync(hmask, (uint32_t)(c >> 32));
+                                if (hl == 0) A.trailer[r] |= ((unsigned long long)hi << 32) | lo;
+                            }
+                        }
+                    }
+                }
             }
             __syncthreads();
             if (S.error) break;
@@ -641,37 +700,59 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                 S.n_valid = nv;
             }
             // ---- merge rank + shadowing ----------------------------------------------------------------------------
+            // (1) one thread per record: validity, position inside its own run, predecessor of the same run;
+            // (2) one thread per (record, other run): LCP-aware binary search for the number of that run's records that sort
+            //     before it; ranks accumulate with shared-memory atomics (A1 = rank, A2 = shadowed)
             for (uint32_t r = tid; r < S.n_rec; r += kScanThreads) {
                 uint32_t j = 0;
                 while (j + 1 < NR && r >= S.rec_base[j + 1]) j++;
                 uint32_t idx = r - S.rec_base[j];
                 if (idx < S.vlo[j] || idx >= S.vhi[j]) { A.flags[r] = 0; continue; }
-                const uint8_t *key = A.arena + (size_t)r * KS;
-                uint32_t kl = A.klen[r];
-                unsigned long long tr = A.trailer[r];
-                uint32_t rank = idx - S.vlo[j];
-                bool shadow = idx > 0 && A.klen[r - 1] == kl && cmp_slots(A.arena + (size_t)(r - 1) * KS, kl, key, kl) == 0;
-                for (uint32_t o = 0; o < NR; o++) {
-                    if (o == j || S.vhi[o] == S.vlo[o]) continue;
+                const uint32_t kl = A.klen[r];
+                const bool shadow = idx > 0 && A.klen[r - 1] == kl && cmp_slots(A.arena + (size_t)(r - 1) * KS, kl, A.arena + (size_t)r * KS, kl) == 0;
+                A.A1[r] = idx - S.vlo[j];
+                A.A2[r] = shadow ? 1u : 0u;
+                A.flags[r] = SF_VALID;
+            }
+            __syncthreads();
+            if (NR > 1) {
+                const uint32_t km1 = NR - 1, ntask = S.n_rec * km1;
+                for (uint32_t id = tid; id < ntask; id += kScanThreads) {
+                    const uint32_t r = id / km1, oi = id - r * km1;
+                    if (!(A.flags[r] & SF_VALID)) continue;
+                    uint32_t j = 0;
+                    while (j + 1 < NR && r >= S.rec_base[j + 1]) j++;
+                    const uint32_t o = oi < j ? oi : oi + 1;
+                    if (S.vhi[o] == S.vlo[o]) continue;
+                    const uint8_t *key = A.arena + (size_t)r * KS;
+                    const uint32_t kl = A.klen[r];
+                    const unsigned long long tr = A.trailer[r];
                     uint32_t base = S.rec_base[o], lo = S.vlo[o], hi = S.vhi[o];
+                    uint32_t lcp_lo = 0, lcp_hi = 0; // words shared with the keys just outside [lo, hi)
                     while (lo < hi) {
-                        uint32_t mid = (lo + hi) >> 1, q = base + mid;
-                        int c = cmp_slots(A.arena + (size_t)q * KS, A.klen[q], key, kl);
-                        bool before = c != 0 ? c < 0 : (A.trailer[q] > tr || (A.trailer[q] == tr && o < j));
-                        if (before) lo = mid + 1; else hi = mid;
+                        uint32_t mid = (lo + hi) >> 1, q = base + mid, d;
+                        int c = cmp_slots_from(A.arena + (size_t)q * KS, A.klen[q], key, kl, min(lcp_lo, lcp_hi), &d);
+                        bool before;
+                        if (c != 0) before = c < 0;
+                        else {
+                            unsigned long long tq = A.trailer[q];
+                            before = tq > tr || (tq == tr && o < j);
+                        }
+                        if (before) { lo = mid + 1; lcp_lo = d; } else { hi = mid; lcp_hi = d; }
                     }
-                    rank += lo - S.vlo[o];
                     if (lo > S.vlo[o]) {
+                        atomicAdd(&A.A1[r], lo - S.vlo[o]);
                         uint32_t q = base + lo - 1;
-                        if (A.klen[q] == kl && cmp_slots(A.arena + (size_t)q * KS, kl, key, kl) == 0) shadow = true;
+                        if (A.klen[q] == kl && cmp_slots(A.arena + (size_t)q * KS, kl, key, kl) == 0) atomicOr(&A.A2[r], 1u);
                     }
                 }
-                A.rank[r] = (uint16_t)rank;
-                A.flags[r] = SF_VALID | (shadow ? SF_SHADOW : 0);
             }
             __syncthreads();
             for (uint32_t r = tid; r < S.n_rec; r += kScanThreads)
-                if (A.flags[r] & SF_VALID) A.order[A.rank[r]] = (uint16_t)r;
+                if (A.flags[r] & SF_VALID) {
+                    A.order[A.A1[r]] = (uint16_t)r;
+                    if (A.A2[r]) A.flags[r] = SF_VALID | SF_SHADOW;
+                }
             __syncthreads();
             // ---- visible records in iteration order ---------------------------------------------------------------------
             const uint32_t nv = S.n_valid;
@@ -698,7 +779,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                     in_prefix = kl >= pre_len;
                     for (uint32_t i = 0; in_prefix && i < pre_len; i++) in_prefix = key[i] == kpre[i];
                 }
-                int c = cmp_bytes(key, kl, endk, endl);
+                int c = cmp_bytes(key, kl, kend, endl); // reads at most min(kl, endl) <= KS bytes of the staged range end
                 bool in_range = rev ? (c > 0 || (c == 0 && end_incl)) : (c < 0 || (c == 0 && end_incl));
                 if (Q.has_upper && !rev) in_prefix = in_prefix && c < 0; // iterate_upper_bound (sortkey_count)
                 const uint8_t *val = A.in + A.voff[r];
@@ -796,7 +877,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                     bool hit_end = false;
                     if (nproc > 0 && end_incl) {
                         uint32_t r = A.vis[nproc - 1];
-                        hit_end = cmp_bytes(A.arena + (size_t)r * KS, A.klen[r], endk, endl) == 0;
+                        hit_end = cmp_bytes(A.arena + (size_t)r * KS, A.klen[r], kend, endl) == 0;
                     }
                     if (hit_end) { S.complete = 1; S.iter_valid = 1; S.done = 1; }
                     else if (Pp <= Ff && Pp < nvis_) { // limits ended the loop while the iterator stands on vis[Pp]
@@ -979,8 +1060,8 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
     // shared memory: one request per CTA; small scans want several CTAs per SM
     cudaFuncAttributes attr;
     PGS_CUDA(cudaFuncGetAttributes(&attr, k_scan));
-    P.warp_scratch = (P.KS + 48 + 15) & ~15u;
-    uint32_t fixed_dyn = 3 * ((P.KS + 8 + 15) & ~15u) + kScanWarps * P.warp_scratch;
+    P.warp_scratch = 0; // (the index-driven decode needs no per-warp key buffer)
+    uint32_t fixed_dyn = (4 + (uint32_t)runs.size()) * ((P.KS + 8 + 15) & ~15u) + kScanWarps * P.warp_scratch;
     uint32_t max_blk = 0, max_rec = 0;
     for (auto &r : runs) { max_blk = std::max(max_blk, r->info.max_block_size); max_rec = std::max(max_rec, r->info.max_block_records); }
     uint64_t one = (((uint64_t)max_blk + 15) & ~15ull) + 32 + (uint64_t)max_rec * (P.KS + kScanRecExtra);
