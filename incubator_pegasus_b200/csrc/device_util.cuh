@@ -85,6 +85,30 @@ PGS_DEV int cmp_bytes(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t 
     }
     return la < lb ? -1 : (la > lb ? 1 : 0);
 }
+// 4 bytes at an arbitrary address of any address space: two aligned 32-bit loads + funnel shift.  Touches at most 3
+// bytes before p and 3 bytes past p+3 inside the same aligned words (buffers carry >= 16 bytes of slack).
+PGS_DEV uint32_t ld_u32_any(const uint8_t *p)
+{
+    const uint32_t *w = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)((uintptr_t)p & 3) * 8;
+    return sh ? __funnelshift_r(w[0], w[1], sh) : w[0];
+}
+// cmp_bytes, four bytes per step (the byte loop pays one dependent load per byte when the strings live in global memory)
+PGS_DEV int cmp_bytes4(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb)
+{
+    const uint32_t m = la < lb ? la : lb;
+    for (uint32_t i = 0; i < m; i += 4) {
+        uint32_t x = ld_u32_any(a + i), y = ld_u32_any(b + i);
+        const uint32_t left = m - i;
+        if (left < 4) { const uint32_t msk = (1u << (8 * left)) - 1u; x &= msk; y &= msk; }
+        if (x != y) {
+            x = __byte_perm(x, 0, 0x0123); // first byte most significant
+            y = __byte_perm(y, 0, 0x0123);
+            return x < y ? -1 : 1;
+        }
+    }
+    return la < lb ? -1 : (la > lb ? 1 : 0);
+}
 PGS_DEV uint64_t bswap64(uint64_t x)
 {
     uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);

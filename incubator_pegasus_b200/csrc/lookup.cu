@@ -13,6 +13,8 @@
 //           reference's loop (stop key, first-exclusive, range_read_limiter counts and sizes, TTL /
 //           hash / sort-key filters) is evaluated with block-wide scans instead of a serial walk.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "device_util.cuh"
@@ -80,7 +82,7 @@ PGS_DEV uint32_t warp_index_bound(const RunDev &r, const uint8_t *key, uint32_t 
         uint32_t span = hi - lo;
         uint32_t piv = lo + (uint32_t)(((unsigned long long)span * (lane + 1)) / 33);
         uint32_t o = r.ikey_off[piv], l = r.ikey_off[piv + 1] - o;
-        int c = cmp_bytes(r.ikeys + o, l, key, klen);
+        int c = cmp_bytes4(r.ikeys + o, l, key, klen);
         bool before = upper ? c <= 0 : c < 0; // pivot block lies strictly before the answer
         uint32_t m = __ballot_sync(kFull, before);
         uint32_t cnt = __popc(m); // monotone: lanes 0..cnt-1 are true
@@ -92,7 +94,7 @@ PGS_DEV uint32_t warp_index_bound(const RunDev &r, const uint8_t *key, uint32_t 
     bool before = false;
     if (lo + lane < hi) {
         uint32_t o = r.ikey_off[lo + lane], l = r.ikey_off[lo + lane + 1] - o;
-        int c = cmp_bytes(r.ikeys + o, l, key, klen);
+        int c = cmp_bytes4(r.ikeys + o, l, key, klen);
         before = upper ? c <= 0 : c < 0;
     }
     return lo + __popc(__ballot_sync(kFull, before));
@@ -263,6 +265,7 @@ struct ScanParams {
     uint32_t resume_stride;
     const unsigned long long *crc_table;
     uint32_t *error;
+    unsigned long long *phase_cycles; // [16] or null (PGS_PHASE_TIMING=1)
 };
 
 struct ScanShared {
@@ -356,7 +359,7 @@ PGS_DEV bool dev_validate_filter(int32_t type, const uint8_t *pat, uint32_t pl, 
 enum : uint8_t { SF_VALID = 1, SF_SHADOW = 2 };
 enum : uint8_t { RS_NORMAL = 0, RS_EXPIRED = 1, RS_FILTERED = 2, RS_HASH_INVALID = 3 };
 
-__global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ ScanParams P)
+__global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant__ ScanParams P)
 {
     extern __shared__ __align__(128) uint8_t dyn[];
     __shared__ ScanShared S;
@@ -372,6 +375,8 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
     if (tid == 0) { mbar_init((uint64_t *)&S.mbar, 1); mbar_fence_init(); }
     __syncthreads();
     uint32_t phase = 0;
+    long long pt_last = P.phase_cycles ? clock64() : 0; // phase timing (diagnostics): thread 0 stamps phase boundaries
+#define SPT(i) do { if (P.phase_cycles && tid == 0) { long long t_ = clock64(); atomicAdd(&P.phase_cycles[i], (unsigned long long)(t_ - pt_last)); pt_last = t_; } } while (0)
 
     for (uint32_t rq = blockIdx.x; rq < P.n; rq += gridDim.x) {
         const ScanReqDev &Q = P.reqs[rq];
@@ -432,6 +437,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
             if (sl > KS) { if (rev) S.hi_incl = 1; else S.lo_incl = 0; }
         }
         __syncthreads();
+        SPT(0);
 
         // ================================ chunk loop ==========================================
         for (;;) {
@@ -496,6 +502,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                 }
             }
             __syncthreads();
+            SPT(1);
             if (S.done || S.error) break;
             const ScanArrays A = scan_carve(pool, S.in_bytes, S.n_rec, KS);
             // ---- stage + block table ----------------------------------------------------------------
@@ -553,6 +560,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
             }
             if (P.use_tma) { mbar_wait((uint64_t *)&S.mbar, phase); phase ^= 1; }
             __syncthreads();
+            SPT(2);
             if (tid == 0) {
                 int best = -1;
                 for (uint32_t j = 0; j < NR; j++) {
@@ -576,6 +584,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                 }
             }
             __syncthreads();
+            SPT(3);
 
             // ---- decode step 1: one THREAD per record parses its entry header; the entry's offset inside its block
             //      comes from the run's rec_off index, so no thread walks a block's entry chain -------------------------
@@ -622,6 +631,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                 }
             }
             __syncthreads();
+            SPT(4);
             if (S.error) break;
             // ---- decode step 2: HALF a warp per block rebuilds the keys, four key bytes per lane (see k_merge) ---------
             {
@@ -666,31 +676,27 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                 }
             }
             __syncthreads();
+            SPT(5);
             if (S.error) break;
 
-            // ---- validity window per run: lo (<|<=) key (<=) hi, plus the iterator's prefix ---------------------
+            // ---- validity window per run: lo (<|<=) key (<=) hi.  Records at or below the lower bound form a prefix of a
+            //      run's slice and records above the upper bound a suffix: counting them in parallel gives the window ------
+            if (tid < NR) { S.vlo[tid] = 0; S.vhi[tid] = 0; } // vhi counts the records above the bound first
+            __syncthreads();
+            for (uint32_t r = tid; r < S.n_rec; r += kScanThreads) {
+                uint32_t j = 0;
+                while (j + 1 < NR && r >= S.rec_base[j + 1]) j++;
+                const uint8_t *key = A.arena + (size_t)r * KS;
+                const uint32_t kl = A.klen[r];
+                bool below = false;
+                if (S.has_lo) { int c = cmp_slots(key, kl, klo, S.lo_len); below = S.lo_incl ? c < 0 : c <= 0; }
+                if (below) atomicAdd(&S.vlo[j], 1u);
+                else if (S.has_hi) { int c = cmp_slots(key, kl, khi, S.hi_len); if (S.hi_incl ? c > 0 : c >= 0) atomicAdd(&S.vhi[j], 1u); }
+            }
+            __syncthreads();
             if (tid < NR) {
-                uint32_t n = S.nrec[tid], base = S.rec_base[tid], vlo = 0, vhi = n;
-                if (S.has_lo) { // first index with key > lo (exclusive) or >= lo (inclusive)
-                    uint32_t lo = 0, hi = n;
-                    while (lo < hi) {
-                        uint32_t mid = (lo + hi) >> 1;
-                        int c = cmp_slots(A.arena + (size_t)(base + mid) * KS, A.klen[base + mid], klo, S.lo_len);
-                        if (S.lo_incl ? c < 0 : c <= 0) lo = mid + 1; else hi = mid;
-                    }
-                    vlo = lo;
-                }
-                if (S.has_hi) {
-                    uint32_t lo = 0, hi = n;
-                    while (lo < hi) {
-                        uint32_t mid = (lo + hi) >> 1;
-                        int c = cmp_slots(A.arena + (size_t)(base + mid) * KS, A.klen[base + mid], khi, S.hi_len);
-                        if (S.hi_incl ? c <= 0 : c < 0) lo = mid + 1; else hi = mid;
-                    }
-                    vhi = lo;
-                }
-                if (vhi < vlo) vhi = vlo;
-                S.vlo[tid] = vlo;
+                uint32_t vhi = S.nrec[tid] - S.vhi[tid];
+                if (vhi < S.vlo[tid]) vhi = S.vlo[tid];
                 S.vhi[tid] = vhi;
             }
             __syncthreads();
@@ -754,6 +760,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                     if (A.A2[r]) A.flags[r] = SF_VALID | SF_SHADOW;
                 }
             __syncthreads();
+            SPT(7);
             // ---- visible records in iteration order ---------------------------------------------------------------------
             const uint32_t nv = S.n_valid;
             auto at = [&](uint32_t p) -> uint32_t { return A.order[rev ? nv - 1 - p : p]; };
@@ -815,6 +822,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                 A.A3[v] = st == RS_NORMAL ? out_k + out_v : 0u;
             }
             __syncthreads();
+            SPT(8);
             // count / size prefixes over the visible list (in place: A2, A3 become exclusive prefixes)
             scan_chunked(nvis, A.A1, S.scan, [&](uint32_t v) -> uint32_t { return A.A2[v]; });
             for (uint32_t v = tid; v <= nvis; v += kScanThreads) A.A2[v] = A.A1[v];
@@ -834,6 +842,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                 if (!ok) atomicMin(&S.P, v);
             }
             __syncthreads();
+            SPT(9);
             const uint32_t Pp = S.P, Ff = S.F;
             const uint32_t nproc = min(Pp, Ff); // processed positions [0, nproc)
             // ---- emit ------------------------------------------------------------------------------------------------------
@@ -861,6 +870,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                 }
             }
             __syncthreads();
+            SPT(10);
             // ---- advance the loop state -----------------------------------------------------------------------------------------
             if (tid == 0) {
                 uint32_t nvis_ = S.n_vis;
@@ -908,6 +918,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
                 S.first_chunk = 0;
             }
             __syncthreads();
+            SPT(11);
             if (!S.done) {
                 // next chunk: forward: lower bound = this chunk's far bound (exclusive); cursors = first block whose
                 // last key > bound.  reverse: upper bound = far bound (inclusive), cursor = first block with last key >= bound
@@ -951,6 +962,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const __grid_constant__ S
             if (S.error) atomicMax(P.error, S.error);
         }
         __syncthreads();
+        SPT(12);
     }
 }
 
@@ -1067,6 +1079,7 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
     uint64_t one = (((uint64_t)max_blk + 15) & ~15ull) + 32 + (uint64_t)max_rec * (P.KS + kScanRecExtra);
     uint64_t want = std::max<uint64_t>(one * std::max<size_t>(1, runs.size()) + 4096, 48 * 1024);
     if (n == 1) want = std::max<uint64_t>(want, 160 * 1024);
+    if (const char *ev = getenv("PGS_SCAN_POOL_KB")) { if (atoi(ev) > 0) want = std::max<uint64_t>(want, (uint64_t)atoi(ev) * 1024); } // tuning knob
     uint64_t max_dyn = (uint64_t)e->max_smem_optin - attr.sharedSizeBytes - 256;
     uint64_t dyn = std::min<uint64_t>(max_dyn, fixed_dyn + want);
     if (dyn < fixed_dyn + one * std::max<size_t>(1, runs.size()) + 64) {
@@ -1094,10 +1107,10 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
     CK(cudaMallocAsync(&d_kvs, sizeof(pgs_kv) * (size_t)kv_stride * n + 16, st));
     CK(cudaMallocAsync(&d_resume, (size_t)P.resume_stride * n + 16, st));
     CK(cudaMallocAsync(&d_res, sizeof(pgs_scan_result) * n, st));
-    CK(cudaMallocAsync(&d_err, 4, st));
+    CK(cudaMallocAsync(&d_err, 256, st));
     CK(cudaMemcpyAsync(d_reqs, dev.data(), sizeof(ScanReqDev) * n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(d_err, 0, 4, st));
+    CK(cudaMemsetAsync(d_err, 0, 256, st));
     if (need_crc) {
         int dv = e->device & 15;
         if (!g_crc_dev_rd[dv]) {
@@ -1109,9 +1122,14 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
         P.crc_table = (const unsigned long long *)g_crc_dev_rd[dv];
     }
     P.reqs = d_reqs; P.blob = d_blob; P.results = d_res; P.kvs = d_kvs; P.arena = d_arena; P.resume = d_resume; P.error = d_err;
+    const char *pt_env = getenv("PGS_PHASE_TIMING"); // diagnostics: per-phase cycle totals of k_scan on stderr
+    const bool phase_timing = pt_env && pt_env[0] == '1';
+    P.phase_cycles = phase_timing ? (unsigned long long *)(d_err + 16) : nullptr;
     CK(cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     CK(cudaFuncSetAttribute(k_scan, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    uint32_t per_sm = (uint32_t)std::max<uint64_t>(1, (228ull * 1024) / (dyn + attr.sharedSizeBytes + 1024));
+    int occ = 0; // resident CTAs per SM for this dynamic shared-memory size (registers count too)
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan, (int)kScanThreads, (size_t)dyn));
+    uint32_t per_sm = (uint32_t)std::max(1, occ);
     uint32_t grid = std::min<uint32_t>(n, per_sm * e->sm_count);
     if (P.rr.n == 0) { // empty DB: every iterator is invalid from the start
         std::vector<pgs_scan_result> z(n);
@@ -1127,6 +1145,17 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
     k_scan<<<grid, kScanThreads, dyn, st>>>(P);
     cudaEventRecord(e->ev_b, st);
     e->launches++;
+    if (phase_timing) {
+        unsigned long long h[16] = {0};
+        cudaMemcpyAsync(h, d_err + 16, sizeof h, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        static const char *names[13] = {"init", "choose", "stage", "farbound", "decode1", "decode2", "window", "rank", "visible", "loop", "emit", "advance", "result"};
+        unsigned long long tot = 0;
+        for (int i = 0; i < 13; i++) tot += h[i];
+        fprintf(stderr, "[k_scan phases] requests=%u grid=%u dyn=%llu", n, grid, (unsigned long long)dyn);
+        for (int i = 0; i < 13; i++) fprintf(stderr, " %s=%.1f%%", names[i], tot ? 100.0 * (double)h[i] / (double)tot : 0.0);
+        fprintf(stderr, " cycles/request=%.0f\n", n ? (double)tot / n : 0.0);
+    }
     uint32_t herr = 0;
     if (n == 1) {
         CK(cudaMemcpyAsync(results, d_res, sizeof(pgs_scan_result), cudaMemcpyDeviceToHost, st));
