@@ -116,13 +116,13 @@ __global__ void __launch_bounds__(256) k_plan(const __grid_constant__ MergeParam
             uint32_t mid = (lo + hi) >> 1;
             const uint8_t *kp = rj.ikeys + rj.ikey_off[mid];
             uint32_t kl = rj.ikey_off[mid + 1] - rj.ikey_off[mid];
-            if (cmp_bytes(kp, kl, U, ulen) <= 0) lo = mid + 1; else hi = mid;
+            if (cmp_bytes4(kp, kl, U, ulen) <= 0) lo = mid + 1; else hi = mid;
         }
         uint32_t ub = lo, lb = lo;
         while (lb > 0) {
             const uint8_t *kp = rj.ikeys + rj.ikey_off[lb - 1];
             uint32_t kl = rj.ikey_off[lb] - rj.ikey_off[lb - 1];
-            if (cmp_bytes(kp, kl, U, ulen) != 0) break;
+            if (cmp_bytes4(kp, kl, U, ulen) != 0) break;
             lb--;
         }
         pos[j] = ub;
