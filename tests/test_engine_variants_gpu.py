@@ -1,0 +1,64 @@
+"""GPU parity under the non-default engine settings: two 512-thread CTAs per SM, the plain-load staging path
+(PGS_ENGINE_NO_TMA) and the early block load switched off.  Same oracle comparison as test_compaction_gpu."""
+import random
+
+import pytest
+
+from incubator_pegasus_b200 import synth
+from rrdb_harness import Backend, same_response
+from test_compaction_gpu import run_case
+
+NOW = synth.NOW
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=[dict(ctas_per_sm=2), dict(flags=1), dict(ctas_per_sm=2, flags=1)], ids=["2cta", "no_tma", "2cta_no_tma"])
+def variant_engine(pgs, request):
+    eng = pgs.Engine(**request.param)
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("bottommost", [True, False])
+def test_compaction_variants(pgs, oracle, variant_engine, bottommost):
+    runs = synth.compaction_runs(k=4, n_per_run=30_000)
+    run_case(pgs, oracle, variant_engine, runs, bottommost=bottommost, default_ttl=3600 if bottommost else 0)
+
+
+def test_compaction_without_early_load(pgs, oracle, engine, monkeypatch):
+    monkeypatch.setenv("PGS_EARLY_TMA", "0")  # read per pgs_compact call
+    runs = synth.compaction_runs(k=3, n_per_run=40_000)
+    run_case(pgs, oracle, engine, runs, bottommost=True)
+
+
+def test_reads_variants(variant_engine):
+    """gets, multi_gets (forward / reverse / limited), sortkey_count and scans through the rrdb surface on the variant engine"""
+    g, o = Backend("gpu", variant_engine, opts={"l0_compaction_trigger": 100}), Backend("oracle", opts={"l0_compaction_trigger": 100})
+    rnd = random.Random(5)
+    try:
+        for round_ in range(4):  # 4 overlapping L0 runs
+            for be in (g, o):
+                be.decree = round_ * 1000
+            for hk in (b"h1", b"h2", b"h3"):
+                kvs = {b"s%04d" % rnd.randrange(300): bytes(rnd.getrandbits(8) for _ in range(rnd.choice([5, 120, 700]))) for _ in range(80)}
+                ets = rnd.choice([0, NOW + 100, NOW - 5])
+                for be in (g, o):
+                    be.multi_put(hk, kvs, expire_ts=ets)
+            for be in (g, o):
+                be.multi_remove(b"h2", [b"s%04d" % (round_ * 5 + j) for j in range(4)])
+                be.flush(NOW)
+        for hk in (b"h1", b"h2", b"h3", b"none"):
+            for sk in [b"s0000", b"s0007", b"s0150", b"s0299", b"nope"]:
+                ok, d = same_response(g.get(hk, sk, now=NOW), o.get(hk, sk, now=NOW))
+                assert ok, (hk, sk, d)
+            for kw in [dict(), dict(reverse=True), dict(max_kv_size=5000), dict(max_kv_count=9, reverse=True), dict(no_value=True),
+                       dict(start=b"s0050", stop=b"s0200", stop_inclusive=True)]:
+                ok, d = same_response(g.multi_get(hk, now=NOW, **kw), o.multi_get(hk, now=NOW, **kw))
+                assert ok, (hk, kw, d[0]["error"], d[1]["error"], len(d[0]["kvs"]), len(d[1]["kvs"]))
+            assert same_response(g.sortkey_count(hk, now=NOW), o.sortkey_count(hk, now=NOW))[0]
+            (kg, _), (ko, _) = g.scan_all(hk, batch_size=37, now=NOW), o.scan_all(hk, batch_size=37, now=NOW)
+            assert kg == ko
+    finally:
+        g.close()
+        o.close()

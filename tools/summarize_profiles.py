@@ -50,7 +50,7 @@ with open(os.path.join(P, f"launches_{TAG}_summary.txt"), "w") as f:
 
 # 2. full captures
 caps = {}
-for rep, label in (("final_k_merge.ncu-rep", "k_merge_full_size"), ("final_reads.ncu-rep", "reads_full_size")):
+for rep, label in (("final_k_merge.ncu-rep", "k_merge_full_size"), ("final_reads.ncu-rep", "reads_full_size"), ("final_scan.ncu-rep", "reads_full_size")):
     pth = os.path.join(G, rep)
     if os.path.exists(pth):
         for name, d in raw(pth).items(): caps[f"{label}:{name}"] = d
