@@ -405,14 +405,20 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
             for (uint32_t i = tid; i < 256; i += kScanThreads) S.crc[i] = P.crc_table[i];
         // initial cursors (one warp per run, 33-ary index search): forward: first block whose last key >= start;
         // reverse: first block whose last key >= stop.  want_end: first block whose last key >= the range end.
-        for (uint32_t j = warp; j < NR; j += kScanWarps) {
+        // (the two searches of a run are independent chains of global round trips: different warps take them)
+        for (uint32_t task = warp; task < 2 * NR; task += kScanWarps) {
+            const uint32_t j = task >> 1;
             const RunDev &r = P.rr.runs[j];
-            const uint8_t *sk = rev ? stop : start;
-            uint32_t sl = rev ? Q.stop_len : Q.start_len;
-            uint32_t b = warp_index_bound(r, sk, sl, lane, false);
-            if (rev && b >= r.nb) b = r.nb ? r.nb - 1 : 0;
-            uint32_t we = warp_index_bound(r, endk, endl, lane, false);
-            if (lane == 0) { S.cur[j] = b; S.want_end[j] = we; }
+            if (task & 1) {
+                uint32_t we = warp_index_bound(r, endk, endl, lane, false);
+                if (lane == 0) S.want_end[j] = we;
+            } else {
+                const uint8_t *sk = rev ? stop : start;
+                uint32_t sl = rev ? Q.stop_len : Q.start_len;
+                uint32_t b = warp_index_bound(r, sk, sl, lane, false);
+                if (rev && b >= r.nb) b = r.nb ? r.nb - 1 : 0;
+                if (lane == 0) S.cur[j] = b;
+            }
         }
         // first chunk bound in iteration direction = the seek key
         for (uint32_t i = tid; i < KS + 8; i += kScanThreads) {
@@ -471,11 +477,34 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
                         uint32_t l = rev ? c + 1 - mm : c, h = l + mm;
                         return (r.blk_off[h] - r.blk_off[l]) + 32 + (unsigned long long)(r.blk_rec[h] - r.blk_rec[l]) * (KS + kScanRecExtra);
                     };
-                    m = maxm;
-                    if (maxm > 1 && weight(maxm) > budget) { // rare: largest m in [1, maxm) that fits (cumulative arrays)
-                        uint32_t lo = 1, hi = maxm;
-                        while (lo + 1 < hi) { uint32_t mid = (lo + hi) >> 1; if (weight(mid) <= budget) lo = mid; else hi = mid; }
-                        m = lo;
+                    // largest m in [1, maxm] whose blocks and records fit the budget (cumulative arrays).  The weights of the
+                    // first eight candidates come from loads issued together (one round trip); only a run that may take
+                    // more than eight blocks continues with a binary search.
+                    constexpr uint32_t kProbe = 8;
+                    const uint32_t np = maxm < kProbe ? maxm : kProbe;
+                    const uint32_t b0 = rev ? c + 1 : c;
+                    unsigned long long o[kProbe + 1];
+                    uint32_t rc[kProbe + 1];
+#pragma unroll
+                    for (uint32_t x = 0; x <= kProbe; x++) {
+                        const uint32_t idx = x <= np ? (rev ? b0 - x : b0 + x) : b0;
+                        o[x] = r.blk_off[idx];
+                        rc[x] = r.blk_rec[idx];
+                    }
+                    m = 1;
+#pragma unroll
+                    for (uint32_t x = 2; x <= kProbe; x++) {
+                        const unsigned long long wb = rev ? o[0] - o[x] : o[x] - o[0];
+                        const uint32_t wr = rev ? rc[0] - rc[x] : rc[x] - rc[0];
+                        if (x <= np && wb + 32 + (unsigned long long)wr * (KS + kScanRecExtra) <= budget) m = x; // weights grow with x
+                    }
+                    if (m == kProbe && maxm > kProbe) {
+                        if (weight(maxm) <= budget) m = maxm;
+                        else {
+                            uint32_t lo = kProbe, hi = maxm;
+                            while (lo + 1 < hi) { uint32_t mid = (lo + hi) >> 1; if (weight(mid) <= budget) lo = mid; else hi = mid; }
+                            m = lo;
+                        }
                     }
                     lo_b = rev ? c + 1 - m : c;
                     bytes_j = (uint32_t)(r.blk_off[lo_b + m] - r.blk_off[lo_b]);
@@ -936,7 +965,22 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
                         if (b >= r.nb) b = r.nb ? r.nb - 1 : 0xFFFFFFFFu;
                         if (!r.nb) b = 0xFFFFFFFFu;
                     } else {
-                        b = warp_index_bound(r, klo, S.lo_len, lane, true);
+                        // forward: the bound is the smallest "last key of the last loaded block" over the runs, so the first
+                        // block whose last key is > bound lies at or right behind this chunk's loaded blocks; their last keys
+                        // are decoded in the arena -- no index search in global memory
+                        const uint32_t m = S.nblk[j];
+                        uint32_t cnt = 0;
+                        for (uint32_t t0 = 0; t0 < m; t0 += 32) {
+                            const uint32_t t = t0 + lane;
+                            bool le = false;
+                            if (t < m) {
+                                const uint32_t tt = S.blk_base[j] + t, nrec = S.tb_nrec[tt];
+                                const uint32_t rl = S.tb_rec[tt] + nrec - 1;
+                                le = nrec == 0 || cmp_slots(A.arena + (size_t)rl * KS, A.klen[rl], klo, S.lo_len) <= 0;
+                            }
+                            cnt += __popc(__ballot_sync(kFull, le));
+                        }
+                        b = S.cur[j] + cnt; // a run without loaded blocks keeps its (exhausted) cursor
                     }
                     if (lane == 0) S.cur[j] = b;
                 }
