@@ -1405,7 +1405,9 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     };
     outr->pool_stream = st;
 #define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr); } } while (0)
-    CK(cudaMallocAsync(&outr->d_data, outr->data_cap, st));
+    outr->eng = e;
+    { uint64_t cap = 0; outr->d_data = outr->data_cap >= (64ull << 20) ? e->take_data(outr->data_cap, &cap) : nullptr; if (outr->d_data) outr->data_cap = cap; }
+    if (!outr->d_data) CK(cudaMallocAsync(&outr->d_data, outr->data_cap, st));
     CK(cudaMallocAsync(&outr->d_blk_off, sizeof(uint64_t) * (blk_cap + 1), st));
     CK(cudaMallocAsync(&outr->d_blk_size, sizeof(uint32_t) * (blk_cap + 1), st));
     CK(cudaMallocAsync(&outr->d_blk_rec, sizeof(uint32_t) * (blk_cap + 1), st));

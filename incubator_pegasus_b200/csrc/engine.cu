@@ -4,6 +4,7 @@
 // IngestExternalFile (rocksdb_wrapper.cpp:248-270) as far as "a sorted run appears in the DB".
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 
 #include "device_util.cuh"
@@ -27,10 +28,51 @@ int32_t cuda_fail(cudaError_t e, const char *what)
     return PGS_IO_ERROR; // CUDA faults map to kIOError
 }
 
+// engines that are still open: a run that outlives its engine (caller closed the engine first) must not touch it
+static std::mutex g_live_mu;
+static std::vector<Engine *> g_live;
+static bool engine_alive(Engine *e)
+{
+    std::lock_guard<std::mutex> g(g_live_mu);
+    return std::find(g_live.begin(), g_live.end(), e) != g_live.end();
+}
+
+constexpr uint64_t kSpareMin = 64ull << 20; // only buffers this large are worth keeping
+constexpr size_t kSpareMax = 8;
+constexpr uint64_t kSpareBytesMax = 24ull << 30;
+
+uint8_t *Engine::take_data(uint64_t need, uint64_t *cap)
+{
+    std::lock_guard<std::mutex> g(spare_mu);
+    int best = -1;
+    for (size_t i = 0; i < spares.size(); i++)
+        if (spares[i].cap >= need && spares[i].cap <= 2 * need + kSpareMin && (best < 0 || spares[i].cap < spares[best].cap)) best = (int)i;
+    if (best < 0) return nullptr;
+    uint8_t *p = spares[best].p;
+    *cap = spares[best].cap;
+    spares.erase(spares.begin() + best);
+    return p;
+}
+void Engine::give_data(uint8_t *p, uint64_t cap)
+{
+    std::lock_guard<std::mutex> g(spare_mu);
+    spares.push_back(Spare{p, cap});
+    uint64_t total = 0;
+    for (auto &s : spares) total += s.cap;
+    while (spares.size() > kSpareMax || total > kSpareBytesMax) { // give the smallest ones back to the pool
+        size_t m = 0;
+        for (size_t i = 1; i < spares.size(); i++) if (spares[i].cap < spares[m].cap) m = i;
+        total -= spares[m].cap;
+        cudaFreeAsync(spares[m].p, stream);
+        spares.erase(spares.begin() + m);
+    }
+}
+
 Run::~Run()
 {
     if (pool_stream) { // stream-ordered pool: the bytes go back to the pool without a device sync
-        cudaFreeAsync(d_data, pool_stream);
+        if (eng && d_data && data_cap >= kSpareMin && engine_alive(eng)) eng->give_data(d_data, data_cap);
+        else cudaFreeAsync(d_data, pool_stream);
         cudaFreeAsync(d_blk_off, pool_stream);
         cudaFreeAsync(d_blk_size, pool_stream);
         cudaFreeAsync(d_blk_rec, pool_stream);
@@ -49,6 +91,12 @@ Run::~Run()
 }
 Engine::~Engine()
 {
+    {
+        std::lock_guard<std::mutex> g(g_live_mu);
+        g_live.erase(std::remove(g_live.begin(), g_live.end(), this), g_live.end());
+    }
+    for (auto &s : spares) cudaFreeAsync(s.p, stream);
+    spares.clear();
     if (h_pinned) cudaFreeHost(h_pinned);
     if (ev_a) cudaEventDestroy(ev_a);
     if (ev_b) cudaEventDestroy(ev_b);
@@ -287,6 +335,10 @@ int32_t pgs_engine_open(const pgs_engine_config *cfg, pgs_engine **out)
         delete h;
         return cuda_fail(err, "engine open");
     }
+    {
+        std::lock_guard<std::mutex> g(g_live_mu);
+        g_live.push_back(&h->e);
+    }
     *out = h;
     return PGS_OK;
 }
@@ -357,7 +409,9 @@ int32_t pgs_run_upload(pgs_partition *ph, int32_t level, const uint8_t *data, ui
     r->data_cap = end + 256;
     cudaStream_t st = e->stream;
     r->pool_stream = st; // stream-ordered pool: repeated flush / compaction cycles reuse the same HBM without driver calls
-    PGS_CUDA(cudaMallocAsync(&r->d_data, r->data_cap, st));
+    r->eng = e;
+    if (r->data_cap >= kSpareMin) { uint64_t cap = 0; r->d_data = e->take_data(r->data_cap, &cap); if (r->d_data) r->data_cap = cap; }
+    if (!r->d_data) PGS_CUDA(cudaMallocAsync(&r->d_data, r->data_cap, st));
     PGS_CUDA(cudaMallocAsync(&r->d_blk_off, sizeof(uint64_t) * (n_blocks + 1), st));
     PGS_CUDA(cudaMallocAsync(&r->d_blk_size, sizeof(uint32_t) * n_blocks, st));
     PGS_CUDA(cudaMemsetAsync(r->d_data + (data_bytes < end ? data_bytes : end), 0, r->data_cap - (data_bytes < end ? data_bytes : end), st));

@@ -41,6 +41,7 @@ struct Run {
     uint32_t *d_rec_off = nullptr;
     uint64_t data_cap = 0;
     cudaStream_t pool_stream = nullptr; // set when the buffers came from cudaMallocAsync on that stream
+    struct Engine *eng = nullptr;       // set with pool_stream: large data buffers go back to the engine's spare list
     RunDev dev() const
     {
         return RunDev{d_data, d_blk_off, d_blk_size, d_blk_rec, d_ikey_off, d_ikeys, d_rec_off, info.n_blocks, info.max_ukey_len};
@@ -64,6 +65,14 @@ struct Engine {
     void *h_pinned = nullptr;
     size_t h_pinned_cap = 0;
     void *pinned(size_t bytes);
+    // Spare list of large block buffers.  A compaction frees a few ~GB buffers and asks for one of a different size; what
+    // the stream-ordered pool does with that depends on its placement choices, and growing the pool costs ~100 ms.
+    // Buffers of dropped runs are therefore kept here (all uses are ordered on `stream`) and handed to the next taker.
+    struct Spare { uint8_t *p; uint64_t cap; };
+    std::mutex spare_mu;
+    std::vector<Spare> spares;
+    uint8_t *take_data(uint64_t need, uint64_t *cap); // nullptr when nothing suitable is kept
+    void give_data(uint8_t *p, uint64_t cap);
     ~Engine();
 };
 
