@@ -448,7 +448,10 @@ PGS_DEV void fetch_next_tile(const MergeParams &P, TileShared &S, uint32_t lane)
     }
 }
 
-template <uint32_t NT>
+// EXP = true compiles the variants that are still being evaluated (PGS_EXPERIMENTAL=1 selects that instantiation;
+// the default instantiation contains none of their code): packed per-record metadata for the key rebuild, varints
+// of the entry heads packed once per survivor, sample-then-refine rank searches.
+template <uint32_t NT, bool EXP>
 __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParams P)
 {
     constexpr uint32_t NW = NT / 32;
@@ -600,8 +603,12 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                     if (!c || klen < 8 || klen - 8 > KS || end > limit || (i == 0 && shared != 0) || (i + 1 == cnt && end != limit)) {
                         err = PGS_CORRUPTION;
                     } else {
-                        A.rank[r] = (uint16_t)shared;      // scratch until the rank phase
-                        A.order[r] = (uint16_t)non_shared; // scratch until the scatter phase
+                        if constexpr (EXP) { // one word per record for step 2: shared | non_shared << 16
+                            A.R[r] = shared | (non_shared << 16);
+                        } else {
+                            A.rank[r] = (uint16_t)shared;      // scratch until the rank phase
+                            A.order[r] = (uint16_t)non_shared; // scratch until the scatter phase
+                        }
                         A.koff[r] = S.tb_off[t] + p + h;
                         A.klen[r] = (uint16_t)(klen - 8);
                         A.voff[r] = S.tb_off[t] + p + h + non_shared;
@@ -612,6 +619,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                         } else {               // part of it is shared with the previous key: rebuilt in step 2
                             A.trailer[r] = 0;
                             A.flags[r] = 1;
+                            if constexpr (EXP) A.koff[r] |= 0x80000000u;
                         }
                     }
                 }
@@ -638,11 +646,19 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                     const uint32_t p0 = pass * 64 + 4 * hl;
                     uint32_t cur = 0, prev_klen = 0; // the four running bytes, little endian
                     uint32_t sh = 0, ns = 0, ulen = 0, ko = 0, fl = 0;
-                    if (nrec) { sh = A.rank[rec0]; ns = A.order[rec0]; ulen = A.klen[rec0]; ko = A.koff[rec0]; fl = A.flags[rec0]; }
+                    if constexpr (EXP) { // two packed words + the key length instead of five arrays
+                        if (nrec) { const uint32_t a = A.R[rec0], b = A.koff[rec0]; sh = a & 0xffffu; ns = a >> 16; ko = b & 0x7fffffffu; fl = b >> 31; ulen = A.klen[rec0]; }
+                    } else {
+                        if (nrec) { sh = A.rank[rec0]; ns = A.order[rec0]; ulen = A.klen[rec0]; ko = A.koff[rec0]; fl = A.flags[rec0]; }
+                    }
                     for (uint32_t i = 0; i < nrec; i++) {
                         const uint32_t r = rec0 + i;
                         const uint32_t c_sh = sh, c_ns = ns, c_ulen = ulen, c_ko = ko, c_fl = fl;
-                        if (i + 1 < nrec) { sh = A.rank[r + 1]; ns = A.order[r + 1]; ulen = A.klen[r + 1]; ko = A.koff[r + 1]; fl = A.flags[r + 1]; } // next entry's metadata in flight
+                        if constexpr (EXP) {
+                            if (i + 1 < nrec) { const uint32_t a = A.R[r + 1], b = A.koff[r + 1]; sh = a & 0xffffu; ns = a >> 16; ko = b & 0x7fffffffu; fl = b >> 31; ulen = A.klen[r + 1]; }
+                        } else {
+                            if (i + 1 < nrec) { sh = A.rank[r + 1]; ns = A.order[r + 1]; ulen = A.klen[r + 1]; ko = A.koff[r + 1]; fl = A.flags[r + 1]; } // next entry's metadata in flight
+                        }
                         if (c_sh > prev_klen) { if (hl == 0) atomicMax(&S.error, (uint32_t)PGS_CORRUPTION); break; } // a prefix longer than the previous key
                         prev_klen = c_ulen + 8;
                         const uint32_t a = max(c_sh, p0), b = min(c_sh + c_ns, p0 + 4);
@@ -724,6 +740,64 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
         if (tile_ok && P.k > 1) {
             const uint32_t k = P.k, km1 = k - 1;
             uint32_t ntask = 0;
+            if constexpr (EXP) {
+                // sample-then-refine: every SS-th record of a run (and its last one) searches the whole window of the other
+                // run; the records in between only search between the positions their two neighbouring samples found
+                constexpr uint32_t SS = 8;
+                auto search = [&](uint32_t j, uint32_t o, uint32_t r, uint32_t lo, uint32_t hi) {
+                    const uint8_t *key = A.arena + (size_t)r * KS;
+                    const uint32_t kl = A.klen[r];
+                    const unsigned long long tr = A.trailer[r];
+                    const uint32_t base = S.rec_base[o];
+                    uint32_t lcp_lo = 0, lcp_hi = 0;
+                    while (lo < hi) { // first position whose internal key is not before ours
+                        uint32_t mid = (lo + hi) >> 1, q = base + mid, d;
+                        int c = cmp_slots_from(A.arena + (size_t)q * KS, A.klen[q], key, kl, min(lcp_lo, lcp_hi), &d);
+                        bool before;
+                        if (c != 0) before = c < 0;
+                        else {
+                            unsigned long long tq = A.trailer[q];
+                            before = tq > tr || (tq == tr && o < j);
+                        }
+                        if (before) { lo = mid + 1; lcp_lo = d; } else { hi = mid; lcp_hi = d; }
+                    }
+                    const uint32_t cnt = lo - S.vlo[o];
+                    A.pos[(size_t)r * km1 + (o - 1)] = (uint16_t)cnt;
+                    if (cnt) {
+                        atomicAdd(&A.R[r], cnt);
+                        uint32_t q = base + lo - 1;
+                        if (A.klen[q] == kl && cmp_slots(A.arena + (size_t)q * KS, kl, key, kl) == 0) atomicOr(&A.E[r], 1u);
+                    }
+                };
+                auto nsamp = [&](uint32_t j) -> uint32_t { const uint32_t nv = S.vhi[j] - S.vlo[j]; return nv ? (nv - 1 + SS - 1) / SS + 1 : 0u; };
+                // pass A: the samples
+                for (uint32_t j = 0; j < k; j++) ntask += nsamp(j) * (km1 - j);
+                for (uint32_t id = tid; id < ntask; id += NT) {
+                    uint32_t j = 0, local = id;
+                    while (local >= nsamp(j) * (km1 - j)) { local -= nsamp(j) * (km1 - j); j++; }
+                    const uint32_t nt = km1 - j, si = local / nt, o = j + 1 + (local - si * nt);
+                    const uint32_t nv = S.vhi[j] - S.vlo[j];
+                    const uint32_t rel = min(si * SS, nv - 1);
+                    if (si > 0 && rel == (si - 1) * SS) continue; // the last sample coincides with the one before it
+                    search(j, o, S.rec_base[j] + S.vlo[j] + rel, S.vlo[o], S.vhi[o]);
+                }
+                __syncthreads();
+                // pass B: everything in between
+                ntask = 0;
+                for (uint32_t j = 0; j < k; j++) ntask += S.nrec[j] * (km1 - j);
+                for (uint32_t id = tid; id < ntask; id += NT) {
+                    uint32_t j = 0, local = id;
+                    while (local >= S.nrec[j] * (km1 - j)) { local -= S.nrec[j] * (km1 - j); j++; }
+                    const uint32_t nt = km1 - j, ri = local / nt;
+                    const uint32_t o = j + 1 + (local - ri * nt), r = S.rec_base[j] + ri;
+                    if (!(A.flags[r] & F_VALID)) continue;
+                    const uint32_t nv = S.vhi[j] - S.vlo[j], rel = ri - S.vlo[j];
+                    if (rel % SS == 0 || rel + 1 == nv) continue; // a sample: done in pass A
+                    const uint32_t s0 = rel - rel % SS, s1 = min(s0 + SS, nv - 1);
+                    const uint32_t rb = S.rec_base[j] + S.vlo[j];
+                    search(j, o, r, S.vlo[o] + A.pos[(size_t)(rb + s0) * km1 + (o - 1)], S.vlo[o] + A.pos[(size_t)(rb + s1) * km1 + (o - 1)]);
+                }
+            } else {
             for (uint32_t j = 0; j < k; j++) ntask += S.nrec[j] * (km1 - j);
             for (uint32_t id = tid; id < ntask; id += NT) {
                 uint32_t j = 0, local = id;
@@ -754,6 +828,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                     uint32_t q = base + lo - 1;
                     if (A.klen[q] == kl && cmp_slots(A.arena + (size_t)q * KS, kl, key, kl) == 0) atomicOr(&A.E[r], 1u);
                 }
+            }
             }
             __syncthreads();
             PT(13);
@@ -1024,6 +1099,16 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                 mn_seq = seq < mn_seq ? seq : mn_seq;
                 mx_seq = seq > mx_seq ? seq : mx_seq;
                 max_chunks = max(max_chunks, ((vl >> 4) + 3) >> 1); // pairs of 16-byte chunks
+                if constexpr (EXP) { // the head's three varints, packed once here instead of by every lane of the head writers
+                    const uint32_t shared = A.shr[p];
+                    uint32_t l1, l2, l3;
+                    unsigned long long hv = varint_pack(shared, l1);
+                    hv |= varint_pack(kl - shared + 8, l2) << (8 * l1);
+                    hv |= varint_pack(vl, l3) << (8 * (l1 + l2));
+                    const uint32_t h = l1 + l2 + l3; // l1 + l2 <= 6: the shifts above stay inside 64 bits whenever h <= 8
+                    A.koff[p] = (uint32_t)hv;
+                    A.order[p] = (uint16_t)(h <= 4 ? h : 0); // 0: the head writers pack it themselves
+                }
             }
             s_outb = __reduce_add_sync(kFull, s_outb); s_otomb = __reduce_add_sync(kFull, s_otomb);
             s_okey = __reduce_add_sync(kFull, s_okey); s_oval = __reduce_add_sync(kFull, s_oval);
@@ -1146,7 +1231,12 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                 uint32_t l1, l2, l3;
                 unsigned long long hv = varint_pack(shared, l1);
                 const unsigned long long hv2 = varint_pack(kd + 8, l2), hv3 = varint_pack(vl, l3);
-                const uint32_t h = l1 + l2 + l3;
+                uint32_t h = l1 + l2 + l3;
+                bool packed = false;
+                if constexpr (EXP) { // packed by the write-prep pass when it fits 4 bytes (the compiler drops the code above then)
+                    const uint32_t hp = A.order[p];
+                    if (hp) { h = hp; hv = A.koff[p]; packed = true; }
+                }
                 if (ql == 0) P.out_rec_off[S.base_recs + p] = doff - S.ob_off[A.blkid[p]]; // entry offset inside its block
                 uint8_t *dst = out + doff;
                 if (h > 8) { // lengths this large do not fit the packed register: one lane writes the head serially
@@ -1160,7 +1250,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                     }
                     continue;
                 }
-                hv |= (hv2 << (8 * l1)) | (hv3 << (8 * (l1 + l2)));
+                if (!packed) hv |= (hv2 << (8 * l1)) | (hv3 << (8 * (l1 + l2)));
                 const uint32_t lead4 = doff & 3; // the tile's output base is 16-byte aligned
                 const uint32_t nwords = (lead4 + hs + 3) >> 2;
                 const int32_t kbase = (int32_t)(r * KS + shared) - (int32_t)h; // arena byte offset of head byte 0, were the key delta to start at byte h
@@ -1352,7 +1442,9 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
 
     // ctas_per_sm: 2 -> two 512-thread CTAs per SM (default); 1 -> one 1024-thread CTA per SM with tiles twice as large
     const bool big = e->cfg.ctas_per_sm == 1;
-    auto kern = big ? k_merge<1024> : k_merge<512>;
+    const char *exp_env = getenv("PGS_EXPERIMENTAL");
+    const bool exp = exp_env && exp_env[0] == '1';
+    auto kern = big ? (exp ? k_merge<1024, true> : k_merge<1024, false>) : (exp ? k_merge<512, true> : k_merge<512, false>);
     const uint32_t nthreads = big ? 1024 : 512;
     cudaFuncAttributes attr;
     PGS_CUDA(cudaFuncGetAttributes(&attr, kern));

@@ -6,7 +6,7 @@ rows=list(csv.reader(open('/tmp/raw.csv'))); d=dict(zip(rows[0],rows[2]))
 for k in ['gpu__time_duration.sum','smsp__inst_executed.sum','smsp__issue_active.avg.pct_of_peak_sustained_active','dram__bytes_read.sum','dram__bytes_write.sum','smsp__thread_inst_executed_per_inst_executed.ratio','smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio','smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio','smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio','smsp__average_warps_issue_stalled_wait_per_issue_active.ratio','smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio','smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','sm__warps_active.avg.pct_of_peak_sustained_active']:
     print(k, d.get(k))
 lines=open('/tmp/merge_sass.txt').read().split('\n')
-start=[i for i,l in enumerate(lines) if (l.startswith('_ZN3pgs7k_mergeILj1024') and l.rstrip().endswith(':'))][0]
+start=[i for i,l in enumerate(lines) if (l.startswith('_ZN3pgs7k_mergeILj1024ELb0') and l.rstrip().endswith(':'))][0]
 end=len(lines)
 for i in range(start+1,len(lines)):
     if lines[i].startswith('//--------------------- .text.'): end=i;break
