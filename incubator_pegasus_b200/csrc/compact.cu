@@ -88,6 +88,7 @@ struct MergeParams {
     uint32_t out_blk_cap, out_ikey_cap;
     MergeStats *stats;
     unsigned long long *phase_cycles; // [16] or null
+    uint32_t exp; // PGS_EXPERIMENTAL bit mask (EXP instantiation only): 1 base items, 2 sample-then-refine rank, 4 staged heads
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -740,7 +741,10 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
         if (tile_ok && P.k > 1) {
             const uint32_t k = P.k, km1 = k - 1;
             uint32_t ntask = 0;
+            bool sampled = false;
             if constexpr (EXP) {
+              if (P.exp & 2) {
+                sampled = true;
                 // sample-then-refine: every SS-th record of a run (and its last one) searches the whole window of the other
                 // run; the records in between only search between the positions their two neighbouring samples found
                 constexpr uint32_t SS = 8;
@@ -797,7 +801,9 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                     const uint32_t rb = S.rec_base[j] + S.vlo[j];
                     search(j, o, r, S.vlo[o] + A.pos[(size_t)(rb + s0) * km1 + (o - 1)], S.vlo[o] + A.pos[(size_t)(rb + s1) * km1 + (o - 1)]);
                 }
-            } else {
+              }
+            }
+            if (!sampled) {
             for (uint32_t j = 0; j < k; j++) ntask += S.nrec[j] * (km1 - j);
             for (uint32_t id = tid; id < ntask; id += NT) {
                 uint32_t j = 0, local = id;
@@ -1443,7 +1449,9 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     // ctas_per_sm: 2 -> two 512-thread CTAs per SM (default); 1 -> one 1024-thread CTA per SM with tiles twice as large
     const bool big = e->cfg.ctas_per_sm == 1;
     const char *exp_env = getenv("PGS_EXPERIMENTAL");
-    const bool exp = exp_env && exp_env[0] == '1';
+    const uint32_t exp_bits = exp_env ? (uint32_t)atoi(exp_env) : 0;
+    const bool exp = exp_bits != 0;
+    P.exp = exp_bits;
     auto kern = big ? (exp ? k_merge<1024, true> : k_merge<1024, false>) : (exp ? k_merge<512, true> : k_merge<512, false>);
     const uint32_t nthreads = big ? 1024 : 512;
     cudaFuncAttributes attr;
