@@ -274,6 +274,8 @@ struct TileShared {
     uint32_t tb_off[kMaxTileBlocks], tb_size[kMaxTileBlocks], tb_rec[kMaxTileBlocks], tb_nrec[kMaxTileBlocks];
     uint32_t cut[kMaxOutBlocks + 1], ob_off[kMaxOutBlocks + 1], ob_size[kMaxOutBlocks], ob_keyoff[kMaxOutBlocks + 1];
     unsigned long long crc[256];
+    // experimental staged heads (EXP instantiation, P.exp & 4); appended so that every other member keeps its offset
+    uint32_t stage_ok, stage_bytes, max_bch, stage_pad;
 };
 
 enum { ST_IN_REC = 0, ST_IN_BYTES, ST_OUT_REC, ST_OUT_BYTES, ST_SHADOW, ST_TOMB, ST_EXPIRED, ST_USER, ST_STALE, ST_TTL,
@@ -483,6 +485,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             const uint32_t t = S.nx_tile;
             S.tile = t;
             S.min_seq = ~0ull; S.max_seq = 0; S.max_ukey = 0; S.max_vlen = 0; S.max_blk_size = 0; S.max_blk_rec = 0; S.max_ch = 0;
+            if constexpr (EXP) { S.max_bch = 0; S.stage_ok = 0; }
             uint32_t err = S.nx_err;
             if (t < P.Q) {
                 uint32_t bytes = 0, recs = 0, blks = 0;
@@ -986,6 +989,18 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
         } else if (tid == 0) {
             S.n_ob = 0; S.n_surv = 0; S.tile_bytes = 0; S.tile_keyb = 0;
         }
+        if constexpr (EXP) {
+            // staged heads: entry heads are assembled in shared memory (in the gap between the record arrays and the staged
+            // input blocks) while the look-back waits; the write phase then stores whole 16-byte chunks that mix head and
+            // value bytes.  koff[p] = offset of survivor p's head inside the staging area.
+            if ((P.exp & 4) && tile_ok && m > 0) {
+                const uint32_t total_heads = chunked_scan(m, A.koff, S.scan, [&](uint32_t p) -> uint32_t { return A.rank[p]; });
+                if (tid == 0) {
+                    S.stage_bytes = total_heads;
+                    S.stage_ok = A.arrays_end + total_heads + 16 <= (uint32_t)(A.in - pool) ? 1u : 0u;
+                }
+            }
+        }
         __syncthreads();
         PT(6);
 
@@ -1086,6 +1101,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             unsigned long long mn_seq = ~0ull, mx_seq = 0;
             // (a) entry start offsets inside the tile's output + per-survivor stats, one thread per survivor
             uint32_t max_chunks = 0;
+            [[maybe_unused]] uint32_t max_bch = 0;
             for (uint32_t p = tid - 32 * LBW; p < m; p += NT - 32 * LBW) {
                 const uint32_t r = A.surv[p], b = A.blkid[p];
                 const uint32_t kl = A.klen[r], vl = A.vlen[r];
@@ -1105,7 +1121,26 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                 mn_seq = seq < mn_seq ? seq : mn_seq;
                 mx_seq = seq > mx_seq ? seq : mx_seq;
                 max_chunks = max(max_chunks, ((vl >> 4) + 3) >> 1); // pairs of 16-byte chunks
-                if constexpr (EXP) { // the head's three varints, packed once here instead of by every lane of the head writers
+                if constexpr (EXP) {
+                  if ((P.exp & 4) && S.stage_ok) {
+                    // stage the head: varints | key delta | trailer, byte stores into shared memory
+                    const uint32_t shared = A.shr[p], hs = A.rank[p], kd = kl - shared;
+                    uint8_t *d = pool + A.arrays_end + A.koff[p];
+                    d += put_varint32(d, shared); d += put_varint32(d, kd + 8); d += put_varint32(d, vl);
+                    const uint8_t *ks = A.arena + (size_t)r * KS + shared;
+                    for (uint32_t i = 0; i < kd; i++) d[i] = ks[i];
+                    d += kd;
+                    const unsigned long long otr = (seq << 8) | type;
+#pragma unroll
+                    for (uint32_t x = 0; x < 8; x++) d[x] = (uint8_t)(otr >> (8 * x));
+                    // chunks this entry owns (their first byte lies inside it) that are not wholly inside its value
+                    const uint32_t s0 = (eoff + 15) & ~15u, hend = eoff + hs, end = hend + vl;
+                    const uint32_t nh = hend > s0 ? (hend - s0 + 15) >> 4 : 0u;
+                    const uint32_t sl = (end - 1) & ~15u;
+                    const uint32_t extra = (sl >= s0 + 16 * nh && sl + 16 > end) ? 1u : 0u;
+                    max_bch = max(max_bch, nh + extra);
+                  } else {
+                    // the head's three varints, packed once here instead of by every lane of the head writers
                     const uint32_t shared = A.shr[p];
                     uint32_t l1, l2, l3;
                     unsigned long long hv = varint_pack(shared, l1);
@@ -1114,12 +1149,14 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                     const uint32_t h = l1 + l2 + l3; // l1 + l2 <= 6: the shifts above stay inside 64 bits whenever h <= 8
                     A.koff[p] = (uint32_t)hv;
                     A.order[p] = (uint16_t)(h <= 4 ? h : 0); // 0: the head writers pack it themselves
+                  }
                 }
             }
             s_outb = __reduce_add_sync(kFull, s_outb); s_otomb = __reduce_add_sync(kFull, s_otomb);
             s_okey = __reduce_add_sync(kFull, s_okey); s_oval = __reduce_add_sync(kFull, s_oval);
             mx_k = __reduce_max_sync(kFull, mx_k); mx_v = __reduce_max_sync(kFull, mx_v);
             max_chunks = __reduce_max_sync(kFull, max_chunks);
+            if constexpr (EXP) max_bch = __reduce_max_sync(kFull, max_bch);
             for (uint32_t d = 16; d; d >>= 1) {
                 unsigned long long o1 = __shfl_xor_sync(kFull, mn_seq, d), o2 = __shfl_xor_sync(kFull, mx_seq, d);
                 mn_seq = o1 < mn_seq ? o1 : mn_seq;
@@ -1127,6 +1164,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             }
             if (lane == 0) {
                 atomicMax(&S.max_ch, max_chunks);
+                if constexpr (EXP) { if (max_bch) atomicMax(&S.max_bch, max_bch); }
                 atomicAdd(&S.stat[ST_OUT_BYTES], s_outb);
                 atomicAdd(&S.stat[ST_OUT_TOMB], s_otomb);
                 atomicAdd(&S.stat[ST_OUT_KEY], s_okey);
@@ -1154,6 +1192,93 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             //     below and overwrite the spill.  Where a spill could touch foreign bytes, a tail is stored as
             //     8/4/2/1-byte pieces (the chunk start is 16-aligned) and a head byte by byte.
             const uint32_t ch_magic = (uint32_t)((0x100000000ull + CH - 1) / CH); // id / CH by multiply-high (exact for id*CH < 2^32)
+            bool staged_tile = false;
+            if constexpr (EXP) {
+              staged_tile = (P.exp & 4) && S.stage_ok;
+              if (staged_tile) {
+                const uint8_t *stage = pool + A.arrays_end;
+                // (b1) chunks that lie wholly inside a value: full 16-byte stores, nothing else to decide
+                for (uint32_t id = tid; id < m * CH; id += NT) {
+                    const uint32_t p = CH == 1 ? id : __umulhi(id, ch_magic), c0 = (id - p * CH) << 1;
+                    const uint32_t r = A.surv[p];
+                    const uint32_t vl = A.vlen[r];
+                    if (vl == 0) continue;
+                    const uint32_t hs = A.rank[p];
+                    uint8_t *dv = out + A.R[p] + hs;
+                    const uint32_t lead = (uint32_t)((uintptr_t)dv & 15);
+                    const uint32_t nch = (lead + vl + 15) >> 4;
+                    if (c0 >= nch) continue;
+                    const int32_t so = (int32_t)(A.voff[r] + (c0 << 4)) - (int32_t)lead;
+                    const uint32_t sh = (uint32_t)(so & 3) * 8;
+                    const uint32_t *w = (const uint32_t *)A.in + (so >> 2);
+                    uint32_t wv[9];
+#pragma unroll
+                    for (uint32_t x = 0; x < 9; x++) wv[x] = w[x];
+#pragma unroll
+                    for (uint32_t half = 0; half < 2; half++) {
+                        const uint32_t c = c0 + half;
+                        if (c >= nch) break;
+                        if ((c == 0 && lead != 0) || lead + vl < (c << 4) + 16) continue; // touches the head or the next entry: (b2)
+                        uint4 o4;
+                        o4.x = __funnelshift_r(wv[4 * half + 0], wv[4 * half + 1], sh); o4.y = __funnelshift_r(wv[4 * half + 1], wv[4 * half + 2], sh);
+                        o4.z = __funnelshift_r(wv[4 * half + 2], wv[4 * half + 3], sh); o4.w = __funnelshift_r(wv[4 * half + 3], wv[4 * half + 4], sh);
+                        *reinterpret_cast<uint4 *>(dv - lead + (c << 4)) = o4;
+                    }
+                }
+                // (b2) the other chunks an entry owns (first byte inside it): head chunks and the last, partly filled chunk of
+                //      its value.  Sixteen bytes are gathered from the staged heads and the staged values of this entry and, where
+                //      the chunk runs on, of the entries behind it; a chunk that reaches the end of the block's entries is cut
+                //      there (the restart array and the padding are written with the block trailers).
+                const uint32_t BCH = S.max_bch;
+                for (uint32_t id = tid; id < m * BCH; id += NT) {
+                    const uint32_t p = id / BCH, bi = id - p * BCH;
+                    const uint32_t e0 = A.R[p];
+                    if (bi == 0) P.out_rec_off[S.base_recs + p] = e0 - S.ob_off[A.blkid[p]]; // entry offset inside its block
+                    uint32_t q = p, rq = A.surv[p];
+                    uint32_t q_hs = A.rank[p], q_vl = A.vlen[rq], q_e0 = e0, q_ho = A.koff[p], q_vo = A.voff[rq];
+                    const uint32_t s0 = (e0 + 15) & ~15u, hend = e0 + q_hs, end = hend + q_vl;
+                    const uint32_t nh = hend > s0 ? (hend - s0 + 15) >> 4 : 0u;
+                    const uint32_t sl = (end - 1) & ~15u;
+                    uint32_t sc; // tile-relative start of this chunk
+                    if (bi < nh) sc = s0 + 16 * bi;
+                    else if (bi == nh && sl >= s0 + 16 * nh && sl + 16 > end) sc = sl;
+                    else continue;
+                    const uint32_t qend = S.cut[A.blkid[p] + 1]; // first survivor of the next block
+                    uint32_t wds[4] = {0, 0, 0, 0};
+                    uint32_t valid = 16;
+#pragma unroll
+                    for (uint32_t i = 0; i < 16; i++) {
+                        if (i < valid) {
+                            const uint32_t pos = sc + i;
+                            while (pos >= q_e0 + q_hs + q_vl) { // on to the next entry of the block
+                                q++;
+                                if (q >= qend) break;
+                                rq = A.surv[q];
+                                q_e0 = A.R[q]; q_hs = A.rank[q]; q_vl = A.vlen[rq]; q_ho = A.koff[q]; q_vo = A.voff[rq];
+                            }
+                            if (q >= qend) valid = i;
+                            else {
+                                const uint32_t off = pos - q_e0;
+                                const uint32_t by = off < q_hs ? stage[q_ho + off] : A.in[q_vo + (off - q_hs)];
+                                wds[i >> 2] |= by << (8 * (i & 3));
+                            }
+                        }
+                    }
+                    uint8_t *addr = out + sc;
+                    if (valid == 16) *reinterpret_cast<uint4 *>(addr) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+                    else { // exact prefix [0, valid) as 8/4/2/1-byte pieces
+                        uint32_t at = 0;
+                        if (valid & 8) { *reinterpret_cast<uint2 *>(addr) = make_uint2(wds[0], wds[1]); at = 8; }
+                        const uint32_t q0 = (valid & 8) ? wds[2] : wds[0], q1 = (valid & 8) ? wds[3] : wds[1];
+                        uint32_t qq = q0;
+                        if (valid & 4) { *reinterpret_cast<uint32_t *>(addr + at) = q0; at += 4; qq = q1; }
+                        if (valid & 2) { *reinterpret_cast<uint16_t *>(addr + at) = (uint16_t)qq; at += 2; qq >>= 16; }
+                        if (valid & 1) addr[at] = (uint8_t)qq;
+                    }
+                }
+              }
+            }
+            if (!staged_tile)
             for (uint32_t id = tid; id < m * CH; id += NT) {
                 const uint32_t p = CH == 1 ? id : __umulhi(id, ch_magic), c0 = (id - p * CH) << 1;
                 const uint32_t r = A.surv[p];
@@ -1228,6 +1353,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             //     destination-aligned 32-bit word of the head from its three sources (packed varints in a register, key
             //     bytes in the arena slot, trailer) with shifts and byte masks, and stores it whole; only a first or
             //     last word that the head covers partly goes out byte by byte.
+            if (!staged_tile)
             for (uint32_t p = 4 * warp + (lane >> 3); p < m; p += 4 * NW) {
                 const uint32_t ql = lane & 7;
                 const uint32_t r = A.surv[p];
