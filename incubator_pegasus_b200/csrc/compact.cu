@@ -88,7 +88,7 @@ struct MergeParams {
     uint32_t out_blk_cap, out_ikey_cap;
     MergeStats *stats;
     unsigned long long *phase_cycles; // [16] or null
-    uint32_t exp; // PGS_EXPERIMENTAL bit mask (EXP instantiation only): 1 base items, 2 sample-then-refine rank, 4 staged heads
+    uint32_t exp; // PGS_EXPERIMENTAL bit mask (EXP instantiation only): 1 base items, 2 sample-then-refine rank, 4 staged heads, 8 scan key rebuild
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -638,7 +638,70 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
         // lane L (0..15) of a half-warp owns internal-key positions 4L..4L+3 (+64 per pass) as one 32-bit word: an
         // entry overwrites the bytes of the word that its delta covers (one unaligned load + byte mask) and inherits
         // the rest from the entry before it.
-        if (tile_ok) {
+        bool d2_scanned = false;
+        if constexpr (EXP) {
+          if ((P.exp & 8) && tile_ok) {
+            // experimental: lanes = the entries of a block (16 per step), loop over the key's 32-bit words.  An entry's update
+            // of a word, word_i = (word_{i-1} & ~mask_i) | bytes_i, composes associatively, so a 4-step shuffle scan
+            // replaces the serial walk over the block's entries.
+            d2_scanned = true;
+            const uint32_t hl = lane & 15, sub = lane >> 4;
+            const uint32_t hmask = sub ? 0xffff0000u : 0x0000ffffu;
+            for (uint32_t t = 2 * warp + sub; t < S.n_blk_in; t += 2 * NW) {
+                const uint32_t rec0 = S.tb_rec[t], nrec = S.tb_nrec[t];
+                uint32_t maxk = 0;
+                for (uint32_t i = hl; i < nrec; i += 16) maxk = max(maxk, (uint32_t)A.klen[rec0 + i] + 8);
+                maxk = __reduce_max_sync(hmask, maxk);
+                auto meta = [&](uint32_t r, uint32_t &sh, uint32_t &ns, uint32_t &ulen, uint32_t &ko, uint32_t &fl) {
+                    const uint32_t a = A.R[r], b = A.koff[r]; // packed by step 1 (EXP)
+                    sh = a & 0xffffu; ns = a >> 16; ko = b & 0x7fffffffu; fl = b >> 31; ulen = A.klen[r];
+                };
+                uint32_t sh0 = 0, ns0 = 0, ulen0 = 0, ko0 = 0, fl0 = 0; // the lane's entry of the first 16
+                if (hl < nrec) meta(rec0 + hl, sh0, ns0, ulen0, ko0, fl0);
+                for (uint32_t p0 = 0; p0 < maxk; p0 += 4) {
+                    uint32_t carry = 0; // the word as of the last entry of the previous 16
+                    for (uint32_t seg = 0; seg < nrec; seg += 16) {
+                        const uint32_t i = seg + hl, r = rec0 + i;
+                        const bool act = i < nrec;
+                        uint32_t sh = sh0, ns = ns0, ulen = ulen0, ko = ko0, fl = fl0;
+                        if (seg && act) meta(r, sh, ns, ulen, ko, fl);
+                        uint32_t msk = 0, d = 0;
+                        if (act) {
+                            if (p0 == 0 && i > 0 && sh > (uint32_t)A.klen[r - 1] + 8) atomicMax(&S.error, (uint32_t)PGS_CORRUPTION); // a prefix longer than the previous key
+                            const uint32_t a = max(sh, p0), b = min(sh + ns, p0 + 4);
+                            if (a < b) {
+                                const uint32_t so = ko + (a - sh); // delta bytes for positions a..a+3
+                                const uint32_t *w = (const uint32_t *)A.in + (so >> 2);
+                                const uint32_t x = __funnelshift_r(w[0], w[1], (so & 3) * 8);
+                                const uint32_t s0 = 8 * (a - p0), s1 = 8 * (p0 + 4 - b);
+                                msk = (0xffffffffu << s0) & (0xffffffffu >> s1);
+                                d = (x << s0) & msk;
+                            }
+                        }
+#pragma unroll
+                        for (uint32_t dl = 1; dl < 16; dl <<= 1) {
+                            const uint32_t pm = __shfl_up_sync(hmask, msk, dl, 16), pd = __shfl_up_sync(hmask, d, dl, 16);
+                            if (hl >= dl) { d = (pd & ~msk) | d; msk |= pm; }
+                        }
+                        const uint32_t word = (carry & ~msk) | d;
+                        carry = __shfl_sync(hmask, word, 15, 16);
+                        if (act) {
+                            const uint32_t pad = (ulen + 7) & ~7u; // slots are zero padded to 8 bytes
+                            if (p0 < pad) {
+                                const uint32_t keep = ulen > p0 ? ulen - p0 : 0;
+                                *(uint32_t *)(A.arena + (size_t)r * KS + p0) = keep >= 4 ? word : (word & ((1u << (8 * keep)) - 1u));
+                            }
+                            if (fl && p0 < ulen + 8 && p0 + 4 > ulen) { // rare: the trailer straddles the shared prefix
+                                const unsigned long long c = p0 >= ulen ? (unsigned long long)word << (8 * (p0 - ulen)) : (unsigned long long)(word >> (8 * (ulen - p0)));
+                                if (c) atomicOr(&A.trailer[r], c);
+                            }
+                        }
+                    }
+                }
+            }
+          }
+        }
+        if (!d2_scanned && tile_ok) {
             const uint32_t hl = lane & 15, sub = lane >> 4;
             const uint32_t hmask = sub ? 0xffff0000u : 0x0000ffffu;
             for (uint32_t t = 2 * warp + sub; t < S.n_blk_in; t += 2 * NW) {

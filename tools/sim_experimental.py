@@ -1,6 +1,7 @@
 """CPU models of the index arithmetic behind two experimental k_merge items (csrc/compact.cu, EXP instantiation):
 the chunk ownership of the staged-heads writer (every entry byte written exactly once, nothing outside the entries) and
-the sample-then-refine rank search (positions equal a plain lower bound).  Restatements for review, not the CUDA code."""
+the sample-then-refine rank search (positions equal a plain lower bound) and the shuffle-scan key rebuild (keys,
+zero padding and straddling trailers equal a plain decode).  Restatements for review, not the CUDA code."""
 import random
 def sim_staged(seed):
     rnd = random.Random(seed)
@@ -96,4 +97,99 @@ def sim_sample(seed):
 for s in range(5000):
     sim_sample(s)
 
+M32 = 0xffffffff
+def sim_d2(seed):
+    rnd = random.Random(seed)
+    nrec = rnd.randint(1, 45)
+    KS = 64
+    # internal keys = user key + 8-byte trailer; build sorted-ish keys with shared prefixes
+    keys = []
+    base = bytes(rnd.randrange(256) for _ in range(rnd.randint(0, 30)))
+    prev = None
+    for i in range(nrec):
+        if prev is not None and rnd.random() < 0.15:
+            uk = prev[:-8]  # same user key, different trailer (another version)
+        else:
+            uk = base + bytes(rnd.randrange(256) for _ in range(rnd.randint(0, 20)))
+        tr_same = prev is not None and uk == prev[:-8]
+        tr = (prev[-8:-3] if tr_same and rnd.random() < 0.7 else bytes(rnd.randrange(256) for _ in range(5))) + bytes(rnd.randrange(256) for _ in range(3))
+        tr = tr[:8]
+        keys.append(uk + tr)
+        prev = keys[-1]
+    # encode: restart every 16 (shared = 0), else LCP with previous
+    IN = bytearray(b"\xAA" * 3)
+    meta = []
+    for i, k in enumerate(keys):
+        sh = 0
+        if i % 16 != 0:
+            p = keys[i - 1]
+            while sh < min(len(p), len(k)) and p[sh] == k[sh]: sh += 1
+            sh = rnd.randint(0, sh)  # any shorter prefix is a legal encoding too
+        ns = len(k) - sh
+        ko = len(IN)
+        IN += k[sh:] + bytes(rnd.randrange(256) for _ in range(rnd.randint(0, 9)))  # value bytes follow
+        meta.append((sh, ns, len(k) - 8, ko, 1 if ns < 8 else 0))
+    IN += b"\x55" * 16
+    def ld32(off):
+        a = off & ~3
+        w0 = int.from_bytes(IN[a:a+4], 'little'); w1 = int.from_bytes(IN[a+4:a+8], 'little')
+        s = (off & 3) * 8
+        return ((w0 | (w1 << 32)) >> s) & M32
+    arena = [bytearray(KS) for _ in range(nrec)]
+    trailer = [0] * nrec
+    for i in range(nrec):
+        if meta[i][4] == 0:
+            trailer[i] = int.from_bytes(keys[i][-8:], 'little')
+    maxk = max(m[2] + 8 for m in meta)
+    for p0 in range(0, maxk, 4):
+        carry = 0
+        for seg in range(0, nrec, 16):
+            lanes = []
+            for hl in range(16):
+                i = seg + hl
+                if i < nrec:
+                    sh, ns, ulen, ko, fl = meta[i]
+                    a = max(sh, p0); b = min(sh + ns, p0 + 4)
+                    msk = d = 0
+                    if a < b:
+                        x = ld32(ko + (a - sh))
+                        s0 = 8 * (a - p0); s1 = 8 * (p0 + 4 - b)
+                        msk = ((M32 << s0) & M32) & (M32 >> s1)
+                        d = ((x << s0) & M32) & msk
+                    lanes.append([msk, d])
+                else:
+                    lanes.append([0, 0])
+            dl = 1
+            while dl < 16:
+                new = [l[:] for l in lanes]
+                for hl in range(16):
+                    if hl >= dl:
+                        pm, pd = lanes[hl - dl]
+                        msk, d = lanes[hl]
+                        new[hl] = [msk | pm, (pd & ~msk & M32) | d]
+                lanes = new
+                dl <<= 1
+            words = [((carry & ~l[0]) & M32) | l[1] for l in lanes]
+            carry = words[15]
+            for hl in range(16):
+                i = seg + hl
+                if i >= nrec: continue
+                sh, ns, ulen, ko, fl = meta[i]
+                word = words[hl]
+                pad = (ulen + 7) & ~7
+                if p0 < pad:
+                    keep = ulen - p0 if ulen > p0 else 0
+                    v = word if keep >= 4 else word & ((1 << (8 * keep)) - 1)
+                    arena[i][p0:p0+4] = v.to_bytes(4, 'little')
+                if fl and p0 < ulen + 8 and p0 + 4 > ulen:
+                    c = (word << (8 * (p0 - ulen))) & 0xffffffffffffffff if p0 >= ulen else word >> (8 * (ulen - p0))
+                    trailer[i] |= c
+    for i, k in enumerate(keys):
+        ulen = len(k) - 8
+        pad = (ulen + 7) & ~7
+        assert bytes(arena[i][:ulen]) == k[:ulen], (seed, i, 'key')
+        assert all(x == 0 for x in arena[i][ulen:pad]), (seed, i, 'pad')
+        assert trailer[i] == int.from_bytes(k[-8:], 'little'), (seed, i, 'trailer', hex(trailer[i]), k[-8:].hex(), meta[i])
+for s in range(2000):
+    sim_d2(s)
 print("ok")
