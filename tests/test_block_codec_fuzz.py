@@ -35,7 +35,7 @@ def record_sets(draw):
     return fixed
 
 
-@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@settings(max_examples=150, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(items=record_sets())
 def test_product_and_oracle_codecs_agree(pgs, oracle, items):
     r = pgs.Records.from_list(items)
