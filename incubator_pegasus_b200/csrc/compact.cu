@@ -88,7 +88,6 @@ struct MergeParams {
     uint32_t out_blk_cap, out_ikey_cap;
     MergeStats *stats;
     unsigned long long *phase_cycles; // [16] or null
-    uint32_t exp; // PGS_EXPERIMENTAL bit mask (EXP instantiation only): 1 base items, 2 sample-then-refine rank, 4 staged heads, 8 scan key rebuild
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -274,8 +273,6 @@ struct TileShared {
     uint32_t tb_off[kMaxTileBlocks], tb_size[kMaxTileBlocks], tb_rec[kMaxTileBlocks], tb_nrec[kMaxTileBlocks];
     uint32_t cut[kMaxOutBlocks + 1], ob_off[kMaxOutBlocks + 1], ob_size[kMaxOutBlocks], ob_keyoff[kMaxOutBlocks + 1];
     unsigned long long crc[256];
-    // experimental staged heads (EXP instantiation, P.exp & 4); appended so that every other member keeps its offset
-    uint32_t stage_ok, stage_bytes, max_bch, stage_pad;
 };
 
 enum { ST_IN_REC = 0, ST_IN_BYTES, ST_OUT_REC, ST_OUT_BYTES, ST_SHADOW, ST_TOMB, ST_EXPIRED, ST_USER, ST_STALE, ST_TTL,
@@ -451,10 +448,7 @@ PGS_DEV void fetch_next_tile(const MergeParams &P, TileShared &S, uint32_t lane)
     }
 }
 
-// EXP = true compiles the variants that are still being evaluated (PGS_EXPERIMENTAL=1 selects that instantiation;
-// the default instantiation contains none of their code): packed per-record metadata for the key rebuild, varints
-// of the entry heads packed once per survivor, sample-then-refine rank searches.
-template <uint32_t NT, bool EXP>
+template <uint32_t NT>
 __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParams P)
 {
     constexpr uint32_t NW = NT / 32;
@@ -485,7 +479,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             const uint32_t t = S.nx_tile;
             S.tile = t;
             S.min_seq = ~0ull; S.max_seq = 0; S.max_ukey = 0; S.max_vlen = 0; S.max_blk_size = 0; S.max_blk_rec = 0; S.max_ch = 0;
-            if constexpr (EXP) { S.max_bch = 0; S.stage_ok = 0; }
+            
             uint32_t err = S.nx_err;
             if (t < P.Q) {
                 uint32_t bytes = 0, recs = 0, blks = 0;
@@ -607,9 +601,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                     if (!c || klen < 8 || klen - 8 > KS || end > limit || (i == 0 && shared != 0) || (i + 1 == cnt && end != limit)) {
                         err = PGS_CORRUPTION;
                     } else {
-                        if constexpr (EXP) { // one word per record for step 2: shared | non_shared << 16
-                            A.R[r] = shared | (non_shared << 16);
-                        } else {
+                        {
                             A.rank[r] = (uint16_t)shared;      // scratch until the rank phase
                             A.order[r] = (uint16_t)non_shared; // scratch until the scatter phase
                         }
@@ -623,7 +615,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                         } else {               // part of it is shared with the previous key: rebuilt in step 2
                             A.trailer[r] = 0;
                             A.flags[r] = 1;
-                            if constexpr (EXP) A.koff[r] |= 0x80000000u;
+                            
                         }
                     }
                 }
@@ -638,70 +630,8 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
         // lane L (0..15) of a half-warp owns internal-key positions 4L..4L+3 (+64 per pass) as one 32-bit word: an
         // entry overwrites the bytes of the word that its delta covers (one unaligned load + byte mask) and inherits
         // the rest from the entry before it.
-        bool d2_scanned = false;
-        if constexpr (EXP) {
-          if ((P.exp & 8) && tile_ok) {
-            // experimental: lanes = the entries of a block (16 per step), loop over the key's 32-bit words.  An entry's update
-            // of a word, word_i = (word_{i-1} & ~mask_i) | bytes_i, composes associatively, so a 4-step shuffle scan
-            // replaces the serial walk over the block's entries.
-            d2_scanned = true;
-            const uint32_t hl = lane & 15, sub = lane >> 4;
-            const uint32_t hmask = sub ? 0xffff0000u : 0x0000ffffu;
-            for (uint32_t t = 2 * warp + sub; t < S.n_blk_in; t += 2 * NW) {
-                const uint32_t rec0 = S.tb_rec[t], nrec = S.tb_nrec[t];
-                uint32_t maxk = 0;
-                for (uint32_t i = hl; i < nrec; i += 16) maxk = max(maxk, (uint32_t)A.klen[rec0 + i] + 8);
-                maxk = __reduce_max_sync(hmask, maxk);
-                auto meta = [&](uint32_t r, uint32_t &sh, uint32_t &ns, uint32_t &ulen, uint32_t &ko, uint32_t &fl) {
-                    const uint32_t a = A.R[r], b = A.koff[r]; // packed by step 1 (EXP)
-                    sh = a & 0xffffu; ns = a >> 16; ko = b & 0x7fffffffu; fl = b >> 31; ulen = A.klen[r];
-                };
-                uint32_t sh0 = 0, ns0 = 0, ulen0 = 0, ko0 = 0, fl0 = 0; // the lane's entry of the first 16
-                if (hl < nrec) meta(rec0 + hl, sh0, ns0, ulen0, ko0, fl0);
-                for (uint32_t p0 = 0; p0 < maxk; p0 += 4) {
-                    uint32_t carry = 0; // the word as of the last entry of the previous 16
-                    for (uint32_t seg = 0; seg < nrec; seg += 16) {
-                        const uint32_t i = seg + hl, r = rec0 + i;
-                        const bool act = i < nrec;
-                        uint32_t sh = sh0, ns = ns0, ulen = ulen0, ko = ko0, fl = fl0;
-                        if (seg && act) meta(r, sh, ns, ulen, ko, fl);
-                        uint32_t msk = 0, d = 0;
-                        if (act) {
-                            if (p0 == 0 && i > 0 && sh > (uint32_t)A.klen[r - 1] + 8) atomicMax(&S.error, (uint32_t)PGS_CORRUPTION); // a prefix longer than the previous key
-                            const uint32_t a = max(sh, p0), b = min(sh + ns, p0 + 4);
-                            if (a < b) {
-                                const uint32_t so = ko + (a - sh); // delta bytes for positions a..a+3
-                                const uint32_t *w = (const uint32_t *)A.in + (so >> 2);
-                                const uint32_t x = __funnelshift_r(w[0], w[1], (so & 3) * 8);
-                                const uint32_t s0 = 8 * (a - p0), s1 = 8 * (p0 + 4 - b);
-                                msk = (0xffffffffu << s0) & (0xffffffffu >> s1);
-                                d = (x << s0) & msk;
-                            }
-                        }
-#pragma unroll
-                        for (uint32_t dl = 1; dl < 16; dl <<= 1) {
-                            const uint32_t pm = __shfl_up_sync(hmask, msk, dl, 16), pd = __shfl_up_sync(hmask, d, dl, 16);
-                            if (hl >= dl) { d = (pd & ~msk) | d; msk |= pm; }
-                        }
-                        const uint32_t word = (carry & ~msk) | d;
-                        carry = __shfl_sync(hmask, word, 15, 16);
-                        if (act) {
-                            const uint32_t pad = (ulen + 7) & ~7u; // slots are zero padded to 8 bytes
-                            if (p0 < pad) {
-                                const uint32_t keep = ulen > p0 ? ulen - p0 : 0;
-                                *(uint32_t *)(A.arena + (size_t)r * KS + p0) = keep >= 4 ? word : (word & ((1u << (8 * keep)) - 1u));
-                            }
-                            if (fl && p0 < ulen + 8 && p0 + 4 > ulen) { // rare: the trailer straddles the shared prefix
-                                const unsigned long long c = p0 >= ulen ? (unsigned long long)word << (8 * (p0 - ulen)) : (unsigned long long)(word >> (8 * (ulen - p0)));
-                                if (c) atomicOr(&A.trailer[r], c);
-                            }
-                        }
-                    }
-                }
-            }
-          }
-        }
-        if (!d2_scanned && tile_ok) {
+        
+        if (tile_ok) {
             const uint32_t hl = lane & 15, sub = lane >> 4;
             const uint32_t hmask = sub ? 0xffff0000u : 0x0000ffffu;
             for (uint32_t t = 2 * warp + sub; t < S.n_blk_in; t += 2 * NW) {
@@ -713,17 +643,13 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                     const uint32_t p0 = pass * 64 + 4 * hl;
                     uint32_t cur = 0, prev_klen = 0; // the four running bytes, little endian
                     uint32_t sh = 0, ns = 0, ulen = 0, ko = 0, fl = 0;
-                    if constexpr (EXP) { // two packed words + the key length instead of five arrays
-                        if (nrec) { const uint32_t a = A.R[rec0], b = A.koff[rec0]; sh = a & 0xffffu; ns = a >> 16; ko = b & 0x7fffffffu; fl = b >> 31; ulen = A.klen[rec0]; }
-                    } else {
+                    {
                         if (nrec) { sh = A.rank[rec0]; ns = A.order[rec0]; ulen = A.klen[rec0]; ko = A.koff[rec0]; fl = A.flags[rec0]; }
                     }
                     for (uint32_t i = 0; i < nrec; i++) {
                         const uint32_t r = rec0 + i;
                         const uint32_t c_sh = sh, c_ns = ns, c_ulen = ulen, c_ko = ko, c_fl = fl;
-                        if constexpr (EXP) {
-                            if (i + 1 < nrec) { const uint32_t a = A.R[r + 1], b = A.koff[r + 1]; sh = a & 0xffffu; ns = a >> 16; ko = b & 0x7fffffffu; fl = b >> 31; ulen = A.klen[r + 1]; }
-                        } else {
+                        {
                             if (i + 1 < nrec) { sh = A.rank[r + 1]; ns = A.order[r + 1]; ulen = A.klen[r + 1]; ko = A.koff[r + 1]; fl = A.flags[r + 1]; } // next entry's metadata in flight
                         }
                         if (c_sh > prev_klen) { if (hl == 0) atomicMax(&S.error, (uint32_t)PGS_CORRUPTION); break; } // a prefix longer than the previous key
@@ -807,69 +733,6 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
         if (tile_ok && P.k > 1) {
             const uint32_t k = P.k, km1 = k - 1;
             uint32_t ntask = 0;
-            bool sampled = false;
-            if constexpr (EXP) {
-              if (P.exp & 2) {
-                sampled = true;
-                // sample-then-refine: every SS-th record of a run (and its last one) searches the whole window of the other
-                // run; the records in between only search between the positions their two neighbouring samples found
-                constexpr uint32_t SS = 8;
-                auto search = [&](uint32_t j, uint32_t o, uint32_t r, uint32_t lo, uint32_t hi) {
-                    const uint8_t *key = A.arena + (size_t)r * KS;
-                    const uint32_t kl = A.klen[r];
-                    const unsigned long long tr = A.trailer[r];
-                    const uint32_t base = S.rec_base[o];
-                    uint32_t lcp_lo = 0, lcp_hi = 0;
-                    while (lo < hi) { // first position whose internal key is not before ours
-                        uint32_t mid = (lo + hi) >> 1, q = base + mid, d;
-                        int c = cmp_slots_from(A.arena + (size_t)q * KS, A.klen[q], key, kl, min(lcp_lo, lcp_hi), &d);
-                        bool before;
-                        if (c != 0) before = c < 0;
-                        else {
-                            unsigned long long tq = A.trailer[q];
-                            before = tq > tr || (tq == tr && o < j);
-                        }
-                        if (before) { lo = mid + 1; lcp_lo = d; } else { hi = mid; lcp_hi = d; }
-                    }
-                    const uint32_t cnt = lo - S.vlo[o];
-                    A.pos[(size_t)r * km1 + (o - 1)] = (uint16_t)cnt;
-                    if (cnt) {
-                        atomicAdd(&A.R[r], cnt);
-                        uint32_t q = base + lo - 1;
-                        if (A.klen[q] == kl && cmp_slots(A.arena + (size_t)q * KS, kl, key, kl) == 0) atomicOr(&A.E[r], 1u);
-                    }
-                };
-                auto nsamp = [&](uint32_t j) -> uint32_t { const uint32_t nv = S.vhi[j] - S.vlo[j]; return nv ? (nv - 1 + SS - 1) / SS + 1 : 0u; };
-                // pass A: the samples
-                for (uint32_t j = 0; j < k; j++) ntask += nsamp(j) * (km1 - j);
-                for (uint32_t id = tid; id < ntask; id += NT) {
-                    uint32_t j = 0, local = id;
-                    while (local >= nsamp(j) * (km1 - j)) { local -= nsamp(j) * (km1 - j); j++; }
-                    const uint32_t nt = km1 - j, si = local / nt, o = j + 1 + (local - si * nt);
-                    const uint32_t nv = S.vhi[j] - S.vlo[j];
-                    const uint32_t rel = min(si * SS, nv - 1);
-                    if (si > 0 && rel == (si - 1) * SS) continue; // the last sample coincides with the one before it
-                    search(j, o, S.rec_base[j] + S.vlo[j] + rel, S.vlo[o], S.vhi[o]);
-                }
-                __syncthreads();
-                // pass B: everything in between
-                ntask = 0;
-                for (uint32_t j = 0; j < k; j++) ntask += S.nrec[j] * (km1 - j);
-                for (uint32_t id = tid; id < ntask; id += NT) {
-                    uint32_t j = 0, local = id;
-                    while (local >= S.nrec[j] * (km1 - j)) { local -= S.nrec[j] * (km1 - j); j++; }
-                    const uint32_t nt = km1 - j, ri = local / nt;
-                    const uint32_t o = j + 1 + (local - ri * nt), r = S.rec_base[j] + ri;
-                    if (!(A.flags[r] & F_VALID)) continue;
-                    const uint32_t nv = S.vhi[j] - S.vlo[j], rel = ri - S.vlo[j];
-                    if (rel % SS == 0 || rel + 1 == nv) continue; // a sample: done in pass A
-                    const uint32_t s0 = rel - rel % SS, s1 = min(s0 + SS, nv - 1);
-                    const uint32_t rb = S.rec_base[j] + S.vlo[j];
-                    search(j, o, r, S.vlo[o] + A.pos[(size_t)(rb + s0) * km1 + (o - 1)], S.vlo[o] + A.pos[(size_t)(rb + s1) * km1 + (o - 1)]);
-                }
-              }
-            }
-            if (!sampled) {
             for (uint32_t j = 0; j < k; j++) ntask += S.nrec[j] * (km1 - j);
             for (uint32_t id = tid; id < ntask; id += NT) {
                 uint32_t j = 0, local = id;
@@ -900,7 +763,6 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                     uint32_t q = base + lo - 1;
                     if (A.klen[q] == kl && cmp_slots(A.arena + (size_t)q * KS, kl, key, kl) == 0) atomicOr(&A.E[r], 1u);
                 }
-            }
             }
             __syncthreads();
             PT(13);
@@ -1052,18 +914,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
         } else if (tid == 0) {
             S.n_ob = 0; S.n_surv = 0; S.tile_bytes = 0; S.tile_keyb = 0;
         }
-        if constexpr (EXP) {
-            // staged heads: entry heads are assembled in shared memory (in the gap between the record arrays and the staged
-            // input blocks) while the look-back waits; the write phase then stores whole 16-byte chunks that mix head and
-            // value bytes.  koff[p] = offset of survivor p's head inside the staging area.
-            if ((P.exp & 4) && tile_ok && m > 0) {
-                const uint32_t total_heads = chunked_scan(m, A.koff, S.scan, [&](uint32_t p) -> uint32_t { return A.rank[p]; });
-                if (tid == 0) {
-                    S.stage_bytes = total_heads;
-                    S.stage_ok = A.arrays_end + total_heads + 16 <= (uint32_t)(A.in - pool) ? 1u : 0u;
-                }
-            }
-        }
+        
         __syncthreads();
         PT(6);
 
@@ -1164,7 +1015,6 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             unsigned long long mn_seq = ~0ull, mx_seq = 0;
             // (a) entry start offsets inside the tile's output + per-survivor stats, one thread per survivor
             uint32_t max_chunks = 0;
-            [[maybe_unused]] uint32_t max_bch = 0;
             for (uint32_t p = tid - 32 * LBW; p < m; p += NT - 32 * LBW) {
                 const uint32_t r = A.surv[p], b = A.blkid[p];
                 const uint32_t kl = A.klen[r], vl = A.vlen[r];
@@ -1184,42 +1034,13 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                 mn_seq = seq < mn_seq ? seq : mn_seq;
                 mx_seq = seq > mx_seq ? seq : mx_seq;
                 max_chunks = max(max_chunks, ((vl >> 4) + 3) >> 1); // pairs of 16-byte chunks
-                if constexpr (EXP) {
-                  if ((P.exp & 4) && S.stage_ok) {
-                    // stage the head: varints | key delta | trailer, byte stores into shared memory
-                    const uint32_t shared = A.shr[p], hs = A.rank[p], kd = kl - shared;
-                    uint8_t *d = pool + A.arrays_end + A.koff[p];
-                    d += put_varint32(d, shared); d += put_varint32(d, kd + 8); d += put_varint32(d, vl);
-                    const uint8_t *ks = A.arena + (size_t)r * KS + shared;
-                    for (uint32_t i = 0; i < kd; i++) d[i] = ks[i];
-                    d += kd;
-                    const unsigned long long otr = (seq << 8) | type;
-#pragma unroll
-                    for (uint32_t x = 0; x < 8; x++) d[x] = (uint8_t)(otr >> (8 * x));
-                    // chunks this entry owns (their first byte lies inside it) that are not wholly inside its value
-                    const uint32_t s0 = (eoff + 15) & ~15u, hend = eoff + hs, end = hend + vl;
-                    const uint32_t nh = hend > s0 ? (hend - s0 + 15) >> 4 : 0u;
-                    const uint32_t sl = (end - 1) & ~15u;
-                    const uint32_t extra = (sl >= s0 + 16 * nh && sl + 16 > end) ? 1u : 0u;
-                    max_bch = max(max_bch, nh + extra);
-                  } else {
-                    // the head's three varints, packed once here instead of by every lane of the head writers
-                    const uint32_t shared = A.shr[p];
-                    uint32_t l1, l2, l3;
-                    unsigned long long hv = varint_pack(shared, l1);
-                    hv |= varint_pack(kl - shared + 8, l2) << (8 * l1);
-                    hv |= varint_pack(vl, l3) << (8 * (l1 + l2));
-                    const uint32_t h = l1 + l2 + l3; // l1 + l2 <= 6: the shifts above stay inside 64 bits whenever h <= 8
-                    A.koff[p] = (uint32_t)hv;
-                    A.order[p] = (uint16_t)(h <= 4 ? h : 0); // 0: the head writers pack it themselves
-                  }
-                }
+                
             }
             s_outb = __reduce_add_sync(kFull, s_outb); s_otomb = __reduce_add_sync(kFull, s_otomb);
             s_okey = __reduce_add_sync(kFull, s_okey); s_oval = __reduce_add_sync(kFull, s_oval);
             mx_k = __reduce_max_sync(kFull, mx_k); mx_v = __reduce_max_sync(kFull, mx_v);
             max_chunks = __reduce_max_sync(kFull, max_chunks);
-            if constexpr (EXP) max_bch = __reduce_max_sync(kFull, max_bch);
+            
             for (uint32_t d = 16; d; d >>= 1) {
                 unsigned long long o1 = __shfl_xor_sync(kFull, mn_seq, d), o2 = __shfl_xor_sync(kFull, mx_seq, d);
                 mn_seq = o1 < mn_seq ? o1 : mn_seq;
@@ -1227,7 +1048,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             }
             if (lane == 0) {
                 atomicMax(&S.max_ch, max_chunks);
-                if constexpr (EXP) { if (max_bch) atomicMax(&S.max_bch, max_bch); }
+                
                 atomicAdd(&S.stat[ST_OUT_BYTES], s_outb);
                 atomicAdd(&S.stat[ST_OUT_TOMB], s_otomb);
                 atomicAdd(&S.stat[ST_OUT_KEY], s_okey);
@@ -1255,93 +1076,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             //     below and overwrite the spill.  Where a spill could touch foreign bytes, a tail is stored as
             //     8/4/2/1-byte pieces (the chunk start is 16-aligned) and a head byte by byte.
             const uint32_t ch_magic = (uint32_t)((0x100000000ull + CH - 1) / CH); // id / CH by multiply-high (exact for id*CH < 2^32)
-            bool staged_tile = false;
-            if constexpr (EXP) {
-              staged_tile = (P.exp & 4) && S.stage_ok;
-              if (staged_tile) {
-                const uint8_t *stage = pool + A.arrays_end;
-                // (b1) chunks that lie wholly inside a value: full 16-byte stores, nothing else to decide
-                for (uint32_t id = tid; id < m * CH; id += NT) {
-                    const uint32_t p = CH == 1 ? id : __umulhi(id, ch_magic), c0 = (id - p * CH) << 1;
-                    const uint32_t r = A.surv[p];
-                    const uint32_t vl = A.vlen[r];
-                    if (vl == 0) continue;
-                    const uint32_t hs = A.rank[p];
-                    uint8_t *dv = out + A.R[p] + hs;
-                    const uint32_t lead = (uint32_t)((uintptr_t)dv & 15);
-                    const uint32_t nch = (lead + vl + 15) >> 4;
-                    if (c0 >= nch) continue;
-                    const int32_t so = (int32_t)(A.voff[r] + (c0 << 4)) - (int32_t)lead;
-                    const uint32_t sh = (uint32_t)(so & 3) * 8;
-                    const uint32_t *w = (const uint32_t *)A.in + (so >> 2);
-                    uint32_t wv[9];
-#pragma unroll
-                    for (uint32_t x = 0; x < 9; x++) wv[x] = w[x];
-#pragma unroll
-                    for (uint32_t half = 0; half < 2; half++) {
-                        const uint32_t c = c0 + half;
-                        if (c >= nch) break;
-                        if ((c == 0 && lead != 0) || lead + vl < (c << 4) + 16) continue; // touches the head or the next entry: (b2)
-                        uint4 o4;
-                        o4.x = __funnelshift_r(wv[4 * half + 0], wv[4 * half + 1], sh); o4.y = __funnelshift_r(wv[4 * half + 1], wv[4 * half + 2], sh);
-                        o4.z = __funnelshift_r(wv[4 * half + 2], wv[4 * half + 3], sh); o4.w = __funnelshift_r(wv[4 * half + 3], wv[4 * half + 4], sh);
-                        *reinterpret_cast<uint4 *>(dv - lead + (c << 4)) = o4;
-                    }
-                }
-                // (b2) the other chunks an entry owns (first byte inside it): head chunks and the last, partly filled chunk of
-                //      its value.  Sixteen bytes are gathered from the staged heads and the staged values of this entry and, where
-                //      the chunk runs on, of the entries behind it; a chunk that reaches the end of the block's entries is cut
-                //      there (the restart array and the padding are written with the block trailers).
-                const uint32_t BCH = S.max_bch;
-                for (uint32_t id = tid; id < m * BCH; id += NT) {
-                    const uint32_t p = id / BCH, bi = id - p * BCH;
-                    const uint32_t e0 = A.R[p];
-                    if (bi == 0) P.out_rec_off[S.base_recs + p] = e0 - S.ob_off[A.blkid[p]]; // entry offset inside its block
-                    uint32_t q = p, rq = A.surv[p];
-                    uint32_t q_hs = A.rank[p], q_vl = A.vlen[rq], q_e0 = e0, q_ho = A.koff[p], q_vo = A.voff[rq];
-                    const uint32_t s0 = (e0 + 15) & ~15u, hend = e0 + q_hs, end = hend + q_vl;
-                    const uint32_t nh = hend > s0 ? (hend - s0 + 15) >> 4 : 0u;
-                    const uint32_t sl = (end - 1) & ~15u;
-                    uint32_t sc; // tile-relative start of this chunk
-                    if (bi < nh) sc = s0 + 16 * bi;
-                    else if (bi == nh && sl >= s0 + 16 * nh && sl + 16 > end) sc = sl;
-                    else continue;
-                    const uint32_t qend = S.cut[A.blkid[p] + 1]; // first survivor of the next block
-                    uint32_t wds[4] = {0, 0, 0, 0};
-                    uint32_t valid = 16;
-#pragma unroll
-                    for (uint32_t i = 0; i < 16; i++) {
-                        if (i < valid) {
-                            const uint32_t pos = sc + i;
-                            while (pos >= q_e0 + q_hs + q_vl) { // on to the next entry of the block
-                                q++;
-                                if (q >= qend) break;
-                                rq = A.surv[q];
-                                q_e0 = A.R[q]; q_hs = A.rank[q]; q_vl = A.vlen[rq]; q_ho = A.koff[q]; q_vo = A.voff[rq];
-                            }
-                            if (q >= qend) valid = i;
-                            else {
-                                const uint32_t off = pos - q_e0;
-                                const uint32_t by = off < q_hs ? stage[q_ho + off] : A.in[q_vo + (off - q_hs)];
-                                wds[i >> 2] |= by << (8 * (i & 3));
-                            }
-                        }
-                    }
-                    uint8_t *addr = out + sc;
-                    if (valid == 16) *reinterpret_cast<uint4 *>(addr) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
-                    else { // exact prefix [0, valid) as 8/4/2/1-byte pieces
-                        uint32_t at = 0;
-                        if (valid & 8) { *reinterpret_cast<uint2 *>(addr) = make_uint2(wds[0], wds[1]); at = 8; }
-                        const uint32_t q0 = (valid & 8) ? wds[2] : wds[0], q1 = (valid & 8) ? wds[3] : wds[1];
-                        uint32_t qq = q0;
-                        if (valid & 4) { *reinterpret_cast<uint32_t *>(addr + at) = q0; at += 4; qq = q1; }
-                        if (valid & 2) { *reinterpret_cast<uint16_t *>(addr + at) = (uint16_t)qq; at += 2; qq >>= 16; }
-                        if (valid & 1) addr[at] = (uint8_t)qq;
-                    }
-                }
-              }
-            }
-            if (!staged_tile)
+            
             for (uint32_t id = tid; id < m * CH; id += NT) {
                 const uint32_t p = CH == 1 ? id : __umulhi(id, ch_magic), c0 = (id - p * CH) << 1;
                 const uint32_t r = A.surv[p];
@@ -1416,7 +1151,6 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
             //     destination-aligned 32-bit word of the head from its three sources (packed varints in a register, key
             //     bytes in the arena slot, trailer) with shifts and byte masks, and stores it whole; only a first or
             //     last word that the head covers partly goes out byte by byte.
-            if (!staged_tile)
             for (uint32_t p = 4 * warp + (lane >> 3); p < m; p += 4 * NW) {
                 const uint32_t ql = lane & 7;
                 const uint32_t r = A.surv[p];
@@ -1428,10 +1162,7 @@ __global__ void __launch_bounds__(NT) k_merge(const __grid_constant__ MergeParam
                 const unsigned long long hv2 = varint_pack(kd + 8, l2), hv3 = varint_pack(vl, l3);
                 uint32_t h = l1 + l2 + l3;
                 bool packed = false;
-                if constexpr (EXP) { // packed by the write-prep pass when it fits 4 bytes (the compiler drops the code above then)
-                    const uint32_t hp = A.order[p];
-                    if (hp) { h = hp; hv = A.koff[p]; packed = true; }
-                }
+                
                 if (ql == 0) P.out_rec_off[S.base_recs + p] = doff - S.ob_off[A.blkid[p]]; // entry offset inside its block
                 uint8_t *dst = out + doff;
                 if (h > 8) { // lengths this large do not fit the packed register: one lane writes the head serially
@@ -1637,11 +1368,7 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
 
     // ctas_per_sm: 2 -> two 512-thread CTAs per SM (default); 1 -> one 1024-thread CTA per SM with tiles twice as large
     const bool big = e->cfg.ctas_per_sm == 1;
-    const char *exp_env = getenv("PGS_EXPERIMENTAL");
-    const uint32_t exp_bits = exp_env ? (uint32_t)atoi(exp_env) : 0;
-    const bool exp = exp_bits != 0;
-    P.exp = exp_bits;
-    auto kern = big ? (exp ? k_merge<1024, true> : k_merge<1024, false>) : (exp ? k_merge<512, true> : k_merge<512, false>);
+    auto kern = big ? k_merge<1024> : k_merge<512>;
     const uint32_t nthreads = big ? 1024 : 512;
     cudaFuncAttributes attr;
     PGS_CUDA(cudaFuncGetAttributes(&attr, kern));
