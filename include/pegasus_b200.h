@@ -174,10 +174,13 @@ typedef struct {
     uint64_t dropped_user;      /* Filter(): user-specified delete op                          */
     uint64_t dropped_stale;     /* Filter(): stale split data                                  */
     uint64_t ttl_rewritten;     /* Filter(): value_changed                                     */
-    uint32_t n_tiles;
+    uint32_t n_tiles;      /* segments of the merge                                               */
     uint32_t n_launches;
-    float device_ms; /* CUDA-event time of the plan + merge kernels                            */
-    float merge_kernel_ms;
+    float device_ms;       /* CUDA-event time of all compaction kernels                           */
+    float merge_kernel_ms; /* k_walk + k_seg_scan + k_emit                                       */
+    float walk_ms;         /* k_walk: the merge (decode, compare, filter, layout)                 */
+    float emit_ms;         /* k_seg_scan + k_emit: block assembly and stores                      */
+    uint32_t reserved;
 } pgs_compact_result;
 
 /* k-way merge of `k` runs of one partition into one new run at `out_level`, newest version of

@@ -65,7 +65,8 @@ class CompactResult(C.Structure):
                 ("dropped_tombstone", C.c_uint64), ("dropped_expired", C.c_uint64),
                 ("dropped_user", C.c_uint64), ("dropped_stale", C.c_uint64), ("ttl_rewritten", C.c_uint64),
                 ("n_tiles", C.c_uint32), ("n_launches", C.c_uint32), ("device_ms", C.c_float),
-                ("merge_kernel_ms", C.c_float)]
+                ("merge_kernel_ms", C.c_float), ("walk_ms", C.c_float), ("emit_ms", C.c_float),
+                ("reserved", C.c_uint32)]
 
 
 class GetResult(C.Structure):

@@ -1,0 +1,924 @@
+// compact_kernels.cuh — level compaction on the GPU: k-way merge of HBM-resident sorted runs with
+// KeyWithTTLCompactionFilter fused into the merge loop.
+//
+// Replaces (reference file:line):
+//   DB::CompactRange / background compaction job ....... src/server/pegasus_server_impl.cpp:3373-3394
+//   RocksDB MergingIterator + CompactionIterator + BlockBasedTableBuilder (v8.5.3, not in tree;
+//   semantics restated in SURVEY.md Appendix A)
+//   KeyWithTTLCompactionFilter::Filter .................. src/server/key_ttl_compaction_filter.h:55-121
+//   compaction_operation / compaction_filter_rule ....... src/server/compaction_operation.cpp:33-113,
+//                                                         src/server/compaction_filter_rule.cpp:31-90
+//
+// Shape of the computation (B200-first; byte/integer work bound by HBM, no tensor cores):
+//   k_plan        one thread per input block ranks the block's last user key against every run's block index
+//                 => cumulative weight of everything <= that key.  Keys where the weight crosses a multiple of the
+//                 segment budget become segment boundaries: segment q = user keys in (U_q, U_q+1], a contiguous
+//                 block range per run.  All versions of a user key fall into one segment.
+//   k_walk        the merge itself.  A *group* of 8 (16, 32) lanes owns one segment and walks it sequentially like
+//                 RocksDB's MergingIterator + CompactionIterator: one cursor per run decoding entries straight from
+//                 HBM (group.cuh), the current keys in shared-memory rows compared with one ballot, newest version
+//                 wins, tombstone / bottommost rules, Filter() per surviving value, prefix compression against the
+//                 previous survivor, 4 KB block cuts.  It copies no values: per survivor it emits a 16-byte descriptor
+//                 (where the value lives, lengths, flags) and the finished entry head (varints | key delta | trailer).
+//                 Four (two, one) groups share a warp in lock step; there is no block-wide barrier anywhere.
+//   k_seg_scan    exclusive prefix of the per-segment output sizes (bytes, blocks, records, index-key bytes).
+//   k_emit        one warp per segment builds the output blocks: heads and values are gathered into a shared-memory
+//                 block buffer (16-byte global loads, byte-exact placement), restart array and padding are appended and
+//                 the finished block leaves with ONE bulk TMA store; the new run's index is written alongside.
+//   Output blocks stay contiguous and in key order; every segment starts a new block.
+#pragma once
+#include "group.cuh"
+
+namespace pgs {
+
+constexpr uint32_t kSegRecCost = 256;          // planner weight = block bytes + 256 per record
+constexpr uint64_t kSegWeight = 128ull << 10;  // segment budget (about 240 records of 300 bytes)
+constexpr uint32_t kWalkThreads = 128;
+constexpr uint32_t kEmitThreads = 128;
+
+enum : uint32_t { DF_NEWBLOCK = 1, DF_REWRITE = 2, DF_BIG = 4 };
+
+// one per surviving record, written by k_walk, read by k_emit
+struct __align__(16) Desc {
+    unsigned long long loc; // bits 0..39 byte offset of the value inside its run, 40..43 run, 44..59 head bytes, 60..63 DF_*
+    uint32_t vlen;          // value bytes to copy (0 for a tombstone)
+    uint32_t aux;           // DF_NEWBLOCK: length of the previous block's last user key (stored in the head stream before this head)
+};
+static_assert(sizeof(Desc) == 16, "Desc");
+
+struct SegLayout { // where a segment's scratch lives (k_seg_layout)
+    unsigned long long desc_off; // index of its first descriptor
+    unsigned long long head_off; // byte offset of its head stream
+};
+struct __align__(16) SegAgg { // what a segment produced (k_walk)
+    unsigned long long out_bytes; // sum of 16-aligned block sizes
+    uint32_t n_entries, n_blocks, keyb, head_bytes, last_klen, pad;
+};
+struct __align__(16) SegBase { // exclusive prefixes over the segments (k_seg_scan)
+    unsigned long long bytes;
+    uint32_t blocks, recs, keyb, pad;
+};
+
+struct MergeStats {
+    unsigned long long in_records, in_bytes, out_records, out_bytes;
+    unsigned long long dropped_shadowed, dropped_tombstone, dropped_expired, dropped_user, dropped_stale, ttl_rewritten;
+    unsigned long long out_tomb, out_raw_key, out_raw_val, spare0, spare1, spare2;
+    unsigned long long max_ukey, max_vlen, max_blk_size, max_blk_rec, max_seq, min_seq_inv; // maxima (min_seq kept as ~min)
+    unsigned long long tot_bytes, tot_blocks, tot_recs, tot_keyb; // k_seg_scan
+    uint32_t error, error_seg;
+};
+enum { ST_IN_REC = 0, ST_IN_BYTES, ST_OUT_REC, ST_OUT_BYTES, ST_SHADOW, ST_TOMB, ST_EXPIRED, ST_USER, ST_STALE, ST_TTL,
+       ST_OUT_TOMB, ST_OUT_KEY, ST_OUT_VAL };
+enum { SM_UKEY = 0, SM_VLEN, SM_BLK_SIZE, SM_BLK_REC, SM_MAX_SEQ, SM_MIN_SEQ_INV };
+
+struct MergeParams {
+    RunDev runs[kMaxRuns];
+    uint32_t k;
+    // plan
+    uint32_t *split_pos; // [(Q+1)*k]
+    uint32_t *split_ref; // [Q+1]  run<<28 | block
+    uint32_t Q;
+    unsigned long long tile_weight;
+    uint32_t rec_cost;
+    uint32_t total_blocks;
+    // scratch
+    SegLayout *seg;
+    SegAgg *agg;
+    SegBase *base;
+    Desc *desc;
+    uint8_t *heads;
+    unsigned long long desc_cap, head_cap;
+    uint32_t *ticket; // [0] k_walk, [1] k_emit
+    uint32_t KS;      // user-key capacity of a key row (multiple of 4)
+    uint32_t KSW;     // 32-bit words per key row
+    uint32_t group_smem, emit_warp_smem, blk_buf, head_stage;
+    // filter + policy
+    uint32_t now, enabled, validate_hash, data_version, default_ttl;
+    int32_t pidx, partition_version;
+    const uint8_t *ops;
+    uint32_t n_ops;
+    uint32_t bottommost, block_size, restart_interval;
+    const unsigned long long *crc_table;
+    // output run
+    uint8_t *out_data;
+    unsigned long long out_cap;
+    unsigned long long *out_blk_off;
+    uint32_t *out_blk_size, *out_blk_rec, *out_ikey_off, *out_rec_off;
+    uint8_t *out_ikeys;
+    uint32_t out_blk_cap, out_ikey_cap;
+    unsigned long long out_rec_cap;
+    MergeStats *stats;
+};
+
+// ---- launch geometry and buffer bounds (host side; shared with the CPU simulation driver under tools/simt) -----------------
+struct CompactTotals { // sums / maxima over the input runs' pgs_run_info
+    uint32_t max_ukey, max_blk, max_blk_rec;
+    uint64_t total_blocks, n_rec, raw_key, raw_val, in_block_bytes;
+};
+struct CompactGeometry {
+    uint32_t G, walk_dyn, emit_warps, emit_dyn;
+    uint64_t blk_cap, out_cap, ikey_cap;
+};
+// fills the derived fields of P (P.k, P.block_size, P.restart_interval must be set); false = not supported
+inline bool compact_geometry(MergeParams &P, const CompactTotals &T, uint32_t max_smem, CompactGeometry &geo)
+{
+    const uint32_t k = P.k;
+    P.total_blocks = (uint32_t)T.total_blocks;
+    P.KS = T.max_ukey < 4 ? 4u : ((T.max_ukey + 3) & ~3u);
+    P.KSW = (P.KS + 8) / 4 + 1;
+    geo.G = k <= 8 ? 8 : 16;
+    P.group_smem = (uint32_t)((k * sizeof(CurState) + (size_t)(k + 4) * P.KSW * 4 + 15) & ~(size_t)15);
+    geo.walk_dyn = 2048 + (kWalkThreads / geo.G) * P.group_smem;
+    if (geo.walk_dyn > max_smem) return false;
+    const uint32_t hs = (2 * P.KS + 64 + 15) & ~15u;
+    P.head_stage = hs < 2048 ? 2048u : hs;
+    // the block buffers of k_emit: two per warp; an entry that does not fit a buffer gets a block of its own, written in place
+    const uint32_t other = 528 + P.head_stage + 32;
+    const uint32_t RI = P.restart_interval;
+    uint32_t blk_buf = (P.block_size + 24 + 15) & ~15u;
+    if (2ull * blk_buf + other + 4ull * (blk_buf / (11 * RI) + 4) + 64 > max_smem) { // huge block_size: cut smaller blocks
+        if (max_smem < other + 4096) return false;
+        blk_buf = (uint32_t)(((max_smem - other - 128) * 11ull / 24)) & ~15u;
+        if (P.block_size > blk_buf - 24) P.block_size = blk_buf - 24;
+    }
+    P.blk_buf = blk_buf;
+    P.emit_warp_smem = (uint32_t)((2ull * blk_buf + other + 4ull * (blk_buf / (11 * RI) + 4) + 15) & ~15ull);
+    geo.emit_warps = max_smem / P.emit_warp_smem;
+    if (geo.emit_warps > kEmitThreads / 32) geo.emit_warps = kEmitThreads / 32;
+    if (geo.emit_warps == 0) return false;
+    geo.emit_dyn = geo.emit_warps * P.emit_warp_smem;
+    // segments
+    P.rec_cost = kSegRecCost;
+    P.tile_weight = kSegWeight;
+    const uint64_t W_total = T.in_block_bytes + T.n_rec * P.rec_cost;
+    uint64_t Q = (W_total + P.tile_weight - 1) / P.tile_weight;
+    if (Q == 0) Q = 1;
+    if (Q > 0x7FFFFFF0ull) return false;
+    P.Q = (uint32_t)Q;
+    // output capacity (every segment starts a new block; two neighbouring blocks of a segment hold more than block_size bytes)
+    const uint64_t raw_total = T.raw_key + T.raw_val + 23 * T.n_rec;
+    geo.blk_cap = 2 * (raw_total / P.block_size) + Q + 2;
+    uint64_t out_cap = raw_total + 19 * geo.blk_cap + 4 * (T.n_rec / RI + geo.blk_cap) + 256;
+    geo.out_cap = (out_cap + 255) & ~255ull;
+    uint64_t ik = geo.blk_cap * (uint64_t)(T.max_ukey ? T.max_ukey : 1);
+    if (ik > T.raw_key) ik = T.raw_key;
+    geo.ikey_cap = ik + 16;
+    if (geo.blk_cap > 0xFFFFFFF0ull || geo.ikey_cap > 0xFFFFFFF0ull || T.n_rec > 0xFFFFFFF0ull) return false;
+    P.out_cap = geo.out_cap;
+    P.out_blk_cap = (uint32_t)geo.blk_cap;
+    P.out_ikey_cap = (uint32_t)geo.ikey_cap;
+    P.out_rec_cap = T.n_rec;
+    // scratch: the blocks on a segment boundary are read by both neighbours
+    const uint64_t Nb = T.n_rec + Q * k * (uint64_t)T.max_blk_rec;
+    const uint64_t Bb = T.in_block_bytes + Q * k * ((uint64_t)T.max_blk + 16);
+    const uint64_t per_head = 15 + P.KS + 8 + 4;
+    P.desc_cap = Nb + 1;
+    P.head_cap = Nb * per_head + (2 * (Bb + Nb * per_head) / P.block_size + 2 * Q + 2) * (uint64_t)(P.KS + 8) + 64 * Q + 64;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_plan
+// ------------------------------------------------------------------------------------------------
+PGS_DEV unsigned long long run_weight(const RunDev &r, uint32_t pos, uint32_t rec_cost)
+{
+    return r.blk_off[pos] + (unsigned long long)r.blk_rec[pos] * rec_cost;
+}
+
+__global__ void __launch_bounds__(256) k_plan(const __grid_constant__ MergeParams P)
+{
+    uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gt >= P.total_blocks) return;
+    uint32_t i = 0, b = gt;
+    while (b >= P.runs[i].nb) { b -= P.runs[i].nb; i++; }
+    const RunDev &ri = P.runs[i];
+    const uint8_t *U = ri.ikeys + ri.ikey_off[b];
+    uint32_t ulen = ri.ikey_off[b + 1] - ri.ikey_off[b];
+    uint32_t pos[kMaxRuns];
+    unsigned long long Wb = 0, W = 0;
+    for (uint32_t j = 0; j < P.k; j++) {
+        const RunDev &rj = P.runs[j];
+        uint32_t lo = 0, hi = rj.nb; // upper bound: #blocks with last key <= U
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            const uint8_t *kp = rj.ikeys + rj.ikey_off[mid];
+            uint32_t kl = rj.ikey_off[mid + 1] - rj.ikey_off[mid];
+            if (cmp_bytes4(kp, kl, U, ulen) <= 0) lo = mid + 1; else hi = mid;
+        }
+        uint32_t ub = lo, lb = lo;
+        while (lb > 0) {
+            const uint8_t *kp = rj.ikeys + rj.ikey_off[lb - 1];
+            uint32_t kl = rj.ikey_off[lb] - rj.ikey_off[lb - 1];
+            if (cmp_bytes4(kp, kl, U, ulen) != 0) break;
+            lb--;
+        }
+        pos[j] = ub;
+        W += run_weight(rj, ub, P.rec_cost);
+        Wb += run_weight(rj, lb, P.rec_cost);
+    }
+    unsigned long long q_lo = Wb / P.tile_weight + 1, q_hi = W / P.tile_weight;
+    if (q_hi > P.Q - 1) q_hi = P.Q - 1;
+    for (unsigned long long q = q_lo; q <= q_hi; q++) {
+        for (uint32_t j = 0; j < P.k; j++) P.split_pos[q * P.k + j] = pos[j];
+        P.split_ref[q] = (i << 28) | b;
+    }
+}
+
+// slice of run j that segment q may touch: blocks [lo, hi_ex); blocks >= chk may hold keys above the upper bound
+PGS_DEV bool seg_slice(const MergeParams &P, uint32_t q, uint32_t j, uint32_t &lo, uint32_t &hi_ex, uint32_t &chk)
+{
+    const RunDev &r = P.runs[j];
+    const bool first = q == 0, last = q == P.Q - 1;
+    lo = first ? 0 : P.split_pos[(size_t)q * P.k + j];
+    const uint32_t hi = last ? r.nb : P.split_pos[(size_t)(q + 1) * P.k + j];
+    if (lo == 0xFFFFFFFFu || hi == 0xFFFFFFFFu || lo > r.nb || hi > r.nb || lo > hi) { lo = hi_ex = 0; chk = 0; return false; }
+    hi_ex = last ? r.nb : (hi + 1 < r.nb ? hi + 1 : r.nb);
+    chk = last ? 0xFFFFFFFFu : hi;
+    return true;
+}
+
+// upper bounds of a segment's scratch use, from its input slice: records and block bytes it may read
+PGS_HD unsigned long long head_bound(unsigned long long n_in, unsigned long long in_bytes, uint32_t KS, uint32_t block_size)
+{
+    const unsigned long long per_head = 15 + KS + 8 + 4; // varints | whole internal key | rewritten expire_ts
+    unsigned long long blocks = 2 * (in_bytes + n_in * per_head) / block_size + 2;
+    if (blocks > n_in + 1) blocks = n_in + 1;
+    return n_in * per_head + blocks * (unsigned long long)(KS + 8) + 64;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_seg_layout: one CTA; per segment the offsets of its descriptor array and head stream (exclusive scans of the bounds)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_seg_layout(const __grid_constant__ MergeParams P)
+{
+    PGS_SMEM_STATIC(unsigned long long s_d[33]);
+    PGS_SMEM_STATIC(unsigned long long s_h[33]);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const uint32_t per = (P.Q + blockDim.x - 1) / blockDim.x;
+    const uint32_t q0 = min(tid * per, P.Q), q1 = min(q0 + per, P.Q);
+    auto bounds = [&](uint32_t q, unsigned long long &nd, unsigned long long &nh) {
+        unsigned long long n_in = 0, in_bytes = 0;
+        bool ok = true;
+        for (uint32_t j = 0; j < P.k; j++) {
+            uint32_t lo, hi_ex, chk;
+            ok &= seg_slice(P, q, j, lo, hi_ex, chk);
+            n_in += P.runs[j].blk_rec[hi_ex] - P.runs[j].blk_rec[lo];
+            in_bytes += P.runs[j].blk_off[hi_ex] - P.runs[j].blk_off[lo];
+        }
+        if (!ok) { atomicMax(&P.stats->error, (uint32_t)PGS_ABORTED); atomicMin(&P.stats->error_seg, q); }
+        nd = n_in;
+        nh = head_bound(n_in, in_bytes, P.KS, P.block_size);
+    };
+    unsigned long long ld = 0, lh = 0;
+    for (uint32_t q = q0; q < q1; q++) { unsigned long long a, b; bounds(q, a, b); ld += a; lh += b; }
+    unsigned long long id = ld, ih = lh;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        unsigned long long a = __shfl_up_sync(kFull, id, d), b = __shfl_up_sync(kFull, ih, d);
+        if (lane >= d) { id += a; ih += b; }
+    }
+    if (lane == 31) { s_d[warp] = id; s_h[warp] = ih; }
+    __syncthreads();
+    unsigned long long wd = lane < nw ? s_d[lane] : 0, wh = lane < nw ? s_h[lane] : 0, xd = wd, xh = wh;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        unsigned long long a = __shfl_up_sync(kFull, xd, d), b = __shfl_up_sync(kFull, xh, d);
+        if (lane >= d) { xd += a; xh += b; }
+    }
+    unsigned long long pd = __shfl_sync(kFull, xd - wd, (int)warp) + id - ld, ph = __shfl_sync(kFull, xh - wh, (int)warp) + ih - lh;
+    const unsigned long long td = __shfl_sync(kFull, xd, 31), th = __shfl_sync(kFull, xh, 31);
+    if (tid == 0 && (td > P.desc_cap || th > P.head_cap)) { atomicMax(&P.stats->error, (uint32_t)PGS_ABORTED); atomicMin(&P.stats->error_seg, 0u); }
+    for (uint32_t q = q0; q < q1; q++) {
+        unsigned long long a, b;
+        bounds(q, a, b);
+        P.seg[q].desc_off = pd;
+        P.seg[q].head_off = ph;
+        pd += a;
+        ph += b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// compaction filter on the device
+// ------------------------------------------------------------------------------------------------
+PGS_DEV bool dev_pattern_match(const uint8_t *v, uint32_t vl, uint32_t match_type, const uint8_t *pat, uint32_t pl)
+{
+    // string_pattern_match: compaction_filter_rule.cpp:31-54 (empty pattern never matches)
+    if (pl == 0 || vl < pl) return false;
+    if (match_type == MATCH_PREFIX) {
+        for (uint32_t i = 0; i < pl; i++) if (v[i] != pat[i]) return false;
+        return true;
+    }
+    if (match_type == MATCH_POSTFIX) {
+        const uint8_t *s = v + vl - pl;
+        for (uint32_t i = 0; i < pl; i++) if (s[i] != pat[i]) return false;
+        return true;
+    }
+    if (match_type == MATCH_ANYWHERE) {
+        for (uint32_t s = 0; s + pl <= vl; s++) {
+            uint32_t i = 0;
+            while (i < pl && v[s + i] == pat[i]) i++;
+            if (i == pl) return true;
+        }
+        return false;
+    }
+    return false;
+}
+
+PGS_DEV uint32_t ld_u32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+PGS_DEV uint32_t ld_u16(const uint8_t *p) { return p[0] | (p[1] << 8); }
+
+// user_specified_operation_filter: key_ttl_compaction_filter.h:94-108 over the binary ops table.
+// Every op sees the value as of entry (entry_ts); returns true when a delete op fired.
+PGS_DEV bool dev_user_ops(const MergeParams &P, const uint8_t *hk, uint32_t hkl, const uint8_t *sk, uint32_t skl,
+                          uint32_t entry_ts, uint32_t &new_ts, bool &changed)
+{
+    const uint8_t *p = P.ops + 4;
+    for (uint32_t o = 0; o < P.n_ops; o++) {
+        uint32_t op_type = p[0], ttl_type = p[1], n_rules = ld_u16(p + 2), ttl_value = ld_u32(p + 4);
+        p += 8;
+        bool all = n_rules > 0; // all_rules_match: empty rule set => false (compaction_operation.cpp:37-39)
+        for (uint32_t r = 0; r < n_rules; r++) {
+            uint32_t rt = p[0], mt = p[1], pl = ld_u16(p + 2), start_ttl = ld_u32(p + 4), stop_ttl = ld_u32(p + 8);
+            const uint8_t *pat = p + 12;
+            p += 12 + ((pl + 3) & ~3u);
+            if (!all) continue;
+            bool m;
+            if (rt == RULE_HASHKEY) m = dev_pattern_match(hk, hkl, mt, pat, pl);
+            else if (rt == RULE_SORTKEY) m = dev_pattern_match(sk, skl, mt, pat, pl);
+            else { // ttl_range_rule::match, compaction_filter_rule.cpp:76-90 (u32 arithmetic)
+                if (entry_ts == 0 && start_ttl == 0 && stop_ttl == 0) m = true;
+                else m = (uint32_t)(start_ttl + P.now) <= entry_ts && (uint32_t)(stop_ttl + P.now) >= entry_ts;
+            }
+            all = m;
+        }
+        if (!all) continue;
+        if (op_type == OP_DELETE) return true; // delete_key::filter
+        // update_ttl::filter, compaction_operation.cpp:77-113
+        uint32_t ts;
+        if (ttl_type == TTL_FROM_NOW) ts = P.now + ttl_value;
+        else if (ttl_type == TTL_FROM_CURRENT) { if (entry_ts == 0) continue; ts = ttl_value + entry_ts; }
+        else if (ttl_type == TTL_TIMESTAMP) ts = ttl_value - kEpochBegin;
+        else continue;
+        new_ts = ts;
+        changed = true;
+    }
+    return false;
+}
+
+PGS_DEV unsigned long long dev_crc64(const unsigned long long *tab, const uint8_t *p, uint32_t n)
+{
+    unsigned long long c = ~0ull; // init 0 -> ~init
+    for (uint32_t i = 0; i < n; i++) c = tab[(uint8_t)(c ^ p[i])] ^ (c >> 8);
+    return ~c;
+}
+
+// KeyWithTTLCompactionFilter::Filter (key_ttl_compaction_filter.h:55-92).  expire_ts = the value's BE32 header field.
+// returns 0 keep, 1 expired, 2 user op, 3 stale split data
+PGS_DEV uint32_t dev_filter(const MergeParams &P, const unsigned long long *crc_tab, const uint8_t *ukey, uint32_t klen,
+                            uint32_t expire_ts, uint32_t vlen, uint32_t &new_ts, bool &changed)
+{
+    changed = false;
+    if (!P.enabled || klen < 2 || vlen < 4) return 0;
+    if (P.default_ttl != 0 && expire_ts == 0) {
+        expire_ts = P.now + P.default_ttl;
+        new_ts = expire_ts;
+        changed = true;
+    }
+    uint32_t hkl = ((uint32_t)ukey[0] << 8) | ukey[1];
+    if (hkl > klen - 2) hkl = klen - 2; // malformed key: never read outside it
+    const uint8_t *hk = ukey + 2, *sk = ukey + 2 + hkl;
+    uint32_t skl = klen - 2 - hkl;
+    if (P.n_ops) {
+        if (dev_user_ops(P, hk, hkl, sk, skl, expire_ts, new_ts, changed)) return 2;
+    }
+    if (ts_expired(P.now, expire_ts)) return 1;
+    if (P.validate_hash && P.partition_version >= 0 && P.pidx <= P.partition_version) {
+        // check_pegasus_key_hash: pegasus_key_schema.h:150-183
+        unsigned long long h = hkl > 0 ? dev_crc64(crc_tab, hk, hkl) : dev_crc64(crc_tab, sk, skl);
+        if ((long long)(h & (unsigned long long)(long long)P.partition_version) != (long long)P.pidx) return 3;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_walk
+// ------------------------------------------------------------------------------------------------
+PGS_DEV unsigned long long varint_byte(uint32_t v, uint32_t idx, uint32_t len) { return ((v >> (7 * idx)) & 0x7fu) | (idx + 1 < len ? 0x80u : 0u); }
+
+// order of two cursor heads as internal keys: user key ascending, then trailer (seq, type) descending, then run index
+template <uint32_t G>
+PGS_DEV bool head_before(const Grp<G> &g, const CurState *cs, const uint32_t *rows, uint32_t KSW, uint32_t a, uint32_t b, uint32_t &dpos, bool &by_byte)
+{
+    const uint32_t la = cs[a].klen - 8, lb = cs[b].klen - 8;
+    const int c = row_cmp(g, rows + a * KSW, la, rows + b * KSW, lb, dpos);
+    by_byte = c != 0 && dpos < (la < lb ? la : lb);
+    if (c) return c < 0;
+    const unsigned long long ta = cur_trailer(&cs[a]), tb = cur_trailer(&cs[b]);
+    if (ta != tb) return ta > tb;
+    return a < b;
+}
+
+template <uint32_t G>
+PGS_DEV void walk_segment(const MergeParams &P, const Grp<G> &g, uint32_t q, CurState *cs, uint32_t *rows, const unsigned long long *crc,
+                          unsigned long long &acc0, unsigned long long &acc1, unsigned long long &accm)
+{
+    const uint32_t k = P.k, KS = P.KS, KSW = P.KSW, RI = P.restart_interval, BS = P.block_size;
+    uint32_t *rowA = rows + k * KSW, *rowB = rowA + KSW, *rowLO = rowB + KSW, *rowHI = rowLO + KSW;
+    const bool first = q == 0, last = q == P.Q - 1;
+    uint32_t err = 0;
+#define STAT_ADD(slot, v) do { if (g.gl == ((slot) % G)) { if ((slot) / G == 0) acc0 += (v); else acc1 += (v); } } while (0)
+#define STAT_MAX(slot, v) do { if (g.gl == ((slot) % G)) { const unsigned long long v_ = (v); if (v_ > accm) accm = v_; } } while (0)
+
+    // ---- boundary keys (U_lo, U_hi] --------------------------------------------------------------------------------
+    uint32_t ulo_len = 0, uhi_len = 0;
+    for (uint32_t which = 0; which < 2; which++) {
+        if (which == 0 ? first : last) continue;
+        const uint32_t ref = P.split_ref[q + which];
+        const uint32_t run = ref >> 28, b = ref & 0x0FFFFFFFu;
+        if (ref == 0xFFFFFFFFu || run >= k || b >= P.runs[run].nb) { err = PGS_ABORTED; break; }
+        const uint32_t off = P.runs[run].ikey_off[b], len = P.runs[run].ikey_off[b + 1] - off;
+        if (len > KS) { err = PGS_ABORTED; break; }
+        uint8_t *dst = (uint8_t *)(which == 0 ? rowLO : rowHI);
+        const uint8_t *src = P.runs[run].ikeys + off;
+        for (uint32_t i = g.gl; i < len; i += G) dst[i] = src[i];
+        if (which == 0) ulo_len = len; else uhi_len = len;
+    }
+    g.sync();
+
+    // ---- open one cursor per run, skip what belongs to the previous segment ---------------------------------------------
+    uint32_t live = 0, my_run = 0xffu; // lanes 0..live-1 hold the runs in merge order
+    uint32_t dpos;
+    bool by_byte;
+    for (uint32_t j = 0; j < k && !err; j++) {
+        uint32_t lo, hi_ex, chk;
+        if (!seg_slice(P, q, j, lo, hi_ex, chk)) { err = PGS_ABORTED; break; }
+        CurState *C = &cs[j];
+        uint32_t *row = rows + j * KSW;
+        err = cur_open(g, P.runs[j], C, row, KS, lo, hi_ex, chk);
+        if (!first)
+            while (!err && C->live && row_cmp(g, row, C->klen - 8, rowLO, ulo_len, dpos) <= 0) err = cur_next(g, P.runs[j], C, row, KS);
+        if (err) break;
+        if (C->live && !last && C->b >= C->chk_from && row_cmp(g, row, C->klen - 8, rowHI, uhi_len, dpos) > 0) {
+            g.sync();
+            if (g.gl == 0) C->live = 0;
+            g.sync();
+        }
+        if (C->live) { // insert into the order
+            uint32_t pos = live;
+            for (uint32_t i = 0; i < live; i++) {
+                const uint32_t r = g.shfl(my_run, i);
+                if (head_before(g, cs, rows, KSW, j, r, dpos, by_byte)) { pos = i; break; }
+            }
+            const uint32_t up = g.shfl_up(my_run, 1);
+            if (g.gl > pos && g.gl <= live) my_run = up;
+            if (g.gl == pos) my_run = j;
+            live++;
+        }
+    }
+
+    // ---- the merge loop --------------------------------------------------------------------------------------------------
+    Desc *desc = P.desc + P.seg[q].desc_off;
+    uint8_t *heads = P.heads + P.seg[q].head_off;
+    uint32_t n_out = 0, hpos = 0;            // descriptors / head-stream bytes written
+    uint32_t blk_n = 0, blk_bytes = 0;       // entries and entry bytes of the open output block
+    uint32_t n_blocks = 0, keyb = 0, lenA = 0;
+    unsigned long long out_bytes = 0;
+    bool have_head = false, head_in_A = false, prev_big = false;
+    uint32_t head_len = 0;
+    uint32_t d1 = 0;
+    bool d1_valid = false;
+    auto close_block = [&]() { // bookkeeping of a finished block (k_emit derives the same numbers)
+        const uint32_t nrest = (blk_n + RI - 1) / RI;
+        const uint32_t size = blk_bytes + 4 * (nrest + 1);
+        out_bytes += (size + kBlockAlign - 1) & ~(unsigned long long)(kBlockAlign - 1);
+        n_blocks++;
+        keyb += lenA;
+        STAT_MAX(SM_BLK_SIZE, size);
+        STAT_MAX(SM_BLK_REC, blk_n);
+    };
+    while (live > 0 && !err) {
+        const uint32_t c = g.shfl(my_run, 0);
+        CurState *C = &cs[c];
+        uint32_t *row = rows + c * KSW;
+        const uint32_t ulen = C->klen - 8, vlen = C->vlen;
+        const unsigned long long tr = cur_trailer(C);
+        const uint32_t type = (uint32_t)tr & 0xffu;
+        STAT_ADD(ST_IN_REC, 1);
+        STAT_ADD(ST_IN_BYTES, ulen + vlen);
+        // (1) an older version of the user key that was just handled?
+        bool shadow = false;
+        uint32_t lcp_head = 0;
+        if (have_head) shadow = row_cmp(g, row, ulen, head_in_A ? rowA : rowB, head_len, lcp_head) == 0;
+        if (shadow) {
+            STAT_ADD(ST_SHADOW, 1);
+        } else {
+            // (2) newest version of a user key: CompactionIterator rules + KeyWithTTLCompactionFilter::Filter
+            bool keep = false, tomb = false, rewrite = false;
+            uint32_t nts = 0, vlen_out = vlen;
+            if (type == PGS_TYPE_VALUE) {
+                bool changed;
+                const uint32_t ets = __byte_perm(C->ets_le, 0, 0x0123);
+                const uint32_t why = dev_filter(P, crc, (const uint8_t *)row, ulen, ets, vlen, nts, changed);
+                if (why) {
+                    if (why == 1) STAT_ADD(ST_EXPIRED, 1); else if (why == 2) STAT_ADD(ST_USER, 1); else STAT_ADD(ST_STALE, 1);
+                    // Decision::kRemove turns the entry into a deletion; it disappears only at the bottommost level
+                    if (!P.bottommost) { keep = tomb = true; vlen_out = 0; }
+                } else {
+                    keep = true;
+                    if (changed) { rewrite = true; STAT_ADD(ST_TTL, 1); }
+                }
+            } else if (type == PGS_TYPE_DELETION) {
+                if (P.bottommost) STAT_ADD(ST_TOMB, 1); else keep = tomb = true;
+            } else {
+                keep = true;
+            }
+            if (keep) {
+                const uint32_t otype = tomb ? (uint32_t)PGS_TYPE_DELETION : type;
+                const unsigned long long seq = (P.bottommost && otype == PGS_TYPE_VALUE) ? 0ull : (tr >> 8);
+                const unsigned long long otr = (seq << 8) | otype;
+                // (3) prefix compression against the previous survivor, block cut
+                bool restart = blk_n % RI == 0;
+                uint32_t shared = 0;
+                if (!restart) {
+                    if (have_head && head_in_A) shared = lcp_head;
+                    else row_cmp(g, row, ulen, rowA, lenA, shared);
+                }
+                uint32_t kd = ulen - shared;
+                uint32_t l1 = varint_len(shared), l2 = varint_len(kd + 8), l3 = varint_len(vlen_out);
+                unsigned long long e = (unsigned long long)l1 + l2 + l3 + kd + 8 + vlen_out;
+                uint32_t flags = 0, aux = 0;
+                if (blk_n > 0 && (prev_big || blk_bytes + e + 4 * ((blk_n + 1 + RI - 1) / RI + 1) > BS)) {
+                    close_block();
+                    blk_n = 0; blk_bytes = 0;
+                    restart = true; shared = 0; kd = ulen;
+                    l1 = 1; l2 = varint_len(kd + 8);
+                    e = (unsigned long long)l1 + l2 + l3 + kd + 8 + vlen_out;
+                }
+                if (blk_n == 0) {
+                    flags |= DF_NEWBLOCK;
+                    if (n_out > 0) { // the finished block's last user key travels in the head stream
+                        aux = lenA;
+                        for (uint32_t i = g.gl; i < lenA; i += G) heads[hpos + i] = ((const uint8_t *)rowA)[i];
+                        hpos += lenA;
+                    }
+                }
+                const bool big = e + 8 > P.blk_buf; // does not fit the block buffer of k_emit: a block of its own, written in place
+                if (big) flags |= DF_BIG;
+                if (e > 0xFFFFFFF0ull || blk_bytes + e > 0xFFFFFFF0ull) { err = PGS_NOT_SUPPORTED; break; }
+                if (rewrite) {
+                    flags |= DF_REWRITE;
+                    if (g.gl < 4) heads[hpos + g.gl] = (uint8_t)(nts >> (8 * (3 - g.gl))); // BE32
+                    hpos += 4;
+                }
+                const uint32_t hv = l1 + l2 + l3, hl = hv + kd + 8;
+                for (uint32_t i = g.gl; i < hl; i += G) {
+                    uint32_t by;
+                    if (i < l1) by = (uint32_t)varint_byte(shared, i, l1);
+                    else if (i < l1 + l2) by = (uint32_t)varint_byte(kd + 8, i - l1, l2);
+                    else if (i < hv) by = (uint32_t)varint_byte(vlen_out, i - l1 - l2, l3);
+                    else if (i < hv + kd) by = ((const uint8_t *)row)[shared + i - hv];
+                    else by = (uint32_t)(otr >> (8 * (i - hv - kd))) & 0xffu;
+                    heads[hpos + i] = (uint8_t)by;
+                }
+                hpos += hl;
+                if (g.gl == 0) {
+                    Desc d;
+                    d.loc = (C->base + C->voff) | ((unsigned long long)c << 40) | ((unsigned long long)hl << 44) | ((unsigned long long)flags << 60);
+                    d.vlen = vlen_out;
+                    d.aux = aux;
+                    *reinterpret_cast<uint4 *>(&desc[n_out]) = *reinterpret_cast<const uint4 *>(&d);
+                }
+                n_out++;
+                blk_n++;
+                blk_bytes += (uint32_t)e;
+                prev_big = big;
+                STAT_ADD(ST_OUT_REC, 1);
+                STAT_ADD(ST_OUT_BYTES, ulen + vlen_out);
+                STAT_ADD(ST_OUT_KEY, ulen);
+                STAT_ADD(ST_OUT_VAL, vlen_out);
+                if (otype == PGS_TYPE_DELETION) STAT_ADD(ST_OUT_TOMB, 1);
+                STAT_MAX(SM_UKEY, ulen);
+                STAT_MAX(SM_VLEN, vlen_out);
+                STAT_MAX(SM_MAX_SEQ, seq);
+                STAT_MAX(SM_MIN_SEQ_INV, ~seq);
+                g.sync(); // every lane has read the previous survivor's key (head-stream copy above)
+                for (uint32_t w = g.gl; 4 * w < ulen; w += G) rowA[w] = row[w];
+                lenA = ulen;
+                head_in_A = true;
+            } else {
+                g.sync();
+                for (uint32_t w = g.gl; 4 * w < ulen; w += G) rowB[w] = row[w];
+                head_in_A = false;
+            }
+            have_head = true;
+            head_len = ulen;
+            g.sync();
+        }
+        // (4) advance the cursor and restore the merge order
+        err = cur_next(g, P.runs[c], C, row, KS);
+        if (err) break;
+        bool alive = C->live != 0;
+        if (alive && !last && C->b >= C->chk_from && row_cmp(g, row, C->klen - 8, rowHI, uhi_len, dpos) > 0) alive = false;
+        if (!alive) {
+            const uint32_t dn = g.shfl_down(my_run, 1);
+            if (g.gl + 1 < live) my_run = dn;
+            live--;
+            d1_valid = false;
+        } else if (live > 1) {
+            // The key differs from the runner-up's at byte d1 < shared: the bytes up to d1 did not change, neither does the order.
+            if (!(d1_valid && C->shared > d1 && C->klen - 8 > d1)) {
+                uint32_t pos = 0;
+                d1_valid = false;
+                for (uint32_t i = 1; i < live; i++) {
+                    const uint32_t r = g.shfl(my_run, i);
+                    if (head_before(g, cs, rows, KSW, c, r, dpos, by_byte)) {
+                        if (i == 1) { d1_valid = by_byte; d1 = dpos; }
+                        break;
+                    }
+                    pos = i;
+                }
+                if (pos > 0) {
+                    const uint32_t dn = g.shfl_down(my_run, 1);
+                    if (g.gl < pos) my_run = dn;
+                    if (g.gl == pos) my_run = c;
+                }
+            }
+        }
+    }
+    if (!err && blk_n > 0) {
+        close_block();
+        for (uint32_t i = g.gl; i < lenA; i += G) heads[hpos + i] = ((const uint8_t *)rowA)[i];
+        hpos += lenA;
+    }
+    if (err) {
+        if (g.gl == 0) { atomicMax(&P.stats->error, err); atomicMin(&P.stats->error_seg, q); }
+        n_out = 0; n_blocks = 0; keyb = 0; out_bytes = 0; hpos = 0; lenA = 0;
+    }
+    if (g.gl == 0) {
+        SegAgg a;
+        a.out_bytes = out_bytes; a.n_entries = n_out; a.n_blocks = n_blocks; a.keyb = keyb; a.head_bytes = hpos; a.last_klen = lenA; a.pad = 0;
+        P.agg[q] = a;
+    }
+#undef STAT_ADD
+#undef STAT_MAX
+}
+
+template <uint32_t G>
+__global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ MergeParams P)
+{
+    PGS_SMEM_DYN(dyn);
+    const Grp<G> g;
+    constexpr uint32_t NGW = 32 / G; // groups per warp
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long *crc = (unsigned long long *)dyn; // 2 KB, only filled when the stale-split check is on
+    if (P.validate_hash)
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) crc[i] = P.crc_table[i];
+    __syncthreads();
+    uint8_t *gs = dyn + 2048 + (size_t)(warp * NGW + g.shift / G) * P.group_smem;
+    CurState *cs = (CurState *)gs;
+    uint32_t *rows = (uint32_t *)(gs + (size_t)P.k * sizeof(CurState));
+    unsigned long long acc0 = 0, acc1 = 0, accm = 0;
+    for (;;) {
+        uint32_t t0 = 0;
+        if (lane == 0) t0 = atomicAdd(P.ticket, NGW);
+        t0 = __shfl_sync(kFull, t0, 0);
+        if (t0 >= P.Q) break;
+        const uint32_t q = t0 + g.shift / G;
+        if (q < P.Q) walk_segment<G>(P, g, q, cs, rows, crc, acc0, acc1, accm);
+        __syncwarp();
+    }
+    // statistics: lane s % G of a group holds counter s
+    unsigned long long *st = &P.stats->in_records;
+    if (g.gl < 16 && acc0) atomicAdd(st + g.gl, acc0);
+    if (g.gl + G < 16 && acc1) atomicAdd(st + g.gl + G, acc1);
+    if (g.gl < 6 && accm) atomicMax(&P.stats->max_ukey + g.gl, accm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_seg_scan: one CTA; exclusive prefixes of the segments' output sizes, totals, index sentinels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_seg_scan(const __grid_constant__ MergeParams P)
+{
+    PGS_SMEM_STATIC(unsigned long long s_w[4][33]);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const uint32_t per = (P.Q + blockDim.x - 1) / blockDim.x;
+    const uint32_t q0 = min(tid * per, P.Q), q1 = min(q0 + per, P.Q);
+    unsigned long long loc[4] = {0, 0, 0, 0};
+    for (uint32_t q = q0; q < q1; q++) {
+        const SegAgg a = P.agg[q];
+        loc[0] += a.out_bytes; loc[1] += a.n_blocks; loc[2] += a.n_entries; loc[3] += a.keyb;
+    }
+    unsigned long long inc[4], pre[4], tot[4];
+#pragma unroll
+    for (uint32_t x = 0; x < 4; x++) {
+        inc[x] = loc[x];
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            unsigned long long o = __shfl_up_sync(kFull, inc[x], d);
+            if (lane >= d) inc[x] += o;
+        }
+        if (lane == 31) s_w[x][warp] = inc[x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t x = 0; x < 4; x++) {
+        unsigned long long w = lane < nw ? s_w[x][lane] : 0, ws = w;
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            unsigned long long o = __shfl_up_sync(kFull, ws, d);
+            if (lane >= d) ws += o;
+        }
+        tot[x] = __shfl_sync(kFull, ws, 31);
+        pre[x] = __shfl_sync(kFull, ws - w, (int)warp) + inc[x] - loc[x];
+    }
+    for (uint32_t q = q0; q < q1; q++) {
+        const SegAgg a = P.agg[q];
+        SegBase b;
+        b.bytes = pre[0]; b.blocks = (uint32_t)pre[1]; b.recs = (uint32_t)pre[2]; b.keyb = (uint32_t)pre[3]; b.pad = 0;
+        P.base[q] = b;
+        pre[0] += a.out_bytes; pre[1] += a.n_blocks; pre[2] += a.n_entries; pre[3] += a.keyb;
+    }
+    if (tid == 0) {
+        P.stats->tot_bytes = tot[0]; P.stats->tot_blocks = tot[1]; P.stats->tot_recs = tot[2]; P.stats->tot_keyb = tot[3];
+        if (tot[0] > P.out_cap || tot[1] > P.out_blk_cap || tot[2] > P.out_rec_cap || tot[3] > P.out_ikey_cap) {
+            atomicMax(&P.stats->error, (uint32_t)PGS_ABORTED);
+        } else { // sentinels of the new run's index
+            P.out_blk_off[tot[1]] = tot[0];
+            P.out_blk_rec[tot[1]] = (uint32_t)tot[2];
+            P.out_ikey_off[tot[1]] = (uint32_t)tot[3];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_emit
+// ------------------------------------------------------------------------------------------------
+// 4 bytes at byte offset `off` of a 4-byte aligned shared-memory buffer (readable one word past)
+PGS_DEV uint32_t lds_u32_at(const uint8_t *base4, uint32_t off)
+{
+    const uint32_t *w = (const uint32_t *)base4 + (off >> 2);
+    const uint32_t sh = (off & 3) * 8;
+    return sh ? __funnelshift_r(w[0], w[1], sh) : w[0];
+}
+// shared -> shared copy of t bytes, any alignment on both sides; words are written aligned on the destination
+PGS_DEV void warp_copy_s2s(uint8_t *dst4, uint32_t doff, const uint8_t *src4, uint32_t soff, uint32_t t, uint32_t lane)
+{
+    uint32_t lead = (4 - (doff & 3)) & 3;
+    if (lead > t) lead = t;
+    if (lane < lead) dst4[doff + lane] = src4[soff + lane];
+    const uint32_t d0 = doff + lead, s0 = soff + lead, nw = (t - lead) >> 2, tail = (t - lead) & 3;
+    uint32_t *dw = (uint32_t *)(dst4 + d0);
+    for (uint32_t w = lane; w < nw; w += 32) dw[w] = lds_u32_at(src4, s0 + 4 * w);
+    if (lane < tail) dst4[d0 + 4 * nw + lane] = src4[s0 + 4 * nw + lane];
+}
+
+__global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ MergeParams P)
+{
+    PGS_SMEM_DYN(dyn);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t RI = P.restart_interval;
+    uint8_t *ws = dyn + (size_t)warp * P.emit_warp_smem;
+    uint8_t *bbuf[2] = {ws, ws + P.blk_buf};
+    uint8_t *vst = ws + 2 * (size_t)P.blk_buf;        // 512 + 16 bytes: one window of a value
+    uint8_t *hst = vst + 528;                          // head_stage + 32 bytes: the head-stream bytes of a batch of entries
+    uint32_t *rst = (uint32_t *)(hst + P.head_stage + 32); // restart offsets of the open block
+    uint32_t which = 0;
+
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(P.ticket + 1, 1u);
+        q = __shfl_sync(kFull, q, 0);
+        if (q >= P.Q) break;
+        const SegAgg A = P.agg[q];
+        if (A.n_entries == 0) continue;
+        const SegBase B = P.base[q];
+        const Desc *desc = P.desc + P.seg[q].desc_off;
+        const uint8_t *heads = P.heads + P.seg[q].head_off;
+        unsigned long long blk_start = B.bytes; // where the open block goes
+        uint32_t blk_idx = B.blocks, rec_idx = B.recs, keyb = B.keyb;
+        uint32_t fill = 0, blk_n = 0, blk_rec0 = rec_idx, hpos = 0, err = 0;
+        bool open = false, cur_big = false;
+        uint8_t *buf = bbuf[which];
+
+        auto close_block = [&](const uint8_t *key, uint32_t klen) {
+            const uint32_t nrest = (blk_n + RI - 1) / RI, size = fill + 4 * (nrest + 1);
+            const uint32_t asz = (size + kBlockAlign - 1) & ~(kBlockAlign - 1);
+            if (!cur_big) {
+                for (uint32_t i = lane; i < 4 * (nrest + 1); i += 32) {
+                    const uint32_t v = (i >> 2) < nrest ? rst[i >> 2] : nrest;
+                    buf[fill + i] = (uint8_t)(v >> (8 * (i & 3)));
+                }
+                for (uint32_t i = size + lane; i < asz; i += 32) buf[i] = 0;
+                __syncwarp();
+                fence_proxy_async(); // the block was assembled with ordinary stores; the TMA unit reads it next
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_1d(P.out_data + blk_start, buf, asz);
+                    tma_store_commit();
+                    tma_store_wait_read1(); // the other buffer's store (one block ago) has read its bytes: it may be refilled
+                }
+                which ^= 1;
+                buf = bbuf[which];
+                __syncwarp();
+            } else { // the entry went straight to global memory; so does its one-entry restart array
+                uint8_t *o = P.out_data + blk_start;
+                for (uint32_t i = lane; i < 4 * (nrest + 1); i += 32) {
+                    const uint32_t v = (i >> 2) < nrest ? 0u : nrest; // a block of one entry: restart offset 0
+                    o[fill + i] = (uint8_t)(v >> (8 * (i & 3)));
+                }
+                for (uint32_t i = size + lane; i < asz; i += 32) o[i] = 0;
+            }
+            if (lane == 0) {
+                P.out_blk_off[blk_idx] = blk_start;
+                P.out_blk_size[blk_idx] = size;
+                P.out_blk_rec[blk_idx] = blk_rec0;
+                P.out_ikey_off[blk_idx] = keyb;
+            }
+            for (uint32_t i = lane; i < klen; i += 32) P.out_ikeys[keyb + i] = key[i];
+#ifdef PGS_SIM_TRACE
+            if (lane == 0) fprintf(stderr, "emit seg %u blk %u keyb %u klen %u key ..%.*s big %d\n", q, blk_idx, keyb, klen, 6, key + (klen > 6 ? klen - 6 : 0), (int)cur_big);
+#endif
+            keyb += klen;
+            blk_idx++;
+            blk_start += asz;
+        };
+
+        for (uint32_t e0 = 0; e0 < A.n_entries && !err;) {
+            // ---- a batch of up to 32 descriptors; their head-stream bytes are staged in shared memory ----------------
+            const uint32_t idx = e0 + lane;
+            Desc d;
+            d.loc = 0; d.vlen = 0; d.aux = 0;
+            if (idx < A.n_entries) *reinterpret_cast<uint4 *>(&d) = *reinterpret_cast<const uint4 *>(&desc[idx]);
+            const uint32_t fl_me = (uint32_t)(d.loc >> 60), hl_me = (uint32_t)(d.loc >> 44) & 0xffffu;
+            const uint32_t sb = idx < A.n_entries ? hl_me + ((fl_me & DF_NEWBLOCK) ? d.aux : 0u) + ((fl_me & DF_REWRITE) ? 4u : 0u) : 0u;
+            const uint32_t s_incl = warp_incl_scan(sb, lane);
+            const uint32_t cnt = (uint32_t)__popc(__ballot_sync(kFull, idx < A.n_entries && s_incl <= P.head_stage));
+            if (cnt == 0) { err = PGS_ABORTED; break; }
+            const uint32_t total = __shfl_sync(kFull, s_incl, (int)cnt - 1);
+            const uint8_t *src = heads + hpos;
+            const uint32_t a = (uint32_t)((uintptr_t)src & 15);
+            for (uint32_t i = lane * 16; i < a + total; i += 512) *reinterpret_cast<uint4 *>(hst + i) = *reinterpret_cast<const uint4 *>(src - a + i);
+            __syncwarp();
+            const uint8_t *hs = hst + a;
+            const uint32_t s_excl = s_incl - sb;
+            for (uint32_t i = 0; i < cnt; i++) {
+                const unsigned long long loc = __shfl_sync(kFull, d.loc, (int)i);
+                const uint32_t vlen = __shfl_sync(kFull, d.vlen, (int)i), aux = __shfl_sync(kFull, d.aux, (int)i);
+                uint32_t so = __shfl_sync(kFull, s_excl, (int)i);
+                const uint32_t fl = (uint32_t)(loc >> 60), hl = (uint32_t)(loc >> 44) & 0xffffu, run = (uint32_t)(loc >> 40) & 15u;
+                const unsigned long long voff = loc & ((1ull << 40) - 1);
+                if (fl & DF_NEWBLOCK) {
+#ifdef PGS_SIM_TRACE
+                    if (lane == 0) fprintf(stderr, "  newblock seg %u e %u so %u aux %u a %u total %u cnt %u hpos %u hl %u\n", q, e0 + i, so, aux, a, total, cnt, hpos, hl);
+#endif
+                    if (open) { close_block(hs + so, aux); so += aux; }
+                    open = true;
+                    fill = 0; blk_n = 0; blk_rec0 = rec_idx;
+                    cur_big = (fl & DF_BIG) != 0;
+                }
+                const uint8_t *ntsb = hs + so;
+                if (fl & DF_REWRITE) so += 4;
+                const uint8_t *vsrc = P.runs[run].data + voff;
+                if (lane == 0) {
+                    if (blk_n % RI == 0 && !cur_big) rst[blk_n / RI] = fill;
+                    P.out_rec_off[rec_idx] = fill;
+                }
+                if (!cur_big) {
+                    for (uint32_t x = lane; x < hl; x += 32) buf[fill + x] = hs[so + x];
+                    // the value: 16-byte global loads of the aligned window around it, byte-exact placement from shared memory
+                    uint32_t n = vlen, doff = fill + hl;
+                    const uint8_t *s = vsrc;
+                    while (n > 0) {
+                        const uint32_t va = (uint32_t)((uintptr_t)s & 15);
+                        const uint32_t span = n + va < 512 ? n + va : 512;
+                        if (lane * 16 < span) *reinterpret_cast<uint4 *>(vst + lane * 16) = *reinterpret_cast<const uint4 *>(s - va + lane * 16);
+                        __syncwarp();
+                        const uint32_t t = span - va;
+                        warp_copy_s2s(buf, doff, vst, va, t, lane);
+                        __syncwarp();
+                        s += t; doff += t; n -= t;
+                    }
+                    if ((fl & DF_REWRITE) && vlen >= 4 && lane < 4) buf[fill + hl + lane] = ntsb[lane];
+                } else {
+                    uint8_t *o = P.out_data + blk_start;
+                    for (uint32_t x = lane; x < hl; x += 32) o[fill + x] = hs[so + x];
+                    for (uint32_t x = lane; x < vlen; x += 32) o[fill + hl + x] = vsrc[x];
+                    if ((fl & DF_REWRITE) && vlen >= 4 && lane < 4) o[fill + hl + lane] = ntsb[lane];
+                }
+                fill += hl + vlen;
+                blk_n++;
+                rec_idx++;
+            }
+            __syncwarp(); // the staged heads are consumed
+            hpos += total;
+            e0 += cnt;
+        }
+        if (!err && open) close_block(heads + A.head_bytes - A.last_klen, A.last_klen);
+        if (!err && (blk_start != B.bytes + A.out_bytes || blk_idx != B.blocks + A.n_blocks || keyb != B.keyb + A.keyb)) err = PGS_CORRUPTION; // the two passes disagree
+        if (err && lane == 0) { atomicMax(&P.stats->error, err); atomicMin(&P.stats->error_seg, q); }
+    }
+    if (lane == 0) tma_store_wait_all();
+}
+
+} // namespace pgs

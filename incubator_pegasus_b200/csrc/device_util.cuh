@@ -2,10 +2,20 @@
 // mbarriers (inline PTX), varint decode, byte-string compares, warp/block scans, misaligned
 // warp copies.
 #pragma once
+#ifndef PGS_SIM
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "format.h"
+
+// PGS_SIM: the same sources compiled by g++ against tools/simt/simt.h (a host-side SIMT interpreter used by the CPU tests
+// of the kernels' logic); inline PTX is replaced by synchronous equivalents there.
+#ifndef PGS_SIM
+#define PGS_SMEM_DYN(name) extern __shared__ __align__(128) uint8_t name[]
+#define PGS_SMEM_STATIC(decl) __shared__ decl
+#define PGS_LAUNCH(kernel, grid, block, dyn, stream, ...) kernel<<<(grid), (block), (dyn), (stream)>>>(__VA_ARGS__)
+#endif
 
 namespace pgs {
 
@@ -15,6 +25,24 @@ constexpr uint32_t kWarp = 32;
 constexpr uint32_t kFull = 0xffffffffu;
 
 // ---- shared-memory addressing / mbarrier / TMA bulk (cp.async.bulk) ----------------------------
+#ifdef PGS_SIM
+PGS_DEV void mbar_init(uint64_t *bar, uint32_t) { *bar = 0; }
+PGS_DEV void mbar_fence_init() {}
+PGS_DEV void mbar_expect_tx(uint64_t *, uint32_t) {}
+PGS_DEV bool mbar_try_wait(uint64_t *, uint32_t) { return true; }
+PGS_DEV void mbar_wait(uint64_t *, uint32_t) {}
+PGS_DEV void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *) { memcpy(smem_dst, gmem_src, bytes); }
+PGS_DEV void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) { memcpy(gmem_dst, smem_src, bytes); }
+PGS_DEV void tma_store_commit() {}
+PGS_DEV void tma_store_wait_read0() {}
+PGS_DEV void tma_store_wait_read1() {}
+PGS_DEV void tma_store_wait_all() {}
+PGS_DEV void fence_proxy_async() {}
+PGS_DEV void async_copy4(void *smem_dst, const void *gmem_src) { memcpy(smem_dst, gmem_src, 4); }
+PGS_DEV void async_copy8(void *smem_dst, const void *gmem_src) { memcpy(smem_dst, gmem_src, 8); }
+PGS_DEV void async_copy_commit() {}
+PGS_DEV void async_copy_wait_all() {}
+#else
 PGS_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 PGS_DEV void mbar_init(uint64_t *bar, uint32_t count)
@@ -51,6 +79,31 @@ PGS_DEV void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, u
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+
+// shared -> global bulk copy through the TMA unit (bulk async-group completion); bytes % 16 == 0, both addresses 16-aligned
+PGS_DEV void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+PGS_DEV void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the source bytes of all but the newest N committed bulk groups have been read (their shared memory may be rewritten)
+PGS_DEV void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+PGS_DEV void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+PGS_DEV void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy (TMA) that reads them next
+PGS_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// small asynchronous global -> shared copies (LDGSTS): the issuing thread does not wait for the data
+PGS_DEV void async_copy4(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+PGS_DEV void async_copy8(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+PGS_DEV void async_copy_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+PGS_DEV void async_copy_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
 
 // ---- varint (RocksDB util/coding.h encoding) ---------------------------------------------------
 // returns bytes consumed, 0 on malformed / out of range

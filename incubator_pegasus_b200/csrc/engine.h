@@ -14,19 +14,6 @@
 
 namespace pgs {
 
-// what kernels see of one HBM-resident sorted run
-struct RunDev {
-    const uint8_t *data;      // blocks, each start 16-aligned; readable up to blk_off[nb] (+slack)
-    const uint64_t *blk_off;  // [nb+1] byte offset of block b; blk_off[nb] = 16-aligned end
-    const uint32_t *blk_size; // [nb]   exact encoded size
-    const uint32_t *blk_rec;  // [nb+1] cumulative record count
-    const uint32_t *ikey_off; // [nb+1] offsets into ikeys
-    const uint8_t *ikeys;     // last user key of every block, back to back
-    const uint32_t *rec_off;  // [n_records] byte offset of every entry inside its block (makes the header walk parallel)
-    uint32_t nb;
-    uint32_t max_ukey_len;
-};
-
 struct Run {
     uint64_t id = 0;
     int32_t level = 0;

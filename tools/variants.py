@@ -27,7 +27,7 @@ for spec in args:
     for i in range(7):
         res = part.compact(ids, out_level=1, bottommost=1, now=synth.NOW, enabled=True, flags=3)
         if i >= 3: ms.append(res.merge_kernel_ms)
-    print(f"== {spec}: kernel_ms {sum(ms)/len(ms):.3f} (min {min(ms):.3f})", flush=True)
+    print(f"== {spec}: kernel_ms {sum(ms)/len(ms):.3f} (min {min(ms):.3f}) walk {res.walk_ms:.3f} emit {res.emit_ms:.3f} plan {res.device_ms - res.merge_kernel_ms:.3f} segs {res.n_tiles}", flush=True)
     os.environ["PGS_PHASE_TIMING"] = "1"
     sys.stderr.flush()
     part.compact(ids, out_level=1, bottommost=1, now=synth.NOW, enabled=True, flags=3)
