@@ -420,16 +420,17 @@ PGS_API int32_t pgs_rrdb_get_many(pgs_server *s, const uint8_t *keys, const uint
                                   pgs_get_result *results, uint64_t *arena_used);
 
 /* write handlers -> memtable (pegasus_server_write.cpp:151-222, rocksdb_wrapper.cpp:129-219).
- * `decree` / `timestamp_us` are the mutation's; expire_ts_seconds as update_request. */
+ * `decree` / `timestamp_us` are the mutation's; expire_ts_seconds as update_request.  Every write carries `now`
+ * (epoch_now): a write that fills the memtable flushes it and may start the L0 compaction, whose filter needs the clock. */
 PGS_API int32_t pgs_rrdb_put(pgs_server *s, pgs_blob raw_key, pgs_blob user_value,
                              uint32_t expire_ts_seconds, int64_t decree, uint64_t timestamp_us,
                              uint32_t now);
-PGS_API int32_t pgs_rrdb_remove(pgs_server *s, pgs_blob raw_key, int64_t decree);
+PGS_API int32_t pgs_rrdb_remove(pgs_server *s, pgs_blob raw_key, int64_t decree, uint32_t now);
 PGS_API int32_t pgs_rrdb_multi_put(pgs_server *s, pgs_blob hash_key, const pgs_blob *sort_keys,
                                    const pgs_blob *values, uint32_t n, uint32_t expire_ts_seconds,
                                    int64_t decree, uint64_t timestamp_us, uint32_t now);
 PGS_API int32_t pgs_rrdb_multi_remove(pgs_server *s, pgs_blob hash_key, const pgs_blob *sort_keys,
-                                      uint32_t n, int64_t decree, int64_t *count);
+                                      uint32_t n, int64_t decree, int64_t *count, uint32_t now);
 /* flush_all_family_columns (pegasus_server_impl.cpp:3471): memtable -> L0 run in HBM, then the
  * L0 trigger check (L0 count >= trigger -> L0(+L1) -> L1 compaction with the filter at `now`).
  * `now` (epoch_now) also feeds the default-TTL substitution of puts (rocksdb_wrapper.cpp:280-288). */
@@ -437,7 +438,14 @@ PGS_API int32_t pgs_rrdb_flush(pgs_server *s, uint32_t now);
 /* do_manual_compact (pegasus_server_impl.cpp:3373-3456): whole-CF CompactRange, bottommost
  * level forced. */
 PGS_API int32_t pgs_rrdb_manual_compact(pgs_server *s, uint32_t now, pgs_compact_result *out);
+/* last_flushed_decree: the newest decree whose data lives in an HBM run (advanced by a memtable flush, like the decree the
+ * reference persists in the SST meta CF); last_committed_decree: the newest decree applied to the memtable.  Nothing here is
+ * durable across a process crash (no WAL / checkpoint yet: SURVEY 8 f4), so neither may drive replication-log GC. */
 PGS_API int64_t pgs_rrdb_last_flushed_decree(pgs_server *s);
+PGS_API int64_t pgs_rrdb_last_committed_decree(pgs_server *s);
+/* drops scan contexts older than 5 minutes (pegasus_server_impl.cpp:1377-1385 schedules the same expiry per context);
+ * also runs implicitly on every scanner call. Returns the number of contexts dropped. */
+PGS_API uint32_t pgs_rrdb_gc(pgs_server *s, uint32_t now);
 
 #ifdef __cplusplus
 }

@@ -208,10 +208,10 @@ def lib() -> C.CDLL:
         "pgs_rrdb_scan": [vp, C.c_int64, C.c_uint32, vp],
         "pgs_rrdb_get_many": [vp, vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp, u64p],
         "pgs_rrdb_put": [vp, Blob, Blob, C.c_uint32, C.c_int64, C.c_uint64, C.c_uint32],
-        "pgs_rrdb_remove": [vp, Blob, C.c_int64],
+        "pgs_rrdb_remove": [vp, Blob, C.c_int64, C.c_uint32],
         "pgs_rrdb_multi_put": [vp, Blob, C.POINTER(Blob), C.POINTER(Blob), C.c_uint32, C.c_uint32, C.c_int64,
                                C.c_uint64, C.c_uint32],
-        "pgs_rrdb_multi_remove": [vp, Blob, C.POINTER(Blob), C.c_uint32, C.c_int64, C.POINTER(C.c_int64)],
+        "pgs_rrdb_multi_remove": [vp, Blob, C.POINTER(Blob), C.c_uint32, C.c_int64, C.POINTER(C.c_int64), C.c_uint32],
         "pgs_rrdb_flush": [vp, C.c_uint32],
         "pgs_rrdb_manual_compact": [vp, C.c_uint32, C.POINTER(CompactResult)],
     }.items():

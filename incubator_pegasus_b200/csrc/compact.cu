@@ -1,5 +1,5 @@
 // compact.cu — host side of level compaction (pgs_compact): sizes the scratch, launches
-// k_plan -> k_seg_layout -> k_walk -> k_seg_scan -> k_emit (compact_kernels.cuh) on the engine stream and installs the
+// k_plan -> k_seg_bounds -> k_seg_layout -> k_walk -> k_seg_scan -> k_emit (compact_kernels.cuh) on the engine stream and installs the
 // merged run.  Replaces DB::CompactRange / the background compaction job (src/server/pegasus_server_impl.cpp:3373-3394).
 #include <algorithm>
 #include <cstdio>
@@ -180,6 +180,7 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     const uint32_t grid_e = (uint32_t)std::min<uint64_t>((Q + geo.emit_warps - 1) / geo.emit_warps, (uint64_t)std::max(1, occ_e) * e->sm_count);
     CK(cudaEventRecord(ev[0], st));
     k_plan<<<(uint32_t)((T.total_blocks + 255) / 256), 256, 0, st>>>(P);
+    k_seg_bounds<<<(uint32_t)((Q + 255) / 256), 256, 0, st>>>(P);
     k_seg_layout<<<1, 1024, 0, st>>>(P);
     CK(cudaEventRecord(ev[1], st));
     walk<<<grid_w, kWalkThreads, geo.walk_dyn, st>>>(P);
@@ -187,7 +188,7 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     k_seg_scan<<<1, 1024, 0, st>>>(P);
     k_emit<<<grid_e, geo.emit_warps * 32, geo.emit_dyn, st>>>(P);
     CK(cudaEventRecord(ev[3], st));
-    e->launches += 5;
+    e->launches += 6;
     CK(cudaMemcpyAsync(&hs, d_stats, sizeof hs, cudaMemcpyDeviceToHost, st));
     cudaError_t se = cudaStreamSynchronize(st);
     if (se != cudaSuccess) { cleanup(); return cuda_fail(se, "compaction kernels"); }
@@ -209,7 +210,7 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     res.dropped_shadowed = hs.dropped_shadowed; res.dropped_tombstone = hs.dropped_tombstone;
     res.dropped_expired = hs.dropped_expired; res.dropped_user = hs.dropped_user; res.dropped_stale = hs.dropped_stale;
     res.ttl_rewritten = hs.ttl_rewritten;
-    res.n_tiles = P.Q; res.n_launches = 5;
+    res.n_tiles = P.Q; res.n_launches = 6;
     res.device_ms = ms_total; res.merge_kernel_ms = ms_merge;
     res.walk_ms = ms_walk; res.emit_ms = ms_emit;
 

@@ -128,12 +128,12 @@ inline bool compact_geometry(MergeParams &P, const CompactTotals &T, uint32_t ma
     P.KSW = (P.KS + 8) / 4 + 1;
     geo.G = k <= 8 ? 8 : 16;
     P.group_smem = (uint32_t)((k * sizeof(CurState) + (size_t)(k + 4) * P.KSW * 4 + 15) & ~(size_t)15);
-    geo.walk_dyn = 2048 + (kWalkThreads / geo.G) * P.group_smem;
+    geo.walk_dyn = 2048 + kMaxRuns * (uint32_t)sizeof(RunDev) + (kWalkThreads / geo.G) * P.group_smem;
     if (geo.walk_dyn > max_smem) return false;
     const uint32_t hs = (2 * P.KS + 64 + 15) & ~15u;
     P.head_stage = hs < 2048 ? 2048u : hs;
     // the block buffers of k_emit: two per warp; an entry that does not fit a buffer gets a block of its own, written in place
-    const uint32_t other = 528 + P.head_stage + 32;
+    const uint32_t other = 4 * 544 + P.head_stage + 32; // kEmitDepth value windows + the head stage
     const uint32_t RI = P.restart_interval;
     uint32_t blk_buf = (P.block_size + 24 + 15) & ~15u;
     if (2ull * blk_buf + other + 4ull * (blk_buf / (11 * RI) + 4) + 64 > max_smem) { // huge block_size: cut smaller blocks
@@ -247,8 +247,26 @@ PGS_HD unsigned long long head_bound(unsigned long long n_in, unsigned long long
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_seg_layout: one CTA; per segment the offsets of its descriptor array and head stream (exclusive scans of the bounds)
+// k_seg_bounds + k_seg_layout: where each segment's descriptor array and head stream live.  One thread per segment computes
+// the bounds of what it may emit (from its input slice); one CTA turns them into offsets with an exclusive scan.
 // ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_seg_bounds(const __grid_constant__ MergeParams P)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.Q) return;
+    unsigned long long n_in = 0, in_bytes = 0;
+    bool ok = true;
+    for (uint32_t j = 0; j < P.k; j++) {
+        uint32_t lo, hi_ex, chk;
+        ok &= seg_slice(P, q, j, lo, hi_ex, chk);
+        n_in += P.runs[j].blk_rec[hi_ex] - P.runs[j].blk_rec[lo];
+        in_bytes += P.runs[j].blk_off[hi_ex] - P.runs[j].blk_off[lo];
+    }
+    if (!ok) { atomicMax(&P.stats->error, (uint32_t)PGS_ABORTED); atomicMin(&P.stats->error_seg, q); }
+    P.seg[q].desc_off = n_in;
+    P.seg[q].head_off = head_bound(n_in, in_bytes, P.KS, P.block_size);
+}
+
 __global__ void __launch_bounds__(1024) k_seg_layout(const __grid_constant__ MergeParams P)
 {
     PGS_SMEM_STATIC(unsigned long long s_d[33]);
@@ -256,21 +274,8 @@ __global__ void __launch_bounds__(1024) k_seg_layout(const __grid_constant__ Mer
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const uint32_t per = (P.Q + blockDim.x - 1) / blockDim.x;
     const uint32_t q0 = min(tid * per, P.Q), q1 = min(q0 + per, P.Q);
-    auto bounds = [&](uint32_t q, unsigned long long &nd, unsigned long long &nh) {
-        unsigned long long n_in = 0, in_bytes = 0;
-        bool ok = true;
-        for (uint32_t j = 0; j < P.k; j++) {
-            uint32_t lo, hi_ex, chk;
-            ok &= seg_slice(P, q, j, lo, hi_ex, chk);
-            n_in += P.runs[j].blk_rec[hi_ex] - P.runs[j].blk_rec[lo];
-            in_bytes += P.runs[j].blk_off[hi_ex] - P.runs[j].blk_off[lo];
-        }
-        if (!ok) { atomicMax(&P.stats->error, (uint32_t)PGS_ABORTED); atomicMin(&P.stats->error_seg, q); }
-        nd = n_in;
-        nh = head_bound(n_in, in_bytes, P.KS, P.block_size);
-    };
     unsigned long long ld = 0, lh = 0;
-    for (uint32_t q = q0; q < q1; q++) { unsigned long long a, b; bounds(q, a, b); ld += a; lh += b; }
+    for (uint32_t q = q0; q < q1; q++) { ld += P.seg[q].desc_off; lh += P.seg[q].head_off; }
     unsigned long long id = ld, ih = lh;
 #pragma unroll
     for (uint32_t d = 1; d < 32; d <<= 1) {
@@ -289,8 +294,7 @@ __global__ void __launch_bounds__(1024) k_seg_layout(const __grid_constant__ Mer
     const unsigned long long td = __shfl_sync(kFull, xd, 31), th = __shfl_sync(kFull, xh, 31);
     if (tid == 0 && (td > P.desc_cap || th > P.head_cap)) { atomicMax(&P.stats->error, (uint32_t)PGS_ABORTED); atomicMin(&P.stats->error_seg, 0u); }
     for (uint32_t q = q0; q < q1; q++) {
-        unsigned long long a, b;
-        bounds(q, a, b);
+        const unsigned long long a = P.seg[q].desc_off, b = P.seg[q].head_off;
         P.seg[q].desc_off = pd;
         P.seg[q].head_off = ph;
         pd += a;
@@ -404,14 +408,26 @@ PGS_DEV uint32_t dev_filter(const MergeParams &P, const unsigned long long *crc_
 // ------------------------------------------------------------------------------------------------
 // k_walk
 // ------------------------------------------------------------------------------------------------
-PGS_DEV unsigned long long varint_byte(uint32_t v, uint32_t idx, uint32_t len) { return ((v >> (7 * idx)) & 0x7fu) | (idx + 1 < len ? 0x80u : 0u); }
-
-// order of two cursor heads as internal keys: user key ascending, then trailer (seq, type) descending, then run index
-template <uint32_t G>
-PGS_DEV bool head_before(const Grp<G> &g, const CurState *cs, const uint32_t *rows, uint32_t KSW, uint32_t a, uint32_t b, uint32_t &dpos, bool &by_byte)
+// the varint32 encoding of v as little-endian bytes in a register (at most 5), len = its length
+PGS_DEV unsigned long long varint_pack(uint32_t v, uint32_t &len)
 {
-    const uint32_t la = cs[a].klen - 8, lb = cs[b].klen - 8;
-    const int c = row_cmp(g, rows + a * KSW, la, rows + b * KSW, lb, dpos);
+    unsigned long long o = 0;
+    uint32_t n = 0;
+    while (v >= 128) { o |= (unsigned long long)((v & 127u) | 128u) << (8 * n); v >>= 7; n++; }
+    o |= (unsigned long long)v << (8 * n);
+    len = n + 1;
+    return o;
+}
+
+// order of two cursor heads as internal keys: user key ascending, then trailer (seq, type) descending, then run index.
+// Whole warp; by_byte = decided by a differing key byte at dpos (the LCP shortcut of the merge loop relies on that).
+template <uint32_t G>
+PGS_DEV bool head_before(const Grp<G> &g, bool en, const CurState *cs, const uint32_t *rows, uint32_t KSW, uint32_t a, uint32_t b, uint32_t &dpos, bool &by_byte)
+{
+    uint32_t la = 0, lb = 0;
+    if (en) { la = cs[a].klen - 8; lb = cs[b].klen - 8; }
+    const int c = row_cmp(g, en, rows + a * KSW, la, rows + b * KSW, lb, dpos);
+    if (!en) { by_byte = false; return false; }
     by_byte = c != 0 && dpos < (la < lb ? la : lb);
     if (c) return c < 0;
     const unsigned long long ta = cur_trailer(&cs[a]), tb = cur_trailer(&cs[b]);
@@ -419,9 +435,11 @@ PGS_DEV bool head_before(const Grp<G> &g, const CurState *cs, const uint32_t *ro
     return a < b;
 }
 
+// One segment per group, all groups of the warp in lock step (see group.cuh): every statement outside an `if (en...)` body is
+// executed by all 32 lanes; `act` marks the groups that still have records.
 template <uint32_t G>
-PGS_DEV void walk_segment(const MergeParams &P, const Grp<G> &g, uint32_t q, CurState *cs, uint32_t *rows, const unsigned long long *crc,
-                          unsigned long long &acc0, unsigned long long &acc1, unsigned long long &accm)
+PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G> &g, bool seg_en, uint32_t q, CurState *cs, uint32_t *rows,
+                          const unsigned long long *crc, unsigned long long &acc0, unsigned long long &acc1, unsigned long long &accm)
 {
     const uint32_t k = P.k, KS = P.KS, KSW = P.KSW, RI = P.restart_interval, BS = P.block_size;
     uint32_t *rowA = rows + k * KSW, *rowB = rowA + KSW, *rowLO = rowB + KSW, *rowHI = rowLO + KSW;
@@ -432,45 +450,59 @@ PGS_DEV void walk_segment(const MergeParams &P, const Grp<G> &g, uint32_t q, Cur
 
     // ---- boundary keys (U_lo, U_hi] --------------------------------------------------------------------------------
     uint32_t ulo_len = 0, uhi_len = 0;
-    for (uint32_t which = 0; which < 2; which++) {
-        if (which == 0 ? first : last) continue;
-        const uint32_t ref = P.split_ref[q + which];
-        const uint32_t run = ref >> 28, b = ref & 0x0FFFFFFFu;
-        if (ref == 0xFFFFFFFFu || run >= k || b >= P.runs[run].nb) { err = PGS_ABORTED; break; }
-        const uint32_t off = P.runs[run].ikey_off[b], len = P.runs[run].ikey_off[b + 1] - off;
-        if (len > KS) { err = PGS_ABORTED; break; }
-        uint8_t *dst = (uint8_t *)(which == 0 ? rowLO : rowHI);
-        const uint8_t *src = P.runs[run].ikeys + off;
-        for (uint32_t i = g.gl; i < len; i += G) dst[i] = src[i];
-        if (which == 0) ulo_len = len; else uhi_len = len;
+    if (seg_en) {
+        for (uint32_t which = 0; which < 2; which++) {
+            if (which == 0 ? first : last) continue;
+            const uint32_t ref = P.split_ref[q + which];
+            const uint32_t run = ref >> 28, b = ref & 0x0FFFFFFFu;
+            if (ref == 0xFFFFFFFFu || run >= k || b >= runs[run].nb) { err = PGS_ABORTED; break; }
+            const uint32_t off = runs[run].ikey_off[b], len = runs[run].ikey_off[b + 1] - off;
+            if (len > KS) { err = PGS_ABORTED; break; }
+            uint8_t *dst = (uint8_t *)(which == 0 ? rowLO : rowHI);
+            const uint8_t *src = runs[run].ikeys + off;
+            for (uint32_t i = g.gl; i < len; i += G) dst[i] = src[i];
+            if (which == 0) ulo_len = len; else uhi_len = len;
+        }
     }
     g.sync();
 
     // ---- open one cursor per run, skip what belongs to the previous segment ---------------------------------------------
-    uint32_t live = 0, my_run = 0xffu; // lanes 0..live-1 hold the runs in merge order
-    uint32_t dpos;
-    bool by_byte;
-    for (uint32_t j = 0; j < k && !err; j++) {
-        uint32_t lo, hi_ex, chk;
-        if (!seg_slice(P, q, j, lo, hi_ex, chk)) { err = PGS_ABORTED; break; }
+    uint32_t live = 0, my_run = 0; // lanes 0..live-1 of a group hold its runs in merge order
+    uint32_t dpos = 0;
+    bool by_byte = false;
+    for (uint32_t j = 0; j < k; j++) {
+        const bool en = seg_en && !err;
+        uint32_t lo = 0, hi_ex = 0, chk = 0;
+        if (en && !seg_slice(P, q, j, lo, hi_ex, chk)) err = PGS_ABORTED;
         CurState *C = &cs[j];
         uint32_t *row = rows + j * KSW;
-        err = cur_open(g, P.runs[j], C, row, KS, lo, hi_ex, chk);
-        if (!first)
-            while (!err && C->live && row_cmp(g, row, C->klen - 8, rowLO, ulo_len, dpos) <= 0) err = cur_next(g, P.runs[j], C, row, KS);
-        if (err) break;
-        if (C->live && !last && C->b >= C->chk_from && row_cmp(g, row, C->klen - 8, rowHI, uhi_len, dpos) > 0) {
-            g.sync();
-            if (g.gl == 0) C->live = 0;
-            g.sync();
+        const uint32_t e1 = cur_open(g, en && !err, runs[j], C, row, KS, lo, hi_ex, chk);
+        if (en && !err) err = e1;
+        for (;;) { // records at or below U_lo belong to the previous segment
+            const bool sk = seg_en && !err && !first && C->live;
+            const int c = row_cmp(g, sk, row, sk ? C->klen - 8 : 0u, rowLO, ulo_len, dpos);
+            const bool more = sk && c <= 0;
+            if (!g.any(more)) break;
+            const uint32_t e2 = cur_next(g, more, runs[j], C, row, KS);
+            if (more) err = e2;
         }
-        if (C->live) { // insert into the order
-            uint32_t pos = live;
-            for (uint32_t i = 0; i < live; i++) {
-                const uint32_t r = g.shfl(my_run, i);
-                if (head_before(g, cs, rows, KSW, j, r, dpos, by_byte)) { pos = i; break; }
-            }
-            const uint32_t up = g.shfl_up(my_run, 1);
+        const bool hi = seg_en && !err && C->live && !last && C->b >= C->chk_from;
+        const int ch = row_cmp(g, hi, row, hi ? C->klen - 8 : 0u, rowHI, uhi_len, dpos);
+        g.sync();
+        if (hi && ch > 0 && g.gl == 0) C->live = 0;
+        g.sync();
+        // insert into the order
+        const bool ins = seg_en && !err && C->live;
+        uint32_t pos = live;
+        bool searching = ins;
+        for (uint32_t i = 0; g.any(searching && i < live); i++) {
+            const uint32_t r = g.shfl(my_run, i);
+            const bool e = searching && i < live;
+            const bool bf = head_before(g, e, cs, rows, KSW, j, r & 15u, dpos, by_byte);
+            if (e && bf) { pos = i; searching = false; }
+        }
+        const uint32_t up = g.shfl_up(my_run, 1);
+        if (ins) {
             if (g.gl > pos && g.gl <= live) my_run = up;
             if (g.gl == pos) my_run = j;
             live++;
@@ -478,10 +510,11 @@ PGS_DEV void walk_segment(const MergeParams &P, const Grp<G> &g, uint32_t q, Cur
     }
 
     // ---- the merge loop --------------------------------------------------------------------------------------------------
-    Desc *desc = P.desc + P.seg[q].desc_off;
-    uint8_t *heads = P.heads + P.seg[q].head_off;
-    uint32_t n_out = 0, hpos = 0;            // descriptors / head-stream bytes written
-    uint32_t blk_n = 0, blk_bytes = 0;       // entries and entry bytes of the open output block
+    Desc *desc = seg_en ? P.desc + P.seg[q].desc_off : nullptr;
+    uint8_t *heads = seg_en ? P.heads + P.seg[q].head_off : nullptr;
+    uint32_t n_out = 0, hpos = 0;                        // descriptors / head-stream bytes written
+    uint32_t blk_n = 0, blk_bytes = 0;                   // entries and entry bytes of the open output block
+    uint32_t to_restart = 0, nrest = 0;                  // entries until the next restart point, restart points so far (no divisions in the loop)
     uint32_t n_blocks = 0, keyb = 0, lenA = 0;
     unsigned long long out_bytes = 0;
     bool have_head = false, head_in_A = false, prev_big = false;
@@ -489,7 +522,6 @@ PGS_DEV void walk_segment(const MergeParams &P, const Grp<G> &g, uint32_t q, Cur
     uint32_t d1 = 0;
     bool d1_valid = false;
     auto close_block = [&]() { // bookkeeping of a finished block (k_emit derives the same numbers)
-        const uint32_t nrest = (blk_n + RI - 1) / RI;
         const uint32_t size = blk_bytes + 4 * (nrest + 1);
         out_bytes += (size + kBlockAlign - 1) & ~(unsigned long long)(kBlockAlign - 1);
         n_blocks++;
@@ -497,26 +529,28 @@ PGS_DEV void walk_segment(const MergeParams &P, const Grp<G> &g, uint32_t q, Cur
         STAT_MAX(SM_BLK_SIZE, size);
         STAT_MAX(SM_BLK_REC, blk_n);
     };
-    while (live > 0 && !err) {
-        const uint32_t c = g.shfl(my_run, 0);
+    for (;;) {
+        const bool act = seg_en && live > 0 && !err;
+        if (!g.any(act)) break;
+        const uint32_t c = g.shfl(my_run, 0) & 15u;
         CurState *C = &cs[c];
         uint32_t *row = rows + c * KSW;
-        const uint32_t ulen = C->klen - 8, vlen = C->vlen;
-        const unsigned long long tr = cur_trailer(C);
-        const uint32_t type = (uint32_t)tr & 0xffu;
-        STAT_ADD(ST_IN_REC, 1);
-        STAT_ADD(ST_IN_BYTES, ulen + vlen);
+        uint32_t ulen = 0, vlen = 0, type = 0;
+        unsigned long long tr = 0;
+        if (act) { ulen = C->klen - 8; vlen = C->vlen; tr = cur_trailer(C); type = (uint32_t)tr & 0xffu; }
         // (1) an older version of the user key that was just handled?
-        bool shadow = false;
         uint32_t lcp_head = 0;
-        if (have_head) shadow = row_cmp(g, row, ulen, head_in_A ? rowA : rowB, head_len, lcp_head) == 0;
-        if (shadow) {
-            STAT_ADD(ST_SHADOW, 1);
-        } else {
-            // (2) newest version of a user key: CompactionIterator rules + KeyWithTTLCompactionFilter::Filter
-            bool keep = false, tomb = false, rewrite = false;
-            uint32_t nts = 0, vlen_out = vlen;
-            if (type == PGS_TYPE_VALUE) {
+        const bool cmp1 = act && have_head;
+        const int c1 = row_cmp(g, cmp1, row, ulen, head_in_A ? rowA : rowB, head_len, lcp_head);
+        const bool shadow = cmp1 && c1 == 0;
+        // (2) newest version of a user key: CompactionIterator rules + KeyWithTTLCompactionFilter::Filter
+        bool keep = false, tomb = false, rewrite = false;
+        uint32_t nts = 0, vlen_out = vlen;
+        if (act) {
+            STAT_ADD(ST_IN_REC, 1);
+            STAT_ADD(ST_IN_BYTES, ulen + vlen);
+            if (shadow) STAT_ADD(ST_SHADOW, 1);
+            else if (type == PGS_TYPE_VALUE) {
                 bool changed;
                 const uint32_t ets = __byte_perm(C->ets_le, 0, 0x0123);
                 const uint32_t why = dev_filter(P, crc, (const uint8_t *)row, ulen, ets, vlen, nts, changed);
@@ -533,133 +567,140 @@ PGS_DEV void walk_segment(const MergeParams &P, const Grp<G> &g, uint32_t q, Cur
             } else {
                 keep = true;
             }
-            if (keep) {
-                const uint32_t otype = tomb ? (uint32_t)PGS_TYPE_DELETION : type;
-                const unsigned long long seq = (P.bottommost && otype == PGS_TYPE_VALUE) ? 0ull : (tr >> 8);
-                const unsigned long long otr = (seq << 8) | otype;
-                // (3) prefix compression against the previous survivor, block cut
-                bool restart = blk_n % RI == 0;
-                uint32_t shared = 0;
-                if (!restart) {
-                    if (have_head && head_in_A) shared = lcp_head;
-                    else row_cmp(g, row, ulen, rowA, lenA, shared);
-                }
-                uint32_t kd = ulen - shared;
-                uint32_t l1 = varint_len(shared), l2 = varint_len(kd + 8), l3 = varint_len(vlen_out);
-                unsigned long long e = (unsigned long long)l1 + l2 + l3 + kd + 8 + vlen_out;
-                uint32_t flags = 0, aux = 0;
-                if (blk_n > 0 && (prev_big || blk_bytes + e + 4 * ((blk_n + 1 + RI - 1) / RI + 1) > BS)) {
-                    close_block();
-                    blk_n = 0; blk_bytes = 0;
-                    restart = true; shared = 0; kd = ulen;
-                    l1 = 1; l2 = varint_len(kd + 8);
-                    e = (unsigned long long)l1 + l2 + l3 + kd + 8 + vlen_out;
-                }
-                if (blk_n == 0) {
-                    flags |= DF_NEWBLOCK;
-                    if (n_out > 0) { // the finished block's last user key travels in the head stream
-                        aux = lenA;
-                        for (uint32_t i = g.gl; i < lenA; i += G) heads[hpos + i] = ((const uint8_t *)rowA)[i];
-                        hpos += lenA;
-                    }
-                }
-                const bool big = e + 8 > P.blk_buf; // does not fit the block buffer of k_emit: a block of its own, written in place
-                if (big) flags |= DF_BIG;
-                if (e > 0xFFFFFFF0ull || blk_bytes + e > 0xFFFFFFF0ull) { err = PGS_NOT_SUPPORTED; break; }
-                if (rewrite) {
-                    flags |= DF_REWRITE;
-                    if (g.gl < 4) heads[hpos + g.gl] = (uint8_t)(nts >> (8 * (3 - g.gl))); // BE32
-                    hpos += 4;
-                }
-                const uint32_t hv = l1 + l2 + l3, hl = hv + kd + 8;
-                for (uint32_t i = g.gl; i < hl; i += G) {
-                    uint32_t by;
-                    if (i < l1) by = (uint32_t)varint_byte(shared, i, l1);
-                    else if (i < l1 + l2) by = (uint32_t)varint_byte(kd + 8, i - l1, l2);
-                    else if (i < hv) by = (uint32_t)varint_byte(vlen_out, i - l1 - l2, l3);
-                    else if (i < hv + kd) by = ((const uint8_t *)row)[shared + i - hv];
-                    else by = (uint32_t)(otr >> (8 * (i - hv - kd))) & 0xffu;
-                    heads[hpos + i] = (uint8_t)by;
-                }
-                hpos += hl;
-                if (g.gl == 0) {
-                    Desc d;
-                    d.loc = (C->base + C->voff) | ((unsigned long long)c << 40) | ((unsigned long long)hl << 44) | ((unsigned long long)flags << 60);
-                    d.vlen = vlen_out;
-                    d.aux = aux;
-                    *reinterpret_cast<uint4 *>(&desc[n_out]) = *reinterpret_cast<const uint4 *>(&d);
-                }
-                n_out++;
-                blk_n++;
-                blk_bytes += (uint32_t)e;
-                prev_big = big;
-                STAT_ADD(ST_OUT_REC, 1);
-                STAT_ADD(ST_OUT_BYTES, ulen + vlen_out);
-                STAT_ADD(ST_OUT_KEY, ulen);
-                STAT_ADD(ST_OUT_VAL, vlen_out);
-                if (otype == PGS_TYPE_DELETION) STAT_ADD(ST_OUT_TOMB, 1);
-                STAT_MAX(SM_UKEY, ulen);
-                STAT_MAX(SM_VLEN, vlen_out);
-                STAT_MAX(SM_MAX_SEQ, seq);
-                STAT_MAX(SM_MIN_SEQ_INV, ~seq);
-                g.sync(); // every lane has read the previous survivor's key (head-stream copy above)
-                for (uint32_t w = g.gl; 4 * w < ulen; w += G) rowA[w] = row[w];
-                lenA = ulen;
-                head_in_A = true;
-            } else {
-                g.sync();
-                for (uint32_t w = g.gl; 4 * w < ulen; w += G) rowB[w] = row[w];
-                head_in_A = false;
+        }
+        // (3) prefix compression against the previous survivor (one more compare when the last group head was dropped)
+        bool restart = to_restart == 0;
+        uint32_t shared = 0;
+        const bool cmp2 = keep && !restart && !(have_head && head_in_A);
+        if (g.any(cmp2)) row_cmp(g, cmp2, row, ulen, rowA, lenA, shared);
+        if (keep && !restart && have_head && head_in_A) shared = lcp_head;
+        if (keep) {
+            const uint32_t otype = tomb ? (uint32_t)PGS_TYPE_DELETION : type;
+            const unsigned long long seq = (P.bottommost && otype == PGS_TYPE_VALUE) ? 0ull : (tr >> 8);
+            const unsigned long long otr = (seq << 8) | otype;
+            uint32_t kd = ulen - shared, l1, l2, l3;
+            unsigned long long v1 = varint_pack(shared, l1), v2 = varint_pack(kd + 8, l2);
+            const unsigned long long v3 = varint_pack(vlen_out, l3);
+            unsigned long long e = (unsigned long long)l1 + l2 + l3 + kd + 8 + vlen_out;
+            uint32_t flags = 0, aux = 0;
+            // block cut: the entry (and the restart array it may extend) must fit the block
+            if (blk_n > 0 && (prev_big || blk_bytes + e + 4 * (nrest + (restart ? 1u : 0u) + 1) > BS)) {
+                close_block();
+                blk_n = 0; blk_bytes = 0; nrest = 0;
+                restart = true; shared = 0; kd = ulen;
+                v1 = 0; l1 = 1; v2 = varint_pack(kd + 8, l2);
+                e = (unsigned long long)l1 + l2 + l3 + kd + 8 + vlen_out;
             }
+            if (blk_n == 0) {
+                flags |= DF_NEWBLOCK;
+                if (n_out > 0) { // the finished block's last user key travels in the head stream
+                    aux = lenA;
+                    for (uint32_t i = g.gl; i < lenA; i += G) heads[hpos + i] = ((const uint8_t *)rowA)[i];
+                    hpos += lenA;
+                }
+            }
+            const bool big = e + 8 > P.blk_buf; // does not fit the block buffer of k_emit: a block of its own, written in place
+            if (big) flags |= DF_BIG;
+            if (e > 0xFFFFFFF0ull || blk_bytes + e > 0xFFFFFFF0ull) err = PGS_NOT_SUPPORTED;
+            if (rewrite) {
+                flags |= DF_REWRITE;
+                if (g.gl < 4) heads[hpos + g.gl] = (uint8_t)(nts >> (8 * (3 - g.gl))); // BE32
+                hpos += 4;
+            }
+            // the entry head: varints | key delta | trailer
+            const uint32_t hv = l1 + l2 + l3, hl = hv + kd + 8;
+            {
+                uint8_t *hp = heads + hpos;
+                // the three varints occupy at most 15 bytes: two 64-bit registers' worth, written byte by byte by the first lanes
+                const unsigned long long lo64 = v1 | (v2 << (8 * l1)) | (l1 + l2 < 8 ? v3 << (8 * (l1 + l2)) : 0ull);
+                const unsigned long long hi64 = l1 + l2 >= 8 ? v3 << (8 * (l1 + l2 - 8)) : (l1 + l2 ? v3 >> (8 * (8 - l1 - l2)) : 0ull);
+                for (uint32_t i = g.gl; i < hv; i += G) hp[i] = (uint8_t)((i < 8 ? lo64 >> (8 * i) : hi64 >> (8 * (i - 8))));
+                for (uint32_t i = g.gl; i < kd; i += G) hp[hv + i] = ((const uint8_t *)row)[shared + i];
+                if (g.gl < 8) hp[hv + kd + g.gl] = (uint8_t)(otr >> (8 * g.gl));
+                if (G < 8) for (uint32_t i = G + g.gl; i < 8; i += G) hp[hv + kd + i] = (uint8_t)(otr >> (8 * i));
+            }
+            hpos += hl;
+            if (g.gl == 0) {
+                Desc d;
+                d.loc = (C->base + C->voff) | ((unsigned long long)c << 40) | ((unsigned long long)hl << 44) | ((unsigned long long)flags << 60);
+                d.vlen = vlen_out;
+                d.aux = aux;
+                *reinterpret_cast<uint4 *>(&desc[n_out]) = *reinterpret_cast<const uint4 *>(&d);
+            }
+            n_out++;
+            blk_n++;
+            blk_bytes += (uint32_t)e;
+            if (restart) { nrest++; to_restart = RI; }
+            to_restart--;
+            prev_big = big;
+            STAT_ADD(ST_OUT_REC, 1);
+            STAT_ADD(ST_OUT_BYTES, ulen + vlen_out);
+            STAT_ADD(ST_OUT_KEY, ulen);
+            STAT_ADD(ST_OUT_VAL, vlen_out);
+            if (otype == PGS_TYPE_DELETION) STAT_ADD(ST_OUT_TOMB, 1);
+            STAT_MAX(SM_UKEY, ulen);
+            STAT_MAX(SM_VLEN, vlen_out);
+            STAT_MAX(SM_MAX_SEQ, seq);
+            STAT_MAX(SM_MIN_SEQ_INV, ~seq);
+        }
+        g.sync(); // every lane has read the previous survivor's key
+        if (act && !shadow) {
+            uint32_t *dst = keep ? rowA : rowB;
+            for (uint32_t w = g.gl; 4 * w < ulen; w += G) dst[w] = row[w];
+            if (keep) lenA = ulen;
+            head_in_A = keep;
             have_head = true;
             head_len = ulen;
-            g.sync();
         }
+        g.sync();
         // (4) advance the cursor and restore the merge order
-        err = cur_next(g, P.runs[c], C, row, KS);
-        if (err) break;
-        bool alive = C->live != 0;
-        if (alive && !last && C->b >= C->chk_from && row_cmp(g, row, C->klen - 8, rowHI, uhi_len, dpos) > 0) alive = false;
-        if (!alive) {
-            const uint32_t dn = g.shfl_down(my_run, 1);
+        const uint32_t e3 = cur_next(g, act && !err, runs[c], C, row, KS);
+        if (act && !err) err = e3;
+        const bool adv = act && !err;
+        bool alive = adv && C->live != 0;
+        const bool hi = alive && !last && C->b >= C->chk_from;
+        if (g.any(hi)) { if (row_cmp(g, hi, row, hi ? C->klen - 8 : 0u, rowHI, uhi_len, dpos) > 0) alive = false; }
+        // The key differs from the runner-up's at byte d1 < shared: the bytes up to d1 did not change, neither does the order.
+        bool searching = adv && alive && live > 1 && !(d1_valid && C->shared > d1 && C->klen - 8 > d1);
+        if (searching) d1_valid = false;
+        uint32_t pos = 0;
+        const bool reorder = searching;
+        for (uint32_t i = 1; g.any(searching && i < live); i++) {
+            const uint32_t r = g.shfl(my_run, i) & 15u;
+            const bool e = searching && i < live;
+            const bool bf = head_before(g, e, cs, rows, KSW, c, r, dpos, by_byte);
+            if (e) {
+                if (bf) { if (i == 1) { d1_valid = by_byte; d1 = dpos; } searching = false; }
+                else pos = i;
+            }
+        }
+        const uint32_t dn = g.shfl_down(my_run, 1);
+        if (adv && !alive) { // drop the exhausted run
             if (g.gl + 1 < live) my_run = dn;
             live--;
             d1_valid = false;
-        } else if (live > 1) {
-            // The key differs from the runner-up's at byte d1 < shared: the bytes up to d1 did not change, neither does the order.
-            if (!(d1_valid && C->shared > d1 && C->klen - 8 > d1)) {
-                uint32_t pos = 0;
-                d1_valid = false;
-                for (uint32_t i = 1; i < live; i++) {
-                    const uint32_t r = g.shfl(my_run, i);
-                    if (head_before(g, cs, rows, KSW, c, r, dpos, by_byte)) {
-                        if (i == 1) { d1_valid = by_byte; d1 = dpos; }
-                        break;
-                    }
-                    pos = i;
-                }
-                if (pos > 0) {
-                    const uint32_t dn = g.shfl_down(my_run, 1);
-                    if (g.gl < pos) my_run = dn;
-                    if (g.gl == pos) my_run = c;
-                }
-            }
+        } else if (reorder && pos > 0) {
+            if (g.gl < pos) my_run = dn;
+            if (g.gl == pos) my_run = c;
         }
     }
-    if (!err && blk_n > 0) {
-        close_block();
-        for (uint32_t i = g.gl; i < lenA; i += G) heads[hpos + i] = ((const uint8_t *)rowA)[i];
-        hpos += lenA;
+    if (seg_en) {
+        if (!err && blk_n > 0) {
+            close_block();
+            for (uint32_t i = g.gl; i < lenA; i += G) heads[hpos + i] = ((const uint8_t *)rowA)[i];
+            hpos += lenA;
+        }
+        if (err) {
+            if (g.gl == 0) { atomicMax(&P.stats->error, err); atomicMin(&P.stats->error_seg, q); }
+            n_out = 0; n_blocks = 0; keyb = 0; out_bytes = 0; hpos = 0; lenA = 0;
+        }
+        if (g.gl == 0) {
+            SegAgg a;
+            a.out_bytes = out_bytes; a.n_entries = n_out; a.n_blocks = n_blocks; a.keyb = keyb; a.head_bytes = hpos; a.last_klen = lenA; a.pad = 0;
+            P.agg[q] = a;
+        }
     }
-    if (err) {
-        if (g.gl == 0) { atomicMax(&P.stats->error, err); atomicMin(&P.stats->error_seg, q); }
-        n_out = 0; n_blocks = 0; keyb = 0; out_bytes = 0; hpos = 0; lenA = 0;
-    }
-    if (g.gl == 0) {
-        SegAgg a;
-        a.out_bytes = out_bytes; a.n_entries = n_out; a.n_blocks = n_blocks; a.keyb = keyb; a.head_bytes = hpos; a.last_klen = lenA; a.pad = 0;
-        P.agg[q] = a;
-    }
+    g.sync();
 #undef STAT_ADD
 #undef STAT_MAX
 }
@@ -671,11 +712,15 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ M
     const Grp<G> g;
     constexpr uint32_t NGW = 32 / G; // groups per warp
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned long long *crc = (unsigned long long *)dyn; // 2 KB, only filled when the stale-split check is on
+    // CTA-wide shared memory: crc table (2 KB, only filled when the stale-split check is on), the run table (the groups of a
+    // warp work on different runs at the same time: a per-lane index into kernel parameters would serialise)
+    unsigned long long *crc = (unsigned long long *)dyn;
+    RunDev *runs = (RunDev *)(dyn + 2048);
     if (P.validate_hash)
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) crc[i] = P.crc_table[i];
+    for (uint32_t i = threadIdx.x; i < kMaxRuns; i += blockDim.x) runs[i] = P.runs[i < P.k ? i : 0];
     __syncthreads();
-    uint8_t *gs = dyn + 2048 + (size_t)(warp * NGW + g.shift / G) * P.group_smem;
+    uint8_t *gs = dyn + 2048 + kMaxRuns * sizeof(RunDev) + (size_t)(warp * NGW + g.shift / G) * P.group_smem;
     CurState *cs = (CurState *)gs;
     uint32_t *rows = (uint32_t *)(gs + (size_t)P.k * sizeof(CurState));
     unsigned long long acc0 = 0, acc1 = 0, accm = 0;
@@ -685,8 +730,7 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ M
         t0 = __shfl_sync(kFull, t0, 0);
         if (t0 >= P.Q) break;
         const uint32_t q = t0 + g.shift / G;
-        if (q < P.Q) walk_segment<G>(P, g, q, cs, rows, crc, acc0, acc1, accm);
-        __syncwarp();
+        walk_segment<G>(P, runs, g, q < P.Q, q < P.Q ? q : 0u, cs, rows, crc, acc0, acc1, accm);
     }
     // statistics: lane s % G of a group holds counter s
     unsigned long long *st = &P.stats->in_records;
@@ -754,24 +798,28 @@ __global__ void __launch_bounds__(1024) k_seg_scan(const __grid_constant__ Merge
 // ------------------------------------------------------------------------------------------------
 // k_emit
 // ------------------------------------------------------------------------------------------------
-// 4 bytes at byte offset `off` of a 4-byte aligned shared-memory buffer (readable one word past)
-PGS_DEV uint32_t lds_u32_at(const uint8_t *base4, uint32_t off)
+// shared -> shared copy of t bytes, any alignment on both sides (src4 / dst16: 4- / 16-byte aligned buffers, the source readable
+// 16 bytes past its end).  Destination-aligned 16-byte stores; a source chunk is five aligned words re-aligned with funnel shifts.
+PGS_DEV void warp_copy_s2s(uint8_t *dst16, uint32_t doff, const uint8_t *src4, uint32_t soff, uint32_t t, uint32_t lane)
 {
-    const uint32_t *w = (const uint32_t *)base4 + (off >> 2);
-    const uint32_t sh = (off & 3) * 8;
-    return sh ? __funnelshift_r(w[0], w[1], sh) : w[0];
-}
-// shared -> shared copy of t bytes, any alignment on both sides; words are written aligned on the destination
-PGS_DEV void warp_copy_s2s(uint8_t *dst4, uint32_t doff, const uint8_t *src4, uint32_t soff, uint32_t t, uint32_t lane)
-{
-    uint32_t lead = (4 - (doff & 3)) & 3;
+    uint32_t lead = (16 - (doff & 15)) & 15;
     if (lead > t) lead = t;
-    if (lane < lead) dst4[doff + lane] = src4[soff + lane];
-    const uint32_t d0 = doff + lead, s0 = soff + lead, nw = (t - lead) >> 2, tail = (t - lead) & 3;
-    uint32_t *dw = (uint32_t *)(dst4 + d0);
-    for (uint32_t w = lane; w < nw; w += 32) dw[w] = lds_u32_at(src4, s0 + 4 * w);
-    if (lane < tail) dst4[d0 + 4 * nw + lane] = src4[s0 + 4 * nw + lane];
+    if (lane < lead) dst16[doff + lane] = src4[soff + lane];
+    const uint32_t d0 = doff + lead, s0 = soff + lead, nch = (t - lead) >> 4, tail = (t - lead) & 15;
+    const uint32_t sh = (s0 & 3) * 8;
+    for (uint32_t c = lane; c < nch; c += 32) {
+        const uint32_t *w = (const uint32_t *)src4 + ((s0 + 16 * c) >> 2);
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+        uint4 o;
+        o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh); o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
+        *reinterpret_cast<uint4 *>(dst16 + d0 + 16 * c) = o;
+    }
+    if (lane < tail) dst16[d0 + 16 * nch + lane] = src4[s0 + 16 * nch + lane];
 }
+
+constexpr uint32_t kEmitDepth = 4;     // value windows in flight per warp
+constexpr uint32_t kEmitWindow = 512;  // bytes of a value moved per window (plus up to 15 bytes of alignment slack)
+constexpr uint32_t kEmitSlot = kEmitWindow + 32;
 
 __global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ MergeParams P)
 {
@@ -780,9 +828,9 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ M
     const uint32_t RI = P.restart_interval;
     uint8_t *ws = dyn + (size_t)warp * P.emit_warp_smem;
     uint8_t *bbuf[2] = {ws, ws + P.blk_buf};
-    uint8_t *vst = ws + 2 * (size_t)P.blk_buf;        // 512 + 16 bytes: one window of a value
-    uint8_t *hst = vst + 528;                          // head_stage + 32 bytes: the head-stream bytes of a batch of entries
-    uint32_t *rst = (uint32_t *)(hst + P.head_stage + 32); // restart offsets of the open block
+    uint8_t *vst = ws + 2 * (size_t)P.blk_buf;                    // kEmitDepth value windows
+    uint8_t *hst = vst + kEmitDepth * kEmitSlot;                  // head_stage + 32 bytes: the head-stream bytes of a batch of entries
+    uint32_t *rst = (uint32_t *)(hst + P.head_stage + 32);        // restart offsets of the open block
     uint32_t which = 0;
 
     for (;;) {
@@ -798,12 +846,14 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ M
         unsigned long long blk_start = B.bytes; // where the open block goes
         uint32_t blk_idx = B.blocks, rec_idx = B.recs, keyb = B.keyb;
         uint32_t fill = 0, blk_n = 0, blk_rec0 = rec_idx, hpos = 0, err = 0;
+        uint32_t to_restart = 0, nrest = 0; // entries until the next restart point, restart points of the open block
         bool open = false, cur_big = false;
         uint8_t *buf = bbuf[which];
 
         auto close_block = [&](const uint8_t *key, uint32_t klen) {
-            const uint32_t nrest = (blk_n + RI - 1) / RI, size = fill + 4 * (nrest + 1);
+            const uint32_t size = fill + 4 * (nrest + 1);
             const uint32_t asz = (size + kBlockAlign - 1) & ~(kBlockAlign - 1);
+            __syncwarp(); // lane 0's restart offsets and every lane's bytes of the last entry are in place
             if (!cur_big) {
                 for (uint32_t i = lane; i < 4 * (nrest + 1); i += 32) {
                     const uint32_t v = (i >> 2) < nrest ? rst[i >> 2] : nrest;
@@ -836,9 +886,6 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ M
                 P.out_ikey_off[blk_idx] = keyb;
             }
             for (uint32_t i = lane; i < klen; i += 32) P.out_ikeys[keyb + i] = key[i];
-#ifdef PGS_SIM_TRACE
-            if (lane == 0) fprintf(stderr, "emit seg %u blk %u keyb %u klen %u key ..%.*s big %d\n", q, blk_idx, keyb, klen, 6, key + (klen > 6 ? klen - 6 : 0), (int)cur_big);
-#endif
             keyb += klen;
             blk_idx++;
             blk_start += asz;
@@ -858,7 +905,29 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ M
             const uint32_t total = __shfl_sync(kFull, s_incl, (int)cnt - 1);
             const uint8_t *src = heads + hpos;
             const uint32_t a = (uint32_t)((uintptr_t)src & 15);
-            for (uint32_t i = lane * 16; i < a + total; i += 512) *reinterpret_cast<uint4 *>(hst + i) = *reinterpret_cast<const uint4 *>(src - a + i);
+            for (uint32_t i = lane * 16; i < a + total; i += 512) async_copy16(hst + i, src - a + i);
+            async_copy_commit();
+            // ---- value windows: up to kEmitDepth 512-byte pieces of the batch's values are in flight (LDGSTS, no registers) ----
+            uint32_t pe = 0, poff = 0, useq = 0, cseq = 0; // producer entry / value bytes requested, windows issued / consumed
+            auto produce = [&]() {
+                while (pe < cnt) {
+                    const unsigned long long loc = __shfl_sync(kFull, d.loc, (int)pe);
+                    const uint32_t vl = __shfl_sync(kFull, d.vlen, (int)pe);
+                    if (((uint32_t)(loc >> 60) & DF_BIG) || poff >= vl) { pe++; poff = 0; continue; }
+                    const uint8_t *s = P.runs[(uint32_t)(loc >> 40) & 15u].data + (loc & ((1ull << 40) - 1)) + poff;
+                    const uint32_t va = (uint32_t)((uintptr_t)s & 15);
+                    const uint32_t span = vl - poff + va < kEmitWindow ? vl - poff + va : kEmitWindow;
+                    uint8_t *slot = vst + (useq % kEmitDepth) * kEmitSlot;
+                    if (lane * 16 < span) async_copy16(slot + lane * 16, s - va + lane * 16);
+                    poff += span - va;
+                    useq++;
+                    break;
+                }
+                async_copy_commit(); // one group per call, empty or not: the consumer counts groups
+            };
+            for (uint32_t x = 0; x < kEmitDepth - 1; x++) produce();
+            // groups committed so far: 1 (heads) + kEmitDepth - 1; the heads are the oldest
+            async_copy_wait_upto(kEmitDepth - 1);
             __syncwarp();
             const uint8_t *hs = hst + a;
             const uint32_t s_excl = s_incl - sb;
@@ -866,41 +935,39 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ M
                 const unsigned long long loc = __shfl_sync(kFull, d.loc, (int)i);
                 const uint32_t vlen = __shfl_sync(kFull, d.vlen, (int)i), aux = __shfl_sync(kFull, d.aux, (int)i);
                 uint32_t so = __shfl_sync(kFull, s_excl, (int)i);
-                const uint32_t fl = (uint32_t)(loc >> 60), hl = (uint32_t)(loc >> 44) & 0xffffu, run = (uint32_t)(loc >> 40) & 15u;
-                const unsigned long long voff = loc & ((1ull << 40) - 1);
+                const uint32_t fl = (uint32_t)(loc >> 60), hl = (uint32_t)(loc >> 44) & 0xffffu;
                 if (fl & DF_NEWBLOCK) {
-#ifdef PGS_SIM_TRACE
-                    if (lane == 0) fprintf(stderr, "  newblock seg %u e %u so %u aux %u a %u total %u cnt %u hpos %u hl %u\n", q, e0 + i, so, aux, a, total, cnt, hpos, hl);
-#endif
                     if (open) { close_block(hs + so, aux); so += aux; }
                     open = true;
-                    fill = 0; blk_n = 0; blk_rec0 = rec_idx;
+                    fill = 0; blk_n = 0; blk_rec0 = rec_idx; to_restart = 0; nrest = 0;
                     cur_big = (fl & DF_BIG) != 0;
                 }
                 const uint8_t *ntsb = hs + so;
                 if (fl & DF_REWRITE) so += 4;
-                const uint8_t *vsrc = P.runs[run].data + voff;
                 if (lane == 0) {
-                    if (blk_n % RI == 0 && !cur_big) rst[blk_n / RI] = fill;
+                    if (to_restart == 0 && !cur_big) rst[nrest] = fill;
                     P.out_rec_off[rec_idx] = fill;
                 }
+                if (to_restart == 0) { nrest++; to_restart = RI; }
+                to_restart--;
                 if (!cur_big) {
                     for (uint32_t x = lane; x < hl; x += 32) buf[fill + x] = hs[so + x];
-                    // the value: 16-byte global loads of the aligned window around it, byte-exact placement from shared memory
+                    // the value: its windows arrive in issue order; byte-exact placement from shared memory
                     uint32_t n = vlen, doff = fill + hl;
-                    const uint8_t *s = vsrc;
                     while (n > 0) {
-                        const uint32_t va = (uint32_t)((uintptr_t)s & 15);
-                        const uint32_t span = n + va < 512 ? n + va : 512;
-                        if (lane * 16 < span) *reinterpret_cast<uint4 *>(vst + lane * 16) = *reinterpret_cast<const uint4 *>(s - va + lane * 16);
+                        produce();                               // keep kEmitDepth - 1 windows ahead
+                        async_copy_wait_upto(kEmitDepth - 1);    // ... so the oldest outstanding one is this window
                         __syncwarp();
-                        const uint32_t t = span - va;
-                        warp_copy_s2s(buf, doff, vst, va, t, lane);
+                        const uint32_t va = (uint32_t)((uintptr_t)(P.runs[(uint32_t)(loc >> 40) & 15u].data + (loc & ((1ull << 40) - 1)) + (vlen - n)) & 15); // as the producer saw it
+                        const uint32_t span = n + va < kEmitWindow ? n + va : kEmitWindow, t = span - va;
+                        warp_copy_s2s(buf, doff, vst + (cseq % kEmitDepth) * kEmitSlot, va, t, lane);
+                        cseq++;
                         __syncwarp();
-                        s += t; doff += t; n -= t;
+                        doff += t; n -= t;
                     }
                     if ((fl & DF_REWRITE) && vlen >= 4 && lane < 4) buf[fill + hl + lane] = ntsb[lane];
                 } else {
+                    const uint8_t *vsrc = P.runs[(uint32_t)(loc >> 40) & 15u].data + (loc & ((1ull << 40) - 1));
                     uint8_t *o = P.out_data + blk_start;
                     for (uint32_t x = lane; x < hl; x += 32) o[fill + x] = hs[so + x];
                     for (uint32_t x = lane; x < vlen; x += 32) o[fill + hl + x] = vsrc[x];
@@ -910,7 +977,8 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ M
                 blk_n++;
                 rec_idx++;
             }
-            __syncwarp(); // the staged heads are consumed
+            async_copy_wait_upto(0);
+            __syncwarp(); // the staged heads and windows are consumed
             hpos += total;
             e0 += cnt;
         }

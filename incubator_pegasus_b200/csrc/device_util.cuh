@@ -40,6 +40,8 @@ PGS_DEV void tma_store_wait_all() {}
 PGS_DEV void fence_proxy_async() {}
 PGS_DEV void async_copy4(void *smem_dst, const void *gmem_src) { memcpy(smem_dst, gmem_src, 4); }
 PGS_DEV void async_copy8(void *smem_dst, const void *gmem_src) { memcpy(smem_dst, gmem_src, 8); }
+PGS_DEV void async_copy16(void *smem_dst, const void *gmem_src) { memcpy(smem_dst, gmem_src, 16); }
+PGS_DEV void async_copy_wait_upto(uint32_t) {}
 PGS_DEV void async_copy_commit() {}
 PGS_DEV void async_copy_wait_all() {}
 #else
@@ -101,7 +103,20 @@ PGS_DEV void async_copy8(void *smem_dst, const void *gmem_src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
+// 16 bytes, both addresses 16-aligned, past L1 (streamed data)
+PGS_DEV void async_copy16(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
 PGS_DEV void async_copy_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most n (0..3) of this thread's newest committed groups are still in flight
+PGS_DEV void async_copy_wait_upto(uint32_t n)
+{
+    if (n == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    else if (n == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else if (n == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else asm volatile("cp.async.wait_group 3;" ::: "memory");
+}
 PGS_DEV void async_copy_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif
 

@@ -3,10 +3,12 @@
 // A *group* is G consecutive lanes of a warp (G = 8, 16 or 32) that together run one sequential iterator over sorted
 // runs: group-uniform scalars (offsets, lengths, counters) are computed redundantly by every lane, the bytes of a key
 // are spread over the lanes (lane L owns the 32-bit words L, L+G, ... of a key row in shared memory) and compared with
-// one ballot.  Several groups share a warp and run in lock step on different data, so one warp instruction advances
-// 32/G iterators.  This is the B200 shape of RocksDB's DataBlockIter / MergingIterator (v8.5.3, not in the reference
-// tree): the per-record decode chain stays sequential, the parallelism comes from thousands of
-// independent groups per GPU.
+// one ballot.  The 32/G groups of a warp run in LOCK STEP on different data: control flow around every collective is
+// warp-uniform (loops run while any group still needs them, per-group work is switched on and off with an `en`
+// predicate), so all shuffles / ballots use the constant full mask -- a collective with a run-time lane mask costs a
+// MATCH.ANY + REDUX convergence check per call and lets the groups drift apart; measured 4x slower.
+// This is the B200 shape of RocksDB's DataBlockIter / MergingIterator (v8.5.3, not in the reference tree; SURVEY.md
+// Appendix A): the per-record decode chain stays sequential, the parallelism comes from thousands of independent groups.
 #pragma once
 #include "../../include/pegasus_b200.h"
 #include "device_util.cuh"
@@ -15,21 +17,22 @@ namespace pgs {
 
 template <uint32_t G>
 struct Grp {
+    static constexpr uint32_t kLow = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
     uint32_t gl;    // lane inside the group
     uint32_t shift; // first lane of the group inside the warp
-    uint32_t mask;  // the group's lanes
     PGS_DEV Grp()
     {
         const uint32_t lane = threadIdx.x & 31;
         gl = lane & (G - 1);
         shift = lane & ~(G - 1);
-        mask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << shift);
     }
-    PGS_DEV uint32_t ballot(bool p) const { return G == 32 ? __ballot_sync(mask, p) : ((__ballot_sync(mask, p) >> shift) & ((1u << (G & 31)) - 1u)); }
-    template <class T> PGS_DEV T shfl(T v, uint32_t src) const { return __shfl_sync(mask, v, (int)src, (int)G); }
-    template <class T> PGS_DEV T shfl_down(T v, uint32_t d) const { return __shfl_down_sync(mask, v, d, (int)G); }
-    template <class T> PGS_DEV T shfl_up(T v, uint32_t d) const { return __shfl_up_sync(mask, v, d, (int)G); }
-    PGS_DEV void sync() const { __syncwarp(mask); }
+    // every lane of the warp executes these together; the result is the own group's
+    PGS_DEV uint32_t ballot(bool p) const { return (__ballot_sync(kFull, p) >> shift) & kLow; }
+    template <class T> PGS_DEV T shfl(T v, uint32_t src) const { return __shfl_sync(kFull, v, (int)(src & (G - 1)), (int)G); }
+    template <class T> PGS_DEV T shfl_down(T v, uint32_t d) const { return __shfl_down_sync(kFull, v, d, (int)G); }
+    template <class T> PGS_DEV T shfl_up(T v, uint32_t d) const { return __shfl_up_sync(kFull, v, d, (int)G); }
+    PGS_DEV static bool any(bool p) { return __any_sync(kFull, p) != 0; }
+    PGS_DEV static void sync() { __syncwarp(); }
 };
 
 // 8 bytes at an arbitrary address (any address space): two aligned 64-bit loads + shift
@@ -44,30 +47,35 @@ PGS_DEV uint64_t ld_u64_any(const uint8_t *p)
 
 // Compare two byte strings held in key rows (4-byte aligned shared memory, readable up to the next multiple of 4).
 // Returns <0, 0, >0; dpos = index of the first differing byte, or min(la, lb) when one is a prefix of the other.
-// Every lane of the group returns the same values.
+// Executed by the whole warp; groups with en = false take part in the collectives and get 0.
 template <uint32_t G>
-PGS_DEV int row_cmp(const Grp<G> &g, const uint32_t *a, uint32_t la, const uint32_t *b, uint32_t lb, uint32_t &dpos)
+PGS_DEV int row_cmp(const Grp<G> &g, bool en, const uint32_t *a, uint32_t la, const uint32_t *b, uint32_t lb, uint32_t &dpos)
 {
-    const uint32_t m = la < lb ? la : lb;
-    for (uint32_t base = 0; base < m; base += 4 * G) {
+    const uint32_t m = en ? (la < lb ? la : lb) : 0u;
+    int res = 2; // undecided
+    for (uint32_t base = 0; g.any(res == 2 && base < m); base += 4 * G) {
         const uint32_t off = base + 4 * g.gl;
         uint32_t x = 0;
-        if (off < m) {
+        if (res == 2 && off < m) {
             x = a[off >> 2] ^ b[off >> 2];
             if (m - off < 4) x &= (1u << (8 * (m - off))) - 1u;
         }
         const uint32_t bal = g.ballot(x != 0);
-        if (bal) {
-            const uint32_t first = (uint32_t)__ffs((int)bal) - 1;
-            const uint32_t xx = g.shfl(x, first);
+        const uint32_t first = (uint32_t)__ffs((int)bal) - 1;
+        const uint32_t xx = g.shfl(x, first);
+        if (res == 2 && bal) {
             const uint32_t at = base + 4 * first + (((uint32_t)__ffs((int)xx) - 1) >> 3);
             dpos = at;
             const uint32_t ba = (a[at >> 2] >> (8 * (at & 3))) & 0xffu, bb = (b[at >> 2] >> (8 * (at & 3))) & 0xffu;
-            return ba < bb ? -1 : 1;
+            res = ba < bb ? -1 : 1;
         }
     }
-    dpos = m;
-    return la < lb ? -1 : (la > lb ? 1 : 0);
+    if (!en) return 0;
+    if (res == 2) {
+        dpos = m;
+        res = la < lb ? -1 : (la > lb ? 1 : 0);
+    }
+    return res;
 }
 
 // ---- sequential cursor over the blocks of one HBM-resident run ------------------------------------------------------------
@@ -90,14 +98,15 @@ struct CurState {
     uint32_t chk_from;         // blocks >= chk_from may hold keys above the range's upper bound
     uint32_t live;             // 0 once the cursor is exhausted
 };
+static_assert(sizeof(CurState) % 8 == 0, "CurState");
 
 PGS_DEV unsigned long long cur_trailer(const CurState *c) { return ((unsigned long long)c->tr_hi << 32) | c->tr_lo; }
 
 // start fetching the metadata of block b + 1 (asynchronous copies into the state; consumed when the block is entered)
 template <uint32_t G>
-PGS_DEV void cur_prefetch_next(const Grp<G> &g, const RunDev &r, CurState *c, uint32_t b)
+PGS_DEV void cur_prefetch_next(const Grp<G> &g, bool en, const RunDev &r, CurState *c, uint32_t b)
 {
-    if (b + 1 < r.nb) { // blk_off and blk_rec have nb + 1 entries
+    if (en && b + 1 < r.nb) { // blk_off and blk_rec have nb + 1 entries
         if (g.gl == 0) async_copy8(&c->nb_off, r.blk_off + b + 1);
         if (g.gl == 1) async_copy4(&c->nb_r0, r.blk_rec + b + 1);
         if (g.gl == 2) async_copy4(&c->nb_r1, r.blk_rec + b + 2);
@@ -106,96 +115,105 @@ PGS_DEV void cur_prefetch_next(const Grp<G> &g, const RunDev &r, CurState *c, ui
     async_copy_commit();
 }
 
-// decode the entry at (base, p) of the current block into the state and the key row.  prev_klen = internal-key length of
-// the previous entry of the block (0 at a block start: the entry must then be a restart point).  Returns 0 or a status.
+// decode the entry at (base, p) of the current block into the state and the key row (groups with en).  prev_klen = internal-
+// key length of the previous entry of the block (0 at a block start: the entry must then be a restart point).
+// Executed by the whole warp (two warp barriers inside).  Returns 0 or a status.
 template <uint32_t G>
-PGS_DEV uint32_t cur_decode(const Grp<G> &g, const RunDev &r, CurState *c, uint32_t *row, uint32_t KS, unsigned long long base,
+PGS_DEV uint32_t cur_decode(const Grp<G> &g, bool en, const RunDev &r, CurState *c, uint32_t *row, uint32_t KS, unsigned long long base,
                             uint32_t p, uint32_t blk_size, uint32_t prev_klen)
 {
-    const uint8_t *A = r.data + base + p;
-    uint32_t sh, ns, vl, h;
-    h = parse_header8(ld_u64_any(A), sh, ns, vl);
-    if (!h) { // uncommon shape (a length of two or more varint bytes): byte-wise decoder
-        uint32_t c1 = get_varint32(A, 5, sh), c2 = 0, c3 = 0;
-        if (c1) c2 = get_varint32(A + c1, 5, ns);
-        if (c2) c3 = get_varint32(A + c1 + c2, 5, vl);
-        if (!c3) return PGS_CORRUPTION;
-        h = c1 + c2 + c3;
-    }
-    const uint32_t klen = sh + ns;
-    if (sh > prev_klen || klen < 8 || klen - 8 > KS || (unsigned long long)p + h + ns + vl + 8 > blk_size) return PGS_CORRUPTION;
-    // key bytes [sh, sh + ns) <- the entry's delta; lane L owns the words L, L + G, ... of the row
-    const uint8_t *src = A + h;
-    const uint32_t end = sh + ns;
-    for (uint32_t w = (sh >> 2) + g.gl; 4 * w < end; w += G) {
-        const uint32_t lo = 4 * w;
-        const uint32_t v = ld_u32_any(src + (int32_t)(lo - sh));
-        uint32_t keep = 0; // bytes of the word that are not covered by the delta keep their old value
-        if (lo < sh) keep = (1u << (8 * (sh - lo))) - 1u;
-        if (end - lo < 4) keep |= ~((1u << (8 * (end - lo))) - 1u);
-        row[w] = keep ? ((row[w] & keep) | (v & ~keep)) : v;
-    }
-    g.sync();
-    unsigned long long tr;
-    if (ns >= 8) tr = ld_u64_any(src + ns - 8);
-    else tr = lds_u64_at((const uint8_t *)row, klen - 8); // part of the trailer is shared with the previous key
-    const uint32_t ets = vl >= 4 ? ld_u32_any(src + ns) : 0u;
-    if (g.gl == 0) {
-        c->p = p; c->elen = h + ns + vl; c->klen = klen; c->vlen = vl; c->voff = p + h + ns; c->shared = sh; c->ets_le = ets;
-        c->tr_lo = (uint32_t)tr; c->tr_hi = (uint32_t)(tr >> 32);
+    uint32_t err = 0, sh = 0, ns = 0, vl = 0, h = 0, klen = 0;
+    const uint8_t *src = nullptr;
+    if (en) {
+        const uint8_t *A = r.data + base + p;
+        h = parse_header8(ld_u64_any(A), sh, ns, vl);
+        if (!h) { // uncommon shape (a length of two or more varint bytes): byte-wise decoder
+            uint32_t c1 = get_varint32(A, 5, sh), c2 = 0, c3 = 0;
+            if (c1) c2 = get_varint32(A + c1, 5, ns);
+            if (c2) c3 = get_varint32(A + c1 + c2, 5, vl);
+            h = c1 + c2 + c3;
+            if (!c3) err = PGS_CORRUPTION;
+        }
+        klen = sh + ns;
+        if (!err && (sh > prev_klen || klen < 8 || klen - 8 > KS || (unsigned long long)p + h + ns + vl + 8 > blk_size)) err = PGS_CORRUPTION;
+        if (!err) {
+            // key bytes [sh, sh + ns) <- the entry's delta; lane L owns the words L, L + G, ... of the row
+            src = A + h;
+            const uint32_t end = sh + ns;
+            for (uint32_t w = (sh >> 2) + g.gl; 4 * w < end; w += G) {
+                const uint32_t lo = 4 * w;
+                const uint32_t v = ld_u32_any(src + (int32_t)(lo - sh));
+                uint32_t keep = 0; // bytes of the word that are not covered by the delta keep their old value
+                if (lo < sh) keep = (1u << (8 * (sh - lo))) - 1u;
+                if (end - lo < 4) keep |= ~((1u << (8 * (end - lo))) - 1u);
+                row[w] = keep ? ((row[w] & keep) | (v & ~keep)) : v;
+            }
+        }
     }
     g.sync();
-    return 0;
+    if (en && !err) {
+        unsigned long long tr;
+        if (ns >= 8) tr = ld_u64_any(src + ns - 8);
+        else tr = lds_u64_at((const uint8_t *)row, klen - 8); // part of the trailer is shared with the previous key
+        const uint32_t ets = vl >= 4 ? ld_u32_any(src + ns) : 0u;
+        if (g.gl == 0) {
+            c->p = p; c->elen = h + ns + vl; c->klen = klen; c->vlen = vl; c->voff = p + h + ns; c->shared = sh; c->ets_le = ets;
+            c->tr_lo = (uint32_t)tr; c->tr_hi = (uint32_t)(tr >> 32);
+        }
+    }
+    g.sync();
+    return err;
 }
 
-// position the cursor on the first entry of block b (b < b_end); synchronous metadata loads (used when a range is opened)
+// position the cursor on the first entry of block b (or leave it exhausted when b >= b_end); synchronous metadata loads
 template <uint32_t G>
-PGS_DEV uint32_t cur_open(const Grp<G> &g, const RunDev &r, CurState *c, uint32_t *row, uint32_t KS, uint32_t b, uint32_t b_end, uint32_t chk_from)
+PGS_DEV uint32_t cur_open(const Grp<G> &g, bool en, const RunDev &r, CurState *c, uint32_t *row, uint32_t KS, uint32_t b, uint32_t b_end, uint32_t chk_from)
 {
-    if (b >= b_end || b >= r.nb) {
-        if (g.gl == 0) { c->live = 0; c->b = b; c->b_end = b_end; c->chk_from = chk_from; }
-        g.sync();
-        return 0;
+    const bool some = en && b < b_end && b < r.nb;
+    unsigned long long base = 0;
+    uint32_t r0 = 0, r1 = 0, bsize = 0;
+    if (some) { base = r.blk_off[b]; r0 = r.blk_rec[b]; r1 = r.blk_rec[b + 1]; bsize = r.blk_size[b]; }
+    if (en && g.gl == 0) {
+        c->live = some ? 1u : 0u; c->b = b; c->b_end = b_end; c->chk_from = chk_from;
+        if (some) { c->base = base; c->rem = r1 - r0; c->bsize = bsize; }
     }
-    const unsigned long long base = r.blk_off[b];
-    const uint32_t r0 = r.blk_rec[b], r1 = r.blk_rec[b + 1], bsize = r.blk_size[b];
-    if (g.gl == 0) { c->live = 1; c->b = b; c->b_end = b_end; c->chk_from = chk_from; c->base = base; c->rem = r1 - r0; c->bsize = bsize; }
     g.sync();
-    cur_prefetch_next(g, r, c, b);
-    if (r1 <= r0) return PGS_CORRUPTION; // a block holds at least one entry
-    return cur_decode(g, r, c, row, KS, base, 0, bsize, 0);
+    cur_prefetch_next(g, some, r, c, b);
+    const uint32_t err = some && r1 <= r0 ? (uint32_t)PGS_CORRUPTION : 0u; // a block holds at least one entry
+    const uint32_t e2 = cur_decode(g, some && !err, r, c, row, KS, base, 0, bsize, 0);
+    return err ? err : e2;
 }
 
-// advance to the next entry; crossing into the next block uses the metadata fetched when the current block was entered.
-// Leaves live = 0 when the range is exhausted.  Returns 0 or a status.
+// advance to the next entry (groups with en); crossing into the next block uses the metadata fetched when the current block
+// was entered.  Leaves live = 0 when the range is exhausted.  Executed by the whole warp.  Returns 0 or a status.
 template <uint32_t G>
-PGS_DEV uint32_t cur_next(const Grp<G> &g, const RunDev &r, CurState *c, uint32_t *row, uint32_t KS)
+PGS_DEV uint32_t cur_next(const Grp<G> &g, bool en, const RunDev &r, CurState *c, uint32_t *row, uint32_t KS)
 {
-    const uint32_t rem = c->rem, b = c->b;
-    if (rem > 1) {
-        const unsigned long long base = c->base;
-        const uint32_t p = c->p + c->elen, prev_klen = c->klen, bsize = c->bsize;
-        g.sync(); // every lane has read the old state
-        if (g.gl == 0) c->rem = rem - 1;
-        return cur_decode(g, r, c, row, KS, base, p, bsize, prev_klen);
+    uint32_t rem = 0, b = 0, p = 0, prev_klen = 0, bsize = 0;
+    unsigned long long base = 0;
+    bool in_block = false, cross = false, done = false;
+    if (en) {
+        rem = c->rem; b = c->b;
+        in_block = rem > 1;
+        if (in_block) { base = c->base; p = c->p + c->elen; prev_klen = c->klen; bsize = c->bsize; }
+        else if (b + 1 >= c->b_end || b + 1 >= r.nb) done = true;
+        else cross = true;
     }
-    const uint32_t nb = b + 1;
-    if (nb >= c->b_end || nb >= r.nb) {
-        g.sync();
-        if (g.gl == 0) { c->live = 0; c->b = nb; }
-        g.sync();
-        return 0;
+    async_copy_wait_all(); // the copies issued when the block was entered (long since complete)
+    g.sync();              // ... and every lane has read the old state
+    uint32_t r0 = 0, r1 = 0;
+    if (cross) { base = c->nb_off; r0 = c->nb_r0; r1 = c->nb_r1; bsize = c->nb_size; }
+    g.sync();
+    if (en && g.gl == 0) {
+        if (in_block) c->rem = rem - 1;
+        else if (done) { c->live = 0; c->b = b + 1; }
+        else { c->b = b + 1; c->base = base; c->rem = r1 - r0; c->bsize = bsize; }
     }
-    async_copy_wait_all(); // the copies issued when block b was entered (long since complete)
     g.sync();
-    const unsigned long long base = c->nb_off;
-    const uint32_t r0 = c->nb_r0, r1 = c->nb_r1, bsize = c->nb_size;
-    g.sync();
-    if (g.gl == 0) { c->b = nb; c->base = base; c->rem = r1 - r0; c->bsize = bsize; }
-    g.sync();
-    cur_prefetch_next(g, r, c, nb);
-    if (r1 <= r0) return PGS_CORRUPTION;
-    return cur_decode(g, r, c, row, KS, base, 0, bsize, 0);
+    cur_prefetch_next(g, cross, r, c, b + 1);
+    const uint32_t err = cross && r1 <= r0 ? (uint32_t)PGS_CORRUPTION : 0u;
+    const uint32_t e2 = cur_decode(g, (in_block || cross) && !err, r, c, row, KS, base, p, bsize, prev_klen);
+    return err ? err : e2;
 }
 
 } // namespace pgs

@@ -5,16 +5,20 @@
 // src/server/pegasus_write_service_impl.h:90-169).  Handlers translate requests into engine calls
 // (pgs_get_batch / range scan / pgs_compact); the per-record loops themselves run in CUDA.
 //
-// Writes land in a host memtable; a read flushes it into an L0 run first (semantically neutral),
-// so the read path is purely the GPU's.  Scan contexts pin the run set they were opened on, like
-// a RocksDB iterator pins its super-version.
+// Writes land in a host memtable.  Point reads (get / ttl / multi_get with sort keys / batch_get) look there first, like
+// DB::Get does (rocksdb_wrapper.cpp:78-127), and send only the misses to the GPU; range reads flush the memtable into an L0
+// run first (semantically neutral) so that the iterator loop runs wholly in CUDA.  Scan contexts pin the run set they were
+// opened on, like a RocksDB iterator pins its super-version.
+// Threading: readers share the replica lock, the single writer / flush / compaction take it exclusively.
 #include <algorithm>
+#include <cerrno>
 #include <climits>
 #include <cstring>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <random>
+#include <shared_mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -70,8 +74,11 @@ struct Resp {
 
 struct MemRec { uint64_t seq; uint8_t type; std::string value; };
 
+constexpr uint32_t kScanContextTtlSeconds = 300; // pegasus_server_impl.cpp:1377-1385: a parked context expires after 5 minutes
+
 struct ScanContext { // pegasus_scan_context.h:33-95, with the iterator replaced by (pinned runs, resume key)
     std::vector<std::shared_ptr<Run>> runs;
+    uint32_t parked_at = 0; // epoch seconds of the call that parked it
     std::string resume, stop;
     bool stop_inclusive, prefix_mode;
     int32_t hash_key_filter_type, sort_key_filter_type;
@@ -90,10 +97,11 @@ struct Server {
     bool validate_partition_hash = false;
     int32_t partition_version = -1;
     std::string ops_bin;
-    std::mutex mu;
+    std::shared_mutex mu; // readers shared; writes, flush, compaction, env updates exclusive
     std::map<std::string, MemRec> mem;
     uint64_t mem_bytes = 0, last_seq = 0;
-    int64_t last_flushed_decree = 0;
+    int64_t last_committed_decree = 0, last_flushed_decree = 0;
+    std::mutex ctx_mu; // the scan-context table (touched by readers)
     int64_t ctx_counter = 0;
     uint64_t manual_compact_last_finish_ms = 0; // pegasus_manual_compact_service: _manual_compact_last_finish_time_ms
     bool manual_compact_disabled = false;
@@ -136,6 +144,7 @@ struct Server {
         if (st != PGS_OK) return st;
         mem.clear();
         mem_bytes = 0;
+        last_flushed_decree = last_committed_decree; // everything applied so far now lives in an HBM run
         return PGS_OK;
     }
     // L0 (+ the L1 run) -> L1, the engine's stand-in for RocksDB's level0_file_num_compaction_trigger
@@ -156,12 +165,33 @@ struct Server {
         for (auto &r : runs()) l0 += r->level == 0;
         return l0 >= trigger ? compact_l0(now) : PGS_OK;
     }
+    // range reads: the memtable becomes an L0 run (and L0 is folded once the run list grows past kReadMaxRuns)
+    bool range_read_needs_prepare() { return !mem.empty() || runs().size() > kReadMaxRuns; }
     int32_t prepare_read(uint32_t now)
     {
         int32_t st = flush_mem();
         if (st != PGS_OK) return st;
         if (runs().size() > kReadMaxRuns) st = compact_l0(now);
         return st;
+    }
+    // point reads: newest version in the memtable, if any.  0 = not there, 1 = value, 2 = tombstone
+    int mem_get(std::string_view key, std::string_view *value) const
+    {
+        auto f = mem.find(std::string(key));
+        if (f == mem.end()) return 0;
+        if (f->second.type != PGS_TYPE_VALUE) return 2;
+        *value = f->second.value;
+        return 1;
+    }
+    uint32_t gc_contexts(uint32_t now)
+    {
+        std::lock_guard<std::mutex> g(ctx_mu);
+        uint32_t n = 0;
+        for (auto it = ctx.begin(); it != ctx.end();) {
+            if (now >= it->second->parked_at && now - it->second->parked_at >= kScanContextTtlSeconds) { it = ctx.erase(it); n++; }
+            else ++it;
+        }
+        return n;
     }
     void mem_write(std::string key, uint8_t type, std::string value, uint32_t now)
     {
@@ -197,7 +227,11 @@ struct Server {
             resume.assign(kMaxUkeyLen + 8, '\0');
             int32_t st = scan_many(part->p, &rq, 1, now, cap, kv_cap, arena.data(), cap, kvs.data(), kv_cap, (uint8_t *)&resume[0],
                                    (uint32_t)resume.size(), &res, nullptr, nullptr, pinned);
-            if (st == PGS_ABORTED && cap < (4ull << 30)) { cap *= 8; continue; }
+            if (st == PGS_ABORTED && cap < (4ull << 30)) { // the result did not fit the arena or the record table: grow both
+                cap *= 8;
+                if (!rq.count_only && kv_cap < rq.max_count) kv_cap = (uint32_t)std::min<uint64_t>((uint64_t)kv_cap * 8, rq.max_count);
+                continue;
+            }
             if (st != PGS_OK) return st;
             resume.resize(res.iter_valid ? res.resume_len : 0);
             return PGS_OK;
@@ -245,22 +279,78 @@ static int32_t read_fail(Resp &r, int32_t st)
     return r.seal(st);
 }
 
+using RLock = std::shared_lock<std::shared_mutex>;
+// A range read runs on HBM runs only: when the memtable holds anything (or L0 has piled up) the shared lock is traded for
+// the exclusive one for the duration of the flush.  Writes that land between the two locks are concurrent with this read.
+static int32_t ensure_range_ready(Server &s, RLock &lk, uint32_t now)
+{
+    if (!s.range_read_needs_prepare()) return PGS_OK;
+    lk.unlock();
+    int32_t st;
+    {
+        std::unique_lock<std::shared_mutex> w(s.mu);
+        st = s.prepare_read(now);
+    }
+    lk.lock();
+    return st;
+}
+
+// Point lookups of n raw keys: the memtable answers what it holds (newest version wins over every run), the rest goes to
+// the GPU in one pgs_get_batch.  res[i].value_off/value_len index `arena` (grown as needed).
+static int32_t point_lookup(Server &s, const std::vector<std::string> &keys, uint32_t now, std::vector<pgs_get_result> &res,
+                            std::vector<uint8_t> &arena)
+{
+    const uint32_t n = (uint32_t)keys.size();
+    res.assign(n, pgs_get_result{});
+    arena.clear();
+    const uint32_t hdr = user_data_offset(s.data_version);
+    std::vector<uint32_t> miss;
+    for (uint32_t i = 0; i < n; i++) {
+        std::string_view v;
+        const int m = s.mem_get(keys[i], &v);
+        if (m == 0) { miss.push_back(i); continue; }
+        pgs_get_result &r = res[i];
+        r.status = PGS_NOT_FOUND;
+        if (m == 2) continue; // tombstone
+        r.expire_ts = v.size() >= 4 ? be32((const uint8_t *)v.data()) : 0;
+        if (ts_expired(now, r.expire_ts)) { r.expired = 1; continue; }
+        r.status = PGS_OK;
+        r.value_off = (uint32_t)arena.size();
+        r.value_len = v.size() >= hdr ? (uint32_t)(v.size() - hdr) : 0;
+        arena.insert(arena.end(), v.begin() + (v.size() >= hdr ? hdr : v.size()), v.end());
+    }
+    if (miss.empty()) return PGS_OK;
+    std::string flat;
+    std::vector<uint32_t> off(1, 0);
+    for (uint32_t i : miss) { flat += keys[i]; off.push_back((uint32_t)flat.size()); }
+    std::vector<pgs_get_result> gr(miss.size());
+    std::vector<uint8_t> dev(std::max<size_t>(1 << 16, miss.size() * 512));
+    uint64_t used = 0;
+    int32_t st;
+    for (;;) {
+        st = pgs_get_batch(s.part, (const uint8_t *)flat.data(), off.data(), (uint32_t)miss.size(), now, dev.data(), dev.size(), gr.data(), &used);
+        if (st == PGS_INCOMPLETE && used > dev.size()) { dev.resize(used + 64); continue; }
+        break;
+    }
+    if (st != PGS_OK) return st;
+    const uint32_t base = (uint32_t)arena.size();
+    arena.insert(arena.end(), dev.begin(), dev.begin() + used);
+    for (size_t j = 0; j < miss.size(); j++) {
+        res[miss[j]] = gr[j];
+        if (gr[j].status == PGS_OK) res[miss[j]].value_off += base;
+    }
+    return PGS_OK;
+}
+
 // ---- on_get / on_ttl (pegasus_server_impl.cpp:418-494, 1088-1149) --------------------------------------
 static int32_t do_get(Server &s, std::string_view key, uint32_t now, Resp &r, bool ttl_only)
 {
     r.reset(s.app_id, s.pidx);
-    int32_t st = s.prepare_read(now);
+    std::vector<pgs_get_result> grv;
+    std::vector<uint8_t> arena;
+    int32_t st = point_lookup(s, {std::string(key)}, now, grv, arena);
     if (st != PGS_OK) return read_fail(r, st);
-    uint32_t off[2] = {0, (uint32_t)key.size()};
-    pgs_get_result gr{};
-    std::vector<uint8_t> arena(1 << 16);
-    uint64_t used = 0;
-    for (;;) {
-        st = pgs_get_batch(s.part, (const uint8_t *)key.data(), off, 1, now, arena.data(), arena.size(), &gr, &used);
-        if (st == PGS_INCOMPLETE && used > arena.size()) { arena.resize(used + 64); continue; }
-        break;
-    }
-    if (st != PGS_OK) return read_fail(r, st);
+    const pgs_get_result &gr = grv[0];
     if (gr.expired) r.view.expire_count = 1;
     if (gr.status != PGS_OK) return r.seal(PGS_NOT_FOUND);
     if (ttl_only) {
@@ -272,11 +362,11 @@ static int32_t do_get(Server &s, std::string_view key, uint32_t now, Resp &r, bo
 }
 
 // ---- on_multi_get (:496-904) ----------------------------------------------------------------------------------
-static int32_t do_multi_get(Server &s, const pgs_multi_get_request &q, uint32_t now, Resp &r)
+static int32_t do_multi_get(Server &s, RLock &lk, const pgs_multi_get_request &q, uint32_t now, Resp &r)
 {
     r.reset(s.app_id, s.pidx);
     if (!filter_type_supported(q.sort_key_filter_type)) return r.seal(PGS_INVALID_ARGUMENT);
-    int32_t st = s.prepare_read(now);
+    int32_t st = q.n_sort_keys == 0 ? ensure_range_ready(s, lk, now) : PGS_OK;
     if (st != PGS_OK) return read_fail(r, st);
     uint32_t max_kv_count = s.cfg_mget_count(), max_iteration_count = s.cfg_mget_count();
     if (q.max_kv_count > 0 && (uint32_t)q.max_kv_count < max_kv_count) max_kv_count = q.max_kv_count;
@@ -334,20 +424,11 @@ static int32_t do_multi_get(Server &s, const pgs_multi_get_request &q, uint32_t 
         return r.seal(res.iter_valid && !res.complete ? PGS_INCOMPLETE : PGS_OK); // :777-787
     }
     // sort_keys given: MultiGet (:789-864)
-    std::string keys;
-    std::vector<uint32_t> off(1, 0);
-    for (uint32_t i = 0; i < q.n_sort_keys; i++) {
-        keys += make_key(hash_key, bsv(q.sort_keys[i]));
-        off.push_back((uint32_t)keys.size());
-    }
-    std::vector<pgs_get_result> gr(q.n_sort_keys);
-    std::vector<uint8_t> arena(1 << 20);
-    uint64_t used = 0;
-    for (;;) {
-        st = pgs_get_batch(s.part, (const uint8_t *)keys.data(), off.data(), q.n_sort_keys, now, arena.data(), arena.size(), gr.data(), &used);
-        if (st == PGS_INCOMPLETE && used > arena.size()) { arena.resize(used + 64); continue; }
-        break;
-    }
+    std::vector<std::string> keys;
+    for (uint32_t i = 0; i < q.n_sort_keys; i++) keys.push_back(make_key(hash_key, bsv(q.sort_keys[i])));
+    std::vector<pgs_get_result> gr;
+    std::vector<uint8_t> arena;
+    st = point_lookup(s, keys, now, gr, arena);
     if (st != PGS_OK) return read_fail(r, st);
     int32_t count = 0;
     int64_t size = 0;
@@ -369,22 +450,11 @@ static int32_t do_batch_get(Server &s, const pgs_full_key *fk, uint32_t n, uint3
 {
     r.reset(s.app_id, s.pidx);
     if (n == 0) return r.seal(PGS_INVALID_ARGUMENT);
-    int32_t st = s.prepare_read(now);
-    if (st != PGS_OK) return read_fail(r, st);
-    std::string keys;
-    std::vector<uint32_t> off(1, 0);
-    for (uint32_t i = 0; i < n; i++) {
-        keys += make_key(bsv(fk[i].hash_key), bsv(fk[i].sort_key));
-        off.push_back((uint32_t)keys.size());
-    }
-    std::vector<pgs_get_result> gr(n);
-    std::vector<uint8_t> arena(1 << 20);
-    uint64_t used = 0;
-    for (;;) {
-        st = pgs_get_batch(s.part, (const uint8_t *)keys.data(), off.data(), n, now, arena.data(), arena.size(), gr.data(), &used);
-        if (st == PGS_INCOMPLETE && used > arena.size()) { arena.resize(used + 64); continue; }
-        break;
-    }
+    std::vector<std::string> keys;
+    for (uint32_t i = 0; i < n; i++) keys.push_back(make_key(bsv(fk[i].hash_key), bsv(fk[i].sort_key)));
+    std::vector<pgs_get_result> gr;
+    std::vector<uint8_t> arena;
+    int32_t st = point_lookup(s, keys, now, gr, arena);
     if (st != PGS_OK) return read_fail(r, st);
     for (uint32_t i = 0; i < n; i++) {
         if (gr[i].expired) { r.view.expire_count++; continue; }
@@ -398,10 +468,10 @@ static int32_t do_batch_get(Server &s, const pgs_full_key *fk, uint32_t n, uint3
 }
 
 // ---- on_sortkey_count (:1018-1086) --------------------------------------------------------------------------------
-static int32_t do_sortkey_count(Server &s, std::string_view hash_key, uint32_t now, Resp &r)
+static int32_t do_sortkey_count(Server &s, RLock &lk, std::string_view hash_key, uint32_t now, Resp &r)
 {
     r.reset(s.app_id, s.pidx);
-    int32_t st = s.prepare_read(now);
+    int32_t st = ensure_range_ready(s, lk, now);
     if (st != PGS_OK) return read_fail(r, st);
     std::string start = make_key(hash_key, {}), stop = make_next(start);
     pgs_scan_request rq{};
@@ -468,8 +538,10 @@ static int32_t scan_batch(Server &s, std::unique_ptr<ScanContext> ctx, bool star
     r.view.iteration_count = res.iter_count;
     r.view.expire_count = res.expire_count;
     r.view.filter_count = res.filter_count;
-    if (res.iter_valid && !res.complete) { // park the cursor (:1360-1387)
+    if (res.iter_valid && !res.complete) { // park the cursor (:1360-1387); it expires after 5 minutes (:1377-1385)
         ctx->resume = resume;
+        ctx->parked_at = now;
+        std::lock_guard<std::mutex> g(s.ctx_mu);
         int64_t handle = s.ctx_counter++;
         s.ctx[handle] = std::move(ctx);
         r.view.context_id = handle;
@@ -479,12 +551,13 @@ static int32_t scan_batch(Server &s, std::unique_ptr<ScanContext> ctx, bool star
     return r.seal(PGS_OK);
 }
 
-static int32_t do_get_scanner(Server &s, const pgs_get_scanner_request &q, uint32_t now, Resp &r)
+static int32_t do_get_scanner(Server &s, RLock &lk, const pgs_get_scanner_request &q, uint32_t now, Resp &r)
 {
     r.reset(s.app_id, s.pidx);
+    s.gc_contexts(now);
     if (!filter_type_supported(q.hash_key_filter_type) || !filter_type_supported(q.sort_key_filter_type))
         return r.seal(PGS_INVALID_ARGUMENT);
-    int32_t st = s.prepare_read(now);
+    int32_t st = ensure_range_ready(s, lk, now);
     if (st != PGS_OK) return read_fail(r, st);
     bool prefix_mode = s.opt.prefix_filter;
     if (s.opt.prefix_filter) { // :1188-1198
@@ -523,10 +596,15 @@ static int32_t do_get_scanner(Server &s, const pgs_get_scanner_request &q, uint3
 static int32_t do_scan(Server &s, int64_t context_id, uint32_t now, Resp &r)
 {
     r.reset(s.app_id, s.pidx);
-    auto f = s.ctx.find(context_id);
-    if (f == s.ctx.end()) return r.seal(PGS_NOT_FOUND); // :1542-1544
-    std::unique_ptr<ScanContext> ctx = std::move(f->second);
-    s.ctx.erase(f);
+    s.gc_contexts(now);
+    std::unique_ptr<ScanContext> ctx;
+    {
+        std::lock_guard<std::mutex> g(s.ctx_mu);
+        auto f = s.ctx.find(context_id);
+        if (f == s.ctx.end()) return r.seal(PGS_NOT_FOUND); // :1542-1544 (unknown, cleared or expired)
+        ctx = std::move(f->second);
+        s.ctx.erase(f);
+    }
     return scan_batch(s, std::move(ctx), true, 0, now, r);
 }
 
@@ -557,18 +635,30 @@ const pgs_response *pgs_response_view(pgs_response_buf *r) { return &r->r.view; 
 int32_t pgs_rrdb_update_app_envs(pgs_server *h, const char *envs, uint32_t n_envs, uint32_t now)
 {
     Server &s = h->s;
-    std::lock_guard<std::mutex> g(s.mu);
+    std::unique_lock<std::shared_mutex> g(s.mu);
     std::vector<std::pair<std::string, std::string>> kv;
     if (envs && n_envs) parse_envs(envs, n_envs, kv);
-    for (auto &e : kv) {
-        if (e.first == "default_ttl") { // update_default_ttl, pegasus_server_impl.cpp:2814-2826
-            s.default_ttl = (uint32_t)strtoul(e.second.c_str(), nullptr, 10);
-        } else if (e.first == "replica.split.validate_partition_hash") { // :2966-2983
-            s.validate_partition_hash = e.second == "true";
-        } else if (e.first == "user_specified_compaction") { // :2985-3001
-            s.ops_bin.clear();
-            if (!e.second.empty()) ops_parse(e.second, s.data_version, s.ops_bin, nullptr);
+    // update_app_envs hands over the table's whole env map (pegasus_server_impl.cpp:2728-2741): an absent key means "deleted"
+    {
+        std::map<std::string, std::string> em(kv.begin(), kv.end());
+        auto fd = em.find("default_ttl"); // update_default_ttl :2814-2826: buf2int32 and >= 0, otherwise the old value stays
+        if (fd != em.end()) {
+            char *endp = nullptr;
+            errno = 0;
+            const long long v = strtoll(fd->second.c_str(), &endp, 10);
+            if (!fd->second.empty() && !*endp && errno == 0 && v >= 0 && v <= INT32_MAX) s.default_ttl = (uint32_t)v;
         }
+        auto fv = em.find("replica.split.validate_partition_hash"); // :2966-2983: absent -> false, unparsable -> unchanged (buf2bool)
+        if (fv == em.end()) s.validate_partition_hash = false;
+        else {
+            std::string v = fv->second;
+            for (auto &c : v) c = (char)tolower((unsigned char)c);
+            if (v == "true") s.validate_partition_hash = true;
+            else if (v == "false") s.validate_partition_hash = false;
+        }
+        auto fo = em.find("user_specified_compaction"); // :2985-3001: absent -> cleared
+        if (fo == em.end()) s.ops_bin.clear();
+        else { s.ops_bin.clear(); if (!fo->second.empty()) ops_parse(fo->second, s.data_version, s.ops_bin, nullptr); }
     }
     // start_manual_compact_if_needed (pegasus_manual_compact_service.cpp:83-121): disabled flag, then the `once` rule:
     // trigger_time (unix seconds) newer than the last finished manual compaction.  (`periodic` HH:MM rules need the
@@ -626,82 +716,96 @@ void pgs_rrdb_stop(pgs_server *h)
 pgs_partition *pgs_rrdb_partition(pgs_server *h) { return h->s.part; }
 void pgs_rrdb_set_partition_version(pgs_server *h, int32_t pv) { h->s.partition_version = pv; }
 
-#define LOCKED(h) std::lock_guard<std::mutex> _g((h)->s.mu)
-int32_t pgs_rrdb_get(pgs_server *h, pgs_blob key, uint32_t now, pgs_response_buf *r) { LOCKED(h); return do_get(h->s, bsv(key), now, r->r, false); }
-int32_t pgs_rrdb_ttl(pgs_server *h, pgs_blob key, uint32_t now, pgs_response_buf *r) { LOCKED(h); return do_get(h->s, bsv(key), now, r->r, true); }
-int32_t pgs_rrdb_multi_get(pgs_server *h, const pgs_multi_get_request *q, uint32_t now, pgs_response_buf *r) { LOCKED(h); return do_multi_get(h->s, *q, now, r->r); }
-int32_t pgs_rrdb_batch_get(pgs_server *h, const pgs_full_key *k, uint32_t n, uint32_t now, pgs_response_buf *r) { LOCKED(h); return do_batch_get(h->s, k, n, now, r->r); }
-int32_t pgs_rrdb_sortkey_count(pgs_server *h, pgs_blob hk, uint32_t now, pgs_response_buf *r) { LOCKED(h); return do_sortkey_count(h->s, bsv(hk), now, r->r); }
-int32_t pgs_rrdb_get_scanner(pgs_server *h, const pgs_get_scanner_request *q, uint32_t now, pgs_response_buf *r) { LOCKED(h); return do_get_scanner(h->s, *q, now, r->r); }
-int32_t pgs_rrdb_scan(pgs_server *h, int64_t context_id, uint32_t now, pgs_response_buf *r) { LOCKED(h); return do_scan(h->s, context_id, now, r->r); }
-void pgs_rrdb_clear_scanner(pgs_server *h, int64_t context_id) { LOCKED(h); h->s.ctx.erase(context_id); }
+#define RLOCKED(h) RLock _g((h)->s.mu)
+#define WLOCKED(h) std::unique_lock<std::shared_mutex> _g((h)->s.mu)
+int32_t pgs_rrdb_get(pgs_server *h, pgs_blob key, uint32_t now, pgs_response_buf *r) { RLOCKED(h); return do_get(h->s, bsv(key), now, r->r, false); }
+int32_t pgs_rrdb_ttl(pgs_server *h, pgs_blob key, uint32_t now, pgs_response_buf *r) { RLOCKED(h); return do_get(h->s, bsv(key), now, r->r, true); }
+int32_t pgs_rrdb_multi_get(pgs_server *h, const pgs_multi_get_request *q, uint32_t now, pgs_response_buf *r) { RLOCKED(h); return do_multi_get(h->s, _g, *q, now, r->r); }
+int32_t pgs_rrdb_batch_get(pgs_server *h, const pgs_full_key *k, uint32_t n, uint32_t now, pgs_response_buf *r) { RLOCKED(h); return do_batch_get(h->s, k, n, now, r->r); }
+int32_t pgs_rrdb_sortkey_count(pgs_server *h, pgs_blob hk, uint32_t now, pgs_response_buf *r) { RLOCKED(h); return do_sortkey_count(h->s, _g, bsv(hk), now, r->r); }
+int32_t pgs_rrdb_get_scanner(pgs_server *h, const pgs_get_scanner_request *q, uint32_t now, pgs_response_buf *r) { RLOCKED(h); return do_get_scanner(h->s, _g, *q, now, r->r); }
+int32_t pgs_rrdb_scan(pgs_server *h, int64_t context_id, uint32_t now, pgs_response_buf *r) { RLOCKED(h); return do_scan(h->s, context_id, now, r->r); }
+void pgs_rrdb_clear_scanner(pgs_server *h, int64_t context_id) { std::lock_guard<std::mutex> g(h->s.ctx_mu); h->s.ctx.erase(context_id); }
+uint32_t pgs_rrdb_gc(pgs_server *h, uint32_t now) { return h->s.gc_contexts(now); }
 
 int32_t pgs_rrdb_get_many(pgs_server *h, const uint8_t *keys, const uint32_t *key_off, uint32_t n, uint32_t now,
                           uint8_t *arena, uint64_t arena_cap, pgs_get_result *results, uint64_t *arena_used)
 {
-    LOCKED(h);
-    int32_t st = h->s.prepare_read(now);
+    RLOCKED(h);
+    Server &s = h->s;
+    if (s.mem.empty()) return pgs_get_batch(s.part, keys, key_off, n, now, arena, arena_cap, results, arena_used);
+    // some keys may live in the memtable: answer those on the host, send the rest to the GPU
+    std::vector<std::string> ks;
+    for (uint32_t i = 0; i < n; i++) ks.emplace_back((const char *)keys + key_off[i], key_off[i + 1] - key_off[i]);
+    std::vector<pgs_get_result> gr;
+    std::vector<uint8_t> ar;
+    int32_t st = point_lookup(s, ks, now, gr, ar);
     if (st != PGS_OK) return st;
-    return pgs_get_batch(h->s.part, keys, key_off, n, now, arena, arena_cap, results, arena_used);
+    if (arena_used) *arena_used = ar.size();
+    memcpy(results, gr.data(), sizeof(pgs_get_result) * n);
+    if (ar.size() > arena_cap) return PGS_INCOMPLETE;
+    if (!ar.empty()) memcpy(arena, ar.data(), ar.size());
+    return PGS_OK;
 }
 
 int32_t pgs_rrdb_put(pgs_server *h, pgs_blob key, pgs_blob value, uint32_t expire_ts, int64_t decree,
                      uint64_t timestamp_us, uint32_t now)
 {
-    LOCKED(h);
+    WLOCKED(h);
+    h->s.last_committed_decree = decree;
     h->s.put_one(bsv(key), bsv(value), expire_ts, timestamp_us, now);
-    h->s.last_flushed_decree = decree;
     return PGS_OK;
 }
-int32_t pgs_rrdb_remove(pgs_server *h, pgs_blob key, int64_t decree)
+int32_t pgs_rrdb_remove(pgs_server *h, pgs_blob key, int64_t decree, uint32_t now)
 {
-    LOCKED(h);
-    h->s.mem_write(std::string(bsv(key)), PGS_TYPE_DELETION, std::string(), 0);
-    h->s.last_flushed_decree = decree;
+    WLOCKED(h);
+    h->s.last_committed_decree = decree;
+    h->s.mem_write(std::string(bsv(key)), PGS_TYPE_DELETION, std::string(), now);
     return PGS_OK;
 }
 int32_t pgs_rrdb_multi_put(pgs_server *h, pgs_blob hash_key, const pgs_blob *sort_keys, const pgs_blob *values,
                            uint32_t n, uint32_t expire_ts, int64_t decree, uint64_t timestamp_us, uint32_t now)
 {
-    LOCKED(h);
+    WLOCKED(h);
     Server &s = h->s;
-    s.last_flushed_decree = decree;
+    s.last_committed_decree = decree;
     if (n == 0) { // request.kvs is empty: kInvalidArgument, but an empty record still advances the decree
-        s.put_one({}, {}, 0, timestamp_us, 0); // empty_put (pegasus_write_service_impl.h:90-99,112-119)
+        s.put_one({}, {}, 0, timestamp_us, now); // empty_put (pegasus_write_service_impl.h:90-99,112-119)
         return PGS_INVALID_ARGUMENT;
     }
     for (uint32_t i = 0; i < n; i++) s.put_one(make_key(bsv(hash_key), bsv(sort_keys[i])), bsv(values[i]), expire_ts, timestamp_us, now);
     return PGS_OK;
 }
 int32_t pgs_rrdb_multi_remove(pgs_server *h, pgs_blob hash_key, const pgs_blob *sort_keys, uint32_t n, int64_t decree,
-                              int64_t *count)
+                              int64_t *count, uint32_t now)
 {
-    LOCKED(h);
+    WLOCKED(h);
     Server &s = h->s;
-    s.last_flushed_decree = decree;
+    s.last_committed_decree = decree;
     if (count) *count = 0;
     if (n == 0) {
-        s.put_one({}, {}, 0, 0, 0);
+        s.put_one({}, {}, 0, 0, now);
         return PGS_INVALID_ARGUMENT;
     }
-    for (uint32_t i = 0; i < n; i++) s.mem_write(make_key(bsv(hash_key), bsv(sort_keys[i])), PGS_TYPE_DELETION, std::string(), 0);
+    for (uint32_t i = 0; i < n; i++) s.mem_write(make_key(bsv(hash_key), bsv(sort_keys[i])), PGS_TYPE_DELETION, std::string(), now);
     if (count) *count = n;
     return PGS_OK;
 }
 int32_t pgs_rrdb_flush(pgs_server *h, uint32_t now)
 {
-    LOCKED(h);
+    WLOCKED(h);
     int32_t st = h->s.flush_mem();
     if (st != PGS_OK) return st;
     return h->s.maybe_compact(now);
 }
 int32_t pgs_rrdb_manual_compact(pgs_server *h, uint32_t now, pgs_compact_result *out)
 {
-    LOCKED(h);
+    WLOCKED(h);
     int32_t st = do_manual_compact(h->s, now, -1, true, out); // bottommost_level_compaction = force
     if (st == PGS_OK) h->s.manual_compact_last_finish_ms = ((uint64_t)now + kEpochBegin) * 1000;
     return st;
 }
-int64_t pgs_rrdb_last_flushed_decree(pgs_server *h) { return h->s.last_flushed_decree; }
+int64_t pgs_rrdb_last_flushed_decree(pgs_server *h) { RLOCKED(h); return h->s.last_flushed_decree; }
+int64_t pgs_rrdb_last_committed_decree(pgs_server *h) { RLOCKED(h); return h->s.last_committed_decree; }
 
 } // extern "C"

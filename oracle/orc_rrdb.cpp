@@ -8,6 +8,7 @@
 #include "orc_internal.h"
 
 #include <algorithm>
+#include <cerrno>
 #include <climits>
 #include <random>
 #include <unordered_map>
@@ -71,6 +72,7 @@ struct ScanContext { // pegasus_scan_context.h:33-95
     std::string hash_key_filter_pattern, sort_key_filter_pattern;
     int32_t batch_size;
     bool no_value, validate_partition_hash, return_expire_ts, only_return_count;
+    uint32_t parked_at = 0; // epoch seconds; a parked context lives 5 minutes (pegasus_server_impl.cpp:1377-1385)
 };
 
 struct Resp {
@@ -127,7 +129,7 @@ struct Server {
     int32_t partition_version = -1;
     std::vector<Op> ops;
     uint64_t last_seq = 0;
-    int64_t last_flushed_decree = 0;
+    int64_t last_committed_decree = 0, last_flushed_decree = 0;
     uint64_t manual_compact_last_finish_ms = 0;
     std::map<std::string, Rec> mem;
     uint64_t mem_bytes = 0;
@@ -167,6 +169,7 @@ struct Server {
     {
         mem_bytes = 0;
         if (mem.empty()) return;
+        last_flushed_decree = last_committed_decree;
         LRun lr{0, {}};
         for (auto &kv : mem) lr.run.recs.push_back(kv.second);
         mem.clear();
@@ -199,17 +202,29 @@ struct Server {
         while (l0 < runs.size() && runs[l0].level == 0) l0++;
         if (l0 >= trigger) compact_l0(now);
     }
-    // the product flushes the memtable before a read (and folds L0 once more than 12 runs pile up);
-    // both steps are invisible in RocksDB terms but the fold runs the compaction filter at `now`.
-    void prepare_read(uint32_t now)
+    // the product flushes the memtable before a RANGE read (and folds L0 once more than 12 runs pile up); point reads
+    // see the memtable in place.  Both steps are invisible in RocksDB terms but the fold runs the compaction filter at `now`.
+    void prepare_read(uint32_t now, bool range)
     {
+        if (!range) return;
+        if (mem.empty() && runs.size() <= 12) return;
         flush_mem();
         if (runs.size() > 12) compact_l0(now);
+    }
+    uint32_t gc_contexts(uint32_t now)
+    {
+        uint32_t n = 0;
+        for (auto it = ctx.begin(); it != ctx.end();) {
+            if (now >= it->second->parked_at && now - it->second->parked_at >= 300) { it = ctx.erase(it); n++; }
+            else ++it;
+        }
+        return n;
     }
     std::shared_ptr<View> get_view()
     {
         if (view) return view;
         std::vector<const Rec *> all;
+        for (auto &kv : mem) all.push_back(&kv.second); // the memtable holds the newest versions
         for (auto &lr : runs)
             for (auto &r : lr.run.recs) all.push_back(&r);
         std::stable_sort(all.begin(), all.end(), [](const Rec *a, const Rec *b) {
@@ -278,7 +293,7 @@ static inline bool filter_type_supported(int t) { return t >= PGS_FT_NO_FILTER &
 static int32_t on_get(Server &s, sv key, uint32_t now, Resp &r)
 {
     r.reset(s.app_id, s.pidx);
-    s.prepare_read(now);
+    s.prepare_read(now, false);
     std::string value;
     int32_t st = s.db_get(key, &value) ? PGS_OK : PGS_NOT_FOUND;
     if (st == PGS_OK && ts_expired(now, extract_expire_ts(s.data_version, value))) {
@@ -295,7 +310,7 @@ static int32_t on_get(Server &s, sv key, uint32_t now, Resp &r)
 static int32_t on_ttl(Server &s, sv key, uint32_t now, Resp &r)
 {
     r.reset(s.app_id, s.pidx);
-    s.prepare_read(now);
+    s.prepare_read(now, false);
     std::string value;
     int32_t st = s.db_get(key, &value) ? PGS_OK : PGS_NOT_FOUND;
     uint32_t expire_ts = 0;
@@ -318,7 +333,7 @@ static int32_t on_multi_get(Server &s, const pgs_multi_get_request &q, uint32_t 
         r.seal();
         return r.view.error;
     }
-    s.prepare_read(now);
+    s.prepare_read(now, q.n_sort_keys == 0);
     uint32_t cfg_count = s.opt.rocksdb_multi_get_max_iteration_count ? s.opt.rocksdb_multi_get_max_iteration_count : 3000;
     uint64_t cfg_size = s.opt.rocksdb_multi_get_max_iteration_size ? s.opt.rocksdb_multi_get_max_iteration_size : 30ull << 20;
     uint32_t max_kv_count = cfg_count, max_iteration_count = cfg_count;
@@ -436,7 +451,7 @@ static int32_t on_batch_get(Server &s, const pgs_full_key *keys, uint32_t n, uin
 {
     r.reset(s.app_id, s.pidx);
     if (n == 0) { r.view.error = PGS_INVALID_ARGUMENT; r.seal(); return r.view.error; }
-    s.prepare_read(now);
+    s.prepare_read(now, false);
     for (uint32_t i = 0; i < n; i++) {
         std::string key = generate_key(bsv(keys[i].hash_key), bsv(keys[i].sort_key));
         std::string value;
@@ -456,7 +471,7 @@ static int32_t on_batch_get(Server &s, const pgs_full_key *keys, uint32_t n, uin
 static int32_t on_sortkey_count(Server &s, sv hash_key, uint32_t now, Resp &r)
 {
     r.reset(s.app_id, s.pidx);
-    s.prepare_read(now);
+    s.prepare_read(now, true);
     std::string start = generate_key(hash_key, sv()), stop = next_blob(hash_key);
     Iter it;
     it.v = s.get_view();
@@ -512,7 +527,8 @@ static int32_t on_get_scanner(Server &s, const pgs_get_scanner_request &q, uint3
         r.seal();
         return r.view.error;
     }
-    s.prepare_read(now);
+    s.gc_contexts(now);
+    s.prepare_read(now, true);
     bool prefix_same_as_start = s.opt.prefix_filter;
     if (s.opt.prefix_filter) {
         sv hk, sk;
@@ -559,6 +575,7 @@ static int32_t on_get_scanner(Server &s, const pgs_get_scanner_request &q, uint3
         ctx->validate_partition_hash = q.validate_partition_hash;
         ctx->return_expire_ts = q.return_expire_ts;
         ctx->only_return_count = q.only_return_count;
+        ctx->parked_at = now;
         int64_t handle = s.ctx_counter++;
         s.ctx[handle] = std::move(ctx);
         r.view.context_id = handle;
@@ -573,6 +590,7 @@ static int32_t on_get_scanner(Server &s, const pgs_get_scanner_request &q, uint3
 static int32_t on_scan(Server &s, int64_t context_id, uint32_t now, Resp &r)
 {
     r.reset(s.app_id, s.pidx);
+    s.gc_contexts(now);
     auto f = s.ctx.find(context_id);
     if (f == s.ctx.end()) { r.view.error = PGS_NOT_FOUND; r.seal(); return r.view.error; }
     std::unique_ptr<ScanContext> ctx = std::move(f->second);
@@ -589,6 +607,7 @@ static int32_t on_scan(Server &s, int64_t context_id, uint32_t now, Resp &r)
     if (ctx->only_return_count) r.view.kv_count = count;
     r.view.error = PGS_OK;
     if (ctx->it.Valid() && !complete) {
+        ctx->parked_at = now;
         int64_t handle = s.ctx_counter++;
         s.ctx[handle] = std::move(ctx);
         r.view.context_id = handle;
@@ -629,14 +648,27 @@ int32_t orc_rrdb_update_app_envs(orc_server *h, const char *envs, uint32_t n_env
     Server &s = h->s;
     std::vector<std::pair<std::string, std::string>> kv;
     parse_envs(envs, n_envs, kv);
-    for (auto &e : kv) {
-        if (e.first == "default_ttl") { // pegasus_server_impl.cpp:2814-2826
-            s.default_ttl = (uint32_t)strtoul(e.second.c_str(), nullptr, 10);
-        } else if (e.first == "replica.split.validate_partition_hash") { // :2966-2983
-            s.validate_partition_hash = e.second == "true";
-        } else if (e.first == "user_specified_compaction") { // :2985-3001
-            s.ops = e.second.empty() ? std::vector<Op>() : ops_from_json(e.second, s.data_version);
+    // update_app_envs hands over the table's whole env map (pegasus_server_impl.cpp:2728-2741): an absent key means "deleted"
+    {
+        std::map<std::string, std::string> em(kv.begin(), kv.end());
+        auto fd = em.find("default_ttl"); // update_default_ttl :2814-2826: buf2int32 and >= 0, otherwise the old value stays
+        if (fd != em.end()) {
+            char *endp = nullptr;
+            errno = 0;
+            const long long v = strtoll(fd->second.c_str(), &endp, 10);
+            if (!fd->second.empty() && !*endp && errno == 0 && v >= 0 && v <= INT32_MAX) s.default_ttl = (uint32_t)v;
         }
+        auto fv = em.find("replica.split.validate_partition_hash"); // :2966-2983: absent -> false, unparsable -> unchanged (buf2bool)
+        if (fv == em.end()) s.validate_partition_hash = false;
+        else {
+            std::string v = fv->second;
+            for (auto &c : v) c = (char)tolower((unsigned char)c);
+            if (v == "true") s.validate_partition_hash = true;
+            else if (v == "false") s.validate_partition_hash = false;
+        }
+        auto fo = em.find("user_specified_compaction"); // :2985-3001: absent -> cleared
+        if (fo == em.end()) s.ops.clear();
+        else s.ops = fo->second.empty() ? std::vector<Op>() : ops_from_json(fo->second, s.data_version);
     }
     // pegasus_manual_compact_service.cpp:83-121,160-173,217-262: disabled flag, `once` rule, options
     std::map<std::string, std::string> m(kv.begin(), kv.end());
@@ -706,6 +738,7 @@ int32_t orc_rrdb_scan(orc_server *s, int64_t context_id, uint32_t now, pgs_respo
     return on_scan(s->s, context_id, now, R(r));
 }
 void orc_rrdb_clear_scanner(orc_server *s, int64_t context_id) { s->s.ctx.erase(context_id); }
+uint32_t orc_rrdb_gc(orc_server *s, uint32_t now) { return s->s.gc_contexts(now); }
 
 // write_batch_put_ctx: rocksdb_wrapper.cpp:129-183 (local write, no timetag verification)
 static void put_one(Server &s, sv raw_key, sv user_value, uint32_t expire_ts, uint64_t timestamp_us, uint32_t now)
@@ -719,35 +752,35 @@ static void put_one(Server &s, sv raw_key, sv user_value, uint32_t expire_ts, ui
     r.value = generate_value(s.data_version, expire_ts, timetag, user_value);
     s.write(std::move(r), now);
 }
-static void del_one(Server &s, sv raw_key)
+static void del_one(Server &s, sv raw_key, uint32_t now)
 {
     Rec r;
     r.ukey = std::string(raw_key);
     r.seq = ++s.last_seq;
     r.type = PGS_TYPE_DELETION;
-    s.write(std::move(r), 0);
+    s.write(std::move(r), now);
 }
 
 int32_t orc_rrdb_put(orc_server *h, pgs_blob key, pgs_blob value, uint32_t expire_ts, int64_t decree,
                      uint64_t timestamp_us, uint32_t now)
 {
+    h->s.last_committed_decree = decree;
     put_one(h->s, bsv2(key), bsv2(value), expire_ts, timestamp_us, now);
-    h->s.last_flushed_decree = decree;
     return PGS_OK;
 }
-int32_t orc_rrdb_remove(orc_server *h, pgs_blob key, int64_t decree)
+int32_t orc_rrdb_remove(orc_server *h, pgs_blob key, int64_t decree, uint32_t now)
 {
-    del_one(h->s, bsv2(key));
-    h->s.last_flushed_decree = decree;
+    h->s.last_committed_decree = decree;
+    del_one(h->s, bsv2(key), now);
     return PGS_OK;
 }
 int32_t orc_rrdb_multi_put(orc_server *h, pgs_blob hash_key, const pgs_blob *sort_keys, const pgs_blob *values,
                            uint32_t n, uint32_t expire_ts, int64_t decree, uint64_t timestamp_us, uint32_t now)
 {
     Server &s = h->s;
-    s.last_flushed_decree = decree;
+    s.last_committed_decree = decree;
     if (n == 0) { // pegasus_write_service_impl.h:112-119: empty_put + kInvalidArgument
-        put_one(s, sv(), sv(), 0, timestamp_us, 0);
+        put_one(s, sv(), sv(), 0, timestamp_us, now);
         return PGS_INVALID_ARGUMENT;
     }
     for (uint32_t i = 0; i < n; i++)
@@ -755,16 +788,16 @@ int32_t orc_rrdb_multi_put(orc_server *h, pgs_blob hash_key, const pgs_blob *sor
     return PGS_OK;
 }
 int32_t orc_rrdb_multi_remove(orc_server *h, pgs_blob hash_key, const pgs_blob *sort_keys, uint32_t n,
-                              int64_t decree, int64_t *count)
+                              int64_t decree, int64_t *count, uint32_t now)
 {
     Server &s = h->s;
-    s.last_flushed_decree = decree;
+    s.last_committed_decree = decree;
     if (count) *count = 0;
     if (n == 0) {
-        put_one(s, sv(), sv(), 0, 0, 0);
+        put_one(s, sv(), sv(), 0, 0, now);
         return PGS_INVALID_ARGUMENT;
     }
-    for (uint32_t i = 0; i < n; i++) del_one(s, generate_key(bsv2(hash_key), bsv2(sort_keys[i])));
+    for (uint32_t i = 0; i < n; i++) del_one(s, generate_key(bsv2(hash_key), bsv2(sort_keys[i])), now);
     if (count) *count = n;
     return PGS_OK;
 }
@@ -789,6 +822,7 @@ int32_t orc_rrdb_manual_compact(orc_server *h, uint32_t now, orc_compact_stats *
     return PGS_OK;
 }
 int64_t orc_rrdb_last_flushed_decree(orc_server *h) { return h->s.last_flushed_decree; }
+int64_t orc_rrdb_last_committed_decree(orc_server *h) { return h->s.last_committed_decree; }
 uint32_t orc_rrdb_run_count(orc_server *h) { return (uint32_t)h->s.runs.size(); }
 orc_run *orc_rrdb_dump(orc_server *h)
 {

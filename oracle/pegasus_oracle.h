@@ -178,15 +178,17 @@ ORC_API int32_t orc_rrdb_scan(orc_server *s, int64_t context_id, uint32_t now,
 ORC_API void orc_rrdb_clear_scanner(orc_server *s, int64_t context_id);
 ORC_API int32_t orc_rrdb_put(orc_server *s, pgs_blob key, pgs_blob value, uint32_t expire_ts,
                              int64_t decree, uint64_t timestamp_us, uint32_t now);
-ORC_API int32_t orc_rrdb_remove(orc_server *s, pgs_blob key, int64_t decree);
+ORC_API int32_t orc_rrdb_remove(orc_server *s, pgs_blob key, int64_t decree, uint32_t now);
 ORC_API int32_t orc_rrdb_multi_put(orc_server *s, pgs_blob hash_key, const pgs_blob *sort_keys,
                                    const pgs_blob *values, uint32_t n, uint32_t expire_ts,
                                    int64_t decree, uint64_t timestamp_us, uint32_t now);
 ORC_API int32_t orc_rrdb_multi_remove(orc_server *s, pgs_blob hash_key, const pgs_blob *sort_keys,
-                                      uint32_t n, int64_t decree, int64_t *count);
+                                      uint32_t n, int64_t decree, int64_t *count, uint32_t now);
 ORC_API int32_t orc_rrdb_flush(orc_server *s, uint32_t now);
 ORC_API int32_t orc_rrdb_manual_compact(orc_server *s, uint32_t now, orc_compact_stats *st);
 ORC_API int64_t orc_rrdb_last_flushed_decree(orc_server *s);
+ORC_API int64_t orc_rrdb_last_committed_decree(orc_server *s);
+ORC_API uint32_t orc_rrdb_gc(orc_server *s, uint32_t now);
 /* test hook: number of runs / export of the whole visible state as one run */
 ORC_API uint32_t orc_rrdb_run_count(orc_server *s);
 ORC_API orc_run *orc_rrdb_dump(orc_server *s);

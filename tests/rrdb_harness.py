@@ -67,18 +67,20 @@ class Backend:
             "rrdb_get_scanner": [vp, C.POINTER(GetScannerRequest), C.c_uint32, vp],
             "rrdb_scan": [vp, C.c_int64, C.c_uint32, vp], "rrdb_clear_scanner": [vp, C.c_int64],
             "rrdb_put": [vp, Blob, Blob, C.c_uint32, C.c_int64, C.c_uint64, C.c_uint32],
-            "rrdb_remove": [vp, Blob, C.c_int64],
+            "rrdb_remove": [vp, Blob, C.c_int64, C.c_uint32],
             "rrdb_multi_put": [vp, Blob, C.POINTER(Blob), C.POINTER(Blob), C.c_uint32, C.c_uint32, C.c_int64,
                                C.c_uint64, C.c_uint32],
-            "rrdb_multi_remove": [vp, Blob, C.POINTER(Blob), C.c_uint32, C.c_int64, C.POINTER(C.c_int64)],
+            "rrdb_multi_remove": [vp, Blob, C.POINTER(Blob), C.c_uint32, C.c_int64, C.POINTER(C.c_int64), C.c_uint32],
             "rrdb_flush": [vp, C.c_uint32], "rrdb_manual_compact": [vp, C.c_uint32, vp],
             "rrdb_update_app_envs": [vp, C.c_char_p, C.c_uint32, C.c_uint32],
             "rrdb_set_partition_version": [vp, C.c_int32], "rrdb_stop": [vp],
-            "rrdb_last_flushed_decree": [vp],
+            "rrdb_last_flushed_decree": [vp], "rrdb_last_committed_decree": [vp], "rrdb_gc": [vp, C.c_uint32],
         }
         for n, a in sigs.items():
             f(n).argtypes = a
         f("rrdb_last_flushed_decree").restype = C.c_int64
+        f("rrdb_last_committed_decree").restype = C.c_int64
+        f("rrdb_gc").restype = C.c_uint32
         f("rrdb_clear_scanner").restype = None
         f("rrdb_set_partition_version").restype = None
         f("rrdb_stop").restype = None
@@ -102,10 +104,10 @@ class Backend:
         self.decree += 1
         return self.f("rrdb_put")(self.h, blob(raw_key(hk, sk), keep), blob(value, keep), expire_ts, self.decree, ts_us, now)
 
-    def remove(self, hk, sk):
+    def remove(self, hk, sk, now=0):
         keep = []
         self.decree += 1
-        return self.f("rrdb_remove")(self.h, blob(raw_key(hk, sk), keep), self.decree)
+        return self.f("rrdb_remove")(self.h, blob(raw_key(hk, sk), keep), self.decree, now)
 
     def multi_put(self, hk, kvs: dict, expire_ts=0, now=0, ts_us=1):
         keep = []
@@ -115,12 +117,12 @@ class Backend:
         vals = (Blob * max(1, len(items)))(*[blob(v, keep) for _, v in items])
         return self.f("rrdb_multi_put")(self.h, blob(hk, keep), sks, vals, len(items), expire_ts, self.decree, ts_us, now)
 
-    def multi_remove(self, hk, sort_keys):
+    def multi_remove(self, hk, sort_keys, now=0):
         keep = []
         self.decree += 1
         sks = (Blob * max(1, len(sort_keys)))(*[blob(k, keep) for k in sort_keys])
         cnt = C.c_int64()
-        st = self.f("rrdb_multi_remove")(self.h, blob(hk, keep), sks, len(sort_keys), self.decree, C.byref(cnt))
+        st = self.f("rrdb_multi_remove")(self.h, blob(hk, keep), sks, len(sort_keys), self.decree, C.byref(cnt), now)
         return st, cnt.value
 
     def flush(self, now=0):

@@ -176,7 +176,7 @@ int32_t sim_compact(uint32_t k, const uint8_t **data, const uint64_t *data_bytes
     if (group_lanes) {
         if (group_lanes < k || (group_lanes != 8 && group_lanes != 16 && group_lanes != 32)) return PGS_INVALID_ARGUMENT;
         geo.G = group_lanes;
-        geo.walk_dyn = 2048 + (kWalkThreads / geo.G) * P.group_smem;
+        geo.walk_dyn = 2048 + kMaxRuns * (uint32_t)sizeof(RunDev) + (kWalkThreads / geo.G) * P.group_smem;
     }
     const uint64_t Q = P.Q;
     std::vector<uint32_t> split_pos((Q + 1) * k, 0xFFFFFFFFu), split_ref(Q + 1, 0xFFFFFFFFu), ticket(64, 0);
@@ -206,6 +206,7 @@ int32_t sim_compact(uint32_t k, const uint8_t **data, const uint64_t *data_bytes
         P.crc_table = (const unsigned long long *)crc_tab;
     }
     PGS_LAUNCH(k_plan, (T.total_blocks + 255) / 256, 256, 0, 0, P);
+    PGS_LAUNCH(k_seg_bounds, (P.Q + 255) / 256, 256, 0, 0, P);
     PGS_LAUNCH(k_seg_layout, 1, 1024, 0, 0, P);
     if (!st.error) {
         if (geo.G == 8) PGS_LAUNCH(k_walk<8>, 2, kWalkThreads, geo.walk_dyn, 0, P);
