@@ -100,8 +100,10 @@ PGS_API uint64_t pgs_engine_launches(pgs_engine *e);
 /* device time (CUDA events on the engine stream) of the kernels of the last pgs_get_batch /
  * pgs_range_scan(_many) call, without the host<->device copies around them */
 PGS_API float pgs_engine_last_kernel_ms(pgs_engine *e);
-/* data blocks fetched by the last pgs_get_batch (one per run probed per key) */
+/* data blocks fetched by the calling thread's last pgs_get_batch (one per run probed per key), and the run probes its
+ * Bloom filters saved.  (These three getters are per calling thread: readers run concurrently.) */
 PGS_API uint64_t pgs_engine_last_blocks_probed(pgs_engine *e);
+PGS_API uint64_t pgs_engine_last_runs_skipped(pgs_engine *e);
 /* thread-local description of the last failure on the calling thread */
 PGS_API const char *pgs_last_error(void);
 

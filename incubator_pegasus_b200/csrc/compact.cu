@@ -13,6 +13,14 @@ namespace pgs {
 const uint64_t *crc64_table();
 static uint64_t *g_crc_dev[16] = {nullptr};
 static std::mutex g_crc_mu;
+// the opt-in shared-memory maximum of the compaction kernels, once per device (a per-call cudaFuncSetAttribute would race)
+int32_t compact_init_kernels(int max_smem)
+{
+    PGS_CUDA(cudaFuncSetAttribute(k_walk<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PGS_CUDA(cudaFuncSetAttribute(k_walk<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PGS_CUDA(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    return PGS_OK;
+}
 } // namespace pgs
 
 using namespace pgs;
@@ -57,6 +65,7 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     MergeParams P{};
     P.k = k;
     CompactTotals T{};
+    uint64_t bloom_entries = 0;
     for (uint32_t i = 0; i < k; i++) {
         P.runs[i] = in[i]->dev();
         const pgs_run_info &fi = in[i]->info;
@@ -68,6 +77,7 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
         T.raw_key += fi.raw_key_bytes;
         T.raw_val += fi.raw_value_bytes;
         T.in_block_bytes += fi.data_bytes;
+        bloom_entries += in[i]->n_bloom_entries ? in[i]->n_bloom_entries : 2 * fi.n_records;
         if (fi.n_blocks >= (1u << 28) || fi.data_bytes >= (1ull << 40)) return PGS_NOT_SUPPORTED;
     }
     if (T.max_ukey > kMaxUkeyLen) { set_error("compact: user key of %u bytes > %u", T.max_ukey, kMaxUkeyLen); return PGS_NOT_SUPPORTED; }
@@ -122,6 +132,9 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     CK(cudaMallocAsync(&outr->d_ikey_off, sizeof(uint32_t) * (geo.blk_cap + 1), st));
     CK(cudaMallocAsync(&outr->d_ikeys, geo.ikey_cap, st));
     CK(cudaMallocAsync(&outr->d_rec_off, sizeof(uint32_t) * (T.n_rec + 1), st));
+    outr->bloom_lines = bloom_lines_for(bloom_entries);
+    CK(cudaMallocAsync(&outr->d_bloom, (size_t)outr->bloom_lines * 64, st));
+    CK(cudaMemsetAsync(outr->d_bloom, 0, (size_t)outr->bloom_lines * 64, st));
     CK(cudaMallocAsync(&d_split_pos, sizeof(uint32_t) * (Q + 1) * k, st));
     CK(cudaMallocAsync(&d_split_ref, sizeof(uint32_t) * (Q + 1), st));
     CK(cudaMallocAsync(&d_ticket, 256, st));
@@ -165,13 +178,13 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     P.out_ikey_off = outr->d_ikey_off;
     P.out_ikeys = outr->d_ikeys;
     P.out_rec_off = outr->d_rec_off;
+    P.out_bloom = outr->d_bloom;
+    P.out_bloom_lines = outr->bloom_lines;
     P.stats = d_stats;
 
     cudaEvent_t ev[4];
     for (auto &x : ev) CK(cudaEventCreate(&x));
     auto walk = geo.G == 8 ? k_walk<8> : k_walk<16>;
-    CK(cudaFuncSetAttribute(walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(geo.walk_dyn, 48u * 1024)));
-    CK(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(geo.emit_dyn, 48u * 1024)));
     int occ_w = 0, occ_e = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, walk, (int)kWalkThreads, (size_t)geo.walk_dyn));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_emit, (int)(geo.emit_warps * 32), (size_t)geo.emit_dyn));
@@ -227,6 +240,7 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     outr->info.max_block_records = (uint32_t)hs.max_blk_rec;
     outr->info.smallest_seq = hs.tot_recs ? ~hs.min_seq_inv : ~0ull;
     outr->info.largest_seq = hs.max_seq;
+    outr->n_bloom_entries = hs.bloom_entries;
     {
         std::lock_guard<std::mutex> g(part.mu);
         if (!(flags & PGS_COMPACT_KEEP_INPUTS))

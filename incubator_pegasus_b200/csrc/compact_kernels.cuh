@@ -62,13 +62,13 @@ struct __align__(16) SegBase { // exclusive prefixes over the segments (k_seg_sc
 struct MergeStats {
     unsigned long long in_records, in_bytes, out_records, out_bytes;
     unsigned long long dropped_shadowed, dropped_tombstone, dropped_expired, dropped_user, dropped_stale, ttl_rewritten;
-    unsigned long long out_tomb, out_raw_key, out_raw_val, spare0, spare1, spare2;
+    unsigned long long out_tomb, out_raw_key, out_raw_val, bloom_entries, spare1, spare2;
     unsigned long long max_ukey, max_vlen, max_blk_size, max_blk_rec, max_seq, min_seq_inv; // maxima (min_seq kept as ~min)
     unsigned long long tot_bytes, tot_blocks, tot_recs, tot_keyb; // k_seg_scan
     uint32_t error, error_seg;
 };
 enum { ST_IN_REC = 0, ST_IN_BYTES, ST_OUT_REC, ST_OUT_BYTES, ST_SHADOW, ST_TOMB, ST_EXPIRED, ST_USER, ST_STALE, ST_TTL,
-       ST_OUT_TOMB, ST_OUT_KEY, ST_OUT_VAL };
+       ST_OUT_TOMB, ST_OUT_KEY, ST_OUT_VAL, ST_BLOOM };
 enum { SM_UKEY = 0, SM_VLEN, SM_BLK_SIZE, SM_BLK_REC, SM_MAX_SEQ, SM_MIN_SEQ_INV };
 
 struct MergeParams {
@@ -107,6 +107,8 @@ struct MergeParams {
     uint8_t *out_ikeys;
     uint32_t out_blk_cap, out_ikey_cap;
     unsigned long long out_rec_cap;
+    uint32_t *out_bloom; // the new run's Bloom filter (zeroed by the host), out_bloom_lines lines of 64 bytes
+    uint32_t out_bloom_lines;
     MergeStats *stats;
 };
 
@@ -519,7 +521,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
     unsigned long long out_bytes = 0;
     bool have_head = false, head_in_A = false, prev_big = false;
     uint32_t head_len = 0;
-    uint32_t d1 = 0;
+    uint32_t d1 = 0, prev_pl = 0xFFFFFFFFu;
     bool d1_valid = false;
     auto close_block = [&]() { // bookkeeping of a finished block (k_emit derives the same numbers)
         const uint32_t size = blk_bytes + 4 * (nrest + 1);
@@ -574,6 +576,19 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         const bool cmp2 = keep && !restart && !(have_head && head_in_A);
         if (g.any(cmp2)) row_cmp(g, cmp2, row, ulen, rowA, lenA, shared);
         if (keep && !restart && have_head && head_in_A) shared = lcp_head;
+        if (P.out_bloom_lines) { // the new run's Bloom filter: the user key, and its hash-key prefix when that changed
+            const bool lcp_known = keep && (cmp2 || (have_head && head_in_A));
+            const uint32_t lcp_out = cmp2 ? shared : lcp_head;
+            const unsigned long long hk = bloom_hash_row(g, row, keep ? ulen : 0u);
+            if (keep && g.gl < 6) bloom_add_bit(P.out_bloom, P.out_bloom_lines, hk, g.gl);
+            const uint32_t pl = keep ? hashkey_prefix_len((const uint8_t *)row, ulen) : 0u;
+            const bool new_prefix = keep && pl && !(lcp_known && pl == prev_pl && lcp_out >= pl);
+            if (g.any(new_prefix)) {
+                const unsigned long long hp = bloom_hash_row(g, row, new_prefix ? pl : 0u);
+                if (new_prefix && g.gl < 6) bloom_add_bit(P.out_bloom, P.out_bloom_lines, hp, g.gl);
+            }
+            if (keep) { prev_pl = pl; STAT_ADD(ST_BLOOM, new_prefix ? 2 : 1); }
+        }
         if (keep) {
             const uint32_t otype = tomb ? (uint32_t)PGS_TYPE_DELETION : type;
             const unsigned long long seq = (P.bottommost && otype == PGS_TYPE_VALUE) ? 0ull : (tr >> 8);

@@ -7,8 +7,8 @@
 #include <algorithm>
 #include <cstring>
 
-#include "device_util.cuh"
 #include "engine.h"
+#include "read_kernels.cuh"
 
 namespace pgs {
 
@@ -79,6 +79,7 @@ Run::~Run()
         cudaFreeAsync(d_ikey_off, pool_stream);
         cudaFreeAsync(d_ikeys, pool_stream);
         cudaFreeAsync(d_rec_off, pool_stream);
+        cudaFreeAsync(d_bloom, pool_stream);
         return;
     }
     cudaFree(d_data);
@@ -88,6 +89,7 @@ Run::~Run()
     cudaFree(d_ikey_off);
     cudaFree(d_ikeys);
     cudaFree(d_rec_off);
+    cudaFree(d_bloom);
 }
 Engine::~Engine()
 {
@@ -98,10 +100,22 @@ Engine::~Engine()
     for (auto &s : spares) cudaFreeAsync(s.p, stream);
     spares.clear();
     if (h_pinned) cudaFreeHost(h_pinned);
-    if (ev_a) cudaEventDestroy(ev_a);
-    if (ev_b) cudaEventDestroy(ev_b);
+    for (auto &s : rd_streams) if (s) cudaStreamDestroy(s);
     if (stream) cudaStreamDestroy(stream);
 }
+cudaStream_t Engine::read_stream()
+{
+    static std::atomic<uint32_t> next{0};
+    thread_local uint32_t mine = next.fetch_add(1);
+    return rd_streams[mine % kReadStreams];
+}
+// device time of the calling thread's last read call (the getters of the ABI are per thread: readers run concurrently)
+static thread_local float t_last_ms = 0.f;
+static thread_local uint64_t t_last_probed = 0, t_last_skipped = 0;
+void set_last_read_stats(float ms, uint64_t probed, uint64_t skipped) { t_last_ms = ms; t_last_probed = probed; t_last_skipped = skipped; }
+int32_t lookup_init_kernels(int max_smem);
+int32_t compact_init_kernels(int max_smem);
+
 void *Engine::pinned(size_t bytes)
 {
     if (bytes > h_pinned_cap) {
@@ -132,7 +146,7 @@ void Partition::insert(std::shared_ptr<Run> r)
 // shared-memory scratch.
 // ------------------------------------------------------------------------------------------------
 struct IndexStats {
-    unsigned long long n_records, n_tomb, raw_key, raw_val, min_seq, max_seq;
+    unsigned long long n_records, n_tomb, raw_key, raw_val, min_seq, max_seq, n_prefix;
     uint32_t max_ukey, max_vlen, max_blk_rec, error;
 };
 constexpr uint32_t kIdxWarps = 8;
@@ -144,8 +158,9 @@ k_index_walk(const uint8_t *__restrict__ data, const uint64_t *__restrict__ blk_
              const uint32_t *__restrict__ blk_size, uint32_t nb, uint32_t *__restrict__ nrec_out,
              uint32_t *__restrict__ lastlen_out, const uint32_t *__restrict__ ikey_off,
              uint8_t *__restrict__ ikeys, const uint32_t *__restrict__ blk_rec, uint32_t *__restrict__ rec_off,
-             IndexStats *__restrict__ stats)
+             uint32_t *__restrict__ bloom, uint32_t bloom_lines, IndexStats *__restrict__ stats)
 {
+    const Grp<32> g;
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t b = blockIdx.x * kIdxWarps + warp;
@@ -164,7 +179,7 @@ k_index_walk(const uint8_t *__restrict__ data, const uint64_t *__restrict__ blk_
     uint32_t limit = err ? 0 : size - 4 - 4 * nr;
     uint32_t p = 0, prev_klen = 0, nrec = 0;
     unsigned long long raw_key = 0, raw_val = 0, n_tomb = 0, min_seq = ~0ull, max_seq = 0;
-    uint32_t max_ukey = 0, max_vlen = 0;
+    uint32_t max_ukey = 0, max_vlen = 0, n_prefix = 0, prev_pl = 0xFFFFFFFFu;
     while (!err && p < limit) {
         uint32_t shared, non_shared, vlen, h = 0, c;
         c = get_varint32(base + p, limit - p, shared);
@@ -178,6 +193,22 @@ k_index_walk(const uint8_t *__restrict__ data, const uint64_t *__restrict__ blk_
         for (uint32_t i = lane; i < non_shared; i += 32) scr[shared + i] = base[p + h + i];
         if (kEmitKey && lane == 0) rec_off[blk_rec[b] + nrec] = p;
         __syncwarp();
+        { // Bloom entries: the whole user key, and its hash-key prefix whenever that differs from the previous entry's
+            const uint32_t ulen = klen - 8;
+            const uint32_t pl = hashkey_prefix_len(scr, ulen);
+            const bool new_prefix = pl != 0 && (pl != prev_pl || shared < pl);
+            prev_pl = pl;
+            if (kEmitKey) {
+                if (bloom_lines) {
+                    const unsigned long long hk = bloom_hash_row(g, (const uint32_t *)scr, ulen);
+                    if (lane < 6) bloom_add_bit(bloom, bloom_lines, hk, lane);
+                    if (new_prefix) {
+                        const unsigned long long hp = bloom_hash_row(g, (const uint32_t *)scr, pl);
+                        if (lane < 6) bloom_add_bit(bloom, bloom_lines, hp, lane);
+                    }
+                }
+            } else if (new_prefix) n_prefix++;
+        }
         if (!kEmitKey && lane == 0) {
             unsigned long long tr = 0;
             for (int i = 7; i >= 0; i--) tr = (tr << 8) | scr[klen - 8 + i];
@@ -209,6 +240,7 @@ k_index_walk(const uint8_t *__restrict__ data, const uint64_t *__restrict__ blk_
         atomicAdd(&stats->n_tomb, n_tomb);
         atomicAdd(&stats->raw_key, raw_key);
         atomicAdd(&stats->raw_val, raw_val);
+        atomicAdd(&stats->n_prefix, (unsigned long long)n_prefix);
         atomicMin(&stats->min_seq, min_seq);
         atomicMax(&stats->max_seq, max_seq);
         atomicMax(&stats->max_ukey, max_ukey);
@@ -235,7 +267,7 @@ int32_t build_index(Engine *e, Run *r, const uint64_t *h_blk_off, const uint32_t
     PGS_CUDA(cudaFuncSetAttribute(k_index_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PGS_CUDA(cudaFuncSetAttribute(k_index_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_index_walk<false><<<grid, kIdxWarps * 32, smem, st>>>(r->d_data, r->d_blk_off, r->d_blk_size, nb, d_nrec,
-                                                            d_lastlen, nullptr, nullptr, nullptr, nullptr, d_stats);
+                                                            d_lastlen, nullptr, nullptr, nullptr, nullptr, nullptr, 0, d_stats);
     e->launches++;
     std::vector<uint32_t> nrec(nb), lastlen(nb);
     PGS_CUDA(cudaMemcpyAsync(nrec.data(), d_nrec, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
@@ -272,8 +304,12 @@ int32_t build_index(Engine *e, Run *r, const uint64_t *h_blk_off, const uint32_t
     PGS_CUDA(cudaMallocAsync(&r->d_rec_off, sizeof(uint32_t) * (rc + 1), st));
     PGS_CUDA(cudaMemcpyAsync(r->d_blk_rec, rec_cum.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
     PGS_CUDA(cudaMemcpyAsync(r->d_ikey_off, key_cum.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
+    r->n_bloom_entries = hs.n_records + hs.n_prefix;
+    r->bloom_lines = bloom_lines_for(r->n_bloom_entries);
+    PGS_CUDA(cudaMallocAsync(&r->d_bloom, (size_t)r->bloom_lines * 64, st));
+    PGS_CUDA(cudaMemsetAsync(r->d_bloom, 0, (size_t)r->bloom_lines * 64, st));
     k_index_walk<true><<<grid, kIdxWarps * 32, smem, st>>>(r->d_data, r->d_blk_off, r->d_blk_size, nb, nullptr,
-                                                           nullptr, r->d_ikey_off, r->d_ikeys, r->d_blk_rec, r->d_rec_off, d_stats);
+                                                           nullptr, r->d_ikey_off, r->d_ikeys, r->d_blk_rec, r->d_rec_off, r->d_bloom, r->bloom_lines, d_stats);
     e->launches++;
     PGS_CUDA(cudaStreamSynchronize(st));
     cudaFreeAsync(d_stats, st);
@@ -322,8 +358,8 @@ int32_t pgs_engine_open(const pgs_engine_config *cfg, pgs_engine **out)
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e.sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (err == cudaSuccess) err = cudaEventCreate(&e.ev_a);
-    if (err == cudaSuccess) err = cudaEventCreate(&e.ev_b);
+    for (auto &s : e.rd_streams) if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (err == cudaSuccess && (lookup_init_kernels(e.max_smem_optin) != PGS_OK || compact_init_kernels(e.max_smem_optin) != PGS_OK)) err = cudaGetLastError() != cudaSuccess ? cudaErrorUnknown : cudaErrorUnknown;
     if (err == cudaSuccess) { // keep freed compaction buffers in the stream-ordered pool
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
@@ -357,8 +393,9 @@ int32_t pgs_engine_sync(pgs_engine *e)
     return PGS_OK;
 }
 uint64_t pgs_engine_launches(pgs_engine *e) { return e->e.launches.load(); }
-float pgs_engine_last_kernel_ms(pgs_engine *e) { return e->e.last_kernel_ms; }
-uint64_t pgs_engine_last_blocks_probed(pgs_engine *e) { return e->e.last_blocks_probed; }
+float pgs_engine_last_kernel_ms(pgs_engine *) { return t_last_ms; }
+uint64_t pgs_engine_last_blocks_probed(pgs_engine *) { return t_last_probed; }
+uint64_t pgs_engine_last_runs_skipped(pgs_engine *) { return t_last_skipped; }
 
 int32_t pgs_partition_create(pgs_engine *e, int32_t app_id, int32_t pidx, uint32_t data_version,
                              pgs_partition **out)

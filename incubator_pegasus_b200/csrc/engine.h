@@ -26,12 +26,15 @@ struct Run {
     uint32_t *d_ikey_off = nullptr;
     uint8_t *d_ikeys = nullptr;
     uint32_t *d_rec_off = nullptr;
+    uint32_t *d_bloom = nullptr;
+    uint32_t bloom_lines = 0;
+    uint64_t n_bloom_entries = 0; // user keys + distinct hash-key prefixes that went into the filter (sizes a merged run's filter)
     uint64_t data_cap = 0;
     cudaStream_t pool_stream = nullptr; // set when the buffers came from cudaMallocAsync on that stream
     struct Engine *eng = nullptr;       // set with pool_stream: large data buffers go back to the engine's spare list
     RunDev dev() const
     {
-        return RunDev{d_data, d_blk_off, d_blk_size, d_blk_rec, d_ikey_off, d_ikeys, d_rec_off, info.n_blocks, info.max_ukey_len};
+        return RunDev{d_data, d_blk_off, d_blk_size, d_blk_rec, d_ikey_off, d_ikeys, d_rec_off, d_bloom, bloom_lines, info.n_blocks, info.max_ukey_len, 0};
     }
     ~Run();
 };
@@ -44,9 +47,11 @@ struct Engine {
     int max_smem_optin = 0;
     std::atomic<uint64_t> launches{0};
     std::atomic<uint64_t> next_run_id{1};
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr; // bracket the kernels of the last read call
-    float last_kernel_ms = 0.f;
-    uint64_t last_blocks_probed = 0;
+    // reads of different host threads go to different streams (runs are complete before they become visible, so a reader
+    // needs no ordering with the stream that built them); writes / uploads / compactions use `stream`
+    static constexpr int kReadStreams = 8;
+    cudaStream_t rd_streams[kReadStreams] = {};
+    cudaStream_t read_stream();
     // reusable pinned staging + device scratch
     std::mutex mu;
     void *h_pinned = nullptr;

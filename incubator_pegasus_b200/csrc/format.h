@@ -55,9 +55,12 @@ struct RunDev {
     const uint32_t *blk_rec;  // [nb+1] cumulative record count
     const uint32_t *ikey_off; // [nb+1] offsets into ikeys
     const uint8_t *ikeys;     // last user key of every block, back to back
-    const uint32_t *rec_off;  // [n_records] byte offset of every entry inside its block (makes the header walk parallel)
+    const uint32_t *rec_off;  // [n_records] byte offset of every entry inside its block (reverse-scan kernel)
+    const uint32_t *bloom;    // Bloom filter over whole user keys and hash-key prefixes: bloom_lines lines of 64 bytes (0 = none)
+    uint32_t bloom_lines;
     uint32_t nb;
     uint32_t max_ukey_len;
+    uint32_t pad;
 };
 
 } // namespace pgs

@@ -216,4 +216,82 @@ PGS_DEV uint32_t cur_next(const Grp<G> &g, bool en, const RunDev &r, CurState *c
     return err ? err : e2;
 }
 
+// ---- Bloom filter of a run (device-built at upload / compaction time) --------------------------------------------------
+// 10 bits per entry, cache-line blocked: an entry hashes to one 64-byte line and sets / tests 6 bits inside it (the shape of
+// RocksDB's cache-local full filter, v8.5.3 util/bloom_impl.h, not in tree).  Entries are whole user keys and hash-key
+// prefixes (HashkeyTransform: the first 2 + BE16 bytes), as the reference configures its filter
+// (src/server/pegasus_server_impl_init.cpp:817-843).  The hash is a position-salted XOR of per-word mixes, so the lanes of
+// a group hash their own words of a key row and combine with shuffles.
+PGS_DEV void bloom_word(uint32_t w, uint32_t idx, uint32_t &ha, uint32_t &hb)
+{
+    uint32_t a = (w + 0x9E3779B9u * (idx + 1)) * 0x85EBCA6Bu;
+    a ^= a >> 15; a *= 0xC2B2AE35u; a ^= a >> 13;
+    uint32_t b = (w ^ (0x7F4A7C15u * (idx + 3))) * 0x27D4EB2Fu;
+    b ^= b >> 16; b *= 0x165667B1u; b ^= b >> 14;
+    ha ^= a; hb ^= b;
+}
+PGS_DEV unsigned long long bloom_finish(uint32_t ha, uint32_t hb, uint32_t len)
+{
+    unsigned long long h = ((unsigned long long)(ha ^ (len * 0x9E3779B1u)) << 32) | hb;
+    h ^= h >> 29; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32;
+    return h;
+}
+// hash of the first len bytes of a key row (4-byte aligned, any address space); every lane of the group gets the result (whole warp)
+template <uint32_t G>
+PGS_DEV unsigned long long bloom_hash_row(const Grp<G> &g, const uint32_t *row, uint32_t len)
+{
+    uint32_t ha = 0, hb = 0;
+    for (uint32_t w = g.gl; 4 * w < len; w += G) {
+        uint32_t x = row[w];
+        if (len - 4 * w < 4) x &= (1u << (8 * (len - 4 * w))) - 1u;
+        bloom_word(x, w, ha, hb);
+    }
+#pragma unroll
+    for (uint32_t d = G / 2; d; d >>= 1) { ha ^= __shfl_xor_sync(kFull, ha, (int)d); hb ^= __shfl_xor_sync(kFull, hb, (int)d); }
+    return bloom_finish(ha, hb, len);
+}
+// the same hash by one thread over bytes anywhere
+PGS_DEV unsigned long long bloom_hash_bytes(const uint8_t *key, uint32_t len)
+{
+    uint32_t ha = 0, hb = 0;
+    for (uint32_t w = 0; 4 * w < len; w++) {
+        uint32_t x = 0;
+        for (uint32_t b = 0; b < 4 && 4 * w + b < len; b++) x |= (uint32_t)key[4 * w + b] << (8 * b);
+        bloom_word(x, w, ha, hb);
+    }
+    return bloom_finish(ha, hb, len);
+}
+PGS_DEV uint32_t bloom_bit(unsigned long long h, uint32_t i) // i-th of the 6 bit positions (0..511) inside the line
+{
+    uint32_t x = (uint32_t)h + i * 0x9E3779B1u;
+    x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12;
+    return x & 511u;
+}
+PGS_DEV bool bloom_may_contain(const uint32_t *bits, uint32_t n_lines, unsigned long long h)
+{
+    if (n_lines == 0) return true; // no filter built
+    const uint32_t *line = bits + 16 * (size_t)(((h >> 32) * (unsigned long long)n_lines) >> 32);
+#pragma unroll
+    for (uint32_t i = 0; i < 6; i++) {
+        const uint32_t bit = bloom_bit(h, i);
+        if (!((line[bit >> 5] >> (bit & 31)) & 1u)) return false;
+    }
+    return true;
+}
+// lanes 0..5 of a group set one bit each (sub < 6); a single thread passes sub = 0..5 in a loop
+PGS_DEV void bloom_add_bit(uint32_t *bits, uint32_t n_lines, unsigned long long h, uint32_t sub)
+{
+    uint32_t *line = bits + 16 * (size_t)(((h >> 32) * (unsigned long long)n_lines) >> 32);
+    const uint32_t bit = bloom_bit(h, sub);
+    atomicOr(&line[bit >> 5], 1u << (bit & 31));
+}
+PGS_HD uint32_t bloom_lines_for(unsigned long long n_entries) { return (uint32_t)((n_entries * 10 + 511) / 512 + 1); }
+// length of the HashkeyTransform prefix of a raw key (hashkey_transform.h:40-60); 0 = not in domain
+PGS_DEV uint32_t hashkey_prefix_len(const uint8_t *key, uint32_t len)
+{
+    if (len < 2) return 0;
+    const uint32_t p = 2 + (((uint32_t)key[0] << 8) | key[1]);
+    return p <= len ? p : 0;
+}
+
 } // namespace pgs

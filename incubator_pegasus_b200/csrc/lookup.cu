@@ -1,76 +1,22 @@
-// lookup.cu — read path on the GPU.
+// lookup.cu — host side of the read path (pgs_get_batch, pgs_range_scan, pgs_range_scan_many) and the reverse-scan kernel.
 //
-//   k_get   batched point lookup (DB::Get / DB::MultiGet as used by on_get / on_multi_get(sort_keys) /
-//           on_batch_get / on_ttl, src/server/pegasus_server_impl.cpp:441,804,948,1106): one warp per
-//           key; for each run newest -> oldest: binary search of the block index (last user key per
-//           block), TMA-stage the 4 KB data block into the warp's shared-memory slot, binary search of
-//           the restart array, linear decode of one restart interval, user-key compare; newest version
-//           wins, a tombstone ends the search; TTL check and header strip fused.
-//   k_scan  range scan (NewIterator + Seek + Next/Prev loops of on_multi_get range mode, on_get_scanner,
-//           on_scan, on_sortkey_count, :617-756,1243-1320,1444-1490,1042-1062): one CTA per request;
-//           chunks of blocks of every run are staged with TMA, decoded, merged by rank (the same merge
-//           the compaction kernel uses), newest version / tombstone visibility applied, then the
-//           reference's loop (stop key, first-exclusive, range_read_limiter counts and sizes, TTL /
-//           hash / sort-key filters) is evaluated with block-wide scans instead of a serial walk.
+//   k_get / k_scan_fwd (read_kernels.cuh)  point lookups and forward range scans: lane-group iterators straight over HBM.
+//   k_scan (this file)  REVERSE range scans (SeekForPrev + Prev loops of on_multi_get reverse mode,
+//           src/server/pegasus_server_impl.cpp:689-756): one CTA per request; chunks of blocks of every run are staged with TMA,
+//           decoded, merged by rank, newest version / tombstone visibility applied, then the reference's loop (stop key,
+//           first-exclusive, range_read_limiter counts and sizes, TTL / sort-key filters) is evaluated with block-wide scans
+//           walking backwards chunk by chunk.  (It also handles forward requests; a batch that mixes directions uses it.)
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
-#include "device_util.cuh"
 #include "engine.h"
+#include "read_kernels.cuh"
 
 namespace pgs {
 
-constexpr uint32_t kGetWarps = 8;
-constexpr uint32_t kGetBlockBuf = 5120; // per-warp staging (a 4 KB-target block fits); larger blocks are read in place from HBM
-constexpr uint32_t kMaxReadRuns = 32;
-
-struct ReadRuns {
-    RunDev runs[kMaxReadRuns];
-    uint32_t n;
-};
-
 PGS_DEV uint32_t ld32le(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
-
-// warp-cooperative bytewise compare of a (shared/generic) and b; every lane returns the same result
-PGS_DEV int warp_cmp(const uint8_t *a, uint32_t la, const uint8_t *b, uint32_t lb, uint32_t lane)
-{
-    uint32_t m = la < lb ? la : lb;
-    for (uint32_t base = 0; base < m; base += 32) {
-        uint32_t i = base + lane;
-        int d = 0;
-        if (i < m) d = (int)a[i] - (int)b[i];
-        uint32_t ne = __ballot_sync(kFull, d != 0);
-        if (ne) {
-            int first = __ffs(ne) - 1;
-            return __shfl_sync(kFull, d, first);
-        }
-    }
-    return la < lb ? -1 : (la > lb ? 1 : 0);
-}
-
-// first block of `r` whose last user key >= key (every lane computes the same answer)
-PGS_DEV uint32_t index_lower_bound(const RunDev &r, const uint8_t *key, uint32_t klen)
-{
-    uint32_t lo = 0, hi = r.nb;
-    while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        uint32_t o = r.ikey_off[mid], l = r.ikey_off[mid + 1] - o;
-        if (cmp_bytes(r.ikeys + o, l, key, klen) < 0) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-PGS_DEV uint32_t index_upper_bound(const RunDev &r, const uint8_t *key, uint32_t klen)
-{
-    uint32_t lo = 0, hi = r.nb;
-    while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        uint32_t o = r.ikey_off[mid], l = r.ikey_off[mid + 1] - o;
-        if (cmp_bytes(r.ikeys + o, l, key, klen) <= 0) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
 
 // warp-cooperative 33-ary search over the block index: every round the 32 lanes probe 32 pivots at once, so the
 // chain of dependent global loads is ~log33(nb) long instead of log2(nb).  upper=false: first block whose last key
@@ -101,172 +47,12 @@ PGS_DEV uint32_t warp_index_bound(const RunDev &r, const uint8_t *key, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_get
-// ------------------------------------------------------------------------------------------------
-struct GetParams {
-    ReadRuns rr;
-    const uint8_t *keys;
-    const uint32_t *key_off;
-    uint32_t n, now, data_version, use_tma;
-    uint32_t KS; // scratch bytes per warp for the running key
-    pgs_get_result *results;
-    uint8_t *arena;
-    unsigned long long arena_cap;
-    unsigned long long *arena_cursor; // [0] = arena bytes, [1] = data blocks probed
-    uint32_t *error;
-};
-
-__global__ void __launch_bounds__(kGetWarps * 32) k_get(const __grid_constant__ GetParams P)
-{
-    extern __shared__ __align__(128) uint8_t dyn[];
-    __shared__ __align__(8) unsigned long long mbar[kGetWarps];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *buf = dyn + warp * (kGetBlockBuf + 16);
-    uint8_t *scr = dyn + kGetWarps * (kGetBlockBuf + 16) + warp * (P.KS + 16);
-    if (lane == 0) {
-        mbar_init((uint64_t *)&mbar[warp], 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
-    uint32_t phase = 0, probes = 0;
-    for (uint32_t q = blockIdx.x * kGetWarps + warp; q < P.n; q += gridDim.x * kGetWarps) {
-        const uint8_t *key = P.keys + P.key_off[q];
-        const uint32_t klen = P.key_off[q + 1] - P.key_off[q];
-        pgs_get_result res;
-        res.status = PGS_NOT_FOUND;
-        res.expire_ts = 0; res.value_off = 0; res.value_len = 0; res.expired = 0;
-        res.reserved[0] = res.reserved[1] = res.reserved[2] = 0;
-        bool done = false;
-        for (uint32_t ri = 0; ri < P.rr.n && !done; ri++) {
-            const RunDev &r = P.rr.runs[ri];
-            uint32_t b = warp_index_bound(r, key, klen, lane, false);
-            if (b >= r.nb) continue;
-            probes++;
-            const uint8_t *gsrc = r.data + r.blk_off[b];
-            uint32_t size = r.blk_size[b];
-            const uint8_t *base;
-            bool in_smem = P.use_tma && size <= kGetBlockBuf;
-            if (in_smem) {
-                uint32_t bytes = (size + 15) & ~15u;
-                if (lane == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_expect_tx((uint64_t *)&mbar[warp], bytes);
-                    tma_load_1d(buf, gsrc, bytes, (uint64_t *)&mbar[warp]);
-                }
-                mbar_wait((uint64_t *)&mbar[warp], phase);
-                phase ^= 1;
-                base = buf;
-            } else {
-                base = gsrc;
-            }
-            uint32_t err = 0;
-            if (size < 8) err = PGS_CORRUPTION;
-            uint32_t nr = err ? 0 : ld32le(base + size - 4);
-            if (!err && (nr == 0 || (unsigned long long)nr * 4 + 4 > size)) err = PGS_CORRUPTION;
-            if (err) { if (lane == 0) atomicMax(P.error, err); break; }
-            const uint32_t limit = size - 4 - 4 * nr;
-            // last restart point whose user key < key
-            uint32_t lo = 0, hi = nr - 1;
-            while (lo < hi) {
-                uint32_t mid = (lo + hi + 1) >> 1;
-                uint32_t p = ld32le(base + limit + 4 * mid);
-                uint32_t sh, ns, vl, h = 0, c;
-                if (p >= limit) { err = PGS_CORRUPTION; break; }
-                c = get_varint32(base + p, limit - p, sh); h += c;
-                if (c) { c = get_varint32(base + p + h, limit - p - h, ns); h += c; }
-                if (c) { c = get_varint32(base + p + h, limit - p - h, vl); h += c; }
-                if (!c || sh != 0 || ns < 8 || p + h + ns > limit) { err = PGS_CORRUPTION; break; }
-                if (warp_cmp(base + p + h, ns - 8, key, klen, lane) < 0) lo = mid; else hi = mid - 1;
-            }
-            if (err) { if (lane == 0) atomicMax(P.error, err); break; }
-            uint32_t p = ld32le(base + limit + 4 * lo), prev_klen = 0;
-            while (p < limit) {
-                uint32_t sh, ns, vl, h = 0, c;
-                c = get_varint32(base + p, limit - p, sh); h += c;
-                if (c) { c = get_varint32(base + p + h, limit - p - h, ns); h += c; }
-                if (c) { c = get_varint32(base + p + h, limit - p - h, vl); h += c; }
-                uint32_t kl = sh + ns;
-                if (!c || sh > prev_klen || kl < 8 || kl - 8 > P.KS || (unsigned long long)p + h + ns + vl > limit) { err = PGS_CORRUPTION; break; }
-                for (uint32_t x = lane; x < ns; x += 32) scr[sh + x] = base[p + h + x];
-                __syncwarp();
-                int c3 = warp_cmp(scr, kl - 8, key, klen, lane);
-                if (c3 >= 0) {
-                    if (c3 == 0) { // newest version of the key in this run
-                        done = true;
-                        uint8_t type = scr[kl - 8];
-                        if (type == PGS_TYPE_VALUE) {
-                            const uint8_t *val = base + p + h + ns;
-                            uint32_t hdr = user_data_offset(P.data_version);
-                            uint32_t ets = vl >= 4 ? be32(val) : 0;
-                            res.expire_ts = ets;
-                            if (ts_expired(P.now, ets)) {
-                                res.expired = 1; // check_if_record_expired -> NotFound (pegasus_server_impl.cpp:443-448)
-                            } else {
-                                uint32_t ulen = vl >= hdr ? vl - hdr : 0;
-                                unsigned long long off = 0;
-                                if (lane == 0) off = atomicAdd(P.arena_cursor, (unsigned long long)((ulen + 3) & ~3u));
-                                off = __shfl_sync(kFull, off, 0);
-                                if (off + ulen > P.arena_cap) {
-                                    res.status = PGS_INCOMPLETE;
-                                } else {
-                                    res.status = PGS_OK;
-                                    res.value_off = (uint32_t)off;
-                                    res.value_len = ulen;
-                                    if (in_smem) warp_copy_s2g(P.arena + off, val + hdr, ulen, lane);
-                                    else warp_copy_bytes(P.arena + off, val + hdr, ulen, lane);
-                                }
-                            }
-                        }
-                    }
-                    break; // first entry >= key: either the hit or proof of absence in this run
-                }
-                __syncwarp();
-                prev_klen = kl;
-                p += h + ns + vl;
-            }
-            if (err) { if (lane == 0) atomicMax(P.error, err); break; }
-            __syncwarp();
-        }
-        if (lane == 0) P.results[q] = res;
-    }
-    if (lane == 0 && probes) atomicAdd(P.arena_cursor + 1, (unsigned long long)probes);
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_scan
+// k_scan (reverse scans)
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kScanThreads = 256;
 constexpr uint32_t kScanWarps = kScanThreads / 32;
 constexpr uint32_t kScanMaxBlocks = 128;
 constexpr uint32_t kScanRecExtra = 48;
-
-struct ScanReqDev {
-    uint32_t start_off, start_len, stop_off, stop_len, hf_off, hf_len, sf_off, sf_len;
-    uint8_t start_inclusive, stop_inclusive, reverse, no_value, key_mode, return_expire_ts, count_only, validate_hash;
-    uint8_t prefix_same_as_start, has_upper, pad[2];
-    int32_t hash_filter_type, sort_filter_type;
-    uint32_t max_count, max_iter_count;
-    unsigned long long max_iter_size;
-    int32_t pidx, partition_version;
-};
-
-struct ScanParams {
-    ReadRuns rr;
-    const ScanReqDev *reqs;
-    const uint8_t *blob; // request byte strings
-    uint32_t n, now, data_version, use_tma;
-    uint32_t KS, pool_bytes, warp_scratch;
-    pgs_scan_result *results;
-    pgs_kv *kvs;
-    uint32_t kv_stride;
-    uint8_t *arena;
-    unsigned long long arena_stride;
-    uint8_t *resume;
-    uint32_t resume_stride;
-    const unsigned long long *crc_table;
-    uint32_t *error;
-    unsigned long long *phase_cycles; // [16] or null (PGS_PHASE_TIMING=1)
-};
 
 struct ScanShared {
     unsigned long long mbar;
@@ -333,31 +119,7 @@ PGS_DEV uint32_t scan_chunked(uint32_t n, uint32_t *out, uint32_t *scratch, F f)
     return total;
 }
 
-// validate_filter of the read path: pegasus_server_impl.cpp:2350-2380 (empty pattern matches)
-PGS_DEV bool dev_validate_filter(int32_t type, const uint8_t *pat, uint32_t pl, const uint8_t *v, uint32_t vl)
-{
-    if (type == PGS_FT_NO_FILTER) return true;
-    if (type < PGS_FT_NO_FILTER || type > PGS_FT_MATCH_POSTFIX) return false;
-    if (pl == 0) return true;
-    if (vl < pl) return false;
-    if (type == PGS_FT_MATCH_PREFIX) {
-        for (uint32_t i = 0; i < pl; i++) if (v[i] != pat[i]) return false;
-        return true;
-    }
-    if (type == PGS_FT_MATCH_POSTFIX) {
-        for (uint32_t i = 0; i < pl; i++) if (v[vl - pl + i] != pat[i]) return false;
-        return true;
-    }
-    for (uint32_t s = 0; s + pl <= vl; s++) {
-        uint32_t i = 0;
-        while (i < pl && v[s + i] == pat[i]) i++;
-        if (i == pl) return true;
-    }
-    return false;
-}
-
 enum : uint8_t { SF_VALID = 1, SF_SHADOW = 2 };
-enum : uint8_t { RS_NORMAL = 0, RS_EXPIRED = 1, RS_FILTERED = 2, RS_HASH_INVALID = 3 };
 
 __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant__ ScanParams P)
 {
@@ -1049,7 +811,9 @@ __global__ void k_pack_copy(const pgs_scan_result *__restrict__ res, uint32_t n,
 }
 
 static uint64_t *g_crc_dev_rd[16] = {nullptr};
+static std::mutex g_crc_rd_mu;
 const uint64_t *crc64_table();
+void set_last_read_stats(float ms, uint64_t probed, uint64_t skipped);
 
 static int32_t snapshot_runs(Partition &part, std::vector<std::shared_ptr<Run>> &runs, ReadRuns &rr, uint32_t &KS,
                              const std::vector<std::shared_ptr<Run>> *pinned = nullptr)
@@ -1072,6 +836,19 @@ static int32_t snapshot_runs(Partition &part, std::vector<std::shared_ptr<Run>> 
     return PGS_OK;
 }
 
+// kernels of this file take their dynamic shared-memory size per launch; the opt-in maximum is set once per device here
+// (a per-call cudaFuncSetAttribute would race between reader threads)
+int32_t lookup_init_kernels(int max_smem)
+{
+    PGS_CUDA(cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PGS_CUDA(cudaFuncSetAttribute(k_scan, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PGS_CUDA(cudaFuncSetAttribute(k_get<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PGS_CUDA(cudaFuncSetAttribute(k_scan_fwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PGS_CUDA(cudaFuncSetAttribute(k_scan_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PGS_CUDA(cudaFuncSetAttribute(k_scan_fwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    return PGS_OK;
+}
+
 int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uint32_t now, unsigned long long arena_stride,
                   uint32_t kv_stride, uint8_t *arena, uint64_t arena_cap, pgs_kv *kvs, uint64_t kv_cap, uint8_t *resume,
                   uint32_t resume_stride, pgs_scan_result *results, uint64_t *arena_base, uint32_t *kv_base,
@@ -1084,11 +861,11 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
     if (rc != PGS_OK) return rc;
     if (n == 0) return PGS_OK;
     PGS_CUDA(cudaSetDevice(e->device));
-    cudaStream_t st = e->stream;
+    cudaStream_t st = e->read_stream();
     // flatten requests
     std::vector<ScanReqDev> dev(n);
     std::string blob;
-    bool need_crc = false;
+    bool need_crc = false, any_reverse = false;
     for (uint32_t i = 0; i < n; i++) {
         const pgs_scan_request &q = reqs[i];
         ScanReqDev &d = dev[i];
@@ -1110,41 +887,34 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
         d.max_count = q.max_count; d.max_iter_count = q.max_iter_count; d.max_iter_size = q.max_iter_size;
         d.pidx = q.pidx; d.partition_version = q.partition_version;
         need_crc |= q.validate_hash != 0;
+        any_reverse |= q.reverse != 0;
     }
     blob.append(16, '\0');
     if (resume_stride < P.KS) resume_stride = 0; // caller gave no room: resume keys are not reported
-    // shared memory: one request per CTA; small scans want several CTAs per SM
-    cudaFuncAttributes attr;
-    PGS_CUDA(cudaFuncGetAttributes(&attr, k_scan));
-    P.warp_scratch = 0; // (the index-driven decode needs no per-warp key buffer)
-    uint32_t fixed_dyn = (4 + (uint32_t)runs.size()) * ((P.KS + 8 + 15) & ~15u) + kScanWarps * P.warp_scratch;
-    uint32_t max_blk = 0, max_rec = 0;
-    for (auto &r : runs) { max_blk = std::max(max_blk, r->info.max_block_size); max_rec = std::max(max_rec, r->info.max_block_records); }
-    uint64_t one = (((uint64_t)max_blk + 15) & ~15ull) + 32 + (uint64_t)max_rec * (P.KS + kScanRecExtra);
-    uint64_t want = std::max<uint64_t>(one * std::max<size_t>(1, runs.size()) + 4096, 48 * 1024);
-    if (n == 1) want = std::max<uint64_t>(want, 160 * 1024);
-    if (const char *ev = getenv("PGS_SCAN_POOL_KB")) { if (atoi(ev) > 0) want = std::max<uint64_t>(want, (uint64_t)atoi(ev) * 1024); } // tuning knob
-    uint64_t max_dyn = (uint64_t)e->max_smem_optin - attr.sharedSizeBytes - 256;
-    uint64_t dyn = std::min<uint64_t>(max_dyn, fixed_dyn + want);
-    if (dyn < fixed_dyn + one * std::max<size_t>(1, runs.size()) + 64) {
-        set_error("scan: blocks too large for shared memory");
-        return PGS_NOT_SUPPORTED;
-    }
-    dyn &= ~127ull;
-    P.pool_bytes = (uint32_t)(dyn - fixed_dyn);
     P.n = n; P.now = now; P.data_version = part.data_version;
     P.use_tma = (e->cfg.flags & PGS_ENGINE_NO_TMA) ? 0 : 1;
     P.kv_stride = kv_stride; P.arena_stride = (arena_stride + 15) & ~15ull; P.resume_stride = resume_stride ? resume_stride : P.KS;
+    if (P.rr.n == 0) { // empty DB: every iterator is invalid from the start
+        memset(results, 0, sizeof(pgs_scan_result) * n);
+        if (arena_base) for (uint32_t i = 0; i <= n; i++) arena_base[i] = 0;
+        if (kv_base) for (uint32_t i = 0; i <= n; i++) kv_base[i] = 0;
+        return PGS_OK;
+    }
 
     ScanReqDev *d_reqs = nullptr; uint8_t *d_blob = nullptr, *d_arena = nullptr, *d_resume = nullptr, *d_parena = nullptr;
     pgs_scan_result *d_res = nullptr; pgs_kv *d_kvs = nullptr, *d_pkvs = nullptr; uint32_t *d_err = nullptr, *d_kbase = nullptr;
     unsigned long long *d_abase = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     auto cleanup = [&]() {
         cudaFreeAsync(d_reqs, st); cudaFreeAsync(d_blob, st); cudaFreeAsync(d_arena, st); cudaFreeAsync(d_resume, st);
         cudaFreeAsync(d_parena, st); cudaFreeAsync(d_res, st); cudaFreeAsync(d_kvs, st); cudaFreeAsync(d_pkvs, st);
         cudaFreeAsync(d_err, st); cudaFreeAsync(d_kbase, st); cudaFreeAsync(d_abase, st);
+        if (ev_a) cudaEventDestroy(ev_a);
+        if (ev_b) cudaEventDestroy(ev_b);
     };
 #define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr); } } while (0)
+    CK(cudaEventCreate(&ev_a));
+    CK(cudaEventCreate(&ev_b));
     CK(cudaMallocAsync(&d_reqs, sizeof(ScanReqDev) * n, st));
     CK(cudaMallocAsync(&d_blob, blob.size(), st));
     CK(cudaMallocAsync(&d_arena, P.arena_stride * n + 16, st));
@@ -1156,50 +926,76 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
     CK(cudaMemcpyAsync(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d_err, 0, 256, st));
     if (need_crc) {
+        std::lock_guard<std::mutex> g(g_crc_rd_mu);
         int dv = e->device & 15;
         if (!g_crc_dev_rd[dv]) {
             uint64_t *t = nullptr;
             CK(cudaMalloc(&t, 2048));
-            CK(cudaMemcpyAsync(t, crc64_table(), 2048, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpy(t, crc64_table(), 2048, cudaMemcpyHostToDevice));
             g_crc_dev_rd[dv] = t;
         }
         P.crc_table = (const unsigned long long *)g_crc_dev_rd[dv];
     }
     P.reqs = d_reqs; P.blob = d_blob; P.results = d_res; P.kvs = d_kvs; P.arena = d_arena; P.resume = d_resume; P.error = d_err;
-    const char *pt_env = getenv("PGS_PHASE_TIMING"); // diagnostics: per-phase cycle totals of k_scan on stderr
-    const bool phase_timing = pt_env && pt_env[0] == '1';
+    P.ticket = d_err + 8;
+    const char *pt_env = getenv("PGS_PHASE_TIMING"); // diagnostics: per-phase cycle totals of the reverse kernel on stderr
+    const bool phase_timing = any_reverse && pt_env && pt_env[0] == '1';
     P.phase_cycles = phase_timing ? (unsigned long long *)(d_err + 16) : nullptr;
-    CK(cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    CK(cudaFuncSetAttribute(k_scan, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    int occ = 0; // resident CTAs per SM for this dynamic shared-memory size (registers count too)
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan, (int)kScanThreads, (size_t)dyn));
-    uint32_t per_sm = (uint32_t)std::max(1, occ);
-    uint32_t grid = std::min<uint32_t>(n, per_sm * e->sm_count);
-    if (P.rr.n == 0) { // empty DB: every iterator is invalid from the start
-        std::vector<pgs_scan_result> z(n);
-        memset(z.data(), 0, sizeof(pgs_scan_result) * n);
-        memcpy(results, z.data(), sizeof(pgs_scan_result) * n);
-        if (arena_base) for (uint32_t i = 0; i <= n; i++) arena_base[i] = 0;
-        if (kv_base) for (uint32_t i = 0; i <= n; i++) kv_base[i] = 0;
-        cleanup();
-        cudaStreamSynchronize(st);
-        return PGS_OK;
+    if (!any_reverse) {
+        // ---- forward scans: lane-group merging iterators (read_kernels.cuh) ------------------------------------------
+        const uint32_t NR = P.rr.n, G = NR <= 8 ? 8 : NR <= 16 ? 16 : 32;
+        P.KS = (P.KS + 3) & ~3u;
+        P.KSW = (P.KS + 8) / 4 + 1;
+        P.group_smem = (uint32_t)((NR * (sizeof(CurState) + P.KSW * 4) + 3 * P.KSW * 4 + 15) & ~(size_t)15);
+        const uint32_t dyn = 2048 + kMaxReadRuns * (uint32_t)sizeof(RunDev) + (kReadThreads / G) * P.group_smem;
+        if (dyn > (uint32_t)e->max_smem_optin) { cleanup(); set_error("scan: %u runs with keys of %u bytes do not fit shared memory", NR, P.KS); return PGS_NOT_SUPPORTED; }
+        auto kern = G == 8 ? k_scan_fwd<8> : G == 16 ? k_scan_fwd<16> : k_scan_fwd<32>;
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)kReadThreads, (size_t)dyn));
+        const uint32_t per_cta = kReadThreads / G;
+        const uint32_t grid = std::min<uint32_t>((n + per_cta - 1) / per_cta, (uint32_t)std::max(1, occ) * e->sm_count);
+        CK(cudaEventRecord(ev_a, st));
+        kern<<<grid, kReadThreads, dyn, st>>>(P);
+        CK(cudaEventRecord(ev_b, st));
+    } else {
+        // ---- reverse scans: the block-staging kernel --------------------------------------------------------------------
+        cudaFuncAttributes attr;
+        CK(cudaFuncGetAttributes(&attr, k_scan));
+        P.warp_scratch = 0;
+        uint32_t fixed_dyn = (4 + (uint32_t)runs.size()) * ((P.KS + 8 + 15) & ~15u) + kScanWarps * P.warp_scratch;
+        uint32_t max_blk = 0, max_rec = 0;
+        for (auto &r : runs) { max_blk = std::max(max_blk, r->info.max_block_size); max_rec = std::max(max_rec, r->info.max_block_records); }
+        uint64_t one = (((uint64_t)max_blk + 15) & ~15ull) + 32 + (uint64_t)max_rec * (P.KS + kScanRecExtra);
+        uint64_t want = std::max<uint64_t>(one * std::max<size_t>(1, runs.size()) + 4096, 48 * 1024);
+        if (n == 1) want = std::max<uint64_t>(want, 160 * 1024);
+        uint64_t max_dyn = (uint64_t)e->max_smem_optin - attr.sharedSizeBytes - 256;
+        uint64_t dyn = std::min<uint64_t>(max_dyn, fixed_dyn + want);
+        if (dyn < fixed_dyn + one * std::max<size_t>(1, runs.size()) + 64) {
+            cleanup();
+            set_error("scan: blocks too large for shared memory");
+            return PGS_NOT_SUPPORTED;
+        }
+        dyn &= ~127ull;
+        P.pool_bytes = (uint32_t)(dyn - fixed_dyn);
+        int occ = 0; // resident CTAs per SM for this dynamic shared-memory size (registers count too)
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan, (int)kScanThreads, (size_t)dyn));
+        uint32_t grid = std::min<uint32_t>(n, (uint32_t)std::max(1, occ) * e->sm_count);
+        CK(cudaEventRecord(ev_a, st));
+        k_scan<<<grid, kScanThreads, dyn, st>>>(P);
+        CK(cudaEventRecord(ev_b, st));
+        if (phase_timing) {
+            unsigned long long h[16] = {0};
+            cudaMemcpyAsync(h, d_err + 16, sizeof h, cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            static const char *names[13] = {"init", "choose", "stage", "farbound", "decode1", "decode2", "window", "rank", "visible", "loop", "emit", "advance", "result"};
+            unsigned long long tot = 0;
+            for (int i = 0; i < 13; i++) tot += h[i];
+            fprintf(stderr, "[k_scan phases] requests=%u grid=%u dyn=%llu", n, grid, (unsigned long long)dyn);
+            for (int i = 0; i < 13; i++) fprintf(stderr, " %s=%.1f%%", names[i], tot ? 100.0 * (double)h[i] / (double)tot : 0.0);
+            fprintf(stderr, " cycles/request=%.0f\n", n ? (double)tot / n : 0.0);
+        }
     }
-    cudaEventRecord(e->ev_a, st);
-    k_scan<<<grid, kScanThreads, dyn, st>>>(P);
-    cudaEventRecord(e->ev_b, st);
     e->launches++;
-    if (phase_timing) {
-        unsigned long long h[16] = {0};
-        cudaMemcpyAsync(h, d_err + 16, sizeof h, cudaMemcpyDeviceToHost, st);
-        cudaStreamSynchronize(st);
-        static const char *names[13] = {"init", "choose", "stage", "farbound", "decode1", "decode2", "window", "rank", "visible", "loop", "emit", "advance", "result"};
-        unsigned long long tot = 0;
-        for (int i = 0; i < 13; i++) tot += h[i];
-        fprintf(stderr, "[k_scan phases] requests=%u grid=%u dyn=%llu", n, grid, (unsigned long long)dyn);
-        for (int i = 0; i < 13; i++) fprintf(stderr, " %s=%.1f%%", names[i], tot ? 100.0 * (double)h[i] / (double)tot : 0.0);
-        fprintf(stderr, " cycles/request=%.0f\n", n ? (double)tot / n : 0.0);
-    }
     uint32_t herr = 0;
     if (n == 1) {
         CK(cudaMemcpyAsync(results, d_res, sizeof(pgs_scan_result), cudaMemcpyDeviceToHost, st));
@@ -1241,7 +1037,9 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
         if (arena_base) for (uint32_t i = 0; i <= n; i++) arena_base[i] = ab[i];
         if (kv_base) for (uint32_t i = 0; i <= n; i++) kv_base[i] = kb[i];
     }
-    cudaEventElapsedTime(&e->last_kernel_ms, e->ev_a, e->ev_b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev_a, ev_b);
+    set_last_read_stats(ms, 0, 0);
     cleanup();
 #undef CK
     if (herr) {
@@ -1274,48 +1072,58 @@ extern "C" int32_t pgs_get_batch(pgs_partition *ph, const uint8_t *keys, const u
         return PGS_OK;
     }
     PGS_CUDA(cudaSetDevice(e->device));
-    cudaStream_t st = e->stream;
+    cudaStream_t st = e->read_stream();
     uint64_t key_bytes = key_off[n];
     uint8_t *d_keys = nullptr, *d_arena = nullptr;
     uint32_t *d_off = nullptr, *d_err = nullptr;
     pgs_get_result *d_res = nullptr;
     unsigned long long *d_cur = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     auto cleanup = [&]() {
         cudaFreeAsync(d_keys, st); cudaFreeAsync(d_arena, st); cudaFreeAsync(d_off, st); cudaFreeAsync(d_err, st);
         cudaFreeAsync(d_res, st); cudaFreeAsync(d_cur, st);
+        if (ev_a) cudaEventDestroy(ev_a);
+        if (ev_b) cudaEventDestroy(ev_b);
     };
 #define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return cuda_fail(_e, #expr); } } while (0)
+    CK(cudaEventCreate(&ev_a));
+    CK(cudaEventCreate(&ev_b));
     CK(cudaMallocAsync(&d_keys, key_bytes + 16, st));
     CK(cudaMallocAsync(&d_off, sizeof(uint32_t) * (n + 1), st));
     CK(cudaMallocAsync(&d_res, sizeof(pgs_get_result) * n, st));
     CK(cudaMallocAsync(&d_arena, arena_cap + 16, st));
-    CK(cudaMallocAsync(&d_cur, 16, st));
-    CK(cudaMallocAsync(&d_err, 4, st));
+    CK(cudaMallocAsync(&d_cur, 32, st));
+    CK(cudaMallocAsync(&d_err, 16, st));
     CK(cudaMemcpyAsync(d_keys, keys, key_bytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_off, key_off, sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(d_cur, 0, 16, st));
-    CK(cudaMemsetAsync(d_err, 0, 4, st));
+    CK(cudaMemsetAsync(d_cur, 0, 32, st));
+    CK(cudaMemsetAsync(d_err, 0, 16, st));
     P.keys = d_keys; P.key_off = d_off; P.n = n; P.now = now; P.data_version = part.data_version;
-    P.use_tma = (e->cfg.flags & PGS_ENGINE_NO_TMA) ? 0 : 1;
-    P.results = d_res; P.arena = d_arena; P.arena_cap = arena_cap; P.arena_cursor = d_cur; P.error = d_err;
-    size_t dyn = kGetWarps * (kGetBlockBuf + 16) + kGetWarps * (P.KS + 16);
-    CK(cudaFuncSetAttribute(k_get, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    CK(cudaFuncSetAttribute(k_get, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    uint32_t per_sm = (uint32_t)std::max<size_t>(1, (228 * 1024) / (dyn + 2048));
-    uint32_t grid = std::min<uint32_t>((n + kGetWarps - 1) / kGetWarps, per_sm * e->sm_count);
-    cudaEventRecord(e->ev_a, st);
-    k_get<<<grid, kGetWarps * 32, dyn, st>>>(P);
-    cudaEventRecord(e->ev_b, st);
+    P.results = d_res; P.arena = d_arena; P.arena_cap = arena_cap; P.arena_cursor = d_cur; P.error = d_err; P.ticket = d_err + 1;
+    constexpr uint32_t G = 8;
+    P.KS = (P.KS + 3) & ~3u;
+    P.KSW = (P.KS + 8) / 4 + 1;
+    P.group_smem = (uint32_t)((sizeof(CurState) + 2 * P.KSW * 4 + 15) & ~(size_t)15);
+    const uint32_t dyn = kMaxReadRuns * (uint32_t)sizeof(RunDev) + (kReadThreads / G) * P.group_smem;
+    if (dyn > (uint32_t)e->max_smem_optin) { cleanup(); return PGS_NOT_SUPPORTED; }
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_get<G>, (int)kReadThreads, (size_t)dyn));
+    const uint32_t per_cta = kReadThreads / G;
+    const uint32_t grid = std::min<uint32_t>((n + per_cta - 1) / per_cta, (uint32_t)std::max(1, occ) * e->sm_count);
+    CK(cudaEventRecord(ev_a, st));
+    k_get<G><<<grid, kReadThreads, dyn, st>>>(P);
+    CK(cudaEventRecord(ev_b, st));
     e->launches++;
     uint32_t herr = 0;
-    unsigned long long cur2[2] = {0, 0};
+    unsigned long long cur3[3] = {0, 0, 0};
     CK(cudaMemcpyAsync(results, d_res, sizeof(pgs_get_result) * n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(cur2, d_cur, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cur3, d_cur, 24, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    cudaEventElapsedTime(&e->last_kernel_ms, e->ev_a, e->ev_b);
-    const unsigned long long used = cur2[0];
-    e->last_blocks_probed = cur2[1];
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev_a, ev_b);
+    set_last_read_stats(ms, cur3[1], cur3[2]);
+    const unsigned long long used = cur3[0];
     if (arena_used) *arena_used = used;
     if (!herr && used) {
         CK(cudaMemcpyAsync(arena, d_arena, std::min<unsigned long long>(used, arena_cap), cudaMemcpyDeviceToHost, st));

@@ -69,7 +69,7 @@ def test_env_parsers_follow_the_reference(make, kind):
     for i in range(64):
         be2.put(b"hk%02d" % i, b"s", b"v", now=NOW)
     be2.flush(NOW)
-    start, stop = b"", b""
+    start, stop = b"", b"\xff\xff\xff"  # the whole table
 
     def scan_count():
         r = be2.get_scanner(start, stop, batch_size=1000, full_scan=True, now=NOW)

@@ -44,3 +44,9 @@ def srcline(c):
 print(f"total warp instructions {tot}, stall samples {ts}")
 for c, n in agg.most_common(topn):
     print(f"{100*n/tot:5.1f}% inst {100*samp[c]/max(1,ts):5.1f}% samp  {c[0] if c else '?':22s}:{c[1] if c else 0:4d}  {srcline(c)}")
+if os.environ.get("NCU_LINES_STATIC"):
+    st = collections.Counter()
+    for n, s, c, txt in per_inst: st[c] += 1
+    print("\nstatic SASS count / executions per instruction, top lines:")
+    for c, n in agg.most_common(topn):
+        print(f"  {c[0] if c else '?':22s}:{c[1] if c else 0:4d}  static {st[c]:4d}  exec/inst {n/max(1,st[c])/1e6:8.2f} M   {srcline(c)[:80]}")

@@ -5,6 +5,7 @@
 
 #define PGS_SIM 1
 #include "../../incubator_pegasus_b200/csrc/compact_kernels.cuh"
+#include "../../incubator_pegasus_b200/csrc/read_kernels.cuh"
 
 #include <string>
 #include <vector>
@@ -18,11 +19,12 @@ struct HostRun {
     std::vector<uint64_t> blk_off;
     std::vector<uint32_t> blk_size, blk_rec, ikey_off, rec_off;
     std::vector<uint8_t> ikeys;
+    std::vector<uint32_t> bloom;
     pgs_run_info info{};
     RunDev dev() const
     {
         return RunDev{data.data(), blk_off.data(), blk_size.data(), blk_rec.data(), ikey_off.data(), ikeys.data(), rec_off.data(),
-                      (uint32_t)blk_size.size(), info.max_ukey_len};
+                      bloom.data(), (uint32_t)(bloom.size() / 16), (uint32_t)blk_size.size(), info.max_ukey_len, 0};
     }
 };
 
@@ -45,6 +47,7 @@ bool build_index(HostRun &r)
     r.info.n_blocks = nb;
     r.info.smallest_seq = ~0ull;
     std::string key;
+    std::vector<std::string> all_keys;
     for (uint32_t b = 0; b < nb; b++) {
         const uint8_t *base = r.data.data() + r.blk_off[b];
         const uint32_t size = r.blk_size[b];
@@ -63,6 +66,7 @@ bool build_index(HostRun &r)
             key.resize(sh);
             key.append((const char *)base + p + h, ns);
             r.rec_off.push_back(p);
+            all_keys.emplace_back(key.data(), key.size() - 8);
             unsigned long long tr;
             memcpy(&tr, key.data() + key.size() - 8, 8);
             r.info.n_tombstones += (uint8_t)tr == PGS_TYPE_DELETION;
@@ -84,6 +88,19 @@ bool build_index(HostRun &r)
     }
     r.ikeys.resize(r.ikeys.size() + 64);
     r.rec_off.push_back(0);
+    // the Bloom filter k_index_walk builds at upload: whole keys + hash-key prefixes
+    std::vector<std::string> pres;
+    for (auto &k : all_keys) {
+        const uint32_t pl = hashkey_prefix_len((const uint8_t *)k.data(), (uint32_t)k.size());
+        if (pl && (pres.empty() || pres.back() != k.substr(0, pl))) pres.push_back(k.substr(0, pl));
+    }
+    const uint32_t lines = bloom_lines_for(all_keys.size() + pres.size());
+    r.bloom.assign((size_t)lines * 16, 0);
+    for (auto *v : {&all_keys, &pres})
+        for (auto &k : *v) {
+            const unsigned long long h = bloom_hash_bytes((const uint8_t *)k.data(), (uint32_t)k.size());
+            for (uint32_t s = 0; s < 6; s++) bloom_add_bit(r.bloom.data(), lines, h, s);
+        }
     return true;
 }
 
@@ -104,6 +121,8 @@ struct Result {
     std::vector<uint64_t> blk_off;
     std::vector<uint32_t> blk_size, blk_rec, ikey_off, rec_off;
     std::vector<uint8_t> ikeys;
+    std::vector<uint32_t> bloom;
+    uint32_t bloom_lines = 0;
     MergeStats st{};
     uint32_t Q = 0;
 } g_res;
@@ -196,6 +215,10 @@ int32_t sim_compact(uint32_t k, const uint8_t **data, const uint64_t *data_bytes
     R.ikey_off.assign(geo.blk_cap + 1, 0);
     R.ikeys.assign(geo.ikey_cap, 0);
     R.rec_off.assign(T.n_rec + 1, 0);
+    R.bloom_lines = bloom_lines_for(2 * T.n_rec);
+    R.bloom.assign((size_t)R.bloom_lines * 16, 0);
+    P.out_bloom = R.bloom.data();
+    P.out_bloom_lines = R.bloom_lines;
     P.split_pos = split_pos.data(); P.split_ref = split_ref.data(); P.ticket = ticket.data();
     P.seg = seg.data(); P.agg = agg.data(); P.base = base.data(); P.desc = desc.data(); P.heads = heads.data();
     P.out_data = R.data.data(); P.out_blk_off = (unsigned long long *)R.blk_off.data(); P.out_blk_size = R.blk_size.data();
@@ -265,6 +288,105 @@ void sim_result_stats(uint64_t *o)
                             s.dropped_user, s.dropped_stale, s.ttl_rewritten, s.out_tomb, s.out_raw_key, s.out_raw_val, s.max_ukey, s.max_vlen,
                             s.max_blk_size, s.max_blk_rec, s.tot_recs ? ~s.min_seq_inv : ~0ull, s.max_seq, s.tot_keyb};
     memcpy(o, v, sizeof v);
+}
+
+// 1 when the merged run's Bloom filter admits the byte string (a user key or a hash-key prefix)
+int32_t sim_result_bloom_check(const uint8_t *key, uint32_t len)
+{
+    return bloom_may_contain(g_res.bloom.data(), g_res.bloom_lines, bloom_hash_bytes(key, len)) ? 1 : 0;
+}
+
+static bool load_runs(uint32_t k, const uint8_t **data, const uint64_t *data_bytes, const uint64_t **blk_off, const uint32_t **blk_size,
+                      const uint32_t *n_blocks, std::vector<HostRun> &runs, ReadRuns &rr, uint32_t &max_ukey)
+{
+    runs.resize(k);
+    rr.n = k;
+    max_ukey = 0;
+    for (uint32_t i = 0; i < k; i++) {
+        HostRun &r = runs[i];
+        r.data.assign(data[i], data[i] + data_bytes[i]);
+        r.data.resize(r.data.size() + 512, 0);
+        r.blk_off.assign(blk_off[i], blk_off[i] + n_blocks[i]);
+        r.blk_size.assign(blk_size[i], blk_size[i] + n_blocks[i]);
+        uint64_t end = n_blocks[i] ? r.blk_off.back() + r.blk_size.back() : 0;
+        r.blk_off.push_back((end + 15) & ~15ull);
+        if (!build_index(r)) return false;
+        rr.runs[i] = r.dev();
+        max_ukey = std::max(max_ukey, r.info.max_ukey_len);
+    }
+    return true;
+}
+
+// k_get over k runs (newest first); results / arena as pgs_get_batch.  stats[0] = arena bytes, [1] = blocks probed, [2] = runs skipped
+int32_t sim_get(uint32_t k, const uint8_t **data, const uint64_t *data_bytes, const uint64_t **blk_off, const uint32_t **blk_size,
+                const uint32_t *n_blocks, const uint8_t *keys, const uint32_t *key_off, uint32_t n, uint32_t now, uint8_t *arena,
+                uint64_t arena_cap, pgs_get_result *results, uint64_t *stats, uint32_t use_bloom)
+{
+    std::vector<HostRun> runs;
+    GetParams P{};
+    uint32_t mk = 0;
+    if (!load_runs(k, data, data_bytes, blk_off, blk_size, n_blocks, runs, P.rr, mk)) return PGS_CORRUPTION;
+    if (!use_bloom) for (uint32_t i = 0; i < k; i++) { P.rr.runs[i].bloom = nullptr; P.rr.runs[i].bloom_lines = 0; }
+    std::vector<uint8_t> kcopy(keys, keys + key_off[n]);
+    kcopy.resize(kcopy.size() + 64);
+    unsigned long long cur[4] = {0, 0, 0, 0};
+    uint32_t err[4] = {0, 0, 0, 0};
+    P.keys = kcopy.data(); P.key_off = key_off; P.n = n; P.now = now; P.data_version = 1;
+    P.results = results; P.arena = arena; P.arena_cap = arena_cap; P.arena_cursor = cur; P.error = err; P.ticket = err + 1;
+    P.KS = std::max(8u, (mk + 3) & ~3u);
+    P.KSW = (P.KS + 8) / 4 + 1;
+    P.group_smem = (uint32_t)((sizeof(CurState) + 2 * P.KSW * 4 + 15) & ~(size_t)15);
+    const uint32_t dyn = kMaxReadRuns * (uint32_t)sizeof(RunDev) + (kReadThreads / 8) * P.group_smem;
+    PGS_LAUNCH(k_get<8>, 2, kReadThreads, dyn, 0, P);
+    stats[0] = cur[0]; stats[1] = cur[1]; stats[2] = cur[2];
+    return err[0] ? (int32_t)err[0] : PGS_OK;
+}
+
+// k_scan_fwd over k runs; outputs as the device side of scan_many (request i uses arena + i*arena_stride, kvs + i*kv_stride)
+int32_t sim_scan(uint32_t k, const uint8_t **data, const uint64_t *data_bytes, const uint64_t **blk_off, const uint32_t **blk_size,
+                 const uint32_t *n_blocks, const pgs_scan_request *reqs, uint32_t n, uint32_t now, uint64_t arena_stride, uint32_t kv_stride,
+                 uint8_t *arena, pgs_kv *kvs, uint8_t *resume, uint32_t resume_stride, pgs_scan_result *results, uint32_t lanes)
+{
+    std::vector<HostRun> runs;
+    ScanParams P{};
+    uint32_t mk = 0;
+    if (!load_runs(k, data, data_bytes, blk_off, blk_size, n_blocks, runs, P.rr, mk)) return PGS_CORRUPTION;
+    std::vector<ScanReqDev> dev(n);
+    std::string blob;
+    bool need_crc = false;
+    for (uint32_t i = 0; i < n; i++) {
+        const pgs_scan_request &q = reqs[i];
+        ScanReqDev &d = dev[i];
+        memset(&d, 0, sizeof d);
+        auto put = [&](const pgs_blob &b, uint32_t &off, uint32_t &len) { off = (uint32_t)blob.size(); len = b.len; if (b.len) blob.append((const char *)b.data, b.len); };
+        put(q.start, d.start_off, d.start_len); put(q.stop, d.stop_off, d.stop_len);
+        put(q.hash_filter, d.hf_off, d.hf_len); put(q.sort_filter, d.sf_off, d.sf_len);
+        d.start_inclusive = q.start_inclusive; d.stop_inclusive = q.stop_inclusive; d.reverse = q.reverse;
+        d.no_value = q.no_value; d.key_mode = q.key_mode; d.return_expire_ts = q.return_expire_ts;
+        d.count_only = q.count_only; d.validate_hash = q.validate_hash; d.prefix_same_as_start = q.prefix_same_as_start;
+        d.has_upper = q.reserved[0];
+        d.hash_filter_type = q.hash_filter_type; d.sort_filter_type = q.sort_filter_type;
+        d.max_count = q.max_count; d.max_iter_count = q.max_iter_count; d.max_iter_size = q.max_iter_size;
+        d.pidx = q.pidx; d.partition_version = q.partition_version;
+        need_crc |= q.validate_hash != 0;
+        if (q.reverse) return PGS_NOT_SUPPORTED;
+    }
+    blob.append(64, '\0');
+    uint32_t err[16] = {0};
+    P.reqs = dev.data(); P.blob = (const uint8_t *)blob.data(); P.n = n; P.now = now; P.data_version = 1;
+    P.results = results; P.kvs = kvs; P.kv_stride = kv_stride; P.arena = arena; P.arena_stride = arena_stride;
+    P.resume = resume; P.resume_stride = resume_stride; P.error = err; P.ticket = err + 8;
+    if (need_crc) { make_crc(); P.crc_table = (const unsigned long long *)crc_tab; }
+    const uint32_t G = lanes ? lanes : (k <= 8 ? 8 : k <= 16 ? 16 : 32);
+    if (G < k) return PGS_INVALID_ARGUMENT;
+    P.KS = std::max(8u, (mk + 3) & ~3u);
+    P.KSW = (P.KS + 8) / 4 + 1;
+    P.group_smem = (uint32_t)((k * (sizeof(CurState) + P.KSW * 4) + 3 * P.KSW * 4 + 15) & ~(size_t)15);
+    const uint32_t dyn = 2048 + kMaxReadRuns * (uint32_t)sizeof(RunDev) + (kReadThreads / G) * P.group_smem;
+    if (G == 8) PGS_LAUNCH(k_scan_fwd<8>, 2, kReadThreads, dyn, 0, P);
+    else if (G == 16) PGS_LAUNCH(k_scan_fwd<16>, 2, kReadThreads, dyn, 0, P);
+    else PGS_LAUNCH(k_scan_fwd<32>, 2, kReadThreads, dyn, 0, P);
+    return err[0] ? (int32_t)err[0] : PGS_OK;
 }
 
 } // extern "C"
