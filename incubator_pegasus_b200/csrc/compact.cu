@@ -16,9 +16,13 @@ static std::mutex g_crc_mu;
 // the opt-in shared-memory maximum of the compaction kernels, once per device (a per-call cudaFuncSetAttribute would race)
 int32_t compact_init_kernels(int max_smem)
 {
-    PGS_CUDA(cudaFuncSetAttribute(k_walk<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PGS_CUDA(cudaFuncSetAttribute(k_walk<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PGS_CUDA(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    cudaFuncAttributes a;
+    PGS_CUDA(cudaFuncGetAttributes(&a, k_walk<8>));
+    PGS_CUDA(cudaFuncSetAttribute(k_walk<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - (int)a.sharedSizeBytes));
+    PGS_CUDA(cudaFuncGetAttributes(&a, k_walk<16>));
+    PGS_CUDA(cudaFuncSetAttribute(k_walk<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - (int)a.sharedSizeBytes));
+    PGS_CUDA(cudaFuncGetAttributes(&a, k_emit));
+    PGS_CUDA(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - (int)a.sharedSizeBytes));
     return PGS_OK;
 }
 } // namespace pgs
@@ -217,12 +221,12 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
         set_error("compaction kernel failed with status %u at segment %u of %u", hs.error, hs.error_seg, P.Q);
         return (int32_t)hs.error;
     }
-    res.in_records = hs.in_records; res.out_records = hs.out_records;
-    res.in_bytes = hs.in_bytes; res.out_bytes = hs.out_bytes;
+    res.in_records = hs.cnt[EV_IN]; res.out_records = hs.cnt[EV_OUT];
+    res.in_bytes = hs.bytes[SB_IN]; res.out_bytes = hs.bytes[SB_OUT];
     res.in_block_bytes = T.in_block_bytes; res.out_block_bytes = hs.tot_bytes;
-    res.dropped_shadowed = hs.dropped_shadowed; res.dropped_tombstone = hs.dropped_tombstone;
-    res.dropped_expired = hs.dropped_expired; res.dropped_user = hs.dropped_user; res.dropped_stale = hs.dropped_stale;
-    res.ttl_rewritten = hs.ttl_rewritten;
+    res.dropped_shadowed = hs.cnt[EV_SHADOW]; res.dropped_tombstone = hs.cnt[EV_TOMB];
+    res.dropped_expired = hs.cnt[EV_EXPIRED]; res.dropped_user = hs.cnt[EV_USER]; res.dropped_stale = hs.cnt[EV_STALE];
+    res.ttl_rewritten = hs.cnt[EV_TTL];
     res.n_tiles = P.Q; res.n_launches = 6;
     res.device_ms = ms_total; res.merge_kernel_ms = ms_merge;
     res.walk_ms = ms_walk; res.emit_ms = ms_emit;
@@ -230,17 +234,17 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     outr->info.level = out_level;
     outr->info.n_blocks = (uint32_t)hs.tot_blocks;
     outr->info.n_records = hs.tot_recs;
-    outr->info.n_tombstones = hs.out_tomb;
+    outr->info.n_tombstones = hs.cnt[EV_OUT_TOMB];
     outr->info.data_bytes = hs.tot_bytes;
-    outr->info.raw_key_bytes = hs.out_raw_key;
-    outr->info.raw_value_bytes = hs.out_raw_val;
-    outr->info.max_ukey_len = (uint32_t)hs.max_ukey;
-    outr->info.max_value_len = (uint32_t)hs.max_vlen;
-    outr->info.max_block_size = (uint32_t)hs.max_blk_size;
-    outr->info.max_block_records = (uint32_t)hs.max_blk_rec;
-    outr->info.smallest_seq = hs.tot_recs ? ~hs.min_seq_inv : ~0ull;
-    outr->info.largest_seq = hs.max_seq;
-    outr->n_bloom_entries = hs.bloom_entries;
+    outr->info.raw_key_bytes = hs.bytes[SB_OUT_KEY];
+    outr->info.raw_value_bytes = hs.bytes[SB_OUT_VAL];
+    outr->info.max_ukey_len = (uint32_t)hs.mx[SM_UKEY];
+    outr->info.max_value_len = (uint32_t)hs.mx[SM_VLEN];
+    outr->info.max_block_size = (uint32_t)hs.mx[SM_BLK_SIZE];
+    outr->info.max_block_records = (uint32_t)hs.mx[SM_BLK_REC];
+    outr->info.smallest_seq = hs.tot_recs ? (~hs.mx[SM_MIN_SEQ_INV] & ((1ull << 56) - 1)) : ~0ull;
+    outr->info.largest_seq = hs.mx[SM_MAX_SEQ];
+    outr->n_bloom_entries = hs.cnt[EV_BLOOM_KEY] + hs.cnt[EV_BLOOM_PREFIX];
     {
         std::lock_guard<std::mutex> g(part.mu);
         if (!(flags & PGS_COMPACT_KEEP_INPUTS))

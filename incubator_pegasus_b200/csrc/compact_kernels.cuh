@@ -59,17 +59,18 @@ struct __align__(16) SegBase { // exclusive prefixes over the segments (k_seg_sc
     uint32_t blocks, recs, keyb, pad;
 };
 
+// counters of one compaction.  k_walk keeps them in lane-distributed registers (lane L of a group counts event L, sums byte
+// sum L, tracks maximum L) and adds them here once per group.
 struct MergeStats {
-    unsigned long long in_records, in_bytes, out_records, out_bytes;
-    unsigned long long dropped_shadowed, dropped_tombstone, dropped_expired, dropped_user, dropped_stale, ttl_rewritten;
-    unsigned long long out_tomb, out_raw_key, out_raw_val, bloom_entries, spare1, spare2;
-    unsigned long long max_ukey, max_vlen, max_blk_size, max_blk_rec, max_seq, min_seq_inv; // maxima (min_seq kept as ~min)
+    unsigned long long cnt[16];  // EV_*
+    unsigned long long bytes[4]; // SB_*
+    unsigned long long mx[8];    // SM_* (maxima; the smallest sequence number is kept as the maximum of its complement)
     unsigned long long tot_bytes, tot_blocks, tot_recs, tot_keyb; // k_seg_scan
     uint32_t error, error_seg;
 };
-enum { ST_IN_REC = 0, ST_IN_BYTES, ST_OUT_REC, ST_OUT_BYTES, ST_SHADOW, ST_TOMB, ST_EXPIRED, ST_USER, ST_STALE, ST_TTL,
-       ST_OUT_TOMB, ST_OUT_KEY, ST_OUT_VAL, ST_BLOOM };
-enum { SM_UKEY = 0, SM_VLEN, SM_BLK_SIZE, SM_BLK_REC, SM_MAX_SEQ, SM_MIN_SEQ_INV };
+enum { EV_IN = 0, EV_OUT, EV_SHADOW, EV_TOMB, EV_EXPIRED, EV_USER, EV_STALE, EV_TTL, EV_OUT_TOMB, EV_BLOOM_KEY, EV_BLOOM_PREFIX };
+enum { SB_IN = 0, SB_OUT, SB_OUT_KEY, SB_OUT_VAL };
+enum { SM_UKEY = 0, SM_VLEN, SM_MAX_SEQ, SM_MIN_SEQ_INV, SM_BLK_SIZE, SM_BLK_REC };
 
 struct MergeParams {
     RunDev runs[kMaxRuns];
@@ -336,7 +337,7 @@ PGS_DEV uint32_t ld_u16(const uint8_t *p) { return p[0] | (p[1] << 8); }
 
 // user_specified_operation_filter: key_ttl_compaction_filter.h:94-108 over the binary ops table.
 // Every op sees the value as of entry (entry_ts); returns true when a delete op fired.
-PGS_DEV bool dev_user_ops(const MergeParams &P, const uint8_t *hk, uint32_t hkl, const uint8_t *sk, uint32_t skl,
+static __device__ __noinline__ bool dev_user_ops(const MergeParams &P, const uint8_t *hk, uint32_t hkl, const uint8_t *sk, uint32_t skl,
                           uint32_t entry_ts, uint32_t &new_ts, bool &changed)
 {
     const uint8_t *p = P.ops + 4;
@@ -372,7 +373,7 @@ PGS_DEV bool dev_user_ops(const MergeParams &P, const uint8_t *hk, uint32_t hkl,
     return false;
 }
 
-PGS_DEV unsigned long long dev_crc64(const unsigned long long *tab, const uint8_t *p, uint32_t n)
+static __device__ __noinline__ unsigned long long dev_crc64(const unsigned long long *tab, const uint8_t *p, uint32_t n)
 {
     unsigned long long c = ~0ull; // init 0 -> ~init
     for (uint32_t i = 0; i < n; i++) c = tab[(uint8_t)(c ^ p[i])] ^ (c >> 8);
@@ -410,15 +411,29 @@ PGS_DEV uint32_t dev_filter(const MergeParams &P, const unsigned long long *crc_
 // ------------------------------------------------------------------------------------------------
 // k_walk
 // ------------------------------------------------------------------------------------------------
-// the varint32 encoding of v as little-endian bytes in a register (at most 5), len = its length
-PGS_DEV unsigned long long varint_pack(uint32_t v, uint32_t &len)
+// entry head, uncommon shape (a length that needs a multi-byte varint beyond the packed fast path): byte by byte, one lane
+static __device__ __noinline__ void emit_head_slow(uint8_t *hp, uint32_t shared, uint32_t kd, uint32_t vlen, const uint8_t *key, uint32_t tr_lo, uint32_t tr_hi)
 {
-    unsigned long long o = 0;
-    uint32_t n = 0;
-    while (v >= 128) { o |= (unsigned long long)((v & 127u) | 128u) << (8 * n); v >>= 7; n++; }
-    o |= (unsigned long long)v << (8 * n);
-    len = n + 1;
-    return o;
+    hp += put_varint32(hp, shared);
+    hp += put_varint32(hp, kd + 8);
+    hp += put_varint32(hp, vlen);
+    for (uint32_t i = 0; i < kd; i++) hp[i] = key[shared + i];
+    hp += kd;
+    for (uint32_t i = 0; i < 4; i++) { hp[i] = (uint8_t)(tr_lo >> (8 * i)); hp[4 + i] = (uint8_t)(tr_hi >> (8 * i)); }
+}
+// the three varints of an entry head packed into (lo, hi) when shared < 128, non_shared < 128 and value_len < 2^21 (the common
+// shape, at most 5 bytes); returns their length, 0 = does not apply
+PGS_DEV uint32_t pack_head_varints(uint32_t shared, uint32_t ns, uint32_t vlen, uint32_t &lo, uint32_t &hi)
+{
+    if ((shared | ns) >= 128u || vlen >= (1u << 21)) return 0;
+    lo = shared | (ns << 8);
+    hi = 0;
+    if (vlen < 128u) { lo |= vlen << 16; return 3; }
+    lo |= ((vlen & 127u) | 128u) << 16;
+    if (vlen < 16384u) { lo |= (vlen >> 7) << 24; return 4; }
+    lo |= (((vlen >> 7) & 127u) | 128u) << 24;
+    hi = vlen >> 14;
+    return 5;
 }
 
 // order of two cursor heads as internal keys: user key ascending, then trailer (seq, type) descending, then run index.
@@ -439,16 +454,21 @@ PGS_DEV bool head_before(const Grp<G> &g, bool en, const CurState *cs, const uin
 
 // One segment per group, all groups of the warp in lock step (see group.cuh): every statement outside an `if (en...)` body is
 // executed by all 32 lanes; `act` marks the groups that still have records.
+// lane-distributed statistics of a group (see MergeStats)
+struct WalkAcc {
+    uint32_t c0, c1;        // event counts: lane L counts event L (c0) and event 8 + L (c1)
+    unsigned long long b;   // byte sums: lane L < 4 sums SB_* L
+    unsigned long long m;   // maxima: lane L < 6 tracks SM_* L
+};
+
 template <uint32_t G>
 PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G> &g, bool seg_en, uint32_t q, CurState *cs, uint32_t *rows,
-                          const unsigned long long *crc, unsigned long long &acc0, unsigned long long &acc1, unsigned long long &accm)
+                          const unsigned long long *crc, WalkAcc &acc)
 {
     const uint32_t k = P.k, KS = P.KS, KSW = P.KSW, RI = P.restart_interval, BS = P.block_size;
     uint32_t *rowA = rows + k * KSW, *rowB = rowA + KSW, *rowLO = rowB + KSW, *rowHI = rowLO + KSW;
     const bool first = q == 0, last = q == P.Q - 1;
     uint32_t err = 0;
-#define STAT_ADD(slot, v) do { if (g.gl == ((slot) % G)) { if ((slot) / G == 0) acc0 += (v); else acc1 += (v); } } while (0)
-#define STAT_MAX(slot, v) do { if (g.gl == ((slot) % G)) { const unsigned long long v_ = (v); if (v_ > accm) accm = v_; } } while (0)
 
     // ---- boundary keys (U_lo, U_hi] --------------------------------------------------------------------------------
     uint32_t ulo_len = 0, uhi_len = 0;
@@ -462,6 +482,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
             if (len > KS) { err = PGS_ABORTED; break; }
             uint8_t *dst = (uint8_t *)(which == 0 ? rowLO : rowHI);
             const uint8_t *src = runs[run].ikeys + off;
+#pragma unroll 1
             for (uint32_t i = g.gl; i < len; i += G) dst[i] = src[i];
             if (which == 0) ulo_len = len; else uhi_len = len;
         }
@@ -472,6 +493,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
     uint32_t live = 0, my_run = 0; // lanes 0..live-1 of a group hold its runs in merge order
     uint32_t dpos = 0;
     bool by_byte = false;
+#pragma unroll 1
     for (uint32_t j = 0; j < k; j++) {
         const bool en = seg_en && !err;
         uint32_t lo = 0, hi_ex = 0, chk = 0;
@@ -480,6 +502,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         uint32_t *row = rows + j * KSW;
         const uint32_t e1 = cur_open(g, en && !err, runs[j], C, row, KS, lo, hi_ex, chk);
         if (en && !err) err = e1;
+#pragma unroll 1
         for (;;) { // records at or below U_lo belong to the previous segment
             const bool sk = seg_en && !err && !first && C->live;
             const int c = row_cmp(g, sk, row, sk ? C->klen - 8 : 0u, rowLO, ulo_len, dpos);
@@ -497,6 +520,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         const bool ins = seg_en && !err && C->live;
         uint32_t pos = live;
         bool searching = ins;
+#pragma unroll 1
         for (uint32_t i = 0; g.any(searching && i < live); i++) {
             const uint32_t r = g.shfl(my_run, i);
             const bool e = searching && i < live;
@@ -528,18 +552,19 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         out_bytes += (size + kBlockAlign - 1) & ~(unsigned long long)(kBlockAlign - 1);
         n_blocks++;
         keyb += lenA;
-        STAT_MAX(SM_BLK_SIZE, size);
-        STAT_MAX(SM_BLK_REC, blk_n);
+        const unsigned long long mv = g.gl == SM_BLK_SIZE ? size : (g.gl == SM_BLK_REC ? blk_n : 0u);
+        if (mv > acc.m && (g.gl == SM_BLK_SIZE || g.gl == SM_BLK_REC)) acc.m = mv;
     };
+#pragma unroll 1
     for (;;) {
         const bool act = seg_en && live > 0 && !err;
         if (!g.any(act)) break;
         const uint32_t c = g.shfl(my_run, 0) & 15u;
         CurState *C = &cs[c];
         uint32_t *row = rows + c * KSW;
-        uint32_t ulen = 0, vlen = 0, type = 0;
-        unsigned long long tr = 0;
-        if (act) { ulen = C->klen - 8; vlen = C->vlen; tr = cur_trailer(C); type = (uint32_t)tr & 0xffu; }
+        uint32_t ulen = 0, vlen = 0, type = 0, tr_lo = 0, tr_hi = 0;
+        if (act) { ulen = C->klen - 8; vlen = C->vlen; tr_lo = C->tr_lo; tr_hi = C->tr_hi; type = tr_lo & 0xffu; }
+        uint32_t ev = act ? 1u << EV_IN : 0u; // what happened to this record, one bit per counter
         // (1) an older version of the user key that was just handled?
         uint32_t lcp_head = 0;
         const bool cmp1 = act && have_head;
@@ -549,23 +574,21 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         bool keep = false, tomb = false, rewrite = false;
         uint32_t nts = 0, vlen_out = vlen;
         if (act) {
-            STAT_ADD(ST_IN_REC, 1);
-            STAT_ADD(ST_IN_BYTES, ulen + vlen);
-            if (shadow) STAT_ADD(ST_SHADOW, 1);
+            if (shadow) ev |= 1u << EV_SHADOW;
             else if (type == PGS_TYPE_VALUE) {
                 bool changed;
                 const uint32_t ets = __byte_perm(C->ets_le, 0, 0x0123);
                 const uint32_t why = dev_filter(P, crc, (const uint8_t *)row, ulen, ets, vlen, nts, changed);
                 if (why) {
-                    if (why == 1) STAT_ADD(ST_EXPIRED, 1); else if (why == 2) STAT_ADD(ST_USER, 1); else STAT_ADD(ST_STALE, 1);
+                    ev |= why == 1 ? 1u << EV_EXPIRED : (why == 2 ? 1u << EV_USER : 1u << EV_STALE);
                     // Decision::kRemove turns the entry into a deletion; it disappears only at the bottommost level
                     if (!P.bottommost) { keep = tomb = true; vlen_out = 0; }
                 } else {
                     keep = true;
-                    if (changed) { rewrite = true; STAT_ADD(ST_TTL, 1); }
+                    if (changed) { rewrite = true; ev |= 1u << EV_TTL; }
                 }
             } else if (type == PGS_TYPE_DELETION) {
-                if (P.bottommost) STAT_ADD(ST_TOMB, 1); else keep = tomb = true;
+                if (P.bottommost) ev |= 1u << EV_TOMB; else keep = tomb = true;
             } else {
                 keep = true;
             }
@@ -587,53 +610,54 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
                 const unsigned long long hp = bloom_hash_row(g, row, new_prefix ? pl : 0u);
                 if (new_prefix && g.gl < 6) bloom_add_bit(P.out_bloom, P.out_bloom_lines, hp, g.gl);
             }
-            if (keep) { prev_pl = pl; STAT_ADD(ST_BLOOM, new_prefix ? 2 : 1); }
+            if (keep) { prev_pl = pl; ev |= 1u << EV_BLOOM_KEY; if (new_prefix) ev |= 1u << EV_BLOOM_PREFIX; }
         }
         if (keep) {
             const uint32_t otype = tomb ? (uint32_t)PGS_TYPE_DELETION : type;
-            const unsigned long long seq = (P.bottommost && otype == PGS_TYPE_VALUE) ? 0ull : (tr >> 8);
-            const unsigned long long otr = (seq << 8) | otype;
-            uint32_t kd = ulen - shared, l1, l2, l3;
-            unsigned long long v1 = varint_pack(shared, l1), v2 = varint_pack(kd + 8, l2);
-            const unsigned long long v3 = varint_pack(vlen_out, l3);
-            unsigned long long e = (unsigned long long)l1 + l2 + l3 + kd + 8 + vlen_out;
+            const bool zero_seq = P.bottommost && otype == PGS_TYPE_VALUE;
+            const uint32_t otr_lo = zero_seq ? otype : ((tr_lo & ~0xffu) | otype), otr_hi = zero_seq ? 0u : tr_hi;
+            if (vlen_out > 0xFFF00000u) err = PGS_NOT_SUPPORTED; // entry sizes are 32-bit below
+            uint32_t kd = ulen - shared, hv_lo, hv_hi;
+            uint32_t hv = pack_head_varints(shared, kd + 8, vlen_out, hv_lo, hv_hi);
+            uint32_t hvl = hv ? hv : varint_len(shared) + varint_len(kd + 8) + varint_len(vlen_out);
+            uint32_t e = hvl + kd + 8 + vlen_out;
             uint32_t flags = 0, aux = 0;
             // block cut: the entry (and the restart array it may extend) must fit the block
             if (blk_n > 0 && (prev_big || blk_bytes + e + 4 * (nrest + (restart ? 1u : 0u) + 1) > BS)) {
                 close_block();
                 blk_n = 0; blk_bytes = 0; nrest = 0;
                 restart = true; shared = 0; kd = ulen;
-                v1 = 0; l1 = 1; v2 = varint_pack(kd + 8, l2);
-                e = (unsigned long long)l1 + l2 + l3 + kd + 8 + vlen_out;
+                hv = pack_head_varints(0, kd + 8, vlen_out, hv_lo, hv_hi);
+                hvl = hv ? hv : 1 + varint_len(kd + 8) + varint_len(vlen_out);
+                e = hvl + kd + 8 + vlen_out;
             }
             if (blk_n == 0) {
                 flags |= DF_NEWBLOCK;
                 if (n_out > 0) { // the finished block's last user key travels in the head stream
                     aux = lenA;
+#pragma unroll 1
                     for (uint32_t i = g.gl; i < lenA; i += G) heads[hpos + i] = ((const uint8_t *)rowA)[i];
                     hpos += lenA;
                 }
             }
             const bool big = e + 8 > P.blk_buf; // does not fit the block buffer of k_emit: a block of its own, written in place
             if (big) flags |= DF_BIG;
-            if (e > 0xFFFFFFF0ull || blk_bytes + e > 0xFFFFFFF0ull) err = PGS_NOT_SUPPORTED;
             if (rewrite) {
                 flags |= DF_REWRITE;
                 if (g.gl < 4) heads[hpos + g.gl] = (uint8_t)(nts >> (8 * (3 - g.gl))); // BE32
                 hpos += 4;
             }
             // the entry head: varints | key delta | trailer
-            const uint32_t hv = l1 + l2 + l3, hl = hv + kd + 8;
-            {
-                uint8_t *hp = heads + hpos;
-                // the three varints occupy at most 15 bytes: two 64-bit registers' worth, written byte by byte by the first lanes
-                const unsigned long long lo64 = v1 | (v2 << (8 * l1)) | (l1 + l2 < 8 ? v3 << (8 * (l1 + l2)) : 0ull);
-                const unsigned long long hi64 = l1 + l2 >= 8 ? v3 << (8 * (l1 + l2 - 8)) : (l1 + l2 ? v3 >> (8 * (8 - l1 - l2)) : 0ull);
-                for (uint32_t i = g.gl; i < hv; i += G) hp[i] = (uint8_t)((i < 8 ? lo64 >> (8 * i) : hi64 >> (8 * (i - 8))));
+            uint8_t *hp = heads + hpos;
+            if (hv) {
+                if (g.gl < hv) hp[g.gl] = (uint8_t)__byte_perm(hv_lo, hv_hi, g.gl);
+#pragma unroll 1
                 for (uint32_t i = g.gl; i < kd; i += G) hp[hv + i] = ((const uint8_t *)row)[shared + i];
-                if (g.gl < 8) hp[hv + kd + g.gl] = (uint8_t)(otr >> (8 * g.gl));
-                if (G < 8) for (uint32_t i = G + g.gl; i < 8; i += G) hp[hv + kd + i] = (uint8_t)(otr >> (8 * i));
+                if (g.gl < 8) hp[hv + kd + g.gl] = (uint8_t)__byte_perm(otr_lo, otr_hi, g.gl);
+            } else if (g.gl == 0) {
+                emit_head_slow(hp, shared, kd, vlen_out, (const uint8_t *)row, otr_lo, otr_hi);
             }
+            const uint32_t hl = hvl + kd + 8;
             hpos += hl;
             if (g.gl == 0) {
                 Desc d;
@@ -644,23 +668,28 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
             }
             n_out++;
             blk_n++;
-            blk_bytes += (uint32_t)e;
+            blk_bytes += e;
             if (restart) { nrest++; to_restart = RI; }
             to_restart--;
             prev_big = big;
-            STAT_ADD(ST_OUT_REC, 1);
-            STAT_ADD(ST_OUT_BYTES, ulen + vlen_out);
-            STAT_ADD(ST_OUT_KEY, ulen);
-            STAT_ADD(ST_OUT_VAL, vlen_out);
-            if (otype == PGS_TYPE_DELETION) STAT_ADD(ST_OUT_TOMB, 1);
-            STAT_MAX(SM_UKEY, ulen);
-            STAT_MAX(SM_VLEN, vlen_out);
-            STAT_MAX(SM_MAX_SEQ, seq);
-            STAT_MAX(SM_MIN_SEQ_INV, ~seq);
+            ev |= 1u << EV_OUT;
+            if (otype == PGS_TYPE_DELETION) ev |= 1u << EV_OUT_TOMB;
+            // maxima: lane L tracks SM_* L (sequence numbers are 56 bits)
+            const unsigned long long seq = ((unsigned long long)otr_hi << 24) | (otr_lo >> 8);
+            const unsigned long long mv = g.gl == SM_UKEY ? ulen : g.gl == SM_VLEN ? vlen_out : g.gl == SM_MAX_SEQ ? seq : ~seq;
+            if (g.gl <= SM_MIN_SEQ_INV && mv > acc.m) acc.m = mv;
+        }
+        // counters: lane L adds event L / byte sum L
+        acc.c0 += (ev >> g.gl) & 1u;
+        if (G == 8) acc.c1 += (ev >> (8 + g.gl)) & 1u;
+        {
+            const uint32_t in_b = act ? ulen + vlen : 0u, out_k = keep ? ulen : 0u, out_v = keep ? vlen_out : 0u;
+            acc.b += g.gl == SB_IN ? in_b : g.gl == SB_OUT ? out_k + out_v : g.gl == SB_OUT_KEY ? out_k : g.gl == SB_OUT_VAL ? out_v : 0u;
         }
         g.sync(); // every lane has read the previous survivor's key
         if (act && !shadow) {
             uint32_t *dst = keep ? rowA : rowB;
+#pragma unroll 1
             for (uint32_t w = g.gl; 4 * w < ulen; w += G) dst[w] = row[w];
             if (keep) lenA = ulen;
             head_in_A = keep;
@@ -680,6 +709,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         if (searching) d1_valid = false;
         uint32_t pos = 0;
         const bool reorder = searching;
+#pragma unroll 1
         for (uint32_t i = 1; g.any(searching && i < live); i++) {
             const uint32_t r = g.shfl(my_run, i) & 15u;
             const bool e = searching && i < live;
@@ -702,6 +732,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
     if (seg_en) {
         if (!err && blk_n > 0) {
             close_block();
+#pragma unroll 1
             for (uint32_t i = g.gl; i < lenA; i += G) heads[hpos + i] = ((const uint8_t *)rowA)[i];
             hpos += lenA;
         }
@@ -716,8 +747,6 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         }
     }
     g.sync();
-#undef STAT_ADD
-#undef STAT_MAX
 }
 
 template <uint32_t G>
@@ -738,20 +767,22 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ M
     uint8_t *gs = dyn + 2048 + kMaxRuns * sizeof(RunDev) + (size_t)(warp * NGW + g.shift / G) * P.group_smem;
     CurState *cs = (CurState *)gs;
     uint32_t *rows = (uint32_t *)(gs + (size_t)P.k * sizeof(CurState));
-    unsigned long long acc0 = 0, acc1 = 0, accm = 0;
+    WalkAcc acc;
+    acc.c0 = acc.c1 = 0; acc.b = 0; acc.m = 0;
+#pragma unroll 1
     for (;;) {
         uint32_t t0 = 0;
         if (lane == 0) t0 = atomicAdd(P.ticket, NGW);
         t0 = __shfl_sync(kFull, t0, 0);
         if (t0 >= P.Q) break;
         const uint32_t q = t0 + g.shift / G;
-        walk_segment<G>(P, runs, g, q < P.Q, q < P.Q ? q : 0u, cs, rows, crc, acc0, acc1, accm);
+        walk_segment<G>(P, runs, g, q < P.Q, q < P.Q ? q : 0u, cs, rows, crc, acc);
     }
-    // statistics: lane s % G of a group holds counter s
-    unsigned long long *st = &P.stats->in_records;
-    if (g.gl < 16 && acc0) atomicAdd(st + g.gl, acc0);
-    if (g.gl + G < 16 && acc1) atomicAdd(st + g.gl + G, acc1);
-    if (g.gl < 6 && accm) atomicMax(&P.stats->max_ukey + g.gl, accm);
+    // statistics: lane L of a group holds event count L (and 8 + L), byte sum L, maximum L
+    if (g.gl < 16 && acc.c0) atomicAdd(&P.stats->cnt[g.gl], (unsigned long long)acc.c0);
+    if (G == 8 && acc.c1) atomicAdd(&P.stats->cnt[8 + g.gl], (unsigned long long)acc.c1);
+    if (g.gl < 4 && acc.b) atomicAdd(&P.stats->bytes[g.gl], acc.b);
+    if (g.gl < 6 && acc.m) atomicMax(&P.stats->mx[g.gl], acc.m);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -359,7 +359,10 @@ int32_t pgs_engine_open(const pgs_engine_config *cfg, pgs_engine **out)
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e.sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     for (auto &s : e.rd_streams) if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-    if (err == cudaSuccess && (lookup_init_kernels(e.max_smem_optin) != PGS_OK || compact_init_kernels(e.max_smem_optin) != PGS_OK)) err = cudaGetLastError() != cudaSuccess ? cudaErrorUnknown : cudaErrorUnknown;
+    if (err == cudaSuccess && (lookup_init_kernels(e.max_smem_optin) != PGS_OK || compact_init_kernels(e.max_smem_optin) != PGS_OK)) {
+        delete h; // the failing call left its description in pgs_last_error()
+        return PGS_IO_ERROR;
+    }
     if (err == cudaSuccess) { // keep freed compaction buffers in the stream-ordered pool
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {

@@ -53,6 +53,7 @@ PGS_DEV int row_cmp(const Grp<G> &g, bool en, const uint32_t *a, uint32_t la, co
 {
     const uint32_t m = en ? (la < lb ? la : lb) : 0u;
     int res = 2; // undecided
+#pragma unroll 1
     for (uint32_t base = 0; g.any(res == 2 && base < m); base += 4 * G) {
         const uint32_t off = base + 4 * g.gl;
         uint32_t x = 0;
@@ -115,6 +116,24 @@ PGS_DEV void cur_prefetch_next(const Grp<G> &g, bool en, const RunDev &r, CurSta
     async_copy_commit();
 }
 
+// three varint32 (shared, non_shared, value_len) at A, any shape; returns the header length or 0 (malformed).  Rare path.
+static __device__ __noinline__ uint32_t parse_header_slow(const uint8_t *A, uint32_t &sh, uint32_t &ns, uint32_t &vl)
+{
+    uint32_t c1 = get_varint32(A, 5, sh), c2 = 0, c3 = 0;
+    if (c1) c2 = get_varint32(A + c1, 5, ns);
+    if (c2) c3 = get_varint32(A + c1 + c2, 5, vl);
+    return c3 ? c1 + c2 + c3 : 0u;
+}
+// 8 bytes at an arbitrary address as two 32-bit halves: three aligned word loads + two funnel shifts (no 64-bit arithmetic)
+PGS_DEV void ld_2x32_any(const uint8_t *p, uint32_t &lo, uint32_t &hi)
+{
+    const uint32_t *w = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)((uintptr_t)p & 3) * 8;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    lo = __funnelshift_r(w0, w1, sh);
+    hi = __funnelshift_r(w1, w2, sh);
+}
+
 // decode the entry at (base, p) of the current block into the state and the key row (groups with en).  prev_klen = internal-
 // key length of the previous entry of the block (0 at a block start: the entry must then be a restart point).
 // Executed by the whole warp (two warp barriers inside).  Returns 0 or a status.
@@ -126,13 +145,12 @@ PGS_DEV uint32_t cur_decode(const Grp<G> &g, bool en, const RunDev &r, CurState 
     const uint8_t *src = nullptr;
     if (en) {
         const uint8_t *A = r.data + base + p;
-        h = parse_header8(ld_u64_any(A), sh, ns, vl);
+        uint32_t h_lo, h_hi;
+        ld_2x32_any(A, h_lo, h_hi);
+        h = parse_header8(((unsigned long long)h_hi << 32) | h_lo, sh, ns, vl);
         if (!h) { // uncommon shape (a length of two or more varint bytes): byte-wise decoder
-            uint32_t c1 = get_varint32(A, 5, sh), c2 = 0, c3 = 0;
-            if (c1) c2 = get_varint32(A + c1, 5, ns);
-            if (c2) c3 = get_varint32(A + c1 + c2, 5, vl);
-            h = c1 + c2 + c3;
-            if (!c3) err = PGS_CORRUPTION;
+            h = parse_header_slow(A, sh, ns, vl);
+            if (!h) err = PGS_CORRUPTION;
         }
         klen = sh + ns;
         if (!err && (sh > prev_klen || klen < 8 || klen - 8 > KS || (unsigned long long)p + h + ns + vl + 8 > blk_size)) err = PGS_CORRUPTION;
@@ -140,6 +158,7 @@ PGS_DEV uint32_t cur_decode(const Grp<G> &g, bool en, const RunDev &r, CurState 
             // key bytes [sh, sh + ns) <- the entry's delta; lane L owns the words L, L + G, ... of the row
             src = A + h;
             const uint32_t end = sh + ns;
+#pragma unroll 1
             for (uint32_t w = (sh >> 2) + g.gl; 4 * w < end; w += G) {
                 const uint32_t lo = 4 * w;
                 const uint32_t v = ld_u32_any(src + (int32_t)(lo - sh));
@@ -152,13 +171,13 @@ PGS_DEV uint32_t cur_decode(const Grp<G> &g, bool en, const RunDev &r, CurState 
     }
     g.sync();
     if (en && !err) {
-        unsigned long long tr;
-        if (ns >= 8) tr = ld_u64_any(src + ns - 8);
-        else tr = lds_u64_at((const uint8_t *)row, klen - 8); // part of the trailer is shared with the previous key
+        uint32_t tr_lo, tr_hi;
+        if (ns >= 8) ld_2x32_any(src + ns - 8, tr_lo, tr_hi);
+        else { const unsigned long long tr = lds_u64_at((const uint8_t *)row, klen - 8); tr_lo = (uint32_t)tr; tr_hi = (uint32_t)(tr >> 32); } // part of the trailer is shared with the previous key
         const uint32_t ets = vl >= 4 ? ld_u32_any(src + ns) : 0u;
         if (g.gl == 0) {
             c->p = p; c->elen = h + ns + vl; c->klen = klen; c->vlen = vl; c->voff = p + h + ns; c->shared = sh; c->ets_le = ets;
-            c->tr_lo = (uint32_t)tr; c->tr_hi = (uint32_t)(tr >> 32);
+            c->tr_lo = tr_lo; c->tr_hi = tr_hi;
         }
     }
     g.sync();
@@ -241,6 +260,7 @@ template <uint32_t G>
 PGS_DEV unsigned long long bloom_hash_row(const Grp<G> &g, const uint32_t *row, uint32_t len)
 {
     uint32_t ha = 0, hb = 0;
+#pragma unroll 1
     for (uint32_t w = g.gl; 4 * w < len; w += G) {
         uint32_t x = row[w];
         if (len - 4 * w < 4) x &= (1u << (8 * (len - 4 * w))) - 1u;

@@ -838,14 +838,22 @@ static int32_t snapshot_runs(Partition &part, std::vector<std::shared_ptr<Run>> 
 
 // kernels of this file take their dynamic shared-memory size per launch; the opt-in maximum is set once per device here
 // (a per-call cudaFuncSetAttribute would race between reader threads)
+template <class K>
+static cudaError_t allow_max_smem(K kernel, int max_smem)
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, kernel);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - (int)a.sharedSizeBytes);
+}
 int32_t lookup_init_kernels(int max_smem)
 {
-    PGS_CUDA(cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PGS_CUDA(allow_max_smem(k_scan, max_smem));
     PGS_CUDA(cudaFuncSetAttribute(k_scan, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    PGS_CUDA(cudaFuncSetAttribute(k_get<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PGS_CUDA(cudaFuncSetAttribute(k_scan_fwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PGS_CUDA(cudaFuncSetAttribute(k_scan_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    PGS_CUDA(cudaFuncSetAttribute(k_scan_fwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    PGS_CUDA(allow_max_smem(k_get<8>, max_smem));
+    PGS_CUDA(allow_max_smem(k_scan_fwd<8>, max_smem));
+    PGS_CUDA(allow_max_smem(k_scan_fwd<16>, max_smem));
+    PGS_CUDA(allow_max_smem(k_scan_fwd<32>, max_smem));
     return PGS_OK;
 }
 

@@ -6,7 +6,7 @@ import collections, csv, os, re, subprocess, sys
 rep, kpref, stem = sys.argv[1], sys.argv[2], sys.argv[3]
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(ROOT, "incubator_pegasus_b200", "libpegasus_b200.so")
+so = os.environ.get("NCU_LINES_SO") or os.path.join(ROOT, "incubator_pegasus_b200", "libpegasus_b200.so")
 os.system(f"rm -rf /tmp/xelf && mkdir -p /tmp/xelf && cd /tmp/xelf && cuobjdump -xelf all {so} >/dev/null 2>&1")
 cub = [f for f in os.listdir("/tmp/xelf") if f.startswith(stem) and f.endswith(".cubin")][0]
 sass = subprocess.check_output(["nvdisasm", "-g", "-c", os.path.join("/tmp/xelf", cub)]).decode().split("\n")

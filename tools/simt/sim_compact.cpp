@@ -284,9 +284,10 @@ void sim_result_copy(uint8_t *data, uint64_t *blk_off, uint32_t *blk_size, uint3
 void sim_result_stats(uint64_t *o)
 {
     const MergeStats &s = g_res.st;
-    const uint64_t v[20] = {s.in_records, s.out_records, s.in_bytes, s.out_bytes, s.dropped_shadowed, s.dropped_tombstone, s.dropped_expired,
-                            s.dropped_user, s.dropped_stale, s.ttl_rewritten, s.out_tomb, s.out_raw_key, s.out_raw_val, s.max_ukey, s.max_vlen,
-                            s.max_blk_size, s.max_blk_rec, s.tot_recs ? ~s.min_seq_inv : ~0ull, s.max_seq, s.tot_keyb};
+    const uint64_t v[20] = {s.cnt[EV_IN], s.cnt[EV_OUT], s.bytes[SB_IN], s.bytes[SB_OUT], s.cnt[EV_SHADOW], s.cnt[EV_TOMB], s.cnt[EV_EXPIRED],
+                            s.cnt[EV_USER], s.cnt[EV_STALE], s.cnt[EV_TTL], s.cnt[EV_OUT_TOMB], s.bytes[SB_OUT_KEY], s.bytes[SB_OUT_VAL], s.mx[SM_UKEY],
+                            s.mx[SM_VLEN], s.mx[SM_BLK_SIZE], s.mx[SM_BLK_REC], s.tot_recs ? (~s.mx[SM_MIN_SEQ_INV] & ((1ull << 56) - 1)) : ~0ull,
+                            s.mx[SM_MAX_SEQ], s.tot_keyb};
     memcpy(o, v, sizeof v);
 }
 

@@ -157,6 +157,7 @@ inline void launch(K kernel, uint32_t grid, uint32_t block, size_t dyn_bytes, A.
 #define __global__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __restrict__
