@@ -92,7 +92,7 @@ struct MergeParams {
     uint32_t *ticket; // [0] k_walk, [1] k_emit
     uint32_t KS;      // user-key capacity of a key row (multiple of 4)
     uint32_t KSW;     // 32-bit words per key row
-    uint32_t group_smem, emit_warp_smem, blk_buf, head_stage;
+    uint32_t group_smem, emit_warp_smem, emit_obuf, blk_buf, head_stage;
     // filter + policy
     uint32_t now, enabled, validate_hash, data_version, default_ttl;
     int32_t pidx, partition_version;
@@ -135,17 +135,19 @@ inline bool compact_geometry(MergeParams &P, const CompactTotals &T, uint32_t ma
     if (geo.walk_dyn > max_smem) return false;
     const uint32_t hs = (2 * P.KS + 64 + 15) & ~15u;
     P.head_stage = hs < 2048 ? 2048u : hs;
-    // the block buffers of k_emit: two per warp; an entry that does not fit a buffer gets a block of its own, written in place
-    const uint32_t other = 4 * 544 + P.head_stage + 32; // kEmitDepth value windows + the head stage
+    // k_emit per warp: an output assembly buffer (at least one block, normally 8 KB = a batch of ~28 entries), the head stage,
+    // the restart offsets of the open block.  An entry that does not fit a block buffer gets a block of its own, written in place.
     const uint32_t RI = P.restart_interval;
     uint32_t blk_buf = (P.block_size + 24 + 15) & ~15u;
-    if (2ull * blk_buf + other + 4ull * (blk_buf / (11 * RI) + 4) + 64 > max_smem) { // huge block_size: cut smaller blocks
-        if (max_smem < other + 4096) return false;
-        blk_buf = (uint32_t)(((max_smem - other - 128) * 11ull / 24)) & ~15u;
+    if (blk_buf + 1024ull + P.head_stage + 8ull * (blk_buf / (11 * RI) + 4) > max_smem) { // huge block_size: cut smaller blocks
+        if (max_smem < P.head_stage + 8192) return false;
+        blk_buf = (uint32_t)(((max_smem - P.head_stage - 1024) * 11ull / 20)) & ~15u;
         if (P.block_size > blk_buf - 24) P.block_size = blk_buf - 24;
     }
     P.blk_buf = blk_buf;
-    P.emit_warp_smem = (uint32_t)((2ull * blk_buf + other + 4ull * (blk_buf / (11 * RI) + 4) + 15) & ~15ull);
+    const uint32_t ob_min = blk_buf + 4 * (blk_buf / (11 * RI) + 4) + 256; // an entry + the restart array of the block it closes
+    P.emit_obuf = ob_min < 8192 ? 8192u : ((ob_min + 15) & ~15u);
+    P.emit_warp_smem = (uint32_t)((P.emit_obuf + 32ull + P.head_stage + 32 + 4ull * (blk_buf / (11 * RI) + 4) + 15) & ~15ull);
     geo.emit_warps = max_smem / P.emit_warp_smem;
     if (geo.emit_warps > kEmitThreads / 32) geo.emit_warps = kEmitThreads / 32;
     if (geo.emit_warps == 0) return false;
@@ -844,40 +846,70 @@ __global__ void __launch_bounds__(1024) k_seg_scan(const __grid_constant__ Merge
 // ------------------------------------------------------------------------------------------------
 // k_emit
 // ------------------------------------------------------------------------------------------------
-// shared -> shared copy of t bytes, any alignment on both sides (src4 / dst16: 4- / 16-byte aligned buffers, the source readable
-// 16 bytes past its end).  Destination-aligned 16-byte stores; a source chunk is five aligned words re-aligned with funnel shifts.
-PGS_DEV void warp_copy_s2s(uint8_t *dst16, uint32_t doff, const uint8_t *src4, uint32_t soff, uint32_t t, uint32_t lane)
+// One 16-byte chunk of a byte stream at destination alignment: the stream continues from aligned source chunk P into C and
+// starts `a` bytes (0..15) into P.  Select network + funnel shifts: no indexed registers, the same code for every lane.
+PGS_DEV uint4 realign16(uint4 Pc, uint4 Cc, uint32_t a)
 {
-    uint32_t lead = (16 - (doff & 15)) & 15;
-    if (lead > t) lead = t;
-    if (lane < lead) dst16[doff + lane] = src4[soff + lane];
-    const uint32_t d0 = doff + lead, s0 = soff + lead, nch = (t - lead) >> 4, tail = (t - lead) & 15;
-    const uint32_t sh = (s0 & 3) * 8;
-    for (uint32_t c = lane; c < nch; c += 32) {
-        const uint32_t *w = (const uint32_t *)src4 + ((s0 + 16 * c) >> 2);
-        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-        uint4 o;
-        o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh); o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
-        *reinterpret_cast<uint4 *>(dst16 + d0 + 16 * c) = o;
+    uint32_t w0 = Pc.x, w1 = Pc.y, w2 = Pc.z, w3 = Pc.w, w4 = Cc.x, w5 = Cc.y, w6 = Cc.z, w7 = Cc.w;
+    if (a & 4) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7; }
+    if (a & 8) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; }
+    const uint32_t bs = (a & 3) * 8;
+    return make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs), __funnelshift_r(w3, w4, bs));
+}
+// store the bytes [lo, hi) of a 16-byte chunk held in registers to a 16-aligned shared-memory chunk (its neighbours own the rest)
+PGS_DEV void store_chunk_part(uint8_t *dst16, uint4 v, uint32_t lo, uint32_t hi)
+{
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) {
+        const uint32_t b0 = 4 * j, b1 = 4 * j + 4;
+        if (lo <= b0 && b1 <= hi) *reinterpret_cast<uint32_t *>(dst16 + b0) = w[j];
+        else if (lo < b1 && b0 < hi) {
+#pragma unroll
+            for (uint32_t b = 0; b < 4; b++)
+                if (b0 + b >= lo && b0 + b < hi) dst16[b0 + b] = (uint8_t)(w[j] >> (8 * b));
+        }
     }
-    if (lane < tail) dst16[d0 + 16 * nch + lane] = src4[s0 + 16 * nch + lane];
+}
+// one THREAD copies n bytes from global memory (any alignment, readable in whole 16-byte chunks inside [lim_lo, ...)) to shared
+// memory at dst (any alignment): 16-byte loads and stores, byte-exact at both ends.
+PGS_DEV void thread_copy_g2s(uint8_t *obuf16, uint32_t doff, const uint8_t *src, uint32_t n, const uint8_t *lim_lo)
+{
+    if (n == 0) return;
+    const uint32_t x0 = doff & ~15u;                   // first destination chunk
+    const uint8_t *A = src - (doff - x0);              // source byte that lands on destination offset x0 (may precede src)
+    const uint32_t a = (uint32_t)((uintptr_t)A & 15);
+    const uint4 *sp = reinterpret_cast<const uint4 *>(A - a);
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    uint4 Pc = (const uint8_t *)sp >= lim_lo ? sp[0] : zero; // only its bytes before src could lie outside the run's buffer
+    const uint32_t end = doff + n;
+#pragma unroll 1
+    for (uint32_t x = x0; x < end; x += 16) {
+        sp++;
+        const uint4 Cc = a ? *sp : zero;               // (reads at most 15 bytes past the value: run buffers carry slack)
+        const uint4 o = a ? realign16(Pc, Cc, a) : Pc;
+        const uint32_t lo = x < doff ? doff - x : 0u, hi = end - x < 16 ? end - x : 16u;
+        if (lo == 0 && hi == 16) *reinterpret_cast<uint4 *>(obuf16 + x) = o;
+        else store_chunk_part(obuf16 + x, o, lo, hi);
+        Pc = a ? Cc : *sp;
+    }
 }
 
-constexpr uint32_t kEmitDepth = 4;     // value windows in flight per warp
-constexpr uint32_t kEmitWindow = 512;  // bytes of a value moved per window (plus up to 15 bytes of alignment slack)
-constexpr uint32_t kEmitSlot = kEmitWindow + 32;
-
+// k_emit: one warp per segment, one THREAD per entry.  A batch of up to 32 descriptors is laid out with warp scans (block
+// membership, offsets inside the block, block starts, restart points), every thread copies its entry's head and value into the
+// warp's output buffer, the threads standing on a block boundary finish the previous block (restart array, padding, index
+// entry), and the batch's bytes leave with one bulk TMA store.  Blocks of a segment are adjacent in the output run, so a
+// batch's bytes are one contiguous range; the partial 16-byte chunk at its end is carried into the next batch.
 __global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ MergeParams P)
 {
     PGS_SMEM_DYN(dyn);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t RI = P.restart_interval;
+    const uint32_t RI = P.restart_interval, OB = P.emit_obuf;
     uint8_t *ws = dyn + (size_t)warp * P.emit_warp_smem;
-    uint8_t *bbuf[2] = {ws, ws + P.blk_buf};
-    uint8_t *vst = ws + 2 * (size_t)P.blk_buf;                    // kEmitDepth value windows
-    uint8_t *hst = vst + kEmitDepth * kEmitSlot;                  // head_stage + 32 bytes: the head-stream bytes of a batch of entries
-    uint32_t *rst = (uint32_t *)(hst + P.head_stage + 32);        // restart offsets of the open block
-    uint32_t which = 0;
+    uint8_t *obuf = ws;                                          // OB + 32 bytes
+    uint8_t *hst = obuf + OB + 32;                               // head_stage + 32 bytes: the head-stream bytes of a batch
+    uint32_t *rst = (uint32_t *)(hst + P.head_stage + 32);       // restart offsets of the open block (it may span batches)
+    const uint32_t lt = (1u << lane) - 1u;                       // lanes before me
 
     for (;;) {
         uint32_t q = 0;
@@ -889,42 +921,24 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ M
         const SegBase B = P.base[q];
         const Desc *desc = P.desc + P.seg[q].desc_off;
         const uint8_t *heads = P.heads + P.seg[q].head_off;
-        unsigned long long blk_start = B.bytes; // where the open block goes
-        uint32_t blk_idx = B.blocks, rec_idx = B.recs, keyb = B.keyb;
-        uint32_t fill = 0, blk_n = 0, blk_rec0 = rec_idx, hpos = 0, err = 0;
-        uint32_t to_restart = 0, nrest = 0; // entries until the next restart point, restart points of the open block
-        bool open = false, cur_big = false;
-        uint8_t *buf = bbuf[which];
+        // carried state (warp-uniform)
+        unsigned long long blk_start = B.bytes; // global offset of the open block (of the segment's first block before it opens)
+        uint32_t fill = 0, blk_n = 0, blk_rec0 = B.recs; // entry bytes / entries of the open block, its first record
+        bool open = false;
+        uint32_t blk_idx = B.blocks, rec_idx = B.recs, keyb = B.keyb, hpos = 0, err = 0;
+        uint32_t carry = 0; // obuf[0, carry) = the bytes of the partial 16-byte chunk in front of the write position
 
-        auto close_block = [&](const uint8_t *key, uint32_t klen) {
+        // finish the open block outside a batch (whole warp): restart array (offsets kept in rst), count and padding go to `at`
+        // (where byte `fill` of the block lives: obuf + carry, or global memory for a block written in place), index entry
+        auto close_open = [&](const uint8_t *key, uint32_t klen, uint8_t *at, uint32_t nrest) {
             const uint32_t size = fill + 4 * (nrest + 1);
             const uint32_t asz = (size + kBlockAlign - 1) & ~(kBlockAlign - 1);
-            __syncwarp(); // lane 0's restart offsets and every lane's bytes of the last entry are in place
-            if (!cur_big) {
-                for (uint32_t i = lane; i < 4 * (nrest + 1); i += 32) {
-                    const uint32_t v = (i >> 2) < nrest ? rst[i >> 2] : nrest;
-                    buf[fill + i] = (uint8_t)(v >> (8 * (i & 3)));
-                }
-                for (uint32_t i = size + lane; i < asz; i += 32) buf[i] = 0;
-                __syncwarp();
-                fence_proxy_async(); // the block was assembled with ordinary stores; the TMA unit reads it next
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_1d(P.out_data + blk_start, buf, asz);
-                    tma_store_commit();
-                    tma_store_wait_read1(); // the other buffer's store (one block ago) has read its bytes: it may be refilled
-                }
-                which ^= 1;
-                buf = bbuf[which];
-                __syncwarp();
-            } else { // the entry went straight to global memory; so does its one-entry restart array
-                uint8_t *o = P.out_data + blk_start;
-                for (uint32_t i = lane; i < 4 * (nrest + 1); i += 32) {
-                    const uint32_t v = (i >> 2) < nrest ? 0u : nrest; // a block of one entry: restart offset 0
-                    o[fill + i] = (uint8_t)(v >> (8 * (i & 3)));
-                }
-                for (uint32_t i = size + lane; i < asz; i += 32) o[i] = 0;
+            __syncwarp();
+            for (uint32_t i = lane; i < 4 * (nrest + 1); i += 32) {
+                const uint32_t v = (i >> 2) < nrest ? rst[i >> 2] : nrest;
+                at[i] = (uint8_t)(v >> (8 * (i & 3)));
             }
+            for (uint32_t i = size - fill + lane; i < asz - fill; i += 32) at[i] = 0;
             if (lane == 0) {
                 P.out_blk_off[blk_idx] = blk_start;
                 P.out_blk_size[blk_idx] = size;
@@ -935,100 +949,183 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ M
             keyb += klen;
             blk_idx++;
             blk_start += asz;
+            fill = 0; blk_n = 0; open = false;
+        };
+        // write obuf[0, bytes) to the run at the 16-aligned global offset gpos (bytes % 16 == 0), wait until it has been read
+        auto flush = [&](unsigned long long gpos, uint32_t bytes) {
+            __syncwarp();
+            if (bytes) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { tma_store_1d(P.out_data + gpos, obuf, bytes); tma_store_commit(); tma_store_wait_read0(); }
+                __syncwarp();
+            }
         };
 
         for (uint32_t e0 = 0; e0 < A.n_entries && !err;) {
-            // ---- a batch of up to 32 descriptors; their head-stream bytes are staged in shared memory ----------------
             const uint32_t idx = e0 + lane;
             Desc d;
             d.loc = 0; d.vlen = 0; d.aux = 0;
             if (idx < A.n_entries) *reinterpret_cast<uint4 *>(&d) = *reinterpret_cast<const uint4 *>(&desc[idx]);
-            const uint32_t fl_me = (uint32_t)(d.loc >> 60), hl_me = (uint32_t)(d.loc >> 44) & 0xffffu;
-            const uint32_t sb = idx < A.n_entries ? hl_me + ((fl_me & DF_NEWBLOCK) ? d.aux : 0u) + ((fl_me & DF_REWRITE) ? 4u : 0u) : 0u;
-            const uint32_t s_incl = warp_incl_scan(sb, lane);
-            const uint32_t cnt = (uint32_t)__popc(__ballot_sync(kFull, idx < A.n_entries && s_incl <= P.head_stage));
-            if (cnt == 0) { err = PGS_ABORTED; break; }
-            const uint32_t total = __shfl_sync(kFull, s_incl, (int)cnt - 1);
-            const uint8_t *src = heads + hpos;
-            const uint32_t a = (uint32_t)((uintptr_t)src & 15);
-            for (uint32_t i = lane * 16; i < a + total; i += 512) async_copy16(hst + i, src - a + i);
-            async_copy_commit();
-            // ---- value windows: up to kEmitDepth 512-byte pieces of the batch's values are in flight (LDGSTS, no registers) ----
-            uint32_t pe = 0, poff = 0, useq = 0, cseq = 0; // producer entry / value bytes requested, windows issued / consumed
-            auto produce = [&]() {
-                while (pe < cnt) {
-                    const unsigned long long loc = __shfl_sync(kFull, d.loc, (int)pe);
-                    const uint32_t vl = __shfl_sync(kFull, d.vlen, (int)pe);
-                    if (((uint32_t)(loc >> 60) & DF_BIG) || poff >= vl) { pe++; poff = 0; continue; }
-                    const uint8_t *s = P.runs[(uint32_t)(loc >> 40) & 15u].data + (loc & ((1ull << 40) - 1)) + poff;
-                    const uint32_t va = (uint32_t)((uintptr_t)s & 15);
-                    const uint32_t span = vl - poff + va < kEmitWindow ? vl - poff + va : kEmitWindow;
-                    uint8_t *slot = vst + (useq % kEmitDepth) * kEmitSlot;
-                    if (lane * 16 < span) async_copy16(slot + lane * 16, s - va + lane * 16);
-                    poff += span - va;
-                    useq++;
-                    break;
-                }
-                async_copy_commit(); // one group per call, empty or not: the consumer counts groups
-            };
-            for (uint32_t x = 0; x < kEmitDepth - 1; x++) produce();
-            // groups committed so far: 1 (heads) + kEmitDepth - 1; the heads are the oldest
-            async_copy_wait_upto(kEmitDepth - 1);
-            __syncwarp();
-            const uint8_t *hs = hst + a;
-            const uint32_t s_excl = s_incl - sb;
-            for (uint32_t i = 0; i < cnt; i++) {
-                const unsigned long long loc = __shfl_sync(kFull, d.loc, (int)i);
-                const uint32_t vlen = __shfl_sync(kFull, d.vlen, (int)i), aux = __shfl_sync(kFull, d.aux, (int)i);
-                uint32_t so = __shfl_sync(kFull, s_excl, (int)i);
-                const uint32_t fl = (uint32_t)(loc >> 60), hl = (uint32_t)(loc >> 44) & 0xffffu;
-                if (fl & DF_NEWBLOCK) {
-                    if (open) { close_block(hs + so, aux); so += aux; }
-                    open = true;
-                    fill = 0; blk_n = 0; blk_rec0 = rec_idx; to_restart = 0; nrest = 0;
-                    cur_big = (fl & DF_BIG) != 0;
+            const bool have = idx < A.n_entries;
+            const uint32_t fl = (uint32_t)(d.loc >> 60), hl = (uint32_t)(d.loc >> 44) & 0xffffu, vl = d.vlen;
+            const uint32_t first_fl = __shfl_sync(kFull, fl, 0);
+            if (first_fl & DF_BIG) {
+                // ---- an entry larger than a block buffer: a block of its own, written in place by the whole warp ---------------
+                const unsigned long long loc = __shfl_sync(kFull, d.loc, 0);
+                const uint32_t bvl = __shfl_sync(kFull, vl, 0), bhl = __shfl_sync(kFull, hl, 0), baux = __shfl_sync(kFull, d.aux, 0);
+                const uint32_t bfl = first_fl;
+                const uint8_t *hs = heads + hpos; // its head-stream bytes, read straight from global memory
+                uint32_t so = baux; // the previous block's last user key (nothing in front of the segment's first entry)
+                if (open) { // finish the block in front of it; what that block still has in obuf leaves with it
+                    const unsigned long long obase = blk_start + fill - carry;
+                    close_open(hs, baux, obuf + carry, (blk_n + RI - 1) / RI);
+                    flush(obase, (uint32_t)(blk_start - obase));
+                    carry = 0;
                 }
                 const uint8_t *ntsb = hs + so;
-                if (fl & DF_REWRITE) so += 4;
-                if (lane == 0) {
-                    if (to_restart == 0 && !cur_big) rst[nrest] = fill;
-                    P.out_rec_off[rec_idx] = fill;
-                }
-                if (to_restart == 0) { nrest++; to_restart = RI; }
-                to_restart--;
-                if (!cur_big) {
-                    for (uint32_t x = lane; x < hl; x += 32) buf[fill + x] = hs[so + x];
-                    // the value: its windows arrive in issue order; byte-exact placement from shared memory
-                    uint32_t n = vlen, doff = fill + hl;
-                    while (n > 0) {
-                        produce();                               // keep kEmitDepth - 1 windows ahead
-                        async_copy_wait_upto(kEmitDepth - 1);    // ... so the oldest outstanding one is this window
-                        __syncwarp();
-                        const uint32_t va = (uint32_t)((uintptr_t)(P.runs[(uint32_t)(loc >> 40) & 15u].data + (loc & ((1ull << 40) - 1)) + (vlen - n)) & 15); // as the producer saw it
-                        const uint32_t span = n + va < kEmitWindow ? n + va : kEmitWindow, t = span - va;
-                        warp_copy_s2s(buf, doff, vst + (cseq % kEmitDepth) * kEmitSlot, va, t, lane);
-                        cseq++;
-                        __syncwarp();
-                        doff += t; n -= t;
-                    }
-                    if ((fl & DF_REWRITE) && vlen >= 4 && lane < 4) buf[fill + hl + lane] = ntsb[lane];
-                } else {
-                    const uint8_t *vsrc = P.runs[(uint32_t)(loc >> 40) & 15u].data + (loc & ((1ull << 40) - 1));
-                    uint8_t *o = P.out_data + blk_start;
-                    for (uint32_t x = lane; x < hl; x += 32) o[fill + x] = hs[so + x];
-                    for (uint32_t x = lane; x < vlen; x += 32) o[fill + hl + x] = vsrc[x];
-                    if ((fl & DF_REWRITE) && vlen >= 4 && lane < 4) o[fill + hl + lane] = ntsb[lane];
-                }
-                fill += hl + vlen;
-                blk_n++;
-                rec_idx++;
+                if (bfl & DF_REWRITE) so += 4;
+                const uint8_t *vsrc = P.runs[(uint32_t)(loc >> 40) & 15u].data + (loc & ((1ull << 40) - 1));
+                uint8_t *o = P.out_data + blk_start;
+                for (uint32_t x = lane; x < bhl; x += 32) o[x] = hs[so + x];
+                for (uint32_t x = lane; x < bvl; x += 32) o[bhl + x] = vsrc[x];
+                if ((bfl & DF_REWRITE) && bvl >= 4 && lane < 4) o[bhl + lane] = ntsb[lane];
+                if (lane == 0) { rst[0] = 0; P.out_rec_off[rec_idx] = 0; }
+                // the block's last user key is this entry's: it travels in front of the next entry's head, or ends the stream
+                const uint32_t sbytes = so + bhl;
+                const bool last_e = e0 + 1 == A.n_entries;
+                const uint32_t klen = last_e ? A.last_klen : __shfl_sync(kFull, d.aux, 1);
+                const uint8_t *key = last_e ? heads + A.head_bytes - A.last_klen : hs + sbytes;
+                fill = bhl + bvl; blk_n = 1; blk_rec0 = rec_idx; open = true;
+                close_open(key, klen, o + fill, 1u);
+                rec_idx++; hpos += sbytes; e0++;
+                continue;
             }
+            // ---- batch = the entries before the first oversized one that fit the output buffer and the head stage --------
+            const uint32_t sz = have ? hl + vl : 0u;
+            const uint32_t sb = have ? hl + ((fl & DF_NEWBLOCK) ? d.aux : 0u) + ((fl & DF_REWRITE) ? 4u : 0u) : 0u;
+            const uint32_t ps_incl = warp_incl_scan(sz, lane), ss_incl = warp_incl_scan(sb, lane);
+            const uint32_t bigmask = __ballot_sync(kFull, have && (fl & DF_BIG));
+            // room: the entries, the restart arrays and paddings of the blocks that close here (the carried block brings its
+            // earlier restart points along), the carried partial chunk
+            const uint32_t room = carry + 32 * (lane + 1) + 64 + (open ? 4 * ((blk_n + RI - 1) / RI) : 0u);
+            const bool fits = have && !(bigmask & (lt | (1u << lane))) && room + ps_incl <= OB && ss_incl <= P.head_stage;
+            const uint32_t cnt = (uint32_t)__popc(__ballot_sync(kFull, fits)); // monotone: lanes 0..cnt-1
+            if (cnt == 0) { err = PGS_ABORTED; break; }
+            const bool mine = lane < cnt;
+            const uint32_t total_s = __shfl_sync(kFull, ss_incl, (int)cnt - 1);
+            {   // stage the batch's head-stream bytes
+                const uint8_t *src = heads + hpos;
+                const uint32_t a = (uint32_t)((uintptr_t)src & 15);
+                for (uint32_t i = lane * 16; i < a + total_s; i += 512) async_copy16(hst + i, src - a + i);
+                async_copy_commit();
+            }
+            // ---- layout: block membership, offsets, block starts ----------------------------------------------------------------
+            const bool head = mine && (fl & DF_NEWBLOCK);
+            const uint32_t hm = __ballot_sync(kFull, head);
+            const uint32_t at_or_before = hm & (lt | (1u << lane)), before = hm & lt;
+            const int h = at_or_before ? 31 - __clz((int)at_or_before) : -1;  // the block I belong to starts at lane h (-1: the carried block)
+            const int ph = before ? 31 - __clz((int)before) : -1;              // the head before me
+            const uint32_t ps = ps_incl - sz;                                   // entry bytes of the batch before me
+            const uint32_t ps_h = __shfl_sync(kFull, ps, h >= 0 ? h : 0), ps_ph = __shfl_sync(kFull, ps, ph >= 0 ? ph : 0);
+            const uint32_t fill_i = h >= 0 ? ps - ps_h : fill + ps;            // my offset inside my block
+            const uint32_t n_i = h >= 0 ? lane - (uint32_t)h : blk_n + lane;   // my index inside my block
+            // a head closes the block before it (if there is one): its entry bytes, entry count, aligned size
+            const bool closes = head && (ph >= 0 || open);
+            const uint32_t T = ph >= 0 ? ps - ps_ph : fill + ps, NN = ph >= 0 ? lane - (uint32_t)ph : blk_n + lane;
+            const uint32_t nrest_c = closes ? (NN + RI - 1) / RI : 0u;
+            const uint32_t size_c = T + 4 * (nrest_c + 1);
+            const uint32_t asz_c = closes ? ((size_c + kBlockAlign - 1) & ~(kBlockAlign - 1)) : 0u;
+            const uint32_t S_incl = warp_incl_scan(asz_c, lane);               // bytes of the blocks closed at or before me
+            const uint32_t S_h = __shfl_sync(kFull, S_incl, h >= 0 ? h : 0);
+            const uint32_t base_i = h >= 0 ? S_h : 0u;                          // start of my block relative to blk_start
+            const uint32_t nclose_incl = (uint32_t)__popc(__ballot_sync(kFull, closes) & (lt | (1u << lane)));
+            const uint32_t kb_incl = warp_incl_scan(closes ? d.aux : 0u, lane); // index-key bytes of the blocks closed at or before me
+            // obuf[0] corresponds to the global offset obase
+            const unsigned long long obase = blk_start + fill - carry;
+            const uint32_t o_i = (uint32_t)(blk_start + base_i + fill_i - obase); // my entry's offset in obuf
             async_copy_wait_upto(0);
-            __syncwarp(); // the staged heads and windows are consumed
-            hpos += total;
-            e0 += cnt;
+            __syncwarp();
+            const uint8_t *hs = hst + ((uintptr_t)(heads + hpos) & 15);
+            // ---- restart points ---------------------------------------------------------------------------------------------------------
+            const uint32_t after = hm & ~(lt | (1u << lane));
+            const int nh = after ? __ffs((int)after) - 1 : -1;                   // the head that closes my block inside this batch
+            const uint32_t T_mine = __shfl_sync(kFull, T, nh >= 0 ? nh : 0);    // my block's entry bytes, when it closes here
+            const bool is_restart = mine && (n_i % RI == 0);
+            const uint32_t r_i = n_i / RI;
+            if (is_restart) {
+                if (nh >= 0) { // the restart array of my block is assembled in this batch
+                    const uint32_t ro = (uint32_t)(blk_start + base_i - obase) + T_mine + 4 * r_i;
+                    obuf[ro] = (uint8_t)fill_i; obuf[ro + 1] = (uint8_t)(fill_i >> 8); obuf[ro + 2] = (uint8_t)(fill_i >> 16); obuf[ro + 3] = (uint8_t)(fill_i >> 24);
+                } else rst[r_i] = fill_i;
+            }
+            if (mine) P.out_rec_off[rec_idx + lane] = fill_i;
+            // ---- copy: one thread per entry ---------------------------------------------------------------------------------------------
+            if (mine) {
+                uint32_t so = ss_incl - sb;
+                if (fl & DF_NEWBLOCK) so += d.aux;
+                const uint8_t *ntsb = hs + so;
+                if (fl & DF_REWRITE) so += 4;
+                uint8_t *dst = obuf + o_i;
+#pragma unroll 1
+                for (uint32_t x = 0; x < hl; x++) dst[x] = hs[so + x];
+                const RunDev &r = P.runs[(uint32_t)(d.loc >> 40) & 15u];
+                thread_copy_g2s(obuf, o_i + hl, r.data + (d.loc & ((1ull << 40) - 1)), vl, r.data);
+                if ((fl & DF_REWRITE) && vl >= 4) { dst[hl] = ntsb[0]; dst[hl + 1] = ntsb[1]; dst[hl + 2] = ntsb[2]; dst[hl + 3] = ntsb[3]; }
+            }
+            __syncwarp();
+            // ---- the heads finish the blocks that end in front of them --------------------------------------------------------------
+            {
+                const uint32_t first_close = __ffs((int)__ballot_sync(kFull, closes)) - 1; // lane of the first closing head (or ~0)
+                // the carried block's earlier restart offsets (from previous batches) go in front of this batch's
+                const bool carried_closes = open && first_close < 32;
+                if (carried_closes) {
+                    const uint32_t Tc = __shfl_sync(kFull, T, (int)first_close), NNc = __shfl_sync(kFull, NN, (int)first_close);
+                    const uint32_t have_r = (blk_n + RI - 1) / RI; // restart points recorded before this batch
+                    const uint32_t ro = (uint32_t)(blk_start - obase) + Tc;
+                    for (uint32_t i = lane; i < 4 * have_r; i += 32) obuf[ro + i] = (uint8_t)(rst[i >> 2] >> (8 * (i & 3)));
+                    (void)NNc;
+                }
+                if (closes) {
+                    const uint32_t bstart = (uint32_t)(blk_start - obase) + (S_incl - asz_c); // obuf offset of the block I close
+                    uint32_t p = bstart + T + 4 * nrest_c;
+                    obuf[p] = (uint8_t)nrest_c; obuf[p + 1] = (uint8_t)(nrest_c >> 8); obuf[p + 2] = (uint8_t)(nrest_c >> 16); obuf[p + 3] = (uint8_t)(nrest_c >> 24);
+                    for (p += 4; p < bstart + asz_c; p++) obuf[p] = 0;
+                    const uint32_t bi = blk_idx + nclose_incl - 1, ko = keyb + kb_incl - d.aux;
+                    P.out_blk_off[bi] = blk_start + (S_incl - asz_c);
+                    P.out_blk_size[bi] = size_c;
+                    P.out_blk_rec[bi] = ph >= 0 ? rec_idx + (uint32_t)ph : blk_rec0;
+                    P.out_ikey_off[bi] = ko;
+                    const uint8_t *key = hs + (ss_incl - sb); // the closed block's last user key travels in front of my head
+#pragma unroll 1
+                    for (uint32_t x = 0; x < d.aux; x++) P.out_ikeys[ko + x] = key[x];
+                }
+            }
+            // ---- carry the state over, flush ------------------------------------------------------------------------------------------------
+            const uint32_t lastl = cnt - 1;
+            const uint32_t l_base = __shfl_sync(kFull, base_i, (int)lastl), l_fill = __shfl_sync(kFull, fill_i + sz, (int)lastl);
+            const uint32_t l_n = __shfl_sync(kFull, n_i, (int)lastl) + 1;
+            const int l_h = __shfl_sync(kFull, h, (int)lastl);
+            const uint32_t n_closed = (uint32_t)__popc(__ballot_sync(kFull, closes));
+            const uint32_t kb_total = __shfl_sync(kFull, kb_incl, 31);
+            if (l_h >= 0) blk_rec0 = rec_idx + (uint32_t)l_h;
+            blk_start += l_base; fill = l_fill; blk_n = l_n; open = true;
+            blk_idx += n_closed; keyb += kb_total; rec_idx += cnt; hpos += total_s; e0 += cnt;
+            const unsigned long long wpos = blk_start + fill;
+            const uint32_t used = (uint32_t)(wpos - obase), whole = used & ~15u;
+            flush(obase, whole);
+            carry = used - whole;
+            const uint8_t cv = lane < carry ? obuf[whole + lane] : (uint8_t)0; // the partial chunk moves to the front
+            __syncwarp();
+            if (lane < carry) obuf[lane] = cv;
+            __syncwarp();
         }
-        if (!err && open) close_block(heads + A.head_bytes - A.last_klen, A.last_klen);
+        if (!err && open) { // the segment's last block
+            const unsigned long long obase = blk_start + fill - carry;
+            close_open(heads + A.head_bytes - A.last_klen, A.last_klen, obuf + carry, (blk_n + RI - 1) / RI);
+            flush(obase, (uint32_t)(blk_start - obase));
+            carry = 0;
+        }
         if (!err && (blk_start != B.bytes + A.out_bytes || blk_idx != B.blocks + A.n_blocks || keyb != B.keyb + A.keyb)) err = PGS_CORRUPTION; // the two passes disagree
         if (err && lane == 0) { atomicMax(&P.stats->error, err); atomicMin(&P.stats->error_seg, q); }
     }

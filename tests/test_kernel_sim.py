@@ -178,6 +178,28 @@ def test_sim_ragged_records(pgs, oracle, sim):
             check(pgs, oracle, sim, runs, bottommost=bm, restart_interval=ri, block_size=bs, seg_weight=8 * 1024, default_ttl=50)
 
 
+def test_sim_long_restart_arrays_and_near_buffer_values(pgs, oracle, sim):
+    """restart interval 1 with tiny entries: a 4 KB block holds ~270 entries and spans many emit batches, so its restart
+    array is carried across batches; values just below / above the emit block buffer switch between the batch and the
+    in-place path right after such a block."""
+    rng = np.random.default_rng(5)
+    def mk(seq0, n, big_every):
+        recs = []
+        for i in range(n):
+            key = b"k%05d" % (i * 3 + seq0 % 3)
+            seq0 += 1
+            if big_every and i % big_every == big_every - 1:
+                vl = int(rng.choice([4050, 4090, 4100, 4130, 4200, 8000]))
+            else:
+                vl = 4
+            recs.append((key, seq0, 1, bytes(rng.integers(0, 256, vl, dtype=np.uint8))))
+        return seq0, pgs.Records.from_list(sorted(recs, key=lambda r: (r[0], -r[1])))
+    seq, a = mk(0, 2000, 0)
+    seq, b = mk(seq, 1500, 301)
+    for ri in (1, 2, 16):
+        check(pgs, oracle, sim, [b, a], bottommost=True, restart_interval=ri, block_size=4096, seg_weight=64 * 1024)
+
+
 def test_sim_single_run_and_empty_output(pgs, oracle, sim):
     runs = synth.compaction_runs(k=1, n_per_run=500, seed=3)
     check(pgs, oracle, sim, runs, bottommost=True, seg_weight=16 * 1024)

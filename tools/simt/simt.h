@@ -35,6 +35,7 @@ struct Cta {
     uint32_t nthreads = 0, live = 0, bid = 0, grid = 0;
     std::vector<Fiber> fibers;
     std::vector<uint64_t> xchg;                       // one exchange slot per thread
+    std::vector<uint32_t> site;                       // source line of the collective each thread is in (divergence check)
     std::map<uint64_t, Barrier> warp_bars;            // (warp << 32 | mask) -> barrier
     std::map<uint32_t, Barrier> named_bars;           // bar.sync id
     Barrier cta_bar;
@@ -82,13 +83,22 @@ inline void sync_mask(uint32_t mask)
 }
 
 // deposit a value, wait for the group, read any lane's value, wait again (nobody overwrites a slot that is still being read)
+inline uint32_t &cur_site() { static uint32_t s = 0; return s; } // set by the collective macros right before the call
 template <class F>
 inline uint64_t exchange(uint32_t mask, uint64_t mine, F pick)
 {
     Cta *c = cta();
-    const uint32_t base = tid_() & ~31u;
+    const uint32_t base = tid_() & ~31u, line = cur_site();
     c->xchg[tid_()] = mine;
+    c->site[tid_()] = line;
     sync_mask(mask);
+    // every lane named by the mask must be inside the SAME collective: a mismatch is a control-flow divergence around a
+    // full-mask collective, which on the GPU is undefined behaviour (hang or garbage)
+    for (uint32_t l = 0; l < 32; l++)
+        if ((mask >> l & 1) && c->site[base + l] != line) {
+            fprintf(stderr, "simt: divergent collective: lane %u is at source line %u, lane %u at line %u (mask %08x)\n", lane_(), line, l, c->site[base + l], mask);
+            abort();
+        }
     uint64_t r = pick(&c->xchg[base]);
     sync_mask(mask);
     return r;
@@ -100,6 +110,7 @@ inline void run_cta(Cta &c, std::function<void()> &fn, size_t stack_bytes)
     body() = &fn;
     c.fibers.resize(c.nthreads);
     c.xchg.assign(c.nthreads, 0);
+    c.site.assign(c.nthreads, 0);
     c.live = c.nthreads;
     for (uint32_t t = 0; t < c.nthreads; t++) {
         Fiber &f = c.fibers[t];
@@ -285,3 +296,12 @@ inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return
 #define PGS_SMEM_DYN(name) uint8_t *name = simt::cta()->dyn
 #define PGS_SMEM_STATIC(decl) static decl
 #define PGS_LAUNCH(kernel, grid, block, dyn, stream, ...) simt::launch(kernel, (uint32_t)(grid), (uint32_t)(block), (size_t)(dyn), __VA_ARGS__)
+
+// the collectives record their source line (see simt::exchange)
+#define __shfl_sync(...) (simt::cur_site() = __LINE__, __shfl_sync(__VA_ARGS__))
+#define __shfl_up_sync(...) (simt::cur_site() = __LINE__, __shfl_up_sync(__VA_ARGS__))
+#define __shfl_down_sync(...) (simt::cur_site() = __LINE__, __shfl_down_sync(__VA_ARGS__))
+#define __shfl_xor_sync(...) (simt::cur_site() = __LINE__, __shfl_xor_sync(__VA_ARGS__))
+#define __ballot_sync(...) (simt::cur_site() = __LINE__, __ballot_sync(__VA_ARGS__))
+#define __any_sync(...) (simt::cur_site() = __LINE__, __any_sync(__VA_ARGS__))
+#define __all_sync(...) (simt::cur_site() = __LINE__, __all_sync(__VA_ARGS__))
