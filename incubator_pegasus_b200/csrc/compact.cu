@@ -14,13 +14,24 @@ const uint64_t *crc64_table();
 static uint64_t *g_crc_dev[16] = {nullptr};
 static std::mutex g_crc_mu;
 // the opt-in shared-memory maximum of the compaction kernels, once per device (a per-call cudaFuncSetAttribute would race)
+typedef void (*walk_kernel_t)(const MergeParams);
+static walk_kernel_t walk_kernel(uint32_t G)
+{
+    switch (G) {
+    case 1: return k_walk<1>;
+    case 2: return k_walk<2>;
+    case 4: return k_walk<4>;
+    case 8: return k_walk<8>;
+    default: return k_walk<16>;
+    }
+}
 int32_t compact_init_kernels(int max_smem)
 {
     cudaFuncAttributes a;
-    PGS_CUDA(cudaFuncGetAttributes(&a, k_walk<8>));
-    PGS_CUDA(cudaFuncSetAttribute(k_walk<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - (int)a.sharedSizeBytes));
-    PGS_CUDA(cudaFuncGetAttributes(&a, k_walk<16>));
-    PGS_CUDA(cudaFuncSetAttribute(k_walk<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - (int)a.sharedSizeBytes));
+    for (uint32_t G = 1; G <= 16; G *= 2) {
+        PGS_CUDA(cudaFuncGetAttributes(&a, walk_kernel(G)));
+        PGS_CUDA(cudaFuncSetAttribute(walk_kernel(G), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - (int)a.sharedSizeBytes));
+    }
     PGS_CUDA(cudaFuncGetAttributes(&a, k_emit));
     PGS_CUDA(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - (int)a.sharedSizeBytes));
     return PGS_OK;
@@ -103,7 +114,9 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
         }
     }
     CompactGeometry geo{};
-    if (!compact_geometry(P, T, (uint32_t)e->max_smem_optin - 1024, geo)) {
+    uint32_t force_G = 0; // diagnostics: PGS_WALK_G = lanes per merge group (1, 2, 4, 8, 16)
+    if (const char *ev = getenv("PGS_WALK_G")) { const int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) force_G = (uint32_t)v; }
+    if (!compact_geometry(P, T, (uint32_t)e->max_smem_optin - 1024, geo, force_G)) {
         set_error("compact: input too large for one merge launch (keys of %u bytes, %llu records)", T.max_ukey, (unsigned long long)T.n_rec);
         return PGS_NOT_SUPPORTED;
     }
@@ -188,7 +201,7 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
 
     cudaEvent_t ev[4];
     for (auto &x : ev) CK(cudaEventCreate(&x));
-    auto walk = geo.G == 8 ? k_walk<8> : k_walk<16>;
+    walk_kernel_t walk = walk_kernel(geo.G);
     int occ_w = 0, occ_e = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, walk, (int)kWalkThreads, (size_t)geo.walk_dyn));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_emit, (int)(geo.emit_warps * 32), (size_t)geo.emit_dyn));

@@ -59,8 +59,8 @@ struct __align__(16) SegBase { // exclusive prefixes over the segments (k_seg_sc
     uint32_t blocks, recs, keyb, pad;
 };
 
-// counters of one compaction.  k_walk keeps them in lane-distributed registers (lane L of a group counts event L, sums byte
-// sum L, tracks maximum L) and adds them here once per group.
+// counters of one compaction.  k_walk keeps them in registers per group, adds them up per CTA in shared memory and adds the
+// CTA's totals here.
 struct MergeStats {
     unsigned long long cnt[16];  // EV_*
     unsigned long long bytes[4]; // SB_*
@@ -123,16 +123,28 @@ struct CompactGeometry {
     uint64_t blk_cap, out_cap, ikey_cap;
 };
 // fills the derived fields of P (P.k, P.block_size, P.restart_interval must be set); false = not supported
-inline bool compact_geometry(MergeParams &P, const CompactTotals &T, uint32_t max_smem, CompactGeometry &geo)
+constexpr uint32_t kWalkMinG = 1; // default lanes per merge group (see group.cuh)
+inline uint32_t walk_fixed_smem();
+inline bool compact_geometry(MergeParams &P, const CompactTotals &T, uint32_t max_smem, CompactGeometry &geo, uint32_t force_G = 0)
 {
     const uint32_t k = P.k;
     P.total_blocks = (uint32_t)T.total_blocks;
     P.KS = T.max_ukey < 4 ? 4u : ((T.max_ukey + 3) & ~3u);
     P.KSW = (P.KS + 8) / 4 + 1;
-    geo.G = k <= 8 ? 8 : 16;
-    P.group_smem = (uint32_t)((k * sizeof(CurState) + (size_t)(k + 4) * P.KSW * 4 + 15) & ~(size_t)15);
-    geo.walk_dyn = 2048 + kMaxRuns * (uint32_t)sizeof(RunDev) + (kWalkThreads / geo.G) * P.group_smem;
-    if (geo.walk_dyn > max_smem) return false;
+    // one group's shared memory: cursor states + key rows; an odd number of words, so that the groups of a warp start in
+    // different banks
+    P.group_smem = (uint32_t)(k * sizeof(CurState) + (size_t)(k + 4) * P.KSW * 4);
+    if ((P.group_smem / 4) % 2 == 0) P.group_smem += 4;
+    // lanes per group: the narrowest shape whose CTA fits shared memory twice per SM (or once); force_G overrides (diagnostics)
+    geo.G = 0;
+    for (uint32_t G = force_G ? force_G : kWalkMinG; G <= 16 && !geo.G; G *= 2) {
+        const uint64_t dyn = walk_fixed_smem() + (uint64_t)(kWalkThreads / G) * P.group_smem;
+        if (dyn <= max_smem / 2 || (force_G && dyn <= max_smem)) geo.G = G;
+    }
+    for (uint32_t G = kWalkMinG; G <= 16 && !geo.G; G *= 2)
+        if (walk_fixed_smem() + (uint64_t)(kWalkThreads / G) * P.group_smem <= max_smem) geo.G = G;
+    if (!geo.G) return false;
+    geo.walk_dyn = walk_fixed_smem() + (kWalkThreads / geo.G) * P.group_smem;
     const uint32_t hs = (2 * P.KS + 64 + 15) & ~15u;
     P.head_stage = hs < 2048 ? 2048u : hs;
     // k_emit per warp: an output assembly buffer (at least one block, normally 8 KB = a batch of ~28 entries), the head stage,
@@ -454,18 +466,51 @@ PGS_DEV bool head_before(const Grp<G> &g, bool en, const CurState *cs, const uin
     return a < b;
 }
 
+// Group-uniform running statistics of a group (every lane computes the same values); flushed into the CTA's totals (shared
+// memory) and from there into MergeStats.
+struct WalkAcc {
+    uint32_t e0, e1, e2;  // event counters, 8 bits each: EV_ 0..3, 4..7, 8..11
+    uint32_t n;           // records since the last flush of e0..e2 (at most 255)
+    unsigned long long b_in, b_key, b_val;
+    uint32_t m_ukey, m_vlen, m_bsize, m_brec;
+    unsigned long long m_seq, m_seq_inv;
+};
+struct WalkCtaStats { // per CTA, shared memory
+    uint32_t cnt[12];
+    unsigned long long bytes[4];
+    unsigned long long mx[6];
+};
+PGS_DEV uint32_t spread4(uint32_t x) { return (x * 0x00204081u) & 0x01010101u; } // bits 0..3 -> the low bit of bytes 0..3
+PGS_DEV void acc_flush_events(WalkAcc &acc, WalkCtaStats *cta, bool lane0)
+{
+    if (lane0) {
+#pragma unroll
+        for (uint32_t i = 0; i < 12; i++) {
+            const uint32_t v = ((i < 4 ? acc.e0 : i < 8 ? acc.e1 : acc.e2) >> (8 * (i & 3))) & 0xffu;
+            if (v) atomicAdd(&cta->cnt[i], v);
+        }
+    }
+    acc.e0 = acc.e1 = acc.e2 = 0; acc.n = 0;
+}
+
+// the merge order of a group's cursors: run indices as 4-bit fields, position 0 = the smallest head
+PGS_DEV uint32_t ord_at(unsigned long long o, uint32_t i) { return (uint32_t)(o >> (4 * i)) & 15u; }
+PGS_DEV unsigned long long ord_insert(unsigned long long o, uint32_t pos, uint32_t run)
+{
+    const unsigned long long low = (1ull << (4 * pos)) - 1ull;
+    return (o & low) | ((unsigned long long)run << (4 * pos)) | ((o & ~low) << 4);
+}
+PGS_DEV unsigned long long ord_head_to(unsigned long long o, uint32_t pos) // the head moves behind the entries 1..pos
+{
+    const unsigned long long low = (1ull << (4 * pos)) - 1ull, c = o & 15ull, rest = o >> 4;
+    return (rest & low) | (c << (4 * pos)) | ((rest & ~low) << 4);
+}
+
 // One segment per group, all groups of the warp in lock step (see group.cuh): every statement outside an `if (en...)` body is
 // executed by all 32 lanes; `act` marks the groups that still have records.
-// lane-distributed statistics of a group (see MergeStats)
-struct WalkAcc {
-    uint32_t c0, c1;        // event counts: lane L counts event L (c0) and event 8 + L (c1)
-    unsigned long long b;   // byte sums: lane L < 4 sums SB_* L
-    unsigned long long m;   // maxima: lane L < 6 tracks SM_* L
-};
-
 template <uint32_t G>
 PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G> &g, bool seg_en, uint32_t q, CurState *cs, uint32_t *rows,
-                          const unsigned long long *crc, WalkAcc &acc)
+                          const unsigned long long *crc, WalkAcc &acc, WalkCtaStats *cta)
 {
     const uint32_t k = P.k, KS = P.KS, KSW = P.KSW, RI = P.restart_interval, BS = P.block_size;
     uint32_t *rowA = rows + k * KSW, *rowB = rowA + KSW, *rowLO = rowB + KSW, *rowHI = rowLO + KSW;
@@ -492,7 +537,8 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
     g.sync();
 
     // ---- open one cursor per run, skip what belongs to the previous segment ---------------------------------------------
-    uint32_t live = 0, my_run = 0; // lanes 0..live-1 of a group hold its runs in merge order
+    uint32_t live = 0;
+    unsigned long long order = 0; // entries 0..live-1: the group's runs in merge order
     uint32_t dpos = 0;
     bool by_byte = false;
 #pragma unroll 1
@@ -524,17 +570,11 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         bool searching = ins;
 #pragma unroll 1
         for (uint32_t i = 0; g.any(searching && i < live); i++) {
-            const uint32_t r = g.shfl(my_run, i);
             const bool e = searching && i < live;
-            const bool bf = head_before(g, e, cs, rows, KSW, j, r & 15u, dpos, by_byte);
+            const bool bf = head_before(g, e, cs, rows, KSW, j, ord_at(order, i), dpos, by_byte);
             if (e && bf) { pos = i; searching = false; }
         }
-        const uint32_t up = g.shfl_up(my_run, 1);
-        if (ins) {
-            if (g.gl > pos && g.gl <= live) my_run = up;
-            if (g.gl == pos) my_run = j;
-            live++;
-        }
+        if (ins) { order = ord_insert(order, pos, j); live++; }
     }
 
     // ---- the merge loop --------------------------------------------------------------------------------------------------
@@ -546,7 +586,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
     uint32_t n_blocks = 0, keyb = 0, lenA = 0;
     unsigned long long out_bytes = 0;
     bool have_head = false, head_in_A = false, prev_big = false;
-    uint32_t head_len = 0;
+    uint32_t head_len = 0, last_run = 0xffu;
     uint32_t d1 = 0, prev_pl = 0xFFFFFFFFu;
     bool d1_valid = false;
     auto close_block = [&]() { // bookkeeping of a finished block (k_emit derives the same numbers)
@@ -554,24 +594,31 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         out_bytes += (size + kBlockAlign - 1) & ~(unsigned long long)(kBlockAlign - 1);
         n_blocks++;
         keyb += lenA;
-        const unsigned long long mv = g.gl == SM_BLK_SIZE ? size : (g.gl == SM_BLK_REC ? blk_n : 0u);
-        if (mv > acc.m && (g.gl == SM_BLK_SIZE || g.gl == SM_BLK_REC)) acc.m = mv;
+        if (size > acc.m_bsize) acc.m_bsize = size;
+        if (blk_n > acc.m_brec) acc.m_brec = blk_n;
     };
 #pragma unroll 1
     for (;;) {
         const bool act = seg_en && live > 0 && !err;
         if (!g.any(act)) break;
-        const uint32_t c = g.shfl(my_run, 0) & 15u;
+        const uint32_t c = (uint32_t)order & 15u;
         CurState *C = &cs[c];
         uint32_t *row = rows + c * KSW;
         uint32_t ulen = 0, vlen = 0, type = 0, tr_lo = 0, tr_hi = 0;
         if (act) { ulen = C->klen - 8; vlen = C->vlen; tr_lo = C->tr_lo; tr_hi = C->tr_hi; type = tr_lo & 0xffu; }
         uint32_t ev = act ? 1u << EV_IN : 0u; // what happened to this record, one bit per counter
-        // (1) an older version of the user key that was just handled?
-        uint32_t lcp_head = 0;
+        // (1) an older version of the user key that was just handled?  The record before this one carried the head's user key;
+        // when it came from the same run, the entry's `shared` field is a known common prefix (all of the key: no compare).
+        uint32_t lcp_head = 0, from = 0;
         const bool cmp1 = act && have_head;
-        const int c1 = row_cmp(g, cmp1, row, ulen, head_in_A ? rowA : rowB, head_len, lcp_head);
-        const bool shadow = cmp1 && c1 == 0;
+        if (cmp1 && last_run == c) { from = C->shared < ulen ? C->shared : ulen; if (from > head_len) from = head_len; }
+        bool shadow = cmp1 && from == ulen && ulen == head_len;
+        const bool cmp1b = cmp1 && !shadow;
+        if (g.any(cmp1b)) {
+            const int c1 = row_cmp(g, cmp1b, row, ulen, head_in_A ? rowA : rowB, head_len, lcp_head, from);
+            if (cmp1b && c1 == 0) shadow = true;
+        }
+        if (shadow) lcp_head = ulen;
         // (2) newest version of a user key: CompactionIterator rules + KeyWithTTLCompactionFilter::Filter
         bool keep = false, tomb = false, rewrite = false;
         uint32_t nts = 0, vlen_out = vlen;
@@ -605,12 +652,18 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
             const bool lcp_known = keep && (cmp2 || (have_head && head_in_A));
             const uint32_t lcp_out = cmp2 ? shared : lcp_head;
             const unsigned long long hk = bloom_hash_row(g, row, keep ? ulen : 0u);
-            if (keep && g.gl < 6) bloom_add_bit(P.out_bloom, P.out_bloom_lines, hk, g.gl);
+            if (keep) {
+#pragma unroll
+                for (uint32_t i = g.gl; i < 6; i += G) bloom_add_bit(P.out_bloom, P.out_bloom_lines, hk, i);
+            }
             const uint32_t pl = keep ? hashkey_prefix_len((const uint8_t *)row, ulen) : 0u;
             const bool new_prefix = keep && pl && !(lcp_known && pl == prev_pl && lcp_out >= pl);
             if (g.any(new_prefix)) {
                 const unsigned long long hp = bloom_hash_row(g, row, new_prefix ? pl : 0u);
-                if (new_prefix && g.gl < 6) bloom_add_bit(P.out_bloom, P.out_bloom_lines, hp, g.gl);
+                if (new_prefix) {
+#pragma unroll
+                    for (uint32_t i = g.gl; i < 6; i += G) bloom_add_bit(P.out_bloom, P.out_bloom_lines, hp, i);
+                }
             }
             if (keep) { prev_pl = pl; ev |= 1u << EV_BLOOM_KEY; if (new_prefix) ev |= 1u << EV_BLOOM_PREFIX; }
         }
@@ -646,16 +699,19 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
             if (big) flags |= DF_BIG;
             if (rewrite) {
                 flags |= DF_REWRITE;
-                if (g.gl < 4) heads[hpos + g.gl] = (uint8_t)(nts >> (8 * (3 - g.gl))); // BE32
+#pragma unroll
+                for (uint32_t i = g.gl; i < 4; i += G) heads[hpos + i] = (uint8_t)(nts >> (8 * (3 - i))); // BE32
                 hpos += 4;
             }
             // the entry head: varints | key delta | trailer
             uint8_t *hp = heads + hpos;
             if (hv) {
-                if (g.gl < hv) hp[g.gl] = (uint8_t)__byte_perm(hv_lo, hv_hi, g.gl);
+#pragma unroll 1
+                for (uint32_t i = g.gl; i < hv; i += G) hp[i] = (uint8_t)__byte_perm(hv_lo, hv_hi, i);
 #pragma unroll 1
                 for (uint32_t i = g.gl; i < kd; i += G) hp[hv + i] = ((const uint8_t *)row)[shared + i];
-                if (g.gl < 8) hp[hv + kd + g.gl] = (uint8_t)__byte_perm(otr_lo, otr_hi, g.gl);
+#pragma unroll
+                for (uint32_t i = g.gl; i < 8; i += G) hp[hv + kd + i] = (uint8_t)__byte_perm(otr_lo, otr_hi, i);
             } else if (g.gl == 0) {
                 emit_head_slow(hp, shared, kd, vlen_out, (const uint8_t *)row, otr_lo, otr_hi);
             }
@@ -663,7 +719,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
             hpos += hl;
             if (g.gl == 0) {
                 Desc d;
-                d.loc = (C->base + C->voff) | ((unsigned long long)c << 40) | ((unsigned long long)hl << 44) | ((unsigned long long)flags << 60);
+                d.loc = (cur_base(C) + C->voff) | ((unsigned long long)c << 40) | ((unsigned long long)hl << 44) | ((unsigned long long)flags << 60);
                 d.vlen = vlen_out;
                 d.aux = aux;
                 *reinterpret_cast<uint4 *>(&desc[n_out]) = *reinterpret_cast<const uint4 *>(&d);
@@ -676,18 +732,21 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
             prev_big = big;
             ev |= 1u << EV_OUT;
             if (otype == PGS_TYPE_DELETION) ev |= 1u << EV_OUT_TOMB;
-            // maxima: lane L tracks SM_* L (sequence numbers are 56 bits)
+            // maxima and byte sums of the output (sequence numbers are 56 bits)
             const unsigned long long seq = ((unsigned long long)otr_hi << 24) | (otr_lo >> 8);
-            const unsigned long long mv = g.gl == SM_UKEY ? ulen : g.gl == SM_VLEN ? vlen_out : g.gl == SM_MAX_SEQ ? seq : ~seq;
-            if (g.gl <= SM_MIN_SEQ_INV && mv > acc.m) acc.m = mv;
+            if (ulen > acc.m_ukey) acc.m_ukey = ulen;
+            if (vlen_out > acc.m_vlen) acc.m_vlen = vlen_out;
+            if (seq > acc.m_seq) acc.m_seq = seq;
+            if (~seq > acc.m_seq_inv) acc.m_seq_inv = ~seq;
+            acc.b_key += ulen;
+            acc.b_val += vlen_out;
         }
-        // counters: lane L adds event L / byte sum L
-        acc.c0 += (ev >> g.gl) & 1u;
-        if (G == 8) acc.c1 += (ev >> (8 + g.gl)) & 1u;
-        {
-            const uint32_t in_b = act ? ulen + vlen : 0u, out_k = keep ? ulen : 0u, out_v = keep ? vlen_out : 0u;
-            acc.b += g.gl == SB_IN ? in_b : g.gl == SB_OUT ? out_k + out_v : g.gl == SB_OUT_KEY ? out_k : g.gl == SB_OUT_VAL ? out_v : 0u;
-        }
+        // counters
+        if (act) acc.b_in += ulen + vlen;
+        acc.e0 += spread4(ev & 15u);
+        acc.e1 += spread4((ev >> 4) & 15u);
+        acc.e2 += spread4((ev >> 8) & 15u);
+        if (++acc.n == 255) acc_flush_events(acc, cta, g.gl == 0);
         g.sync(); // every lane has read the previous survivor's key
         if (act && !shadow) {
             uint32_t *dst = keep ? rowA : rowB;
@@ -698,6 +757,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
             have_head = true;
             head_len = ulen;
         }
+        last_run = c;
         g.sync();
         // (4) advance the cursor and restore the merge order
         const uint32_t e3 = cur_next(g, act && !err, runs[c], C, row, KS);
@@ -713,22 +773,20 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         const bool reorder = searching;
 #pragma unroll 1
         for (uint32_t i = 1; g.any(searching && i < live); i++) {
-            const uint32_t r = g.shfl(my_run, i) & 15u;
             const bool e = searching && i < live;
-            const bool bf = head_before(g, e, cs, rows, KSW, c, r, dpos, by_byte);
+            const bool bf = head_before(g, e, cs, rows, KSW, c, ord_at(order, i), dpos, by_byte);
             if (e) {
                 if (bf) { if (i == 1) { d1_valid = by_byte; d1 = dpos; } searching = false; }
                 else pos = i;
             }
         }
-        const uint32_t dn = g.shfl_down(my_run, 1);
         if (adv && !alive) { // drop the exhausted run
-            if (g.gl + 1 < live) my_run = dn;
+            order >>= 4;
             live--;
             d1_valid = false;
+            last_run = 0xffu;
         } else if (reorder && pos > 0) {
-            if (g.gl < pos) my_run = dn;
-            if (g.gl == pos) my_run = c;
+            order = ord_head_to(order, pos);
         }
     }
     if (seg_en) {
@@ -751,6 +809,9 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
     g.sync();
 }
 
+constexpr uint32_t kWalkFixedSmem = 2048 + kMaxRuns * (uint32_t)sizeof(RunDev) + (uint32_t)sizeof(WalkCtaStats);
+inline uint32_t walk_fixed_smem() { return kWalkFixedSmem; }
+
 template <uint32_t G>
 __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ MergeParams P)
 {
@@ -759,18 +820,23 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ M
     constexpr uint32_t NGW = 32 / G; // groups per warp
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // CTA-wide shared memory: crc table (2 KB, only filled when the stale-split check is on), the run table (the groups of a
-    // warp work on different runs at the same time: a per-lane index into kernel parameters would serialise)
+    // warp work on different runs at the same time: a per-lane index into kernel parameters would serialise), the CTA's totals
     unsigned long long *crc = (unsigned long long *)dyn;
     RunDev *runs = (RunDev *)(dyn + 2048);
+    WalkCtaStats *cta = (WalkCtaStats *)(dyn + 2048 + kMaxRuns * sizeof(RunDev));
     if (P.validate_hash)
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) crc[i] = P.crc_table[i];
     for (uint32_t i = threadIdx.x; i < kMaxRuns; i += blockDim.x) runs[i] = P.runs[i < P.k ? i : 0];
+    for (uint32_t i = threadIdx.x; i < sizeof(WalkCtaStats) / 4; i += blockDim.x) ((uint32_t *)cta)[i] = 0;
     __syncthreads();
-    uint8_t *gs = dyn + 2048 + kMaxRuns * sizeof(RunDev) + (size_t)(warp * NGW + g.shift / G) * P.group_smem;
+    uint8_t *gs = dyn + kWalkFixedSmem + (size_t)(warp * NGW + g.shift / G) * P.group_smem;
     CurState *cs = (CurState *)gs;
     uint32_t *rows = (uint32_t *)(gs + (size_t)P.k * sizeof(CurState));
     WalkAcc acc;
-    acc.c0 = acc.c1 = 0; acc.b = 0; acc.m = 0;
+    acc.e0 = acc.e1 = acc.e2 = acc.n = 0;
+    acc.b_in = acc.b_key = acc.b_val = 0;
+    acc.m_ukey = acc.m_vlen = acc.m_bsize = acc.m_brec = 0;
+    acc.m_seq = acc.m_seq_inv = 0;
 #pragma unroll 1
     for (;;) {
         uint32_t t0 = 0;
@@ -778,13 +844,27 @@ __global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ M
         t0 = __shfl_sync(kFull, t0, 0);
         if (t0 >= P.Q) break;
         const uint32_t q = t0 + g.shift / G;
-        walk_segment<G>(P, runs, g, q < P.Q, q < P.Q ? q : 0u, cs, rows, crc, acc);
+        walk_segment<G>(P, runs, g, q < P.Q, q < P.Q ? q : 0u, cs, rows, crc, acc, cta);
     }
-    // statistics: lane L of a group holds event count L (and 8 + L), byte sum L, maximum L
-    if (g.gl < 16 && acc.c0) atomicAdd(&P.stats->cnt[g.gl], (unsigned long long)acc.c0);
-    if (G == 8 && acc.c1) atomicAdd(&P.stats->cnt[8 + g.gl], (unsigned long long)acc.c1);
-    if (g.gl < 4 && acc.b) atomicAdd(&P.stats->bytes[g.gl], acc.b);
-    if (g.gl < 6 && acc.m) atomicMax(&P.stats->mx[g.gl], acc.m);
+    // statistics: group -> CTA (shared-memory atomics) -> MergeStats
+    acc_flush_events(acc, cta, g.gl == 0);
+    if (g.gl == 0) {
+        if (acc.b_in) atomicAdd(&cta->bytes[SB_IN], acc.b_in);
+        if (acc.b_key + acc.b_val) atomicAdd(&cta->bytes[SB_OUT], acc.b_key + acc.b_val);
+        if (acc.b_key) atomicAdd(&cta->bytes[SB_OUT_KEY], acc.b_key);
+        if (acc.b_val) atomicAdd(&cta->bytes[SB_OUT_VAL], acc.b_val);
+        if (acc.m_ukey) atomicMax(&cta->mx[SM_UKEY], (unsigned long long)acc.m_ukey);
+        if (acc.m_vlen) atomicMax(&cta->mx[SM_VLEN], (unsigned long long)acc.m_vlen);
+        if (acc.m_seq) atomicMax(&cta->mx[SM_MAX_SEQ], acc.m_seq);
+        if (acc.m_seq_inv) atomicMax(&cta->mx[SM_MIN_SEQ_INV], acc.m_seq_inv);
+        if (acc.m_bsize) atomicMax(&cta->mx[SM_BLK_SIZE], (unsigned long long)acc.m_bsize);
+        if (acc.m_brec) atomicMax(&cta->mx[SM_BLK_REC], (unsigned long long)acc.m_brec);
+    }
+    __syncthreads();
+    const uint32_t t = threadIdx.x;
+    if (t < 12 && cta->cnt[t]) atomicAdd(&P.stats->cnt[t], (unsigned long long)cta->cnt[t]);
+    if (t >= 32 && t < 36 && cta->bytes[t - 32]) atomicAdd(&P.stats->bytes[t - 32], cta->bytes[t - 32]);
+    if (t >= 64 && t < 70 && cta->mx[t - 64]) atomicMax(&P.stats->mx[t - 64], cta->mx[t - 64]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -872,7 +952,7 @@ PGS_DEV void store_chunk_part(uint8_t *dst16, uint4 v, uint32_t lo, uint32_t hi)
     }
 }
 // one THREAD copies n bytes from global memory (any alignment, readable in whole 16-byte chunks inside [lim_lo, ...)) to shared
-// memory at dst (any alignment): 16-byte loads and stores, byte-exact at both ends.
+// memory at dst (any alignment): 16-byte loads and stores, byte-exact at both ends.  Four loads are in flight per round trip.
 PGS_DEV void thread_copy_g2s(uint8_t *obuf16, uint32_t doff, const uint8_t *src, uint32_t n, const uint8_t *lim_lo)
 {
     if (n == 0) return;
@@ -884,14 +964,22 @@ PGS_DEV void thread_copy_g2s(uint8_t *obuf16, uint32_t doff, const uint8_t *src,
     uint4 Pc = (const uint8_t *)sp >= lim_lo ? sp[0] : zero; // only its bytes before src could lie outside the run's buffer
     const uint32_t end = doff + n;
 #pragma unroll 1
-    for (uint32_t x = x0; x < end; x += 16) {
-        sp++;
-        const uint4 Cc = a ? *sp : zero;               // (reads at most 15 bytes past the value: run buffers carry slack)
-        const uint4 o = a ? realign16(Pc, Cc, a) : Pc;
-        const uint32_t lo = x < doff ? doff - x : 0u, hi = end - x < 16 ? end - x : 16u;
-        if (lo == 0 && hi == 16) *reinterpret_cast<uint4 *>(obuf16 + x) = o;
-        else store_chunk_part(obuf16 + x, o, lo, hi);
-        Pc = a ? Cc : *sp;
+    for (uint32_t x = x0; x < end; x += 64) {
+        uint4 nx[4];                                   // (reads at most 31 bytes past the value: run buffers carry slack)
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) nx[j] = x + 16 * j < end ? sp[j + 1] : zero;
+        sp += 4;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) {
+            const uint32_t xx = x + 16 * j;
+            if (xx < end) {
+                const uint4 o = realign16(j == 0 ? Pc : nx[j - 1], nx[j], a);
+                const uint32_t lo = xx < doff ? doff - xx : 0u, hi = end - xx < 16 ? end - xx : 16u;
+                if (lo == 0 && hi == 16) *reinterpret_cast<uint4 *>(obuf16 + xx) = o;
+                else store_chunk_part(obuf16 + xx, o, lo, hi);
+            }
+        }
+        Pc = nx[3];
     }
 }
 
@@ -900,7 +988,7 @@ PGS_DEV void thread_copy_g2s(uint8_t *obuf16, uint32_t doff, const uint8_t *src,
 // warp's output buffer, the threads standing on a block boundary finish the previous block (restart array, padding, index
 // entry), and the batch's bytes leave with one bulk TMA store.  Blocks of a segment are adjacent in the output run, so a
 // batch's bytes are one contiguous range; the partial 16-byte chunk at its end is carried into the next batch.
-__global__ void __launch_bounds__(kEmitThreads) k_emit(const __grid_constant__ MergeParams P)
+__global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant__ MergeParams P)
 {
     PGS_SMEM_DYN(dyn);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -1,12 +1,14 @@
 // group.cuh — lane-group primitives shared by the compaction walker and the read kernels.
 //
-// A *group* is G consecutive lanes of a warp (G = 8, 16 or 32) that together run one sequential iterator over sorted
+// A *group* is G consecutive lanes of a warp (G = 1, 2, 4, 8, 16 or 32) that together run one sequential iterator over sorted
 // runs: group-uniform scalars (offsets, lengths, counters) are computed redundantly by every lane, the bytes of a key
 // are spread over the lanes (lane L owns the 32-bit words L, L+G, ... of a key row in shared memory) and compared with
 // one ballot.  The 32/G groups of a warp run in LOCK STEP on different data: control flow around every collective is
 // warp-uniform (loops run while any group still needs them, per-group work is switched on and off with an `en`
 // predicate), so all shuffles / ballots use the constant full mask -- a collective with a run-time lane mask costs a
 // MATCH.ANY + REDUX convergence check per call and lets the groups drift apart; measured 4x slower.
+// G = 1 is the degenerate case: one thread per iterator, no collectives at all, so its control flow may diverge freely (the
+// hardware serialises the paths); the same source serves both shapes.
 // This is the B200 shape of RocksDB's DataBlockIter / MergingIterator (v8.5.3, not in the reference tree; SURVEY.md
 // Appendix A): the per-record decode chain stays sequential, the parallelism comes from thousands of independent groups.
 #pragma once
@@ -35,6 +37,18 @@ struct Grp {
     PGS_DEV static void sync() { __syncwarp(); }
 };
 
+template <>
+struct Grp<1> { // one thread = one group: every "collective" is the identity, nothing synchronises
+    uint32_t gl, shift;
+    PGS_DEV Grp() : gl(0), shift(threadIdx.x & 31) {}
+    PGS_DEV uint32_t ballot(bool p) const { return p ? 1u : 0u; }
+    template <class T> PGS_DEV T shfl(T v, uint32_t) const { return v; }
+    template <class T> PGS_DEV T shfl_down(T v, uint32_t) const { return v; }
+    template <class T> PGS_DEV T shfl_up(T v, uint32_t) const { return v; }
+    PGS_DEV static bool any(bool p) { return p; }
+    PGS_DEV static void sync() {}
+};
+
 // 8 bytes at an arbitrary address (any address space): two aligned 64-bit loads + shift
 PGS_DEV uint64_t ld_u64_any(const uint8_t *p)
 {
@@ -47,14 +61,15 @@ PGS_DEV uint64_t ld_u64_any(const uint8_t *p)
 
 // Compare two byte strings held in key rows (4-byte aligned shared memory, readable up to the next multiple of 4).
 // Returns <0, 0, >0; dpos = index of the first differing byte, or min(la, lb) when one is a prefix of the other.
+// `from` = a number of leading bytes already known to be equal (the compare starts at the word that holds byte `from`).
 // Executed by the whole warp; groups with en = false take part in the collectives and get 0.
 template <uint32_t G>
-PGS_DEV int row_cmp(const Grp<G> &g, bool en, const uint32_t *a, uint32_t la, const uint32_t *b, uint32_t lb, uint32_t &dpos)
+PGS_DEV int row_cmp(const Grp<G> &g, bool en, const uint32_t *a, uint32_t la, const uint32_t *b, uint32_t lb, uint32_t &dpos, uint32_t from = 0)
 {
     const uint32_t m = en ? (la < lb ? la : lb) : 0u;
     int res = 2; // undecided
 #pragma unroll 1
-    for (uint32_t base = 0; g.any(res == 2 && base < m); base += 4 * G) {
+    for (uint32_t base = from & ~3u; g.any(res == 2 && base < m); base += 4 * G) {
         const uint32_t off = base + 4 * g.gl;
         uint32_t x = 0;
         if (res == 2 && off < m) {
@@ -83,9 +98,9 @@ PGS_DEV int row_cmp(const Grp<G> &g, bool en, const uint32_t *a, uint32_t la, co
 // Group-uniform state of one cursor, in shared memory.  The cursor reads entries straight from global memory: one
 // dependent round trip per entry (the header), everything else of the entry's head lies in the same or the next cache line.
 // Latency is hidden by the number of groups in flight, not by staging.
-struct CurState {
-    unsigned long long base;   // blk_off[b]
-    unsigned long long nb_off; // blk_off[b + 1], fetched asynchronously when block b was entered
+struct CurState { // 32-bit fields only: any 4-byte-aligned stride between the states of neighbouring groups works
+    uint32_t base_lo, base_hi; // blk_off[b]
+    uint32_t nb_lo, nb_hi;     // blk_off[b + 1], fetched asynchronously when block b was entered
     uint32_t nb_r0, nb_r1;     // blk_rec[b + 1], blk_rec[b + 2] (same)
     uint32_t bsize, nb_size;   // blk_size[b], blk_size[b + 1] (same)
     uint32_t b, b_end;         // current block; first block that does not belong to the cursor's range
@@ -99,19 +114,22 @@ struct CurState {
     uint32_t chk_from;         // blocks >= chk_from may hold keys above the range's upper bound
     uint32_t live;             // 0 once the cursor is exhausted
 };
-static_assert(sizeof(CurState) % 8 == 0, "CurState");
-
 PGS_DEV unsigned long long cur_trailer(const CurState *c) { return ((unsigned long long)c->tr_hi << 32) | c->tr_lo; }
+PGS_DEV unsigned long long cur_base(const CurState *c) { return ((unsigned long long)c->base_hi << 32) | c->base_lo; }
 
 // start fetching the metadata of block b + 1 (asynchronous copies into the state; consumed when the block is entered)
 template <uint32_t G>
 PGS_DEV void cur_prefetch_next(const Grp<G> &g, bool en, const RunDev &r, CurState *c, uint32_t b)
 {
     if (en && b + 1 < r.nb) { // blk_off and blk_rec have nb + 1 entries
-        if (g.gl == 0) async_copy8(&c->nb_off, r.blk_off + b + 1);
-        if (g.gl == 1) async_copy4(&c->nb_r0, r.blk_rec + b + 1);
-        if (g.gl == 2) async_copy4(&c->nb_r1, r.blk_rec + b + 2);
-        if (g.gl == 3) async_copy4(&c->nb_size, r.blk_size + b + 1);
+#pragma unroll
+        for (uint32_t i = g.gl; i < 5; i += G) {
+            if (i == 0) async_copy4(&c->nb_lo, (const uint32_t *)(r.blk_off + b + 1));
+            if (i == 1) async_copy4(&c->nb_hi, (const uint32_t *)(r.blk_off + b + 1) + 1);
+            if (i == 2) async_copy4(&c->nb_r0, r.blk_rec + b + 1);
+            if (i == 3) async_copy4(&c->nb_r1, r.blk_rec + b + 2);
+            if (i == 4) async_copy4(&c->nb_size, r.blk_size + b + 1);
+        }
     }
     async_copy_commit();
 }
@@ -194,7 +212,7 @@ PGS_DEV uint32_t cur_open(const Grp<G> &g, bool en, const RunDev &r, CurState *c
     if (some) { base = r.blk_off[b]; r0 = r.blk_rec[b]; r1 = r.blk_rec[b + 1]; bsize = r.blk_size[b]; }
     if (en && g.gl == 0) {
         c->live = some ? 1u : 0u; c->b = b; c->b_end = b_end; c->chk_from = chk_from;
-        if (some) { c->base = base; c->rem = r1 - r0; c->bsize = bsize; }
+        if (some) { c->base_lo = (uint32_t)base; c->base_hi = (uint32_t)(base >> 32); c->rem = r1 - r0; c->bsize = bsize; }
     }
     g.sync();
     cur_prefetch_next(g, some, r, c, b);
@@ -214,19 +232,19 @@ PGS_DEV uint32_t cur_next(const Grp<G> &g, bool en, const RunDev &r, CurState *c
     if (en) {
         rem = c->rem; b = c->b;
         in_block = rem > 1;
-        if (in_block) { base = c->base; p = c->p + c->elen; prev_klen = c->klen; bsize = c->bsize; }
+        if (in_block) { base = cur_base(c); p = c->p + c->elen; prev_klen = c->klen; bsize = c->bsize; }
         else if (b + 1 >= c->b_end || b + 1 >= r.nb) done = true;
         else cross = true;
     }
     async_copy_wait_all(); // the copies issued when the block was entered (long since complete)
     g.sync();              // ... and every lane has read the old state
     uint32_t r0 = 0, r1 = 0;
-    if (cross) { base = c->nb_off; r0 = c->nb_r0; r1 = c->nb_r1; bsize = c->nb_size; }
+    if (cross) { base = ((unsigned long long)c->nb_hi << 32) | c->nb_lo; r0 = c->nb_r0; r1 = c->nb_r1; bsize = c->nb_size; }
     g.sync();
     if (en && g.gl == 0) {
         if (in_block) c->rem = rem - 1;
         else if (done) { c->live = 0; c->b = b + 1; }
-        else { c->b = b + 1; c->base = base; c->rem = r1 - r0; c->bsize = bsize; }
+        else { c->b = b + 1; c->base_lo = (uint32_t)base; c->base_hi = (uint32_t)(base >> 32); c->rem = r1 - r0; c->bsize = bsize; }
     }
     g.sync();
     cur_prefetch_next(g, cross, r, c, b + 1);

@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kReadThreads) k_get(const __grid_constant__ Ge
                     res.status = PGS_OK;
                     res.value_off = (uint32_t)off;
                     res.value_len = ulen;
-                    grp_copy(g, P.arena + off, r.data + C->base + C->voff + hdr, ulen);
+                    grp_copy(g, P.arena + off, r.data + cur_base(C) + C->voff + hdr, ulen);
                 }
             }
         }
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(kReadThreads) k_scan_fwd(const __grid_constant
                             else {
                                 uint8_t *dst = arena + arena_used;
                                 for (uint32_t i = g.gl; i < klen_out; i += G) dst[i] = key[koff + i];
-                                if (vlen_out) grp_copy(g, dst + klen_out, runs[c].data + C->base + C->voff + hdr, vlen_out);
+                                if (vlen_out) grp_copy(g, dst + klen_out, runs[c].data + cur_base(C) + C->voff + hdr, vlen_out);
                                 if (g.gl == 0) {
                                     pgs_kv kv;
                                     kv.key_off = (uint32_t)arena_used; kv.key_len = klen_out;

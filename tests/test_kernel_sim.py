@@ -84,6 +84,9 @@ STAT_FIELDS = ("in_records", "out_records", "in_bytes", "out_bytes", "dropped_sh
 
 
 def check(pgs, oracle, sim, runs, *, bottommost, ops_json=None, **kw):
+    if "lanes" not in kw:  # the one-thread-per-segment shape and a lane-group shape of the same source
+        check(pgs, oracle, sim, runs, bottommost=bottommost, ops_json=ops_json, lanes=8, **kw)
+        kw["lanes"] = 1
     ops_bin = pgs.parse_ops(ops_json) if ops_json else None
     got_run, x = sim_compact(pgs, sim, runs, bottommost=bottommost, ops=ops_bin, **kw)
     okw = {k: v for k, v in kw.items() if k in ("enabled", "default_ttl", "validate_hash", "pidx", "partition_version")}
@@ -133,7 +136,7 @@ def test_sim_l0_to_l1(pgs, oracle, sim, bottommost):
     assert x["nseg"] > 8
 
 
-@pytest.mark.parametrize("lanes", [8, 16, 32])
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16])
 def test_sim_group_widths(pgs, oracle, sim, lanes):
     runs = synth.compaction_runs(k=3, n_per_run=300, seed=5)
     check(pgs, oracle, sim, runs, bottommost=True, lanes=lanes, seg_weight=16 * 1024)

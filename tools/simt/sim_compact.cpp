@@ -173,7 +173,8 @@ int32_t sim_compact(uint32_t k, const uint8_t **data, const uint64_t *data_bytes
         if (fp->ops && fp->ops_len >= 4) { memcpy(&P.n_ops, fp->ops, 4); ops.assign(fp->ops, fp->ops + fp->ops_len); ops.resize(ops.size() + 16); P.ops = ops.data(); }
     }
     CompactGeometry geo{};
-    if (!compact_geometry(P, T, 227 * 1024, geo)) return PGS_NOT_SUPPORTED;
+    if (group_lanes && group_lanes != 1 && group_lanes != 2 && group_lanes != 4 && group_lanes != 8 && group_lanes != 16) return PGS_INVALID_ARGUMENT;
+    if (!compact_geometry(P, T, 227 * 1024, geo, group_lanes)) return PGS_NOT_SUPPORTED;
     if (seg_weight) { // smaller segments: more boundaries per record in a small test
         P.tile_weight = seg_weight;
         const uint64_t W = T.in_block_bytes + T.n_rec * P.rec_cost;
@@ -191,11 +192,6 @@ int32_t sim_compact(uint32_t k, const uint8_t **data, const uint64_t *data_bytes
         P.desc_cap = Nb + 1;
         P.head_cap = Nb * per_head + (2 * (Bb + Nb * per_head) / P.block_size + 2 * Q + 2) * (uint64_t)(P.KS + 8) + 64 * Q + 64;
         (void)P2;
-    }
-    if (group_lanes) {
-        if (group_lanes < k || (group_lanes != 8 && group_lanes != 16 && group_lanes != 32)) return PGS_INVALID_ARGUMENT;
-        geo.G = group_lanes;
-        geo.walk_dyn = 2048 + kMaxRuns * (uint32_t)sizeof(RunDev) + (kWalkThreads / geo.G) * P.group_smem;
     }
     const uint64_t Q = P.Q;
     std::vector<uint32_t> split_pos((Q + 1) * k, 0xFFFFFFFFu), split_ref(Q + 1, 0xFFFFFFFFu), ticket(64, 0);
@@ -232,9 +228,11 @@ int32_t sim_compact(uint32_t k, const uint8_t **data, const uint64_t *data_bytes
     PGS_LAUNCH(k_seg_bounds, (P.Q + 255) / 256, 256, 0, 0, P);
     PGS_LAUNCH(k_seg_layout, 1, 1024, 0, 0, P);
     if (!st.error) {
-        if (geo.G == 8) PGS_LAUNCH(k_walk<8>, 2, kWalkThreads, geo.walk_dyn, 0, P);
-        else if (geo.G == 16) PGS_LAUNCH(k_walk<16>, 2, kWalkThreads, geo.walk_dyn, 0, P);
-        else PGS_LAUNCH(k_walk<32>, 2, kWalkThreads, geo.walk_dyn, 0, P);
+        if (geo.G == 1) PGS_LAUNCH(k_walk<1>, 2, kWalkThreads, geo.walk_dyn, 0, P);
+        else if (geo.G == 2) PGS_LAUNCH(k_walk<2>, 2, kWalkThreads, geo.walk_dyn, 0, P);
+        else if (geo.G == 4) PGS_LAUNCH(k_walk<4>, 2, kWalkThreads, geo.walk_dyn, 0, P);
+        else if (geo.G == 8) PGS_LAUNCH(k_walk<8>, 2, kWalkThreads, geo.walk_dyn, 0, P);
+        else PGS_LAUNCH(k_walk<16>, 2, kWalkThreads, geo.walk_dyn, 0, P);
     }
     if (getenv("PGS_SIM_DUMP")) {
         for (uint32_t q = 0; q < P.Q; q++) {
