@@ -139,6 +139,19 @@ typedef struct {
 PGS_API int32_t pgs_run_upload(pgs_partition *p, int32_t level, const uint8_t *data,
                                uint64_t data_bytes, const uint64_t *blk_off,
                                const uint32_t *blk_size, uint32_t n_blocks, uint64_t *run_id_out);
+/* Several runs in one call, in order (runs[0] is installed first).  The block bytes travel in 32 MB chunks; the device
+ * index build of a chunk overlaps the copy of the next one, and the next run's bytes are on the link before the
+ * current run's index is finished: with pinned host buffers the call takes the transfer time plus one short tail.
+ * All or nothing: on an error no run of the call stays installed. */
+typedef struct {
+    const uint8_t *data;
+    uint64_t data_bytes;
+    const uint64_t *blk_off;
+    const uint32_t *blk_size;
+    uint32_t n_blocks;
+    int32_t level;
+} pgs_run_src;
+PGS_API int32_t pgs_run_upload_many(pgs_partition *p, const pgs_run_src *runs, uint32_t n, uint64_t *run_ids_out);
 PGS_API int32_t pgs_run_drop(pgs_partition *p, uint64_t run_id);
 PGS_API int32_t pgs_run_info_get(pgs_partition *p, uint64_t run_id, pgs_run_info *out);
 /* run ids in read order (newest first: L0 by recency, then L1, L2, ...) */
@@ -448,6 +461,23 @@ PGS_API int64_t pgs_rrdb_last_committed_decree(pgs_server *s);
 /* drops scan contexts older than 5 minutes (pegasus_server_impl.cpp:1377-1385 schedules the same expiry per context);
  * also runs implicitly on every scanner call. Returns the number of contexts dropped. */
 PGS_API uint32_t pgs_rrdb_gc(pgs_server *s, uint32_t now);
+
+/* ============================================================================================
+ * 7. box-level placement: one engine per visible GPU
+ * ==========================================================================================
+ * A table is hash-partitioned and its replicas are independent (src/client/partition_resolver.cpp:48-51 picks
+ * pidx = pegasus_key_hash(key) % partition_count; src/replica/replica_stub.h hosts one storage engine per gpid).
+ * The router opens an engine on each of the first n_devices GPUs (0 = all visible) with the same configuration
+ * (cfg->device is ignored) and pins replica (app_id, pidx) to GPU pidx % n.  No collective, no peer traffic. */
+typedef struct pgs_router pgs_router;
+PGS_API int32_t pgs_router_open(const pgs_engine_config *cfg, int32_t n_devices, pgs_router **out);
+PGS_API void pgs_router_close(pgs_router *r); /* closes its engines: close their partitions / servers first */
+PGS_API int32_t pgs_router_device_count(const pgs_router *r);
+PGS_API int32_t pgs_router_device_for(const pgs_router *r, int32_t app_id, int32_t pidx); /* -1: no such */
+PGS_API pgs_engine *pgs_router_engine_for(pgs_router *r, int32_t app_id, int32_t pidx);
+/* pegasus_key_hash(hash_key, sort_key) % partition_count (src/base/pegasus_key_schema.h:150-165): the client-side half */
+PGS_API uint32_t pgs_partition_index(const uint8_t *hash_key, uint32_t hash_key_len, const uint8_t *sort_key,
+                                     uint32_t sort_key_len, uint32_t partition_count);
 
 #ifdef __cplusplus
 }

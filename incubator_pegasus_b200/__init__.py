@@ -52,6 +52,11 @@ class RunInfo(C.Structure):
                 ("smallest_seq", C.c_uint64), ("largest_seq", C.c_uint64)]
 
 
+class RunSrc(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("data_bytes", C.c_uint64), ("blk_off", C.c_void_p), ("blk_size", C.c_void_p),
+                ("n_blocks", C.c_uint32), ("level", C.c_int32)]
+
+
 class FilterParams(C.Structure):
     _fields_ = [("enabled", C.c_uint8), ("validate_hash", C.c_uint8), ("reserved", C.c_uint8 * 2),
                 ("data_version", C.c_uint32), ("default_ttl", C.c_uint32), ("pidx", C.c_int32),
@@ -163,12 +168,24 @@ def lib() -> C.CDLL:
     L.pgs_engine_last_kernel_ms.restype = C.c_float
     L.pgs_engine_last_blocks_probed.argtypes = [vp]
     L.pgs_engine_last_blocks_probed.restype = C.c_uint64
+    L.pgs_router_open.argtypes = [C.POINTER(EngineConfig), C.c_int32, C.POINTER(vp)]
+    L.pgs_router_close.argtypes = [vp]
+    L.pgs_router_close.restype = None
+    L.pgs_router_device_count.argtypes = [vp]
+    L.pgs_router_device_for.argtypes = [vp, C.c_int32, C.c_int32]
+    L.pgs_router_engine_for.argtypes = [vp, C.c_int32, C.c_int32]
+    L.pgs_router_engine_for.restype = vp
+    L.pgs_partition_index.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32]
+    L.pgs_partition_index.restype = C.c_uint32
+    L.pgs_engine_last_runs_skipped.argtypes = [vp]
+    L.pgs_engine_last_runs_skipped.restype = C.c_uint64
     L.pgs_range_scan_many.argtypes = [vp, C.POINTER(ScanRequest), C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, vp, C.c_uint64,
                                       vp, C.c_uint64, vp, C.c_uint32, vp, vp, vp]
     L.pgs_partition_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(vp)]
     L.pgs_partition_destroy.argtypes = [vp]
     L.pgs_partition_destroy.restype = None
     L.pgs_run_upload.argtypes = [vp, C.c_int32, vp, C.c_uint64, vp, vp, C.c_uint32, u64p]
+    L.pgs_run_upload_many.argtypes = [vp, C.POINTER(RunSrc), C.c_uint32, u64p]
     L.pgs_run_drop.argtypes = [vp, C.c_uint64]
     L.pgs_run_info_get.argtypes = [vp, C.c_uint64, C.POINTER(RunInfo)]
     L.pgs_run_list.argtypes = [vp, u64p, C.c_uint32, u32p]
@@ -377,6 +394,10 @@ class Engine:
     def last_blocks_probed(self) -> int:
         return int(lib().pgs_engine_last_blocks_probed(self.h))
 
+    @property
+    def last_runs_skipped(self) -> int:
+        return int(lib().pgs_engine_last_runs_skipped(self.h))
+
     def partition(self, app_id: int = 1, pidx: int = 0, data_version: int = 1) -> "Partition":
         return Partition(self, app_id, pidx, data_version)
 
@@ -385,6 +406,46 @@ class Engine:
 
     def __exit__(self, *a):
         self.close()
+
+
+class Router:
+    """One engine per visible GPU; replica (app_id, pidx) lives on GPU pidx % n (pgs_router_*, include/pegasus_b200.h §7)."""
+
+    def __init__(self, n_devices: int = 0, ctas_per_sm: int = 0, flags: int = 0, block_size: int = 0, restart_interval: int = 0):
+        cfg = EngineConfig(-1, block_size, restart_interval, ctas_per_sm, flags)
+        self.h = C.c_void_p()
+        _check(lib().pgs_router_open(C.byref(cfg), n_devices, C.byref(self.h)), "router_open")
+
+    @property
+    def device_count(self) -> int:
+        return int(lib().pgs_router_device_count(self.h))
+
+    def device_for(self, app_id: int, pidx: int) -> int:
+        return int(lib().pgs_router_device_for(self.h, app_id, pidx))
+
+    def engine_for(self, app_id: int, pidx: int) -> Engine:
+        h = lib().pgs_router_engine_for(self.h, app_id, pidx)
+        if not h:
+            raise PegasusError(INVALID_ARGUMENT, "router_engine_for")
+        e = Engine.__new__(Engine)  # borrowed: the router owns and closes it
+        e.h = C.c_void_p(h)
+        e.close = lambda: None
+        return e
+
+    def close(self):
+        if self.h:
+            lib().pgs_router_close(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def partition_index(hash_key: bytes, sort_key: bytes, partition_count: int) -> int:
+    return int(lib().pgs_partition_index(hash_key, len(hash_key), sort_key, len(sort_key), partition_count))
 
 
 class Partition:
@@ -407,6 +468,17 @@ class Partition:
         _check(lib().pgs_run_upload(self.h, level, _ptr(run.data), run.data.shape[0], _ptr(run.blk_off),
                                     _ptr(run.blk_size), run.n_blocks, C.byref(rid)), "run_upload")
         return rid.value
+
+    def upload_many(self, runs, levels=None) -> list[int]:
+        """several runs in one pipelined call (pgs_run_upload_many); runs[0] is installed first"""
+        n = len(runs)
+        src = (RunSrc * max(1, n))()
+        for i, r in enumerate(runs):
+            src[i] = RunSrc(r.data.ctypes.data, r.data.shape[0], r.blk_off.ctypes.data, r.blk_size.ctypes.data, r.n_blocks,
+                            0 if levels is None else levels[i])
+        ids = np.zeros(max(1, n), np.uint64)
+        _check(lib().pgs_run_upload_many(self.h, src, n, ids.ctypes.data_as(u64p)), "run_upload_many")
+        return [int(x) for x in ids[:n]]
 
     def upload_records(self, recs: Records, level: int = 0) -> int:
         return self.upload(build_run(recs), level)

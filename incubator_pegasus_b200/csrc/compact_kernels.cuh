@@ -123,9 +123,10 @@ struct CompactGeometry {
     uint64_t blk_cap, out_cap, ikey_cap;
 };
 // fills the derived fields of P (P.k, P.block_size, P.restart_interval must be set); false = not supported
-constexpr uint32_t kWalkMinG = 1; // default lanes per merge group (see group.cuh)
+constexpr uint32_t kWalkMinG = 4; // default lanes per merge group (see group.cuh)
 inline uint32_t walk_fixed_smem();
-inline bool compact_geometry(MergeParams &P, const CompactTotals &T, uint32_t max_smem, CompactGeometry &geo, uint32_t force_G = 0)
+inline bool compact_geometry(MergeParams &P, const CompactTotals &T, uint32_t max_smem, CompactGeometry &geo, uint32_t force_G = 0,
+                             uint64_t force_weight = 0)
 {
     const uint32_t k = P.k;
     P.total_blocks = (uint32_t)T.total_blocks;
@@ -166,7 +167,7 @@ inline bool compact_geometry(MergeParams &P, const CompactTotals &T, uint32_t ma
     geo.emit_dyn = geo.emit_warps * P.emit_warp_smem;
     // segments
     P.rec_cost = kSegRecCost;
-    P.tile_weight = kSegWeight;
+    P.tile_weight = force_weight ? force_weight : kSegWeight;
     const uint64_t W_total = T.in_block_bytes + T.n_rec * P.rec_cost;
     uint64_t Q = (W_total + P.tile_weight - 1) / P.tile_weight;
     if (Q == 0) Q = 1;
@@ -456,9 +457,29 @@ template <uint32_t G>
 PGS_DEV bool head_before(const Grp<G> &g, bool en, const CurState *cs, const uint32_t *rows, uint32_t KSW, uint32_t a, uint32_t b, uint32_t &dpos, bool &by_byte)
 {
     uint32_t la = 0, lb = 0;
-    if (en) { la = cs[a].klen - 8; lb = cs[b].klen - 8; }
-    const int c = row_cmp(g, en, rows + a * KSW, la, rows + b * KSW, lb, dpos);
+    bool full = en; // the first eight bytes decide most of the time: two scalar compares, no collective
+    if (en) {
+        la = cs[a].klen - 8; lb = cs[b].klen - 8;
+        const uint32_t ah = cs[a].kp_hi, al = cs[a].kp_lo, bh = cs[b].kp_hi, bl = cs[b].kp_lo;
+        if ((ah != bh || al != bl) && la >= 8 && lb >= 8) {
+            dpos = ah != bh ? (uint32_t)__clz((int)(ah ^ bh)) >> 3 : 4 + ((uint32_t)__clz((int)(al ^ bl)) >> 3);
+            by_byte = true;
+            full = false;
+        }
+    }
+    if (!g.any(full)) {
+        if (!en) { by_byte = false; return false; }
+        const uint32_t ah = cs[a].kp_hi, bh = cs[b].kp_hi;
+        return ah != bh ? ah < bh : cs[a].kp_lo < cs[b].kp_lo;
+    }
+    uint32_t dfull = 0;
+    const int c = row_cmp(g, full, rows + a * KSW, la, rows + b * KSW, lb, dfull);
     if (!en) { by_byte = false; return false; }
+    if (!full) {
+        const uint32_t ah = cs[a].kp_hi, bh = cs[b].kp_hi;
+        return ah != bh ? ah < bh : cs[a].kp_lo < cs[b].kp_lo;
+    }
+    dpos = dfull;
     by_byte = c != 0 && dpos < (la < lb ? la : lb);
     if (c) return c < 0;
     const unsigned long long ta = cur_trailer(&cs[a]), tb = cur_trailer(&cs[b]);
@@ -586,7 +607,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
     uint32_t n_blocks = 0, keyb = 0, lenA = 0;
     unsigned long long out_bytes = 0;
     bool have_head = false, head_in_A = false, prev_big = false;
-    uint32_t head_len = 0, last_run = 0xffu;
+    uint32_t head_len = 0, last_run = 0xffu, lcpA = 0; // lcpA: bytes the head shares with A (the last survivor's key)
     uint32_t d1 = 0, prev_pl = 0xFFFFFFFFu;
     bool d1_valid = false;
     auto close_block = [&]() { // bookkeeping of a finished block (k_emit derives the same numbers)
@@ -608,14 +629,21 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         if (act) { ulen = C->klen - 8; vlen = C->vlen; tr_lo = C->tr_lo; tr_hi = C->tr_hi; type = tr_lo & 0xffu; }
         uint32_t ev = act ? 1u << EV_IN : 0u; // what happened to this record, one bit per counter
         // (1) an older version of the user key that was just handled?  The record before this one carried the head's user key;
-        // when it came from the same run, the entry's `shared` field is a known common prefix (all of the key: no compare).
+        // when it came from the same run, the entry's `shared` field is a known common prefix: all of the key (a shadow, no
+        // compare), or it ends in front of a byte that differs (one byte to look at; a block writer that stored less than
+        // the exact shared length falls through to the compare).
         uint32_t lcp_head = 0, from = 0;
         const bool cmp1 = act && have_head;
+        const uint32_t *hrow = head_in_A ? rowA : rowB;
         if (cmp1 && last_run == c) { from = C->shared < ulen ? C->shared : ulen; if (from > head_len) from = head_len; }
         bool shadow = cmp1 && from == ulen && ulen == head_len;
-        const bool cmp1b = cmp1 && !shadow;
+        bool cmp1b = cmp1 && !shadow;
+        if (cmp1b && last_run == c) {
+            if (from == ulen || from == head_len) { lcp_head = from; cmp1b = false; } // one key is a proper prefix of the other
+            else if (((row[from >> 2] ^ hrow[from >> 2]) >> (8 * (from & 3))) & 0xffu) { lcp_head = from; cmp1b = false; }
+        }
         if (g.any(cmp1b)) {
-            const int c1 = row_cmp(g, cmp1b, row, ulen, head_in_A ? rowA : rowB, head_len, lcp_head, from);
+            const int c1 = row_cmp(g, cmp1b, row, ulen, hrow, head_len, lcp_head, from);
             if (cmp1b && c1 == 0) shadow = true;
         }
         if (shadow) lcp_head = ulen;
@@ -642,15 +670,14 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
                 keep = true;
             }
         }
-        // (3) prefix compression against the previous survivor (one more compare when the last group head was dropped)
+        // (3) prefix compression against the previous survivor A.  Keys arrive in ascending order, so the prefix shared with A
+        // is the minimum over the heads in between: lcp(K, A) = min(lcp(K, head), lcp(head, A)) -- no compare.
         bool restart = to_restart == 0;
-        uint32_t shared = 0;
-        const bool cmp2 = keep && !restart && !(have_head && head_in_A);
-        if (g.any(cmp2)) row_cmp(g, cmp2, row, ulen, rowA, lenA, shared);
-        if (keep && !restart && have_head && head_in_A) shared = lcp_head;
+        const uint32_t lcp_KA = !have_head ? 0u : head_in_A ? lcp_head : (lcp_head < lcpA ? lcp_head : lcpA);
+        uint32_t shared = keep && !restart ? lcp_KA : 0u;
         if (P.out_bloom_lines) { // the new run's Bloom filter: the user key, and its hash-key prefix when that changed
-            const bool lcp_known = keep && (cmp2 || (have_head && head_in_A));
-            const uint32_t lcp_out = cmp2 ? shared : lcp_head;
+            const bool lcp_known = keep && have_head;
+            const uint32_t lcp_out = lcp_KA;
             const unsigned long long hk = bloom_hash_row(g, row, keep ? ulen : 0u);
             if (keep) {
 #pragma unroll
@@ -752,7 +779,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
             uint32_t *dst = keep ? rowA : rowB;
 #pragma unroll 1
             for (uint32_t w = g.gl; 4 * w < ulen; w += G) dst[w] = row[w];
-            if (keep) lenA = ulen;
+            if (keep) { lenA = ulen; lcpA = ulen; } else lcpA = lcp_KA; // lcp(new head, A)
             head_in_A = keep;
             have_head = true;
             head_len = ulen;
@@ -812,8 +839,9 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
 constexpr uint32_t kWalkFixedSmem = 2048 + kMaxRuns * (uint32_t)sizeof(RunDev) + (uint32_t)sizeof(WalkCtaStats);
 inline uint32_t walk_fixed_smem() { return kWalkFixedSmem; }
 
-template <uint32_t G>
-__global__ void __launch_bounds__(kWalkThreads) k_walk(const __grid_constant__ MergeParams P)
+// MINB = resident CTAs per SM the register allocation aims for
+template <uint32_t G, uint32_t MINB>
+__global__ void __launch_bounds__(kWalkThreads, MINB) k_walk(const __grid_constant__ MergeParams P)
 {
     PGS_SMEM_DYN(dyn);
     const Grp<G> g;

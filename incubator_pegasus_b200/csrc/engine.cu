@@ -101,6 +101,7 @@ Engine::~Engine()
     spares.clear();
     if (h_pinned) cudaFreeHost(h_pinned);
     for (auto &s : rd_streams) if (s) cudaStreamDestroy(s);
+    if (up_copy) cudaStreamDestroy(up_copy);
     if (stream) cudaStreamDestroy(stream);
 }
 cudaStream_t Engine::read_stream()
@@ -158,12 +159,12 @@ k_index_walk(const uint8_t *__restrict__ data, const uint64_t *__restrict__ blk_
              const uint32_t *__restrict__ blk_size, uint32_t nb, uint32_t *__restrict__ nrec_out,
              uint32_t *__restrict__ lastlen_out, const uint32_t *__restrict__ ikey_off,
              uint8_t *__restrict__ ikeys, const uint32_t *__restrict__ blk_rec, uint32_t *__restrict__ rec_off,
-             uint32_t *__restrict__ bloom, uint32_t bloom_lines, IndexStats *__restrict__ stats)
+             uint32_t *__restrict__ bloom, uint32_t bloom_lines, IndexStats *__restrict__ stats, uint32_t b_begin)
 {
     const Grp<32> g;
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t b = blockIdx.x * kIdxWarps + warp;
+    uint32_t b = b_begin + blockIdx.x * kIdxWarps + warp; // blocks [b_begin, nb)
     if (b >= nb) return;
     uint8_t *scr = smem + warp * kIdxScratch;
     const uint8_t *base = data + blk_off[b];
@@ -250,80 +251,196 @@ k_index_walk(const uint8_t *__restrict__ data, const uint64_t *__restrict__ blk_
     if (err && lane == 0) atomicMax(&stats->error, err);
 }
 
-int32_t build_index(Engine *e, Run *r, const uint64_t *h_blk_off, const uint32_t *h_blk_size)
+int32_t index_init_kernels()
 {
-    uint32_t nb = r->info.n_blocks;
-    cudaStream_t st = e->stream;
+    const int smem = (int)(kIdxWarps * kIdxScratch);
+    PGS_CUDA(cudaFuncSetAttribute(k_index_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PGS_CUDA(cudaFuncSetAttribute(k_index_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return PGS_OK;
+}
+
+// ---- staged upload of one run ---------------------------------------------------------------------------------------------
+// stage A (asynchronous): the block bytes travel in chunks on the engine's copy stream; the first index pass (records and
+//          last-key length per block, run statistics) runs on each chunk as soon as it has landed, while the next chunk
+//          is still on the link
+// stage B: waits for the first pass only, lays out the index (host prefix sums over the blocks), starts the second pass
+//          (index keys, entry offsets, Bloom filter)
+// stage C: waits for the second pass, publishes the run
+// pgs_run_upload runs A, B, C back to back; pgs_run_upload_many issues A of the next run before B of the current one, so
+// the link never idles between runs.
+constexpr uint64_t kUploadChunk = 32ull << 20;
+
+struct UploadJob {
+    std::shared_ptr<Run> r;
+    std::vector<uint64_t> off;
+    const uint32_t *h_blk_size = nullptr;
     uint32_t *d_nrec = nullptr, *d_lastlen = nullptr;
     IndexStats *d_stats = nullptr;
-    PGS_CUDA(cudaMallocAsync(&d_nrec, sizeof(uint32_t) * nb, st));
-    PGS_CUDA(cudaMallocAsync(&d_lastlen, sizeof(uint32_t) * nb, st));
-    PGS_CUDA(cudaMallocAsync(&d_stats, sizeof(IndexStats), st));
     IndexStats hs{};
-    hs.min_seq = ~0ull;
-    PGS_CUDA(cudaMemcpyAsync(d_stats, &hs, sizeof hs, cudaMemcpyHostToDevice, st));
-    uint32_t grid = (nb + kIdxWarps - 1) / kIdxWarps;
-    size_t smem = kIdxWarps * kIdxScratch;
-    PGS_CUDA(cudaFuncSetAttribute(k_index_walk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PGS_CUDA(cudaFuncSetAttribute(k_index_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_index_walk<false><<<grid, kIdxWarps * 32, smem, st>>>(r->d_data, r->d_blk_off, r->d_blk_size, nb, d_nrec,
-                                                            d_lastlen, nullptr, nullptr, nullptr, nullptr, nullptr, 0, d_stats);
-    e->launches++;
-    std::vector<uint32_t> nrec(nb), lastlen(nb);
-    PGS_CUDA(cudaMemcpyAsync(nrec.data(), d_nrec, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
-    PGS_CUDA(cudaMemcpyAsync(lastlen.data(), d_lastlen, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
-    PGS_CUDA(cudaMemcpyAsync(&hs, d_stats, sizeof hs, cudaMemcpyDeviceToHost, st));
-    PGS_CUDA(cudaStreamSynchronize(st));
-    cudaFreeAsync(d_nrec, st);
-    cudaFreeAsync(d_lastlen, st);
-    if (hs.error) {
-        cudaFreeAsync(d_stats, st);
-        set_error("run upload: block scan failed with status %u", hs.error);
-        return (int32_t)hs.error;
-    }
-    std::vector<uint32_t> rec_cum(nb + 1), key_cum(nb + 1);
-    uint64_t rc = 0, kc = 0;
+    std::vector<uint32_t> nrec, lastlen, rec_cum, key_cum;
+    std::vector<cudaEvent_t> events;
+    cudaEvent_t pass1 = nullptr;
     uint32_t max_blk = 0;
+    ~UploadJob()
+    {
+        for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+        if (pass1) cudaEventDestroy(pass1);
+    }
+};
+
+static int32_t upload_stage_a(Engine *e, int32_t level, const uint8_t *data, uint64_t data_bytes, const uint64_t *blk_off,
+                              const uint32_t *blk_size, uint32_t nb, UploadJob &j)
+{
+    uint64_t prev_end = 0;
     for (uint32_t b = 0; b < nb; b++) {
-        rec_cum[b] = (uint32_t)rc;
-        key_cum[b] = (uint32_t)kc;
-        rc += nrec[b];
-        kc += lastlen[b];
-        max_blk = std::max(max_blk, h_blk_size[b]);
+        if (blk_off[b] % kBlockAlign || blk_off[b] < prev_end || blk_off[b] + blk_size[b] > data_bytes) {
+            set_error("run upload: bad block handle %u", b);
+            return PGS_INVALID_ARGUMENT;
+        }
+        prev_end = blk_off[b] + blk_size[b];
+        j.max_blk = std::max(j.max_blk, blk_size[b]);
+    }
+    auto r = std::make_shared<Run>();
+    j.r = r;
+    j.h_blk_size = blk_size;
+    r->level = level;
+    r->info.level = level;
+    r->info.n_blocks = nb;
+    const uint64_t end = (prev_end + kBlockAlign - 1) / kBlockAlign * kBlockAlign;
+    const uint64_t nbytes = data_bytes < end ? data_bytes : end;
+    r->info.data_bytes = end;
+    r->data_cap = end + 256;
+    cudaStream_t st = e->stream, cp = e->up_copy;
+    r->pool_stream = st; // stream-ordered pool: repeated flush / compaction cycles reuse the same HBM without driver calls
+    r->eng = e;
+    if (r->data_cap >= kSpareMin) { uint64_t cap = 0; r->d_data = e->take_data(r->data_cap, &cap); if (r->d_data) r->data_cap = cap; }
+    if (!r->d_data) PGS_CUDA(cudaMallocAsync(&r->d_data, r->data_cap, st));
+    PGS_CUDA(cudaMallocAsync(&r->d_blk_off, sizeof(uint64_t) * (nb + 1), st));
+    PGS_CUDA(cudaMallocAsync(&r->d_blk_size, sizeof(uint32_t) * nb, st));
+    PGS_CUDA(cudaMallocAsync(&j.d_nrec, sizeof(uint32_t) * nb, st));
+    PGS_CUDA(cudaMallocAsync(&j.d_lastlen, sizeof(uint32_t) * nb, st));
+    PGS_CUDA(cudaMallocAsync(&j.d_stats, sizeof(IndexStats), st));
+    PGS_CUDA(cudaMemsetAsync(r->d_data + nbytes, 0, r->data_cap - nbytes, st));
+    j.off.assign(blk_off, blk_off + nb);
+    j.off.push_back(end);
+    j.hs = IndexStats{};
+    j.hs.min_seq = ~0ull;
+    PGS_CUDA(cudaMemcpyAsync(r->d_blk_off, j.off.data(), sizeof(uint64_t) * (nb + 1), cudaMemcpyHostToDevice, st));
+    PGS_CUDA(cudaMemcpyAsync(r->d_blk_size, blk_size, sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, st));
+    PGS_CUDA(cudaMemcpyAsync(j.d_stats, &j.hs, sizeof j.hs, cudaMemcpyHostToDevice, st));
+    cudaEvent_t ready;
+    PGS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    j.events.push_back(ready);
+    PGS_CUDA(cudaEventRecord(ready, st)); // the copy stream may touch the new buffers from here on
+    PGS_CUDA(cudaStreamWaitEvent(cp, ready, 0));
+    const size_t smem = kIdxWarps * kIdxScratch;
+    uint32_t b0 = 0;
+    while (b0 < nb) { // chunks end on block boundaries
+        uint32_t b1 = b0 + 1;
+        while (b1 < nb && j.off[b1] - j.off[b0] < kUploadChunk) b1++;
+        const uint64_t lo = j.off[b0], hi = b1 == nb ? nbytes : std::min<uint64_t>(j.off[b1], nbytes);
+        if (hi > lo) PGS_CUDA(cudaMemcpyAsync(r->d_data + lo, data + lo, hi - lo, cudaMemcpyHostToDevice, cp));
+        cudaEvent_t ev;
+        PGS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        j.events.push_back(ev);
+        PGS_CUDA(cudaEventRecord(ev, cp));
+        PGS_CUDA(cudaStreamWaitEvent(st, ev, 0));
+        k_index_walk<false><<<(b1 - b0 + kIdxWarps - 1) / kIdxWarps, kIdxWarps * 32, smem, st>>>(
+            r->d_data, r->d_blk_off, r->d_blk_size, b1, j.d_nrec, j.d_lastlen, nullptr, nullptr, nullptr, nullptr, nullptr, 0, j.d_stats, b0);
+        e->launches++;
+        b0 = b1;
+    }
+    j.nrec.resize(nb);
+    j.lastlen.resize(nb);
+    PGS_CUDA(cudaMemcpyAsync(j.nrec.data(), j.d_nrec, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
+    PGS_CUDA(cudaMemcpyAsync(j.lastlen.data(), j.d_lastlen, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
+    PGS_CUDA(cudaMemcpyAsync(&j.hs, j.d_stats, sizeof j.hs, cudaMemcpyDeviceToHost, st));
+    PGS_CUDA(cudaEventCreateWithFlags(&j.pass1, cudaEventDisableTiming));
+    PGS_CUDA(cudaEventRecord(j.pass1, st));
+    return PGS_OK;
+}
+
+static int32_t upload_stage_b(Engine *e, UploadJob &j)
+{
+    Run *r = j.r.get();
+    const uint32_t nb = r->info.n_blocks;
+    cudaStream_t st = e->stream;
+    PGS_CUDA(cudaEventSynchronize(j.pass1));
+    cudaFreeAsync(j.d_nrec, st);
+    cudaFreeAsync(j.d_lastlen, st);
+    j.d_nrec = j.d_lastlen = nullptr;
+    if (j.hs.error) {
+        set_error("run upload: block scan failed with status %u", j.hs.error);
+        return (int32_t)j.hs.error;
+    }
+    j.rec_cum.resize(nb + 1);
+    j.key_cum.resize(nb + 1);
+    uint64_t rc = 0, kc = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+        j.rec_cum[b] = (uint32_t)rc;
+        j.key_cum[b] = (uint32_t)kc;
+        rc += j.nrec[b];
+        kc += j.lastlen[b];
     }
     if (rc > 0xFFFFFFF0ull || kc > 0xFFFFFFF0ull) {
-        cudaFreeAsync(d_stats, st);
         set_error("run too large for 32-bit record / index-key offsets");
         return PGS_NOT_SUPPORTED;
     }
-    rec_cum[nb] = (uint32_t)rc;
-    key_cum[nb] = (uint32_t)kc;
+    j.rec_cum[nb] = (uint32_t)rc;
+    j.key_cum[nb] = (uint32_t)kc;
     PGS_CUDA(cudaMallocAsync(&r->d_blk_rec, sizeof(uint32_t) * (nb + 1), st));
     PGS_CUDA(cudaMallocAsync(&r->d_ikey_off, sizeof(uint32_t) * (nb + 1), st));
     PGS_CUDA(cudaMallocAsync(&r->d_ikeys, kc + 16, st));
     PGS_CUDA(cudaMallocAsync(&r->d_rec_off, sizeof(uint32_t) * (rc + 1), st));
-    PGS_CUDA(cudaMemcpyAsync(r->d_blk_rec, rec_cum.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
-    PGS_CUDA(cudaMemcpyAsync(r->d_ikey_off, key_cum.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
-    r->n_bloom_entries = hs.n_records + hs.n_prefix;
+    PGS_CUDA(cudaMemcpyAsync(r->d_blk_rec, j.rec_cum.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
+    PGS_CUDA(cudaMemcpyAsync(r->d_ikey_off, j.key_cum.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
+    r->n_bloom_entries = j.hs.n_records + j.hs.n_prefix;
     r->bloom_lines = bloom_lines_for(r->n_bloom_entries);
     PGS_CUDA(cudaMallocAsync(&r->d_bloom, (size_t)r->bloom_lines * 64, st));
     PGS_CUDA(cudaMemsetAsync(r->d_bloom, 0, (size_t)r->bloom_lines * 64, st));
-    k_index_walk<true><<<grid, kIdxWarps * 32, smem, st>>>(r->d_data, r->d_blk_off, r->d_blk_size, nb, nullptr,
-                                                           nullptr, r->d_ikey_off, r->d_ikeys, r->d_blk_rec, r->d_rec_off, r->d_bloom, r->bloom_lines, d_stats);
+    k_index_walk<true><<<(nb + kIdxWarps - 1) / kIdxWarps, kIdxWarps * 32, kIdxWarps * kIdxScratch, st>>>(
+        r->d_data, r->d_blk_off, r->d_blk_size, nb, nullptr, nullptr, r->d_ikey_off, r->d_ikeys, r->d_blk_rec, r->d_rec_off, r->d_bloom,
+        r->bloom_lines, j.d_stats, 0);
     e->launches++;
-    PGS_CUDA(cudaStreamSynchronize(st));
-    cudaFreeAsync(d_stats, st);
-    r->info.n_records = hs.n_records;
-    r->info.n_tombstones = hs.n_tomb;
-    r->info.raw_key_bytes = hs.raw_key;
-    r->info.raw_value_bytes = hs.raw_val;
-    r->info.max_ukey_len = hs.max_ukey;
-    r->info.max_value_len = hs.max_vlen;
-    r->info.max_block_size = max_blk;
-    r->info.max_block_records = hs.max_blk_rec;
-    r->info.smallest_seq = hs.min_seq;
-    r->info.largest_seq = hs.max_seq;
+    PGS_CUDA(cudaEventRecord(j.pass1, st)); // reused: now marks the end of the second pass
     return PGS_OK;
+}
+
+static int32_t upload_stage_c(Engine *e, Partition &p, UploadJob &j, uint64_t *run_id_out)
+{
+    Run *r = j.r.get();
+    PGS_CUDA(cudaEventSynchronize(j.pass1));
+    cudaFreeAsync(j.d_stats, e->stream);
+    j.d_stats = nullptr;
+    r->info.n_records = j.hs.n_records;
+    r->info.n_tombstones = j.hs.n_tomb;
+    r->info.raw_key_bytes = j.hs.raw_key;
+    r->info.raw_value_bytes = j.hs.raw_val;
+    r->info.max_ukey_len = j.hs.max_ukey;
+    r->info.max_value_len = j.hs.max_vlen;
+    r->info.max_block_size = j.max_blk;
+    r->info.max_block_records = j.hs.max_blk_rec;
+    r->info.smallest_seq = j.hs.min_seq;
+    r->info.largest_seq = j.hs.max_seq;
+    r->id = e->next_run_id++;
+    r->info.run_id = r->id;
+    {
+        std::lock_guard<std::mutex> g(p.mu);
+        p.insert(j.r);
+    }
+    if (run_id_out) *run_id_out = r->id;
+    return PGS_OK;
+}
+// a failed job: nothing of it may still be in flight when its host vectors and device buffers go away
+static void upload_abandon(Engine *e, UploadJob &j)
+{
+    cudaStreamSynchronize(e->up_copy);
+    cudaStreamSynchronize(e->stream);
+    if (j.d_nrec) cudaFreeAsync(j.d_nrec, e->stream);
+    if (j.d_lastlen) cudaFreeAsync(j.d_lastlen, e->stream);
+    if (j.d_stats) cudaFreeAsync(j.d_stats, e->stream);
+    j.d_nrec = j.d_lastlen = nullptr;
+    j.d_stats = nullptr;
 }
 
 } // namespace pgs
@@ -359,7 +476,9 @@ int32_t pgs_engine_open(const pgs_engine_config *cfg, pgs_engine **out)
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e.sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (err == cudaSuccess) err = cudaDeviceGetAttribute(&e.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     for (auto &s : e.rd_streams) if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-    if (err == cudaSuccess && (lookup_init_kernels(e.max_smem_optin) != PGS_OK || compact_init_kernels(e.max_smem_optin) != PGS_OK)) {
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e.up_copy, cudaStreamNonBlocking);
+    if (err == cudaSuccess && (lookup_init_kernels(e.max_smem_optin) != PGS_OK || compact_init_kernels(e.max_smem_optin) != PGS_OK ||
+                               index_init_kernels() != PGS_OK)) {
         delete h; // the failing call left its description in pgs_last_error()
         return PGS_IO_ERROR;
     }
@@ -424,52 +543,41 @@ int32_t pgs_run_upload(pgs_partition *ph, int32_t level, const uint8_t *data, ui
                        const uint64_t *blk_off, const uint32_t *blk_size, uint32_t n_blocks,
                        uint64_t *run_id_out)
 {
-    if (!ph || level < 0 || (n_blocks && (!data || !blk_off || !blk_size))) return PGS_INVALID_ARGUMENT;
+    pgs_run_src src{data, data_bytes, blk_off, blk_size, n_blocks, level};
+    return pgs_run_upload_many(ph, &src, 1, run_id_out);
+}
+
+int32_t pgs_run_upload_many(pgs_partition *ph, const pgs_run_src *runs, uint32_t n, uint64_t *run_ids_out)
+{
+    if (!ph || (n && !runs)) return PGS_INVALID_ARGUMENT;
+    for (uint32_t i = 0; i < n; i++)
+        if (runs[i].level < 0 || (runs[i].n_blocks && (!runs[i].data || !runs[i].blk_off || !runs[i].blk_size))) return PGS_INVALID_ARGUMENT;
     Partition &p = ph->p;
     Engine *e = p.eng;
-    if (n_blocks == 0) {
-        if (run_id_out) *run_id_out = 0;
-        return PGS_OK;
-    }
-    uint64_t prev_end = 0;
-    for (uint32_t b = 0; b < n_blocks; b++) {
-        if (blk_off[b] % kBlockAlign || blk_off[b] < prev_end || blk_off[b] + blk_size[b] > data_bytes) {
-            set_error("run upload: bad block handle %u", b);
-            return PGS_INVALID_ARGUMENT;
-        }
-        prev_end = blk_off[b] + blk_size[b];
-    }
     PGS_CUDA(cudaSetDevice(e->device));
-    auto r = std::make_shared<Run>();
-    r->level = level;
-    r->info.level = level;
-    r->info.n_blocks = n_blocks;
-    uint64_t end = (prev_end + kBlockAlign - 1) / kBlockAlign * kBlockAlign;
-    r->info.data_bytes = end;
-    r->data_cap = end + 256;
-    cudaStream_t st = e->stream;
-    r->pool_stream = st; // stream-ordered pool: repeated flush / compaction cycles reuse the same HBM without driver calls
-    r->eng = e;
-    if (r->data_cap >= kSpareMin) { uint64_t cap = 0; r->d_data = e->take_data(r->data_cap, &cap); if (r->d_data) r->data_cap = cap; }
-    if (!r->d_data) PGS_CUDA(cudaMallocAsync(&r->d_data, r->data_cap, st));
-    PGS_CUDA(cudaMallocAsync(&r->d_blk_off, sizeof(uint64_t) * (n_blocks + 1), st));
-    PGS_CUDA(cudaMallocAsync(&r->d_blk_size, sizeof(uint32_t) * n_blocks, st));
-    PGS_CUDA(cudaMemsetAsync(r->d_data + (data_bytes < end ? data_bytes : end), 0, r->data_cap - (data_bytes < end ? data_bytes : end), st));
-    PGS_CUDA(cudaMemcpyAsync(r->d_data, data, data_bytes < end ? data_bytes : end, cudaMemcpyHostToDevice, st));
-    std::vector<uint64_t> off(blk_off, blk_off + n_blocks);
-    off.push_back(end);
-    PGS_CUDA(cudaMemcpyAsync(r->d_blk_off, off.data(), sizeof(uint64_t) * (n_blocks + 1), cudaMemcpyHostToDevice, st));
-    PGS_CUDA(cudaMemcpyAsync(r->d_blk_size, blk_size, sizeof(uint32_t) * n_blocks, cudaMemcpyHostToDevice, st));
-    PGS_CUDA(cudaStreamSynchronize(st)); // `off` and the caller's buffers may go away
-    int32_t rc = build_index(e, r.get(), blk_off, blk_size);
-    if (rc != PGS_OK) return rc;
-    r->id = e->next_run_id++;
-    r->info.run_id = r->id;
-    {
-        std::lock_guard<std::mutex> g(p.mu);
-        p.insert(r);
+    std::vector<std::unique_ptr<UploadJob>> jobs(n);
+    std::vector<uint64_t> ids(n, 0);
+    int32_t rc = PGS_OK;
+    auto stage_a = [&](uint32_t i) {
+        if (runs[i].n_blocks == 0) return (int32_t)PGS_OK; // an empty run: id 0, nothing resident
+        jobs[i] = std::make_unique<UploadJob>();
+        return upload_stage_a(e, runs[i].level, runs[i].data, runs[i].data_bytes, runs[i].blk_off, runs[i].blk_size, runs[i].n_blocks, *jobs[i]);
+    };
+    // the next run's bytes are queued on the link before this run's index is finished
+    if (n) rc = stage_a(0);
+    uint32_t done = 0;
+    for (uint32_t i = 0; i < n && rc == PGS_OK; i++) {
+        if (i + 1 < n) rc = stage_a(i + 1);
+        if (rc == PGS_OK && jobs[i]) rc = upload_stage_b(e, *jobs[i]);
+        if (rc == PGS_OK && i > 0 && jobs[i - 1]) { rc = upload_stage_c(e, p, *jobs[i - 1], &ids[i - 1]); if (rc == PGS_OK) done = i; }
     }
-    if (run_id_out) *run_id_out = r->id;
+    if (rc == PGS_OK && n && jobs[n - 1]) { rc = upload_stage_c(e, p, *jobs[n - 1], &ids[n - 1]); if (rc == PGS_OK) done = n; }
+    if (rc != PGS_OK) { // all or nothing
+        for (auto &j : jobs) if (j) upload_abandon(e, *j);
+        for (uint32_t i = 0; i < done; i++) if (ids[i]) pgs_run_drop(ph, ids[i]);
+        return rc;
+    }
+    if (run_ids_out) for (uint32_t i = 0; i < n; i++) run_ids_out[i] = ids[i];
     return PGS_OK;
 }
 

@@ -50,6 +50,7 @@ struct Engine {
     // reads of different host threads go to different streams (runs are complete before they become visible, so a reader
     // needs no ordering with the stream that built them); writes / uploads / compactions use `stream`
     static constexpr int kReadStreams = 8;
+    cudaStream_t up_copy = nullptr;     // host -> HBM copies of run uploads (the index build follows chunk by chunk on `stream`)
     cudaStream_t rd_streams[kReadStreams] = {};
     cudaStream_t read_stream();
     // reusable pinned staging + device scratch
@@ -87,7 +88,6 @@ int32_t cuda_fail(cudaError_t e, const char *what);
     } while (0)
 
 // scans an uploaded / freshly merged run's blocks on the device and fills the index + info
-int32_t build_index(Engine *e, Run *r, const uint64_t *h_blk_off, const uint32_t *h_blk_size);
 
 } // namespace pgs
 

@@ -113,6 +113,8 @@ struct CurState { // 32-bit fields only: any 4-byte-aligned stride between the s
     uint32_t tr_lo, tr_hi;     // trailer: seq << 8 | type
     uint32_t chk_from;         // blocks >= chk_from may hold keys above the range's upper bound
     uint32_t live;             // 0 once the cursor is exhausted
+    uint32_t kp_hi, kp_lo;     // the first eight key bytes as a big-endian number (zero padded): most order decisions need no more
+    uint32_t hi_lcp;           // compaction walker: bytes the key shares with the range's upper bound (0x80000000: not known)
 };
 PGS_DEV unsigned long long cur_trailer(const CurState *c) { return ((unsigned long long)c->tr_hi << 32) | c->tr_lo; }
 PGS_DEV unsigned long long cur_base(const CurState *c) { return ((unsigned long long)c->base_hi << 32) | c->base_lo; }
@@ -196,6 +198,13 @@ PGS_DEV uint32_t cur_decode(const Grp<G> &g, bool en, const RunDev &r, CurState 
         if (g.gl == 0) {
             c->p = p; c->elen = h + ns + vl; c->klen = klen; c->vlen = vl; c->voff = p + h + ns; c->shared = sh; c->ets_le = ets;
             c->tr_lo = tr_lo; c->tr_hi = tr_hi;
+            if (sh < 8) { // the leading bytes changed
+                const uint32_t ul = klen - 8;
+                uint32_t w0 = row[0], w1 = row[1];
+                if (ul < 4) { w0 &= (1u << (8 * ul)) - 1u; w1 = 0; }
+                else if (ul < 8) w1 &= (1u << (8 * (ul - 4))) - 1u;
+                c->kp_hi = __byte_perm(w0, 0, 0x0123); c->kp_lo = __byte_perm(w1, 0, 0x0123);
+            }
         }
     }
     g.sync();
@@ -263,8 +272,8 @@ PGS_DEV void bloom_word(uint32_t w, uint32_t idx, uint32_t &ha, uint32_t &hb)
 {
     uint32_t a = (w + 0x9E3779B9u * (idx + 1)) * 0x85EBCA6Bu;
     a ^= a >> 15; a *= 0xC2B2AE35u; a ^= a >> 13;
-    uint32_t b = (w ^ (0x7F4A7C15u * (idx + 3))) * 0x27D4EB2Fu;
-    b ^= b >> 16; b *= 0x165667B1u; b ^= b >> 14;
+    uint32_t b = a * 0x27D4EB2Fu; // the second half rides on the first mix
+    b ^= b >> 16;
     ha ^= a; hb ^= b;
 }
 PGS_DEV unsigned long long bloom_finish(uint32_t ha, uint32_t hb, uint32_t len)

@@ -87,6 +87,14 @@ class Backend:
         self.resp = vp(f("response_new")())
         self.decree = 0
 
+    def reader(self) -> "Backend":
+        """a second handle on the same server with its own response object, for a concurrent reader thread"""
+        import copy
+        r = copy.copy(self)
+        r.resp = C.c_void_p(self.f("response_new")())
+        r.is_reader = True
+        return r
+
     @staticmethod
     def _envs(envs: dict):
         b = b"".join(k.encode() + b"\0" + v.encode() + b"\0" for k, v in envs.items())
@@ -95,7 +103,8 @@ class Backend:
     def close(self):
         if self.h:
             self.f("response_free")(self.resp)
-            self.f("rrdb_stop")(self.h)
+            if not getattr(self, "is_reader", False):
+                self.f("rrdb_stop")(self.h)
             self.h = None
 
     # ---- writes ----

@@ -9,18 +9,27 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.environ.get("NCU_LINES_SO") or os.path.join(ROOT, "incubator_pegasus_b200", "libpegasus_b200.so")
 os.system(f"rm -rf /tmp/xelf && mkdir -p /tmp/xelf && cd /tmp/xelf && cuobjdump -xelf all {so} >/dev/null 2>&1")
 cub = [f for f in os.listdir("/tmp/xelf") if f.startswith(stem) and f.endswith(".cubin")][0]
-sass = subprocess.check_output(["nvdisasm", "-g", "-c", os.path.join("/tmp/xelf", cub)]).decode().split("\n")
+DEPTH = int(os.environ.get("NCU_LINES_OUTER", "0"))  # >0: attribute to the DEPTH-th frame from the outside of the inline chain
+sass = subprocess.check_output(["nvdisasm", "-gi" if DEPTH else "-g", "-c", os.path.join("/tmp/xelf", cub)]).decode().split("\n")
 start = [i for i, l in enumerate(sass) if l.startswith(kpref) and l.rstrip().endswith(":")][0]
 end = len(sass)
 for i in range(start + 1, len(sass)):
     if sass[i].startswith("//--------------------- .text."): end = i; break
-insts, cur = [], None
+insts, cur, chain, in_chain = [], None, [], False
 for l in sass[start:end]:
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)(.*)', l)
     if m:
-        cur = (os.path.basename(m.group(1)), int(m.group(2)))
+        loc = (os.path.basename(m.group(1)), int(m.group(2)))
+        if not in_chain: chain = []
+        in_chain = True
+        chain.append(loc)  # innermost first; the following lines walk outwards
         continue
-    if re.match(r"\s*/\*[0-9a-f]{4,6}\*/\s+\S", l): insts.append((cur, l.split("*/", 1)[1].strip()[:60]))
+    if re.match(r"\s*/\*[0-9a-f]{4,6}\*/\s+\S", l):
+        if in_chain:
+            cur = chain[0]
+            if DEPTH and len(chain) >= DEPTH: cur = chain[-DEPTH]
+            in_chain = False
+        insts.append((cur, l.split("*/", 1)[1].strip()[:60]))
 out = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv"], stderr=subprocess.DEVNULL).decode()
 rows = list(csv.reader(out.split("\n")))
 hdr = rows[1]
