@@ -479,6 +479,28 @@ PGS_API pgs_engine *pgs_router_engine_for(pgs_router *r, int32_t app_id, int32_t
 PGS_API uint32_t pgs_partition_index(const uint8_t *hash_key, uint32_t hash_key_len, const uint8_t *sort_key,
                                      uint32_t sort_key_len, uint32_t partition_count);
 
+/* ============================================================================================
+ * 8. BlockBasedTable images (SST egress + ingest), first slice
+ * ==========================================================================================
+ * format_version 2, no compression: data blocks with 5-byte trailers (type 0 + masked crc32c), legacy full Bloom
+ * filter block (10 bits/key, whole user keys + HashkeyTransform prefixes), properties, metaindex, kBinarySearch index
+ * with full internal keys, 53-byte footer.  What a replica writes for L0/L1 and what rocksdb_wrapper.cpp:248-270
+ * (IngestExternalFile) reads.  Layout from RocksDB's public format description: not yet
+ * checked against a RocksDB build.  Compressed blocks / other format versions answer PGS_NOT_SUPPORTED.
+ * The encode / decode pair works on host block runs (the layout of pgs_run_upload / pgs_run_download); export / ingest
+ * wrap them around a resident run.  PGS_INCOMPLETE: the output did not fit, *out_size / *data_bytes / *n_blocks say
+ * what is needed. */
+PGS_API int32_t pgs_sst_encode(const uint8_t *data, const uint64_t *blk_off, const uint32_t *blk_size,
+                               uint32_t n_blocks, uint8_t *out, uint64_t out_cap, uint64_t *out_size);
+PGS_API int32_t pgs_sst_decode(const uint8_t *sst, uint64_t size, uint8_t *data, uint64_t data_cap,
+                               uint64_t *blk_off, uint32_t *blk_size, uint32_t blk_cap, uint64_t *data_bytes,
+                               uint32_t *n_blocks);
+/* 1 / 0: the file's Bloom filter may contain / excludes `key` (a user key or a HashkeyTransform prefix); < 0: -status */
+PGS_API int32_t pgs_sst_filter_may_match(const uint8_t *sst, uint64_t size, const uint8_t *key, uint32_t key_len);
+PGS_API int32_t pgs_sst_export(pgs_partition *p, uint64_t run_id, uint8_t *out, uint64_t out_cap, uint64_t *out_size);
+PGS_API int32_t pgs_sst_ingest(pgs_partition *p, int32_t level, const uint8_t *sst, uint64_t size, uint64_t *run_id_out);
+PGS_API uint32_t pgs_crc32c(const uint8_t *data, uint64_t len, uint32_t init);
+
 #ifdef __cplusplus
 }
 #endif

@@ -130,7 +130,16 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     if (const char *ev = getenv("PGS_WALK_G")) { const int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) force_G = (uint32_t)v; }
     uint64_t force_w = 0; // diagnostics: PGS_SEG_WEIGHT = segment budget in bytes
     if (const char *ev = getenv("PGS_SEG_WEIGHT")) { const long long v = atoll(ev); if (v >= 4096 && v <= (64ll << 20)) force_w = (uint64_t)v; }
-    if (!compact_geometry(P, T, (uint32_t)e->max_smem_optin - 1024, geo, force_G, force_w)) {
+    uint32_t minb = 4; // diagnostics: PGS_WALK_MINB
+    if (const char *ev = getenv("PGS_WALK_MINB")) minb = (uint32_t)atoi(ev);
+    bool geo_ok = compact_geometry(P, T, (uint32_t)e->max_smem_optin - 1024, geo, force_G, force_w);
+    if (geo_ok) { // second pass: the segment budget follows from how many groups the device runs at once
+        int occ = 0;
+        PGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel(geo.G, minb), (int)kWalkThreads, (size_t)geo.walk_dyn));
+        const uint64_t groups = (uint64_t)std::max(1, occ) * e->sm_count * (kWalkThreads / geo.G);
+        geo_ok = compact_geometry(P, T, (uint32_t)e->max_smem_optin - 1024, geo, geo.G, force_w, groups);
+    }
+    if (!geo_ok) {
         set_error("compact: input too large for one merge launch (keys of %u bytes, %llu records)", T.max_ukey, (unsigned long long)T.n_rec);
         return PGS_NOT_SUPPORTED;
     }
@@ -215,8 +224,6 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
 
     cudaEvent_t ev[4];
     for (auto &x : ev) CK(cudaEventCreate(&x));
-    uint32_t minb = 4; // diagnostics: PGS_WALK_MINB
-    if (const char *ev = getenv("PGS_WALK_MINB")) minb = (uint32_t)atoi(ev);
     walk_kernel_t walk = walk_kernel(geo.G, minb);
     int occ_w = 0, occ_e = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, walk, (int)kWalkThreads, (size_t)geo.walk_dyn));

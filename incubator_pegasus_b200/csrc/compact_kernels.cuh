@@ -32,7 +32,8 @@
 namespace pgs {
 
 constexpr uint32_t kSegRecCost = 256;          // planner weight = block bytes + 256 per record
-constexpr uint64_t kSegWeight = 128ull << 10;  // segment budget (about 240 records of 300 bytes)
+constexpr uint64_t kSegWeight = 128ull << 10;  // default segment budget (about 240 records of 300 bytes)
+constexpr uint64_t kSegWeightMax = 160ull << 10, kSegWeightMin = 16ull << 10; // bounds of the wave-fitted budget
 constexpr uint32_t kWalkThreads = 128;
 constexpr uint32_t kEmitThreads = 128;
 
@@ -125,8 +126,9 @@ struct CompactGeometry {
 // fills the derived fields of P (P.k, P.block_size, P.restart_interval must be set); false = not supported
 constexpr uint32_t kWalkMinG = 4; // default lanes per merge group (see group.cuh)
 inline uint32_t walk_fixed_smem();
+// walk_groups = merge groups the device runs at the same time (0: not known yet, the default segment budget is used)
 inline bool compact_geometry(MergeParams &P, const CompactTotals &T, uint32_t max_smem, CompactGeometry &geo, uint32_t force_G = 0,
-                             uint64_t force_weight = 0)
+                             uint64_t force_weight = 0, uint64_t walk_groups = 0)
 {
     const uint32_t k = P.k;
     P.total_blocks = (uint32_t)T.total_blocks;
@@ -167,8 +169,19 @@ inline bool compact_geometry(MergeParams &P, const CompactTotals &T, uint32_t ma
     geo.emit_dyn = geo.emit_warps * P.emit_warp_smem;
     // segments
     P.rec_cost = kSegRecCost;
-    P.tile_weight = force_weight ? force_weight : kSegWeight;
     const uint64_t W_total = T.in_block_bytes + T.n_rec * P.rec_cost;
+    P.tile_weight = kSegWeight;
+    if (walk_groups) {
+        // A group walks its segments one after the other and a segment is a sequential job of ~1.5 ms: the walk takes
+        // (waves of segments) x (time of a segment), and a last, partly filled wave costs as much as a full one.  Size the
+        // segments so that they fill a whole number of waves; small inputs get one wave of short segments.
+        const uint64_t waves = (W_total + kSegWeightMax * walk_groups - 1) / (kSegWeightMax * walk_groups);
+        const uint64_t slots = (waves ? waves : 1) * walk_groups;
+        uint64_t w = (W_total + slots - 1) / slots;
+        w += w / 64; // the planner cuts at block boundaries: keep the segment count just under the slot count
+        P.tile_weight = w < kSegWeightMin ? kSegWeightMin : w;
+    }
+    if (force_weight) P.tile_weight = force_weight;
     uint64_t Q = (W_total + P.tile_weight - 1) / P.tile_weight;
     if (Q == 0) Q = 1;
     if (Q > 0x7FFFFFF0ull) return false;
@@ -454,7 +467,8 @@ PGS_DEV uint32_t pack_head_varints(uint32_t shared, uint32_t ns, uint32_t vlen, 
 // order of two cursor heads as internal keys: user key ascending, then trailer (seq, type) descending, then run index.
 // Whole warp; by_byte = decided by a differing key byte at dpos (the LCP shortcut of the merge loop relies on that).
 template <uint32_t G>
-PGS_DEV bool head_before(const Grp<G> &g, bool en, const CurState *cs, const uint32_t *rows, uint32_t KSW, uint32_t a, uint32_t b, uint32_t &dpos, bool &by_byte)
+PGS_DEV bool head_before(const Grp<G> &g, bool en, const CurState *cs, const uint32_t *rows, uint32_t KSW, uint32_t a, uint32_t b, uint32_t &dpos, bool &by_byte,
+                         uint32_t from = 0) // from: leading bytes known to be equal
 {
     uint32_t la = 0, lb = 0;
     bool full = en; // the first eight bytes decide most of the time: two scalar compares, no collective
@@ -473,7 +487,7 @@ PGS_DEV bool head_before(const Grp<G> &g, bool en, const CurState *cs, const uin
         return ah != bh ? ah < bh : cs[a].kp_lo < cs[b].kp_lo;
     }
     uint32_t dfull = 0;
-    const int c = row_cmp(g, full, rows + a * KSW, la, rows + b * KSW, lb, dfull);
+    const int c = row_cmp(g, full, rows + a * KSW, la, rows + b * KSW, lb, dfull, from);
     if (!en) { by_byte = false; return false; }
     if (!full) {
         const uint32_t ah = cs[a].kp_hi, bh = cs[b].kp_hi;
@@ -607,6 +621,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
     uint32_t n_blocks = 0, keyb = 0, lenA = 0;
     unsigned long long out_bytes = 0;
     bool have_head = false, head_in_A = false, prev_big = false;
+    uint32_t hi_run = 0xffu, hi_l = 0, hi_ulen = 0; // the run whose last key was compared with the upper bound, and the bytes it shared with it
     uint32_t head_len = 0, last_run = 0xffu, lcpA = 0; // lcpA: bytes the head shares with A (the last survivor's key)
     uint32_t d1 = 0, prev_pl = 0xFFFFFFFFu;
     bool d1_valid = false;
@@ -636,6 +651,14 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         const bool cmp1 = act && have_head;
         const uint32_t *hrow = head_in_A ? rowA : rowB;
         if (cmp1 && last_run == c) { from = C->shared < ulen ? C->shared : ulen; if (from > head_len) from = head_len; }
+        else if (cmp1 && last_run != 0xffu && cs[last_run].live) {
+            // another run leads now: head <= this key <= the key the head's run moved on to, so this key shares with the
+            // head at least what that one does
+            const uint32_t ls = cs[last_run].shared, lu = cs[last_run].klen - 8;
+            from = ls < lu ? ls : lu;
+            if (from > ulen) from = ulen;
+            if (from > head_len) from = head_len;
+        }
         bool shadow = cmp1 && from == ulen && ulen == head_len;
         bool cmp1b = cmp1 && !shadow;
         if (cmp1b && last_run == c) {
@@ -791,18 +814,40 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         if (act && !err) err = e3;
         const bool adv = act && !err;
         bool alive = adv && C->live != 0;
+        // Upper bound of the segment.  The key before this one (same run) was below the bound and shared hi_l bytes with it: a
+        // key that shares more than hi_l bytes with its predecessor stands in the same relation; one that shares fewer rose
+        // above the bound at that byte (checked: a block writer may have stored less than the exact shared length).
         const bool hi = alive && !last && C->b >= C->chk_from;
-        if (g.any(hi)) { if (row_cmp(g, hi, row, hi ? C->klen - 8 : 0u, rowHI, uhi_len, dpos) > 0) alive = false; }
+        bool hi_cmp = hi;
+        uint32_t hi_from = 0;
+        if (hi && hi_run == c) {
+            const uint32_t sh_c = C->shared, ul = C->klen - 8;
+            // (`shared` counts internal-key bytes: it says something about user keys only inside the predecessor's user key)
+            if (sh_c > hi_l) { if (hi_l < hi_ulen) hi_cmp = false; }
+            else if (sh_c == hi_l) { if (hi_l <= ul) hi_from = hi_l; }
+            else if (sh_c < ul && ((row[sh_c >> 2] >> (8 * (sh_c & 3))) & 0xffu) > ((rowHI[sh_c >> 2] >> (8 * (sh_c & 3))) & 0xffu)) { alive = false; hi_cmp = false; }
+        }
+        if (g.any(hi_cmp)) {
+            uint32_t dp = 0;
+            const int ch = row_cmp(g, hi_cmp, row, hi_cmp ? C->klen - 8 : 0u, rowHI, uhi_len, dp, hi_from);
+            if (hi_cmp) { if (ch > 0) alive = false; else hi_l = dp; }
+        }
+        if (hi && alive) { hi_run = c; hi_ulen = C->klen - 8; } else if (hi_run == c) hi_run = 0xffu;
         // The key differs from the runner-up's at byte d1 < shared: the bytes up to d1 did not change, neither does the order.
         bool searching = adv && alive && live > 1 && !(d1_valid && C->shared > d1 && C->klen - 8 > d1);
+        // ... and what it shares with its predecessor and the predecessor shared with the runner-up, it shares with the runner-up
+        uint32_t from1 = 0;
+        if (searching && d1_valid) { from1 = C->shared < C->klen - 8 ? C->shared : C->klen - 8; if (from1 > d1) from1 = d1; }
         if (searching) d1_valid = false;
-        uint32_t pos = 0;
+        uint32_t pos = 0, d1n = 0;
+        bool d1n_valid = false;
         const bool reorder = searching;
 #pragma unroll 1
         for (uint32_t i = 1; g.any(searching && i < live); i++) {
             const bool e = searching && i < live;
-            const bool bf = head_before(g, e, cs, rows, KSW, c, ord_at(order, i), dpos, by_byte);
+            const bool bf = head_before(g, e, cs, rows, KSW, c, ord_at(order, i), dpos, by_byte, i == 1 ? from1 : 0u);
             if (e) {
+                if (i == 1) { d1n_valid = by_byte; d1n = dpos; } // what the key shares with the old runner-up
                 if (bf) { if (i == 1) { d1_valid = by_byte; d1 = dpos; } searching = false; }
                 else pos = i;
             }
@@ -814,6 +859,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
             last_run = 0xffu;
         } else if (reorder && pos > 0) {
             order = ord_head_to(order, pos);
+            if (pos == 1) { d1_valid = d1n_valid; d1 = d1n; } // the old runner-up leads, this key is its runner-up
         }
     }
     if (seg_en) {
@@ -1078,11 +1124,14 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
             }
         };
 
+        uint4 dn = make_uint4(0u, 0u, 0u, 0u); // the next batch's descriptors, fetched while this batch's values are copied
+        uint32_t dn_e0 = 0xFFFFFFFFu;
         for (uint32_t e0 = 0; e0 < A.n_entries && !err;) {
             const uint32_t idx = e0 + lane;
             Desc d;
             d.loc = 0; d.vlen = 0; d.aux = 0;
-            if (idx < A.n_entries) *reinterpret_cast<uint4 *>(&d) = *reinterpret_cast<const uint4 *>(&desc[idx]);
+            if (dn_e0 == e0) *reinterpret_cast<uint4 *>(&d) = dn;
+            else if (idx < A.n_entries) *reinterpret_cast<uint4 *>(&d) = *reinterpret_cast<const uint4 *>(&desc[idx]);
             const bool have = idx < A.n_entries;
             const uint32_t fl = (uint32_t)(d.loc >> 60), hl = (uint32_t)(d.loc >> 44) & 0xffffu, vl = d.vlen;
             const uint32_t first_fl = __shfl_sync(kFull, fl, 0);
@@ -1129,6 +1178,8 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
             const uint32_t cnt = (uint32_t)__popc(__ballot_sync(kFull, fits)); // monotone: lanes 0..cnt-1
             if (cnt == 0) { err = PGS_ABORTED; break; }
             const bool mine = lane < cnt;
+            dn_e0 = e0 + cnt;
+            dn = dn_e0 + lane < A.n_entries ? *reinterpret_cast<const uint4 *>(&desc[dn_e0 + lane]) : make_uint4(0u, 0u, 0u, 0u);
             const uint32_t total_s = __shfl_sync(kFull, ss_incl, (int)cnt - 1);
             {   // stage the batch's head-stream bytes
                 const uint8_t *src = heads + hpos;
