@@ -41,9 +41,9 @@ enum : uint32_t { DF_NEWBLOCK = 1, DF_REWRITE = 2, DF_BIG = 4 };
 
 // one per surviving record, written by k_walk, read by k_emit
 struct __align__(16) Desc {
-    unsigned long long loc; // bits 0..39 byte offset of the value inside its run, 40..43 run, 44..59 head bytes, 60..63 DF_*
+    unsigned long long loc; // bits 0..39 byte offset of the value inside its run, 40..43 run, 44..59 user-key bytes, 60..63 DF_*
     uint32_t vlen;          // value bytes to copy (0 for a tombstone)
-    uint32_t aux;           // DF_NEWBLOCK: length of the previous block's last user key (stored in the head stream before this head)
+    uint32_t aux;           // bytes the user key shares with the previous survivor of the segment
 };
 static_assert(sizeof(Desc) == 16, "Desc");
 
@@ -274,7 +274,7 @@ PGS_HD unsigned long long head_bound(unsigned long long n_in, unsigned long long
     const unsigned long long per_head = 15 + KS + 8 + 4; // varints | whole internal key | rewritten expire_ts
     unsigned long long blocks = 2 * (in_bytes + n_in * per_head) / block_size + 2;
     if (blocks > n_in + 1) blocks = n_in + 1;
-    return n_in * per_head + blocks * (unsigned long long)(KS + 8) + 64;
+    return (n_in * per_head + blocks * (unsigned long long)(KS + 8) + 64 + 15) & ~15ull; // key-stream records are stored as words
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -439,31 +439,6 @@ PGS_DEV uint32_t dev_filter(const MergeParams &P, const unsigned long long *crc_
 // ------------------------------------------------------------------------------------------------
 // k_walk
 // ------------------------------------------------------------------------------------------------
-// entry head, uncommon shape (a length that needs a multi-byte varint beyond the packed fast path): byte by byte, one lane
-static __device__ __noinline__ void emit_head_slow(uint8_t *hp, uint32_t shared, uint32_t kd, uint32_t vlen, const uint8_t *key, uint32_t tr_lo, uint32_t tr_hi)
-{
-    hp += put_varint32(hp, shared);
-    hp += put_varint32(hp, kd + 8);
-    hp += put_varint32(hp, vlen);
-    for (uint32_t i = 0; i < kd; i++) hp[i] = key[shared + i];
-    hp += kd;
-    for (uint32_t i = 0; i < 4; i++) { hp[i] = (uint8_t)(tr_lo >> (8 * i)); hp[4 + i] = (uint8_t)(tr_hi >> (8 * i)); }
-}
-// the three varints of an entry head packed into (lo, hi) when shared < 128, non_shared < 128 and value_len < 2^21 (the common
-// shape, at most 5 bytes); returns their length, 0 = does not apply
-PGS_DEV uint32_t pack_head_varints(uint32_t shared, uint32_t ns, uint32_t vlen, uint32_t &lo, uint32_t &hi)
-{
-    if ((shared | ns) >= 128u || vlen >= (1u << 21)) return 0;
-    lo = shared | (ns << 8);
-    hi = 0;
-    if (vlen < 128u) { lo |= vlen << 16; return 3; }
-    lo |= ((vlen & 127u) | 128u) << 16;
-    if (vlen < 16384u) { lo |= (vlen >> 7) << 24; return 4; }
-    lo |= (((vlen >> 7) & 127u) | 128u) << 24;
-    hi = vlen >> 14;
-    return 5;
-}
-
 // order of two cursor heads as internal keys: user key ascending, then trailer (seq, type) descending, then run index.
 // Whole warp; by_byte = decided by a differing key byte at dpos (the LCP shortcut of the merge loop relies on that).
 template <uint32_t G>
@@ -623,7 +598,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
     bool have_head = false, head_in_A = false, prev_big = false;
     uint32_t hi_run = 0xffu, hi_l = 0, hi_ulen = 0; // the run whose last key was compared with the upper bound, and the bytes it shared with it
     uint32_t head_len = 0, last_run = 0xffu, lcpA = 0; // lcpA: bytes the head shares with A (the last survivor's key)
-    uint32_t d1 = 0, prev_pl = 0xFFFFFFFFu;
+    uint32_t d1 = 0;
     bool d1_valid = false;
     auto close_block = [&]() { // bookkeeping of a finished block (k_emit derives the same numbers)
         const uint32_t size = blk_bytes + 4 * (nrest + 1);
@@ -698,80 +673,40 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         bool restart = to_restart == 0;
         const uint32_t lcp_KA = !have_head ? 0u : head_in_A ? lcp_head : (lcp_head < lcpA ? lcp_head : lcpA);
         uint32_t shared = keep && !restart ? lcp_KA : 0u;
-        if (P.out_bloom_lines) { // the new run's Bloom filter: the user key, and its hash-key prefix when that changed
-            const bool lcp_known = keep && have_head;
-            const uint32_t lcp_out = lcp_KA;
-            const unsigned long long hk = bloom_hash_row(g, row, keep ? ulen : 0u);
-            if (keep) {
-#pragma unroll
-                for (uint32_t i = g.gl; i < 6; i += G) bloom_add_bit(P.out_bloom, P.out_bloom_lines, hk, i);
-            }
-            const uint32_t pl = keep ? hashkey_prefix_len((const uint8_t *)row, ulen) : 0u;
-            const bool new_prefix = keep && pl && !(lcp_known && pl == prev_pl && lcp_out >= pl);
-            if (g.any(new_prefix)) {
-                const unsigned long long hp = bloom_hash_row(g, row, new_prefix ? pl : 0u);
-                if (new_prefix) {
-#pragma unroll
-                    for (uint32_t i = g.gl; i < 6; i += G) bloom_add_bit(P.out_bloom, P.out_bloom_lines, hp, i);
-                }
-            }
-            if (keep) { prev_pl = pl; ev |= 1u << EV_BLOOM_KEY; if (new_prefix) ev |= 1u << EV_BLOOM_PREFIX; }
-        }
         if (keep) {
             const uint32_t otype = tomb ? (uint32_t)PGS_TYPE_DELETION : type;
             const bool zero_seq = P.bottommost && otype == PGS_TYPE_VALUE;
             const uint32_t otr_lo = zero_seq ? otype : ((tr_lo & ~0xffu) | otype), otr_hi = zero_seq ? 0u : tr_hi;
             if (vlen_out > 0xFFF00000u) err = PGS_NOT_SUPPORTED; // entry sizes are 32-bit below
-            uint32_t kd = ulen - shared, hv_lo, hv_hi;
-            uint32_t hv = pack_head_varints(shared, kd + 8, vlen_out, hv_lo, hv_hi);
-            uint32_t hvl = hv ? hv : varint_len(shared) + varint_len(kd + 8) + varint_len(vlen_out);
-            uint32_t e = hvl + kd + 8 + vlen_out;
-            uint32_t flags = 0, aux = 0;
+            uint32_t kd = ulen - shared;
+            uint32_t e = varint_len(shared) + varint_len(kd + 8) + varint_len(vlen_out) + kd + 8 + vlen_out;
+            uint32_t flags = 0;
             // block cut: the entry (and the restart array it may extend) must fit the block
             if (blk_n > 0 && (prev_big || blk_bytes + e + 4 * (nrest + (restart ? 1u : 0u) + 1) > BS)) {
                 close_block();
                 blk_n = 0; blk_bytes = 0; nrest = 0;
                 restart = true; shared = 0; kd = ulen;
-                hv = pack_head_varints(0, kd + 8, vlen_out, hv_lo, hv_hi);
-                hvl = hv ? hv : 1 + varint_len(kd + 8) + varint_len(vlen_out);
-                e = hvl + kd + 8 + vlen_out;
+                e = 1 + varint_len(kd + 8) + varint_len(vlen_out) + kd + 8 + vlen_out;
             }
-            if (blk_n == 0) {
-                flags |= DF_NEWBLOCK;
-                if (n_out > 0) { // the finished block's last user key travels in the head stream
-                    aux = lenA;
-#pragma unroll 1
-                    for (uint32_t i = g.gl; i < lenA; i += G) heads[hpos + i] = ((const uint8_t *)rowA)[i];
-                    hpos += lenA;
-                }
-            }
+            if (blk_n == 0) flags |= DF_NEWBLOCK;
             const bool big = e + 8 > P.blk_buf; // does not fit the block buffer of k_emit: a block of its own, written in place
             if (big) flags |= DF_BIG;
-            if (rewrite) {
-                flags |= DF_REWRITE;
+            if (rewrite) flags |= DF_REWRITE;
+            // the survivor's record in the key stream: trailer | [new expire_ts] | the whole user key, padded to 4 bytes
+            // (k_emit builds the entry head, the index key and the Bloom filter bits from it, one thread per entry)
+            uint32_t *sp = reinterpret_cast<uint32_t *>(heads + hpos);
+            const uint32_t fixed = rewrite ? 3u : 2u;
 #pragma unroll
-                for (uint32_t i = g.gl; i < 4; i += G) heads[hpos + i] = (uint8_t)(nts >> (8 * (3 - i))); // BE32
-                hpos += 4;
-            }
-            // the entry head: varints | key delta | trailer
-            uint8_t *hp = heads + hpos;
-            if (hv) {
+            for (uint32_t i = g.gl; i < 3; i += G)
+                if (i < fixed) sp[i] = i == 0 ? otr_lo : i == 1 ? otr_hi : __byte_perm(nts, 0, 0x0123); // BE32 in memory
 #pragma unroll 1
-                for (uint32_t i = g.gl; i < hv; i += G) hp[i] = (uint8_t)__byte_perm(hv_lo, hv_hi, i);
-#pragma unroll 1
-                for (uint32_t i = g.gl; i < kd; i += G) hp[hv + i] = ((const uint8_t *)row)[shared + i];
-#pragma unroll
-                for (uint32_t i = g.gl; i < 8; i += G) hp[hv + kd + i] = (uint8_t)__byte_perm(otr_lo, otr_hi, i);
-            } else if (g.gl == 0) {
-                emit_head_slow(hp, shared, kd, vlen_out, (const uint8_t *)row, otr_lo, otr_hi);
-            }
-            const uint32_t hl = hvl + kd + 8;
-            hpos += hl;
+            for (uint32_t w = g.gl; 4 * w < ulen; w += G) sp[fixed + w] = row[w];
+            hpos += 4 * fixed + ((ulen + 3) & ~3u);
             if (g.gl == 0) {
                 Desc d;
-                d.loc = (cur_base(C) + C->voff) | ((unsigned long long)c << 40) | ((unsigned long long)hl << 44) | ((unsigned long long)flags << 60);
+                d.loc = (cur_base(C) + C->voff) | ((unsigned long long)c << 40) | ((unsigned long long)ulen << 44) | ((unsigned long long)flags << 60);
                 d.vlen = vlen_out;
-                d.aux = aux;
+                d.aux = lcp_KA;
                 *reinterpret_cast<uint4 *>(&desc[n_out]) = *reinterpret_cast<const uint4 *>(&d);
             }
             n_out++;
@@ -863,12 +798,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         }
     }
     if (seg_en) {
-        if (!err && blk_n > 0) {
-            close_block();
-#pragma unroll 1
-            for (uint32_t i = g.gl; i < lenA; i += G) heads[hpos + i] = ((const uint8_t *)rowA)[i];
-            hpos += lenA;
-        }
+        if (!err && blk_n > 0) close_block();
         if (err) {
             if (g.gl == 0) { atomicMax(&P.stats->error, err); atomicMin(&P.stats->error_seg, q); }
             n_out = 0; n_blocks = 0; keyb = 0; out_bytes = 0; hpos = 0; lenA = 0;
@@ -1057,11 +987,33 @@ PGS_DEV void thread_copy_g2s(uint8_t *obuf16, uint32_t doff, const uint8_t *src,
     }
 }
 
+// the Bloom hash of a key held as 32-bit words (4-byte aligned, any address space), one thread: same function as bloom_hash_row
+PGS_DEV unsigned long long bloom_hash_words(const uint32_t *w32, uint32_t len)
+{
+    uint32_t ha = 0, hb = 0;
+#pragma unroll 1
+    for (uint32_t w = 0; 4 * w < len; w++) {
+        uint32_t x = w32[w];
+        if (len - 4 * w < 4) x &= (1u << (8 * (len - 4 * w))) - 1u;
+        bloom_word(x, w, ha, hb);
+    }
+    return bloom_finish(ha, hb, len);
+}
+PGS_DEV uint32_t put_varint32_s(uint8_t *p, uint32_t v) // shared-memory / generic byte stores
+{
+    uint32_t n = 0;
+    while (v >= 128u) { p[n++] = (uint8_t)(v | 128u); v >>= 7; }
+    p[n++] = (uint8_t)v;
+    return n;
+}
+
 // k_emit: one warp per segment, one THREAD per entry.  A batch of up to 32 descriptors is laid out with warp scans (block
-// membership, offsets inside the block, block starts, restart points), every thread copies its entry's head and value into the
-// warp's output buffer, the threads standing on a block boundary finish the previous block (restart array, padding, index
-// entry), and the batch's bytes leave with one bulk TMA store.  Blocks of a segment are adjacent in the output run, so a
-// batch's bytes are one contiguous range; the partial 16-byte chunk at its end is carried into the next batch.
+// membership, restart points, entry sizes, offsets inside the block, block starts); every thread builds its entry's head from
+// its key-stream record (varints | key bytes after the shared prefix | trailer), copies the value into the warp's output
+// buffer and adds the key (and a new hash-key prefix) to the run's Bloom filter; the threads standing on a block boundary
+// finish the previous block (restart array, padding, index entry); the batch's bytes leave with one bulk TMA store.  Blocks
+// of a segment are adjacent in the output run, so a batch's bytes are one contiguous range; the partial 16-byte chunk at its
+// end is carried into the next batch.
 __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant__ MergeParams P)
 {
     PGS_SMEM_DYN(dyn);
@@ -1069,9 +1021,10 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
     const uint32_t RI = P.restart_interval, OB = P.emit_obuf;
     uint8_t *ws = dyn + (size_t)warp * P.emit_warp_smem;
     uint8_t *obuf = ws;                                          // OB + 32 bytes
-    uint8_t *hst = obuf + OB + 32;                               // head_stage + 32 bytes: the head-stream bytes of a batch
+    uint8_t *hst = obuf + OB + 32;                               // head_stage + 32 bytes: the key-stream records of a batch
     uint32_t *rst = (uint32_t *)(hst + P.head_stage + 32);       // restart offsets of the open block (it may span batches)
     const uint32_t lt = (1u << lane) - 1u;                       // lanes before me
+    uint32_t n_bloom_keys = 0, n_bloom_prefixes = 0;             // lane 0 counts what the warp added to the filter
 
     for (;;) {
         uint32_t q = 0;
@@ -1089,6 +1042,7 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
         bool open = false;
         uint32_t blk_idx = B.blocks, rec_idx = B.recs, keyb = B.keyb, hpos = 0, err = 0;
         uint32_t carry = 0; // obuf[0, carry) = the bytes of the partial 16-byte chunk in front of the write position
+        uint32_t last_key_off = 0, last_ulen = 0; // the previous entry's user key in the key stream (the index key of a block it ends)
 
         // finish the open block outside a batch (whole warp): restart array (offsets kept in rst), count and padding go to `at`
         // (where byte `fill` of the block lives: obuf + carry, or global memory for a block written in place), index entry
@@ -1123,6 +1077,21 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
                 __syncwarp();
             }
         };
+        // one thread: the key (and its hash-key prefix when the previous survivor did not share it) goes into the filter
+        auto bloom_add = [&](const uint32_t *key32, uint32_t ulen, uint32_t lcp, bool &new_prefix) {
+            new_prefix = false;
+            if (!P.out_bloom_lines) return;
+            const unsigned long long hk = bloom_hash_words(key32, ulen);
+#pragma unroll
+            for (uint32_t i = 0; i < 6; i++) bloom_add_bit(P.out_bloom, P.out_bloom_lines, hk, i);
+            const uint32_t pl = hashkey_prefix_len((const uint8_t *)key32, ulen);
+            if (pl && lcp < pl) {
+                new_prefix = true;
+                const unsigned long long hp = bloom_hash_words(key32, pl);
+#pragma unroll
+                for (uint32_t i = 0; i < 6; i++) bloom_add_bit(P.out_bloom, P.out_bloom_lines, hp, i);
+            }
+        };
 
         uint4 dn = make_uint4(0u, 0u, 0u, 0u); // the next batch's descriptors, fetched while this batch's values are copied
         uint32_t dn_e0 = 0xFFFFFFFFu;
@@ -1133,70 +1102,86 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
             if (dn_e0 == e0) *reinterpret_cast<uint4 *>(&d) = dn;
             else if (idx < A.n_entries) *reinterpret_cast<uint4 *>(&d) = *reinterpret_cast<const uint4 *>(&desc[idx]);
             const bool have = idx < A.n_entries;
-            const uint32_t fl = (uint32_t)(d.loc >> 60), hl = (uint32_t)(d.loc >> 44) & 0xffffu, vl = d.vlen;
+            const uint32_t fl = (uint32_t)(d.loc >> 60), ulen = (uint32_t)(d.loc >> 44) & 0xffffu, vl = d.vlen, lcp = d.aux;
             const uint32_t first_fl = __shfl_sync(kFull, fl, 0);
             if (first_fl & DF_BIG) {
                 // ---- an entry larger than a block buffer: a block of its own, written in place by the whole warp ---------------
                 const unsigned long long loc = __shfl_sync(kFull, d.loc, 0);
-                const uint32_t bvl = __shfl_sync(kFull, vl, 0), bhl = __shfl_sync(kFull, hl, 0), baux = __shfl_sync(kFull, d.aux, 0);
+                const uint32_t bvl = __shfl_sync(kFull, vl, 0), bul = __shfl_sync(kFull, ulen, 0), blcp = __shfl_sync(kFull, lcp, 0);
                 const uint32_t bfl = first_fl;
-                const uint8_t *hs = heads + hpos; // its head-stream bytes, read straight from global memory
-                uint32_t so = baux; // the previous block's last user key (nothing in front of the segment's first entry)
+                const uint32_t *rec = reinterpret_cast<const uint32_t *>(heads + hpos); // its key-stream record, read from global memory
+                const uint32_t fixed = (bfl & DF_REWRITE) ? 12u : 8u;
+                const uint8_t *key = (const uint8_t *)rec + fixed;
                 if (open) { // finish the block in front of it; what that block still has in obuf leaves with it
                     const unsigned long long obase = blk_start + fill - carry;
-                    close_open(hs, baux, obuf + carry, (blk_n + RI - 1) / RI);
+                    close_open(heads + last_key_off, last_ulen, obuf + carry, (blk_n + RI - 1) / RI);
                     flush(obase, (uint32_t)(blk_start - obase));
                     carry = 0;
                 }
-                const uint8_t *ntsb = hs + so;
-                if (bfl & DF_REWRITE) so += 4;
                 const uint8_t *vsrc = P.runs[(uint32_t)(loc >> 40) & 15u].data + (loc & ((1ull << 40) - 1));
                 uint8_t *o = P.out_data + blk_start;
-                for (uint32_t x = lane; x < bhl; x += 32) o[x] = hs[so + x];
+                uint32_t hv = 0;
+                if (lane == 0) { // a restart point: nothing shared
+                    hv = put_varint32_s(o, 0u);
+                    hv += put_varint32_s(o + hv, bul + 8);
+                    hv += put_varint32_s(o + hv, bvl);
+                    bool np;
+                    bloom_add(reinterpret_cast<const uint32_t *>(key), bul, blcp, np);
+                    n_bloom_keys += P.out_bloom_lines ? 1u : 0u;
+                    n_bloom_prefixes += np ? 1u : 0u;
+                }
+                hv = __shfl_sync(kFull, hv, 0);
+                const uint32_t bhl = hv + bul + 8;
+                for (uint32_t x = lane; x < bul; x += 32) o[hv + x] = key[x];
+                if (lane < 8) o[hv + bul + lane] = ((const uint8_t *)rec)[lane]; // trailer
                 for (uint32_t x = lane; x < bvl; x += 32) o[bhl + x] = vsrc[x];
-                if ((bfl & DF_REWRITE) && bvl >= 4 && lane < 4) o[bhl + lane] = ntsb[lane];
+                if ((bfl & DF_REWRITE) && bvl >= 4 && lane < 4) o[bhl + lane] = ((const uint8_t *)rec)[8 + lane];
                 if (lane == 0) { rst[0] = 0; P.out_rec_off[rec_idx] = 0; }
-                // the block's last user key is this entry's: it travels in front of the next entry's head, or ends the stream
-                const uint32_t sbytes = so + bhl;
-                const bool last_e = e0 + 1 == A.n_entries;
-                const uint32_t klen = last_e ? A.last_klen : __shfl_sync(kFull, d.aux, 1);
-                const uint8_t *key = last_e ? heads + A.head_bytes - A.last_klen : hs + sbytes;
                 fill = bhl + bvl; blk_n = 1; blk_rec0 = rec_idx; open = true;
-                close_open(key, klen, o + fill, 1u);
-                rec_idx++; hpos += sbytes; e0++;
+                close_open(key, bul, o + fill, 1u); // the block's last user key is this entry's
+                last_key_off = hpos + fixed; last_ulen = bul;
+                rec_idx++; hpos += fixed + ((bul + 3) & ~3u); e0++;
                 continue;
             }
-            // ---- batch = the entries before the first oversized one that fit the output buffer and the head stage --------
-            const uint32_t sz = have ? hl + vl : 0u;
-            const uint32_t sb = have ? hl + ((fl & DF_NEWBLOCK) ? d.aux : 0u) + ((fl & DF_REWRITE) ? 4u : 0u) : 0u;
-            const uint32_t ps_incl = warp_incl_scan(sz, lane), ss_incl = warp_incl_scan(sb, lane);
+            // ---- layout, part 1: block membership and restart points follow from the flags alone ------------------------------------
             const uint32_t bigmask = __ballot_sync(kFull, have && (fl & DF_BIG));
+            const bool cand = have && !(bigmask & (lt | (1u << lane)));       // before the first oversized entry
+            const uint32_t hm_all = __ballot_sync(kFull, cand && (fl & DF_NEWBLOCK));
+            const uint32_t at_or_before = hm_all & (lt | (1u << lane)), before = hm_all & lt;
+            const int h = at_or_before ? 31 - __clz((int)at_or_before) : -1;  // the block I belong to starts at lane h (-1: the carried block)
+            const int ph = before ? 31 - __clz((int)before) : -1;              // the head before me
+            const uint32_t n_i = h >= 0 ? lane - (uint32_t)h : blk_n + lane;   // my index inside my block
+            const bool is_restart = n_i % RI == 0;
+            const uint32_t sh_out = is_restart ? 0u : (lcp < ulen ? lcp : ulen);
+            const uint32_t kd = ulen - sh_out;
+            const uint32_t hvl = varint_len(sh_out) + varint_len(kd + 8) + varint_len(vl);
+            const uint32_t hl = hvl + kd + 8;
+            // ---- batch = the entries before the first oversized one that fit the output buffer and the stage -------------------------
+            const uint32_t sz = cand ? hl + vl : 0u;
+            const uint32_t sb = cand ? ((fl & DF_REWRITE) ? 12u : 8u) + ((ulen + 3) & ~3u) : 0u; // my key-stream record
+            const uint32_t ps_incl = warp_incl_scan(sz, lane), ss_incl = warp_incl_scan(sb, lane);
             // room: the entries, the restart arrays and paddings of the blocks that close here (the carried block brings its
             // earlier restart points along), the carried partial chunk
             const uint32_t room = carry + 32 * (lane + 1) + 64 + (open ? 4 * ((blk_n + RI - 1) / RI) : 0u);
-            const bool fits = have && !(bigmask & (lt | (1u << lane))) && room + ps_incl <= OB && ss_incl <= P.head_stage;
+            const bool fits = cand && room + ps_incl <= OB && ss_incl <= P.head_stage;
             const uint32_t cnt = (uint32_t)__popc(__ballot_sync(kFull, fits)); // monotone: lanes 0..cnt-1
             if (cnt == 0) { err = PGS_ABORTED; break; }
             const bool mine = lane < cnt;
             dn_e0 = e0 + cnt;
             dn = dn_e0 + lane < A.n_entries ? *reinterpret_cast<const uint4 *>(&desc[dn_e0 + lane]) : make_uint4(0u, 0u, 0u, 0u);
             const uint32_t total_s = __shfl_sync(kFull, ss_incl, (int)cnt - 1);
-            {   // stage the batch's head-stream bytes
+            {   // stage the batch's key-stream records
                 const uint8_t *src = heads + hpos;
                 const uint32_t a = (uint32_t)((uintptr_t)src & 15);
                 for (uint32_t i = lane * 16; i < a + total_s; i += 512) async_copy16(hst + i, src - a + i);
                 async_copy_commit();
             }
-            // ---- layout: block membership, offsets, block starts ----------------------------------------------------------------
+            // ---- layout, part 2: offsets, block starts -------------------------------------------------------------------------------
+            const uint32_t hm = cnt >= 32 ? hm_all : hm_all & ((1u << cnt) - 1u);
             const bool head = mine && (fl & DF_NEWBLOCK);
-            const uint32_t hm = __ballot_sync(kFull, head);
-            const uint32_t at_or_before = hm & (lt | (1u << lane)), before = hm & lt;
-            const int h = at_or_before ? 31 - __clz((int)at_or_before) : -1;  // the block I belong to starts at lane h (-1: the carried block)
-            const int ph = before ? 31 - __clz((int)before) : -1;              // the head before me
             const uint32_t ps = ps_incl - sz;                                   // entry bytes of the batch before me
             const uint32_t ps_h = __shfl_sync(kFull, ps, h >= 0 ? h : 0), ps_ph = __shfl_sync(kFull, ps, ph >= 0 ? ph : 0);
             const uint32_t fill_i = h >= 0 ? ps - ps_h : fill + ps;            // my offset inside my block
-            const uint32_t n_i = h >= 0 ? lane - (uint32_t)h : blk_n + lane;   // my index inside my block
             // a head closes the block before it (if there is one): its entry bytes, entry count, aligned size
             const bool closes = head && (ph >= 0 || open);
             const uint32_t T = ph >= 0 ? ps - ps_ph : fill + ps, NN = ph >= 0 ? lane - (uint32_t)ph : blk_n + lane;
@@ -1207,7 +1192,12 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
             const uint32_t S_h = __shfl_sync(kFull, S_incl, h >= 0 ? h : 0);
             const uint32_t base_i = h >= 0 ? S_h : 0u;                          // start of my block relative to blk_start
             const uint32_t nclose_incl = (uint32_t)__popc(__ballot_sync(kFull, closes) & (lt | (1u << lane)));
-            const uint32_t kb_incl = warp_incl_scan(closes ? d.aux : 0u, lane); // index-key bytes of the blocks closed at or before me
+            // the index key of the block a head closes = the user key of the entry before it
+            const uint32_t rec_off_i = ss_incl - sb;                            // my record inside the stage
+            const uint32_t key_off_i = rec_off_i + ((fl & DF_REWRITE) ? 12u : 8u);
+            const uint32_t pk_off = __shfl_up_sync(kFull, key_off_i, 1), pk_len_l = __shfl_up_sync(kFull, ulen, 1);
+            const uint32_t pk_len = lane == 0 ? last_ulen : pk_len_l;
+            const uint32_t kb_incl = warp_incl_scan(closes ? pk_len : 0u, lane); // index-key bytes of the blocks closed at or before me
             // obuf[0] corresponds to the global offset obase
             const unsigned long long obase = blk_start + fill - carry;
             const uint32_t o_i = (uint32_t)(blk_start + base_i + fill_i - obase); // my entry's offset in obuf
@@ -1218,27 +1208,35 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
             const uint32_t after = hm & ~(lt | (1u << lane));
             const int nh = after ? __ffs((int)after) - 1 : -1;                   // the head that closes my block inside this batch
             const uint32_t T_mine = __shfl_sync(kFull, T, nh >= 0 ? nh : 0);    // my block's entry bytes, when it closes here
-            const bool is_restart = mine && (n_i % RI == 0);
             const uint32_t r_i = n_i / RI;
-            if (is_restart) {
+            if (mine && is_restart) {
                 if (nh >= 0) { // the restart array of my block is assembled in this batch
                     const uint32_t ro = (uint32_t)(blk_start + base_i - obase) + T_mine + 4 * r_i;
                     obuf[ro] = (uint8_t)fill_i; obuf[ro + 1] = (uint8_t)(fill_i >> 8); obuf[ro + 2] = (uint8_t)(fill_i >> 16); obuf[ro + 3] = (uint8_t)(fill_i >> 24);
                 } else rst[r_i] = fill_i;
             }
             if (mine) P.out_rec_off[rec_idx + lane] = fill_i;
-            // ---- copy: one thread per entry ---------------------------------------------------------------------------------------------
+            // ---- one thread per entry: head, value, filter bits ---------------------------------------------------------------------------
+            bool new_prefix = false;
             if (mine) {
-                uint32_t so = ss_incl - sb;
-                if (fl & DF_NEWBLOCK) so += d.aux;
-                const uint8_t *ntsb = hs + so;
-                if (fl & DF_REWRITE) so += 4;
+                const uint8_t *rec = hs + rec_off_i;
+                const uint8_t *key = hs + key_off_i;
                 uint8_t *dst = obuf + o_i;
+                uint32_t p = put_varint32_s(dst, sh_out);
+                p += put_varint32_s(dst + p, kd + 8);
+                p += put_varint32_s(dst + p, vl);
 #pragma unroll 1
-                for (uint32_t x = 0; x < hl; x++) dst[x] = hs[so + x];
+                for (uint32_t x = 0; x < kd; x++) dst[p + x] = key[sh_out + x];
+#pragma unroll
+                for (uint32_t x = 0; x < 8; x++) dst[p + kd + x] = rec[x];
                 const RunDev &r = P.runs[(uint32_t)(d.loc >> 40) & 15u];
                 thread_copy_g2s(obuf, o_i + hl, r.data + (d.loc & ((1ull << 40) - 1)), vl, r.data);
-                if ((fl & DF_REWRITE) && vl >= 4) { dst[hl] = ntsb[0]; dst[hl + 1] = ntsb[1]; dst[hl + 2] = ntsb[2]; dst[hl + 3] = ntsb[3]; }
+                if ((fl & DF_REWRITE) && vl >= 4) { dst[hl] = rec[8]; dst[hl + 1] = rec[9]; dst[hl + 2] = rec[10]; dst[hl + 3] = rec[11]; }
+                bloom_add(reinterpret_cast<const uint32_t *>(key), ulen, lcp, new_prefix);
+            }
+            {
+                const uint32_t np = (uint32_t)__popc(__ballot_sync(kFull, new_prefix));
+                if (P.out_bloom_lines) { n_bloom_keys += cnt; n_bloom_prefixes += np; }
             }
             __syncwarp();
             // ---- the heads finish the blocks that end in front of them --------------------------------------------------------------
@@ -1247,25 +1245,24 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
                 // the carried block's earlier restart offsets (from previous batches) go in front of this batch's
                 const bool carried_closes = open && first_close < 32;
                 if (carried_closes) {
-                    const uint32_t Tc = __shfl_sync(kFull, T, (int)first_close), NNc = __shfl_sync(kFull, NN, (int)first_close);
+                    const uint32_t Tc = __shfl_sync(kFull, T, (int)first_close);
                     const uint32_t have_r = (blk_n + RI - 1) / RI; // restart points recorded before this batch
                     const uint32_t ro = (uint32_t)(blk_start - obase) + Tc;
                     for (uint32_t i = lane; i < 4 * have_r; i += 32) obuf[ro + i] = (uint8_t)(rst[i >> 2] >> (8 * (i & 3)));
-                    (void)NNc;
                 }
                 if (closes) {
                     const uint32_t bstart = (uint32_t)(blk_start - obase) + (S_incl - asz_c); // obuf offset of the block I close
                     uint32_t p = bstart + T + 4 * nrest_c;
                     obuf[p] = (uint8_t)nrest_c; obuf[p + 1] = (uint8_t)(nrest_c >> 8); obuf[p + 2] = (uint8_t)(nrest_c >> 16); obuf[p + 3] = (uint8_t)(nrest_c >> 24);
                     for (p += 4; p < bstart + asz_c; p++) obuf[p] = 0;
-                    const uint32_t bi = blk_idx + nclose_incl - 1, ko = keyb + kb_incl - d.aux;
+                    const uint32_t bi = blk_idx + nclose_incl - 1, ko = keyb + kb_incl - pk_len;
                     P.out_blk_off[bi] = blk_start + (S_incl - asz_c);
                     P.out_blk_size[bi] = size_c;
                     P.out_blk_rec[bi] = ph >= 0 ? rec_idx + (uint32_t)ph : blk_rec0;
                     P.out_ikey_off[bi] = ko;
-                    const uint8_t *key = hs + (ss_incl - sb); // the closed block's last user key travels in front of my head
+                    const uint8_t *pk = lane == 0 ? heads + last_key_off : hs + pk_off; // the entry before me: staged, or the last one of the batch before
 #pragma unroll 1
-                    for (uint32_t x = 0; x < d.aux; x++) P.out_ikeys[ko + x] = key[x];
+                    for (uint32_t x = 0; x < pk_len; x++) P.out_ikeys[ko + x] = pk[x];
                 }
             }
             // ---- carry the state over, flush ------------------------------------------------------------------------------------------------
@@ -1275,6 +1272,8 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
             const int l_h = __shfl_sync(kFull, h, (int)lastl);
             const uint32_t n_closed = (uint32_t)__popc(__ballot_sync(kFull, closes));
             const uint32_t kb_total = __shfl_sync(kFull, kb_incl, 31);
+            last_key_off = hpos + __shfl_sync(kFull, key_off_i, (int)lastl);
+            last_ulen = __shfl_sync(kFull, ulen, (int)lastl);
             if (l_h >= 0) blk_rec0 = rec_idx + (uint32_t)l_h;
             blk_start += l_base; fill = l_fill; blk_n = l_n; open = true;
             blk_idx += n_closed; keyb += kb_total; rec_idx += cnt; hpos += total_s; e0 += cnt;
@@ -1289,14 +1288,18 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
         }
         if (!err && open) { // the segment's last block
             const unsigned long long obase = blk_start + fill - carry;
-            close_open(heads + A.head_bytes - A.last_klen, A.last_klen, obuf + carry, (blk_n + RI - 1) / RI);
+            close_open(heads + last_key_off, last_ulen, obuf + carry, (blk_n + RI - 1) / RI);
             flush(obase, (uint32_t)(blk_start - obase));
             carry = 0;
         }
         if (!err && (blk_start != B.bytes + A.out_bytes || blk_idx != B.blocks + A.n_blocks || keyb != B.keyb + A.keyb)) err = PGS_CORRUPTION; // the two passes disagree
         if (err && lane == 0) { atomicMax(&P.stats->error, err); atomicMin(&P.stats->error_seg, q); }
     }
-    if (lane == 0) tma_store_wait_all();
+    if (lane == 0) {
+        tma_store_wait_all();
+        if (n_bloom_keys) atomicAdd(&P.stats->cnt[EV_BLOOM_KEY], (unsigned long long)n_bloom_keys);
+        if (n_bloom_prefixes) atomicAdd(&P.stats->cnt[EV_BLOOM_PREFIX], (unsigned long long)n_bloom_prefixes);
+    }
 }
 
 } // namespace pgs

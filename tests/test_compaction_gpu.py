@@ -175,3 +175,31 @@ def test_large_partition_properties(pgs, oracle, engine):
         assert info.max_block_size < 2 * 4096 + 512 and info.n_records == got.n
     finally:
         part.close()
+
+
+def test_bench_size_digest(pgs, oracle, engine):
+    """BASELINE configs[1] at full size, the data set bench.py times (4 x 2.5 M records, seed 1000): the decoded output and
+    every statistic equal the oracle's; compared through a digest of the flat arrays and the arrays themselves."""
+    import hashlib
+    runs = synth.compaction_runs(k=4, n_per_run=2_500_000, hk_len=16, sk_len=32, user_len=256, now=300_000_000, seed=1000)
+    part = engine.partition()
+    try:
+        ids = part.upload_many([pgs.build_run(r) for r in runs])
+        res = part.compact(ids, out_level=1, bottommost=1, now=300_000_000, enabled=True)
+        got = pgs.decode_blocks(part.download(res.new_run_id))
+        bruns = [oracle.BlockRunCPU.from_run(oracle.Run.from_records(r)) for r in runs]
+        want_b, st, _ = oracle.compact_blocks(bruns, True, oracle.filter_params(enabled=True), 300_000_000, threads=16)
+        want = want_b.decode().records()
+        for f in ("in_records", "out_records", "in_bytes", "out_bytes", "dropped_shadowed", "dropped_tombstone", "dropped_expired",
+                  "dropped_user", "dropped_stale", "ttl_rewritten"):
+            assert getattr(res, f) == getattr(st, f), f
+
+        def digest(r):
+            h = hashlib.blake2b(digest_size=16)
+            for a in (r.key_off, r.keys, r.val_off, r.vals, r.seq, r.type):
+                h.update(np.ascontiguousarray(a).view(np.uint8).data)
+            return h.hexdigest()
+        assert got.n == want.n == res.out_records == 8_240_347  # the survivor count of this seed (BENCH_r01.json)
+        assert digest(got) == digest(want)
+    finally:
+        part.close()
