@@ -566,6 +566,7 @@ def main():
             g_wall.append((time.perf_counter() - t0) * 1e3)
             g_ms.append(eng.last_kernel_ms)
             probes = eng.last_blocks_probed
+            skipped = eng.last_runs_skipped
         found = sum(1 for i in range(args.n_get) if gres[i].status == 0)
         # prefix scans = multi_get(hash_key, all sort keys)
         sb = part.prefix_scan_batch(hashkeys, max_records=80, arena_stride=24576, alloc=pinned_alloc)  # request structs marshalled once
@@ -610,7 +611,7 @@ def main():
             "statistic": "mean over the repetitions, for the device (kernel CUDA events) and the e2e (host wall clock) numbers alike",
             "get": {"metric": "get_keys_per_s", "value": float(vals[0]), "e2e": float(vals[1]), "unit": "keys/s", "batch": args.n_get,
                     "kernel_ms": gm, "e2e_ms": gw, "found_frac": found / args.n_get, "blocks_probed_per_key": probes / args.n_get,
-                    "bloom_runs_skipped_per_key": eng.last_runs_skipped / args.n_get if hasattr(eng, "last_runs_skipped") else None,
+                    "bloom_runs_skipped_per_key": skipped / args.n_get,
                     "roofline": roof("k_get", get_algo, gm)},
             "scan": {"metric": "scan_keys_per_s", "value": float(vals[2]), "e2e": float(vals[3]), "unit": "keys/s", "requests": args.n_scan,
                      "returned_per_launch": returned, "iterated_per_launch": iterated, "kernel_ms": sm, "e2e_ms": sw, "d2h_bytes": scan_bytes,

@@ -439,43 +439,6 @@ PGS_DEV uint32_t dev_filter(const MergeParams &P, const unsigned long long *crc_
 // ------------------------------------------------------------------------------------------------
 // k_walk
 // ------------------------------------------------------------------------------------------------
-// order of two cursor heads as internal keys: user key ascending, then trailer (seq, type) descending, then run index.
-// Whole warp; by_byte = decided by a differing key byte at dpos (the LCP shortcut of the merge loop relies on that).
-template <uint32_t G>
-PGS_DEV bool head_before(const Grp<G> &g, bool en, const CurState *cs, const uint32_t *rows, uint32_t KSW, uint32_t a, uint32_t b, uint32_t &dpos, bool &by_byte,
-                         uint32_t from = 0) // from: leading bytes known to be equal
-{
-    uint32_t la = 0, lb = 0;
-    bool full = en; // the first eight bytes decide most of the time: two scalar compares, no collective
-    if (en) {
-        la = cs[a].klen - 8; lb = cs[b].klen - 8;
-        const uint32_t ah = cs[a].kp_hi, al = cs[a].kp_lo, bh = cs[b].kp_hi, bl = cs[b].kp_lo;
-        if ((ah != bh || al != bl) && la >= 8 && lb >= 8) {
-            dpos = ah != bh ? (uint32_t)__clz((int)(ah ^ bh)) >> 3 : 4 + ((uint32_t)__clz((int)(al ^ bl)) >> 3);
-            by_byte = true;
-            full = false;
-        }
-    }
-    if (!g.any(full)) {
-        if (!en) { by_byte = false; return false; }
-        const uint32_t ah = cs[a].kp_hi, bh = cs[b].kp_hi;
-        return ah != bh ? ah < bh : cs[a].kp_lo < cs[b].kp_lo;
-    }
-    uint32_t dfull = 0;
-    const int c = row_cmp(g, full, rows + a * KSW, la, rows + b * KSW, lb, dfull, from);
-    if (!en) { by_byte = false; return false; }
-    if (!full) {
-        const uint32_t ah = cs[a].kp_hi, bh = cs[b].kp_hi;
-        return ah != bh ? ah < bh : cs[a].kp_lo < cs[b].kp_lo;
-    }
-    dpos = dfull;
-    by_byte = c != 0 && dpos < (la < lb ? la : lb);
-    if (c) return c < 0;
-    const unsigned long long ta = cur_trailer(&cs[a]), tb = cur_trailer(&cs[b]);
-    if (ta != tb) return ta > tb;
-    return a < b;
-}
-
 // Group-uniform running statistics of a group (every lane computes the same values); flushed into the CTA's totals (shared
 // memory) and from there into MergeStats.
 struct WalkAcc {
@@ -673,6 +636,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         bool restart = to_restart == 0;
         const uint32_t lcp_KA = !have_head ? 0u : head_in_A ? lcp_head : (lcp_head < lcpA ? lcp_head : lcpA);
         uint32_t shared = keep && !restart ? lcp_KA : 0u;
+        uint32_t *kdst = nullptr;
         if (keep) {
             const uint32_t otype = tomb ? (uint32_t)PGS_TYPE_DELETION : type;
             const bool zero_seq = P.bottommost && otype == PGS_TYPE_VALUE;
@@ -699,8 +663,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
 #pragma unroll
             for (uint32_t i = g.gl; i < 3; i += G)
                 if (i < fixed) sp[i] = i == 0 ? otr_lo : i == 1 ? otr_hi : __byte_perm(nts, 0, 0x0123); // BE32 in memory
-#pragma unroll 1
-            for (uint32_t w = g.gl; 4 * w < ulen; w += G) sp[fixed + w] = row[w];
+            kdst = sp + fixed; // the key words follow below, together with the copy that becomes the new A
             hpos += 4 * fixed + ((ulen + 3) & ~3u);
             if (g.gl == 0) {
                 Desc d;
@@ -733,10 +696,10 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         acc.e2 += spread4((ev >> 8) & 15u);
         if (++acc.n == 255) acc_flush_events(acc, cta, g.gl == 0);
         g.sync(); // every lane has read the previous survivor's key
-        if (act && !shadow) {
+        if (act && !shadow) { // the new head: a survivor goes to A and to its stream record, a dropped head to B
             uint32_t *dst = keep ? rowA : rowB;
 #pragma unroll 1
-            for (uint32_t w = g.gl; 4 * w < ulen; w += G) dst[w] = row[w];
+            for (uint32_t w = g.gl; 4 * w < ulen; w += G) { const uint32_t x = row[w]; dst[w] = x; if (keep) kdst[w] = x; }
             if (keep) { lenA = ulen; lcpA = ulen; } else lcpA = lcp_KA; // lcp(new head, A)
             head_in_A = keep;
             have_head = true;

@@ -1,5 +1,6 @@
-"""GPU parity under the non-default engine settings: two 512-thread CTAs per SM, the plain-load staging path
-(PGS_ENGINE_NO_TMA) and the early block load switched off.  Same oracle comparison as test_compaction_gpu."""
+"""GPU parity under the non-default settings: every lane-group width of the compaction walker (PGS_WALK_G; the default is 4, wider
+groups are what long keys fall back to) and the plain-load staging path of the reverse-scan kernel (PGS_ENGINE_NO_TMA).
+Same oracle comparison as test_compaction_gpu."""
 import random
 
 import pytest
@@ -13,22 +14,36 @@ NOW = synth.NOW
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[dict(ctas_per_sm=2), dict(flags=1), dict(ctas_per_sm=2, flags=1)], ids=["2cta", "no_tma", "2cta_no_tma"])
+@pytest.fixture(params=[dict(flags=1)], ids=["no_tma"])
 def variant_engine(pgs, request):
     eng = pgs.Engine(**request.param)
     yield eng
     eng.close()
 
 
+@pytest.mark.parametrize("lanes", [1, 2, 8, 16])
 @pytest.mark.parametrize("bottommost", [True, False])
-def test_compaction_variants(pgs, oracle, variant_engine, bottommost):
+def test_compaction_group_widths(pgs, oracle, engine, monkeypatch, lanes, bottommost):
+    monkeypatch.setenv("PGS_WALK_G", str(lanes))  # read per pgs_compact call
     runs = synth.compaction_runs(k=4, n_per_run=30_000)
-    run_case(pgs, oracle, variant_engine, runs, bottommost=bottommost, default_ttl=3600 if bottommost else 0)
+    run_case(pgs, oracle, engine, runs, bottommost=bottommost, default_ttl=3600 if bottommost else 0)
 
 
-def test_compaction_without_early_load(pgs, oracle, engine, monkeypatch):
-    monkeypatch.setenv("PGS_EARLY_TMA", "0")  # read per pgs_compact call
-    runs = synth.compaction_runs(k=3, n_per_run=40_000)
+def test_long_keys_pick_a_wider_group(pgs, oracle, engine):
+    """2 KB user keys: the per-group shared memory no longer fits the narrow shape, the geometry widens the groups"""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    runs = []
+    seq = 1
+    for i in range(3):
+        items = {}
+        for j in range(300):
+            hk = b"h%03d" % rng.integers(0, 40)
+            sk = bytes(rng.integers(97, 100, int(rng.integers(1500, 2000))).astype(np.uint8))
+            key = len(hk).to_bytes(2, "big") + hk + sk
+            items[key] = (key, seq, 1, (0).to_bytes(4, "big") + bytes(8) + b"v%d" % j)
+            seq += 1
+        runs.append(pgs.Records.from_list([items[k] for k in sorted(items)]))
     run_case(pgs, oracle, engine, runs, bottommost=True)
 
 

@@ -208,3 +208,19 @@ def test_sim_single_run_and_empty_output(pgs, oracle, sim):
     check(pgs, oracle, sim, runs, bottommost=True, seg_weight=16 * 1024)
     # everything expired -> no output run
     check(pgs, oracle, sim, runs, bottommost=True, now=synth.NOW + 10_000_000, default_ttl=1, seg_weight=16 * 1024)
+
+
+def test_sim_long_keys_widen_the_groups(pgs, oracle, sim):
+    """2 KB user keys: a narrow group's key rows no longer fit shared memory, the geometry falls back to wider groups"""
+    rng = np.random.default_rng(3)
+    runs, seq = [], 1
+    for i in range(3):
+        items = {}
+        for j in range(120):
+            hk = b"h%03d" % rng.integers(0, 20)
+            sk = bytes(rng.integers(97, 100, int(rng.integers(1500, 2000))).astype(np.uint8))
+            key = len(hk).to_bytes(2, "big") + hk + sk
+            items[key] = (key, seq, 1, (0).to_bytes(4, "big") + bytes(8) + b"v%d" % j)
+            seq += 1
+        runs.append(pgs.Records.from_list([items[k] for k in sorted(items)]))
+    check(pgs, oracle, sim, runs, bottommost=True, lanes=0, seg_weight=64 * 1024)
