@@ -230,6 +230,11 @@ __global__ void __launch_bounds__(256) k_plan(const __grid_constant__ MergeParam
     for (uint32_t j = 0; j < P.k; j++) {
         const RunDev &rj = P.runs[j];
         uint32_t lo = 0, hi = rj.nb; // upper bound: #blocks with last key <= U
+        if (j == i) { // the key's own run: its block, and the blocks after it that end with the same user key (older versions)
+            lo = b + 1;
+            while (lo < rj.nb && cmp_bytes4(rj.ikeys + rj.ikey_off[lo], rj.ikey_off[lo + 1] - rj.ikey_off[lo], U, ulen) == 0) lo++;
+            hi = lo;
+        }
         while (lo < hi) {
             uint32_t mid = (lo + hi) >> 1;
             const uint8_t *kp = rj.ikeys + rj.ikey_off[mid];
@@ -479,6 +484,33 @@ PGS_DEV unsigned long long ord_head_to(unsigned long long o, uint32_t pos) // th
     return (rest & low) | (c << (4 * pos)) | ((rest & ~low) << 4);
 }
 
+// What neighbours in the merge order share: field i (16 bits) = bytes the user keys at positions i and i + 1 have in common,
+// kLcpUnknown when not known; positions past the fourth are never known (deep stacks fall back to whole compares).
+constexpr uint32_t kLcpUnknown = 0xFFFFu;
+PGS_DEV uint32_t adj_get(unsigned long long a, uint32_t i) { return i < 4 ? (uint32_t)(a >> (16 * i)) & 0xFFFFu : kLcpUnknown; }
+PGS_DEV unsigned long long adj_set(unsigned long long a, uint32_t i, uint32_t v)
+{
+    if (i >= 4) return a;
+    if (v > kLcpUnknown) v = kLcpUnknown;
+    return (a & ~(0xFFFFull << (16 * i))) | ((unsigned long long)v << (16 * i));
+}
+// the head leaves position 0 and lands behind the entries 1..pos: the fields before it move down, lo / hi are what it shares
+// with its new neighbours
+PGS_DEV unsigned long long adj_head_to(unsigned long long a, uint32_t pos, uint32_t lo, uint32_t hi)
+{
+    unsigned long long n = ~0ull;
+#pragma unroll
+    for (uint32_t i = 0; i < 4; i++) {
+        uint32_t v;
+        if (i + 1 < pos) v = adj_get(a, i + 1);
+        else if (i + 1 == pos) v = lo;
+        else if (i == pos) v = hi;
+        else v = adj_get(a, i);
+        n = adj_set(n, i, v);
+    }
+    return n;
+}
+
 // One segment per group, all groups of the warp in lock step (see group.cuh): every statement outside an `if (en...)` body is
 // executed by all 32 lanes; `act` marks the groups that still have records.
 template <uint32_t G>
@@ -549,6 +581,14 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         }
         if (ins) { order = ord_insert(order, pos, j); live++; }
     }
+    unsigned long long adj = ~0ull; // see adj_get
+#pragma unroll 1
+    for (uint32_t i = 0; g.any(seg_en && !err && i + 1 < live) && i < 4; i++) {
+        const bool e = seg_en && !err && i + 1 < live;
+        uint32_t dp = 0;
+        head_before(g, e, cs, rows, KSW, ord_at(order, i), ord_at(order, i + 1), dp, by_byte);
+        if (e) adj = adj_set(adj, i, dp);
+    }
 
     // ---- the merge loop --------------------------------------------------------------------------------------------------
     Desc *desc = seg_en ? P.desc + P.seg[q].desc_off : nullptr;
@@ -561,8 +601,6 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
     bool have_head = false, head_in_A = false, prev_big = false;
     uint32_t hi_run = 0xffu, hi_l = 0, hi_ulen = 0; // the run whose last key was compared with the upper bound, and the bytes it shared with it
     uint32_t head_len = 0, last_run = 0xffu, lcpA = 0; // lcpA: bytes the head shares with A (the last survivor's key)
-    uint32_t d1 = 0;
-    bool d1_valid = false;
     auto close_block = [&]() { // bookkeeping of a finished block (k_emit derives the same numbers)
         const uint32_t size = blk_bytes + 4 * (nrest + 1);
         out_bytes += (size + kBlockAlign - 1) & ~(unsigned long long)(kBlockAlign - 1);
@@ -731,33 +769,49 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
             if (hi_cmp) { if (ch > 0) alive = false; else hi_l = dp; }
         }
         if (hi && alive) { hi_run = c; hi_ulen = C->klen - 8; } else if (hi_run == c) hi_run = 0xffu;
-        // The key differs from the runner-up's at byte d1 < shared: the bytes up to d1 did not change, neither does the order.
-        bool searching = adv && alive && live > 1 && !(d1_valid && C->shared > d1 && C->klen - 8 > d1);
-        // ... and what it shares with its predecessor and the predecessor shared with the runner-up, it shares with the runner-up
-        uint32_t from1 = 0;
-        if (searching && d1_valid) { from1 = C->shared < C->klen - 8 ? C->shared : C->klen - 8; if (from1 > d1) from1 = d1; }
-        if (searching) d1_valid = false;
-        uint32_t pos = 0, d1n = 0;
-        bool d1n_valid = false;
+        // Restore the merge order.  Keys are sorted, so what this key shares with a neighbour follows from what it shares with
+        // the one before and what those two share (adj): more -> it sorts before the neighbour, less -> after it (the byte is
+        // checked: a block writer may have stored less than the exact shared length), the same -> compare from that byte on.
+        bool searching = adv && alive && live > 1;
+        uint32_t cur = 0; // bytes this key shares with the entry examined last (first: its predecessor in the run, the old head)
+        if (searching) {
+            const uint32_t ku = C->klen - 8;
+            cur = C->shared < ku ? C->shared : ku;
+            if (cur > ulen) cur = ulen;
+            const uint32_t a0 = adj_get(adj, 0);
+            if (a0 != kLcpUnknown && cur > a0) searching = false; // stays in front, shares with the runner-up what its predecessor did
+        }
+        uint32_t pos = 0, nxt = kLcpUnknown;
         const bool reorder = searching;
 #pragma unroll 1
         for (uint32_t i = 1; g.any(searching && i < live); i++) {
             const bool e = searching && i < live;
-            const bool bf = head_before(g, e, cs, rows, KSW, c, ord_at(order, i), dpos, by_byte, i == 1 ? from1 : 0u);
+            const uint32_t r = ord_at(order, i);
+            const uint32_t a_i = adj_get(adj, i - 1);
+            bool need = e, bf = false;
+            uint32_t from = 0, d = 0;
+            if (e && a_i != kLcpUnknown) {
+                if (cur > a_i) { bf = true; d = a_i; need = false; }
+                else if (cur == a_i) from = cur;
+                else if (cur < C->klen - 8 && ((row[cur >> 2] >> (8 * (cur & 3))) & 0xffu) > ((rows[r * KSW + (cur >> 2)] >> (8 * (cur & 3))) & 0xffu)) { d = cur; need = false; }
+            }
+            if (g.any(need)) {
+                const bool bfc = head_before(g, need, cs, rows, KSW, c, r, dpos, by_byte, from);
+                if (need) { bf = bfc; d = dpos; }
+            }
             if (e) {
-                if (i == 1) { d1n_valid = by_byte; d1n = dpos; } // what the key shares with the old runner-up
-                if (bf) { if (i == 1) { d1_valid = by_byte; d1 = dpos; } searching = false; }
-                else pos = i;
+                if (bf) { nxt = d; searching = false; }
+                else { pos = i; cur = d; }
             }
         }
         if (adv && !alive) { // drop the exhausted run
             order >>= 4;
+            adj = (adj >> 16) | (0xFFFFull << 48);
             live--;
-            d1_valid = false;
             last_run = 0xffu;
-        } else if (reorder && pos > 0) {
-            order = ord_head_to(order, pos);
-            if (pos == 1) { d1_valid = d1n_valid; d1 = d1n; } // the old runner-up leads, this key is its runner-up
+        } else if (reorder) {
+            if (pos > 0) { order = ord_head_to(order, pos); adj = adj_head_to(adj, pos, cur, nxt); }
+            else adj = adj_set(adj, 0, nxt);
         }
     }
     if (seg_en) {
@@ -961,6 +1015,26 @@ PGS_DEV unsigned long long bloom_hash_words(const uint32_t *w32, uint32_t len)
         bloom_word(x, w, ha, hb);
     }
     return bloom_finish(ha, hb, len);
+}
+// one thread copies n bytes between two shared-memory buffers of any alignment: words where the destination allows, the
+// source re-aligned with a funnel shift (reads up to 3 bytes past the source's end: stages carry slack)
+PGS_DEV void copy_bytes_s2s(uint8_t *dst, const uint8_t *src, uint32_t n)
+{
+    while (n && ((uintptr_t)dst & 3)) { *dst++ = *src++; n--; }
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>((uintptr_t)src & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)((uintptr_t)src & 3) * 8;
+    uint32_t w0 = sw[0];
+#pragma unroll 1
+    for (; n >= 4; n -= 4) {
+        const uint32_t w1 = *++sw;
+        *reinterpret_cast<uint32_t *>(dst) = __funnelshift_r(w0, w1, sh);
+        w0 = w1;
+        dst += 4;
+    }
+    if (n) {
+        const uint32_t v = __funnelshift_r(w0, sh ? sw[1] : 0u, sh);
+        for (uint32_t i = 0; i < n; i++) dst[i] = (uint8_t)(v >> (8 * i));
+    }
 }
 PGS_DEV uint32_t put_varint32_s(uint8_t *p, uint32_t v) // shared-memory / generic byte stores
 {
@@ -1188,10 +1262,8 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
                 uint32_t p = put_varint32_s(dst, sh_out);
                 p += put_varint32_s(dst + p, kd + 8);
                 p += put_varint32_s(dst + p, vl);
-#pragma unroll 1
-                for (uint32_t x = 0; x < kd; x++) dst[p + x] = key[sh_out + x];
-#pragma unroll
-                for (uint32_t x = 0; x < 8; x++) dst[p + kd + x] = rec[x];
+                copy_bytes_s2s(dst + p, key + sh_out, kd);
+                copy_bytes_s2s(dst + p + kd, rec, 8u);
                 const RunDev &r = P.runs[(uint32_t)(d.loc >> 40) & 15u];
                 thread_copy_g2s(obuf, o_i + hl, r.data + (d.loc & ((1ull << 40) - 1)), vl, r.data);
                 if ((fl & DF_REWRITE) && vl >= 4) { dst[hl] = rec[8]; dst[hl + 1] = rec[9]; dst[hl + 2] = rec[10]; dst[hl + 3] = rec[11]; }

@@ -159,7 +159,7 @@ PGS_DEV void ld_2x32_any(const uint8_t *p, uint32_t &lo, uint32_t &hi)
 // Executed by the whole warp (two warp barriers inside).  Returns 0 or a status.
 template <uint32_t G>
 PGS_DEV uint32_t cur_decode(const Grp<G> &g, bool en, const RunDev &r, CurState *c, uint32_t *row, uint32_t KS, unsigned long long base,
-                            uint32_t p, uint32_t blk_size, uint32_t prev_klen)
+                            uint32_t p, uint32_t blk_size, uint32_t prev_klen, uint32_t rem_new)
 {
     uint32_t err = 0, sh = 0, ns = 0, vl = 0, h = 0, klen = 0;
     const uint8_t *src = nullptr;
@@ -197,6 +197,7 @@ PGS_DEV uint32_t cur_decode(const Grp<G> &g, bool en, const RunDev &r, CurState 
         const uint32_t ets = vl >= 4 ? ld_u32_any(src + ns) : 0u;
         if (g.gl == 0) {
             c->p = p; c->elen = h + ns + vl; c->klen = klen; c->vlen = vl; c->voff = p + h + ns; c->shared = sh; c->ets_le = ets;
+            c->rem = rem_new;
             c->tr_lo = tr_lo; c->tr_hi = tr_hi;
             if (sh < 8) { // the leading bytes changed
                 const uint32_t ul = klen - 8;
@@ -226,7 +227,7 @@ PGS_DEV uint32_t cur_open(const Grp<G> &g, bool en, const RunDev &r, CurState *c
     g.sync();
     cur_prefetch_next(g, some, r, c, b);
     const uint32_t err = some && r1 <= r0 ? (uint32_t)PGS_CORRUPTION : 0u; // a block holds at least one entry
-    const uint32_t e2 = cur_decode(g, some && !err, r, c, row, KS, base, 0, bsize, 0);
+    const uint32_t e2 = cur_decode(g, some && !err, r, c, row, KS, base, 0, bsize, 0, r1 - r0);
     return err ? err : e2;
 }
 
@@ -245,20 +246,22 @@ PGS_DEV uint32_t cur_next(const Grp<G> &g, bool en, const RunDev &r, CurState *c
         else if (b + 1 >= c->b_end || b + 1 >= r.nb) done = true;
         else cross = true;
     }
-    async_copy_wait_all(); // the copies issued when the block was entered (long since complete)
-    g.sync();              // ... and every lane has read the old state
+    g.sync(); // every lane is done with the old key row and state
     uint32_t r0 = 0, r1 = 0;
-    if (cross) { base = ((unsigned long long)c->nb_hi << 32) | c->nb_lo; r0 = c->nb_r0; r1 = c->nb_r1; bsize = c->nb_size; }
-    g.sync();
-    if (en && g.gl == 0) {
-        if (in_block) c->rem = rem - 1;
-        else if (done) { c->live = 0; c->b = b + 1; }
-        else { c->b = b + 1; c->base_lo = (uint32_t)base; c->base_hi = (uint32_t)(base >> 32); c->rem = r1 - r0; c->bsize = bsize; }
+    if (g.any(cross || done)) { // a block boundary (about one step in thirteen)
+        async_copy_wait_all(); // the copies issued when the block was entered (long since complete)
+        g.sync();
+        if (cross) { base = ((unsigned long long)c->nb_hi << 32) | c->nb_lo; r0 = c->nb_r0; r1 = c->nb_r1; bsize = c->nb_size; }
+        g.sync();
+        if (en && g.gl == 0) {
+            if (done) { c->live = 0; c->b = b + 1; }
+            else if (cross) { c->b = b + 1; c->base_lo = (uint32_t)base; c->base_hi = (uint32_t)(base >> 32); c->bsize = bsize; }
+        }
+        g.sync();
+        cur_prefetch_next(g, cross, r, c, b + 1);
     }
-    g.sync();
-    cur_prefetch_next(g, cross, r, c, b + 1);
     const uint32_t err = cross && r1 <= r0 ? (uint32_t)PGS_CORRUPTION : 0u;
-    const uint32_t e2 = cur_decode(g, (in_block || cross) && !err, r, c, row, KS, base, p, bsize, prev_klen);
+    const uint32_t e2 = cur_decode(g, (in_block || cross) && !err, r, c, row, KS, base, p, bsize, prev_klen, in_block ? rem - 1 : r1 - r0);
     return err ? err : e2;
 }
 

@@ -348,8 +348,7 @@ __global__ void __launch_bounds__(kReadThreads) k_scan_fwd(const __grid_constant
         uint32_t count = 0, iter_count = 0, expire_count = 0, filter_count = 0, n_out = 0, resume_len = 0;
         unsigned long long size = 0, arena_used = 0;
         bool complete = false, iter_valid = false, done = !en || err != 0, have_last = false, first_excl = en && !Q.start_inclusive;
-        uint32_t last_len = 0, last_run = 0xffu, stop_l = 0, d1 = 0;
-        bool stop_known = false, last_in_prefix = false, d1_valid = false;
+        uint32_t last_len = 0;
         for (;;) {
             const bool act = !done;
             if (!g.any(act)) break;
@@ -361,44 +360,14 @@ __global__ void __launch_bounds__(kReadThreads) k_scan_fwd(const __grid_constant
             uint32_t *row = rows + c * KSW;
             uint32_t ulen = 0, vlen = 0, type = 0;
             if (rec) { ulen = C->klen - 8; vlen = C->vlen; type = C->tr_lo & 0xffu; }
-            // newest version of each user key only; a tombstone hides the key.  Records arrive in ascending order, so what a
-            // key shares with the key before it (a_lcp) bounds every other relation: same run -> the entry's `shared` field
-            // (checked by one byte), another run -> at least what that run's next key shares with it (see k_walk).
+            // newest version of each user key only; a tombstone hides the key
             const bool cmpl = rec && have_last;
-            uint32_t a_lcp = 0, from = 0;
-            if (cmpl && last_run == c) { from = C->shared < ulen ? C->shared : ulen; if (from > last_len) from = last_len; }
-            else if (cmpl && last_run != 0xffu && cs[last_run].live) {
-                const uint32_t ls = cs[last_run].shared, lu = cs[last_run].klen - 8;
-                from = ls < lu ? ls : lu;
-                if (from > ulen) from = ulen;
-                if (from > last_len) from = last_len;
-            }
-            bool shadow = cmpl && from == ulen && ulen == last_len;
-            bool cmpb = cmpl && !shadow;
-            if (cmpb && last_run == c) {
-                if (from == ulen || from == last_len) { a_lcp = from; cmpb = false; }
-                else if (((row[from >> 2] ^ rowLAST[from >> 2]) >> (8 * (from & 3))) & 0xffu) { a_lcp = from; cmpb = false; }
-            }
-            if (g.any(cmpb)) {
-                const int cl = row_cmp(g, cmpb, row, ulen, rowLAST, last_len, a_lcp, from);
-                if (cmpb && cl == 0) shadow = true;
-            }
-            if (shadow) a_lcp = ulen;
+            const int cl = row_cmp(g, cmpl, row, ulen, rowLAST, last_len, dpos);
+            const bool shadow = cmpl && cl == 0;
             const bool visible = rec && !shadow && type == PGS_TYPE_VALUE;
-            // the loop's view of a visible record: the stop key.  LAST was below it and shared stop_l bytes with it.
+            // the loop's view of a visible record
             uint32_t d_stop = 0, d_start = 0;
-            int c2 = 0;
-            bool cmp_stop = visible;
-            uint32_t stop_from = 0;
-            if (visible && cmpl && stop_known) {
-                if (a_lcp > stop_l) { if (stop_l < last_len) { c2 = -1; d_stop = stop_l; cmp_stop = false; } }
-                else if (a_lcp < stop_l) { if (a_lcp < ulen) { c2 = 1; cmp_stop = false; } }
-                else if (stop_l <= ulen) stop_from = stop_l;
-            }
-            if (g.any(cmp_stop)) {
-                const int cs2 = row_cmp(g, cmp_stop, row, ulen, rowSTOP, stop_len, d_stop, stop_from);
-                if (cmp_stop) c2 = cs2;
-            }
+            const int c2 = row_cmp(g, visible, row, ulen, rowSTOP, stop_len, d_stop);
             const bool need_first = visible && first_excl;
             int c_first = 1;
             if (g.any(need_first)) c_first = row_cmp(g, need_first, row, ulen, rowSTART, start_len, d_start);
@@ -406,10 +375,7 @@ __global__ void __launch_bounds__(kReadThreads) k_scan_fwd(const __grid_constant
             if (visible) {
                 const uint8_t *key = (const uint8_t *)row;
                 bool valid = true; // Iterator::Valid(): inside the seek prefix, below iterate_upper_bound
-                if (pre_len) { // LAST carried the prefix: this key does iff it shares that much with LAST
-                    if (cmpl && last_in_prefix) valid = a_lcp >= pre_len;
-                    else { valid = ulen >= pre_len; for (uint32_t i = 0; valid && i < pre_len; i++) valid = key[i] == ((const uint8_t *)rowSTART)[i]; }
-                }
+                if (pre_len) { valid = ulen >= pre_len; for (uint32_t i = 0; valid && i < pre_len; i++) valid = key[i] == ((const uint8_t *)rowSTART)[i]; }
                 if (Q.has_upper && c2 >= 0) valid = false;
                 const bool guards = count < Q.max_count && iter_count < Q.max_iter_count && !(Q.max_iter_size > 0 && size >= Q.max_iter_size);
                 if (!guards || !valid) { // the while condition fails: the loop ends with the iterator standing here
@@ -481,43 +447,34 @@ __global__ void __launch_bounds__(kReadThreads) k_scan_fwd(const __grid_constant
             g.sync(); // every lane has read rowLAST
             if (rec && !shadow && advance) {
                 for (uint32_t w = g.gl; 4 * w < ulen; w += G) rowLAST[w] = row[w];
-                // what the new LAST shares with the stop key / whether it lies inside the seek prefix
-                if (visible) { stop_known = c2 < 0; stop_l = d_stop; last_in_prefix = true; } // (a visible record that advanced was valid and below the stop key)
-                else { stop_known = stop_known && cmpl && a_lcp > stop_l && stop_l < last_len; last_in_prefix = last_in_prefix && cmpl && a_lcp >= pre_len; }
                 have_last = true;
                 last_len = ulen;
             }
-            if (rec) last_run = c;
             g.sync();
             // step the cursor, restore the merge order
             const bool adv = rec && advance && !err;
             const uint32_t e3 = cur_next(g, adv, runs[c], C, row, KS);
             if (adv && e3) { err = e3; done = true; }
             const bool alive = adv && !e3 && C->live != 0;
-            // The key differs from the runner-up's at byte d1 < shared: the bytes up to d1 did not change, neither does the order.
-            bool searching = alive && live > 1 && !(d1_valid && C->shared > d1 && C->klen - 8 > d1);
-            uint32_t from1 = 0;
-            if (searching && d1_valid) { from1 = C->shared < C->klen - 8 ? C->shared : C->klen - 8; if (from1 > d1) from1 = d1; }
-            if (searching) d1_valid = false;
-            uint32_t pos = 0, d1n = 0;
-            bool d1n_valid = false;
+            bool searching = alive && live > 1;
+            uint32_t pos = 0;
             const bool reorder = searching;
             for (uint32_t i = 1; g.any(searching && i < live); i++) {
                 const uint32_t r = g.shfl(my_run, i) & 31u;
                 const bool e = searching && i < live;
-                const bool bf = head_before(g, e, cs, rows, KSW, c, r, dpos, by_byte, i == 1 ? from1 : 0u);
+                uint32_t la = 0, lb = 0;
+                if (e) { la = cs[c].klen - 8; lb = cs[r].klen - 8; }
+                const int cc = row_cmp(g, e, rows + c * KSW, la, rows + r * KSW, lb, dpos);
                 if (e) {
-                    if (i == 1) { d1n_valid = by_byte; d1n = dpos; }
-                    if (bf) { if (i == 1) { d1_valid = by_byte; d1 = dpos; } searching = false; } else pos = i;
+                    bool bf = cc < 0;
+                    if (cc == 0) { const unsigned long long ta = cur_trailer(&cs[c]), tb = cur_trailer(&cs[r]); bf = ta != tb ? ta > tb : c < r; }
+                    if (bf) searching = false; else pos = i;
                 }
             }
             const uint32_t dn = g.shfl_down(my_run, 1);
-            if (adv && !e3 && !alive) { if (g.gl + 1 < live) my_run = dn; live--; d1_valid = false; last_run = 0xffu; }
-            else if (reorder && pos > 0) {
-                if (g.gl < pos) my_run = dn;
-                if (g.gl == pos) my_run = c;
-                if (pos == 1) { d1_valid = d1n_valid; d1 = d1n; }
-            }
+            if (adv && !e3 && !alive) { if (g.gl + 1 < live) my_run = dn; live--; }
+            else if (reorder && pos > 0) { if (g.gl < pos) my_run = dn; if (g.gl == pos) my_run = c; }
+            (void)by_byte;
         }
         if (en && g.gl == 0) {
             pgs_scan_result res;
