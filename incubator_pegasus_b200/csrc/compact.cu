@@ -15,35 +15,24 @@ static uint64_t *g_crc_dev[16] = {nullptr};
 static std::mutex g_crc_mu;
 // the opt-in shared-memory maximum of the compaction kernels, once per device (a per-call cudaFuncSetAttribute would race)
 typedef void (*walk_kernel_t)(const MergeParams);
-static const uint32_t kWalkGs[] = {1, 2, 4, 8, 16}, kWalkMinBs[] = {4, 5, 6, 8};
-template <uint32_t MINB>
-static walk_kernel_t walk_kernel_g(uint32_t G)
+static const uint32_t kWalkGs[] = {1, 2, 4, 8, 16};
+static walk_kernel_t walk_kernel(uint32_t G)
 {
     switch (G) {
-    case 1: return k_walk<1, MINB>;
-    case 2: return k_walk<2, MINB>;
-    case 4: return k_walk<4, MINB>;
-    case 8: return k_walk<8, MINB>;
-    default: return k_walk<16, MINB>;
-    }
-}
-static walk_kernel_t walk_kernel(uint32_t G, uint32_t minb)
-{
-    switch (minb) {
-    case 5: return walk_kernel_g<5>(G);
-    case 6: return walk_kernel_g<6>(G);
-    case 8: return walk_kernel_g<8>(G);
-    default: return walk_kernel_g<4>(G);
+    case 1: return k_walk<1>;
+    case 2: return k_walk<2>;
+    case 4: return k_walk<4>;
+    case 8: return k_walk<8>;
+    default: return k_walk<16>;
     }
 }
 int32_t compact_init_kernels(int max_smem)
 {
     cudaFuncAttributes a;
-    for (uint32_t G : kWalkGs)
-        for (uint32_t mb : kWalkMinBs) {
-            PGS_CUDA(cudaFuncGetAttributes(&a, walk_kernel(G, mb)));
-            PGS_CUDA(cudaFuncSetAttribute(walk_kernel(G, mb), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - (int)a.sharedSizeBytes));
-        }
+    for (uint32_t G : kWalkGs) {
+        PGS_CUDA(cudaFuncGetAttributes(&a, walk_kernel(G)));
+        PGS_CUDA(cudaFuncSetAttribute(walk_kernel(G), cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - (int)a.sharedSizeBytes));
+    }
     PGS_CUDA(cudaFuncGetAttributes(&a, k_emit));
     PGS_CUDA(cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - (int)a.sharedSizeBytes));
     return PGS_OK;
@@ -128,16 +117,12 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
     CompactGeometry geo{};
     uint32_t force_G = 0; // diagnostics: PGS_WALK_G = lanes per merge group (1, 2, 4, 8, 16)
     if (const char *ev = getenv("PGS_WALK_G")) { const int v = atoi(ev); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) force_G = (uint32_t)v; }
-    uint64_t force_w = 0; // diagnostics: PGS_SEG_WEIGHT = segment budget in bytes
-    if (const char *ev = getenv("PGS_SEG_WEIGHT")) { const long long v = atoll(ev); if (v >= 4096 && v <= (64ll << 20)) force_w = (uint64_t)v; }
-    uint32_t minb = 4; // diagnostics: PGS_WALK_MINB
-    if (const char *ev = getenv("PGS_WALK_MINB")) minb = (uint32_t)atoi(ev);
-    bool geo_ok = compact_geometry(P, T, (uint32_t)e->max_smem_optin - 1024, geo, force_G, force_w);
+    bool geo_ok = compact_geometry(P, T, (uint32_t)e->max_smem_optin - 1024, geo, force_G);
     if (geo_ok) { // second pass: the segment budget follows from how many groups the device runs at once
         int occ = 0;
-        PGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel(geo.G, minb), (int)kWalkThreads, (size_t)geo.walk_dyn));
+        PGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_kernel(geo.G), (int)kWalkThreads, (size_t)geo.walk_dyn));
         const uint64_t groups = (uint64_t)std::max(1, occ) * e->sm_count * (kWalkThreads / geo.G);
-        geo_ok = compact_geometry(P, T, (uint32_t)e->max_smem_optin - 1024, geo, geo.G, force_w, groups);
+        geo_ok = compact_geometry(P, T, (uint32_t)e->max_smem_optin - 1024, geo, geo.G, 0, groups);
     }
     if (!geo_ok) {
         set_error("compact: input too large for one merge launch (keys of %u bytes, %llu records)", T.max_ukey, (unsigned long long)T.n_rec);
@@ -224,7 +209,7 @@ extern "C" int32_t pgs_compact_ex(pgs_partition *ph, const uint64_t *run_ids, ui
 
     cudaEvent_t ev[4];
     for (auto &x : ev) CK(cudaEventCreate(&x));
-    walk_kernel_t walk = walk_kernel(geo.G, minb);
+    walk_kernel_t walk = walk_kernel(geo.G);
     int occ_w = 0, occ_e = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, walk, (int)kWalkThreads, (size_t)geo.walk_dyn));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, k_emit, (int)(geo.emit_warps * 32), (size_t)geo.emit_dyn));

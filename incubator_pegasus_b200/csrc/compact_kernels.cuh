@@ -599,7 +599,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
     uint32_t n_blocks = 0, keyb = 0, lenA = 0;
     unsigned long long out_bytes = 0;
     bool have_head = false, head_in_A = false, prev_big = false;
-    uint32_t hi_run = 0xffu, hi_l = 0, hi_ulen = 0; // the run whose last key was compared with the upper bound, and the bytes it shared with it
+    uint32_t hi_run = 0xffu, hi_l = 0, hi_ulen = 0, sw_lcp = kLcpUnknown; // the run whose last key was compared with the upper bound, and the bytes it shared with it
     uint32_t head_len = 0, last_run = 0xffu, lcpA = 0; // lcpA: bytes the head shares with A (the last survivor's key)
     auto close_block = [&]() { // bookkeeping of a finished block (k_emit derives the same numbers)
         const uint32_t size = blk_bytes + 4 * (nrest + 1);
@@ -626,8 +626,13 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         uint32_t lcp_head = 0, from = 0;
         const bool cmp1 = act && have_head;
         const uint32_t *hrow = head_in_A ? rowA : rowB;
+        bool from_exact = false;
         if (cmp1 && last_run == c) { from = C->shared < ulen ? C->shared : ulen; if (from > head_len) from = head_len; }
-        else if (cmp1 && last_run != 0xffu && cs[last_run].live) {
+        else if (cmp1 && sw_lcp != kLcpUnknown) { // the old runner-up leads now: the order knew what it shared with the old head
+            from = sw_lcp < ulen ? sw_lcp : ulen;
+            if (from > head_len) from = head_len;
+            from_exact = true;
+        } else if (cmp1 && last_run != 0xffu && cs[last_run].live) {
             // another run leads now: head <= this key <= the key the head's run moved on to, so this key shares with the
             // head at least what that one does
             const uint32_t ls = cs[last_run].shared, lu = cs[last_run].klen - 8;
@@ -637,6 +642,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         }
         bool shadow = cmp1 && from == ulen && ulen == head_len;
         bool cmp1b = cmp1 && !shadow;
+        if (cmp1b && from_exact) { lcp_head = from; cmp1b = false; }
         if (cmp1b && last_run == c) {
             if (from == ulen || from == head_len) { lcp_head = from; cmp1b = false; } // one key is a proper prefix of the other
             else if (((row[from >> 2] ^ hrow[from >> 2]) >> (8 * (from & 3))) & 0xffu) { lcp_head = from; cmp1b = false; }
@@ -772,6 +778,7 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
         // Restore the merge order.  Keys are sorted, so what this key shares with a neighbour follows from what it shares with
         // the one before and what those two share (adj): more -> it sorts before the neighbour, less -> after it (the byte is
         // checked: a block writer may have stored less than the exact shared length), the same -> compare from that byte on.
+        sw_lcp = live > 1 ? adj_get(adj, 0) : kLcpUnknown; // what the record just handled shares with the runner-up: needed if that one takes over
         bool searching = adv && alive && live > 1;
         uint32_t cur = 0; // bytes this key shares with the entry examined last (first: its predecessor in the run, the old head)
         if (searching) {
@@ -832,9 +839,8 @@ PGS_DEV void walk_segment(const MergeParams &P, const RunDev *runs, const Grp<G>
 constexpr uint32_t kWalkFixedSmem = 2048 + kMaxRuns * (uint32_t)sizeof(RunDev) + (uint32_t)sizeof(WalkCtaStats);
 inline uint32_t walk_fixed_smem() { return kWalkFixedSmem; }
 
-// MINB = resident CTAs per SM the register allocation aims for
-template <uint32_t G, uint32_t MINB>
-__global__ void __launch_bounds__(kWalkThreads, MINB) k_walk(const __grid_constant__ MergeParams P)
+template <uint32_t G>
+__global__ void __launch_bounds__(kWalkThreads, 4) k_walk(const __grid_constant__ MergeParams P)
 {
     PGS_SMEM_DYN(dyn);
     const Grp<G> g;
@@ -1290,14 +1296,22 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
                     uint32_t p = bstart + T + 4 * nrest_c;
                     obuf[p] = (uint8_t)nrest_c; obuf[p + 1] = (uint8_t)(nrest_c >> 8); obuf[p + 2] = (uint8_t)(nrest_c >> 16); obuf[p + 3] = (uint8_t)(nrest_c >> 24);
                     for (p += 4; p < bstart + asz_c; p++) obuf[p] = 0;
-                    const uint32_t bi = blk_idx + nclose_incl - 1, ko = keyb + kb_incl - pk_len;
+                    const uint32_t bi = blk_idx + nclose_incl - 1;
                     P.out_blk_off[bi] = blk_start + (S_incl - asz_c);
                     P.out_blk_size[bi] = size_c;
                     P.out_blk_rec[bi] = ph >= 0 ? rec_idx + (uint32_t)ph : blk_rec0;
-                    P.out_ikey_off[bi] = ko;
-                    const uint8_t *pk = lane == 0 ? heads + last_key_off : hs + pk_off; // the entry before me: staged, or the last one of the batch before
-#pragma unroll 1
-                    for (uint32_t x = 0; x < pk_len; x++) P.out_ikeys[ko + x] = pk[x];
+                    P.out_ikey_off[bi] = keyb + kb_incl - pk_len;
+                }
+                // the closed blocks' index keys (the user key of the entry in front of each closing head): the whole warp copies
+                // one key at a time
+                uint32_t cm = __ballot_sync(kFull, closes);
+                while (cm) {
+                    const int L = __ffs((int)cm) - 1;
+                    cm &= cm - 1;
+                    const uint32_t klen_b = __shfl_sync(kFull, pk_len, L), ko_b = keyb + __shfl_sync(kFull, kb_incl, L) - klen_b;
+                    const uint32_t poff = __shfl_sync(kFull, pk_off, L);
+                    const uint8_t *pk = L == 0 ? heads + last_key_off : hs + poff; // staged, or the last entry of the batch before
+                    for (uint32_t x = lane; x < klen_b; x += 32) P.out_ikeys[ko_b + x] = pk[x];
                 }
             }
             // ---- carry the state over, flush ------------------------------------------------------------------------------------------------

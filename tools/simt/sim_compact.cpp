@@ -228,11 +228,11 @@ int32_t sim_compact(uint32_t k, const uint8_t **data, const uint64_t *data_bytes
     PGS_LAUNCH(k_seg_bounds, (P.Q + 255) / 256, 256, 0, 0, P);
     PGS_LAUNCH(k_seg_layout, 1, 1024, 0, 0, P);
     if (!st.error) {
-        if (geo.G == 1) PGS_LAUNCH((k_walk<1, 4>), 2, kWalkThreads, geo.walk_dyn, 0, P);
-        else if (geo.G == 2) PGS_LAUNCH((k_walk<2, 4>), 2, kWalkThreads, geo.walk_dyn, 0, P);
-        else if (geo.G == 4) PGS_LAUNCH((k_walk<4, 4>), 2, kWalkThreads, geo.walk_dyn, 0, P);
-        else if (geo.G == 8) PGS_LAUNCH((k_walk<8, 4>), 2, kWalkThreads, geo.walk_dyn, 0, P);
-        else PGS_LAUNCH((k_walk<16, 4>), 2, kWalkThreads, geo.walk_dyn, 0, P);
+        if (geo.G == 1) PGS_LAUNCH(k_walk<1>, 2, kWalkThreads, geo.walk_dyn, 0, P);
+        else if (geo.G == 2) PGS_LAUNCH(k_walk<2>, 2, kWalkThreads, geo.walk_dyn, 0, P);
+        else if (geo.G == 4) PGS_LAUNCH(k_walk<4>, 2, kWalkThreads, geo.walk_dyn, 0, P);
+        else if (geo.G == 8) PGS_LAUNCH(k_walk<8>, 2, kWalkThreads, geo.walk_dyn, 0, P);
+        else PGS_LAUNCH(k_walk<16>, 2, kWalkThreads, geo.walk_dyn, 0, P);
     }
     if (getenv("PGS_SIM_DUMP")) {
         for (uint32_t q = 0; q < P.Q; q++) {
