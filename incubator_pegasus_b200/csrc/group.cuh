@@ -115,6 +115,8 @@ struct CurState { // 32-bit fields only: any 4-byte-aligned stride between the s
     uint32_t live;             // 0 once the cursor is exhausted
     uint32_t kp_hi, kp_lo;     // the first eight key bytes as a big-endian number (zero padded): most order decisions need no more
     uint32_t hi_lcp;           // compaction walker: bytes the key shares with the range's upper bound (0x80000000: not known)
+    uint32_t hw0, hw1, hw2;    // the aligned words that hold the NEXT entry's first eight bytes (its header), fetched
+    uint32_t hvalid;           // asynchronously when this entry was decoded; hvalid = there is such an entry and it was fetched
 };
 PGS_DEV unsigned long long cur_trailer(const CurState *c) { return ((unsigned long long)c->tr_hi << 32) | c->tr_lo; }
 PGS_DEV unsigned long long cur_base(const CurState *c) { return ((unsigned long long)c->base_hi << 32) | c->base_lo; }
@@ -159,14 +161,19 @@ PGS_DEV void ld_2x32_any(const uint8_t *p, uint32_t &lo, uint32_t &hi)
 // Executed by the whole warp (two warp barriers inside).  Returns 0 or a status.
 template <uint32_t G>
 PGS_DEV uint32_t cur_decode(const Grp<G> &g, bool en, const RunDev &r, CurState *c, uint32_t *row, uint32_t KS, unsigned long long base,
-                            uint32_t p, uint32_t blk_size, uint32_t prev_klen, uint32_t rem_new)
+                            uint32_t p, uint32_t blk_size, uint32_t prev_klen, uint32_t rem_new, bool stashed = false)
 {
     uint32_t err = 0, sh = 0, ns = 0, vl = 0, h = 0, klen = 0;
     const uint8_t *src = nullptr;
+    const uint8_t *A = nullptr;
     if (en) {
-        const uint8_t *A = r.data + base + p;
+        A = r.data + base + p;
         uint32_t h_lo, h_hi;
-        ld_2x32_any(A, h_lo, h_hi);
+        if (stashed) { // the header words arrived while the previous entry was being handled
+            const uint32_t s8 = (uint32_t)((uintptr_t)A & 3) * 8, w0 = c->hw0, w1 = c->hw1, w2 = c->hw2;
+            h_lo = __funnelshift_r(w0, w1, s8);
+            h_hi = __funnelshift_r(w1, w2, s8);
+        } else ld_2x32_any(A, h_lo, h_hi);
         h = parse_header8(((unsigned long long)h_hi << 32) | h_lo, sh, ns, vl);
         if (!h) { // uncommon shape (a length of two or more varint bytes): byte-wise decoder
             h = parse_header_slow(A, sh, ns, vl);
@@ -198,6 +205,7 @@ PGS_DEV uint32_t cur_decode(const Grp<G> &g, bool en, const RunDev &r, CurState 
         if (g.gl == 0) {
             c->p = p; c->elen = h + ns + vl; c->klen = klen; c->vlen = vl; c->voff = p + h + ns; c->shared = sh; c->ets_le = ets;
             c->rem = rem_new;
+            c->hvalid = rem_new >= 2 ? 1u : 0u;
             c->tr_lo = tr_lo; c->tr_hi = tr_hi;
             if (sh < 8) { // the leading bytes changed
                 const uint32_t ul = klen - 8;
@@ -207,7 +215,13 @@ PGS_DEV uint32_t cur_decode(const Grp<G> &g, bool en, const RunDev &r, CurState 
                 c->kp_hi = __byte_perm(w0, 0, 0x0123); c->kp_lo = __byte_perm(w1, 0, 0x0123);
             }
         }
+        if (rem_new >= 2) { // the next entry of the block: start fetching its header words (consumed by the next cur_next)
+            const uint32_t *nw = reinterpret_cast<const uint32_t *>((uintptr_t)(A + h + ns + vl) & ~(uintptr_t)3);
+#pragma unroll
+            for (uint32_t i = g.gl; i < 3; i += G) async_copy4(i == 0 ? &c->hw0 : i == 1 ? &c->hw1 : &c->hw2, nw + i);
+        }
     }
+    async_copy_commit();
     g.sync();
     return err;
 }
@@ -238,19 +252,18 @@ PGS_DEV uint32_t cur_next(const Grp<G> &g, bool en, const RunDev &r, CurState *c
 {
     uint32_t rem = 0, b = 0, p = 0, prev_klen = 0, bsize = 0;
     unsigned long long base = 0;
-    bool in_block = false, cross = false, done = false;
+    bool in_block = false, cross = false, done = false, stashed = false;
     if (en) {
         rem = c->rem; b = c->b;
         in_block = rem > 1;
-        if (in_block) { base = cur_base(c); p = c->p + c->elen; prev_klen = c->klen; bsize = c->bsize; }
+        if (in_block) { base = cur_base(c); p = c->p + c->elen; prev_klen = c->klen; bsize = c->bsize; stashed = c->hvalid != 0; }
         else if (b + 1 >= c->b_end || b + 1 >= r.nb) done = true;
         else cross = true;
     }
-    g.sync(); // every lane is done with the old key row and state
+    async_copy_wait_all(); // the header words fetched when the current entry was decoded (and, long ago, the next block's metadata)
+    g.sync(); // every lane is done with the old key row and state, and sees the fetched words
     uint32_t r0 = 0, r1 = 0;
     if (g.any(cross || done)) { // a block boundary (about one step in thirteen)
-        async_copy_wait_all(); // the copies issued when the block was entered (long since complete)
-        g.sync();
         if (cross) { base = ((unsigned long long)c->nb_hi << 32) | c->nb_lo; r0 = c->nb_r0; r1 = c->nb_r1; bsize = c->nb_size; }
         g.sync();
         if (en && g.gl == 0) {
@@ -261,7 +274,7 @@ PGS_DEV uint32_t cur_next(const Grp<G> &g, bool en, const RunDev &r, CurState *c
         cur_prefetch_next(g, cross, r, c, b + 1);
     }
     const uint32_t err = cross && r1 <= r0 ? (uint32_t)PGS_CORRUPTION : 0u;
-    const uint32_t e2 = cur_decode(g, (in_block || cross) && !err, r, c, row, KS, base, p, bsize, prev_klen, in_block ? rem - 1 : r1 - r0);
+    const uint32_t e2 = cur_decode(g, (in_block || cross) && !err, r, c, row, KS, base, p, bsize, prev_klen, in_block ? rem - 1 : r1 - r0, stashed);
     return err ? err : e2;
 }
 
