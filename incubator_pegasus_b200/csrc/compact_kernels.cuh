@@ -980,11 +980,7 @@ PGS_DEV void store_chunk_part(uint8_t *dst16, uint4 v, uint32_t lo, uint32_t hi)
 }
 // one THREAD copies n bytes from global memory (any alignment, readable in whole 16-byte chunks inside [lim_lo, ...)) to shared
 // memory at dst (any alignment): 16-byte loads and stores, byte-exact at both ends.  Four loads are in flight per round trip.
-// front_own = bytes in front of doff that the caller will overwrite afterwards (its own entry head): a first chunk that
-// reaches back no further is stored whole; tail_free = bytes behind the value that nobody else writes before the caller's
-// later pass: a last chunk that spills no further is stored whole.  Only the remaining edge chunks are stored byte-wise.
-PGS_DEV void thread_copy_g2s(uint8_t *obuf16, uint32_t doff, const uint8_t *src, uint32_t n, const uint8_t *lim_lo, uint32_t front_own = 0,
-                             uint32_t tail_free = 0)
+PGS_DEV void thread_copy_g2s(uint8_t *obuf16, uint32_t doff, const uint8_t *src, uint32_t n, const uint8_t *lim_lo)
 {
     if (n == 0) return;
     const uint32_t x0 = doff & ~15u;                   // first destination chunk
@@ -1005,9 +1001,7 @@ PGS_DEV void thread_copy_g2s(uint8_t *obuf16, uint32_t doff, const uint8_t *src,
             const uint32_t xx = x + 16 * j;
             if (xx < end) {
                 const uint4 o = realign16(j == 0 ? Pc : nx[j - 1], nx[j], a);
-                uint32_t lo = xx < doff ? doff - xx : 0u, hi = end - xx < 16 ? end - xx : 16u;
-                if (lo <= front_own) lo = 0;
-                if (16 - hi <= tail_free) hi = 16;
+                const uint32_t lo = xx < doff ? doff - xx : 0u, hi = end - xx < 16 ? end - xx : 16u;
                 if (lo == 0 && hi == 16) *reinterpret_cast<uint4 *>(obuf16 + xx) = o;
                 else store_chunk_part(obuf16 + xx, o, lo, hi);
             }
@@ -1253,15 +1247,6 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
             async_copy_wait_upto(0);
             __syncwarp();
             const uint8_t *hs = hst + ((uintptr_t)(heads + hpos) & 15);
-            // ---- one thread per entry ---------------------------------------------------------------------------------------------------
-            // pass 1, values: whole 16-byte chunks wherever the spill lands on bytes that pass 2 rewrites -- the entry's own head in
-            // front (hl bytes), the next entry's head behind (at least 11 bytes: three varints and the trailer), or, behind the
-            // batch's last entry, nothing yet.  Restart arrays and block tails are written after pass 1 as well.
-            if (mine) {
-                const RunDev &r = P.runs[(uint32_t)(d.loc >> 40) & 15u];
-                thread_copy_g2s(obuf, o_i + hl, r.data + (d.loc & ((1ull << 40) - 1)), vl, r.data, hl, lane + 1 == cnt ? 15u : 11u);
-            }
-            __syncwarp();
             // ---- restart points ---------------------------------------------------------------------------------------------------------
             const uint32_t after = hm & ~(lt | (1u << lane));
             const int nh = after ? __ffs((int)after) - 1 : -1;                   // the head that closes my block inside this batch
@@ -1274,7 +1259,7 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
                 } else rst[r_i] = fill_i;
             }
             if (mine) P.out_rec_off[rec_idx + lane] = fill_i;
-            // pass 2, heads and filter bits
+            // ---- one thread per entry: head, value, filter bits ---------------------------------------------------------------------------
             bool new_prefix = false;
             if (mine) {
                 const uint8_t *rec = hs + rec_off_i;
@@ -1285,6 +1270,8 @@ __global__ void __launch_bounds__(kEmitThreads, 5) k_emit(const __grid_constant_
                 p += put_varint32_s(dst + p, vl);
                 copy_bytes_s2s(dst + p, key + sh_out, kd);
                 copy_bytes_s2s(dst + p + kd, rec, 8u);
+                const RunDev &r = P.runs[(uint32_t)(d.loc >> 40) & 15u];
+                thread_copy_g2s(obuf, o_i + hl, r.data + (d.loc & ((1ull << 40) - 1)), vl, r.data);
                 if ((fl & DF_REWRITE) && vl >= 4) { dst[hl] = rec[8]; dst[hl + 1] = rec[9]; dst[hl + 2] = rec[10]; dst[hl + 3] = rec[11]; }
                 bloom_add(reinterpret_cast<const uint32_t *>(key), ulen, lcp, new_prefix);
             }

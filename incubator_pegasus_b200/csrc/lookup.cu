@@ -851,7 +851,6 @@ int32_t lookup_init_kernels(int max_smem)
     PGS_CUDA(allow_max_smem(k_scan, max_smem));
     PGS_CUDA(cudaFuncSetAttribute(k_scan, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     PGS_CUDA(allow_max_smem(k_get<8>, max_smem));
-    PGS_CUDA(allow_max_smem(k_scan_fwd<4>, max_smem));
     PGS_CUDA(allow_max_smem(k_scan_fwd<8>, max_smem));
     PGS_CUDA(allow_max_smem(k_scan_fwd<16>, max_smem));
     PGS_CUDA(allow_max_smem(k_scan_fwd<32>, max_smem));
@@ -952,13 +951,13 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
     P.phase_cycles = phase_timing ? (unsigned long long *)(d_err + 16) : nullptr;
     if (!any_reverse) {
         // ---- forward scans: lane-group merging iterators (read_kernels.cuh) ------------------------------------------
-        const uint32_t NR = P.rr.n, G = NR <= 4 ? 4 : NR <= 8 ? 8 : NR <= 16 ? 16 : 32; // the narrowest group that holds the order
+        const uint32_t NR = P.rr.n, G = NR <= 8 ? 8 : NR <= 16 ? 16 : 32;
         P.KS = (P.KS + 3) & ~3u;
         P.KSW = (P.KS + 8) / 4 + 1;
         P.group_smem = (uint32_t)((NR * (sizeof(CurState) + P.KSW * 4) + 3 * P.KSW * 4 + 15) & ~(size_t)15);
         const uint32_t dyn = 2048 + kMaxReadRuns * (uint32_t)sizeof(RunDev) + (kReadThreads / G) * P.group_smem;
         if (dyn > (uint32_t)e->max_smem_optin) { cleanup(); set_error("scan: %u runs with keys of %u bytes do not fit shared memory", NR, P.KS); return PGS_NOT_SUPPORTED; }
-        auto kern = G == 4 ? k_scan_fwd<4> : G == 8 ? k_scan_fwd<8> : G == 16 ? k_scan_fwd<16> : k_scan_fwd<32>;
+        auto kern = G == 8 ? k_scan_fwd<8> : G == 16 ? k_scan_fwd<16> : k_scan_fwd<32>;
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)kReadThreads, (size_t)dyn));
         const uint32_t per_cta = kReadThreads / G;

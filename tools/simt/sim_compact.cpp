@@ -376,14 +376,13 @@ int32_t sim_scan(uint32_t k, const uint8_t **data, const uint64_t *data_bytes, c
     P.results = results; P.kvs = kvs; P.kv_stride = kv_stride; P.arena = arena; P.arena_stride = arena_stride;
     P.resume = resume; P.resume_stride = resume_stride; P.error = err; P.ticket = err + 8;
     if (need_crc) { make_crc(); P.crc_table = (const unsigned long long *)crc_tab; }
-    const uint32_t G = lanes ? lanes : (k <= 4 ? 4 : k <= 8 ? 8 : k <= 16 ? 16 : 32);
+    const uint32_t G = lanes ? lanes : (k <= 8 ? 8 : k <= 16 ? 16 : 32);
     if (G < k) return PGS_INVALID_ARGUMENT;
     P.KS = std::max(8u, (mk + 3) & ~3u);
     P.KSW = (P.KS + 8) / 4 + 1;
     P.group_smem = (uint32_t)((k * (sizeof(CurState) + P.KSW * 4) + 3 * P.KSW * 4 + 15) & ~(size_t)15);
     const uint32_t dyn = 2048 + kMaxReadRuns * (uint32_t)sizeof(RunDev) + (kReadThreads / G) * P.group_smem;
-    if (G == 4) PGS_LAUNCH(k_scan_fwd<4>, 2, kReadThreads, dyn, 0, P);
-    else if (G == 8) PGS_LAUNCH(k_scan_fwd<8>, 2, kReadThreads, dyn, 0, P);
+    if (G == 8) PGS_LAUNCH(k_scan_fwd<8>, 2, kReadThreads, dyn, 0, P);
     else if (G == 16) PGS_LAUNCH(k_scan_fwd<16>, 2, kReadThreads, dyn, 0, P);
     else PGS_LAUNCH(k_scan_fwd<32>, 2, kReadThreads, dyn, 0, P);
     return err[0] ? (int32_t)err[0] : PGS_OK;
