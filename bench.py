@@ -396,7 +396,7 @@ def main():
     ap.add_argument("--partitions", type=int, default=256)
     ap.add_argument("--table-hashkeys", type=int, default=65536)
     ap.add_argument("--read-threads", type=int, default=8)
-    ap.add_argument("--sweep-mb", type=int, nargs="*", default=[8, 32, 128, 256])
+    ap.add_argument("--sweep-mb", type=int, nargs="*", default=[8, 16, 32, 64, 128, 256])
     ap.add_argument("--ycsb-keys", type=int, default=20000)
     ap.add_argument("--ycsb-ops", type=int, default=20000)
     args = ap.parse_args()

@@ -441,6 +441,13 @@ PGS_API int32_t pgs_rrdb_put(pgs_server *s, pgs_blob raw_key, pgs_blob user_valu
                              uint32_t expire_ts_seconds, int64_t decree, uint64_t timestamp_us,
                              uint32_t now);
 PGS_API int32_t pgs_rrdb_remove(pgs_server *s, pgs_blob raw_key, int64_t decree, uint32_t now);
+/* incr (pegasus_write_service_impl.h:264-342; RPC_RRDB_RRDB_INCR): read-before-write on the replica's single writer.  Absent,
+ * expired or empty base = 0; a non-integer base or an int64 overflow is reported in *resp_error (kInvalidArgument, *new_value =
+ * the old value on overflow) while the call still returns kOk and writes an empty record for the decree, as the reference
+ * does.  expire_ts_seconds: 0 keeps the record's expiry, < 0 clears it, > 0 sets it. */
+PGS_API int32_t pgs_rrdb_incr(pgs_server *s, pgs_blob raw_key, int64_t increment, int32_t expire_ts_seconds,
+                              int64_t decree, uint64_t timestamp_us, uint32_t now, int32_t *resp_error,
+                              int64_t *new_value);
 PGS_API int32_t pgs_rrdb_multi_put(pgs_server *s, pgs_blob hash_key, const pgs_blob *sort_keys,
                                    const pgs_blob *values, uint32_t n, uint32_t expire_ts_seconds,
                                    int64_t decree, uint64_t timestamp_us, uint32_t now);
@@ -499,6 +506,17 @@ PGS_API int32_t pgs_sst_decode(const uint8_t *sst, uint64_t size, uint8_t *data,
 PGS_API int32_t pgs_sst_filter_may_match(const uint8_t *sst, uint64_t size, const uint8_t *key, uint32_t key_len);
 PGS_API int32_t pgs_sst_export(pgs_partition *p, uint64_t run_id, uint8_t *out, uint64_t out_cap, uint64_t *out_size);
 PGS_API int32_t pgs_sst_ingest(pgs_partition *p, int32_t level, const uint8_t *sst, uint64_t size, uint64_t *run_id_out);
+/* compression: 0 = none, 4 = LZ4 (kLZ4Compression; what Pegasus configures for levels >= 2, pegasus_server_impl.cpp:3040-3056).
+ * Data blocks are stored compressed when that saves 12.5 %; compress_format_version 2 (varint32 raw size | LZ4 block).
+ * pgs_sst_decode / pgs_sst_ingest read either kind. */
+PGS_API int32_t pgs_sst_encode_ex(const uint8_t *data, const uint64_t *blk_off, const uint32_t *blk_size,
+                                  uint32_t n_blocks, uint32_t compression, uint8_t *out, uint64_t out_cap,
+                                  uint64_t *out_size);
+PGS_API int32_t pgs_sst_export_ex(pgs_partition *p, uint64_t run_id, uint32_t compression, uint8_t *out,
+                                  uint64_t out_cap, uint64_t *out_size);
+/* the raw LZ4 block codec used above (decompress: out_cap must be the exact raw size) */
+PGS_API int32_t pgs_lz4_block(int32_t decompress, const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_cap,
+                              uint64_t *out_size);
 PGS_API uint32_t pgs_crc32c(const uint8_t *data, uint64_t len, uint32_t init);
 
 #ifdef __cplusplus

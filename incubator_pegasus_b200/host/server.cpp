@@ -763,6 +763,62 @@ int32_t pgs_rrdb_remove(pgs_server *h, pgs_blob key, int64_t decree, uint32_t no
     h->s.mem_write(std::string(bsv(key)), PGS_TYPE_DELETION, std::string(), now);
     return PGS_OK;
 }
+// dsn::buf2int64 (src/utils/string_conv.h:35-62): the whole buffer is one integer for strtoll with base 0 (decimal, 0x.., 0..)
+static bool buf2int64(std::string_view buf, int64_t &out)
+{
+    if (buf.empty()) return false;
+    const std::string str(buf);
+    errno = 0;
+    char *p = nullptr;
+    const long long v = std::strtoll(str.c_str(), &p, 0);
+    if ((size_t)(p - str.c_str()) != str.size() || errno != 0) return false;
+    out = v;
+    return true;
+}
+// incr (pegasus_write_service_impl.h:264-342): read-before-write on the single writer; an absent / expired / empty base counts
+// as 0; a base that is not an integer or a sum that leaves int64 answers kInvalidArgument *in the response* (the return value
+// stays kOk) and still writes an empty record so that the decree advances; expire_ts_seconds: 0 keeps the record's, < 0
+// clears it, > 0 sets it (only > 0 matters for a new record).  *resp_error / *new_value mirror incr_response.
+int32_t pgs_rrdb_incr(pgs_server *h, pgs_blob key, int64_t increment, int32_t expire_ts_seconds, int64_t decree, uint64_t timestamp_us,
+                      uint32_t now, int32_t *resp_error, int64_t *new_value)
+{
+    WLOCKED(h);
+    Server &s = h->s;
+    s.last_committed_decree = decree;
+    int32_t dummy_e;
+    int64_t dummy_v;
+    if (!resp_error) resp_error = &dummy_e;
+    if (!new_value) new_value = &dummy_v;
+    *new_value = 0;
+    std::vector<pgs_get_result> gr;
+    std::vector<uint8_t> arena;
+    const int32_t st = point_lookup(s, {std::string(bsv(key))}, now, gr, arena);
+    if (st != PGS_OK) { *resp_error = st; return st; }
+    int64_t nv = increment;
+    uint32_t new_ets = expire_ts_seconds > 0 ? (uint32_t)expire_ts_seconds : 0u;
+    if (gr[0].status == PGS_OK) { // found and alive
+        const std::string_view old((const char *)arena.data() + gr[0].value_off, gr[0].value_len);
+        if (!old.empty()) {
+            int64_t base;
+            if (!buf2int64(old, base)) {
+                *resp_error = PGS_INVALID_ARGUMENT;
+                s.put_one({}, {}, 0, timestamp_us, now); // empty_put
+                return PGS_OK;
+            }
+            if (__builtin_add_overflow(base, increment, &nv)) {
+                *resp_error = PGS_INVALID_ARGUMENT;
+                *new_value = base;
+                s.put_one({}, {}, 0, timestamp_us, now);
+                return PGS_OK;
+            }
+        }
+        new_ets = expire_ts_seconds == 0 ? gr[0].expire_ts : expire_ts_seconds < 0 ? 0u : (uint32_t)expire_ts_seconds;
+    }
+    s.put_one(bsv(key), std::to_string(nv), new_ets, timestamp_us, now);
+    *resp_error = PGS_OK;
+    *new_value = nv;
+    return PGS_OK;
+}
 int32_t pgs_rrdb_multi_put(pgs_server *h, pgs_blob hash_key, const pgs_blob *sort_keys, const pgs_blob *values,
                            uint32_t n, uint32_t expire_ts, int64_t decree, uint64_t timestamp_us, uint32_t now)
 {

@@ -53,6 +53,75 @@ uint32_t crc32c(uint32_t crc, const uint8_t *p, uint64_t n)
 }
 static uint32_t crc_mask(uint32_t crc) { return ((crc >> 15) | (crc << 17)) + 0xa282ead8u; } // util/crc32c.h Mask()
 
+// ---- LZ4 block format (the raw block codec RocksDB's kLZ4Compression wraps; lz4 is not linked: the format is small) ---------
+// sequence = token (literal length : match length) | [length bytes] | literals | offset LE16 | [length bytes]; the last sequence
+// has only literals; a match is at least 4 bytes, the last 5 bytes of a block are literals and the last match starts at
+// least 12 bytes before the end.
+static bool lz4_decompress(const uint8_t *ip, size_t n, uint8_t *out, size_t out_n)
+{
+    const uint8_t *iend = ip + n;
+    size_t op = 0;
+    while (ip < iend) {
+        const uint32_t token = *ip++;
+        size_t lit = token >> 4;
+        if (lit == 15) { uint8_t b; do { if (ip >= iend) return false; b = *ip++; lit += b; } while (b == 255); }
+        if ((size_t)(iend - ip) < lit || out_n - op < lit) return false;
+        memcpy(out + op, ip, lit);
+        op += lit; ip += lit;
+        if (ip >= iend) break; // the last sequence
+        if (iend - ip < 2) return false;
+        const size_t off = (size_t)ip[0] | ((size_t)ip[1] << 8);
+        ip += 2;
+        if (off == 0 || off > op) return false;
+        size_t ml = token & 15;
+        if (ml == 15) { uint8_t b; do { if (ip >= iend) return false; b = *ip++; ml += b; } while (b == 255); }
+        ml += 4;
+        if (out_n - op < ml) return false;
+        for (size_t i = 0; i < ml; i++) out[op + i] = out[op + i - off]; // may overlap
+        op += ml;
+    }
+    return op == out_n;
+}
+static void lz4_put_len(std::string &d, size_t v) { while (v >= 255) { d.push_back((char)255); v -= 255; } d.push_back((char)v); }
+static std::string lz4_compress(const uint8_t *in, size_t n)
+{
+    std::string out;
+    std::vector<uint32_t> table(1u << 13, 0xFFFFFFFFu);
+    size_t anchor = 0, i = 0;
+    auto emit = [&](size_t lit_end, size_t match_len, size_t offset) { // literals [anchor, lit_end), then a match (match_len 0: none)
+        const size_t lit = lit_end - anchor, ml = match_len ? match_len - 4 : 0;
+        out.push_back((char)(((lit < 15 ? lit : 15) << 4) | (match_len ? (ml < 15 ? ml : 15) : 0)));
+        if (lit >= 15) lz4_put_len(out, lit - 15);
+        out.append((const char *)in + anchor, lit);
+        if (match_len) {
+            out.push_back((char)(offset & 255));
+            out.push_back((char)(offset >> 8));
+            if (ml >= 15) lz4_put_len(out, ml - 15);
+        }
+    };
+    if (n >= 13) {
+        const size_t mflimit = n - 12, matchlimit = n - 5;
+        while (i < mflimit) {
+            uint32_t v;
+            memcpy(&v, in + i, 4);
+            const uint32_t h = (v * 2654435761u) >> 19;
+            const uint32_t cand = table[h];
+            table[h] = (uint32_t)i;
+            uint32_t cv = 0;
+            if (cand != 0xFFFFFFFFu) memcpy(&cv, in + cand, 4);
+            if (cand != 0xFFFFFFFFu && cv == v && i - cand <= 65535) {
+                size_t ml = 4;
+                while (i + ml < matchlimit && in[cand + ml] == in[i + ml]) ml++;
+                emit(i, ml, i - cand);
+                i += ml;
+                anchor = i;
+            } else i++;
+        }
+    }
+    emit(n, 0, 0);
+    return out;
+}
+
 // ---- small encoders --------------------------------------------------------------------------------------------------
 static void put_v32(std::string &d, uint32_t v)
 {
@@ -211,19 +280,29 @@ static const char *kPropsName = "rocksdb.properties";
 struct Handle { uint64_t off = 0, size = 0; };
 static void put_handle(std::string &d, Handle h) { put_v64(d, h.off); put_v64(d, h.size); }
 
-static Handle append_block(std::string &file, const uint8_t *b, uint64_t n)
+static const uint8_t kNoCompression = 0, kLZ4Compression = 4;
+static Handle append_block(std::string &file, const uint8_t *b, uint64_t n, uint8_t compression = kNoCompression)
 {
-    Handle h{file.size(), n};
-    file.append((const char *)b, n);
-    const uint8_t type = 0; // kNoCompression
-    uint32_t crc = crc32c(0, b, n);
+    std::string packed;
+    uint8_t type = kNoCompression;
+    if (compression == kLZ4Compression && n < 0xffffffffull) { // compress_format_version 2: varint32 raw size | LZ4 block
+        put_v32(packed, (uint32_t)n);
+        packed += lz4_compress(b, n);
+        if (packed.size() < n - n / 8) type = kLZ4Compression; // kept only when it saves 12.5 % (RocksDB's GoodCompressionRatio)
+    }
+    const uint8_t *p = type ? (const uint8_t *)packed.data() : b;
+    const uint64_t pn = type ? packed.size() : n;
+    Handle h{file.size(), pn};
+    file.append((const char *)p, pn);
+    uint32_t crc = crc32c(0, p, pn);
     crc = crc32c(crc, &type, 1);
     file.push_back((char)type);
     put_f32(file, crc_mask(crc));
     return h;
 }
 
-int32_t sst_encode(const uint8_t *data, const uint64_t *blk_off, const uint32_t *blk_size, uint32_t nb, std::string &file)
+int32_t sst_encode(const uint8_t *data, const uint64_t *blk_off, const uint32_t *blk_size, uint32_t nb, std::string &file,
+                   uint8_t compression = kNoCompression)
 {
     file.clear();
     KvBlock index(1); // index_block_restart_interval = 1
@@ -251,7 +330,7 @@ int32_t sst_encode(const uint8_t *data, const uint64_t *blk_off, const uint32_t 
             last.assign(ik.data(), ik.size());
         });
         if (!ok || last.empty()) return PGS_CORRUPTION;
-        const Handle h = append_block(file, data + blk_off[b], blk_size[b]);
+        const Handle h = append_block(file, data + blk_off[b], blk_size[b], compression);
         data_size = file.size();
         std::string hv;
         put_handle(hv, h);
@@ -273,7 +352,7 @@ int32_t sst_encode(const uint8_t *data, const uint64_t *blk_off, const uint32_t 
     num("rocksdb.raw.key.size", raw_key);
     num("rocksdb.raw.value.size", raw_val);
     props["rocksdb.comparator"] = "leveldb.BytewiseComparator";
-    props["rocksdb.compression"] = "NoCompression";
+    props["rocksdb.compression"] = compression == kLZ4Compression ? "LZ4" : "NoCompression";
     props["rocksdb.filter.policy"] = "rocksdb.BuiltinBloomFilter";
     props["rocksdb.prefix.extractor.name"] = "HashkeyTransform";
     KvBlock pb(1);
@@ -297,15 +376,23 @@ int32_t sst_encode(const uint8_t *data, const uint64_t *blk_off, const uint32_t 
     return PGS_OK;
 }
 
-static int32_t read_block(const uint8_t *sst, uint64_t size, Handle h, std::string_view &out)
+// `inflated` keeps the bytes of a block that was stored compressed (out points into it then)
+static int32_t read_block(const uint8_t *sst, uint64_t size, Handle h, std::string_view &out, std::string &inflated)
 {
     if (h.off > size || h.size + 5 > size - h.off) return PGS_CORRUPTION;
     const uint8_t *b = sst + h.off;
-    if (b[h.size] != 0) return PGS_NOT_SUPPORTED; // a compressed block
+    const uint8_t type = b[h.size];
+    if (type != kNoCompression && type != kLZ4Compression) return PGS_NOT_SUPPORTED; // snappy / zstd / ...: later slices
     uint32_t stored;
     memcpy(&stored, b + h.size + 1, 4);
     if (crc_mask(crc32c(0, b, h.size + 1)) != stored) return PGS_CORRUPTION;
-    out = std::string_view((const char *)b, h.size);
+    if (type == kNoCompression) { out = std::string_view((const char *)b, h.size); return PGS_OK; }
+    uint32_t raw = 0;
+    const uint8_t *p = get_v32(b, b + h.size, &raw);
+    if (!p || raw > (64u << 20)) return PGS_CORRUPTION;
+    inflated.assign(raw, '\0');
+    if (!lz4_decompress(p, (size_t)(b + h.size - p), (uint8_t *)inflated.data(), raw)) return PGS_CORRUPTION;
+    out = inflated;
     return PGS_OK;
 }
 
@@ -326,8 +413,9 @@ int32_t sst_decode(const uint8_t *sst, uint64_t size, std::string &data, std::ve
     if (!(p = get_v64(p, lim, &mh.off)) || !(p = get_v64(p, lim, &mh.size)) || !(p = get_v64(p, lim, &ih.off)) || !(p = get_v64(p, lim, &ih.size)))
         return PGS_CORRUPTION;
     std::string_view meta, index;
-    int32_t rc = read_block(sst, size, mh, meta);
-    if (rc == PGS_OK) rc = read_block(sst, size, ih, index);
+    std::string meta_buf, index_buf, blk_buf;
+    int32_t rc = read_block(sst, size, mh, meta, meta_buf);
+    if (rc == PGS_OK) rc = read_block(sst, size, ih, index, index_buf);
     if (rc != PGS_OK) return rc;
     if (filter_out) {
         filter_out->clear();
@@ -342,7 +430,7 @@ int32_t sst_decode(const uint8_t *sst, uint64_t size, std::string &data, std::ve
             return PGS_CORRUPTION;
         if (found) {
             std::string_view fb;
-            if ((rc = read_block(sst, size, fh, fb)) != PGS_OK) return rc;
+            if ((rc = read_block(sst, size, fh, fb, blk_buf)) != PGS_OK) return rc;
             filter_out->assign(fb.data(), fb.size());
         }
     }
@@ -356,7 +444,7 @@ int32_t sst_decode(const uint8_t *sst, uint64_t size, std::string &data, std::ve
         return PGS_CORRUPTION;
     for (const Handle &h : blocks) {
         std::string_view blk;
-        if ((rc = read_block(sst, size, h, blk)) != PGS_OK) return rc;
+        if ((rc = read_block(sst, size, h, blk, blk_buf)) != PGS_OK) return rc;
         if (blk.size() > 0xffffffffull) return PGS_NOT_SUPPORTED;
         data.resize((data.size() + 15) & ~(size_t)15, '\0');
         off.push_back(data.size());
@@ -384,6 +472,35 @@ int32_t pgs_sst_encode(const uint8_t *data, const uint64_t *blk_off, const uint3
     *out_size = file.size();
     if (!out || out_cap < file.size()) return PGS_INCOMPLETE; // *out_size tells how much room the image needs
     memcpy(out, file.data(), file.size());
+    return PGS_OK;
+}
+
+int32_t pgs_sst_encode_ex(const uint8_t *data, const uint64_t *blk_off, const uint32_t *blk_size, uint32_t n_blocks, uint32_t compression,
+                          uint8_t *out, uint64_t out_cap, uint64_t *out_size)
+{
+    if (!out_size || (n_blocks && (!data || !blk_off || !blk_size))) return PGS_INVALID_ARGUMENT;
+    if (compression != kNoCompression && compression != kLZ4Compression) return PGS_NOT_SUPPORTED;
+    std::string file;
+    const int32_t rc = sst_encode(data, blk_off, blk_size, n_blocks, file, (uint8_t)compression);
+    if (rc != PGS_OK) return rc;
+    *out_size = file.size();
+    if (!out || out_cap < file.size()) return PGS_INCOMPLETE;
+    memcpy(out, file.data(), file.size());
+    return PGS_OK;
+}
+
+int32_t pgs_lz4_block(int32_t decompress, const uint8_t *in, uint64_t n, uint8_t *out, uint64_t out_cap, uint64_t *out_size)
+{
+    if (!in || !out || !out_size) return PGS_INVALID_ARGUMENT;
+    if (decompress) {
+        if (!lz4_decompress(in, n, out, out_cap)) return PGS_CORRUPTION; // out_cap = the exact raw size
+        *out_size = out_cap;
+        return PGS_OK;
+    }
+    const std::string c = lz4_compress(in, n);
+    *out_size = c.size();
+    if (c.size() > out_cap) return PGS_INCOMPLETE;
+    memcpy(out, c.data(), c.size());
     return PGS_OK;
 }
 
@@ -427,6 +544,20 @@ int32_t pgs_sst_export(pgs_partition *p, uint64_t run_id, uint8_t *out, uint64_t
     rc = pgs_run_download(p, run_id, data.data(), data.size(), off.data(), sz.data(), info.n_blocks);
     if (rc != PGS_OK) return rc;
     return pgs_sst_encode(data.data(), off.data(), sz.data(), info.n_blocks, out, out_cap, out_size);
+}
+
+int32_t pgs_sst_export_ex(pgs_partition *p, uint64_t run_id, uint32_t compression, uint8_t *out, uint64_t out_cap, uint64_t *out_size)
+{
+    if (!p || !out_size) return PGS_INVALID_ARGUMENT;
+    pgs_run_info info;
+    int32_t rc = pgs_run_info_get(p, run_id, &info);
+    if (rc != PGS_OK) return rc;
+    std::vector<uint8_t> data(info.data_bytes + 16);
+    std::vector<uint64_t> off(info.n_blocks + 1);
+    std::vector<uint32_t> sz(info.n_blocks + 1);
+    rc = pgs_run_download(p, run_id, data.data(), data.size(), off.data(), sz.data(), info.n_blocks);
+    if (rc != PGS_OK) return rc;
+    return pgs_sst_encode_ex(data.data(), off.data(), sz.data(), info.n_blocks, compression, out, out_cap, out_size);
 }
 
 int32_t pgs_sst_ingest(pgs_partition *p, int32_t level, const uint8_t *sst, uint64_t size, uint64_t *run_id_out)

@@ -768,6 +768,46 @@ int32_t orc_rrdb_put(orc_server *h, pgs_blob key, pgs_blob value, uint32_t expir
     put_one(h->s, bsv2(key), bsv2(value), expire_ts, timestamp_us, now);
     return PGS_OK;
 }
+// incr: pegasus_write_service_impl.h:264-342 (buf2int64: src/utils/string_conv.h:35-62; safe_add: src/utils/safe_arithmetic.h:44, int64 overflow check)
+int32_t orc_rrdb_incr(orc_server *h, pgs_blob key, int64_t increment, int32_t expire_ts_seconds, int64_t decree, uint64_t timestamp_us,
+                      uint32_t now, int32_t *resp_error, int64_t *new_value)
+{
+    Server &s = h->s;
+    s.last_committed_decree = decree;
+    *new_value = 0;
+    s.prepare_read(now, false);
+    std::string value;
+    const bool found = s.db_get(bsv2(key), &value);
+    const uint32_t old_ets = found ? extract_expire_ts(s.data_version, value) : 0;
+    int64_t nv = increment;
+    uint32_t new_ets = expire_ts_seconds > 0 ? (uint32_t)expire_ts_seconds : 0u;
+    if (found && !ts_expired(now, old_ets)) {
+        const std::string old(s.user_data(value));
+        if (!old.empty()) {
+            errno = 0;
+            char *p = nullptr;
+            const long long base = std::strtoll(old.c_str(), &p, 0);
+            if ((size_t)(p - old.c_str()) != old.size() || errno != 0) {
+                *resp_error = PGS_INVALID_ARGUMENT;
+                put_one(s, sv(), sv(), 0, timestamp_us, now); // empty_put: the decree still advances
+                return PGS_OK;
+            }
+            long long sum;
+            if (__builtin_add_overflow(base, (long long)increment, &sum)) {
+                *resp_error = PGS_INVALID_ARGUMENT;
+                *new_value = base;
+                put_one(s, sv(), sv(), 0, timestamp_us, now);
+                return PGS_OK;
+            }
+            nv = sum;
+        }
+        new_ets = expire_ts_seconds == 0 ? old_ets : expire_ts_seconds < 0 ? 0u : (uint32_t)expire_ts_seconds;
+    }
+    put_one(s, bsv2(key), std::to_string(nv), new_ets, timestamp_us, now);
+    *resp_error = PGS_OK;
+    *new_value = nv;
+    return PGS_OK;
+}
 int32_t orc_rrdb_remove(orc_server *h, pgs_blob key, int64_t decree, uint32_t now)
 {
     h->s.last_committed_decree = decree;

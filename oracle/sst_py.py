@@ -61,6 +61,35 @@ def get_varint(b: bytes, p: int):
         s += 7
 
 
+def lz4_block_decode(b: bytes, raw_size: int) -> bytes:
+    """LZ4 block format (lz4_Block_format.md): token | literal length bytes | literals | offset LE16 | match length bytes"""
+    out, p = bytearray(), 0
+    while p < len(b):
+        tok = b[p]; p += 1
+        lit = tok >> 4
+        if lit == 15:
+            while True:
+                x = b[p]; p += 1; lit += x
+                if x != 255:
+                    break
+        out += b[p:p + lit]; p += lit
+        if p >= len(b):
+            break
+        off = b[p] | (b[p + 1] << 8); p += 2
+        ml = tok & 15
+        if ml == 15:
+            while True:
+                x = b[p]; p += 1; ml += x
+                if x != 255:
+                    break
+        ml += 4
+        assert 0 < off <= len(out)
+        for _ in range(ml):
+            out.append(out[-off])
+    assert len(out) == raw_size
+    return bytes(out)
+
+
 def build_block(entries, restart_interval: int) -> bytes:
     buf, restarts, last, counter = bytearray(), [0], b"", 0
     for k, v in entries:
@@ -196,15 +225,20 @@ def write_sst(blocks, restart_interval: int = 16) -> bytes:
 def read_sst(sst: bytes):
     """-> dict(records=[(user_key, seq, type, value)], blocks=[[...]], filter=bytes, props={...}, index_keys=[...]); raises on a bad checksum"""
     assert len(sst) >= 53
+    stats = {"lz4_blocks": 0}
     foot = sst[-53:]
     assert struct.unpack_from("<Q", foot, 45)[0] == MAGIC and struct.unpack_from("<I", foot, 41)[0] == 2 and foot[0] == 1
     p = 1
     mo, p = get_varint(foot, p); ms, p = get_varint(foot, p); io, p = get_varint(foot, p); isz, p = get_varint(foot, p)
 
     def block(off, size):
-        b = sst[off:off + size]
-        assert sst[off + size] == 0, "compressed block"
-        assert struct.unpack_from("<I", sst, off + size + 1)[0] == mask(crc32c(b + b"\x00")), "bad block checksum"
+        b, typ = sst[off:off + size], sst[off + size]
+        assert typ in (0, 4), "unsupported block type"
+        assert struct.unpack_from("<I", sst, off + size + 1)[0] == mask(crc32c(b + bytes([typ]))), "bad block checksum"
+        if typ == 4:  # kLZ4Compression, compress_format_version 2: varint32 raw size | LZ4 block
+            raw, p = get_varint(b, 0)
+            b = lz4_block_decode(b[p:], raw)
+            stats["lz4_blocks"] += 1
         return b
 
     def handle(v):
@@ -224,4 +258,4 @@ def read_sst(sst: bytes):
             recs.append((ik[:-8], t >> 8, t & 0xFF, v))
         blocks.append(recs)
         records += recs
-    return {"records": records, "blocks": blocks, "filter": filt, "props": props, "index_keys": [k for k, _ in idx]}
+    return {"records": records, "blocks": blocks, "filter": filt, "props": props, "index_keys": [k for k, _ in idx], **stats}

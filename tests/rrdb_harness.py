@@ -68,6 +68,7 @@ class Backend:
             "rrdb_scan": [vp, C.c_int64, C.c_uint32, vp], "rrdb_clear_scanner": [vp, C.c_int64],
             "rrdb_put": [vp, Blob, Blob, C.c_uint32, C.c_int64, C.c_uint64, C.c_uint32],
             "rrdb_remove": [vp, Blob, C.c_int64, C.c_uint32],
+            "rrdb_incr": [vp, Blob, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int64)],
             "rrdb_multi_put": [vp, Blob, C.POINTER(Blob), C.POINTER(Blob), C.c_uint32, C.c_uint32, C.c_int64,
                                C.c_uint64, C.c_uint32],
             "rrdb_multi_remove": [vp, Blob, C.POINTER(Blob), C.c_uint32, C.c_int64, C.POINTER(C.c_int64), C.c_uint32],
@@ -112,6 +113,14 @@ class Backend:
         keep = []
         self.decree += 1
         return self.f("rrdb_put")(self.h, blob(raw_key(hk, sk), keep), blob(value, keep), expire_ts, self.decree, ts_us, now)
+
+    def incr(self, hk, sk, increment, expire_ts_seconds=0, now=0, ts_us=1):
+        """-> (return code, response error, response new_value)"""
+        keep = []
+        self.decree += 1
+        e, v = C.c_int32(-1), C.c_int64(0)
+        rc = self.f("rrdb_incr")(self.h, blob(raw_key(hk, sk), keep), increment, expire_ts_seconds, self.decree, ts_us, now, C.byref(e), C.byref(v))
+        return rc, e.value, v.value
 
     def remove(self, hk, sk, now=0):
         keep = []
