@@ -448,6 +448,47 @@ PGS_API int32_t pgs_rrdb_remove(pgs_server *s, pgs_blob raw_key, int64_t decree,
 PGS_API int32_t pgs_rrdb_incr(pgs_server *s, pgs_blob raw_key, int64_t increment, int32_t expire_ts_seconds,
                               int64_t decree, uint64_t timestamp_us, uint32_t now, int32_t *resp_error,
                               int64_t *new_value);
+/* check_and_set / check_and_mutate (pegasus_write_service_impl.h:436-530, 710-840; RPC_RRDB_RRDB_CHECK_AND_SET / _MUTATE): the
+ * value of (hash_key, check_sort_key) is read, validate_check (:1144-1270) compares it with check_operand by check_type
+ * (rrdb.thrift cas_check_type 0..17), and only if the check passes the writes are applied.  The call returns kOk whenever the
+ * storage worked; res->error carries what the client sees: kOk, kTryAgain (check failed), kInvalidArgument (unsupported check
+ * type / empty or bad mutate list / a value that is not an int64 for the integer compares).  A failed request still writes an
+ * empty record so that the decree advances.  The checked value comes back in check_value_out (res->check_value_len = its full
+ * length) when return_check_value is set. */
+typedef struct {
+    uint32_t operation; /* 0 = MO_PUT, 1 = MO_DELETE */
+    pgs_blob sort_key;
+    pgs_blob value;
+    int32_t set_expire_ts_seconds;
+} pgs_mutate;
+typedef struct {
+    pgs_blob hash_key, check_sort_key;
+    int32_t check_type;
+    pgs_blob check_operand;
+    const pgs_mutate *mutate_list;
+    uint32_t n_mutate;
+    uint8_t return_check_value;
+} pgs_check_and_mutate_request;
+typedef struct {
+    pgs_blob hash_key, check_sort_key;
+    int32_t check_type;
+    pgs_blob check_operand;
+    uint8_t set_diff_sort_key; /* 0: the set goes to check_sort_key */
+    pgs_blob set_sort_key, set_value;
+    int32_t set_expire_ts_seconds;
+    uint8_t return_check_value;
+} pgs_check_and_set_request;
+typedef struct {
+    int32_t error;
+    uint8_t check_value_returned, check_value_exist, reserved[2];
+    uint32_t check_value_len;
+} pgs_cas_result;
+PGS_API int32_t pgs_rrdb_check_and_set(pgs_server *s, const pgs_check_and_set_request *req, int64_t decree,
+                                       uint64_t timestamp_us, uint32_t now, pgs_cas_result *res,
+                                       uint8_t *check_value_out, uint32_t check_value_cap);
+PGS_API int32_t pgs_rrdb_check_and_mutate(pgs_server *s, const pgs_check_and_mutate_request *req, int64_t decree,
+                                          uint64_t timestamp_us, uint32_t now, pgs_cas_result *res,
+                                          uint8_t *check_value_out, uint32_t check_value_cap);
 PGS_API int32_t pgs_rrdb_multi_put(pgs_server *s, pgs_blob hash_key, const pgs_blob *sort_keys,
                                    const pgs_blob *values, uint32_t n, uint32_t expire_ts_seconds,
                                    int64_t decree, uint64_t timestamp_us, uint32_t now);

@@ -819,6 +819,103 @@ int32_t pgs_rrdb_incr(pgs_server *h, pgs_blob key, int64_t increment, int32_t ex
     *new_value = nv;
     return PGS_OK;
 }
+
+// validate_check (pegasus_write_service_impl.h:1144-1270)
+static bool cas_validate(int32_t type, std::string_view operand, bool exist, std::string_view value, bool &invalid)
+{
+    invalid = false;
+    switch (type) {
+    case 0: return true;                              // CT_NO_CHECK
+    case 1: return !exist;                            // CT_VALUE_NOT_EXIST
+    case 2: return !exist || value.empty();           // CT_VALUE_NOT_EXIST_OR_EMPTY
+    case 3: return exist;                             // CT_VALUE_EXIST
+    case 4: return exist && !value.empty();           // CT_VALUE_NOT_EMPTY
+    case 5: case 6: case 7:                           // CT_VALUE_MATCH_ANYWHERE / PREFIX / POSTFIX
+        if (!exist) return false;
+        if (operand.empty()) return true;
+        if (value.size() < operand.size()) return false;
+        if (type == 5) return value.find(operand) != std::string_view::npos;
+        if (type == 6) return value.substr(0, operand.size()) == operand;
+        return value.substr(value.size() - operand.size()) == operand;
+    case 8: case 9: case 10: case 11: case 12: {      // CT_VALUE_BYTES_LESS .. GREATER
+        if (!exist) return false;
+        const int c = value.compare(operand);
+        if (c < 0) return type <= 9;
+        if (c > 0) return type >= 11;
+        return type >= 9 && type <= 11;
+    }
+    case 13: case 14: case 15: case 16: case 17: {    // CT_VALUE_INT_LESS .. GREATER
+        if (!exist) return false;
+        int64_t a = 0, b = 0;
+        if (!buf2int64(value, a) || !buf2int64(operand, b)) { invalid = true; return false; }
+        if (a < b) return type <= 14;
+        if (a > b) return type >= 16;
+        return type >= 14 && type <= 16;
+    }
+    }
+    return false;
+}
+
+static int32_t check_and_mutate(Server &s, const pgs_check_and_mutate_request &q, int64_t decree, uint64_t timestamp_us, uint32_t now,
+                                pgs_cas_result *res, uint8_t *cv_out, uint32_t cv_cap)
+{
+    s.last_committed_decree = decree;
+    pgs_cas_result dummy;
+    if (!res) res = &dummy;
+    *res = pgs_cas_result{};
+    bool bad = q.n_mutate == 0 || q.check_type < 0 || q.check_type > 17; // empty list / unsupported check type
+    for (uint32_t i = 0; i < q.n_mutate && !bad; i++) bad = q.mutate_list[i].operation > 1;
+    if (bad) {
+        res->error = PGS_INVALID_ARGUMENT;
+        s.put_one({}, {}, 0, timestamp_us, now); // empty_put: the decree still advances
+        return PGS_OK;
+    }
+    std::vector<pgs_get_result> gr;
+    std::vector<uint8_t> arena;
+    const int32_t st = point_lookup(s, {make_key(bsv(q.hash_key), bsv(q.check_sort_key))}, now, gr, arena);
+    if (st != PGS_OK) { res->error = st; return st; }
+    const bool exist = gr[0].status == PGS_OK;
+    const std::string_view value = exist ? std::string_view((const char *)arena.data() + gr[0].value_off, gr[0].value_len) : std::string_view();
+    if (q.return_check_value) {
+        res->check_value_returned = 1;
+        if (exist) {
+            res->check_value_exist = 1;
+            res->check_value_len = (uint32_t)value.size();
+            if (cv_out && cv_cap) memcpy(cv_out, value.data(), std::min<size_t>(cv_cap, value.size()));
+        }
+    }
+    bool invalid = false;
+    const bool passed = cas_validate(q.check_type, bsv(q.check_operand), exist, value, invalid);
+    if (passed) {
+        for (uint32_t i = 0; i < q.n_mutate; i++) {
+            const pgs_mutate &m = q.mutate_list[i];
+            const std::string key = make_key(bsv(q.hash_key), bsv(m.sort_key));
+            if (m.operation == 0) s.put_one(key, bsv(m.value), (uint32_t)m.set_expire_ts_seconds, timestamp_us, now);
+            else s.mem_write(key, PGS_TYPE_DELETION, std::string(), now);
+        }
+        res->error = PGS_OK;
+    } else {
+        s.put_one({}, {}, 0, timestamp_us, now);
+        res->error = invalid ? PGS_INVALID_ARGUMENT : PGS_TRY_AGAIN;
+    }
+    return PGS_OK;
+}
+int32_t pgs_rrdb_check_and_mutate(pgs_server *h, const pgs_check_and_mutate_request *q, int64_t decree, uint64_t timestamp_us, uint32_t now,
+                                  pgs_cas_result *res, uint8_t *cv_out, uint32_t cv_cap)
+{
+    if (!h || !q) return PGS_INVALID_ARGUMENT;
+    WLOCKED(h);
+    return check_and_mutate(h->s, *q, decree, timestamp_us, now, res, cv_out, cv_cap);
+}
+int32_t pgs_rrdb_check_and_set(pgs_server *h, const pgs_check_and_set_request *q, int64_t decree, uint64_t timestamp_us, uint32_t now,
+                               pgs_cas_result *res, uint8_t *cv_out, uint32_t cv_cap)
+{
+    if (!h || !q) return PGS_INVALID_ARGUMENT;
+    WLOCKED(h);
+    pgs_mutate m{0, q->set_diff_sort_key ? q->set_sort_key : q->check_sort_key, q->set_value, q->set_expire_ts_seconds};
+    pgs_check_and_mutate_request r{q->hash_key, q->check_sort_key, q->check_type, q->check_operand, &m, 1, q->return_check_value};
+    return check_and_mutate(h->s, r, decree, timestamp_us, now, res, cv_out, cv_cap);
+}
 int32_t pgs_rrdb_multi_put(pgs_server *h, pgs_blob hash_key, const pgs_blob *sort_keys, const pgs_blob *values,
                            uint32_t n, uint32_t expire_ts, int64_t decree, uint64_t timestamp_us, uint32_t now)
 {

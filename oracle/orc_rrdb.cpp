@@ -808,6 +808,105 @@ int32_t orc_rrdb_incr(orc_server *h, pgs_blob key, int64_t increment, int32_t ex
     *new_value = nv;
     return PGS_OK;
 }
+static bool orc_buf2int64(sv buf, int64_t &out) // dsn::buf2int64, src/utils/string_conv.h:35-62
+{
+    if (buf.empty()) return false;
+    const std::string str(buf);
+    errno = 0;
+    char *p = nullptr;
+    const long long v = std::strtoll(str.c_str(), &p, 0);
+    if ((size_t)(p - str.c_str()) != str.size() || errno != 0) return false;
+    out = v;
+    return true;
+}
+
+// validate_check (pegasus_write_service_impl.h:1144-1270)
+static bool cas_validate(int32_t type, sv operand, bool exist, sv value, bool &invalid)
+{
+    invalid = false;
+    switch (type) {
+    case 0: return true;                              // CT_NO_CHECK
+    case 1: return !exist;                            // CT_VALUE_NOT_EXIST
+    case 2: return !exist || value.empty();           // CT_VALUE_NOT_EXIST_OR_EMPTY
+    case 3: return exist;                             // CT_VALUE_EXIST
+    case 4: return exist && !value.empty();           // CT_VALUE_NOT_EMPTY
+    case 5: case 6: case 7:                           // CT_VALUE_MATCH_ANYWHERE / PREFIX / POSTFIX
+        if (!exist) return false;
+        if (operand.empty()) return true;
+        if (value.size() < operand.size()) return false;
+        if (type == 5) return value.find(operand) != sv::npos;
+        if (type == 6) return value.substr(0, operand.size()) == operand;
+        return value.substr(value.size() - operand.size()) == operand;
+    case 8: case 9: case 10: case 11: case 12: {      // CT_VALUE_BYTES_LESS .. GREATER
+        if (!exist) return false;
+        const int c = value.compare(operand);
+        if (c < 0) return type <= 9;
+        if (c > 0) return type >= 11;
+        return type >= 9 && type <= 11;
+    }
+    case 13: case 14: case 15: case 16: case 17: {    // CT_VALUE_INT_LESS .. GREATER
+        if (!exist) return false;
+        int64_t a = 0, b = 0;
+        if (!orc_buf2int64(value, a) || !orc_buf2int64(operand, b)) { invalid = true; return false; }
+        if (a < b) return type <= 14;
+        if (a > b) return type >= 16;
+        return type >= 14 && type <= 16;
+    }
+    }
+    return false;
+}
+
+// check_and_mutate: pegasus_write_service_impl.h:710-840 (check_and_set :436-530 is the one-put case)
+int32_t orc_rrdb_check_and_mutate(orc_server *h, const pgs_check_and_mutate_request *q, int64_t decree, uint64_t timestamp_us, uint32_t now,
+                                  pgs_cas_result *res, uint8_t *cv_out, uint32_t cv_cap)
+{
+    Server &s = h->s;
+    s.last_committed_decree = decree;
+    *res = pgs_cas_result{};
+    bool bad = q->n_mutate == 0 || q->check_type < 0 || q->check_type > 17;
+    for (uint32_t i = 0; i < q->n_mutate && !bad; i++) bad = q->mutate_list[i].operation > 1;
+    if (bad) {
+        res->error = PGS_INVALID_ARGUMENT;
+        put_one(s, sv(), sv(), 0, timestamp_us, now);
+        return PGS_OK;
+    }
+    s.prepare_read(now, false);
+    std::string raw;
+    const std::string ck = generate_key(bsv2(q->hash_key), bsv2(q->check_sort_key));
+    bool exist = s.db_get(ck, &raw);
+    if (exist && ts_expired(now, extract_expire_ts(s.data_version, raw))) exist = false;
+    const std::string value = exist ? std::string(s.user_data(raw)) : std::string();
+    if (q->return_check_value) {
+        res->check_value_returned = 1;
+        if (exist) {
+            res->check_value_exist = 1;
+            res->check_value_len = (uint32_t)value.size();
+            if (cv_out && cv_cap) memcpy(cv_out, value.data(), std::min<size_t>(cv_cap, value.size()));
+        }
+    }
+    bool invalid = false;
+    const bool passed = cas_validate(q->check_type, bsv2(q->check_operand), exist, value, invalid);
+    if (passed) {
+        for (uint32_t i = 0; i < q->n_mutate; i++) {
+            const pgs_mutate &m = q->mutate_list[i];
+            const std::string key = generate_key(bsv2(q->hash_key), bsv2(m.sort_key));
+            if (m.operation == 0) put_one(s, key, bsv2(m.value), (uint32_t)m.set_expire_ts_seconds, timestamp_us, now);
+            else del_one(s, key, now);
+        }
+        res->error = PGS_OK;
+    } else {
+        put_one(s, sv(), sv(), 0, timestamp_us, now);
+        res->error = invalid ? PGS_INVALID_ARGUMENT : PGS_TRY_AGAIN;
+    }
+    return PGS_OK;
+}
+int32_t orc_rrdb_check_and_set(orc_server *h, const pgs_check_and_set_request *q, int64_t decree, uint64_t timestamp_us, uint32_t now,
+                               pgs_cas_result *res, uint8_t *cv_out, uint32_t cv_cap)
+{
+    pgs_mutate m{0, q->set_diff_sort_key ? q->set_sort_key : q->check_sort_key, q->set_value, q->set_expire_ts_seconds};
+    pgs_check_and_mutate_request r{q->hash_key, q->check_sort_key, q->check_type, q->check_operand, &m, 1, q->return_check_value};
+    return orc_rrdb_check_and_mutate(h, &r, decree, timestamp_us, now, res, cv_out, cv_cap);
+}
 int32_t orc_rrdb_remove(orc_server *h, pgs_blob key, int64_t decree, uint32_t now)
 {
     h->s.last_committed_decree = decree;

@@ -180,6 +180,10 @@ ORC_API int32_t orc_rrdb_put(orc_server *s, pgs_blob key, pgs_blob value, uint32
                              int64_t decree, uint64_t timestamp_us, uint32_t now);
 ORC_API int32_t orc_rrdb_incr(orc_server *s, pgs_blob raw_key, int64_t increment, int32_t expire_ts_seconds, int64_t decree,
                               uint64_t timestamp_us, uint32_t now, int32_t *resp_error, int64_t *new_value);
+ORC_API int32_t orc_rrdb_check_and_set(orc_server *s, const pgs_check_and_set_request *req, int64_t decree, uint64_t timestamp_us,
+                                       uint32_t now, pgs_cas_result *res, uint8_t *check_value_out, uint32_t check_value_cap);
+ORC_API int32_t orc_rrdb_check_and_mutate(orc_server *s, const pgs_check_and_mutate_request *req, int64_t decree, uint64_t timestamp_us,
+                                          uint32_t now, pgs_cas_result *res, uint8_t *check_value_out, uint32_t check_value_cap);
 ORC_API int32_t orc_rrdb_remove(orc_server *s, pgs_blob key, int64_t decree, uint32_t now);
 ORC_API int32_t orc_rrdb_multi_put(orc_server *s, pgs_blob hash_key, const pgs_blob *sort_keys,
                                    const pgs_blob *values, uint32_t n, uint32_t expire_ts,

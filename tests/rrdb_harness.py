@@ -28,6 +28,26 @@ def next_blob(b: bytes) -> bytes:
     return bytes(b)
 
 
+class Mutate(C.Structure):
+    _fields_ = [("operation", C.c_uint32), ("sort_key", Blob), ("value", Blob), ("set_expire_ts_seconds", C.c_int32)]
+
+
+class CheckAndMutateRequest(C.Structure):
+    _fields_ = [("hash_key", Blob), ("check_sort_key", Blob), ("check_type", C.c_int32), ("check_operand", Blob),
+                ("mutate_list", C.POINTER(Mutate)), ("n_mutate", C.c_uint32), ("return_check_value", C.c_uint8)]
+
+
+class CheckAndSetRequest(C.Structure):
+    _fields_ = [("hash_key", Blob), ("check_sort_key", Blob), ("check_type", C.c_int32), ("check_operand", Blob),
+                ("set_diff_sort_key", C.c_uint8), ("set_sort_key", Blob), ("set_value", Blob), ("set_expire_ts_seconds", C.c_int32),
+                ("return_check_value", C.c_uint8)]
+
+
+class CasResult(C.Structure):
+    _fields_ = [("error", C.c_int32), ("check_value_returned", C.c_uint8), ("check_value_exist", C.c_uint8), ("reserved", C.c_uint8 * 2),
+                ("check_value_len", C.c_uint32)]
+
+
 class Backend:
     def __init__(self, kind: str, engine=None, app_id=1, pidx=0, opts: dict | None = None, envs: dict | None = None):
         self.kind = kind
@@ -68,6 +88,8 @@ class Backend:
             "rrdb_scan": [vp, C.c_int64, C.c_uint32, vp], "rrdb_clear_scanner": [vp, C.c_int64],
             "rrdb_put": [vp, Blob, Blob, C.c_uint32, C.c_int64, C.c_uint64, C.c_uint32],
             "rrdb_remove": [vp, Blob, C.c_int64, C.c_uint32],
+            "rrdb_check_and_set": [vp, C.POINTER(CheckAndSetRequest), C.c_int64, C.c_uint64, C.c_uint32, C.POINTER(CasResult), vp, C.c_uint32],
+            "rrdb_check_and_mutate": [vp, C.POINTER(CheckAndMutateRequest), C.c_int64, C.c_uint64, C.c_uint32, C.POINTER(CasResult), vp, C.c_uint32],
             "rrdb_incr": [vp, Blob, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int64)],
             "rrdb_multi_put": [vp, Blob, C.POINTER(Blob), C.POINTER(Blob), C.c_uint32, C.c_uint32, C.c_int64,
                                C.c_uint64, C.c_uint32],
@@ -121,6 +143,38 @@ class Backend:
         e, v = C.c_int32(-1), C.c_int64(0)
         rc = self.f("rrdb_incr")(self.h, blob(raw_key(hk, sk), keep), increment, expire_ts_seconds, self.decree, ts_us, now, C.byref(e), C.byref(v))
         return rc, e.value, v.value
+
+    def _cas_out(self, rc, res, buf):
+        return {"rc": rc, "error": res.error, "returned": bool(res.check_value_returned), "exist": bool(res.check_value_exist),
+                "check_value": bytes(buf[:res.check_value_len]) if res.check_value_exist else None}
+
+    def check_and_set(self, hk, check_sk, check_type, operand, set_sk, set_value, return_check_value=True, ttl_ts=0, now=0, ts_us=1):
+        keep = []
+        self.decree += 1
+        q = CheckAndSetRequest()
+        q.hash_key, q.check_sort_key, q.check_type, q.check_operand = blob(hk, keep), blob(check_sk, keep), check_type, blob(operand, keep)
+        q.set_diff_sort_key, q.set_sort_key, q.set_value = int(set_sk != check_sk), blob(set_sk, keep), blob(set_value, keep)
+        q.set_expire_ts_seconds, q.return_check_value = ttl_ts, int(return_check_value)
+        res, buf = CasResult(), (C.c_uint8 * 4096)()
+        rc = self.f("rrdb_check_and_set")(self.h, C.byref(q), self.decree, ts_us, now, C.byref(res), buf, 4096)
+        return self._cas_out(rc, res, buf)
+
+    def check_and_mutate(self, hk, check_sk, check_type, operand, mutations, return_check_value=True, now=0, ts_us=1):
+        """mutations: list of ("put", sort_key, value, expire_ts) / ("del", sort_key)"""
+        keep = []
+        self.decree += 1
+        arr = (Mutate * max(1, len(mutations)))()
+        for i, m in enumerate(mutations):
+            arr[i].operation = {"put": 0, "del": 1}.get(m[0], m[0] if isinstance(m[0], int) else 9)
+            arr[i].sort_key = blob(m[1], keep)
+            arr[i].value = blob(m[2] if len(m) > 2 else b"", keep)
+            arr[i].set_expire_ts_seconds = m[3] if len(m) > 3 else 0
+        q = CheckAndMutateRequest()
+        q.hash_key, q.check_sort_key, q.check_type, q.check_operand = blob(hk, keep), blob(check_sk, keep), check_type, blob(operand, keep)
+        q.mutate_list, q.n_mutate, q.return_check_value = arr, len(mutations), int(return_check_value)
+        res, buf = CasResult(), (C.c_uint8 * 4096)()
+        rc = self.f("rrdb_check_and_mutate")(self.h, C.byref(q), self.decree, ts_us, now, C.byref(res), buf, 4096)
+        return self._cas_out(rc, res, buf)
 
     def remove(self, hk, sk, now=0):
         keep = []
