@@ -141,6 +141,32 @@ def test_corrupt_and_unsupported_uploads(pgs, engine):
         part.close()
 
 
+def test_upload_many_is_all_or_nothing(pgs, engine):
+    """a damaged run in the middle of a pipelined upload: the call fails, no run of it stays installed, the partition still works;
+    a multi-chunk run (> 32 MB) goes through the chunked copy + per-chunk index pass"""
+    runs = [pgs.build_run(r) for r in synth.compaction_runs(k=3, n_per_run=800, seed=6)]
+    part = engine.partition()
+    try:
+        bad = pgs.BlockRun(runs[1].data.copy(), runs[1].blk_off, runs[1].blk_size)
+        bad.data[int(bad.blk_off[2]) + 1] = 0xFF
+        bad.data[int(bad.blk_off[2]) + 2] = 0xFF
+        with pytest.raises(pgs.PegasusError) as e:
+            part.upload_many([runs[0], bad, runs[2]])
+        assert e.value.code == pgs.CORRUPTION and part.runs() == []
+        ids = part.upload_many(runs + [pgs.BlockRun(np.zeros(0, np.uint8), np.zeros(0, np.uint64), np.zeros(0, np.uint32))])
+        assert ids[3] == 0 and sorted(part.runs()) == sorted(ids[:3])
+        for rid, r in zip(ids, runs):
+            assert pgs.decode_blocks(part.download(rid)).same_as(pgs.decode_blocks(r))
+        big = pgs.build_run(synth.compaction_runs(k=1, n_per_run=150_000, seed=9)[0])  # ~48 MB of blocks: two chunks
+        assert big.data.shape[0] > (32 << 20)
+        rid = part.upload_many([big])[0]
+        info = part.run_info(rid)
+        assert info.n_records == 150_000 and info.n_blocks == big.n_blocks
+        assert pgs.decode_blocks(part.download(rid)).same_as(pgs.decode_blocks(big))
+    finally:
+        part.close()
+
+
 def test_empty_partition_reads(engine):
     g, o = Backend("gpu", engine), Backend("oracle")
     try:
