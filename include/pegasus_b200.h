@@ -441,6 +441,22 @@ PGS_API int32_t pgs_rrdb_put(pgs_server *s, pgs_blob raw_key, pgs_blob user_valu
                              uint32_t expire_ts_seconds, int64_t decree, uint64_t timestamp_us,
                              uint32_t now);
 PGS_API int32_t pgs_rrdb_remove(pgs_server *s, pgs_blob raw_key, int64_t decree, uint32_t now);
+/* on_batched_write_requests (src/server/pegasus_server_write.cpp:92-222): one decree's worth of batchable writes -- single puts
+ * and removes -- applied as one batch by the replica's single writer.  count == 0 is RPC_REPLICATION_WRITE_EMPTY: an empty
+ * record that only advances the decree.  The return value is the apply status the replication layer sees (kOk unless the
+ * storage failed; an unknown operation is kInvalidArgument and nothing is applied); resp_errors[i] is what request i's client
+ * sees.  The non-batchable writes (multi_put, multi_remove, incr, check_and_set, check_and_mutate) arrive alone in their
+ * decree, as in the reference (`count == 1` is CHECKed there), through their own entry points: for pgs_rrdb_multi_put /
+ * _multi_remove the return value is the *response* error (kInvalidArgument for an empty list, after the empty record was
+ * written) and the apply status is kOk whenever the return is not a storage error (kIOError / kCorruption). */
+typedef struct {
+    uint32_t op; /* 0 = RPC_RRDB_RRDB_PUT, 1 = RPC_RRDB_RRDB_REMOVE */
+    pgs_blob raw_key;
+    pgs_blob value;              /* PUT: user data */
+    uint32_t expire_ts_seconds;  /* PUT */
+} pgs_write_request;
+PGS_API int32_t pgs_rrdb_on_batched_writes(pgs_server *s, const pgs_write_request *reqs, uint32_t count, int64_t decree,
+                                           uint64_t timestamp_us, uint32_t now, int32_t *resp_errors);
 /* incr (pegasus_write_service_impl.h:264-342; RPC_RRDB_RRDB_INCR): read-before-write on the replica's single writer.  Absent,
  * expired or empty base = 0; a non-integer base or an int64 overflow is reported in *resp_error (kInvalidArgument, *new_value =
  * the old value on overflow) while the call still returns kOk and writes an empty record for the decree, as the reference

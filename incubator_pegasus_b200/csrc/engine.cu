@@ -53,6 +53,30 @@ uint8_t *Engine::take_data(uint64_t need, uint64_t *cap)
     spares.erase(spares.begin() + best);
     return p;
 }
+void *Engine::take_pinned(size_t need, size_t *cap)
+{
+    {
+        std::lock_guard<std::mutex> g(pin_mu);
+        for (size_t i = 0; i < pins.size(); i++)
+            if (pins[i].cap >= need) {
+                void *p = pins[i].p;
+                *cap = pins[i].cap;
+                pins.erase(pins.begin() + i);
+                return p;
+            }
+    }
+    void *p = nullptr;
+    const size_t want = (need + (1u << 20)) & ~(size_t)((1u << 20) - 1);
+    if (cudaMallocHost(&p, want) != cudaSuccess) return nullptr;
+    *cap = want;
+    return p;
+}
+void Engine::give_pinned(void *p, size_t cap)
+{
+    std::lock_guard<std::mutex> g(pin_mu);
+    if (pins.size() < 8) pins.push_back(Pin{p, cap});
+    else cudaFreeHost(p);
+}
 void Engine::give_data(uint8_t *p, uint64_t cap)
 {
     std::lock_guard<std::mutex> g(spare_mu);
@@ -102,6 +126,7 @@ Engine::~Engine()
     if (h_pinned) cudaFreeHost(h_pinned);
     for (auto &s : rd_streams) if (s) cudaStreamDestroy(s);
     if (up_copy) cudaStreamDestroy(up_copy);
+    for (auto &pn : pins) cudaFreeHost(pn.p);
     if (stream) cudaStreamDestroy(stream);
 }
 cudaStream_t Engine::read_stream()
@@ -272,12 +297,16 @@ constexpr uint64_t kUploadChunk = 32ull << 20;
 
 struct UploadJob {
     std::shared_ptr<Run> r;
-    std::vector<uint64_t> off;
-    const uint32_t *h_blk_size = nullptr;
+    Engine *eng = nullptr;
+    // pinned staging (one allocation): off[nb+1] u64 | blk_size[nb] u32 | nrec[nb] | lastlen[nb] | rec_cum[nb+1] | key_cum[nb+1] | 2 x IndexStats
+    void *pin = nullptr;
+    size_t pin_cap = 0;
+    uint64_t *off = nullptr;
+    uint32_t *h_size = nullptr, *nrec = nullptr, *lastlen = nullptr, *rec_cum = nullptr, *key_cum = nullptr;
+    IndexStats *hs_in = nullptr, *hs_out = nullptr;
     uint32_t *d_nrec = nullptr, *d_lastlen = nullptr;
     IndexStats *d_stats = nullptr;
     IndexStats hs{};
-    std::vector<uint32_t> nrec, lastlen, rec_cum, key_cum;
     std::vector<cudaEvent_t> events;
     cudaEvent_t pass1 = nullptr;
     uint32_t max_blk = 0;
@@ -285,6 +314,7 @@ struct UploadJob {
     {
         for (cudaEvent_t ev : events) cudaEventDestroy(ev);
         if (pass1) cudaEventDestroy(pass1);
+        if (pin && eng) eng->give_pinned(pin, pin_cap);
     }
 };
 
@@ -302,7 +332,21 @@ static int32_t upload_stage_a(Engine *e, int32_t level, const uint8_t *data, uin
     }
     auto r = std::make_shared<Run>();
     j.r = r;
-    j.h_blk_size = blk_size;
+    j.eng = e;
+    {
+        const size_t need = 8ull * (nb + 2) + 4ull * (nb + 1) * 5 + 2 * sizeof(IndexStats) + 64;
+        j.pin = e->take_pinned(need, &j.pin_cap);
+        if (!j.pin) { set_error("run upload: no pinned staging memory"); return PGS_IO_ERROR; }
+        uint8_t *q = (uint8_t *)j.pin;
+        j.off = (uint64_t *)q; q += 8ull * (nb + 2);
+        j.h_size = (uint32_t *)q; q += 4ull * (nb + 1);
+        j.nrec = (uint32_t *)q; q += 4ull * (nb + 1);
+        j.lastlen = (uint32_t *)q; q += 4ull * (nb + 1);
+        j.rec_cum = (uint32_t *)q; q += 4ull * (nb + 1);
+        j.key_cum = (uint32_t *)q; q += 4ull * (nb + 1);
+        q = (uint8_t *)(((uintptr_t)q + 15) & ~(uintptr_t)15);
+        j.hs_in = (IndexStats *)q; j.hs_out = j.hs_in + 1;
+    }
     r->level = level;
     r->info.level = level;
     r->info.n_blocks = nb;
@@ -321,13 +365,14 @@ static int32_t upload_stage_a(Engine *e, int32_t level, const uint8_t *data, uin
     PGS_CUDA(cudaMallocAsync(&j.d_lastlen, sizeof(uint32_t) * nb, st));
     PGS_CUDA(cudaMallocAsync(&j.d_stats, sizeof(IndexStats), st));
     PGS_CUDA(cudaMemsetAsync(r->d_data + nbytes, 0, r->data_cap - nbytes, st));
-    j.off.assign(blk_off, blk_off + nb);
-    j.off.push_back(end);
-    j.hs = IndexStats{};
-    j.hs.min_seq = ~0ull;
-    PGS_CUDA(cudaMemcpyAsync(r->d_blk_off, j.off.data(), sizeof(uint64_t) * (nb + 1), cudaMemcpyHostToDevice, st));
-    PGS_CUDA(cudaMemcpyAsync(r->d_blk_size, blk_size, sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, st));
-    PGS_CUDA(cudaMemcpyAsync(j.d_stats, &j.hs, sizeof j.hs, cudaMemcpyHostToDevice, st));
+    memcpy(j.off, blk_off, sizeof(uint64_t) * nb);
+    j.off[nb] = end;
+    memcpy(j.h_size, blk_size, sizeof(uint32_t) * nb);
+    *j.hs_in = IndexStats{};
+    j.hs_in->min_seq = ~0ull;
+    PGS_CUDA(cudaMemcpyAsync(r->d_blk_off, j.off, sizeof(uint64_t) * (nb + 1), cudaMemcpyHostToDevice, st));
+    PGS_CUDA(cudaMemcpyAsync(r->d_blk_size, j.h_size, sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, st));
+    PGS_CUDA(cudaMemcpyAsync(j.d_stats, j.hs_in, sizeof(IndexStats), cudaMemcpyHostToDevice, st));
     cudaEvent_t ready;
     PGS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     j.events.push_back(ready);
@@ -350,11 +395,9 @@ static int32_t upload_stage_a(Engine *e, int32_t level, const uint8_t *data, uin
         e->launches++;
         b0 = b1;
     }
-    j.nrec.resize(nb);
-    j.lastlen.resize(nb);
-    PGS_CUDA(cudaMemcpyAsync(j.nrec.data(), j.d_nrec, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
-    PGS_CUDA(cudaMemcpyAsync(j.lastlen.data(), j.d_lastlen, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
-    PGS_CUDA(cudaMemcpyAsync(&j.hs, j.d_stats, sizeof j.hs, cudaMemcpyDeviceToHost, st));
+    PGS_CUDA(cudaMemcpyAsync(j.nrec, j.d_nrec, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
+    PGS_CUDA(cudaMemcpyAsync(j.lastlen, j.d_lastlen, sizeof(uint32_t) * nb, cudaMemcpyDeviceToHost, st));
+    PGS_CUDA(cudaMemcpyAsync(j.hs_out, j.d_stats, sizeof(IndexStats), cudaMemcpyDeviceToHost, st));
     PGS_CUDA(cudaEventCreateWithFlags(&j.pass1, cudaEventDisableTiming));
     PGS_CUDA(cudaEventRecord(j.pass1, st));
     return PGS_OK;
@@ -366,6 +409,7 @@ static int32_t upload_stage_b(Engine *e, UploadJob &j)
     const uint32_t nb = r->info.n_blocks;
     cudaStream_t st = e->stream;
     PGS_CUDA(cudaEventSynchronize(j.pass1));
+    j.hs = *j.hs_out;
     cudaFreeAsync(j.d_nrec, st);
     cudaFreeAsync(j.d_lastlen, st);
     j.d_nrec = j.d_lastlen = nullptr;
@@ -373,8 +417,6 @@ static int32_t upload_stage_b(Engine *e, UploadJob &j)
         set_error("run upload: block scan failed with status %u", j.hs.error);
         return (int32_t)j.hs.error;
     }
-    j.rec_cum.resize(nb + 1);
-    j.key_cum.resize(nb + 1);
     uint64_t rc = 0, kc = 0;
     for (uint32_t b = 0; b < nb; b++) {
         j.rec_cum[b] = (uint32_t)rc;
@@ -392,8 +434,8 @@ static int32_t upload_stage_b(Engine *e, UploadJob &j)
     PGS_CUDA(cudaMallocAsync(&r->d_ikey_off, sizeof(uint32_t) * (nb + 1), st));
     PGS_CUDA(cudaMallocAsync(&r->d_ikeys, kc + 16, st));
     PGS_CUDA(cudaMallocAsync(&r->d_rec_off, sizeof(uint32_t) * (rc + 1), st));
-    PGS_CUDA(cudaMemcpyAsync(r->d_blk_rec, j.rec_cum.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
-    PGS_CUDA(cudaMemcpyAsync(r->d_ikey_off, j.key_cum.data(), sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
+    PGS_CUDA(cudaMemcpyAsync(r->d_blk_rec, j.rec_cum, sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
+    PGS_CUDA(cudaMemcpyAsync(r->d_ikey_off, j.key_cum, sizeof(uint32_t) * (nb + 1), cudaMemcpyHostToDevice, st));
     r->n_bloom_entries = j.hs.n_records + j.hs.n_prefix;
     r->bloom_lines = bloom_lines_for(r->n_bloom_entries);
     PGS_CUDA(cudaMallocAsync(&r->d_bloom, (size_t)r->bloom_lines * 64, st));

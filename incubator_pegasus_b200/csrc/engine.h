@@ -66,6 +66,13 @@ struct Engine {
     std::vector<Spare> spares;
     uint8_t *take_data(uint64_t need, uint64_t *cap); // nullptr when nothing suitable is kept
     void give_data(uint8_t *p, uint64_t cap);
+    // pinned host staging for the small arrays of an upload (block handles in, per-block counts out): with pageable memory a
+    // cudaMemcpyAsync waits for everything queued before it on its stream, which stalls the upload pipeline between runs
+    struct Pin { void *p; size_t cap; };
+    std::mutex pin_mu;
+    std::vector<Pin> pins;
+    void *take_pinned(size_t need, size_t *cap);
+    void give_pinned(void *p, size_t cap);
     ~Engine();
 };
 

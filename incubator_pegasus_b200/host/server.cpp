@@ -763,6 +763,23 @@ int32_t pgs_rrdb_remove(pgs_server *h, pgs_blob key, int64_t decree, uint32_t no
     h->s.mem_write(std::string(bsv(key)), PGS_TYPE_DELETION, std::string(), now);
     return PGS_OK;
 }
+int32_t pgs_rrdb_on_batched_writes(pgs_server *h, const pgs_write_request *reqs, uint32_t count, int64_t decree, uint64_t timestamp_us,
+                                   uint32_t now, int32_t *resp_errors)
+{
+    if (!h || (count && !reqs)) return PGS_INVALID_ARGUMENT;
+    for (uint32_t i = 0; i < count; i++)
+        if (reqs[i].op > 1) return PGS_INVALID_ARGUMENT; // not batchable: nothing of the batch is applied
+    WLOCKED(h);
+    Server &s = h->s;
+    s.last_committed_decree = decree;
+    if (count == 0) { s.put_one({}, {}, 0, timestamp_us, now); return PGS_OK; } // RPC_REPLICATION_WRITE_EMPTY
+    for (uint32_t i = 0; i < count; i++) {
+        if (reqs[i].op == 0) s.put_one(bsv(reqs[i].raw_key), bsv(reqs[i].value), reqs[i].expire_ts_seconds, timestamp_us, now);
+        else s.mem_write(std::string(bsv(reqs[i].raw_key)), PGS_TYPE_DELETION, std::string(), now);
+        if (resp_errors) resp_errors[i] = PGS_OK;
+    }
+    return PGS_OK;
+}
 // dsn::buf2int64 (src/utils/string_conv.h:35-62): the whole buffer is one integer for strtoll with base 0 (decimal, 0x.., 0..)
 static bool buf2int64(std::string_view buf, int64_t &out)
 {

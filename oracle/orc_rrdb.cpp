@@ -768,6 +768,22 @@ int32_t orc_rrdb_put(orc_server *h, pgs_blob key, pgs_blob value, uint32_t expir
     put_one(h->s, bsv2(key), bsv2(value), expire_ts, timestamp_us, now);
     return PGS_OK;
 }
+// on_batched_write_requests: src/server/pegasus_server_write.cpp:92-222 (puts and removes of one decree; count 0 = empty write)
+int32_t orc_rrdb_on_batched_writes(orc_server *h, const pgs_write_request *reqs, uint32_t count, int64_t decree, uint64_t timestamp_us,
+                                   uint32_t now, int32_t *resp_errors)
+{
+    for (uint32_t i = 0; i < count; i++)
+        if (reqs[i].op > 1) return PGS_INVALID_ARGUMENT;
+    Server &s = h->s;
+    s.last_committed_decree = decree;
+    if (count == 0) { put_one(s, sv(), sv(), 0, timestamp_us, now); return PGS_OK; }
+    for (uint32_t i = 0; i < count; i++) {
+        if (reqs[i].op == 0) put_one(s, bsv2(reqs[i].raw_key), bsv2(reqs[i].value), reqs[i].expire_ts_seconds, timestamp_us, now);
+        else del_one(s, bsv2(reqs[i].raw_key), now);
+        if (resp_errors) resp_errors[i] = PGS_OK;
+    }
+    return PGS_OK;
+}
 // incr: pegasus_write_service_impl.h:264-342 (buf2int64: src/utils/string_conv.h:35-62; safe_add: src/utils/safe_arithmetic.h:44, int64 overflow check)
 int32_t orc_rrdb_incr(orc_server *h, pgs_blob key, int64_t increment, int32_t expire_ts_seconds, int64_t decree, uint64_t timestamp_us,
                       uint32_t now, int32_t *resp_error, int64_t *new_value)

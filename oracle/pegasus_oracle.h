@@ -178,6 +178,8 @@ ORC_API int32_t orc_rrdb_scan(orc_server *s, int64_t context_id, uint32_t now,
 ORC_API void orc_rrdb_clear_scanner(orc_server *s, int64_t context_id);
 ORC_API int32_t orc_rrdb_put(orc_server *s, pgs_blob key, pgs_blob value, uint32_t expire_ts,
                              int64_t decree, uint64_t timestamp_us, uint32_t now);
+ORC_API int32_t orc_rrdb_on_batched_writes(orc_server *s, const pgs_write_request *reqs, uint32_t count, int64_t decree,
+                                           uint64_t timestamp_us, uint32_t now, int32_t *resp_errors);
 ORC_API int32_t orc_rrdb_incr(orc_server *s, pgs_blob raw_key, int64_t increment, int32_t expire_ts_seconds, int64_t decree,
                               uint64_t timestamp_us, uint32_t now, int32_t *resp_error, int64_t *new_value);
 ORC_API int32_t orc_rrdb_check_and_set(orc_server *s, const pgs_check_and_set_request *req, int64_t decree, uint64_t timestamp_us,

@@ -28,6 +28,10 @@ def next_blob(b: bytes) -> bytes:
     return bytes(b)
 
 
+class WriteRequest(C.Structure):
+    _fields_ = [("op", C.c_uint32), ("raw_key", Blob), ("value", Blob), ("expire_ts_seconds", C.c_uint32)]
+
+
 class Mutate(C.Structure):
     _fields_ = [("operation", C.c_uint32), ("sort_key", Blob), ("value", Blob), ("set_expire_ts_seconds", C.c_int32)]
 
@@ -88,6 +92,7 @@ class Backend:
             "rrdb_scan": [vp, C.c_int64, C.c_uint32, vp], "rrdb_clear_scanner": [vp, C.c_int64],
             "rrdb_put": [vp, Blob, Blob, C.c_uint32, C.c_int64, C.c_uint64, C.c_uint32],
             "rrdb_remove": [vp, Blob, C.c_int64, C.c_uint32],
+            "rrdb_on_batched_writes": [vp, C.POINTER(WriteRequest), C.c_uint32, C.c_int64, C.c_uint64, C.c_uint32, C.POINTER(C.c_int32)],
             "rrdb_check_and_set": [vp, C.POINTER(CheckAndSetRequest), C.c_int64, C.c_uint64, C.c_uint32, C.POINTER(CasResult), vp, C.c_uint32],
             "rrdb_check_and_mutate": [vp, C.POINTER(CheckAndMutateRequest), C.c_int64, C.c_uint64, C.c_uint32, C.POINTER(CasResult), vp, C.c_uint32],
             "rrdb_incr": [vp, Blob, C.c_int64, C.c_int32, C.c_int64, C.c_uint64, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int64)],
@@ -143,6 +148,20 @@ class Backend:
         e, v = C.c_int32(-1), C.c_int64(0)
         rc = self.f("rrdb_incr")(self.h, blob(raw_key(hk, sk), keep), increment, expire_ts_seconds, self.decree, ts_us, now, C.byref(e), C.byref(v))
         return rc, e.value, v.value
+
+    def batched_writes(self, ops, now=0, ts_us=1):
+        """ops: list of ("put", hk, sk, value, expire_ts) / ("remove", hk, sk); one decree -> (apply status, [response errors])"""
+        keep = []
+        self.decree += 1
+        arr = (WriteRequest * max(1, len(ops)))()
+        for i, o in enumerate(ops):
+            arr[i].op = {"put": 0, "remove": 1}.get(o[0], 7)
+            arr[i].raw_key = blob(raw_key(o[1], o[2]), keep)
+            arr[i].value = blob(o[3] if len(o) > 3 else b"", keep)
+            arr[i].expire_ts_seconds = o[4] if len(o) > 4 else 0
+        errs = (C.c_int32 * max(1, len(ops)))(*([-1] * max(1, len(ops))))
+        rc = self.f("rrdb_on_batched_writes")(self.h, arr, len(ops), self.decree, ts_us, now, errs)
+        return rc, list(errs[:len(ops)])
 
     def _cas_out(self, rc, res, buf):
         return {"rc": rc, "error": res.error, "returned": bool(res.check_value_returned), "exist": bool(res.check_value_exist),

@@ -127,3 +127,19 @@ def test_decrees_and_memtable_reads(make, kind):
     r = be.multi_get(b"h", now=NOW)                           # a range read does
     assert [(k, v) for k, v, _ in r["kvs"]] == [(b"a", b"new"), (b"b", b"only-mem")]
     assert be.f("rrdb_last_flushed_decree")(be.h) == be.decree
+
+
+@pytest.mark.parametrize("kind", backends())
+def test_batched_writes_of_one_decree(make, kind):
+    """on_batched_write_requests (pegasus_server_write.cpp:92-222): puts and removes of one decree apply together, an empty
+    batch only advances the decree, an operation that may not be batched applies nothing"""
+    be = make(kind)
+    be.put(b"h", b"gone", b"x", now=NOW)
+    rc, errs = be.batched_writes([("put", b"h", b"a", b"1", NOW + 40), ("put", b"h", b"b", b"2"), ("remove", b"h", b"gone"), ("put", b"h", b"a", b"3")], now=NOW)
+    assert rc == 0 and errs == [0, 0, 0, 0]
+    assert be.get(b"h", b"a", now=NOW)["kvs"][0][1] == b"3" and be.ttl(b"h", b"a", now=NOW)["ttl"] == -1   # the later put of the batch wins
+    assert be.get(b"h", b"b", now=NOW)["error"] == 0 and be.get(b"h", b"gone", now=NOW)["error"] == 1
+    d = be.decree
+    assert be.batched_writes([], now=NOW) == (0, []) and be.f("rrdb_last_committed_decree")(be.h) == d + 1
+    assert be.batched_writes([("put", b"h", b"c", b"9"), ("multi_put", b"h", b"d", b"9")], now=NOW)[0] == 4
+    assert be.get(b"h", b"c", now=NOW)["error"] == 1
