@@ -305,16 +305,6 @@ __global__ void __launch_bounds__(kReadThreads, 8) k_scan_fwd(const __grid_const
             if (2 + hl <= Q.start_len && 2 + hl <= KS) pre_len = 2 + hl;
             else if (2 + hl <= Q.start_len) pre_len = 0xFFFFFFFFu; // a prefix longer than any stored key: nothing is in the domain
         }
-        // stop key == the end of the prefix (next_blob of it, as multi_get / prefix scans build it, pegasus_server_impl.cpp:553-557):
-        // every key inside the prefix is below it, no compare per record
-        bool stop_is_prefix_end = false;
-        if (en && pre_len && pre_len != 0xFFFFFFFFu && !Q.has_upper && Q.stop_len >= 1 && Q.stop_len <= pre_len) {
-            const uint32_t m = Q.stop_len;
-            bool same = stop[m - 1] == (uint8_t)(start[m - 1] + 1) && start[m - 1] != 0xFF;
-            for (uint32_t i = 0; same && i + 1 < m; i++) same = stop[i] == start[i];
-            for (uint32_t i = m; same && i < pre_len; i++) same = start[i] == 0xFF;
-            stop_is_prefix_end = same;
-        }
         const unsigned long long pre_hash = bloom_hash_row(g, rowSTART, pre_len != 0xFFFFFFFFu ? pre_len : 0u);
         pgs_kv *kvs = P.kvs + (size_t)rq * P.kv_stride;
         uint8_t *arena = P.arena + (size_t)rq * P.arena_stride;
@@ -377,30 +367,15 @@ __global__ void __launch_bounds__(kReadThreads, 8) k_scan_fwd(const __grid_const
             const bool visible = rec && !shadow && type == PGS_TYPE_VALUE;
             // the loop's view of a visible record
             uint32_t d_stop = 0, d_start = 0;
-            int c2 = -1; // (inside the prefix = below its end; a key outside the prefix ends the loop as not Valid() below)
-            if (g.any(visible && !stop_is_prefix_end)) {
-                const int cs2 = row_cmp(g, visible && !stop_is_prefix_end, row, ulen, rowSTOP, stop_len, d_stop);
-                if (!stop_is_prefix_end) c2 = cs2;
-            }
+            const int c2 = row_cmp(g, visible, row, ulen, rowSTOP, stop_len, d_stop);
             const bool need_first = visible && first_excl;
             int c_first = 1;
             if (g.any(need_first)) c_first = row_cmp(g, need_first, row, ulen, rowSTART, start_len, d_start);
-            // Iterator::Valid() under prefix_same_as_start: the key carries the seek prefix (compared by the whole group)
-            bool in_prefix = true;
-            {
-                const bool chk = visible && pre_len != 0 && pre_len != 0xFFFFFFFFu;
-                if (g.any(chk)) {
-                    uint32_t dpre = 0;
-                    const bool cmpp = chk && ulen >= pre_len;
-                    const int cp = row_cmp(g, cmpp, row, cmpp ? pre_len : 0u, rowSTART, pre_len, dpre);
-                    if (chk) in_prefix = cmpp && cp == 0;
-                }
-            }
             bool advance = rec; // hidden records are stepped over
             if (visible) {
                 const uint8_t *key = (const uint8_t *)row;
                 bool valid = true; // Iterator::Valid(): inside the seek prefix, below iterate_upper_bound
-                if (pre_len) valid = in_prefix && pre_len != 0xFFFFFFFFu;
+                if (pre_len) { valid = ulen >= pre_len; for (uint32_t i = 0; valid && i < pre_len; i++) valid = key[i] == ((const uint8_t *)rowSTART)[i]; }
                 if (Q.has_upper && c2 >= 0) valid = false;
                 const bool guards = count < Q.max_count && iter_count < Q.max_iter_count && !(Q.max_iter_size > 0 && size >= Q.max_iter_size);
                 if (!guards || !valid) { // the while condition fails: the loop ends with the iterator standing here
