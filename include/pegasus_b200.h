@@ -522,6 +522,16 @@ PGS_API int32_t pgs_rrdb_manual_compact(pgs_server *s, uint32_t now, pgs_compact
  * durable across a process crash (no WAL / checkpoint yet: SURVEY 8 f4), so neither may drive replication-log GC. */
 PGS_API int64_t pgs_rrdb_last_flushed_decree(pgs_server *s);
 PGS_API int64_t pgs_rrdb_last_committed_decree(pgs_server *s);
+/* Checkpoints (first slice of SURVEY 8 f4; sync_checkpoint / storage_apply_checkpoint, pegasus_server_impl.cpp:1951-2336).
+ * pgs_rrdb_sync_checkpoint flushes the memtable and writes every resident run as a BlockBasedTable file (section 8; LZ4 for
+ * levels >= 2 like the reference's per-level compression) plus a MANIFEST (levels, file names, decree, sequence number,
+ * data version) into `dir`/checkpoint.<last_flushed_decree>, the reference's directory naming; the decree becomes the
+ * replica's last_durable_decree.  pgs_rrdb_apply_checkpoint replaces the replica's state (runs, memtable, scan contexts,
+ * decrees) with that of a checkpoint directory: what learn / restore do.  Checkpoint files are plain SST images: a RocksDB
+ * replica's uncompressed or LZ4 files of the same format version ingest the same way (pgs_sst_ingest). */
+PGS_API int32_t pgs_rrdb_sync_checkpoint(pgs_server *s, const char *dir, uint32_t now, int64_t *decree_out);
+PGS_API int64_t pgs_rrdb_last_durable_decree(pgs_server *s);
+PGS_API int32_t pgs_rrdb_apply_checkpoint(pgs_server *s, const char *checkpoint_dir);
 /* drops scan contexts older than 5 minutes (pegasus_server_impl.cpp:1377-1385 schedules the same expiry per context);
  * also runs implicitly on every scanner call. Returns the number of contexts dropped. */
 PGS_API uint32_t pgs_rrdb_gc(pgs_server *s, uint32_t now);

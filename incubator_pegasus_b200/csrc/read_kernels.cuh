@@ -263,7 +263,7 @@ struct ScanParams {
 enum : uint8_t { RS_NORMAL = 0, RS_EXPIRED = 1, RS_FILTERED = 2, RS_HASH_INVALID = 3 };
 
 template <uint32_t G>
-__global__ void __launch_bounds__(kReadThreads, 8) k_scan_fwd(const __grid_constant__ ScanParams P)
+__global__ void __launch_bounds__(kReadThreads) k_scan_fwd(const __grid_constant__ ScanParams P)
 {
     PGS_SMEM_DYN(dyn);
     const Grp<G> g;

@@ -103,9 +103,16 @@ class Backend:
             "rrdb_update_app_envs": [vp, C.c_char_p, C.c_uint32, C.c_uint32],
             "rrdb_set_partition_version": [vp, C.c_int32], "rrdb_stop": [vp],
             "rrdb_last_flushed_decree": [vp], "rrdb_last_committed_decree": [vp], "rrdb_gc": [vp, C.c_uint32],
+            "rrdb_sync_checkpoint": [vp, C.c_char_p, C.c_uint32, C.POINTER(C.c_int64)], "rrdb_last_durable_decree": [vp],
+            "rrdb_apply_checkpoint": [vp, C.c_char_p],
         }
+        if kind != "gpu":  # checkpoints exist on the product side only
+            for n in ("rrdb_sync_checkpoint", "rrdb_last_durable_decree", "rrdb_apply_checkpoint"):
+                sigs.pop(n)
         for n, a in sigs.items():
             f(n).argtypes = a
+        if kind == "gpu":
+            f("rrdb_last_durable_decree").restype = C.c_int64
         f("rrdb_last_flushed_decree").restype = C.c_int64
         f("rrdb_last_committed_decree").restype = C.c_int64
         f("rrdb_gc").restype = C.c_uint32
