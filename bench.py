@@ -387,7 +387,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--records-per-run", type=int, default=2_500_000)
-    ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-reads", action="store_true")
@@ -448,7 +447,7 @@ def main():
         pinned_tensors.append(t)
     h2d_bytes = sum(int(p.data.shape[0]) for p in pinned)
 
-    eng = pgs.Engine(device=local_rank, ctas_per_sm=args.ctas_per_sm)
+    eng = pgs.Engine(device=local_rank)
     part = eng.partition(app_id=1, pidx=rank)
     ids = part.upload_many(pinned)
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))

@@ -509,7 +509,6 @@ int32_t pgs_engine_open(const pgs_engine_config *cfg, pgs_engine **out)
     if (cfg) e.cfg = *cfg;
     if (!e.cfg.block_size) e.cfg.block_size = kDefaultBlockSize;
     if (!e.cfg.restart_interval) e.cfg.restart_interval = kDefaultRestartInterval;
-    if (!e.cfg.ctas_per_sm) e.cfg.ctas_per_sm = 1; // one 1024-thread CTA per SM measured faster than two 512-thread CTAs
     int dev = e.cfg.device;
     if (dev < 0) cudaGetDevice(&dev);
     e.device = dev;

@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) k_scan(const __grid_constant_
             __syncthreads();
             SPT(4);
             if (S.error) break;
-            // ---- decode step 2: HALF a warp per block rebuilds the keys, four key bytes per lane (see k_merge) ---------
+            // ---- decode step 2: HALF a warp per block rebuilds the keys, four key bytes per lane ---------
             {
                 const uint32_t hl = lane & 15, sub = lane >> 4;
                 const uint32_t hmask = sub ? 0xffff0000u : 0x0000ffffu;

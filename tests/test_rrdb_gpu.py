@@ -1,5 +1,5 @@
 """GPU parity of the rrdb operator surface (on_get / on_multi_get / on_batch_get / on_sortkey_count / on_ttl /
-on_get_scanner / on_scan through pgs_rrdb_*, kernels k_get / k_scan / k_merge) against the CPU oracle and
+on_get_scanner / on_scan through pgs_rrdb_*, kernels k_get / k_scan_fwd / k_scan / k_walk / k_emit) against the CPU oracle and
 the reference's own golden tables."""
 import json
 import os
