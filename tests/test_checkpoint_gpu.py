@@ -48,7 +48,7 @@ def same_reads(a, b):
 def test_checkpoint_and_apply(pgs, engine, tmp_path):
     opts = {"l0_compaction_trigger": 3, "memtable_bytes": 64 << 10}
     g, o = Backend("gpu", engine, pidx=21, opts=opts), Backend("oracle", pidx=21, opts=opts)
-    g2 = Backend("gpu", engine, pidx=22, opts=opts)
+    g2 = Backend("gpu", engine, pidx=21, opts=opts)  # a second replica object of the same gpid (the learner)
     try:
         history([g, o], seed=1, rounds=5)
         g.manual_compact(NOW); o.manual_compact(NOW)       # a bottom level (LZ4 in the checkpoint) ...
