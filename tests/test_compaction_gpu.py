@@ -203,3 +203,39 @@ def test_bench_size_digest(pgs, oracle, engine):
         assert digest(got) == digest(want)
     finally:
         part.close()
+
+
+def test_value_schema_v0(pgs, oracle, engine):
+    """data_version 0 (src/base/pegasus_value_schema.h:133-170: BE32 expire_ts | data, no timetag): the filter's expiry check and
+    default-TTL rewrite and the 4-byte header strip of point reads on the device, against the oracle"""
+    rng = np.random.default_rng(31)
+    runs, seq = [], 1
+    for i in range(3):
+        items = {}
+        for j in range(3000):
+            key = (3).to_bytes(2, "big") + b"h%02d" % rng.integers(0, 60) + b"s%03d" % rng.integers(0, 400)
+            ets = int(rng.choice([0, 0, synth.NOW + 500, synth.NOW - 7]))
+            items[key] = (key, seq, 1, ets.to_bytes(4, "big") + bytes(rng.integers(0, 256, int(rng.integers(0, 90)), dtype=np.uint8)))
+            seq += 1
+        runs.append(pgs.Records.from_list([items[k] for k in sorted(items)]))
+    part = engine.partition(data_version=0)
+    try:
+        ids = [part.upload_records(r) for r in runs]
+        res = part.compact(ids, out_level=1, bottommost=1, now=synth.NOW, default_ttl=900, data_version=0)
+        want_run, st = oracle.compact([oracle.Run.from_records(r) for r in runs], True, oracle.filter_params(default_ttl=900, data_version=0), synth.NOW)
+        want = want_run.records()
+        got = pgs.decode_blocks(part.download(res.new_run_id))
+        assert got.same_as(want) and res.ttl_rewritten == st.ttl_rewritten > 0 and res.dropped_expired == st.dropped_expired > 0
+        pick = np.arange(0, want.n, 37)
+        keys = b"".join(want.key(int(i)) for i in pick)
+        off = np.zeros(len(pick) + 1, np.uint32)
+        off[1:] = np.cumsum([len(want.key(int(i))) for i in pick])
+        st_, results, arena, _ = part.get_batch(np.frombuffer(keys, np.uint8), off, synth.NOW)
+        assert st_ == 0
+        for j, i in enumerate(pick):
+            v = want.value(int(i))
+            assert results[j].status == pgs.OK and results[j].expire_ts == int.from_bytes(v[:4], "big")
+            o, l = results[j].value_off, results[j].value_len
+            assert arena[o:o + l].tobytes() == v[4:]   # v0: the user data starts right after the expire_ts
+    finally:
+        part.close()
