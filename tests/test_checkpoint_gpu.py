@@ -28,8 +28,9 @@ def history(backends, seed, rounds):
             ets = rnd.choice([0, 0, NOW + 1000, NOW - 3])
             for be in backends:
                 be.multi_put(hk, kvs, expire_ts=ets, now=NOW)
+        gone = [b"s%03d" % rnd.randrange(120) for _ in range(5)]
         for be in backends:
-            be.multi_remove(b"hk%02d" % (r % 6), [b"s%03d" % rnd.randrange(120) for _ in range(5)], now=NOW)
+            be.multi_remove(b"hk%02d" % (r % 6), gone, now=NOW)
             be.flush(NOW)
 
 
