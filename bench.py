@@ -213,15 +213,19 @@ def sharded_read_leg(pgs, torch, dist, eng, rank, world, args, barrier, check_cp
     from incubator_pegasus_b200 import synth
     work = []  # (kind, partition, payload)
     my_gets = my_scans = 0
+    # gets: all of this rank's partitions in ONE launch (pgs_get_batch_multi: the shape a batching front end gives the engine)
+    plist = sorted(parts)
+    slot_of = {p: i for i, p in enumerate(plist)}
+    sel = np.nonzero(np.isin(g_owner, plist))[0]
+    if sel.size:
+        keys = synth.make_keys(gh[sel], gs[sel], HK, SK, table.seed)
+        flat = np.ascontiguousarray(keys.reshape(-1))
+        off = (np.arange(sel.size + 1, dtype=np.uint32) * np.uint32(keys.shape[1]))
+        kslot = np.array([slot_of[int(p)] for p in g_owner[sel]], np.uint32)
+        cap = int(sel.size) * (VAL + 16)
+        work.append(("get", -1, (flat, off, kslot, np.zeros(cap, np.uint8), (pgs.GetResult * int(sel.size))(), g_owner[sel].copy())))
+        my_gets = int(sel.size)
     for p, part in parts.items():
-        sel = np.nonzero(g_owner == p)[0]
-        if sel.size:
-            keys = synth.make_keys(gh[sel], gs[sel], HK, SK, table.seed)
-            flat = np.ascontiguousarray(keys.reshape(-1))
-            off = (np.arange(sel.size + 1, dtype=np.uint32) * np.uint32(keys.shape[1]))
-            cap = sel.size * (VAL + 16)
-            work.append(("get", p, (flat, off, np.zeros(cap, np.uint8), (pgs.GetResult * int(sel.size))(), cap)))
-            my_gets += int(sel.size)
         sel = np.nonzero(s_owner == p)[0]
         if sel.size:
             sb = part.prefix_scan_batch([table.hashkeys[int(h)].tobytes() for h in sh[sel]], max_records=80, arena_stride=24576)
@@ -235,8 +239,8 @@ def sharded_read_leg(pgs, torch, dist, eng, rank, world, args, barrier, check_cp
     def serve(item):
         kind, p, payload = item
         if kind == "get":
-            flat, off, arena, res, cap = payload
-            st, res, _, _ = parts[p].get_batch(flat, off, NOW, arena_cap=cap, arena=arena, results=res)
+            flat, off, kslot, arena, res, _owners = payload
+            st, res, _, _ = pgs.get_batch_multi([parts[q] for q in plist], flat, off, kslot, NOW, arena, res)
             assert st == 0, st
             ms = eng.last_kernel_ms
             found = sum(1 for i in range(off.shape[0] - 1) if res[i].status == 0) if verify[0] else 0
@@ -274,7 +278,8 @@ def sharded_read_leg(pgs, torch, dist, eng, rank, world, args, barrier, check_cp
     out = {
         "workload": f"{args.partitions} partitions x 3 runs (L2 full, L1 30 %, L0 10 % newer versions), {args.table_hashkeys} hash keys x 64 sort keys; "
                     f"YCSB-C zipfian(0.99) over hash keys: {args.n_get} get(hk,sk) + {args.n_scan} multi_get(hk, all sort keys), "
-                    f"routed by crc64(hash_key) % {args.partitions}; partition p on rank p % N; {args.read_threads} host threads per rank",
+                    f"routed by crc64(hash_key) % {args.partitions}; partition p on rank p % N; per rank the gets of all its partitions go through "
+                    f"one pgs_get_batch_multi launch, the prefix scans through one pgs_range_scan_many call per partition on {args.read_threads} host threads",
         "scaling": "strong", "collective": "none on the data path (partitions are independent)",
         "partitions_per_rank": len(parts), "records_resident": int(t[4]),
         "get_keys_per_s": float(t[1]) / wall_max, "scan_keys_per_s": float(t[2]) / wall_max,
@@ -290,13 +295,25 @@ def sharded_read_leg(pgs, torch, dist, eng, rank, world, args, barrier, check_cp
         threads = os.cpu_count() or 1
         c_found = c_ret = 0
         c_secs = 0.0
-        for kind, p, payload in work:
-            bruns = [orc.BlockRunCPU.from_blocks(b) for b in reversed(host_runs[p])]  # newest first
-            if kind == "get":
-                flat, off = payload[0], payload[1]
-                f, _vb, secs = orc.get_many(bruns, flat, off, NOW, threads)
+        for kind, p, payload in work:  # gets: the oracle answers them partition by partition
+            if kind != "get":
+                continue
+            flat, off, _kslot, _arena, _res, owners = payload
+            klen = int(off[1] - off[0])
+            for q in plist:
+                selq = np.nonzero(owners == q)[0]
+                if not selq.size:
+                    continue
+                bruns = [orc.BlockRunCPU.from_blocks(b) for b in reversed(host_runs[q])]  # newest first
+                sub = np.ascontiguousarray(flat.reshape(-1, klen)[selq].reshape(-1))
+                f, _vb, secs = orc.get_many(bruns, sub, np.arange(selq.size + 1, dtype=np.uint32) * np.uint32(klen), NOW, threads)
                 c_found += f
-            else:
+                c_secs += secs
+        for kind, p, payload in work:
+            if kind == "get":
+                continue
+            bruns = [orc.BlockRunCPU.from_blocks(b) for b in reversed(host_runs[p])]  # newest first
+            if True:
                 hks = np.frombuffer(b"".join(bytes(payload.reqs[i].start.data[2:2 + HK]) for i in range(payload.n)), np.uint8)
                 cnt, _nb, secs = orc.prefix_scan_many(bruns, hks, np.arange(payload.n + 1, dtype=np.uint32) * np.uint32(HK), NOW, threads)
                 c_ret += cnt

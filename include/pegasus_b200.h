@@ -237,6 +237,12 @@ typedef struct {
 PGS_API int32_t pgs_get_batch(pgs_partition *p, const uint8_t *keys, const uint32_t *key_off,
                               uint32_t n, uint32_t now, uint8_t *arena, uint64_t arena_cap,
                               pgs_get_result *results, uint64_t *arena_used);
+/* The same for keys of several partitions of one engine in ONE launch (a batching front end's shape: concurrent handlers of
+ * many replicas coalesced): key i is looked up in parts[key_part[i]].  Results and arena as above. */
+PGS_API int32_t pgs_get_batch_multi(pgs_partition *const *parts, uint32_t n_parts, const uint8_t *keys,
+                                    const uint32_t *key_off, const uint32_t *key_part, uint32_t n, uint32_t now,
+                                    uint8_t *arena, uint64_t arena_cap, pgs_get_result *results,
+                                    uint64_t *arena_used);
 
 /* ---- range scan: NewIterator + Seek + Next/Prev loop --------------------------------------- */
 typedef struct {

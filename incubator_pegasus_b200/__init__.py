@@ -185,6 +185,7 @@ def lib() -> C.CDLL:
     L.pgs_partition_destroy.argtypes = [vp]
     L.pgs_partition_destroy.restype = None
     L.pgs_run_upload.argtypes = [vp, C.c_int32, vp, C.c_uint64, vp, vp, C.c_uint32, u64p]
+    L.pgs_get_batch_multi.argtypes = [C.POINTER(vp), C.c_uint32, vp, vp, vp, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp, u64p]
     L.pgs_run_upload_many.argtypes = [vp, C.POINTER(RunSrc), C.c_uint32, u64p]
     L.pgs_run_drop.argtypes = [vp, C.c_uint64]
     L.pgs_run_info_get.argtypes = [vp, C.c_uint64, C.POINTER(RunInfo)]
@@ -442,6 +443,17 @@ class Router:
 
     def __exit__(self, *a):
         self.close()
+
+
+def get_batch_multi(parts, keys: np.ndarray, key_off: np.ndarray, key_part: np.ndarray, now: int, arena: np.ndarray, results=None):
+    """keys of several partitions of one engine in one launch (pgs_get_batch_multi); key i goes to parts[key_part[i]]"""
+    n = key_off.shape[0] - 1
+    results = (GetResult * n)() if results is None else results
+    handles = (C.c_void_p * len(parts))(*[p.h for p in parts])
+    used = C.c_uint64()
+    st = lib().pgs_get_batch_multi(handles, len(parts), _ptr(keys), _ptr(key_off), _ptr(key_part), n, now, _ptr(arena), arena.shape[0],
+                                   results, C.byref(used))
+    return st, results, arena, used.value
 
 
 def partition_index(hash_key: bytes, sort_key: bytes, partition_count: int) -> int:

@@ -1062,20 +1062,43 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
 
 using namespace pgs;
 
-extern "C" int32_t pgs_get_batch(pgs_partition *ph, const uint8_t *keys, const uint32_t *key_off, uint32_t n,
-                                 uint32_t now, uint8_t *arena, uint64_t arena_cap, pgs_get_result *results,
-                                 uint64_t *arena_used)
+// one get launch over the keys of one partition (parts[0], key_part null) or of several partitions of one engine
+static int32_t get_batch_impl(pgs_partition *const *parts, uint32_t n_parts, const uint8_t *keys, const uint32_t *key_off, const uint32_t *key_part,
+                              uint32_t n, uint32_t now, uint8_t *arena, uint64_t arena_cap, pgs_get_result *results, uint64_t *arena_used)
 {
-    if (!ph || (n && (!keys || !key_off || !results))) return PGS_INVALID_ARGUMENT;
-    Partition &part = ph->p;
+    Partition &part = parts[0]->p;
     Engine *e = part.eng;
     if (arena_used) *arena_used = 0;
     if (n == 0) return PGS_OK;
-    std::vector<std::shared_ptr<Run>> runs;
+    std::vector<std::shared_ptr<Run>> runs; // every run a key may touch stays alive until the launch is done
     GetParams P{};
-    int32_t rc = snapshot_runs(part, runs, P.rr, P.KS);
-    if (rc != PGS_OK) return rc;
-    if (P.rr.n == 0) {
+    std::vector<RunDev> packed;
+    std::vector<uint32_t> begin;
+    if (!key_part) {
+        int32_t rc = snapshot_runs(part, runs, P.rr, P.KS);
+        if (rc != PGS_OK) return rc;
+    } else {
+        P.rr.n = 0;
+        P.KS = 8;
+        begin.push_back(0);
+        for (uint32_t p = 0; p < n_parts; p++) {
+            Partition &pp = parts[p]->p;
+            if (pp.eng != e || pp.data_version != part.data_version) { set_error("get_batch_multi: partitions of different engines / data versions"); return PGS_INVALID_ARGUMENT; }
+            std::vector<std::shared_ptr<Run>> rs;
+            ReadRuns rr;
+            uint32_t ks = 0;
+            int32_t rc = snapshot_runs(pp, rs, rr, ks);
+            if (rc != PGS_OK) return rc;
+            for (uint32_t i = 0; i < rr.n; i++) packed.push_back(rr.runs[i]);
+            begin.push_back((uint32_t)packed.size());
+            runs.insert(runs.end(), rs.begin(), rs.end());
+            P.KS = std::max(P.KS, ks);
+        }
+        for (uint32_t i = 0; i < n; i++)
+            if (key_part[i] >= n_parts) { set_error("get_batch_multi: key %u names partition slot %u of %u", i, key_part[i], n_parts); return PGS_INVALID_ARGUMENT; }
+        if (!packed.empty()) P.rr.runs[0] = packed[0]; // a valid dummy for idle groups
+    }
+    if (key_part ? packed.empty() : P.rr.n == 0) {
         for (uint32_t i = 0; i < n; i++) { memset(&results[i], 0, sizeof results[i]); results[i].status = PGS_NOT_FOUND; }
         return PGS_OK;
     }
@@ -1086,10 +1109,15 @@ extern "C" int32_t pgs_get_batch(pgs_partition *ph, const uint8_t *keys, const u
     uint32_t *d_off = nullptr, *d_err = nullptr;
     pgs_get_result *d_res = nullptr;
     unsigned long long *d_cur = nullptr;
+    RunDev *d_multi = nullptr;
+    uint32_t *d_begin = nullptr, *d_part = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     auto cleanup = [&]() {
         cudaFreeAsync(d_keys, st); cudaFreeAsync(d_arena, st); cudaFreeAsync(d_off, st); cudaFreeAsync(d_err, st);
         cudaFreeAsync(d_res, st); cudaFreeAsync(d_cur, st);
+        if (d_multi) cudaFreeAsync(d_multi, st);
+        if (d_begin) cudaFreeAsync(d_begin, st);
+        if (d_part) cudaFreeAsync(d_part, st);
         if (ev_a) cudaEventDestroy(ev_a);
         if (ev_b) cudaEventDestroy(ev_b);
     };
@@ -1106,6 +1134,15 @@ extern "C" int32_t pgs_get_batch(pgs_partition *ph, const uint8_t *keys, const u
     CK(cudaMemcpyAsync(d_off, key_off, sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d_cur, 0, 32, st));
     CK(cudaMemsetAsync(d_err, 0, 16, st));
+    if (key_part) {
+        CK(cudaMallocAsync(&d_multi, sizeof(RunDev) * packed.size(), st));
+        CK(cudaMallocAsync(&d_begin, sizeof(uint32_t) * begin.size(), st));
+        CK(cudaMallocAsync(&d_part, sizeof(uint32_t) * n, st));
+        CK(cudaMemcpyAsync(d_multi, packed.data(), sizeof(RunDev) * packed.size(), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_begin, begin.data(), sizeof(uint32_t) * begin.size(), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_part, key_part, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+        P.multi_runs = d_multi; P.multi_begin = d_begin; P.key_part = d_part;
+    }
     P.keys = d_keys; P.key_off = d_off; P.n = n; P.now = now; P.data_version = part.data_version;
     P.results = d_res; P.arena = d_arena; P.arena_cap = arena_cap; P.arena_cursor = d_cur; P.error = d_err; P.ticket = d_err + 1;
     constexpr uint32_t G = 8;
@@ -1141,6 +1178,23 @@ extern "C" int32_t pgs_get_batch(pgs_partition *ph, const uint8_t *keys, const u
 #undef CK
     if (herr) { set_error("get kernel failed with status %u", herr); return herr == PGS_CORRUPTION ? PGS_CORRUPTION : PGS_IO_ERROR; }
     return used > arena_cap ? PGS_INCOMPLETE : PGS_OK;
+}
+
+extern "C" int32_t pgs_get_batch(pgs_partition *ph, const uint8_t *keys, const uint32_t *key_off, uint32_t n, uint32_t now, uint8_t *arena,
+                                 uint64_t arena_cap, pgs_get_result *results, uint64_t *arena_used)
+{
+    if (!ph || (n && (!keys || !key_off || !results))) return PGS_INVALID_ARGUMENT;
+    return get_batch_impl(&ph, 1, keys, key_off, nullptr, n, now, arena, arena_cap, results, arena_used);
+}
+
+extern "C" int32_t pgs_get_batch_multi(pgs_partition *const *parts, uint32_t n_parts, const uint8_t *keys, const uint32_t *key_off,
+                                       const uint32_t *key_part, uint32_t n, uint32_t now, uint8_t *arena, uint64_t arena_cap,
+                                       pgs_get_result *results, uint64_t *arena_used)
+{
+    if (!parts || !n_parts || (n && (!keys || !key_off || !key_part || !results))) return PGS_INVALID_ARGUMENT;
+    for (uint32_t p = 0; p < n_parts; p++)
+        if (!parts[p]) return PGS_INVALID_ARGUMENT;
+    return get_batch_impl(parts, n_parts, keys, key_off, key_part, n, now, arena, arena_cap, results, arena_used);
 }
 
 extern "C" int32_t pgs_range_scan(pgs_partition *ph, const pgs_scan_request *req, uint32_t now, uint8_t *arena,

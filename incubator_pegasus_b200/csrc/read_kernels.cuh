@@ -151,6 +151,11 @@ struct GetParams {
     unsigned long long *arena_cursor; // [0] = arena bytes, [1] = data blocks probed, [2] = runs skipped by the Bloom filter
     uint32_t *error;
     uint32_t *ticket;
+    // several partitions in one launch (pgs_get_batch_multi): key q belongs to partition slot key_part[q], whose runs are
+    // multi_runs[multi_begin[slot] .. multi_begin[slot + 1]); null for a single-partition batch (rr)
+    const RunDev *multi_runs;
+    const uint32_t *multi_begin;
+    const uint32_t *key_part;
 };
 
 template <uint32_t G>
@@ -187,10 +192,17 @@ __global__ void __launch_bounds__(kReadThreads) k_get(const __grid_constant__ Ge
         res.expire_ts = 0; res.value_off = 0; res.value_len = 0; res.expired = 0;
         res.reserved[0] = res.reserved[1] = res.reserved[2] = 0;
         bool pending = en && klen <= KS; // a key longer than every stored key cannot be found
-        for (uint32_t ri = 0; ri < NR; ri++) { // newest -> oldest
-            if (!g.any(pending)) break;
-            const RunDev &r = runs[ri];
-            bool probe = pending;
+        const RunDev *rbase = runs;      // the runs of the key's partition, newest -> oldest
+        uint32_t nr = NR;
+        if (P.multi_runs && en) {
+            const uint32_t slot = P.key_part[q];
+            rbase = P.multi_runs + P.multi_begin[slot];
+            nr = P.multi_begin[slot + 1] - P.multi_begin[slot];
+        }
+        for (uint32_t ri = 0; g.any(pending && ri < nr); ri++) {
+            const bool act = pending && ri < nr;
+            const RunDev &r = act ? rbase[ri] : runs[0];
+            bool probe = act;
             if (probe && !bloom_may_contain(r.bloom, r.bloom_lines, bh)) { probe = false; if (g.gl == 0) skipped++; }
             if (!g.any(probe)) continue;
             const uint32_t e1 = cur_seek(g, probe, r, C, row, KS, keyrow, klen_row);

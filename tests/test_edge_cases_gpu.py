@@ -167,6 +167,53 @@ def test_upload_many_is_all_or_nothing(pgs, engine):
         part.close()
 
 
+def test_get_batch_over_several_partitions(pgs, engine):
+    """pgs_get_batch_multi: one launch answers keys of several replicas; the same answers as one pgs_get_batch per partition"""
+    rng = np.random.default_rng(8)
+    parts, keysets = [], []
+    try:
+        for p, n_runs in enumerate((1, 3, 5, 0)):  # the last partition holds nothing
+            part = engine.partition(app_id=4, pidx=p)
+            parts.append(part)
+            runs = synth.compaction_runs(k=max(1, n_runs), n_per_run=3000, seed=40 + p)[:n_runs]
+            for r in runs:
+                part.upload_records(r)
+            ks = [r.key(int(i)) for r in runs for i in rng.integers(0, r.n, 150)]
+            keysets.append(ks + [raw_key(b"absent%d" % p, b"x")])
+        keys, slot = [], []
+        for p, ks in enumerate(keysets):          # every partition is also asked for the other partitions' keys
+            for q in range(len(parts)):
+                keys += keysets[q][:40]
+                slot += [p] * len(keysets[q][:40])
+        order = rng.permutation(len(keys))
+        keys, slot = [keys[i] for i in order], np.array([slot[i] for i in order], np.uint32)
+        flat = np.frombuffer(b"".join(keys), np.uint8).copy()
+        off = np.zeros(len(keys) + 1, np.uint32)
+        off[1:] = np.cumsum([len(k) for k in keys])
+        arena = np.zeros(len(keys) * 400, np.uint8)
+        st, res, arena, used = pgs.get_batch_multi(parts, flat, off, slot, synth.NOW, arena)
+        assert st == 0 and used > 0
+        for p, part in enumerate(parts):
+            sel = np.nonzero(slot == p)[0]
+            sub = [keys[i] for i in sel]
+            f2 = np.frombuffer(b"".join(sub), np.uint8).copy()
+            o2 = np.zeros(len(sub) + 1, np.uint32)
+            o2[1:] = np.cumsum([len(k) for k in sub])
+            st2, res2, arena2, _ = part.get_batch(f2, o2, synth.NOW)
+            assert st2 == 0
+            for j, i in enumerate(sel):
+                a, b = res[int(i)], res2[j]
+                assert (a.status, a.expire_ts, a.expired, a.value_len) == (b.status, b.expire_ts, b.expired, b.value_len), (p, j)
+                if a.status == pgs.OK:
+                    assert arena[a.value_off:a.value_off + a.value_len].tobytes() == arena2[b.value_off:b.value_off + b.value_len].tobytes()
+        assert sum(1 for i in range(len(keys)) if res[i].status == pgs.OK) > 100
+        bad = slot.copy(); bad[0] = 9
+        assert pgs.get_batch_multi(parts, flat, off, bad, synth.NOW, arena)[0] == pgs.INVALID_ARGUMENT
+    finally:
+        for part in parts:
+            part.close()
+
+
 def test_empty_partition_reads(engine):
     g, o = Backend("gpu", engine), Backend("oracle")
     try:

@@ -107,6 +107,49 @@ def test_sim_get(pgs, sim, use_bloom):
     print("probes", stats[1], "skipped", stats[2])
 
 
+def test_sim_get_multi_partition(pgs, sim):
+    """pgs_get_batch_multi's kernel shape: one launch, every key looked up in the runs of its own partition slot only"""
+    rng = np.random.default_rng(15)
+    hks = [bytes(rng.integers(0, 256, int(rng.integers(1, 6)), dtype=np.uint8)) for _ in range(8)]
+    runs, items = make_db(pgs, rng, 4, hks, 30)
+    per_run = {}
+    for key, seq, typ, val, run in [(k, s, t, v, r) for r, rr in enumerate(runs) for k, s, t, v in [(rr.key(i), int(rr.seq[i]), int(rr.type[i]), rr.value(i)) for i in range(rr.n)]]:
+        per_run.setdefault(run, []).append((key, seq, typ, val))
+    def best_of(run_ids):
+        best = {}
+        for r in run_ids:
+            for k, s, t, v in per_run.get(r, []):
+                if k not in best or s > best[k][0]:
+                    best[k] = (s, t, v)
+        return best
+    slots = [best_of([0, 1]), best_of([2, 3]), {}]
+    allkeys = sorted(set(k for b in slots for k in b))
+    keys = [allkeys[i] for i in rng.permutation(len(allkeys))[:240]] + [b"", b"\x00\x09nothing"]
+    flat = np.frombuffer(b"".join(keys), np.uint8).copy()
+    off = np.zeros(len(keys) + 1, np.uint32)
+    off[1:] = np.cumsum([len(k) for k in keys])
+    args, keep = run_args(pgs, runs, block_size=1024)
+    res = (pgs.GetResult * len(keys))()
+    arena = np.zeros(1 << 20, np.uint8)
+    stats = (C.c_uint64 * 3)()
+    assert sim.sim_get(*args, flat.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), len(keys), NOW,
+                       arena.ctypes.data_as(C.c_void_p), C.c_uint64(arena.shape[0]), res, stats, 3) == 0
+    hits = 0
+    for i, k in enumerate(keys):
+        best, r = slots[i % 3], res[i]
+        if k not in best or best[k][1] == 0:
+            assert r.status == pgs.NOT_FOUND and not r.expired, (i, k)
+            continue
+        v = best[k][2]
+        ets = int.from_bytes(v[:4], "big")
+        if 0 < ets <= NOW:
+            assert r.status == pgs.NOT_FOUND and r.expired
+        else:
+            hits += 1
+            assert r.status == pgs.OK and arena[r.value_off:r.value_off + r.value_len].tobytes() == v[12:], (i, k)
+    assert hits > 30
+
+
 def model_scan(vis, q, now):
     """the reference loop over the visible records; returns dict like pgs_scan_result + kvs"""
     start, stop = q["start"], q["stop"]

@@ -325,7 +325,7 @@ int32_t sim_get(uint32_t k, const uint8_t **data, const uint64_t *data_bytes, co
     GetParams P{};
     uint32_t mk = 0;
     if (!load_runs(k, data, data_bytes, blk_off, blk_size, n_blocks, runs, P.rr, mk)) return PGS_CORRUPTION;
-    if (!use_bloom) for (uint32_t i = 0; i < k; i++) { P.rr.runs[i].bloom = nullptr; P.rr.runs[i].bloom_lines = 0; }
+    if (!(use_bloom & 1)) for (uint32_t i = 0; i < k; i++) { P.rr.runs[i].bloom = nullptr; P.rr.runs[i].bloom_lines = 0; }
     std::vector<uint8_t> kcopy(keys, keys + key_off[n]);
     kcopy.resize(kcopy.size() + 64);
     unsigned long long cur[4] = {0, 0, 0, 0};
@@ -336,6 +336,14 @@ int32_t sim_get(uint32_t k, const uint8_t **data, const uint64_t *data_bytes, co
     P.KSW = (P.KS + 8) / 4 + 1;
     P.group_smem = (uint32_t)((sizeof(CurState) + 2 * P.KSW * 4 + 15) & ~(size_t)15);
     const uint32_t dyn = kMaxReadRuns * (uint32_t)sizeof(RunDev) + (kReadThreads / 8) * P.group_smem;
+    // use_bloom & 2: the multi-partition shape of pgs_get_batch_multi -- slot 0 owns the runs [0, k/2), slot 1 the rest, slot 2
+    // is an empty partition; key i belongs to slot i % 3
+    std::vector<RunDev> packed(P.rr.runs, P.rr.runs + k);
+    std::vector<uint32_t> begin = {0, k / 2, k, k}, kp(n);
+    if (use_bloom & 2) {
+        for (uint32_t i = 0; i < n; i++) kp[i] = i % 3;
+        P.multi_runs = packed.data(); P.multi_begin = begin.data(); P.key_part = kp.data();
+    }
     PGS_LAUNCH(k_get<8>, 2, kReadThreads, dyn, 0, P);
     stats[0] = cur[0]; stats[1] = cur[1]; stats[2] = cur[2];
     return err[0] ? (int32_t)err[0] : PGS_OK;
