@@ -225,12 +225,13 @@ def sharded_read_leg(pgs, torch, dist, eng, rank, world, args, barrier, check_cp
         cap = int(sel.size) * (VAL + 16)
         work.append(("get", -1, (flat, off, kslot, np.zeros(cap, np.uint8), (pgs.GetResult * int(sel.size))(), g_owner[sel].copy())))
         my_gets = int(sel.size)
-    for p, part in parts.items():
-        sel = np.nonzero(s_owner == p)[0]
-        if sel.size:
-            sb = part.prefix_scan_batch([table.hashkeys[int(h)].tobytes() for h in sh[sel]], max_records=80, arena_stride=24576)
-            work.append(("scan", p, sb))
-            my_scans += int(sel.size)
+    # prefix scans: likewise one launch over all of this rank's partitions (pgs_range_scan_many_multi)
+    sel = np.nonzero(np.isin(s_owner, plist))[0]
+    if sel.size:
+        sslot = np.array([slot_of[int(p)] for p in s_owner[sel]], np.uint32)
+        sb = pgs.ScanBatch(None, [table.hashkeys[int(h)].tobytes() for h in sh[sel]], 80, 24576, parts=[parts[q] for q in plist], req_part=sslot)
+        work.append(("scan", -1, (sb, s_owner[sel].copy())))
+        my_scans = int(sel.size)
     lock = threading.Lock()
     tot = {"found": 0, "returned": 0, "kernel_ms": 0.0, "calls": 0}
 
@@ -247,11 +248,12 @@ def sharded_read_leg(pgs, torch, dist, eng, rank, world, args, barrier, check_cp
             with lock:
                 tot["found"] += found; tot["kernel_ms"] += ms; tot["calls"] += 1
         else:
-            st = payload.run(NOW)
+            sb = payload[0]
+            st = sb.run(NOW)
             assert st == 0, st
             ms = eng.last_kernel_ms
             with lock:
-                tot["returned"] += int(payload.kbase[-1]); tot["kernel_ms"] += ms; tot["calls"] += 1
+                tot["returned"] += int(sb.kbase[-1]); tot["kernel_ms"] += ms; tot["calls"] += 1
 
     pool = ThreadPoolExecutor(max_workers=args.read_threads)
     list(pool.map(serve, work))  # warm-up pass (also the answer that is checked below)
@@ -279,7 +281,7 @@ def sharded_read_leg(pgs, torch, dist, eng, rank, world, args, barrier, check_cp
         "workload": f"{args.partitions} partitions x 3 runs (L2 full, L1 30 %, L0 10 % newer versions), {args.table_hashkeys} hash keys x 64 sort keys; "
                     f"YCSB-C zipfian(0.99) over hash keys: {args.n_get} get(hk,sk) + {args.n_scan} multi_get(hk, all sort keys), "
                     f"routed by crc64(hash_key) % {args.partitions}; partition p on rank p % N; per rank the gets of all its partitions go through "
-                    f"one pgs_get_batch_multi launch, the prefix scans through one pgs_range_scan_many call per partition on {args.read_threads} host threads",
+                    f"one pgs_get_batch_multi launch and the prefix scans through one pgs_range_scan_many_multi launch, the two calls on separate host threads",
         "scaling": "strong", "collective": "none on the data path (partitions are independent)",
         "partitions_per_rank": len(parts), "records_resident": int(t[4]),
         "get_keys_per_s": float(t[1]) / wall_max, "scan_keys_per_s": float(t[2]) / wall_max,
@@ -312,12 +314,16 @@ def sharded_read_leg(pgs, torch, dist, eng, rank, world, args, barrier, check_cp
         for kind, p, payload in work:
             if kind == "get":
                 continue
-            bruns = [orc.BlockRunCPU.from_blocks(b) for b in reversed(host_runs[p])]  # newest first
-            if True:
-                hks = np.frombuffer(b"".join(bytes(payload.reqs[i].start.data[2:2 + HK]) for i in range(payload.n)), np.uint8)
-                cnt, _nb, secs = orc.prefix_scan_many(bruns, hks, np.arange(payload.n + 1, dtype=np.uint32) * np.uint32(HK), NOW, threads)
+            sb, owners = payload
+            for q in plist:  # scans: likewise partition by partition
+                selq = np.nonzero(owners == q)[0]
+                if not selq.size:
+                    continue
+                bruns = [orc.BlockRunCPU.from_blocks(b) for b in reversed(host_runs[q])]  # newest first
+                hks = np.frombuffer(b"".join(bytes(sb.reqs[int(i)].start.data[2:2 + HK]) for i in selq), np.uint8)
+                cnt, _nb, secs = orc.prefix_scan_many(bruns, hks, np.arange(selq.size + 1, dtype=np.uint32) * np.uint32(HK), NOW, threads)
                 c_ret += cnt
-            c_secs += secs
+                c_secs += secs
         out["parity_checked"] = bool(c_found == first["found"] and c_ret == first["returned"])
         out["cpu_baseline"] = {"requests_per_s": (my_gets + my_scans) / c_secs, "cores": threads, "kind": "port",
                                "what": "oracle-CPU lookups on the same block runs (not RocksDB)",

@@ -298,6 +298,13 @@ PGS_API int32_t pgs_range_scan_many(pgs_partition *p, const pgs_scan_request *re
                                     uint8_t *arena, uint64_t arena_cap, pgs_kv *kvs, uint64_t kv_cap,
                                     uint8_t *resume_keys, uint32_t resume_stride,
                                     pgs_scan_result *results, uint64_t *arena_base, uint32_t *kv_base);
+/* The same for FORWARD scans over several partitions of one engine in ONE launch: request i merges the runs of
+ * parts[req_part[i]] only.  A reverse request gets PGS_NOT_SUPPORTED (those go through pgs_range_scan_many). */
+PGS_API int32_t pgs_range_scan_many_multi(pgs_partition *const *parts, uint32_t n_parts, const pgs_scan_request *reqs,
+                                          const uint32_t *req_part, uint32_t n, uint32_t now, uint64_t arena_stride,
+                                          uint32_t kv_stride, uint8_t *arena, uint64_t arena_cap, pgs_kv *kvs,
+                                          uint64_t kv_cap, uint8_t *resume_keys, uint32_t resume_stride,
+                                          pgs_scan_result *results, uint64_t *arena_base, uint32_t *kv_base);
 
 /* ============================================================================================
  * host-side helpers of the product (no device work)

@@ -181,6 +181,8 @@ def lib() -> C.CDLL:
     L.pgs_engine_last_runs_skipped.restype = C.c_uint64
     L.pgs_range_scan_many.argtypes = [vp, C.POINTER(ScanRequest), C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, vp, C.c_uint64,
                                       vp, C.c_uint64, vp, C.c_uint32, vp, vp, vp]
+    L.pgs_range_scan_many_multi.argtypes = [C.POINTER(vp), C.c_uint32, C.POINTER(ScanRequest), vp, C.c_uint32, C.c_uint32, C.c_uint64,
+                                            C.c_uint32, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint32, vp, vp, vp]
     L.pgs_partition_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(vp)]
     L.pgs_partition_destroy.argtypes = [vp]
     L.pgs_partition_destroy.restype = None
@@ -555,9 +557,16 @@ class Partition:
 
 
 class ScanBatch:
-    def __init__(self, part: Partition, hashkeys, max_records: int, arena_stride: int, alloc=None):
+    def __init__(self, part, hashkeys, max_records: int, arena_stride: int, alloc=None, parts=None, req_part=None):
+        """part: one Partition; or parts = a list of partitions of one engine and req_part[i] = the slot of request i
+        (pgs_range_scan_many_multi: one launch over all of them)"""
         alloc = alloc or (lambda n, dt: np.zeros(n, dt))  # bench.py passes a pinned-memory allocator
         self.part = part
+        self.parts = parts
+        if parts is not None:
+            self.handles = (vp * len(parts))(*[p.h for p in parts])
+            self.req_part = np.ascontiguousarray(req_part, np.uint32)
+            assert self.req_part.shape[0] == len(hashkeys)
         n = len(hashkeys)
         self.n = n
         self.reqs = (ScanRequest * n)()
@@ -583,6 +592,11 @@ class ScanBatch:
         self.kbase = np.zeros(n + 1, np.uint32)
 
     def run(self, now: int) -> int:
+        if self.parts is not None:
+            return lib().pgs_range_scan_many_multi(self.handles, len(self.parts), self.reqs, _ptr(self.req_part), self.n, now,
+                                                   self.arena_stride, self.max_records, _ptr(self.arena), self.arena.shape[0],
+                                                   _ptr(self.kvs), self.kvs.shape[0] // 5, None, 0, self.results, _ptr(self.abase),
+                                                   _ptr(self.kbase))
         return lib().pgs_range_scan_many(self.part.h, self.reqs, self.n, now, self.arena_stride, self.max_records,
                                          _ptr(self.arena), self.arena.shape[0], _ptr(self.kvs), self.kvs.shape[0] // 5, None, 0,
                                          self.results, _ptr(self.abase), _ptr(self.kbase))

@@ -850,24 +850,85 @@ int32_t lookup_init_kernels(int max_smem)
 {
     PGS_CUDA(allow_max_smem(k_scan, max_smem));
     PGS_CUDA(cudaFuncSetAttribute(k_scan, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    PGS_CUDA(allow_max_smem(k_get<8>, max_smem));
-    PGS_CUDA(allow_max_smem(k_scan_fwd<8>, max_smem));
-    PGS_CUDA(allow_max_smem(k_scan_fwd<16>, max_smem));
-    PGS_CUDA(allow_max_smem(k_scan_fwd<32>, max_smem));
+    PGS_CUDA(allow_max_smem(k_get<8, false>, max_smem)); PGS_CUDA(allow_max_smem(k_get<8, true>, max_smem));
+    PGS_CUDA(allow_max_smem(k_scan_fwd<8, false>, max_smem)); PGS_CUDA(allow_max_smem(k_scan_fwd<8, true>, max_smem));
+    PGS_CUDA(allow_max_smem(k_scan_fwd<16, false>, max_smem)); PGS_CUDA(allow_max_smem(k_scan_fwd<16, true>, max_smem));
+    PGS_CUDA(allow_max_smem(k_scan_fwd<32, false>, max_smem)); PGS_CUDA(allow_max_smem(k_scan_fwd<32, true>, max_smem));
     return PGS_OK;
 }
+
+// the runs of several partitions, packed for one launch (pgs_range_scan_many_multi)
+struct ScanMulti {
+    std::vector<RunDev> packed;
+    std::vector<uint32_t> begin;
+    const uint32_t *req_part;
+};
+
+static int32_t scan_launch(Partition &part, std::vector<std::shared_ptr<Run>> &runs, ScanParams &P, const ScanMulti *multi,
+                           const pgs_scan_request *reqs, uint32_t n, uint32_t now, unsigned long long arena_stride, uint32_t kv_stride,
+                           uint8_t *arena, uint64_t arena_cap, pgs_kv *kvs, uint64_t kv_cap, uint8_t *resume, uint32_t resume_stride,
+                           pgs_scan_result *results, uint64_t *arena_base, uint32_t *kv_base);
 
 int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uint32_t now, unsigned long long arena_stride,
                   uint32_t kv_stride, uint8_t *arena, uint64_t arena_cap, pgs_kv *kvs, uint64_t kv_cap, uint8_t *resume,
                   uint32_t resume_stride, pgs_scan_result *results, uint64_t *arena_base, uint32_t *kv_base,
                   const std::vector<std::shared_ptr<Run>> *pinned)
 {
-    Engine *e = part.eng;
     std::vector<std::shared_ptr<Run>> runs;
     ScanParams P{};
     int32_t rc = snapshot_runs(part, runs, P.rr, P.KS, pinned);
     if (rc != PGS_OK) return rc;
     if (n == 0) return PGS_OK;
+    return scan_launch(part, runs, P, nullptr, reqs, n, now, arena_stride, kv_stride, arena, arena_cap, kvs, kv_cap, resume, resume_stride,
+                       results, arena_base, kv_base);
+}
+
+// forward scans over several partitions of one engine in one launch: request i reads partition slot req_part[i]
+static int32_t scan_many_multi(pgs_partition *const *parts, uint32_t n_parts, const pgs_scan_request *reqs, const uint32_t *req_part, uint32_t n,
+                               uint32_t now, unsigned long long arena_stride, uint32_t kv_stride, uint8_t *arena, uint64_t arena_cap, pgs_kv *kvs,
+                               uint64_t kv_cap, uint8_t *resume, uint32_t resume_stride, pgs_scan_result *results, uint64_t *arena_base,
+                               uint32_t *kv_base)
+{
+    Partition &part = parts[0]->p;
+    std::vector<std::shared_ptr<Run>> runs; // every run a request may touch stays alive until the launch is done
+    ScanParams P{};
+    ScanMulti M;
+    M.req_part = req_part;
+    M.begin.push_back(0);
+    P.KS = 8;
+    uint32_t max_nr = 0;
+    for (uint32_t p = 0; p < n_parts; p++) {
+        Partition &pp = parts[p]->p;
+        if (pp.eng != part.eng || pp.data_version != part.data_version) { set_error("range_scan_many_multi: partitions of different engines / data versions"); return PGS_INVALID_ARGUMENT; }
+        std::vector<std::shared_ptr<Run>> rs;
+        ReadRuns rr;
+        uint32_t ks = 0;
+        int32_t rc = snapshot_runs(pp, rs, rr, ks);
+        if (rc != PGS_OK) return rc;
+        for (uint32_t i = 0; i < rr.n; i++) M.packed.push_back(rr.runs[i]);
+        M.begin.push_back((uint32_t)M.packed.size());
+        runs.insert(runs.end(), rs.begin(), rs.end());
+        P.KS = std::max(P.KS, ks);
+        max_nr = std::max(max_nr, rr.n);
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        if (req_part[i] >= n_parts) { set_error("range_scan_many_multi: request %u names partition slot %u of %u", i, req_part[i], n_parts); return PGS_INVALID_ARGUMENT; }
+        if (reqs[i].reverse) { set_error("range_scan_many_multi: reverse scans go through pgs_range_scan_many"); return PGS_NOT_SUPPORTED; }
+    }
+    if (n == 0) return PGS_OK;
+    P.rr.n = max_nr;
+    if (!M.packed.empty())
+        for (uint32_t i = 0; i < kMaxReadRuns; i++) P.rr.runs[i] = M.packed[0]; // a valid dummy for idle groups
+    return scan_launch(part, runs, P, &M, reqs, n, now, arena_stride, kv_stride, arena, arena_cap, kvs, kv_cap, resume, resume_stride, results,
+                       arena_base, kv_base);
+}
+
+static int32_t scan_launch(Partition &part, std::vector<std::shared_ptr<Run>> &runs, ScanParams &P, const ScanMulti *multi,
+                           const pgs_scan_request *reqs, uint32_t n, uint32_t now, unsigned long long arena_stride, uint32_t kv_stride,
+                           uint8_t *arena, uint64_t arena_cap, pgs_kv *kvs, uint64_t kv_cap, uint8_t *resume, uint32_t resume_stride,
+                           pgs_scan_result *results, uint64_t *arena_base, uint32_t *kv_base)
+{
+    Engine *e = part.eng;
     PGS_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = e->read_stream();
     // flatten requests
@@ -902,7 +963,7 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
     P.n = n; P.now = now; P.data_version = part.data_version;
     P.use_tma = (e->cfg.flags & PGS_ENGINE_NO_TMA) ? 0 : 1;
     P.kv_stride = kv_stride; P.arena_stride = (arena_stride + 15) & ~15ull; P.resume_stride = resume_stride ? resume_stride : P.KS;
-    if (P.rr.n == 0) { // empty DB: every iterator is invalid from the start
+    if (multi ? multi->packed.empty() : P.rr.n == 0) { // empty DB: every iterator is invalid from the start
         memset(results, 0, sizeof(pgs_scan_result) * n);
         if (arena_base) for (uint32_t i = 0; i <= n; i++) arena_base[i] = 0;
         if (kv_base) for (uint32_t i = 0; i <= n; i++) kv_base[i] = 0;
@@ -912,8 +973,13 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
     ScanReqDev *d_reqs = nullptr; uint8_t *d_blob = nullptr, *d_arena = nullptr, *d_resume = nullptr, *d_parena = nullptr;
     pgs_scan_result *d_res = nullptr; pgs_kv *d_kvs = nullptr, *d_pkvs = nullptr; uint32_t *d_err = nullptr, *d_kbase = nullptr;
     unsigned long long *d_abase = nullptr;
+    RunDev *d_multi = nullptr;
+    uint32_t *d_begin = nullptr, *d_part = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     auto cleanup = [&]() {
+        if (d_multi) cudaFreeAsync(d_multi, st);
+        if (d_begin) cudaFreeAsync(d_begin, st);
+        if (d_part) cudaFreeAsync(d_part, st);
         cudaFreeAsync(d_reqs, st); cudaFreeAsync(d_blob, st); cudaFreeAsync(d_arena, st); cudaFreeAsync(d_resume, st);
         cudaFreeAsync(d_parena, st); cudaFreeAsync(d_res, st); cudaFreeAsync(d_kvs, st); cudaFreeAsync(d_pkvs, st);
         cudaFreeAsync(d_err, st); cudaFreeAsync(d_kbase, st); cudaFreeAsync(d_abase, st);
@@ -933,6 +999,15 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
     CK(cudaMemcpyAsync(d_reqs, dev.data(), sizeof(ScanReqDev) * n, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d_err, 0, 256, st));
+    if (multi) {
+        CK(cudaMallocAsync(&d_multi, sizeof(RunDev) * multi->packed.size(), st));
+        CK(cudaMallocAsync(&d_begin, sizeof(uint32_t) * multi->begin.size(), st));
+        CK(cudaMallocAsync(&d_part, sizeof(uint32_t) * n, st));
+        CK(cudaMemcpyAsync(d_multi, multi->packed.data(), sizeof(RunDev) * multi->packed.size(), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_begin, multi->begin.data(), sizeof(uint32_t) * multi->begin.size(), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_part, multi->req_part, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+        P.multi_runs = d_multi; P.multi_begin = d_begin; P.req_part = d_part;
+    }
     if (need_crc) {
         std::lock_guard<std::mutex> g(g_crc_rd_mu);
         int dv = e->device & 15;
@@ -957,7 +1032,8 @@ int32_t scan_many(Partition &part, const pgs_scan_request *reqs, uint32_t n, uin
         P.group_smem = (uint32_t)((NR * (sizeof(CurState) + P.KSW * 4) + 3 * P.KSW * 4 + 15) & ~(size_t)15);
         const uint32_t dyn = 2048 + kMaxReadRuns * (uint32_t)sizeof(RunDev) + (kReadThreads / G) * P.group_smem;
         if (dyn > (uint32_t)e->max_smem_optin) { cleanup(); set_error("scan: %u runs with keys of %u bytes do not fit shared memory", NR, P.KS); return PGS_NOT_SUPPORTED; }
-        auto kern = G == 8 ? k_scan_fwd<8> : G == 16 ? k_scan_fwd<16> : k_scan_fwd<32>;
+        auto kern = multi ? (G == 8 ? k_scan_fwd<8, true> : G == 16 ? k_scan_fwd<16, true> : k_scan_fwd<32, true>)
+                          : (G == 8 ? k_scan_fwd<8, false> : G == 16 ? k_scan_fwd<16, false> : k_scan_fwd<32, false>);
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)kReadThreads, (size_t)dyn));
         const uint32_t per_cta = kReadThreads / G;
@@ -1152,11 +1228,12 @@ static int32_t get_batch_impl(pgs_partition *const *parts, uint32_t n_parts, con
     const uint32_t dyn = kMaxReadRuns * (uint32_t)sizeof(RunDev) + (kReadThreads / G) * P.group_smem;
     if (dyn > (uint32_t)e->max_smem_optin) { cleanup(); return PGS_NOT_SUPPORTED; }
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_get<G>, (int)kReadThreads, (size_t)dyn));
+    auto kern = key_part ? k_get<G, true> : k_get<G, false>;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)kReadThreads, (size_t)dyn));
     const uint32_t per_cta = kReadThreads / G;
     const uint32_t grid = std::min<uint32_t>((n + per_cta - 1) / per_cta, (uint32_t)std::max(1, occ) * e->sm_count);
     CK(cudaEventRecord(ev_a, st));
-    k_get<G><<<grid, kReadThreads, dyn, st>>>(P);
+    kern<<<grid, kReadThreads, dyn, st>>>(P);
     CK(cudaEventRecord(ev_b, st));
     e->launches++;
     uint32_t herr = 0;
@@ -1213,4 +1290,16 @@ extern "C" int32_t pgs_range_scan_many(pgs_partition *ph, const pgs_scan_request
     if (!ph || (n && (!reqs || !results))) return PGS_INVALID_ARGUMENT;
     return scan_many(ph->p, reqs, n, now, arena_stride, kv_stride, arena, arena_cap, kvs, kv_cap, resume_keys, resume_stride, results,
                      arena_base, kv_base, nullptr);
+}
+
+extern "C" int32_t pgs_range_scan_many_multi(pgs_partition *const *parts, uint32_t n_parts, const pgs_scan_request *reqs, const uint32_t *req_part,
+                                             uint32_t n, uint32_t now, uint64_t arena_stride, uint32_t kv_stride, uint8_t *arena,
+                                             uint64_t arena_cap, pgs_kv *kvs, uint64_t kv_cap, uint8_t *resume_keys, uint32_t resume_stride,
+                                             pgs_scan_result *results, uint64_t *arena_base, uint32_t *kv_base)
+{
+    if (!parts || !n_parts || (n && (!reqs || !req_part || !results))) return PGS_INVALID_ARGUMENT;
+    for (uint32_t p = 0; p < n_parts; p++)
+        if (!parts[p]) return PGS_INVALID_ARGUMENT;
+    return scan_many_multi(parts, n_parts, reqs, req_part, n, now, arena_stride, kv_stride, arena, arena_cap, kvs, kv_cap, resume_keys,
+                           resume_stride, results, arena_base, kv_base);
 }

@@ -158,7 +158,7 @@ struct GetParams {
     const uint32_t *key_part;
 };
 
-template <uint32_t G>
+template <uint32_t G, bool MULTI>
 __global__ void __launch_bounds__(kReadThreads) k_get(const __grid_constant__ GetParams P)
 {
     PGS_SMEM_DYN(dyn);
@@ -192,16 +192,19 @@ __global__ void __launch_bounds__(kReadThreads) k_get(const __grid_constant__ Ge
         res.expire_ts = 0; res.value_off = 0; res.value_len = 0; res.expired = 0;
         res.reserved[0] = res.reserved[1] = res.reserved[2] = 0;
         bool pending = en && klen <= KS; // a key longer than every stored key cannot be found
-        const RunDev *rbase = runs;      // the runs of the key's partition, newest -> oldest
+        const RunDev *rbase = runs;      // the runs of the key's partition, newest -> oldest (MULTI: in global memory)
         uint32_t nr = NR;
-        if (P.multi_runs && en) {
-            const uint32_t slot = P.key_part[q];
-            rbase = P.multi_runs + P.multi_begin[slot];
-            nr = P.multi_begin[slot + 1] - P.multi_begin[slot];
+        if constexpr (MULTI) {
+            if (en) {
+                const uint32_t slot = P.key_part[q];
+                rbase = P.multi_runs + P.multi_begin[slot];
+                nr = P.multi_begin[slot + 1] - P.multi_begin[slot];
+            }
         }
-        for (uint32_t ri = 0; g.any(pending && ri < nr); ri++) {
+        for (uint32_t ri = 0; MULTI ? g.any(pending && ri < nr) : ri < NR; ri++) {
+            if (!MULTI && !g.any(pending)) break;
             const bool act = pending && ri < nr;
-            const RunDev &r = act ? rbase[ri] : runs[0];
+            const RunDev &r = MULTI ? (act ? rbase[ri] : runs[0]) : runs[ri];
             bool probe = act;
             if (probe && !bloom_may_contain(r.bloom, r.bloom_lines, bh)) { probe = false; if (g.gl == 0) skipped++; }
             if (!g.any(probe)) continue;
@@ -270,11 +273,16 @@ struct ScanParams {
     uint32_t *error;
     uint32_t *ticket;
     unsigned long long *phase_cycles; // [16] or null (PGS_PHASE_TIMING=1, reverse kernel only)
+    // requests of several partitions in one launch (pgs_range_scan_many_multi, forward only): request i reads the runs
+    // multi_runs[multi_begin[req_part[i]] .. multi_begin[req_part[i] + 1]); rr.n = the largest run count; null otherwise
+    const RunDev *multi_runs;
+    const uint32_t *multi_begin;
+    const uint32_t *req_part;
 };
 
 enum : uint8_t { RS_NORMAL = 0, RS_EXPIRED = 1, RS_FILTERED = 2, RS_HASH_INVALID = 3 };
 
-template <uint32_t G>
+template <uint32_t G, bool MULTI>
 __global__ void __launch_bounds__(kReadThreads) k_scan_fwd(const __grid_constant__ ScanParams P)
 {
     PGS_SMEM_DYN(dyn);
@@ -322,15 +330,26 @@ __global__ void __launch_bounds__(kReadThreads) k_scan_fwd(const __grid_constant
         uint8_t *arena = P.arena + (size_t)rq * P.arena_stride;
         uint32_t err = 0;
 
+        // the runs of the request's partition (MULTI: in global memory, per request)
+        const RunDev *rbase = runs;
+        uint32_t nr = NR;
+        if constexpr (MULTI) {
+            if (en) {
+                const uint32_t slot = P.req_part[rq];
+                rbase = P.multi_runs + P.multi_begin[slot];
+                nr = P.multi_begin[slot + 1] - P.multi_begin[slot];
+            }
+        }
         // ---- Seek: every run's cursor to its first entry >= start; runs whose Bloom filter excludes the prefix stay closed ----
         uint32_t live = 0, my_run = 0, dpos = 0;
         bool by_byte = false;
         for (uint32_t j = 0; j < NR; j++) {
-            bool use = en && !err && pre_len != 0xFFFFFFFFu;
-            if (use && pre_len && !bloom_may_contain(runs[j].bloom, runs[j].bloom_lines, pre_hash)) use = false;
+            bool use = en && !err && pre_len != 0xFFFFFFFFu && j < nr;
+            const RunDev &rj = MULTI ? (use ? rbase[j] : runs[0]) : runs[j];
+            if (use && pre_len && !bloom_may_contain(rj.bloom, rj.bloom_lines, pre_hash)) use = false;
             CurState *C = &cs[j];
             if (en && !use && g.gl == 0) C->live = 0;
-            const uint32_t e1 = cur_seek(g, use, runs[j], C, rows + j * KSW, KS, rowSTART, start_len);
+            const uint32_t e1 = cur_seek(g, use, rj, C, rows + j * KSW, KS, rowSTART, start_len);
             if (use) err = e1;
             g.sync();
             const bool ins = use && !err && C->live;
@@ -435,7 +454,7 @@ __global__ void __launch_bounds__(kReadThreads) k_scan_fwd(const __grid_constant
                             else {
                                 uint8_t *dst = arena + arena_used;
                                 for (uint32_t i = g.gl; i < klen_out; i += G) dst[i] = key[koff + i];
-                                if (vlen_out) grp_copy(g, dst + klen_out, runs[c].data + cur_base(C) + C->voff + hdr, vlen_out);
+                                if (vlen_out) grp_copy(g, dst + klen_out, (MULTI ? rbase[c] : runs[c]).data + cur_base(C) + C->voff + hdr, vlen_out);
                                 if (g.gl == 0) {
                                     pgs_kv kv;
                                     kv.key_off = (uint32_t)arena_used; kv.key_len = klen_out;
@@ -465,7 +484,7 @@ __global__ void __launch_bounds__(kReadThreads) k_scan_fwd(const __grid_constant
             g.sync();
             // step the cursor, restore the merge order
             const bool adv = rec && advance && !err;
-            const uint32_t e3 = cur_next(g, adv, runs[c], C, row, KS);
+            const uint32_t e3 = cur_next(g, adv, MULTI ? (adv ? rbase[c] : runs[0]) : runs[c], C, row, KS);
             if (adv && e3) { err = e3; done = true; }
             const bool alive = adv && !e3 && C->live != 0;
             bool searching = alive && live > 1;

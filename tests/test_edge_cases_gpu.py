@@ -229,3 +229,51 @@ def test_empty_partition_reads(engine):
     finally:
         g.close()
         o.close()
+
+
+def test_prefix_scans_over_several_partitions(pgs, engine):
+    """pgs_range_scan_many_multi: one launch answers multi_get-shaped scans of several replicas, with the same records as one
+    pgs_range_scan_many per partition"""
+    rng = np.random.default_rng(9)
+    parts, hksets = [], []
+    try:
+        for p, n_runs in enumerate((2, 4, 0, 7)):  # partition 2 holds nothing
+            part = engine.partition(app_id=5, pidx=p)
+            parts.append(part)
+            runs = synth.compaction_runs(k=max(1, n_runs), n_per_run=3000, seed=60 + p)[:n_runs]
+            for r in runs:
+                part.upload_records(r)
+            hks = set()
+            for r in runs:
+                for i in rng.integers(0, r.n, 40):
+                    k = r.key(int(i))
+                    hks.add(k[2:2 + int.from_bytes(k[:2], "big")])
+            hksets.append(sorted(hks)[:60] + [b"absent%d" % p])
+        hashkeys, slot = [], []
+        for p in range(len(parts)):               # every partition is also asked for the other partitions' hash keys
+            for q in range(len(parts)):
+                hashkeys += hksets[q][:25]
+                slot += [p] * len(hksets[q][:25])
+        order = rng.permutation(len(hashkeys))
+        hashkeys, slot = [hashkeys[i] for i in order], np.array([slot[i] for i in order], np.uint32)
+        multi = pgs.ScanBatch(None, hashkeys, 200, 65536, parts=parts, req_part=slot)
+        assert multi.run(synth.NOW) == 0
+        total = 0
+        for p, part in enumerate(parts):
+            sel = np.nonzero(slot == p)[0]
+            one = part.prefix_scan_batch([hashkeys[i] for i in sel], max_records=200, arena_stride=65536)
+            assert one.run(synth.NOW) == 0
+            for j, i in enumerate(sel):
+                a, b = multi.results[int(i)], one.results[j]
+                assert (a.count, a.iter_count, a.expire_count, a.filter_count, a.size, a.complete, a.iter_valid) == \
+                       (b.count, b.iter_count, b.expire_count, b.filter_count, b.size, b.complete, b.iter_valid), (p, j)
+                assert multi.records(int(i)) == one.records(j), (p, j)
+                total += a.count
+        assert total > 200
+        bad = slot.copy(); bad[0] = 9
+        assert pgs.ScanBatch(None, hashkeys, 200, 65536, parts=parts, req_part=bad).run(synth.NOW) == pgs.INVALID_ARGUMENT
+        multi.reqs[0].reverse = 1
+        assert multi.run(synth.NOW) == pgs.NOT_SUPPORTED
+    finally:
+        for part in parts:
+            part.close()

@@ -292,6 +292,39 @@ def test_sim_scan_forward(pgs, sim, n_runs, lanes):
         assert g_ == want, (i, q, {k: (g_[k], want[k]) for k in want if g_[k] != want[k]})
 
 
+@pytest.mark.parametrize("n_runs,lanes", [(4, 0), (5, 16)])
+def test_sim_scan_multi_partition(pgs, sim, n_runs, lanes):
+    """pgs_range_scan_many_multi's kernel shape: one launch, every request merges the runs of its own partition slot only"""
+    rng = np.random.default_rng(300 + n_runs)
+    hks = [b"h%d" % i for i in range(5)] + [b"", bytes([0xff, 0xff])]
+    runs, items = make_db(pgs, rng, n_runs, hks, 30)
+    assert len(runs) == n_runs
+    half = n_runs // 2
+    vis_of = [visible(items[:half])[0], visible(items[half:])[0], []]
+    args, keep = run_args(pgs, runs, block_size=512, ri=4)
+    reqs = []
+    for hk in hks + [b"nope"]:
+        nxt = bytearray(raw_key(hk, b""))
+        while nxt and nxt[-1] == 0xff:
+            nxt.pop()
+        nxt[-1] += 1
+        base = dict(start=raw_key(hk, b""), stop=bytes(nxt), start_inclusive=True, stop_inclusive=False, key_mode=1, prefix=1,
+                    max_count=3000, max_iter_count=3000, max_iter_size=0)
+        for q in (base, dict(base, max_count=7), dict(base, start=raw_key(hk, b"s0010"), stop=raw_key(hk, b"s0020"), stop_inclusive=True),
+                  dict(base, sft=1, spat=b"01", count_only=1),
+                  dict(base, key_mode=0, prefix=0, stop=raw_key(hk, b"\xff" * 8), return_expire_ts=1, max_count=11)):
+            reqs += [q, q, q]   # the same request against each of the three slots
+    reqs.append(dict(start=b"", stop=b"\xff\xff\xff", start_inclusive=True, stop_inclusive=True, key_mode=0, prefix=0,
+                     max_count=100000, max_iter_count=100000, max_iter_size=0))
+    got = do_scans(pgs, sim, args, reqs, lanes | 0x100)
+    nonempty = 0
+    for i, (q, g_) in enumerate(zip(reqs, got)):
+        want = model_scan(vis_of[i % 3], q, NOW)
+        nonempty += want["count"] > 0
+        assert g_ == want, (i, i % 3, q, {k: (g_[k], want[k]) for k in want if g_[k] != want[k]})
+    assert nonempty > 20
+
+
 def test_sim_bloom_no_false_negatives(pgs, sim):
     rng = np.random.default_rng(9)
     runs = synth.compaction_runs(k=3, n_per_run=400, seed=9)

@@ -344,7 +344,8 @@ int32_t sim_get(uint32_t k, const uint8_t **data, const uint64_t *data_bytes, co
         for (uint32_t i = 0; i < n; i++) kp[i] = i % 3;
         P.multi_runs = packed.data(); P.multi_begin = begin.data(); P.key_part = kp.data();
     }
-    PGS_LAUNCH(k_get<8>, 2, kReadThreads, dyn, 0, P);
+    if (use_bloom & 2) PGS_LAUNCH((k_get<8, true>), 2, kReadThreads, dyn, 0, P);
+    else PGS_LAUNCH((k_get<8, false>), 2, kReadThreads, dyn, 0, P);
     stats[0] = cur[0]; stats[1] = cur[1]; stats[2] = cur[2];
     return err[0] ? (int32_t)err[0] : PGS_OK;
 }
@@ -384,15 +385,30 @@ int32_t sim_scan(uint32_t k, const uint8_t **data, const uint64_t *data_bytes, c
     P.results = results; P.kvs = kvs; P.kv_stride = kv_stride; P.arena = arena; P.arena_stride = arena_stride;
     P.resume = resume; P.resume_stride = resume_stride; P.error = err; P.ticket = err + 8;
     if (need_crc) { make_crc(); P.crc_table = (const unsigned long long *)crc_tab; }
+    // lanes & 0x100: the multi-partition shape of pgs_range_scan_many_multi -- slot 0 owns the runs [0, k/2), slot 1 the rest,
+    // slot 2 is an empty partition; request i belongs to slot i % 3
+    const bool multi = (lanes & 0x100) != 0;
+    lanes &= 0xFF;
+    std::vector<RunDev> packed(P.rr.runs, P.rr.runs + k);
+    std::vector<uint32_t> begin = {0, k / 2, k, k}, rp(n);
+    if (multi) {
+        for (uint32_t i = 0; i < n; i++) rp[i] = i % 3;
+        P.multi_runs = packed.data(); P.multi_begin = begin.data(); P.req_part = rp.data();
+        P.rr.n = k - k / 2;
+    }
     const uint32_t G = lanes ? lanes : (k <= 8 ? 8 : k <= 16 ? 16 : 32);
     if (G < k) return PGS_INVALID_ARGUMENT;
     P.KS = std::max(8u, (mk + 3) & ~3u);
     P.KSW = (P.KS + 8) / 4 + 1;
     P.group_smem = (uint32_t)((k * (sizeof(CurState) + P.KSW * 4) + 3 * P.KSW * 4 + 15) & ~(size_t)15);
     const uint32_t dyn = 2048 + kMaxReadRuns * (uint32_t)sizeof(RunDev) + (kReadThreads / G) * P.group_smem;
-    if (G == 8) PGS_LAUNCH(k_scan_fwd<8>, 2, kReadThreads, dyn, 0, P);
-    else if (G == 16) PGS_LAUNCH(k_scan_fwd<16>, 2, kReadThreads, dyn, 0, P);
-    else PGS_LAUNCH(k_scan_fwd<32>, 2, kReadThreads, dyn, 0, P);
+    if (multi) {
+        if (G == 8) PGS_LAUNCH((k_scan_fwd<8, true>), 2, kReadThreads, dyn, 0, P);
+        else if (G == 16) PGS_LAUNCH((k_scan_fwd<16, true>), 2, kReadThreads, dyn, 0, P);
+        else PGS_LAUNCH((k_scan_fwd<32, true>), 2, kReadThreads, dyn, 0, P);
+    } else if (G == 8) PGS_LAUNCH((k_scan_fwd<8, false>), 2, kReadThreads, dyn, 0, P);
+    else if (G == 16) PGS_LAUNCH((k_scan_fwd<16, false>), 2, kReadThreads, dyn, 0, P);
+    else PGS_LAUNCH((k_scan_fwd<32, false>), 2, kReadThreads, dyn, 0, P);
     return err[0] ? (int32_t)err[0] : PGS_OK;
 }
 
