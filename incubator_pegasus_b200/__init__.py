@@ -564,7 +564,7 @@ class ScanBatch:
         self.part = part
         self.parts = parts
         if parts is not None:
-            self.handles = (vp * len(parts))(*[p.h for p in parts])
+            self.handles = (C.c_void_p * len(parts))(*[p.h for p in parts])
             self.req_part = np.ascontiguousarray(req_part, np.uint32)
             assert self.req_part.shape[0] == len(hashkeys)
         n = len(hashkeys)
