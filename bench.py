@@ -213,23 +213,37 @@ def sharded_read_leg(pgs, torch, dist, eng, rank, world, args, barrier, check_cp
     from incubator_pegasus_b200 import synth
     work = []  # (kind, partition, payload)
     my_gets = my_scans = 0
+    pins = []
+
+    def pinned_alloc(n, dt):  # request and answer buffers live in pinned memory, like a server's I/O buffers
+        t = torch.empty(max(1, int(n)) * np.dtype(dt).itemsize, dtype=torch.uint8).pin_memory()
+        pins.append(t)
+        return t.numpy().view(dt)
+
+    def pinned_copy(a):
+        out = pinned_alloc(a.size, a.dtype)
+        out[:] = a.reshape(-1)
+        return out
     # gets: all of this rank's partitions in ONE launch (pgs_get_batch_multi: the shape a batching front end gives the engine)
     plist = sorted(parts)
     slot_of = {p: i for i, p in enumerate(plist)}
     sel = np.nonzero(np.isin(g_owner, plist))[0]
     if sel.size:
         keys = synth.make_keys(gh[sel], gs[sel], HK, SK, table.seed)
-        flat = np.ascontiguousarray(keys.reshape(-1))
-        off = (np.arange(sel.size + 1, dtype=np.uint32) * np.uint32(keys.shape[1]))
-        kslot = np.array([slot_of[int(p)] for p in g_owner[sel]], np.uint32)
+        flat = pinned_copy(np.ascontiguousarray(keys.reshape(-1)))
+        off = pinned_copy(np.arange(sel.size + 1, dtype=np.uint32) * np.uint32(keys.shape[1]))
+        kslot = pinned_copy(np.array([slot_of[int(p)] for p in g_owner[sel]], np.uint32))
         cap = int(sel.size) * (VAL + 16)
-        work.append(("get", -1, (flat, off, kslot, np.zeros(cap, np.uint8), (pgs.GetResult * int(sel.size))(), g_owner[sel].copy())))
+        res_buf = pinned_alloc(int(sel.size) * C.sizeof(pgs.GetResult), np.uint8)
+        work.append(("get", -1, (flat, off, kslot, pinned_alloc(cap, np.uint8), (pgs.GetResult * int(sel.size)).from_buffer(res_buf),
+                                 g_owner[sel].copy())))
         my_gets = int(sel.size)
     # prefix scans: likewise one launch over all of this rank's partitions (pgs_range_scan_many_multi)
     sel = np.nonzero(np.isin(s_owner, plist))[0]
     if sel.size:
         sslot = np.array([slot_of[int(p)] for p in s_owner[sel]], np.uint32)
-        sb = pgs.ScanBatch(None, [table.hashkeys[int(h)].tobytes() for h in sh[sel]], 80, 24576, parts=[parts[q] for q in plist], req_part=sslot)
+        sb = pgs.ScanBatch(None, [table.hashkeys[int(h)].tobytes() for h in sh[sel]], 80, 24576, alloc=pinned_alloc,
+                           parts=[parts[q] for q in plist], req_part=sslot)
         work.append(("scan", -1, (sb, s_owner[sel].copy())))
         my_scans = int(sel.size)
     lock = threading.Lock()

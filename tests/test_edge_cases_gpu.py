@@ -277,3 +277,29 @@ def test_prefix_scans_over_several_partitions(pgs, engine):
     finally:
         for part in parts:
             part.close()
+
+
+def test_run_count_limits_are_reported(pgs, engine):
+    """more than 16 runs in one merge launch and more than 32 runs under one read are refused with NOT_SUPPORTED,
+    not answered wrongly; 16 / 32 themselves work"""
+    runs = synth.compaction_runs(k=33, n_per_run=200, seed=77)
+    part = engine.partition(app_id=6, pidx=0)
+    try:
+        ids = [part.upload_records(r) for r in runs]
+        key = runs[0].key(0)
+        flat = np.frombuffer(key, np.uint8).copy()
+        off = np.array([0, len(key)], np.uint32)
+        assert part.get_batch(flat, off, synth.NOW)[0] == pgs.NOT_SUPPORTED
+        sb = part.prefix_scan_batch([key[2:2 + int.from_bytes(key[:2], "big")]], max_records=50, arena_stride=32768)
+        assert sb.run(synth.NOW) == pgs.NOT_SUPPORTED
+        with pytest.raises(pgs.PegasusError) as e:
+            part.compact(ids[:17])
+        assert e.value.code == pgs.NOT_SUPPORTED
+        assert len(part.runs()) == 33  # nothing was consumed by the refused merge
+        res = part.compact(ids[:16])
+        assert res.out_records > 0 and len(part.runs()) == 33 - 16 + 1
+        st, r, arena, _ = part.get_batch(flat, off, synth.NOW)  # 18 runs: served
+        assert st == 0
+        assert sb.run(synth.NOW) == 0
+    finally:
+        part.close()
