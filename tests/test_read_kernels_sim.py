@@ -297,7 +297,7 @@ def test_sim_scan_multi_partition(pgs, sim, n_runs, lanes):
     """pgs_range_scan_many_multi's kernel shape: one launch, every request merges the runs of its own partition slot only"""
     rng = np.random.default_rng(300 + n_runs)
     hks = [b"h%d" % i for i in range(5)] + [b"", bytes([0xff, 0xff])]
-    runs, items = make_db(pgs, rng, n_runs, hks, 30)
+    runs, items = make_db(pgs, rng, n_runs, hks, 30, big=True)  # values of 600..1500 bytes among them: several copy rounds
     assert len(runs) == n_runs
     half = n_runs // 2
     vis_of = [visible(items[:half])[0], visible(items[half:])[0], []]
@@ -314,8 +314,6 @@ def test_sim_scan_multi_partition(pgs, sim, n_runs, lanes):
                   dict(base, sft=1, spat=b"01", count_only=1),
                   dict(base, key_mode=0, prefix=0, stop=raw_key(hk, b"\xff" * 8), return_expire_ts=1, max_count=11)):
             reqs += [q, q, q]   # the same request against each of the three slots
-    reqs.append(dict(start=b"", stop=b"\xff\xff\xff", start_inclusive=True, stop_inclusive=True, key_mode=0, prefix=0,
-                     max_count=100000, max_iter_count=100000, max_iter_size=0))
     got = do_scans(pgs, sim, args, reqs, lanes | 0x100)
     nonempty = 0
     for i, (q, g_) in enumerate(zip(reqs, got)):
