@@ -406,7 +406,12 @@ __global__ void __launch_bounds__(kReadThreads) k_scan_fwd(const __grid_constant
             if (visible) {
                 const uint8_t *key = (const uint8_t *)row;
                 bool valid = true; // Iterator::Valid(): inside the seek prefix, below iterate_upper_bound
-                if (pre_len) { valid = ulen >= pre_len; for (uint32_t i = 0; valid && i < pre_len; i++) valid = key[i] == ((const uint8_t *)rowSTART)[i]; }
+                if (pre_len) { // the key starts with the seek prefix: word by word (the rows are 4-byte aligned)
+                    valid = ulen >= pre_len;
+                    const uint32_t nw = pre_len >> 2;
+                    for (uint32_t w = 0; valid && w < nw; w++) valid = row[w] == rowSTART[w];
+                    if (valid && (pre_len & 3)) valid = ((row[nw] ^ rowSTART[nw]) & ((1u << (8 * (pre_len & 3))) - 1u)) == 0;
+                }
                 if (Q.has_upper && c2 >= 0) valid = false;
                 const bool guards = count < Q.max_count && iter_count < Q.max_iter_count && !(Q.max_iter_size > 0 && size >= Q.max_iter_size);
                 if (!guards || !valid) { // the while condition fails: the loop ends with the iterator standing here
