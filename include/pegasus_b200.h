@@ -310,6 +310,32 @@ PGS_API int32_t pgs_range_scan_many_multi(pgs_partition *const *parts, uint32_t 
  * host-side helpers of the product (no device work)
  * ========================================================================================== */
 
+/* pegasus_manual_compact_service.cpp:83-313, the rules only (no device work, no clock of its own): which manual-compaction
+ * rule of the env map ("k\0v\0..." pairs as pgs_rrdb_start takes them) fires at now_ms, and with which CompactRange options.
+ *   disabled .......... manual_compact.disabled == "true" (:122-145); nothing fires
+ *   max_concurrent .... manual_compact.max_concurrent_running_count, INT_MAX when absent or unparsable (:147-166); <= 0: nothing fires
+ *   once .............. manual_compact.once.trigger_time (unix seconds, buf2int64, > 0) newer than last_finish_ms / 1000 (:168-184)
+ *   periodic .......... manual_compact.periodic.trigger_time = "H:M,H:M,...": some valid time of day t (today_midnight_s + seconds)
+ *                       with last_finish_ms < t * 1000 < now_ms (:186-219); checked only when `once` did not fire
+ *   options ........... <rule prefix>target_level: -1 or 1..num_levels, else -1; <rule prefix>bottommost_level_compaction:
+ *                       "force" -> 1, anything else -> 0 (skip) (:231-272)
+ * today_midnight_s: unix seconds of the local day's 00:00:00 (the reference asks localtime; pass -1 to derive it from now_ms). */
+typedef struct {
+    int32_t rule;                 /* 0 = none, 1 = once, 2 = periodic */
+    int32_t disabled;
+    int32_t max_concurrent_running_count;
+    int32_t target_level;
+    int32_t bottommost_force;
+    int32_t reserved;
+} pgs_manual_compact_decision;
+PGS_API int32_t pgs_manual_compact_decide(const char *envs, uint32_t n_envs, uint64_t now_ms,
+                                          uint64_t last_finish_ms, int64_t today_midnight_s,
+                                          int32_t num_levels, pgs_manual_compact_decision *out);
+/* check_manual_compact_state (:273-289): may a compaction be enqueued now?  1 = yes and *enqueue_ms becomes now_ms; 0 = one is
+ * queued / running (*enqueue_ms != 0) or the last one finished less than min_interval_s ago (<= 0: no limit). */
+PGS_API int32_t pgs_manual_compact_state_check(uint64_t now_ms, uint64_t last_finish_ms,
+                                               int32_t min_interval_s, uint64_t *enqueue_ms);
+
 /* pegasus_key_schema.h:41-98,150-165 */
 PGS_API int32_t pgs_generate_key(const uint8_t *hk, uint32_t hk_len, const uint8_t *sk,
                                  uint32_t sk_len, uint8_t *out, uint32_t cap);

@@ -458,6 +458,30 @@ def get_batch_multi(parts, keys: np.ndarray, key_off: np.ndarray, key_part: np.n
     return st, results, arena, used.value
 
 
+class ManualCompactDecision(C.Structure):
+    _fields_ = [("rule", C.c_int32), ("disabled", C.c_int32), ("max_concurrent_running_count", C.c_int32),
+                ("target_level", C.c_int32), ("bottommost_force", C.c_int32), ("reserved", C.c_int32)]
+
+
+def manual_compact_decide(envs: dict, now_ms: int, last_finish_ms: int, today_midnight_s: int = -1, num_levels: int = 7):
+    """pgs_manual_compact_decide: which manual-compaction rule of the env map fires at now_ms (host logic only)"""
+    blob = b"".join(k.encode() + b"\0" + v.encode() + b"\0" for k, v in envs.items())
+    out = ManualCompactDecision()
+    f = lib().pgs_manual_compact_decide
+    f.argtypes = [C.c_char_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, C.POINTER(ManualCompactDecision)]
+    _check(f(blob if blob else None, len(envs), now_ms, last_finish_ms, today_midnight_s, num_levels, C.byref(out)), "manual_compact_decide")
+    return out
+
+
+def manual_compact_state_check(now_ms: int, last_finish_ms: int, min_interval_s: int, enqueue_ms: int):
+    """pgs_manual_compact_state_check -> (allowed, new enqueue_ms)"""
+    e = C.c_uint64(enqueue_ms)
+    f = lib().pgs_manual_compact_state_check
+    f.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_uint64)]
+    ok = f(now_ms, last_finish_ms, min_interval_s, C.byref(e))
+    return bool(ok), e.value
+
+
 def partition_index(hash_key: bytes, sort_key: bytes, partition_count: int) -> int:
     return int(lib().pgs_partition_index(hash_key, len(hash_key), sort_key, len(sort_key), partition_count))
 

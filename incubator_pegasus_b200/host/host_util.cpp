@@ -3,8 +3,15 @@
 //   * the sorted-run builder used by flush (RocksDB BlockBuilder + FlushBlockBySizePolicy)
 //   * raw block decode (egress)
 //   * `user_specified_compaction` JSON -> binary ops table (compaction_operation.cpp:162-186)
+//   * the manual-compaction rules (pegasus_manual_compact_service.cpp:83-313)
 #include <algorithm>
+#include <cerrno>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <map>
 #include <string>
 #include <string_view>
 #include <vector>
@@ -557,6 +564,99 @@ int64_t pgs_compaction_ops_parse(const char *json, uint32_t json_len, uint32_t d
     if ((uint64_t)n > cap) return -PGS_INCOMPLETE;
     memcpy(out, bin.data(), bin.size());
     return n;
+}
+
+// ---- manual-compaction rules -------------------------------------------------------------------------------------------------
+// dsn::buf2int32 / buf2int64 (utils/string_conv.h:35-62): the whole buffer is one strtoll(base 0) integer inside the type's range
+static bool whole_int(const std::string &str, long long lo, long long hi, long long &out)
+{
+    if (str.empty()) return false;
+    errno = 0;
+    char *p = nullptr;
+    const long long v = std::strtoll(str.c_str(), &p, 0);
+    if ((size_t)(p - str.c_str()) != str.size() || errno != 0 || v < lo || v > hi) return false;
+    out = v;
+    return true;
+}
+// utils/time_utils.h:118-129: "H:M" with 0 <= H <= 23, 0 <= M <= 59 (sscanf: trailing text is ignored) -> seconds of the day, or -1
+static int hh_mm_seconds(const std::string &s)
+{
+    int hour = 0, min = 0;
+    if (sscanf(s.c_str(), "%d:%d", &hour, &min) == 2 && hour >= 0 && hour <= 23 && min >= 0 && min <= 59) return 3600 * hour + 60 * min;
+    return -1;
+}
+
+int32_t pgs_manual_compact_decide(const char *envs, uint32_t n_envs, uint64_t now_ms, uint64_t last_finish_ms, int64_t today_midnight_s,
+                                  int32_t num_levels, pgs_manual_compact_decision *out)
+{
+    if (!out || (n_envs && !envs)) return PGS_INVALID_ARGUMENT;
+    std::map<std::string, std::string> m;
+    const char *p = envs;
+    for (uint32_t i = 0; i < n_envs; i++) {
+        std::string k(p);
+        p += k.size() + 1;
+        std::string v(p);
+        p += v.size() + 1;
+        m[k] = v;
+    }
+    memset(out, 0, sizeof *out);
+    out->target_level = -1;
+    auto f = m.find("manual_compact.disabled");
+    out->disabled = f != m.end() && f->second == "true";
+    out->max_concurrent_running_count = INT_MAX;
+    long long v = 0;
+    f = m.find("manual_compact.max_concurrent_running_count");
+    if (f != m.end() && whole_int(f->second, INT_MIN, INT_MAX, v)) out->max_concurrent_running_count = (int32_t)v;
+    if (out->disabled || out->max_concurrent_running_count <= 0) return PGS_OK;
+
+    std::string prefix;
+    f = m.find("manual_compact.once.trigger_time");
+    if (f != m.end() && whole_int(f->second, LLONG_MIN, LLONG_MAX, v) && v > 0 && (uint64_t)v > last_finish_ms / 1000) {
+        out->rule = 1;
+        prefix = "manual_compact.once.";
+    }
+    if (!out->rule) {
+        f = m.find("manual_compact.periodic.trigger_time");
+        if (f != m.end()) {
+            if (today_midnight_s < 0) { // the local day that holds now_ms
+                time_t t = (time_t)(now_ms / 1000);
+                struct tm tmv;
+                localtime_r(&t, &tmv);
+                tmv.tm_hour = tmv.tm_min = tmv.tm_sec = 0;
+                today_midnight_s = (int64_t)mktime(&tmv);
+            }
+            size_t b = 0;
+            const std::string &list = f->second;
+            while (b <= list.size() && !out->rule) {
+                size_t e = list.find(',', b);
+                if (e == std::string::npos) e = list.size();
+                const int sec = e > b ? hh_mm_seconds(list.substr(b, e - b)) : -1;
+                if (sec >= 0) {
+                    const uint64_t t_ms = (uint64_t)(today_midnight_s + sec) * 1000;
+                    if (last_finish_ms < t_ms && t_ms < now_ms) out->rule = 2;
+                }
+                b = e + 1;
+            }
+            if (out->rule) prefix = "manual_compact.periodic.";
+        }
+    }
+    if (!out->rule) return PGS_OK;
+    f = m.find(prefix + "target_level");
+    if (f != m.end() && whole_int(f->second, INT_MIN, INT_MAX, v) && (v == -1 || (v >= 1 && v <= num_levels))) out->target_level = (int32_t)v;
+    f = m.find(prefix + "bottommost_level_compaction");
+    out->bottommost_force = f != m.end() && f->second == "force";
+    return PGS_OK;
+}
+
+int32_t pgs_manual_compact_state_check(uint64_t now_ms, uint64_t last_finish_ms, int32_t min_interval_s, uint64_t *enqueue_ms)
+{
+    if (!enqueue_ms) return 0;
+    if (min_interval_s <= 0 || last_finish_ms == 0 || now_ms - last_finish_ms > (uint64_t)min_interval_s * 1000) {
+        if (*enqueue_ms != 0) return 0;
+        *enqueue_ms = now_ms;
+        return 1;
+    }
+    return 0;
 }
 
 } // extern "C"

@@ -663,28 +663,17 @@ int32_t pgs_rrdb_update_app_envs(pgs_server *h, const char *envs, uint32_t n_env
         if (fo == em.end()) s.ops_bin.clear();
         else { s.ops_bin.clear(); if (!fo->second.empty()) ops_parse(fo->second, s.data_version, s.ops_bin, nullptr); }
     }
-    // start_manual_compact_if_needed (pegasus_manual_compact_service.cpp:83-121): disabled flag, then the `once` rule:
-    // trigger_time (unix seconds) newer than the last finished manual compaction.  (`periodic` HH:MM rules need the
-    // wall clock of the host process and stay with the caller.)
-    std::map<std::string, std::string> m(kv.begin(), kv.end());
-    auto f = m.find("manual_compact.disabled");
-    s.manual_compact_disabled = f != m.end() && f->second == "true";
-    if (s.manual_compact_disabled) return PGS_OK;
-    f = m.find("manual_compact.once.trigger_time");
-    if (f == m.end()) return PGS_OK;
-    char *endp = nullptr;
-    long long trigger = strtoll(f->second.c_str(), &endp, 10);
-    if (f->second.empty() || *endp || trigger <= 0) return PGS_OK;
-    if ((uint64_t)trigger <= s.manual_compact_last_finish_ms / 1000) return PGS_OK; // check_once_compact :160-173
-    int32_t target_level = -1; // extract_manual_compact_opts :217-262
-    f = m.find("manual_compact.once.target_level");
-    if (f != m.end()) {
-        long tl = strtol(f->second.c_str(), &endp, 10);
-        if (!f->second.empty() && !*endp && (tl == -1 || (tl >= 1 && tl <= 6))) target_level = (int32_t)tl;
-    }
-    bool force = false; // default BottommostLevelCompaction::kSkip
-    f = m.find("manual_compact.once.bottommost_level_compaction");
-    if (f != m.end() && f->second == "force") force = true;
+    // start_manual_compact_if_needed (pegasus_manual_compact_service.cpp:83-121): the disabled flag, the running-count limit, then
+    // the `once` rule and, when it does not fire, the `periodic` one (times of the local day that holds `now`); the compaction
+    // runs inside this call, so check_manual_compact_state's "one is already queued" never applies.  Levels: 0..6.
+    pgs_manual_compact_decision dec;
+    const uint64_t now_ms = ((uint64_t)now + kEpochBegin) * 1000;
+    if (pgs_manual_compact_decide(envs, envs ? n_envs : 0, now_ms, s.manual_compact_last_finish_ms, -1, 6, &dec) != PGS_OK) return PGS_OK;
+    s.manual_compact_disabled = dec.disabled != 0;
+    if (dec.rule == 0) return PGS_OK;
+    if (dec.rule == 2 && now == 0) return PGS_OK; // a call without a clock (pgs_rrdb_start) cannot tell the time of day
+    const int32_t target_level = dec.target_level;
+    const bool force = dec.bottommost_force != 0;
     int32_t st = do_manual_compact(s, now, target_level, force, nullptr);
     if (st == PGS_OK) s.manual_compact_last_finish_ms = ((uint64_t)now + kEpochBegin) * 1000;
     return st;

@@ -10,7 +10,11 @@
 #include <algorithm>
 #include <cerrno>
 #include <climits>
+#include <cstdio>
+#include <ctime>
+#include <map>
 #include <random>
+#include <sstream>
 #include <unordered_map>
 
 namespace orc {
@@ -670,25 +674,45 @@ int32_t orc_rrdb_update_app_envs(orc_server *h, const char *envs, uint32_t n_env
         if (fo == em.end()) s.ops.clear();
         else s.ops = fo->second.empty() ? std::vector<Op>() : ops_from_json(fo->second, s.data_version);
     }
-    // pegasus_manual_compact_service.cpp:83-121,160-173,217-262: disabled flag, `once` rule, options
+    // pegasus_manual_compact_service.cpp:83-121 (order of the checks), :122-166 (disabled, running-count limit), :168-184 (`once`),
+    // :186-219 (`periodic`: a "H:M" of today's local day between the last finish and now), :231-272 (options of the rule that fired)
     std::map<std::string, std::string> m(kv.begin(), kv.end());
-    auto f = m.find("manual_compact.disabled");
-    if (f != m.end() && f->second == "true") return PGS_OK;
-    f = m.find("manual_compact.once.trigger_time");
-    if (f == m.end()) return PGS_OK;
-    char *endp = nullptr;
-    long long trigger = strtoll(f->second.c_str(), &endp, 10);
-    if (f->second.empty() || *endp || trigger <= 0) return PGS_OK;
-    if ((uint64_t)trigger <= s.manual_compact_last_finish_ms / 1000) return PGS_OK;
-    int target_level = -1;
-    f = m.find("manual_compact.once.target_level");
-    if (f != m.end()) {
-        long tl = strtol(f->second.c_str(), &endp, 10);
-        if (!f->second.empty() && !*endp && (tl == -1 || (tl >= 1 && tl <= 6))) target_level = (int)tl;
+    auto env = [&](const std::string &k) -> const std::string * { auto f = m.find(k); return f == m.end() ? nullptr : &f->second; };
+    auto as_int = [](const std::string *v, long long &out) { // dsn::buf2int*: one whole strtoll(base 0) number
+        if (!v || v->empty()) return false;
+        char *e = nullptr;
+        errno = 0;
+        out = strtoll(v->c_str(), &e, 0);
+        return *e == 0 && errno == 0;
+    };
+    if (const std::string *d = env("manual_compact.disabled"); d && *d == "true") return PGS_OK;
+    long long num = 0;
+    if (as_int(env("manual_compact.max_concurrent_running_count"), num) && num >= INT32_MIN && num <= INT32_MAX && num <= 0) return PGS_OK;
+    const uint64_t last_ms = s.manual_compact_last_finish_ms, now_ms = ((uint64_t)now + kEpochBegin) * 1000;
+    const char *rule = nullptr;
+    if (as_int(env("manual_compact.once.trigger_time"), num) && num > 0 && (uint64_t)num > last_ms / 1000) rule = "manual_compact.once.";
+    if (!rule && now != 0) {
+        if (const std::string *times = env("manual_compact.periodic.trigger_time")) {
+            time_t tt = (time_t)(now_ms / 1000);
+            struct tm day;
+            localtime_r(&tt, &day);
+            day.tm_hour = 0; day.tm_min = 0; day.tm_sec = 0;
+            const long long midnight = (long long)mktime(&day);
+            std::stringstream ss(*times);
+            std::string item;
+            while (std::getline(ss, item, ',')) {
+                int hh = 0, mm = 0;
+                if (sscanf(item.c_str(), "%d:%d", &hh, &mm) != 2 || hh < 0 || hh > 23 || mm < 0 || mm > 59) continue;
+                const uint64_t at_ms = (uint64_t)(midnight + hh * 3600 + mm * 60) * 1000;
+                if (last_ms < at_ms && at_ms < now_ms) { rule = "manual_compact.periodic."; break; }
+            }
+        }
     }
-    bool force = false;
-    f = m.find("manual_compact.once.bottommost_level_compaction");
-    if (f != m.end() && f->second == "force") force = true;
+    if (!rule) return PGS_OK;
+    int target_level = -1;
+    if (as_int(env(std::string(rule) + "target_level"), num) && (num == -1 || (num >= 1 && num <= 6))) target_level = (int)num;
+    const std::string *bl = env(std::string(rule) + "bottommost_level_compaction");
+    const bool force = bl && *bl == "force";
     s.flush_mem();
     if (!s.runs.empty() && (force || !(s.runs.size() == 1 && s.runs[0].level >= 1))) {
         int level = 1;

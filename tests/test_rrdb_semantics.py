@@ -143,3 +143,35 @@ def test_batched_writes_of_one_decree(make, kind):
     assert be.batched_writes([], now=NOW) == (0, []) and be.f("rrdb_last_committed_decree")(be.h) == d + 1
     assert be.batched_writes([("put", b"h", b"c", b"9"), ("multi_put", b"h", b"d", b"9")], now=NOW)[0] == 4
     assert be.get(b"h", b"c", now=NOW)["error"] == 1
+
+
+@pytest.mark.parametrize("kind", backends())
+def test_periodic_manual_compaction(make, kind):
+    """pegasus_manual_compact_service.cpp:186-219: a time of the local day between the last finished manual compaction and
+    now starts one; the same env afterwards does nothing until the next time of day passes; `once` is looked at first"""
+    import time
+    unix = NOW + 1451606400
+    lt = time.localtime(unix)
+    noon = NOW - (lt.tm_hour * 3600 + lt.tm_min * 60 + lt.tm_sec) + 12 * 3600  # 12:00 of NOW's local day, Pegasus seconds
+    be = make(kind)
+    be.put(b"h", b"keep", b"1", now=noon)                       # expire_ts 0: default_ttl is not set yet
+    be.flush(noon)
+    be.put(b"h", b"keep2", b"2", now=noon)
+    per = "manual_compact.periodic.trigger_time"
+    be.update_envs({"default_ttl": "9000", per: "13:00,25:00,xx"}, now=noon)           # 13:00 has not come, the rest is not a time
+    assert be.ttl(b"h", b"keep", now=noon)["ttl"] == -1
+    be.update_envs({"default_ttl": "9000", per: "11:00,13:00", "manual_compact.disabled": "true"}, now=noon)
+    assert be.ttl(b"h", b"keep", now=noon)["ttl"] == -1        # disabled wins
+    be.update_envs({"default_ttl": "9000", per: "11:00,13:00", "manual_compact.max_concurrent_running_count": "0"}, now=noon)
+    assert be.ttl(b"h", b"keep", now=noon)["ttl"] == -1        # no compaction may run
+    be.update_envs({"default_ttl": "9000", per: "11:00,13:00"}, now=noon)              # 11:00 passed since the last finish (never)
+    assert be.ttl(b"h", b"keep", now=noon)["ttl"] == 9000      # the filter's default-TTL rewrite happened
+    assert be.ttl(b"h", b"keep2", now=noon)["ttl"] == 9000     # the memtable was flushed into it
+    be.update_envs({"default_ttl": "0", per: "11:00,13:00"}, now=noon + 60)
+    be.put(b"h", b"late", b"3", now=noon + 60)                  # expire_ts 0 again
+    be.update_envs({"default_ttl": "100", per: "11:00,13:00"}, now=noon + 120)         # finished at 12:00: 11:00 no longer fires
+    assert be.ttl(b"h", b"late", now=noon + 120)["ttl"] == -1
+    be.update_envs({"default_ttl": "100", per: "11:00,13:00"}, now=noon + 3600 + 30)   # 13:00 passed
+    assert be.ttl(b"h", b"late", now=noon + 3600 + 30)["ttl"] == 100
+    assert be.ttl(b"h", b"keep", now=noon + 3600 + 30)["ttl"] == 9000- 3630
+    assert be.get(b"h", b"keep2", now=noon + 3600 + 30)["error"] == 0
