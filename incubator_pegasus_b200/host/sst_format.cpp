@@ -379,7 +379,7 @@ int32_t sst_encode(const uint8_t *data, const uint64_t *blk_off, const uint32_t 
 // `inflated` keeps the bytes of a block that was stored compressed (out points into it then)
 static int32_t read_block(const uint8_t *sst, uint64_t size, Handle h, std::string_view &out, std::string &inflated)
 {
-    if (h.off > size || h.size + 5 > size - h.off) return PGS_CORRUPTION;
+    if (h.off > size || h.size > size - h.off || size - h.off - h.size < 5) return PGS_CORRUPTION; // block + 5-byte trailer inside the file
     const uint8_t *b = sst + h.off;
     const uint8_t type = b[h.size];
     if (type != kNoCompression && type != kLZ4Compression) return PGS_NOT_SUPPORTED; // snappy / zstd / ...: later slices
