@@ -86,7 +86,7 @@ bool build_index(HostRun &r)
         r.info.max_block_records = std::max(r.info.max_block_records, n);
         r.info.n_records += n;
     }
-    r.ikeys.resize(r.ikeys.size() + 64);
+    r.ikeys.resize(r.ikeys.size() + 16); // the product's slack (engine.cu)
     r.rec_off.push_back(0);
     // the Bloom filter k_index_walk builds at upload: whole keys + hash-key prefixes
     std::vector<std::string> pres;
@@ -143,7 +143,7 @@ int32_t sim_compact(uint32_t k, const uint8_t **data, const uint64_t *data_bytes
     for (uint32_t i = 0; i < k; i++) {
         HostRun &r = runs[i];
         r.data.assign(data[i], data[i] + data_bytes[i]);
-        r.data.resize(r.data.size() + 512, 0);
+        r.data.resize(r.data.size() + 256, 0); // the product's slack after a run's blocks (engine.cu, compact.cu)
         r.blk_off.assign(blk_off[i], blk_off[i] + n_blocks[i]);
         r.blk_size.assign(blk_size[i], blk_size[i] + n_blocks[i]);
         uint64_t end = n_blocks[i] ? r.blk_off.back() + r.blk_size.back() : 0;
@@ -304,7 +304,7 @@ static bool load_runs(uint32_t k, const uint8_t **data, const uint64_t *data_byt
     for (uint32_t i = 0; i < k; i++) {
         HostRun &r = runs[i];
         r.data.assign(data[i], data[i] + data_bytes[i]);
-        r.data.resize(r.data.size() + 512, 0);
+        r.data.resize(r.data.size() + 256, 0); // the product's slack after a run's blocks (engine.cu, compact.cu)
         r.blk_off.assign(blk_off[i], blk_off[i] + n_blocks[i]);
         r.blk_size.assign(blk_size[i], blk_size[i] + n_blocks[i]);
         uint64_t end = n_blocks[i] ? r.blk_off.back() + r.blk_size.back() : 0;
@@ -327,7 +327,7 @@ int32_t sim_get(uint32_t k, const uint8_t **data, const uint64_t *data_bytes, co
     if (!load_runs(k, data, data_bytes, blk_off, blk_size, n_blocks, runs, P.rr, mk)) return PGS_CORRUPTION;
     if (!(use_bloom & 1)) for (uint32_t i = 0; i < k; i++) { P.rr.runs[i].bloom = nullptr; P.rr.runs[i].bloom_lines = 0; }
     std::vector<uint8_t> kcopy(keys, keys + key_off[n]);
-    kcopy.resize(kcopy.size() + 64);
+    kcopy.resize(kcopy.size() + 16); // as lookup.cu allocates the key buffer
     unsigned long long cur[4] = {0, 0, 0, 0};
     uint32_t err[4] = {0, 0, 0, 0};
     P.keys = kcopy.data(); P.key_off = key_off; P.n = n; P.now = now; P.data_version = 1;
@@ -379,7 +379,7 @@ int32_t sim_scan(uint32_t k, const uint8_t **data, const uint64_t *data_bytes, c
         need_crc |= q.validate_hash != 0;
         if (q.reverse) return PGS_NOT_SUPPORTED;
     }
-    blob.append(64, '\0');
+    blob.append(16, '\0'); // as lookup.cu
     uint32_t err[16] = {0};
     P.reqs = dev.data(); P.blob = (const uint8_t *)blob.data(); P.n = n; P.now = now; P.data_version = 1;
     P.results = results; P.kvs = kvs; P.kv_stride = kv_stride; P.arena = arena; P.arena_stride = arena_stride;
