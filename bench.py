@@ -22,7 +22,7 @@ collective on the data path (hash partitions are independent).
   reads    = get / prefix-scan legs on the resident partition (device and end-to-end numbers use the same
              statistic: the mean over the repetitions).
   sharded_reads = BASELINE.json configs[2]: a 256-partition table, partition p served by rank p % N, YCSB-C
-             zipfian get + multi_get(hash_key) requests routed by crc64 like a client; 8 host threads per rank.
+             zipfian get + multi_get(hash_key) requests routed by crc64 like a client; per rank two multi-partition launches.
   sweep    = BASELINE.json configs[3] (N=1): manual-compact style L0..L4 merges with 30 % expired records at run
              sizes 8..256 MB, bottommost forced, roofline fraction per size.
   ycsb_a   = BASELINE.json configs[4] at small scale (N=1): 50/50 put+get through the rrdb surface.
