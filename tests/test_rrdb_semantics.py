@@ -143,6 +143,14 @@ def test_batched_writes_of_one_decree(make, kind):
     assert be.batched_writes([], now=NOW) == (0, []) and be.f("rrdb_last_committed_decree")(be.h) == d + 1
     assert be.batched_writes([("put", b"h", b"c", b"9"), ("multi_put", b"h", b"d", b"9")], now=NOW)[0] == 4
     assert be.get(b"h", b"c", now=NOW)["error"] == 1
+    # pegasus_write_service_test.cpp:170-207 (test_batched_writes): 100 puts, then removes of the same 100 keys, one decree, every
+    # response kOk; what the batch leaves behind is nothing
+    ops = [("put", b"hash_key", b"sort_key_%d" % i, b"value_%d" % i) for i in range(100)]
+    ops += [("remove", b"hash_key", b"sort_key_%d" % i) for i in range(100)]
+    rc, errs = be.batched_writes(ops, now=NOW, ts_us=1000)
+    assert rc == 0 and errs == [0] * 200
+    assert be.multi_get(b"hash_key", now=NOW)["kvs"] == []
+    assert be.sortkey_count(b"hash_key", now=NOW)["count"] == 0
 
 
 @pytest.mark.parametrize("kind", backends())
