@@ -625,6 +625,27 @@ PGS_API int32_t pgs_lz4_block(int32_t decompress, const uint8_t *in, uint64_t n,
                               uint64_t *out_size);
 PGS_API uint32_t pgs_crc32c(const uint8_t *data, uint64_t len, uint32_t init);
 
+/* ============================================================================================
+ * 9. request-batching front end for point reads, first slice
+ * ========================================================================================== */
+/* The read handlers of the reference run one blocking call per RPC on a thread pool (THREAD_POOL_LOCAL_APP,
+ * src/server/config.ini:140-150; on_get pegasus_server_impl.cpp:418-494).  A batcher lets the calls of many threads over the
+ * replicas `parts` (one engine) share launches: the first caller of a window waits up to max_wait_us for company (or until
+ * max_batch requests are queued; 0 = 4096), then everything queued goes through ONE pgs_get_batch_multi launch; callers that
+ * arrive meanwhile form the next window.  max_wait_us = 0: no waiting, a lone caller launches at once.
+ * pgs_batcher_get blocks until the request's window is done: *result as pgs_get_batch fills it (status PGS_OK / PGS_NOT_FOUND
+ * with `expired`, expire_ts, value_len); the value is copied to `value`; a value longer than value_cap gives status
+ * PGS_INCOMPLETE with value_len = the need.  The return value is the launch's own status (PGS_OK unless the engine failed).
+ * Close only when no call is in flight.  Answers come from the device only (the memtable-aware path is pgs_rrdb_get_many). */
+typedef struct pgs_batcher pgs_batcher;
+PGS_API int32_t pgs_batcher_open(pgs_partition *const *parts, uint32_t n_parts, uint32_t max_batch,
+                                 uint32_t max_wait_us, pgs_batcher **out);
+PGS_API void pgs_batcher_close(pgs_batcher *b);
+PGS_API int32_t pgs_batcher_get(pgs_batcher *b, uint32_t part_slot, const uint8_t *key, uint32_t key_len,
+                                uint32_t now, uint8_t *value, uint32_t value_cap, pgs_get_result *result);
+/* requests served and launches made so far */
+PGS_API void pgs_batcher_stats(pgs_batcher *b, uint64_t *requests, uint64_t *launches);
+
 #ifdef __cplusplus
 }
 #endif

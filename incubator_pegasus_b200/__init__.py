@@ -458,6 +458,40 @@ def get_batch_multi(parts, keys: np.ndarray, key_off: np.ndarray, key_part: np.n
     return st, results, arena, used.value
 
 
+class Batcher:
+    """pgs_batcher_*: blocking point reads of many host threads share pgs_get_batch_multi launches"""
+
+    def __init__(self, parts, max_batch: int = 0, max_wait_us: int = 200):
+        L = lib()
+        L.pgs_batcher_open.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.pgs_batcher_close.argtypes = [C.c_void_p]
+        L.pgs_batcher_close.restype = None
+        L.pgs_batcher_get.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(GetResult)]
+        L.pgs_batcher_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.pgs_batcher_stats.restype = None
+        self._parts = list(parts)
+        handles = (C.c_void_p * len(self._parts))(*[p.h for p in self._parts])
+        self.h = C.c_void_p()
+        _check(L.pgs_batcher_open(handles, len(self._parts), max_batch, max_wait_us, C.byref(self.h)), "batcher_open")
+
+    def get(self, slot: int, key: bytes, now: int, cap: int = 4096):
+        """-> (launch status, GetResult, value bytes or None)"""
+        buf = C.create_string_buffer(max(1, cap))
+        r = GetResult()
+        st = lib().pgs_batcher_get(self.h, slot, key, len(key), now, buf, cap, C.byref(r))
+        return st, r, (buf.raw[:r.value_len] if st == 0 and r.status == OK else None)
+
+    def stats(self):
+        rq, ln = C.c_uint64(), C.c_uint64()
+        lib().pgs_batcher_stats(self.h, C.byref(rq), C.byref(ln))
+        return rq.value, ln.value
+
+    def close(self):
+        if self.h:
+            lib().pgs_batcher_close(self.h)
+            self.h = None
+
+
 class ManualCompactDecision(C.Structure):
     _fields_ = [("rule", C.c_int32), ("disabled", C.c_int32), ("max_concurrent_running_count", C.c_int32),
                 ("target_level", C.c_int32), ("bottommost_force", C.c_int32), ("reserved", C.c_int32)]
