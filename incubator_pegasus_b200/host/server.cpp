@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "../csrc/engine.h"
+#include "checkpoint_dir.h"
 #include "host_internal.h"
 
 namespace pgs {
@@ -968,25 +969,7 @@ int32_t pgs_rrdb_manual_compact(pgs_server *h, uint32_t now, pgs_compact_result 
     return st;
 }
 // ---- checkpoints (pegasus_server_impl.cpp:1951-2336: sync_checkpoint, get_checkpoint, storage_apply_checkpoint) ---------------
-static bool write_file(const std::string &path, const void *p, size_t n)
-{
-    FILE *f = fopen(path.c_str(), "wb");
-    if (!f) return false;
-    const bool ok = fwrite(p, 1, n, f) == n;
-    return fclose(f) == 0 && ok;
-}
-static bool read_file(const std::string &path, std::vector<uint8_t> &out)
-{
-    FILE *f = fopen(path.c_str(), "rb");
-    if (!f) return false;
-    fseek(f, 0, SEEK_END);
-    const long n = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    out.resize(n > 0 ? (size_t)n : 0);
-    const bool ok = n >= 0 && fread(out.data(), 1, out.size(), f) == out.size();
-    fclose(f);
-    return ok;
-}
+// The directory protocol (temporary name, MANIFEST last, rename) lives in checkpoint_dir.h.
 int32_t pgs_rrdb_sync_checkpoint(pgs_server *h, const char *dir, uint32_t now, int64_t *decree_out)
 {
     (void)now;
@@ -997,33 +980,29 @@ int32_t pgs_rrdb_sync_checkpoint(pgs_server *h, const char *dir, uint32_t now, i
     if (st != PGS_OK) return st;
     const int64_t decree = s.last_flushed_decree;
     if (decree_out) *decree_out = decree;
-    const std::string cdir = std::string(dir) + "/checkpoint." + std::to_string(decree);
-    if (mkdir(dir, 0755) != 0 && errno != EEXIST) { set_error("checkpoint: cannot create %s", dir); return PGS_IO_ERROR; }
-    if (mkdir(cdir.c_str(), 0755) != 0) {
-        if (errno == EEXIST) { s.last_durable_decree = std::max(s.last_durable_decree, decree); return PGS_OK; } // already there (ERR_WRONG_TIMING upstream)
-        set_error("checkpoint: cannot create %s", cdir.c_str());
-        return PGS_IO_ERROR;
-    }
+    CheckpointWriter w;
+    const int started = w.begin(dir, decree);
+    if (started < 0) { set_error("%s", w.error().c_str()); return PGS_IO_ERROR; }
+    if (started == 1) { s.last_durable_decree = std::max(s.last_durable_decree, decree); return PGS_OK; } // already there (ERR_WRONG_TIMING upstream)
     auto rs = s.runs(); // level ascending, newest first inside a level
-    std::string manifest = "pegasus_b200_checkpoint 1\n";
-    manifest += "app_id " + std::to_string(s.app_id) + "\npidx " + std::to_string(s.pidx) + "\ndata_version " + std::to_string(s.data_version) + "\n";
-    manifest += "last_flushed_decree " + std::to_string(decree) + "\nlast_seq " + std::to_string(s.last_seq) + "\nruns " + std::to_string(rs.size()) + "\n";
+    CheckpointManifest m;
+    m.app_id = s.app_id; m.pidx = s.pidx; m.data_version = s.data_version; m.decree = decree; m.last_seq = (long long)s.last_seq;
     std::vector<uint8_t> img;
     uint32_t fileno = 0;
     for (size_t i = rs.size(); i-- > 0;) { // oldest first: re-ingesting in this order rebuilds the same recency order
         const uint32_t comp = rs[i]->level >= 2 ? 4u : 0u; // parse_compression_types default "lz4": none for L0/L1 (pegasus_server_impl.cpp:3040-3056)
         uint64_t need = 0;
         st = pgs_sst_export_ex(s.part, rs[i]->id, comp, nullptr, 0, &need);
-        if (st != PGS_INCOMPLETE && st != PGS_OK) return st;
+        if (st != PGS_INCOMPLETE && st != PGS_OK) return st; // the writer's destructor removes the temporary directory
         img.resize(need);
         st = pgs_sst_export_ex(s.part, rs[i]->id, comp, img.data(), img.size(), &need);
         if (st != PGS_OK) return st;
         char name[32];
         snprintf(name, sizeof name, "%06u.sst", ++fileno);
-        if (!write_file(cdir + "/" + name, img.data(), need)) { set_error("checkpoint: cannot write %s/%s", cdir.c_str(), name); return PGS_IO_ERROR; }
-        manifest += std::to_string(rs[i]->level) + " " + name + " " + std::to_string(need) + "\n";
+        if (!w.add_file(name, img.data(), need)) { set_error("%s", w.error().c_str()); return PGS_IO_ERROR; }
+        m.files.push_back({rs[i]->level, name, (long long)need});
     }
-    if (!write_file(cdir + "/MANIFEST", manifest.data(), manifest.size())) { set_error("checkpoint: cannot write the manifest"); return PGS_IO_ERROR; }
+    if (!w.commit(m.str())) { set_error("%s", w.error().c_str()); return PGS_IO_ERROR; }
     s.last_durable_decree = std::max(s.last_durable_decree, decree);
     return PGS_OK;
 }
@@ -1032,39 +1011,30 @@ int32_t pgs_rrdb_apply_checkpoint(pgs_server *h, const char *cdir)
 {
     if (!h || !cdir) return PGS_INVALID_ARGUMENT;
     std::vector<uint8_t> mf;
-    if (!read_file(std::string(cdir) + "/MANIFEST", mf)) { set_error("checkpoint: no MANIFEST in %s", cdir); return PGS_NOT_FOUND; }
-    std::istringstream in(std::string(mf.begin(), mf.end()));
-    std::string word;
-    int version = 0;
-    long long app = 0, pidx = 0, dv = -1, decree = -1, seq = 0, nruns = -1;
-    in >> word >> version;
-    if (word != "pegasus_b200_checkpoint" || version != 1) return PGS_CORRUPTION;
-    std::string k;
-    in >> k >> app >> k >> pidx >> k >> dv >> k >> decree >> k >> seq >> k >> nruns;
-    if (!in || nruns < 0 || decree < 0) return PGS_CORRUPTION;
+    if (!ckpt_read_file(std::string(cdir) + "/MANIFEST", mf)) { set_error("checkpoint: no MANIFEST in %s", cdir); return PGS_NOT_FOUND; }
+    CheckpointManifest m;
+    if (!m.parse(std::string(mf.begin(), mf.end()))) { set_error("checkpoint: damaged MANIFEST in %s", cdir); return PGS_CORRUPTION; }
     WLOCKED(h);
     Server &s = h->s;
-    if (dv != (long long)s.data_version) { set_error("checkpoint: data version %lld, replica has %u", dv, s.data_version); return PGS_NOT_SUPPORTED; }
-    struct Item { int level; std::string file; std::vector<uint8_t> bytes; };
-    std::vector<Item> items((size_t)nruns);
-    for (auto &it : items) {
-        long long bytes = 0;
-        in >> it.level >> it.file >> bytes;
-        if (!in || it.level < 0 || it.file.find('/') != std::string::npos) return PGS_CORRUPTION;
-        if (!read_file(std::string(cdir) + "/" + it.file, it.bytes) || (long long)it.bytes.size() != bytes) return PGS_CORRUPTION;
-    }
+    if (m.data_version != (long long)s.data_version) { set_error("checkpoint: data version %lld, replica has %u", m.data_version, s.data_version); return PGS_NOT_SUPPORTED; }
+    std::vector<std::vector<uint8_t>> images(m.files.size());
+    for (size_t i = 0; i < m.files.size(); i++)
+        if (!ckpt_read_file(std::string(cdir) + "/" + m.files[i].name, images[i]) || (long long)images[i].size() != m.files[i].bytes) {
+            set_error("checkpoint: %s/%s is missing or has the wrong size", cdir, m.files[i].name.c_str());
+            return PGS_CORRUPTION;
+        }
     // from here on the old state is gone (storage_apply_checkpoint: the learner's data is replaced)
     for (auto &r : s.runs()) pgs_run_drop(s.part, r->id);
     s.mem.clear();
     s.mem_bytes = 0;
     { std::lock_guard<std::mutex> g(s.ctx_mu); s.ctx.clear(); }
-    for (auto &it : items) {
+    for (size_t i = 0; i < m.files.size(); i++) {
         uint64_t rid = 0;
-        const int32_t st = pgs_sst_ingest(s.part, it.level, it.bytes.data(), it.bytes.size(), &rid);
+        const int32_t st = pgs_sst_ingest(s.part, m.files[i].level, images[i].data(), images[i].size(), &rid);
         if (st != PGS_OK) return st;
     }
-    s.last_seq = (uint64_t)seq;
-    s.last_committed_decree = s.last_flushed_decree = s.last_durable_decree = decree;
+    s.last_seq = (uint64_t)m.last_seq;
+    s.last_committed_decree = s.last_flushed_decree = s.last_durable_decree = m.decree;
     return PGS_OK;
 }
 int64_t pgs_rrdb_last_flushed_decree(pgs_server *h) { RLOCKED(h); return h->s.last_flushed_decree; }
