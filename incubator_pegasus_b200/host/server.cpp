@@ -1023,6 +1023,12 @@ int32_t pgs_rrdb_apply_checkpoint(pgs_server *h, const char *cdir)
             set_error("checkpoint: %s/%s is missing or has the wrong size", cdir, m.files[i].name.c_str());
             return PGS_CORRUPTION;
         }
+    for (size_t i = 0; i < m.files.size(); i++) { // every image must decode (checksums, block handles) before anything is given up
+        uint64_t nbytes = 0;
+        uint32_t nblocks = 0;
+        const int32_t st = pgs_sst_decode(images[i].data(), images[i].size(), nullptr, 0, nullptr, nullptr, 0, &nbytes, &nblocks);
+        if (st != PGS_OK && st != PGS_INCOMPLETE) { set_error("checkpoint: %s/%s does not decode", cdir, m.files[i].name.c_str()); return st; }
+    }
     // from here on the old state is gone (storage_apply_checkpoint: the learner's data is replaced)
     for (auto &r : s.runs()) pgs_run_drop(s.part, r->id);
     s.mem.clear();

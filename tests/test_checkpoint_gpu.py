@@ -96,6 +96,18 @@ def test_checkpoint_and_apply(pgs, engine, tmp_path):
         (bad / "MANIFEST").write_text("something else 1\n")
         assert g2.f("rrdb_apply_checkpoint")(g2.h, str(bad).encode()) == pgs.CORRUPTION
         same_reads(g2, o)  # a refused checkpoint left the replica as it was
+        import shutil
+        torn = tmp_path / "torn"
+        shutil.copytree(cdir, torn)
+        victim = torn / small
+        raw = bytearray(victim.read_bytes())
+        raw[len(raw) // 2] ^= 0x40                      # one flipped bit inside a block: its checksum no longer matches
+        victim.write_bytes(bytes(raw))
+        assert g2.f("rrdb_apply_checkpoint")(g2.h, str(torn).encode()) == pgs.CORRUPTION
+        same_reads(g2, o)  # every image is decoded before the old state is given up
+        (torn / small).write_bytes(bytes(raw[:-7]))     # wrong size
+        assert g2.f("rrdb_apply_checkpoint")(g2.h, str(torn).encode()) == pgs.CORRUPTION
+        same_reads(g2, o)
     finally:
         for b in (g, o, g2):
             b.close()
