@@ -101,7 +101,7 @@ def test_checkpoint_and_apply(pgs, engine, tmp_path):
         shutil.copytree(cdir, torn)
         victim = torn / small
         raw = bytearray(victim.read_bytes())
-        raw[len(raw) // 2] ^= 0x40                      # one flipped bit inside a block: its checksum no longer matches
+        raw[1] ^= 0x40                                  # one flipped bit inside the first data block: its checksum no longer matches
         victim.write_bytes(bytes(raw))
         assert g2.f("rrdb_apply_checkpoint")(g2.h, str(torn).encode()) == pgs.CORRUPTION
         same_reads(g2, o)  # every image is decoded before the old state is given up
