@@ -56,3 +56,40 @@ def test_product_does_not_link_the_oracle(pgs):
     assert "oracle" not in out
     syms = subprocess.run(["nm", "-D", "--defined-only", pgs.LIB_PATH], capture_output=True, text=True).stdout
     assert " orc_" not in syms
+
+
+def test_header_is_plain_c_and_a_c_program_links(pgs, tmp_path):
+    """the drop-in boundary is a C ABI: include/pegasus_b200.h compiles as strict C99 (no C++, no torch types) and a C program
+    that uses nothing but the header links against the library and runs its host-side entry points"""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc")
+    assert cc
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "pegasus_b200.h"
+int main(void)
+{
+    unsigned char key[64];
+    const unsigned char hk[] = "hash", sk[] = "sort";
+    int n = pgs_generate_key(hk, 4, sk, 4, key, sizeof key);
+    if (n != 10 || key[0] != 0 || key[1] != 4 || memcmp(key + 2, "hashsort", 8)) return 1;
+    if (pgs_partition_index(hk, 4, sk, 4, 8) >= 8) return 2;
+    pgs_manual_compact_decision d;
+    if (pgs_manual_compact_decide("manual_compact.disabled\0true\0", 1, 1000, 0, 0, 7, &d) != PGS_OK || !d.disabled) return 3;
+    pgs_engine *e = NULL;
+    if (pgs_engine_open(NULL, &e) == PGS_OK) pgs_engine_close(e); /* a GPU box: fine; here: it must fail, not fall back */
+    printf("%d\n", (int)sizeof(pgs_get_result));
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(pgs.LIB_PATH)
+    subprocess.check_call([cc, "-std=c99", "-pedantic-errors", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe),
+                           "-L", libdir, "-lpegasus_b200", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, (out.returncode, out.stderr)
+    assert int(out.stdout.strip()) == C.sizeof(pgs.GetResult)
