@@ -331,6 +331,11 @@ typedef struct {
 PGS_API int32_t pgs_manual_compact_decide(const char *envs, uint32_t n_envs, uint64_t now_ms,
                                           uint64_t last_finish_ms, int64_t today_midnight_s,
                                           int32_t num_levels, pgs_manual_compact_decision *out);
+/* parse_compression_types (pegasus_server_impl.cpp:3019-3060), the `rocksdb_compression_type` setting: "none|snappy|lz4|zstd"
+ * compresses levels >= 2 with that type; "per_level:t0,t1,..." names every level, the last type repeats.  per_level[i] gets
+ * RocksDB's CompressionType of level i (0 none, 1 snappy, 4 lz4, 7 zstd).  PGS_INVALID_ARGUMENT (and per_level untouched)
+ * for anything else.  The SST writer of this library produces types 0 and 4. */
+PGS_API int32_t pgs_parse_compression_types(const char *config, uint32_t num_levels, uint8_t *per_level);
 /* check_manual_compact_state (:273-289): may a compaction be enqueued now?  1 = yes and *enqueue_ms becomes now_ms; 0 = one is
  * queued / running (*enqueue_ms != 0) or the last one finished less than min_interval_s ago (<= 0: no limit). */
 PGS_API int32_t pgs_manual_compact_state_check(uint64_t now_ms, uint64_t last_finish_ms,

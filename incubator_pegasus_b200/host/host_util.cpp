@@ -648,6 +648,46 @@ int32_t pgs_manual_compact_decide(const char *envs, uint32_t n_envs, uint64_t no
     return PGS_OK;
 }
 
+// compression_str_to_type (pegasus_server_impl.cpp:3062-3080): exact names only
+static bool compression_of(const std::string &s, uint8_t &t)
+{
+    if (s == "none") t = 0;
+    else if (s == "snappy") t = 1;
+    else if (s == "lz4") t = 4;
+    else if (s == "zstd") t = 7;
+    else return false;
+    return true;
+}
+int32_t pgs_parse_compression_types(const char *config, uint32_t num_levels, uint8_t *per_level)
+{
+    if (!config || !per_level || num_levels == 0 || num_levels > 64) return PGS_INVALID_ARGUMENT;
+    static const std::string header = "per_level:";
+    const std::string cfg(config);
+    std::vector<uint8_t> tmp(num_levels, 0);
+    if (cfg.find(header) != std::string::npos) { // one type per level; split_args drops empty items, the last type repeats
+        std::vector<std::string> types;
+        const std::string list = cfg.size() >= header.size() ? cfg.substr(header.size()) : std::string();
+        size_t b = 0;
+        while (b <= list.size()) {
+            size_t e = list.find(',', b);
+            if (e == std::string::npos) e = list.size();
+            if (e > b) types.push_back(list.substr(b, e - b));
+            b = e + 1;
+        }
+        uint8_t last = 0;
+        for (uint32_t i = 0; i < num_levels; i++) {
+            if (i < types.size() && !compression_of(types[i], last)) return PGS_INVALID_ARGUMENT;
+            tmp[i] = last;
+        }
+    } else { // one type for the levels >= 2 (ColumnFamilyOptions::OptimizeLevelStyleCompaction)
+        uint8_t t = 0;
+        if (!compression_of(cfg, t)) return PGS_INVALID_ARGUMENT;
+        for (uint32_t i = 2; i < num_levels; i++) tmp[i] = t;
+    }
+    memcpy(per_level, tmp.data(), num_levels);
+    return PGS_OK;
+}
+
 int32_t pgs_manual_compact_state_check(uint64_t now_ms, uint64_t last_finish_ms, int32_t min_interval_s, uint64_t *enqueue_ms)
 {
     if (!enqueue_ms) return 0;

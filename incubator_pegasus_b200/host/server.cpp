@@ -989,8 +989,10 @@ int32_t pgs_rrdb_sync_checkpoint(pgs_server *h, const char *dir, uint32_t now, i
     m.app_id = s.app_id; m.pidx = s.pidx; m.data_version = s.data_version; m.decree = decree; m.last_seq = (long long)s.last_seq;
     std::vector<uint8_t> img;
     uint32_t fileno = 0;
+    uint8_t per_level[7]; // rocksdb_compression_type = "lz4" (the reference's default): none for L0 / L1, LZ4 below
+    if (pgs_parse_compression_types("lz4", 7, per_level) != PGS_OK) return PGS_INVALID_ARGUMENT;
     for (size_t i = rs.size(); i-- > 0;) { // oldest first: re-ingesting in this order rebuilds the same recency order
-        const uint32_t comp = rs[i]->level >= 2 ? 4u : 0u; // parse_compression_types default "lz4": none for L0/L1 (pegasus_server_impl.cpp:3040-3056)
+        const uint32_t comp = per_level[std::min(std::max(rs[i]->level, 0), 6)];
         uint64_t need = 0;
         st = pgs_sst_export_ex(s.part, rs[i]->id, comp, nullptr, 0, &need);
         if (st != PGS_INCOMPLETE && st != PGS_OK) return st; // the writer's destructor removes the temporary directory

@@ -1,5 +1,6 @@
 """The manual-compaction rules of the product's host library (pgs_manual_compact_decide / _state_check) against the cases the
-reference's own test holds (src/server/test/manual_compact_service_test.cpp:120-330).  No device work."""
+reference's own test holds (src/server/test/manual_compact_service_test.cpp:120-330), and the compression setting
+(pgs_parse_compression_types) against src/server/test/pegasus_compression_options_test.cpp:115-155.  No device work."""
 import incubator_pegasus_b200 as pgs
 
 COMPACTED_TS = 1500000000  # manual_compact_service_test.cpp:45
@@ -120,3 +121,27 @@ def test_check_manual_compact_state_1h_interval():  # :317-343
         ok, enq = pgs.manual_compact_state_check((first + past) * 1000, last, 3600, 0)
         assert ok == want, past
     assert not pgs.manual_compact_state_check((first + 3611) * 1000, last, 3600, enq)[0]
+
+
+def test_parse_compression_types():
+    """pegasus_compression_options_test.cpp:115-155 (num_levels = 7): the rocksdb_compression_type setting"""
+    import ctypes as C
+    L = pgs.lib()
+    L.pgs_parse_compression_types.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p]
+    none, snappy, lz4, zstd = 0, 1, 4, 7
+    H = "per_level:"
+
+    def parse(cfg, before=None):
+        buf = (C.c_uint8 * 7)(*(before or [9] * 7))
+        return L.pgs_parse_compression_types(cfg.encode(), 7, buf), list(buf)
+    ok = [("none", [none] * 7), ("snappy", [none, none] + [snappy] * 5), ("lz4", [none, none] + [lz4] * 5), ("zstd", [none, none] + [zstd] * 5),
+          (H + "none", [none] * 7), (H + "none,snappy", [none] + [snappy] * 6), (H + "none,lz4,snappy,zstd", [none, lz4, snappy, zstd, zstd, zstd, zstd]),
+          (H + "none,lz4,snappy,zstd,lz4,snappy,zstd", [none, lz4, snappy, zstd, lz4, snappy, zstd]),
+          (H + "none,lz4,snappy,zstd,lz4,snappy,zstd,zstd", [none, lz4, snappy, zstd, lz4, snappy, zstd])]
+    for cfg, want in ok:
+        assert parse(cfg) == (0, want), cfg
+    old = [none, lz4, snappy, zstd, lz4, snappy, zstd]
+    for cfg in ("none1", "Snappy", ",zstd", H + ":snappy", H + "snappy,snappy1", "per_leve:snappy", "per_levelsnappy", "not_support_zip"):
+        assert parse(cfg, old) == (pgs.INVALID_ARGUMENT, old), cfg   # refused, the previous table stays
+    # the default the reference starts with (check_rocksdb_compression_types_default, 6 levels shown there)
+    assert parse("lz4")[1][:6] == [none, none, lz4, lz4, lz4, lz4]
