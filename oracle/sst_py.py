@@ -3,8 +3,10 @@ layout (format_version 2, no compression), used to check the product's SST egres
 (incubator_pegasus_b200/host/sst_format.cpp).  Small cases only.
 
 Follows RocksDB 8.5.3's public format description (table/block_based/block_based_table_builder.cc,
-table/format.cc, util/crc32c.h, util/hash.cc, util/bloom_impl.h, none of which are in the reference tree).  PARITY UNPINNED:
-no RocksDB build is available in this image, so these bytes have not been read by RocksDB itself.
+table/format.cc, util/crc32c.h, util/hash.cc, util/bloom_impl.h, none of which are in the reference tree).  Pinned pieces:
+crc32c by the RFC 3720 vectors, the filter hash by the known answers of RocksDB's own util/hash_test.cc (HashTest.Values), the
+LZ4 codec by the system liblz4 (tests/test_sst_format.py).  PARITY UNPINNED for the container itself (block handles, metaindex,
+properties, footer): no RocksDB build is available in this image, so these files have not been read by RocksDB.
 
   data block   : entries  varint32 shared | varint32 non_shared | varint32 value_len | key delta | value,
                  restart array (fixed32 each) | fixed32 count
